@@ -1,0 +1,230 @@
+/*
+ * invertavatar_b200 -- C-ABI of the B200-native generator-forward hot path.
+ *
+ * This is the drop-in boundary: a plain-C shared library (libinvertavatar_b200.so) with raw device
+ * pointers, sizes and a CUDA stream handle.  No torch types appear here.  Every entry point cites the
+ * reference interface it replaces (paths relative to the XChenZ/invertAvatar tree).
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in _host
+ *   - activations are fp32, channels-last ("NHWC": [B][H][W][C]) unless stated otherwise
+ *   - "split" activations are a pair of bf16 tensors (hi, lo) with hi = rn_bf16(v), lo = rn_bf16(v - hi);
+ *     the tensor-core convolution computes hi*hi + hi*lo + lo*hi with fp32 accumulation (3-term split)
+ *   - stream is a cudaStream_t passed as void*; work is enqueued, never synchronised
+ *   - return value: 0 on success, non-zero on error; ia_last_error() gives the message
+ *     (the reference raises RuntimeError through TORCH_CHECK, e.g. torch_utils/ops/bias_act.cpp:39-55;
+ *      the Python host layer turns a non-zero return into RuntimeError as well)
+ *   - inputs are borrowed and never mutated; outputs are caller-allocated
+ */
+#ifndef INVERTAVATAR_B200_H_
+#define INVERTAVATAR_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IA_ABI_VERSION 1
+
+/* ---- library management ------------------------------------------------------------------------ */
+int ia_abi_version(void);
+const char* ia_last_error(void);
+/* Select the device for the calling host thread (the library carries its own CUDA runtime instance). */
+int ia_set_device(int device);
+/* Number of kernels this library has launched since load / since the last reset (bench.py gpu_launches). */
+int64_t ia_launch_count(void);
+void ia_reset_launch_count(void);
+
+/* ---- torch_utils/ops plugin equivalents --------------------------------------------------------- */
+
+/* Activation ids follow the reference's cuda_idx (torch_utils/ops/bias_act.py:23-33). */
+enum { IA_ACT_LINEAR = 1, IA_ACT_RELU = 2, IA_ACT_LRELU = 3, IA_ACT_TANH = 4, IA_ACT_SIGMOID = 5,
+       IA_ACT_ELU = 6, IA_ACT_SELU = 7, IA_ACT_SOFTPLUS = 8, IA_ACT_SWISH = 9 };
+
+/* y = clamp(act(x + b[c]) * gain).  Replaces bias_act_plugin.bias_act(x,b,xref,yref,dy,grad=0,dim,act,alpha,
+ * gain,clamp) (torch_utils/ops/bias_act.cpp:36-94, kernel bias_act.cu:27-151), forward only.
+ * x is a dense tensor viewed as [outer][C][inner]; channel of element i is (i / inner) % C.
+ * b may be NULL (no bias).  clamp < 0 disables clamping. */
+int ia_bias_act(const float* x, const float* b, float* y, int64_t numel, int64_t C, int64_t inner,
+                int act, float alpha, float gain, float clamp, void* stream);
+
+/* Generic upfirdn2d: zero-insert x(up), pad/crop, 2-D FIR, decimate.  Replaces
+ * upfirdn2d_plugin.upfirdn2d(x,f,upx,upy,downx,downy,padx0,padx1,pady0,pady1,flip,gain)
+ * (torch_utils/ops/upfirdn2d.cpp:20-102, kernels upfirdn2d.cu:33-204).  Arbitrary element strides for x and y
+ * (covers contiguous and channels-last, like upfirdn2d.cpp:56-63); f is a dense fp32 [fh][fw] filter. */
+typedef struct {
+    const float* x; const float* f; float* y;
+    int32_t N, C, inH, inW, outH, outW, fh, fw;
+    int32_t upx, upy, downx, downy, padx0, pady0;
+    int32_t flip;              /* reference semantics: flip=0 -> true convolution (filter is flipped) */
+    float gain;
+    int64_t xs_n, xs_c, xs_h, xs_w;   /* element strides of x */
+    int64_t ys_n, ys_c, ys_h, ys_w;   /* element strides of y */
+} ia_upfirdn2d_params;
+int ia_upfirdn2d(const ia_upfirdn2d_params* p, void* stream);
+
+/* ---- small dense layers (MappingNetwork, style affines; networks_stylegan2_new.py:96-127,233-268) ------- */
+
+/* y[b][o] = act((sum_i x[b][i] * w[o][i]) * w_gain + bias[o] * b_gain) * act_gain ; w is [Out][In] row-major. */
+int ia_fully_connected(const float* x, const float* w, const float* bias, float* y, int32_t B, int32_t In,
+                       int32_t Out, float w_gain, float b_gain, int act, float alpha, float act_gain,
+                       int64_t x_stride, int64_t y_stride, void* stream);
+/* y = x * rsqrt(mean(x^2, dim=1) + eps)  (normalize_2nd_moment, networks_stylegan2_new.py:28-29) */
+int ia_normalize_2nd_moment(const float* x, float* y, int32_t B, int32_t D, float eps, int64_t x_stride,
+                            int64_t y_stride, void* stream);
+/* ws[b][k][:] = k < cutoff ? lerp(w_avg, w[b], psi) : w[b]   (broadcast + truncation, :256-267) */
+int ia_broadcast_truncate(const float* w, const float* w_avg, float* ws, int32_t B, int32_t num_ws, int32_t D,
+                          float psi, int32_t cutoff, void* stream);
+
+/* ---- modulated convolution stack (networks_stylegan2_new.py:34-91,311-357; conv2d_resample.py:48-143) --- */
+
+/* One entry per SynthesisLayer / ToRGBLayer of a network; the table lives in device memory. */
+typedef struct {
+    const float* affine_w;   /* [Cin][w_dim] */
+    const float* affine_b;   /* [Cin] */
+    const float* wsq;        /* [Cout][Cin]  sum over taps of weight^2, or NULL (no demodulation: ToRGB) */
+    float* styles;           /* out [B][Cin] */
+    float* dcoef;            /* out [B][Cout] or NULL */
+    int32_t Cin, Cout, w_index, w_dim;
+    float affine_gain;       /* 1/sqrt(w_dim) */
+    float style_gain;        /* 1 for conv layers, 1/sqrt(Cin) for ToRGB (:354) */
+} ia_style_layer;
+/* styles[l] = (affine_w[l] * ws[:, w_index[l]] * affine_gain + affine_b[l]) * style_gain ;
+ * dcoef[l][b][o] = rsqrt(sum_i styles[b][i]^2 * wsq[o][i] + 1e-8)   (:63-65, reassociated) */
+int ia_styles(const ia_style_layer* layers_dev, const ia_style_layer* layers_host, int32_t n_layers,
+              const float* ws, int32_t B, int32_t num_ws, void* stream);
+
+/* Prepare the tensor-core A operand: v = x * styles[b][c] (optionally after x = cond*a + x*(1-a), the
+ * cond_list blend of networks_stylegan2_new.py:538-540), then split into bf16 hi/lo, zero-padded to C_pad. */
+typedef struct {
+    const float* x; int64_t x_ld;            /* [B][HW][C], pixel stride x_ld */
+    const float* styles;                      /* [B][C] or NULL (=1) */
+    const float* cond; int64_t cond_ld;       /* [B][HW][C] or NULL */
+    const float* cond_alpha;                  /* [B][HW] */
+    uint16_t* hi; uint16_t* lo;               /* bf16 [B][HW][C_pad] */
+    int32_t B, HW, C, C_pad;
+} ia_modsplit_params;
+int ia_modsplit(const ia_modsplit_params* p, void* stream);
+
+/* Pack an OIHW fp32 weight into the GEMM layout [tap][Cout_pad][Cin_pad] bf16 hi/lo (+ wsq[Cout][Cin]). */
+int ia_pack_conv_weight(const float* w, int32_t Cout, int32_t Cin, int32_t kh, int32_t kw, int32_t Cout_pad,
+                        int32_t Cin_pad, uint16_t* w_hi, uint16_t* w_lo, float* wsq, void* stream);
+
+typedef struct {
+    /* what to emit from the fp32 result v[b][oy][ox][co] (any subset) */
+    float* out32; int64_t out32_ld;                       /* fp32 NHWC */
+    uint16_t* hi1; uint16_t* lo1; const float* s1; int32_t c1_pad;   /* split of v*s1[b][co] (next conv) */
+    uint16_t* hi2; uint16_t* lo2; const float* s2; int32_t c2_pad;   /* split of v*s2[b][co] (ToRGB) */
+} ia_emit;
+
+typedef struct {
+    /* A operand: split activations [B][H][W][Cin_pad]; B operand: packed weights */
+    const uint16_t* a_hi; const uint16_t* a_lo; int32_t B, H, W, Cin_pad;
+    const uint16_t* w_hi; const uint16_t* w_lo; int32_t Cout, Cout_pad, n_taps_total;
+    /* tile grid and taps: output grid position (gy,gx) accumulates sum_t A[gy+dy_t][gx+dx_t] * W[wtap_t] */
+    int32_t GH, GW, ntaps; int32_t dy[9]; int32_t dx[9]; int32_t wtap[9];
+    /* output pixel = (gy*sy+py, gx*sx+px) of an [B][OH][OW] image */
+    int32_t OH, OW, sy, sx, py, px;
+    /* epilogue: mode 0 = raw accumulator; mode 1 = v = acc*dcoef + noise*strength; v = act(v+bias)*gain, clamp */
+    int32_t mode; const float* dcoef; const float* noise; const float* noise_strength; const float* bias;
+    int64_t noise_bstride;   /* 0: one [OH][OW] noise image shared by the batch ('const'); OH*OW: per-sample ('random') */
+    int32_t act; float alpha; float gain; float clamp;
+    ia_emit emit;
+} ia_conv_params;
+/* Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05.mma, TMEM accumulators, TMA-fed). */
+int ia_conv_tc(const ia_conv_params* p, void* stream);
+/* Same contract on CUDA cores (fp32 FMA over hi+lo); cross-check and bring-up path. */
+int ia_conv_simt(const ia_conv_params* p, void* stream);
+
+/* Post-processing of an up=2 layer: 4x4 FIR (gain 4, pad 1) over the raw (2H+1)x(2W+1) transposed-conv
+ * output, then demod/noise/bias/activation exactly as mode 1 above (conv2d_resample.py:127-128 + bias_act). */
+typedef struct {
+    const float* raw; int32_t B, RH, RW, C;     /* raw [B][RH][RW][C], RH = 2H+1 */
+    const float* fir;                            /* [4][4] filter already multiplied by the gain */
+    int32_t OH, OW;
+    const float* dcoef; const float* noise; const float* noise_strength; const float* bias;
+    int64_t noise_bstride;
+    int32_t act; float alpha; float gain; float clamp;
+    ia_emit emit;
+} ia_fir_params;
+int ia_fir_epilogue(const ia_fir_params* p, void* stream);
+
+/* ToRGB tail: img_out = upsample2d(img_prev) + clamp(raw + bias)  (networks_stylegan2_new.py:456-463,
+ * upfirdn2d.upsample2d :315-350 with the [1,3,3,1] filter).  img_prev may be NULL.  out_nchw=1 writes planar. */
+typedef struct {
+    const float* raw; int64_t raw_ld;           /* [B][H][W][>=C] */
+    const float* bias; float clamp;
+    const float* img_prev;                       /* [B][H/2][W/2][C] or NULL */
+    float* img_out; int32_t B, H, W, C; int32_t out_nchw;
+} ia_torgb_params;
+int ia_torgb_finish(const ia_torgb_params* p, void* stream);
+
+/* ---- UV rasterize / stitch (triplane_v20.py:119-128,317-339; renderer.py:716-741) ------------------------ */
+
+/* GPU replacement of cv2.floodFill (seed (0,0), FIXED_RANGE lo 0 / up 254, 4-connectivity) + mask algebra:
+ * mouth = (255 - filled(alpha*255))/255 ; full_alpha = clip(alpha+mouth,0,1) ;
+ * upper_alpha = clip(alpha + mouth[rows >= upper_row0], 0, 1).  alpha is read with element stride a_stride
+ * (the mask channel of uvcoords_image [B][H][W][3] has stride 3).  H,W <= 256. */
+int ia_fill_mouth(const float* alpha, int64_t a_stride, int64_t a_batch_stride, int32_t B, int32_t H, int32_t W,
+                  int32_t upper_row0, float* full_alpha, float* mouth, float* upper_alpha, void* stream);
+
+/* F.grid_sample(bilinear, zeros, align_corners=False) on NHWC input; grid [B][Ho][Wo][>=2] with pixel stride g_ld. */
+int ia_grid_sample(const float* in, int32_t B, int32_t Hi, int32_t Wi, int32_t C, int64_t in_ld,
+                   const float* grid, int64_t g_ld, int32_t Ho, int32_t Wo, float* out, int64_t out_ld, void* stream);
+
+/* F.interpolate(bilinear, antialias=True) (ATen _upsample_bilinear2d_aa) on a window of an NHWC tensor,
+ * written into a window of another NHWC tensor.  Tap tables are built by the host (one per axis):
+ * for output index i, taps j in [start[i], start[i]+count[i]) with weights w[i*max_taps + k]. */
+typedef struct {
+    const float* in; int64_t in_ld; int32_t in_H, in_W;      /* full input image dims (per batch) */
+    int32_t in_y0, in_x0;                                      /* crop origin */
+    float* out; int64_t out_ld; int32_t out_H, out_W;         /* full output image dims (per batch) */
+    int32_t out_y0, out_x0;                                    /* paste origin */
+    int32_t B, C, oh, ow;                                      /* resized window size */
+    const int32_t* y_start; const int32_t* y_count; const float* y_w; int32_t y_max_taps;
+    const int32_t* x_start; const int32_t* x_count; const float* x_w; int32_t x_max_taps;
+} ia_resize_params;
+int ia_resize_aa(const ia_resize_params* p, void* stream);
+
+/* out = a*alpha + b*(1-alpha) with per-pixel alpha; windows given by pixel strides and base pointers. */
+typedef struct {
+    const float* a; int64_t a_ld; int64_t a_row; int64_t a_batch;
+    const float* b; int64_t b_ld; int64_t b_row; int64_t b_batch;
+    const float* alpha; int64_t al_ld; int64_t al_row; int64_t al_batch;
+    float* out; int64_t o_ld; int64_t o_row; int64_t o_batch;
+    int32_t B, H, W, C;
+} ia_lerp_params;
+int ia_lerp_alpha(const ia_lerp_params* p, void* stream);
+
+/* ---- volume renderer (renderer.py:309-469, ray_sampler.py:70-107, ray_marcher.py:25-57, triplane_v20.py:415-438) */
+typedef struct {
+    const float* planes; int64_t plane_px_ld;    /* [B][PH][PW][>=96]: plane p = channels [32p, 32p+32) */
+    int32_t B, PH, PW;
+    const float* cam;  int64_t cam_ld;           /* [B][>=25] c2w(16) | K(9); may be NULL when rays are given */
+    const float* rays_o; const float* rays_d;    /* optional explicit rays [B][rays][3] (ImportanceRenderer API) */
+    int32_t res;                                  /* neural rendering resolution N; rays = N*N */
+    int32_t Dc, Df;                               /* coarse / importance samples (Dc<=96, Df<=96, Dc+Df<=192) */
+    const float* jitter;                          /* [B][rays][Dc] U[0,1) (replaces rand_like, renderer.py:406) */
+    const float* u;                               /* [B*rays][Df] or NULL -> linspace(0,1,Df) (evaluation) */
+    float box_warp; int32_t white_back;
+    const float* near_far;                        /* device [2] from ia_ray_bounds */
+    const float* w1; const float* b1; const float* w2; const float* b2;  /* decoder [64][32],[64],[33][64],[33] raw */
+    float* feat;                                  /* out [B][res][res][32] (NHWC feature image) */
+    float* depth;                                 /* out [B][res][res] unclamped composite depth */
+    float* wsum;                                  /* out [B][res][res] */
+    float* depth_minmax;                          /* device [2] global min/max of all sample depths (init by callee) */
+} ia_render_params;
+/* near/far = mean_b ||c2w_b[:3,3]|| - 0.45 / + 0.6 (renderer.py:311-313), computed on device (no host sync). */
+int ia_ray_bounds(const float* cam, int64_t cam_ld, int32_t B, float* near_far, void* stream);
+int ia_ray_bounds_from_origins(const float* origins, int64_t n, float* near_far, void* stream);
+int ia_render(const ia_render_params* p, void* stream);
+/* depth = clamp(nan_to_num(depth, inf), min, max) (ray_marcher.py:49-50) */
+int ia_depth_clamp(float* depth, int64_t n, const float* depth_minmax, void* stream);
+/* Ray generation only (RaySampler_zxc API): origins/dirs [B][rays][3]. */
+int ia_ray_sampler(const float* cam, int64_t cam_ld, int32_t B, int32_t res, float* origins, float* dirs, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* INVERTAVATAR_B200_H_ */

@@ -1,0 +1,5 @@
+"""invertavatar_b200: B200-native (sm_100a) implementation of the InvertAvatar generator-forward hot path.
+
+Host side: Python modules mirroring the reference's classes (``TriPlaneGenerator`` etc.); device side: hand-written CUDA
+behind the C-ABI in ``include/invertavatar_b200.h`` (``libinvertavatar_b200.so``).  There is no CPU fallback."""
+__version__ = '0.1.0'

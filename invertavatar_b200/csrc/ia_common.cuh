@@ -1,0 +1,107 @@
+// Shared helpers for the invertavatar_b200 CUDA sources (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/invertavatar_b200.h"
+
+namespace ia {
+
+void set_error(const char* fmt, ...);
+void count_launch();
+
+#define IA_CHECK(cond, ...)                                   \
+    do {                                                      \
+        if (!(cond)) {                                        \
+            ia::set_error(__VA_ARGS__);                       \
+            return 1;                                         \
+        }                                                     \
+    } while (0)
+
+#define IA_LAUNCH_CHECK(name)                                                        \
+    do {                                                                             \
+        ia::count_launch();                                                          \
+        cudaError_t e__ = cudaGetLastError();                                        \
+        if (e__ != cudaSuccess) {                                                    \
+            ia::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));   \
+            return 2;                                                                \
+        }                                                                            \
+    } while (0)
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// bf16 split: hi = rn(v), lo = rn(v - hi)
+__device__ __forceinline__ void split_bf16(float v, uint16_t& hi, uint16_t& lo) {
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    float r = v - __bfloat162float(h);
+    __nv_bfloat16 l = __float2bfloat16_rn(r);
+    hi = __bfloat16_as_ushort(h);
+    lo = __bfloat16_as_ushort(l);
+}
+__device__ __forceinline__ float bf16_bits_to_float(uint16_t b) { return __uint_as_float(((uint32_t)b) << 16); }
+
+// activation + gain + clamp shared by every epilogue (reference bias_act.cu:27-151 forward path; only the
+// activations the generator uses get the fast path, the rest are exact expressions).
+__device__ __forceinline__ float apply_act(float x, int act, float alpha) {
+    switch (act) {
+        case IA_ACT_LINEAR: return x;
+        case IA_ACT_RELU: return x > 0.f ? x : 0.f;
+        case IA_ACT_LRELU: return x > 0.f ? x : x * alpha;
+        case IA_ACT_TANH: return tanhf(x);
+        case IA_ACT_SIGMOID: return 1.f / (1.f + expf(-x));
+        case IA_ACT_ELU: return x > 0.f ? x : expm1f(x);
+        case IA_ACT_SELU: return x > 0.f ? 1.0507009873554805f * x : 1.0507009873554805f * 1.6732632423543772f * expm1f(x);
+        case IA_ACT_SOFTPLUS: return x > 20.f ? x : log1pf(expf(x));
+        case IA_ACT_SWISH: return x / (1.f + expf(-x));
+    }
+    return x;
+}
+__device__ __forceinline__ float act_gain_clamp(float x, int act, float alpha, float gain, float clamp) {
+    x = apply_act(x, act, alpha) * gain;
+    if (clamp >= 0.f) x = fminf(fmaxf(x, -clamp), clamp);
+    return x;
+}
+
+// Emit one group of 4 consecutive channels (co..co+3) of pixel `pix` of image b.
+__device__ __forceinline__ void emit4(const ia_emit& e, int b, int64_t pix, int co, int C, const float v[4]) {
+    if (e.out32) {
+        float* o = e.out32 + pix * e.out32_ld + co;
+        if (co + 3 < C && ((e.out32_ld & 3) == 0)) {
+            *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+            for (int k = 0; k < 4; ++k) if (co + k < C) o[k] = v[k];
+        }
+    }
+    if (e.hi1) {
+        uint16_t h[4], l[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float s = (co + k < C) ? (e.s1 ? e.s1[(int64_t)b * C + co + k] : 1.f) : 0.f;
+            float m = (co + k < C) ? v[k] * s : 0.f;
+            split_bf16(m, h[k], l[k]);
+        }
+        uint2 hv = make_uint2(h[0] | ((uint32_t)h[1] << 16), h[2] | ((uint32_t)h[3] << 16));
+        uint2 lv = make_uint2(l[0] | ((uint32_t)l[1] << 16), l[2] | ((uint32_t)l[3] << 16));
+        *reinterpret_cast<uint2*>(e.hi1 + pix * e.c1_pad + co) = hv;
+        *reinterpret_cast<uint2*>(e.lo1 + pix * e.c1_pad + co) = lv;
+    }
+    if (e.hi2) {
+        uint16_t h[4], l[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float s = (co + k < C) ? (e.s2 ? e.s2[(int64_t)b * C + co + k] : 1.f) : 0.f;
+            float m = (co + k < C) ? v[k] * s : 0.f;
+            split_bf16(m, h[k], l[k]);
+        }
+        uint2 hv = make_uint2(h[0] | ((uint32_t)h[1] << 16), h[2] | ((uint32_t)h[3] << 16));
+        uint2 lv = make_uint2(l[0] | ((uint32_t)l[1] << 16), l[2] | ((uint32_t)l[3] << 16));
+        *reinterpret_cast<uint2*>(e.hi2 + pix * e.c2_pad + co) = hv;
+        *reinterpret_cast<uint2*>(e.lo2 + pix * e.c2_pad + co) = lv;
+    }
+}
+
+}  // namespace ia

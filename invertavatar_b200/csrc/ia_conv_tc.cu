@@ -1,0 +1,378 @@
+// Implicit-GEMM modulated convolution on the Blackwell 5th-generation tensor cores.
+//
+//   D[pixel, cout] = sum_{tap} sum_{cin} A[pixel + shift(tap), cin] * W[tap][cout, cin]
+//
+// A = modulated activations, NHWC bf16 hi/lo pair (3-term split: hi*hi + hi*lo + lo*hi, fp32 accumulate in
+// TMEM), W = packed weights [tap][Cout_pad][Cin_pad] bf16 hi/lo.  Both operands are K-major, staged by TMA
+// (cp.async.bulk.tensor, 128-byte swizzle) straight from their natural layouts: the activation tile of a tap is
+// a 4-D box {64 ch, tw, th, nb} whose origin is shifted by the tap offset -- out-of-bounds rows are zero-filled
+// by the TMA unit, which implements the convolution padding and the ragged edges of transposed-conv phases.
+//
+// One CTA computes a 128-pixel x n_tile-cout tile.  Warp roles (192 threads): warp 0 = TMA producer,
+// warp 1 = tcgen05.mma issuer (one elected lane), warps 2..5 = epilogue (tcgen05.ld TMEM -> registers ->
+// demod / noise / bias / leaky-ReLU / clamp -> fp32 NHWC and/or modulated bf16 hi/lo for the next layer).
+//
+// Replaces the cuDNN grouped conv2d / conv_transpose2d reached through reference
+// torch_utils/ops/conv2d_gradfix.py:127-129 <- conv2d_resample.py:31-43 <- modulated_conv2d
+// (training_avatar_texture/networks_stylegan2_new.py:34-91) together with the bias_act that follows it.
+#include <cuda.h>
+
+#include "ia_common.cuh"
+
+using namespace ia;
+
+int ia_conv_validate(const ia_conv_params* p, const char* who);
+
+namespace {
+
+constexpr int kTileM = 128;
+constexpr int kBlockK = 64;           // bf16 elements per k-block = 128 bytes = one swizzle row
+constexpr int kMaxStages = 6;
+constexpr int kThreads = 192;
+constexpr uint32_t kABytes = kTileM * kBlockK * 2;  // 16 KB per A tile
+
+struct TcParams {
+    // tile geometry
+    int B, GH, GW, th, tw, nb, tiles_x, tiles_y;
+    int Cin_blocks;       // Cin_pad / 64
+    int Cout, Cout_pad, n_tile, stages, tmem_cols;
+    int ntaps; int dy[9]; int dx[9]; int wtap[9];
+    int OH, OW, sy, sx, py, px;
+    int mode; const float* dcoef; const float* noise; const float* noise_strength; const float* bias;
+    long long noise_bstride;
+    int act; float alpha, gain, clamp;
+    ia_emit emit;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a trapped kernel, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {
+            printf("ia_conv_tc: mbarrier timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+// K-major, 128-byte-swizzled operand tile: rows of 128 B, 8-row atoms of 1024 B (SBO), descriptor version 1.
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);        // start address, 16-byte units
+    d |= (uint64_t)1 << 16;                           // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset between 8-row atoms
+    d |= (uint64_t)1 << 46;                           // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                           // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---- the kernel ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+               const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
+               const TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    // 1024-byte alignment for the 128B-swizzled tiles
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t b_bytes = (uint32_t)p.n_tile * 128u;
+    const uint32_t stage_bytes = 2u * kABytes + 2u * b_bytes;
+    const uint32_t bar_base = smem_base + (uint32_t)p.stages * stage_bytes;
+    // barriers: full[stages], empty[stages], tmem_full ; then the TMEM base-address slot
+    auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(kMaxStages + s); };
+    const uint32_t tmem_full_bar = bar_base + 8u * (2 * kMaxStages);
+    const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    // tile coordinates
+    int tile = blockIdx.x;
+    const int txi = tile % p.tiles_x; tile /= p.tiles_x;
+    const int tyi = tile % p.tiles_y; tile /= p.tiles_y;
+    const int tni = tile;
+    const int x0 = txi * p.tw, y0 = tyi * p.th, n0 = tni * p.nb;
+    const int col0 = blockIdx.y * p.n_tile;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tm_a_hi); prefetch_tmap(&tm_a_lo); prefetch_tmap(&tm_w_hi); prefetch_tmap(&tm_w_lo);
+    }
+    if (warp == 2) {  // TMEM allocation (whole warp); the same warp frees it at the end
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    const int num_kb = p.ntaps * p.Cin_blocks;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int t = kb / p.Cin_blocks;
+                const int kc = kb - t * p.Cin_blocks;
+                mbar_wait(empty_bar(stage), phase ^ 1u);
+                const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
+                mbar_expect_tx(full_bar(stage), stage_bytes);
+                tma_load_4d(sa, &tm_a_hi, full_bar(stage), kc * kBlockK, x0 + p.dx[t], y0 + p.dy[t], n0);
+                tma_load_4d(sa + kABytes, &tm_a_lo, full_bar(stage), kc * kBlockK, x0 + p.dx[t], y0 + p.dy[t], n0);
+                const int wrow = p.wtap[t] * p.Cout_pad + col0;
+                tma_load_2d(sa + 2u * kABytes, &tm_w_hi, full_bar(stage), kc * kBlockK, wrow);
+                tma_load_2d(sa + 2u * kABytes + b_bytes, &tm_w_lo, full_bar(stage), kc * kBlockK, wrow);
+                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            // instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=n_tile
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+            int stage = 0; uint32_t phase = 0;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(full_bar(stage), phase);
+                tc_fence_after();
+                const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
+                const uint64_t a_hi = make_sw128_desc(sa);
+                const uint64_t a_lo = make_sw128_desc(sa + kABytes);
+                const uint64_t b_hi = make_sw128_desc(sa + 2u * kABytes);
+                const uint64_t b_lo = make_sw128_desc(sa + 2u * kABytes + b_bytes);
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k) {
+                    const uint64_t koff = (uint64_t)((k * 32) >> 4);  // +32 bytes per 16-element K step
+                    umma_bf16(tmem_base, a_hi + koff, b_hi + koff, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    umma_bf16(tmem_base, a_hi + koff, b_lo + koff, idesc, 1u);
+                    umma_bf16(tmem_base, a_lo + koff, b_hi + koff, idesc, 1u);
+                }
+                umma_commit(empty_bar(stage));   // frees the smem slot once these MMAs have read it
+                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            }
+            umma_commit(tmem_full_bar);          // accumulator complete
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int lg = warp & 3;                 // TMEM lane group this warp may access
+        const int row = lg * 32 + lane;          // tile row == TMEM lane
+        const int w_l = row % p.tw;
+        const int h_l = (row / p.tw) % p.th;
+        const int n_l = row / (p.tw * p.th);
+        const int gy = y0 + h_l, gx = x0 + w_l, img = n0 + n_l;
+        const int oy = gy * p.sy + p.py, ox = gx * p.sx + p.px;
+        const bool valid = gy < p.GH && gx < p.GW && img < p.B && oy < p.OH && ox < p.OW;
+        const int64_t pix = ((int64_t)img * p.OH + oy) * p.OW + ox;
+        float nz = 0.f;
+        if (valid && p.mode == 1 && p.noise) nz = p.noise[(int64_t)img * p.noise_bstride + (int64_t)oy * p.OW + ox] * p.noise_strength[0];
+
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        for (int c = 0; c < p.n_tile; c += 32) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)c, r);
+            if (!valid) continue;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int co = col0 + c + q * 4;
+                if (co >= p.Cout) break;
+                float v[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float a = __uint_as_float(r[q * 4 + k]);
+                    if (p.mode == 1 && co + k < p.Cout) {
+                        if (p.dcoef) a = fmaf(a, p.dcoef[(int64_t)img * p.Cout + co + k], nz); else a += nz;
+                        if (p.bias) a += p.bias[co + k];
+                        a = act_gain_clamp(a, p.act, p.alpha, p.gain, p.clamp);
+                    }
+                    v[k] = a;
+                }
+                emit4(p.emit, img, pix, co, p.Cout, v);
+            }
+        }
+        tc_fence_before();
+    }
+
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+    }
+}
+
+// ---- host side -------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !sym) return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(sym);
+    return fn;
+}
+
+int make_act_map(CUtensorMap* m, const void* ptr, int B, int H, int W, int C_pad, int nb, int th, int tw) {
+    EncodeTiledFn enc = get_encode_fn();
+    IA_CHECK(enc, "ia_conv_tc: cuTensorMapEncodeTiled unavailable");
+    cuuint64_t dims[4] = {(cuuint64_t)C_pad, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)C_pad * 2, (cuuint64_t)W * C_pad * 2, (cuuint64_t)H * W * C_pad * 2};
+    cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)nb};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    IA_CHECK(r == CUDA_SUCCESS, "ia_conv_tc: activation tensor map encode failed (CUresult %d; B=%d H=%d W=%d C=%d box %d,%d,%d)",
+             (int)r, B, H, W, C_pad, nb, th, tw);
+    return 0;
+}
+
+int make_weight_map(CUtensorMap* m, const void* ptr, int rows, int Cin_pad, int n_tile) {
+    EncodeTiledFn enc = get_encode_fn();
+    IA_CHECK(enc, "ia_conv_tc: cuTensorMapEncodeTiled unavailable");
+    cuuint64_t dims[2] = {(cuuint64_t)Cin_pad, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)Cin_pad * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)n_tile};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    IA_CHECK(r == CUDA_SUCCESS, "ia_conv_tc: weight tensor map encode failed (CUresult %d; rows=%d Cin=%d n_tile=%d)", (int)r,
+             rows, Cin_pad, n_tile);
+    return 0;
+}
+
+// Choose the 128-row patch {nb, th, tw} (powers of two) that covers the [B][GH][GW] grid with the fewest tiles.
+void choose_patch(int B, int GH, int GW, int& nb, int& th, int& tw) {
+    int64_t best = -1;
+    int wmax = 1, hmax = 1;
+    while (wmax < GW && wmax < 128) wmax <<= 1;
+    while (hmax < GH && hmax < 128) hmax <<= 1;
+    for (int w = 1; w <= wmax; w <<= 1) {
+        for (int h = 1; h <= hmax && h * w <= 128; h <<= 1) {
+            int n = 128 / (w * h);
+            int64_t tiles = cdiv(GW, w) * cdiv(GH, h) * cdiv(B, n);
+            // prefer fewer tiles, then wider rows (longer contiguous runs per TMA box row)
+            if (best < 0 || tiles < best || (tiles == best && w > tw)) { best = tiles; nb = n; th = h; tw = w; }
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int ia_conv_tc(const ia_conv_params* p, void* stream) {
+    if (int rc = ia_conv_validate(p, "ia_conv_tc")) return rc;
+    IA_CHECK((reinterpret_cast<uintptr_t>(p->a_hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->a_lo) & 15) == 0 &&
+             (reinterpret_cast<uintptr_t>(p->w_hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->w_lo) & 15) == 0,
+             "ia_conv_tc: operands must be 16-byte aligned");
+    TcParams t;
+    memset(&t, 0, sizeof(t));
+    t.B = p->B; t.GH = p->GH; t.GW = p->GW;
+    choose_patch(p->B, p->GH, p->GW, t.nb, t.th, t.tw);
+    t.tiles_x = (int)cdiv(p->GW, t.tw); t.tiles_y = (int)cdiv(p->GH, t.th);
+    const int tiles_n = (int)cdiv(p->B, t.nb);
+    t.Cin_blocks = p->Cin_pad / kBlockK;
+    t.Cout = p->Cout; t.Cout_pad = p->Cout_pad;
+    // N tile: the largest of {256,128,64,32}-multiples that divides Cout_pad, capped at 256
+    int n_tile = p->Cout_pad <= 256 ? p->Cout_pad : 256;
+    while (p->Cout_pad % n_tile) n_tile -= 32;
+    t.n_tile = n_tile;
+    t.tmem_cols = 32; while (t.tmem_cols < n_tile) t.tmem_cols <<= 1;
+    const uint32_t stage_bytes = 2u * kABytes + 2u * (uint32_t)n_tile * 128u;
+    const uint32_t budget = 227u * 1024u - 1024u /*alignment*/ - 256u /*barriers*/;
+    int stages = (int)(budget / stage_bytes);
+    if (stages > kMaxStages) stages = kMaxStages;
+    IA_CHECK(stages >= 2, "ia_conv_tc: tile does not fit shared memory");
+    t.stages = stages;
+    t.ntaps = p->ntaps;
+    for (int i = 0; i < p->ntaps; ++i) { t.dy[i] = p->dy[i]; t.dx[i] = p->dx[i]; t.wtap[i] = p->wtap[i]; }
+    t.OH = p->OH; t.OW = p->OW; t.sy = p->sy; t.sx = p->sx; t.py = p->py; t.px = p->px;
+    t.mode = p->mode; t.dcoef = p->dcoef; t.noise = p->noise; t.noise_strength = p->noise_strength; t.bias = p->bias;
+    t.noise_bstride = p->noise_bstride;
+    t.act = p->act; t.alpha = p->alpha; t.gain = p->gain; t.clamp = p->clamp;
+    t.emit = p->emit;
+
+    CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
+    if (int rc = make_act_map(&ma_hi, p->a_hi, p->B, p->H, p->W, p->Cin_pad, t.nb, t.th, t.tw)) return rc;
+    if (int rc = make_act_map(&ma_lo, p->a_lo, p->B, p->H, p->W, p->Cin_pad, t.nb, t.th, t.tw)) return rc;
+    const int wrows = p->n_taps_total * p->Cout_pad;
+    if (int rc = make_weight_map(&mw_hi, p->w_hi, wrows, p->Cin_pad, n_tile)) return rc;
+    if (int rc = make_weight_map(&mw_lo, p->w_lo, wrows, p->Cin_pad, n_tile)) return rc;
+
+    const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+    {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        IA_CHECK(e == cudaSuccess, "ia_conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    }
+    dim3 grid((unsigned)(t.tiles_x * t.tiles_y * tiles_n), (unsigned)(p->Cout_pad / n_tile));
+    conv_tc_kernel<<<grid, kThreads, smem, as_stream(stream)>>>(ma_hi, ma_lo, mw_hi, mw_lo, t);
+    IA_LAUNCH_CHECK("ia_conv_tc");
+    return 0;
+}

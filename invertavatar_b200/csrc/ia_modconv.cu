@@ -1,0 +1,407 @@
+// Modulated-convolution support kernels: style affines + demodulation coefficients, operand preparation
+// (modulate + bf16 hi/lo split), weight packing, the up=2 FIR epilogue, the ToRGB tail and the CUDA-core
+// implicit-GEMM convolution used for bring-up / cross-checking the tcgen05 kernel.
+// Arithmetic follows reference training_avatar_texture/networks_stylegan2_new.py:34-91 (unfused branch :70-79),
+// :311-357, torch_utils/ops/conv2d_resample.py:114-131 and torch_utils/ops/upfirdn2d.py:315-350.
+#include "ia_common.cuh"
+
+using namespace ia;
+
+// ------------------------------------------------------------------------------------------------
+// styles + demodulation coefficients for every layer of a network in two launches
+// ------------------------------------------------------------------------------------------------
+__global__ void styles_kernel(const ia_style_layer* __restrict__ layers, const float* __restrict__ ws, int B, int num_ws) {
+    const ia_style_layer L = layers[blockIdx.y];
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (warp >= L.Cin) return;
+    const float* wr = L.affine_w + (int64_t)warp * L.w_dim;
+    for (int b0 = 0; b0 < B; b0 += 8) {
+        int nb = min(8, B - b0);
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+        for (int k = lane; k < L.w_dim; k += 32) {
+            float wv = wr[k];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (i < nb) acc[i] = fmaf(ws[((int64_t)(b0 + i) * num_ws + L.w_index) * L.w_dim + k], wv, acc[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float v = acc[i];
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0 && i < nb)
+                L.styles[(int64_t)(b0 + i) * L.Cin + warp] = (v * L.affine_gain + L.affine_b[warp]) * L.style_gain;
+        }
+    }
+}
+
+__global__ void demod_kernel(const ia_style_layer* __restrict__ layers, int B) {
+    const ia_style_layer L = layers[blockIdx.y];
+    if (L.wsq == nullptr || L.dcoef == nullptr) return;
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (warp >= L.Cout) return;
+    const float* wr = L.wsq + (int64_t)warp * L.Cin;
+    for (int b0 = 0; b0 < B; b0 += 8) {
+        int nb = min(8, B - b0);
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+        for (int k = lane; k < L.Cin; k += 32) {
+            float wv = wr[k];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (i < nb) {
+                    float s = L.styles[(int64_t)(b0 + i) * L.Cin + k];
+                    acc[i] = fmaf(s * s, wv, acc[i]);
+                }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float v = acc[i];
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0 && i < nb) L.dcoef[(int64_t)(b0 + i) * L.Cout + warp] = rsqrtf(v + 1e-8f);
+        }
+    }
+}
+
+extern "C" int ia_styles(const ia_style_layer* layers_dev, const ia_style_layer* layers_host, int32_t n_layers,
+                         const float* ws, int32_t B, int32_t num_ws, void* stream) {
+    IA_CHECK(layers_dev && layers_host && ws, "ia_styles: null argument");
+    if (n_layers == 0 || B == 0) return 0;
+    int max_cin = 0, max_cout = 0;
+    for (int i = 0; i < n_layers; ++i) {
+        IA_CHECK(layers_host[i].w_index >= 0 && layers_host[i].w_index < num_ws, "ia_styles: layer %d w_index out of range", i);
+        max_cin = layers_host[i].Cin > max_cin ? layers_host[i].Cin : max_cin;
+        if (layers_host[i].wsq) max_cout = layers_host[i].Cout > max_cout ? layers_host[i].Cout : max_cout;
+    }
+    dim3 g1((unsigned)cdiv((int64_t)max_cin * 32, 256), n_layers);
+    styles_kernel<<<g1, 256, 0, as_stream(stream)>>>(layers_dev, ws, B, num_ws);
+    IA_LAUNCH_CHECK("ia_styles(styles)");
+    if (max_cout > 0) {
+        dim3 g2((unsigned)cdiv((int64_t)max_cout * 32, 256), n_layers);
+        demod_kernel<<<g2, 256, 0, as_stream(stream)>>>(layers_dev, B);
+        IA_LAUNCH_CHECK("ia_styles(demod)");
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// modulate (+ optional cond blend) and split into bf16 hi/lo, zero-padded to C_pad
+// ------------------------------------------------------------------------------------------------
+__global__ void modsplit_kernel(ia_modsplit_params p) {
+    const int groups = p.C_pad >> 2;  // 4 channels per thread
+    int64_t total = (int64_t)p.B * p.HW * groups;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int g = i % groups;
+    int64_t pix = i / groups;  // b*HW + hw
+    int b = (int)(pix / p.HW);
+    int c0 = g * 4;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (c0 < p.C) {
+        const float* xp = p.x + pix * p.x_ld + c0;
+        if (c0 + 3 < p.C && (p.x_ld & 3) == 0) {
+            float4 t = *reinterpret_cast<const float4*>(xp);
+            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+        } else {
+            for (int k = 0; k < 4; ++k) if (c0 + k < p.C) v[k] = xp[k];
+        }
+        if (p.cond) {
+            float a = p.cond_alpha[pix];
+            const float* cp = p.cond + pix * p.cond_ld + c0;
+            for (int k = 0; k < 4; ++k)
+                if (c0 + k < p.C) v[k] = cp[k] * a + v[k] * (1.f - a);
+        }
+        if (p.styles) {
+            const float* sp = p.styles + (int64_t)b * p.C + c0;
+            for (int k = 0; k < 4; ++k)
+                if (c0 + k < p.C) v[k] *= sp[k];
+        }
+    }
+    uint16_t h[4], l[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) split_bf16(v[k], h[k], l[k]);
+    *reinterpret_cast<uint2*>(p.hi + pix * p.C_pad + c0) = make_uint2(h[0] | ((uint32_t)h[1] << 16), h[2] | ((uint32_t)h[3] << 16));
+    *reinterpret_cast<uint2*>(p.lo + pix * p.C_pad + c0) = make_uint2(l[0] | ((uint32_t)l[1] << 16), l[2] | ((uint32_t)l[3] << 16));
+}
+
+extern "C" int ia_modsplit(const ia_modsplit_params* p, void* stream) {
+    IA_CHECK(p && p->x && p->hi && p->lo, "ia_modsplit: null tensor");
+    IA_CHECK(p->C > 0 && p->C_pad >= p->C && (p->C_pad & 3) == 0, "ia_modsplit: C_pad must be >= C and a multiple of 4");
+    IA_CHECK(p->cond == nullptr || p->cond_alpha != nullptr, "ia_modsplit: cond needs cond_alpha");
+    int64_t total = (int64_t)p->B * p->HW * (p->C_pad >> 2);
+    if (total == 0) return 0;
+    modsplit_kernel<<<(unsigned)cdiv(total, 256), 256, 0, as_stream(stream)>>>(*p);
+    IA_LAUNCH_CHECK("ia_modsplit");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight packing: OIHW fp32 -> [tap][Cout_pad][Cin_pad] bf16 hi/lo, wsq[o][i] = sum_taps w^2
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int taps, int Cout_pad, int Cin_pad,
+                                   uint16_t* __restrict__ w_hi, uint16_t* __restrict__ w_lo) {
+    int64_t total = (int64_t)taps * Cout_pad * Cin_pad;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int ci = i % Cin_pad; int64_t t = i / Cin_pad;
+    int co = t % Cout_pad; int tap = (int)(t / Cout_pad);
+    float v = (ci < Cin && co < Cout) ? w[((int64_t)co * Cin + ci) * taps + tap] : 0.f;
+    uint16_t h, l;
+    split_bf16(v, h, l);
+    w_hi[i] = h;
+    w_lo[i] = l;
+}
+__global__ void wsq_kernel(const float* __restrict__ w, int Cout, int Cin, int taps, float* __restrict__ wsq) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)Cout * Cin) return;
+    float s = 0.f;
+    for (int t = 0; t < taps; ++t) { float v = w[i * taps + t]; s = fmaf(v, v, s); }
+    wsq[i] = s;
+}
+
+extern "C" int ia_pack_conv_weight(const float* w, int32_t Cout, int32_t Cin, int32_t kh, int32_t kw, int32_t Cout_pad,
+                                   int32_t Cin_pad, uint16_t* w_hi, uint16_t* w_lo, float* wsq, void* stream) {
+    IA_CHECK(w && w_hi && w_lo, "ia_pack_conv_weight: null tensor");
+    IA_CHECK(Cout_pad >= Cout && Cin_pad >= Cin, "ia_pack_conv_weight: bad padding");
+    int taps = kh * kw;
+    int64_t total = (int64_t)taps * Cout_pad * Cin_pad;
+    pack_weight_kernel<<<(unsigned)cdiv(total, 256), 256, 0, as_stream(stream)>>>(w, Cout, Cin, taps, Cout_pad, Cin_pad, w_hi, w_lo);
+    IA_LAUNCH_CHECK("ia_pack_conv_weight");
+    if (wsq) {
+        wsq_kernel<<<(unsigned)cdiv((int64_t)Cout * Cin, 256), 256, 0, as_stream(stream)>>>(w, Cout, Cin, taps, wsq);
+        IA_LAUNCH_CHECK("ia_pack_conv_weight(wsq)");
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// shared epilogue math
+// ------------------------------------------------------------------------------------------------
+struct EpiArgs {
+    const float* dcoef; const float* noise; const float* noise_strength; const float* bias;
+    int act; float alpha, gain, clamp;
+};
+__device__ __forceinline__ float epi_value(float acc, const EpiArgs& e, int b, int co, int C, float noise_term) {
+    float v = acc;
+    if (e.dcoef) v = fmaf(v, e.dcoef[(int64_t)b * C + co], noise_term);  // fma(x, dcoef, noise), :74
+    else v += noise_term;
+    if (e.bias) v += e.bias[co];
+    return act_gain_clamp(v, e.act, e.alpha, e.gain, e.clamp);
+}
+
+// ------------------------------------------------------------------------------------------------
+// FIR epilogue for up=2 layers
+// ------------------------------------------------------------------------------------------------
+__global__ void fir_epilogue_kernel(ia_fir_params p) {
+    const int groups = p.C >> 2;
+    int64_t total = (int64_t)p.B * p.OH * p.OW * groups;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int g = i % groups; int64_t t = i / groups;
+    int ox = t % p.OW; t /= p.OW;
+    int oy = t % p.OH; int b = (int)(t / p.OH);
+    int c0 = g * 4;
+    // out[oy][ox] = sum_{ty,tx} F[ty][tx] * raw[oy+ty-1][ox+tx-1]   (pad [1,1,1,1]; F symmetric, gain folded in)
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int ty = 0; ty < 4; ++ty) {
+        int ry = oy + ty - 1;
+        if (ry < 0 || ry >= p.RH) continue;
+#pragma unroll
+        for (int tx = 0; tx < 4; ++tx) {
+            int rx = ox + tx - 1;
+            if (rx < 0 || rx >= p.RW) continue;
+            float f = p.fir[(3 - ty) * 4 + (3 - tx)];
+            float4 r = *reinterpret_cast<const float4*>(p.raw + (((int64_t)b * p.RH + ry) * p.RW + rx) * p.C + c0);
+            acc[0] = fmaf(f, r.x, acc[0]); acc[1] = fmaf(f, r.y, acc[1]);
+            acc[2] = fmaf(f, r.z, acc[2]); acc[3] = fmaf(f, r.w, acc[3]);
+        }
+    }
+    EpiArgs e{p.dcoef, p.noise, p.noise_strength, p.bias, p.act, p.alpha, p.gain, p.clamp};
+    float nz = p.noise ? p.noise[(int64_t)b * p.noise_bstride + (int64_t)oy * p.OW + ox] * p.noise_strength[0] : 0.f;
+    float v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = epi_value(acc[k], e, b, c0 + k, p.C, nz);
+    emit4(p.emit, b, ((int64_t)b * p.OH + oy) * p.OW + ox, c0, p.C, v);
+}
+
+extern "C" int ia_fir_epilogue(const ia_fir_params* p, void* stream) {
+    IA_CHECK(p && p->raw && p->fir, "ia_fir_epilogue: null tensor");
+    IA_CHECK((p->C & 3) == 0, "ia_fir_epilogue: C must be a multiple of 4");
+    IA_CHECK(p->noise == nullptr || p->noise_strength != nullptr, "ia_fir_epilogue: noise needs noise_strength");
+    int64_t total = (int64_t)p->B * p->OH * p->OW * (p->C >> 2);
+    if (total == 0) return 0;
+    fir_epilogue_kernel<<<(unsigned)cdiv(total, 256), 256, 0, as_stream(stream)>>>(*p);
+    IA_LAUNCH_CHECK("ia_fir_epilogue");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ToRGB tail: img_out = upsample2d(img_prev) + clamp(raw + bias)
+// ------------------------------------------------------------------------------------------------
+__global__ void torgb_finish_kernel(ia_torgb_params p) {
+    int64_t total = (int64_t)p.B * p.H * p.W * p.C;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int c, x, y, b;
+    if (p.out_nchw) {
+        x = i % p.W; int64_t t = i / p.W; y = t % p.H; t /= p.H; c = t % p.C; b = (int)(t / p.C);
+    } else {
+        c = i % p.C; int64_t t = i / p.C; x = t % p.W; t /= p.W; y = t % p.H; b = (int)(t / p.H);
+    }
+    float v = p.raw[(((int64_t)b * p.H + y) * p.W + x) * p.raw_ld + c];
+    if (p.bias) v += p.bias[c];
+    if (p.clamp >= 0.f) v = fminf(fmaxf(v, -p.clamp), p.clamp);
+    if (p.img_prev) {
+        // upsample2d: zero-stuff x2, pad (2,1), 4-tap [1,3,3,1]/8 * 2 per axis.  Even output 2m: .25*x[m-1] + .75*x[m];
+        // odd output 2m+1: .75*x[m] + .25*x[m+1]; samples outside the image are zero.
+        const int h2 = p.H >> 1, w2 = p.W >> 1;
+        int my = y >> 1, mx = x >> 1;
+        int y0, y1, x0, x1; float wy0, wy1, wx0, wx1;
+        if (y & 1) { y0 = my; y1 = my + 1; wy0 = 0.75f; wy1 = 0.25f; } else { y0 = my - 1; y1 = my; wy0 = 0.25f; wy1 = 0.75f; }
+        if (x & 1) { x0 = mx; x1 = mx + 1; wx0 = 0.75f; wx1 = 0.25f; } else { x0 = mx - 1; x1 = mx; wx0 = 0.25f; wx1 = 0.75f; }
+        const float* ip = p.img_prev + (int64_t)b * h2 * w2 * p.C + c;
+        float up = 0.f;
+        // accumulate in the order of the reference's 4x4 correlation (row-major over taps)
+        if (y0 >= 0 && y0 < h2) {
+            if (x0 >= 0 && x0 < w2) up = fmaf(wy0 * wx0, ip[((int64_t)y0 * w2 + x0) * p.C], up);
+            if (x1 >= 0 && x1 < w2) up = fmaf(wy0 * wx1, ip[((int64_t)y0 * w2 + x1) * p.C], up);
+        }
+        if (y1 >= 0 && y1 < h2) {
+            if (x0 >= 0 && x0 < w2) up = fmaf(wy1 * wx0, ip[((int64_t)y1 * w2 + x0) * p.C], up);
+            if (x1 >= 0 && x1 < w2) up = fmaf(wy1 * wx1, ip[((int64_t)y1 * w2 + x1) * p.C], up);
+        }
+        v = up + v;
+    }
+    if (p.out_nchw) p.img_out[(((int64_t)b * p.C + c) * p.H + y) * p.W + x] = v;
+    else p.img_out[(((int64_t)b * p.H + y) * p.W + x) * p.C + c] = v;
+}
+
+extern "C" int ia_torgb_finish(const ia_torgb_params* p, void* stream) {
+    IA_CHECK(p && p->raw && p->img_out, "ia_torgb_finish: null tensor");
+    IA_CHECK(p->img_prev == nullptr || ((p->H & 1) == 0 && (p->W & 1) == 0), "ia_torgb_finish: odd size with skip image");
+    int64_t total = (int64_t)p->B * p->H * p->W * p->C;
+    if (total == 0) return 0;
+    torgb_finish_kernel<<<(unsigned)cdiv(total, 256), 256, 0, as_stream(stream)>>>(*p);
+    IA_LAUNCH_CHECK("ia_torgb_finish");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// CUDA-core implicit GEMM (64 rows x 64 couts per CTA, 4x4 per thread, fp32 over hi+lo)
+// ------------------------------------------------------------------------------------------------
+#define SIMT_TM 64
+#define SIMT_TN 64
+#define SIMT_TK 16
+__global__ void __launch_bounds__(256) conv_simt_kernel(ia_conv_params p) {
+    __shared__ float As[SIMT_TK][SIMT_TM + 4];
+    __shared__ float Bs[SIMT_TK][SIMT_TN + 4];
+    const int tid = threadIdx.x;
+    const int64_t rows_total = (int64_t)p.B * p.GH * p.GW;
+    const int64_t row0 = (int64_t)blockIdx.x * SIMT_TM;
+    const int col0 = blockIdx.y * SIMT_TN;
+    // loader mapping: thread -> (row lr, 4 consecutive k)
+    const int lr = tid >> 2, lk = (tid & 3) * 4;
+    int64_t r = row0 + lr;
+    bool rvalid = r < rows_total;
+    int gx = 0, gy = 0, img = 0;
+    if (rvalid) { gx = r % p.GW; int64_t t = r / p.GW; gy = t % p.GH; img = (int)(t / p.GH); }
+    const int ty = tid >> 4, tx = tid & 15;  // compute mapping: rows ty*4.., cols tx*4..
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int t = 0; t < p.ntaps; ++t) {
+        int iy = gy + p.dy[t], ix = gx + p.dx[t];
+        bool avalid = rvalid && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+        const int64_t abase = avalid ? ((((int64_t)img * p.H + iy) * p.W + ix) * p.Cin_pad) : 0;
+        const int64_t wrow = ((int64_t)p.wtap[t] * p.Cout_pad + col0 + lr) * p.Cin_pad;
+        const bool wvalid = (col0 + lr) < p.Cout_pad;
+        for (int k0 = 0; k0 < p.Cin_pad; k0 += SIMT_TK) {
+            float av[4] = {0.f, 0.f, 0.f, 0.f}, wv[4] = {0.f, 0.f, 0.f, 0.f};
+            if (avalid) {
+                uint2 h = *reinterpret_cast<const uint2*>(p.a_hi + abase + k0 + lk);
+                uint2 l = *reinterpret_cast<const uint2*>(p.a_lo + abase + k0 + lk);
+                av[0] = bf16_bits_to_float(h.x & 0xffff) + bf16_bits_to_float(l.x & 0xffff);
+                av[1] = bf16_bits_to_float(h.x >> 16) + bf16_bits_to_float(l.x >> 16);
+                av[2] = bf16_bits_to_float(h.y & 0xffff) + bf16_bits_to_float(l.y & 0xffff);
+                av[3] = bf16_bits_to_float(h.y >> 16) + bf16_bits_to_float(l.y >> 16);
+            }
+            if (wvalid) {
+                uint2 h = *reinterpret_cast<const uint2*>(p.w_hi + wrow + k0 + lk);
+                uint2 l = *reinterpret_cast<const uint2*>(p.w_lo + wrow + k0 + lk);
+                wv[0] = bf16_bits_to_float(h.x & 0xffff) + bf16_bits_to_float(l.x & 0xffff);
+                wv[1] = bf16_bits_to_float(h.x >> 16) + bf16_bits_to_float(l.x >> 16);
+                wv[2] = bf16_bits_to_float(h.y & 0xffff) + bf16_bits_to_float(l.y & 0xffff);
+                wv[3] = bf16_bits_to_float(h.y >> 16) + bf16_bits_to_float(l.y >> 16);
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { As[lk + k][lr] = av[k]; Bs[lk + k][lr] = wv[k]; }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < SIMT_TK; ++k) {
+                float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+                float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+                float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+            }
+        }
+    }
+    EpiArgs e{p.dcoef, p.noise, p.noise_strength, p.bias, p.act, p.alpha, p.gain, p.clamp};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int64_t rr = row0 + ty * 4 + i;
+        if (rr >= rows_total) continue;
+        int ox = rr % p.GW; int64_t t = rr / p.GW; int oy = t % p.GH; int b = (int)(t / p.GH);
+        oy = oy * p.sy + p.py; ox = ox * p.sx + p.px;
+        if (oy >= p.OH || ox >= p.OW) continue;
+        int co = col0 + tx * 4;
+        if (co >= p.Cout) continue;
+        float v[4];
+        if (p.mode == 1) {
+            float nz = p.noise ? p.noise[(int64_t)b * p.noise_bstride + (int64_t)oy * p.OW + ox] * p.noise_strength[0] : 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = (co + j < p.Cout) ? epi_value(acc[i][j], e, b, co + j, p.Cout, nz) : 0.f;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = acc[i][j];
+        }
+        emit4(p.emit, b, ((int64_t)b * p.OH + oy) * p.OW + ox, co, p.Cout, v);
+    }
+}
+
+int ia_conv_validate(const ia_conv_params* p, const char* who) {
+    IA_CHECK(p && p->a_hi && p->a_lo && p->w_hi && p->w_lo, "%s: null operand", who);
+    IA_CHECK(p->Cin_pad > 0 && (p->Cin_pad % 64) == 0, "%s: Cin_pad must be a multiple of 64 (got %d)", who, p->Cin_pad);
+    IA_CHECK(p->Cout > 0 && p->Cout_pad >= p->Cout && (p->Cout_pad % 32) == 0, "%s: Cout_pad must be a multiple of 32 >= Cout", who);
+    IA_CHECK(p->ntaps >= 1 && p->ntaps <= 9, "%s: ntaps must be in [1,9]", who);
+    for (int t = 0; t < p->ntaps; ++t)
+        IA_CHECK(p->wtap[t] >= 0 && p->wtap[t] < p->n_taps_total, "%s: tap %d weight index out of range", who, t);
+    IA_CHECK(p->GH > 0 && p->GW > 0 && p->B > 0 && p->H > 0 && p->W > 0, "%s: empty geometry", who);
+    IA_CHECK(p->sy >= 1 && p->sx >= 1, "%s: bad output stride", who);
+    IA_CHECK(p->mode == 0 || p->mode == 1, "%s: bad epilogue mode", who);
+    IA_CHECK(p->noise == nullptr || p->noise_strength != nullptr, "%s: noise needs noise_strength", who);
+    IA_CHECK(p->emit.out32 || p->emit.hi1 || p->emit.hi2, "%s: nothing to emit", who);
+    IA_CHECK(!p->emit.hi1 || (p->emit.lo1 && p->emit.c1_pad >= p->Cout && (p->emit.c1_pad & 3) == 0), "%s: bad emit 1", who);
+    IA_CHECK(!p->emit.hi2 || (p->emit.lo2 && p->emit.c2_pad >= p->Cout && (p->emit.c2_pad & 3) == 0), "%s: bad emit 2", who);
+    return 0;
+}
+
+extern "C" int ia_conv_simt(const ia_conv_params* p, void* stream) {
+    if (int rc = ia_conv_validate(p, "ia_conv_simt")) return rc;
+    int64_t rows = (int64_t)p->B * p->GH * p->GW;
+    dim3 grid((unsigned)cdiv(rows, SIMT_TM), (unsigned)cdiv(p->Cout_pad, SIMT_TN));
+    conv_simt_kernel<<<grid, 256, 0, as_stream(stream)>>>(*p);
+    IA_LAUNCH_CHECK("ia_conv_simt");
+    return 0;
+}

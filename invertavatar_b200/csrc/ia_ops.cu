@@ -1,0 +1,259 @@
+// Library management + the torch_utils/ops plugin equivalents + small dense layers.
+// Behaviour follows reference torch_utils/ops/{bias_act,upfirdn2d}.{py,cu} and
+// training_avatar_texture/networks_stylegan2_new.py:96-127,233-268 (written from scratch).
+#include <stdarg.h>
+#include <atomic>
+
+#include "ia_common.cuh"
+
+namespace ia {
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+}  // namespace ia
+
+using namespace ia;
+
+extern "C" int ia_abi_version(void) { return IA_ABI_VERSION; }
+extern "C" const char* ia_last_error(void) { return ia::g_err; }
+extern "C" int64_t ia_launch_count(void) { return ia::g_launches.load(); }
+extern "C" void ia_reset_launch_count(void) { ia::g_launches.store(0); }
+extern "C" int ia_set_device(int device) {
+    cudaError_t e = cudaSetDevice(device);
+    IA_CHECK(e == cudaSuccess, "ia_set_device(%d): %s", device, cudaGetErrorString(e));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// bias_act
+// ------------------------------------------------------------------------------------------------
+__global__ void bias_act_kernel(const float* __restrict__ x, const float* __restrict__ b, float* __restrict__ y,
+                                int64_t numel, int64_t C, int64_t inner, int act, float alpha, float gain, float clamp) {
+    int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i0 >= numel) return;
+    if (i0 + 3 < numel && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
+        float4 v = *reinterpret_cast<const float4*>(x + i0);
+        float r[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float t = r[k];
+            if (b) t += b[((i0 + k) / inner) % C];
+            r[k] = act_gain_clamp(t, act, alpha, gain, clamp);
+        }
+        *reinterpret_cast<float4*>(y + i0) = make_float4(r[0], r[1], r[2], r[3]);
+    } else {
+        for (int k = 0; k < 4 && i0 + k < numel; ++k) {
+            float t = x[i0 + k];
+            if (b) t += b[((i0 + k) / inner) % C];
+            y[i0 + k] = act_gain_clamp(t, act, alpha, gain, clamp);
+        }
+    }
+}
+
+extern "C" int ia_bias_act(const float* x, const float* b, float* y, int64_t numel, int64_t C, int64_t inner,
+                           int act, float alpha, float gain, float clamp, void* stream) {
+    IA_CHECK(x && y, "ia_bias_act: null tensor");
+    IA_CHECK(act >= IA_ACT_LINEAR && act <= IA_ACT_SWISH, "ia_bias_act: bad activation id %d", act);
+    IA_CHECK(numel >= 0 && numel <= 0x7fffffffLL * 4, "ia_bias_act: numel too large");
+    IA_CHECK(b == nullptr || (C > 0 && inner > 0), "ia_bias_act: bias needs C>0 and inner>0");
+    if (numel == 0) return 0;
+    int threads = 256;
+    int64_t blocks = cdiv(cdiv(numel, 4), threads);
+    bias_act_kernel<<<(unsigned)blocks, threads, 0, as_stream(stream)>>>(x, b, y, numel, C > 0 ? C : 1,
+                                                                          inner > 0 ? inner : 1, act, alpha, gain, clamp);
+    IA_LAUNCH_CHECK("ia_bias_act");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// upfirdn2d (generic, strided)
+// ------------------------------------------------------------------------------------------------
+__global__ void upfirdn2d_kernel(ia_upfirdn2d_params p) {
+    int64_t total = (int64_t)p.N * p.C * p.outH * p.outW;
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    // decode with the fastest index following the smallest output stride (NCHW vs NHWC)
+    int n, c, oy, ox;
+    if (p.ys_c == 1) {  // channels-last: c fastest
+        c = idx % p.C; int64_t t = idx / p.C;
+        ox = t % p.outW; t /= p.outW;
+        oy = t % p.outH; n = (int)(t / p.outH);
+    } else {
+        ox = idx % p.outW; int64_t t = idx / p.outW;
+        oy = t % p.outH; t /= p.outH;
+        c = t % p.C; n = (int)(t / p.C);
+    }
+    // position in the zero-stuffed, padded signal
+    const int uy0 = oy * p.downy - p.pady0;  // top-left of the filter window in upsampled coordinates
+    const int ux0 = ox * p.downx - p.padx0;
+    const float* xb = p.x + n * p.xs_n + c * p.xs_c;
+    float acc = 0.f;
+    for (int fy = 0; fy < p.fh; ++fy) {
+        int uy = uy0 + fy;
+        if (uy < 0 || uy % p.upy != 0) continue;
+        int iy = uy / p.upy;
+        if (iy >= p.inH) continue;
+        for (int fx = 0; fx < p.fw; ++fx) {
+            int ux = ux0 + fx;
+            if (ux < 0 || ux % p.upx != 0) continue;
+            int ix = ux / p.upx;
+            if (ix >= p.inW) continue;
+            // reference: correlate with the flipped filter unless flip_filter is set
+            int ky = p.flip ? fy : (p.fh - 1 - fy);
+            int kx = p.flip ? fx : (p.fw - 1 - fx);
+            acc += p.f[ky * p.fw + kx] * xb[iy * p.xs_h + ix * p.xs_w];
+        }
+    }
+    p.y[n * p.ys_n + c * p.ys_c + oy * p.ys_h + ox * p.ys_w] = acc * p.gain;
+}
+
+extern "C" int ia_upfirdn2d(const ia_upfirdn2d_params* p, void* stream) {
+    IA_CHECK(p && p->x && p->y && p->f, "ia_upfirdn2d: null tensor");
+    IA_CHECK(p->upx >= 1 && p->upy >= 1 && p->downx >= 1 && p->downy >= 1, "ia_upfirdn2d: bad up/down factors");
+    IA_CHECK(p->fh >= 1 && p->fw >= 1 && p->fh <= 64 && p->fw <= 64, "ia_upfirdn2d: bad filter size");
+    int64_t total = (int64_t)p->N * p->C * p->outH * p->outW;
+    IA_CHECK(total >= 0 && total < (1LL << 40), "ia_upfirdn2d: output too large");
+    if (total == 0) return 0;
+    upfirdn2d_kernel<<<(unsigned)cdiv(total, 256), 256, 0, as_stream(stream)>>>(*p);
+    IA_LAUNCH_CHECK("ia_upfirdn2d");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fully connected: one warp per output feature, all batch rows per warp (weights read once)
+// ------------------------------------------------------------------------------------------------
+template <int MAXB>
+__global__ void fc_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                          float* __restrict__ y, int B, int In, int Out, float w_gain, float b_gain, int act,
+                          float alpha, float act_gain, int64_t xs, int64_t ys, int b0) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (warp >= Out) return;
+    int nb = min(MAXB, B - b0);
+    float acc[MAXB];
+#pragma unroll
+    for (int i = 0; i < MAXB; ++i) acc[i] = 0.f;
+    const float* wr = w + (int64_t)warp * In;
+    for (int k = lane; k < In; k += 32) {
+        float wv = wr[k];
+#pragma unroll
+        for (int i = 0; i < MAXB; ++i)
+            if (i < nb) acc[i] = fmaf(x[(int64_t)(b0 + i) * xs + k], wv, acc[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < MAXB; ++i) {
+        float v = acc[i];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0 && i < nb) {
+            float t = v * w_gain + (bias ? bias[warp] * b_gain : 0.f);
+            y[(int64_t)(b0 + i) * ys + warp] = apply_act(t, act, alpha) * act_gain;
+        }
+    }
+}
+
+extern "C" int ia_fully_connected(const float* x, const float* w, const float* bias, float* y, int32_t B, int32_t In,
+                                  int32_t Out, float w_gain, float b_gain, int act, float alpha, float act_gain,
+                                  int64_t x_stride, int64_t y_stride, void* stream) {
+    IA_CHECK(x && w && y, "ia_fully_connected: null tensor");
+    IA_CHECK(B >= 0 && In > 0 && Out > 0, "ia_fully_connected: bad shape");
+    if (B == 0) return 0;
+    int threads = 256;
+    int blocks = (int)cdiv((int64_t)Out * 32, threads);
+    for (int b0 = 0; b0 < B; b0 += 8) {
+        fc_kernel<8><<<blocks, threads, 0, as_stream(stream)>>>(x, w, bias, y, B, In, Out, w_gain, b_gain, act, alpha,
+                                                                  act_gain, x_stride, y_stride, b0);
+        IA_LAUNCH_CHECK("ia_fully_connected");
+    }
+    return 0;
+}
+
+__global__ void normalize_2nd_moment_kernel(const float* __restrict__ x, float* __restrict__ y, int D, float eps,
+                                            int64_t xs, int64_t ys) {
+    int b = blockIdx.x;
+    __shared__ float red[32];
+    float s = 0.f;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) {
+        float v = x[b * xs + i];
+        s += v * v;
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (threadIdx.x == 0) red[0] = rsqrtf(t / (float)D + eps);
+    }
+    __syncthreads();
+    float r = red[0];
+    for (int i = threadIdx.x; i < D; i += blockDim.x) y[b * ys + i] = x[b * xs + i] * r;
+}
+
+extern "C" int ia_normalize_2nd_moment(const float* x, float* y, int32_t B, int32_t D, float eps, int64_t x_stride,
+                                       int64_t y_stride, void* stream) {
+    IA_CHECK(x && y && D > 0, "ia_normalize_2nd_moment: bad arguments");
+    if (B == 0) return 0;
+    normalize_2nd_moment_kernel<<<B, 256, 0, as_stream(stream)>>>(x, y, D, eps, x_stride, y_stride);
+    IA_LAUNCH_CHECK("ia_normalize_2nd_moment");
+    return 0;
+}
+
+__global__ void broadcast_truncate_kernel(const float* __restrict__ w, const float* __restrict__ w_avg,
+                                          float* __restrict__ ws, int B, int num_ws, int D, float psi, int cutoff) {
+    int64_t total = (int64_t)B * num_ws * D;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int d = i % D;
+    int k = (i / D) % num_ws;
+    int b = (int)(i / ((int64_t)D * num_ws));
+    float v = w[(int64_t)b * D + d];
+    if (psi != 1.f && k < cutoff) {
+        // torch.lerp(start=w_avg, end=v, weight=psi): weight < 0.5 ? a + t*(b-a) : b - (b-a)*(1-t)
+        float a = w_avg[d];
+        v = (psi < 0.5f) ? a + psi * (v - a) : v - (v - a) * (1.f - psi);
+    }
+    ws[i] = v;
+}
+
+extern "C" int ia_broadcast_truncate(const float* w, const float* w_avg, float* ws, int32_t B, int32_t num_ws,
+                                     int32_t D, float psi, int32_t cutoff, void* stream) {
+    IA_CHECK(w && ws, "ia_broadcast_truncate: null tensor");
+    IA_CHECK(psi == 1.f || w_avg, "ia_broadcast_truncate: truncation needs w_avg");
+    int64_t total = (int64_t)B * num_ws * D;
+    if (total == 0) return 0;
+    broadcast_truncate_kernel<<<(unsigned)cdiv(total, 256), 256, 0, as_stream(stream)>>>(w, w_avg, ws, B, num_ws, D,
+                                                                                        psi, cutoff);
+    IA_LAUNCH_CHECK("ia_broadcast_truncate");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-pixel alpha blend
+// ------------------------------------------------------------------------------------------------
+__global__ void lerp_alpha_kernel(ia_lerp_params p) {
+    int64_t total = (int64_t)p.B * p.H * p.W * p.C;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int c = i % p.C; int64_t t = i / p.C;
+    int x = t % p.W; t /= p.W;
+    int y = t % p.H; int b = (int)(t / p.H);
+    float al = p.alpha[b * p.al_batch + y * p.al_row + x * p.al_ld];
+    float av = p.a[b * p.a_batch + y * p.a_row + x * p.a_ld + c];
+    float bv = p.b[b * p.b_batch + y * p.b_row + x * p.b_ld + c];
+    p.out[b * p.o_batch + y * p.o_row + x * p.o_ld + c] = av * al + bv * (1.f - al);
+}
+
+extern "C" int ia_lerp_alpha(const ia_lerp_params* p, void* stream) {
+    IA_CHECK(p && p->a && p->b && p->alpha && p->out, "ia_lerp_alpha: null tensor");
+    int64_t total = (int64_t)p->B * p->H * p->W * p->C;
+    if (total == 0) return 0;
+    lerp_alpha_kernel<<<(unsigned)cdiv(total, 256), 256, 0, as_stream(stream)>>>(*p);
+    IA_LAUNCH_CHECK("ia_lerp_alpha");
+    return 0;
+}

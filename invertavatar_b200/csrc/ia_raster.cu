@@ -1,0 +1,231 @@
+// UV rasterize / stitch kernels: GPU flood fill replacing cv2.floodFill, bilinear grid_sample, antialiased
+// bilinear resize.  Semantics follow reference training_avatar_texture/volumetric_rendering/renderer.py:716-741
+// (fill_mouth), triplane_v20.py:317-339 (rasterize) and the ATen ops they call.
+#include "ia_common.cuh"
+
+using namespace ia;
+
+// ------------------------------------------------------------------------------------------------
+// fill_mouth: one CTA per image, bit-packed masks in shared memory.
+//   passable(p) := 0 <= 255*alpha(p) - 255*alpha(0,0) <= 254   (FLOODFILL_FIXED_RANGE, lo=0, up=254, float image)
+//   reached     := 4-connected component of (0,0) inside passable
+// Propagation alternates a bit-parallel fill along rows (carry trick, one thread per row) with sequential
+// sweeps along columns (32 columns per thread) until nothing changes.
+// ------------------------------------------------------------------------------------------------
+#define FM_MAXW 8  // words per row (W <= 256)
+__global__ void __launch_bounds__(256) fill_mouth_kernel(const float* __restrict__ alpha, int64_t a_stride, int64_t a_batch,
+                                                         int H, int W, int upper_row0, float* __restrict__ full_alpha,
+                                                         float* __restrict__ mouth, float* __restrict__ upper_alpha) {
+    __shared__ uint32_t pass[256][FM_MAXW];
+    __shared__ uint32_t reach[256][FM_MAXW];
+    __shared__ int changed;
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x;
+    const float* ab = alpha + b * a_batch;
+    const int words = (W + 31) >> 5;
+    const float seed = ab[0] * 255.0f;
+    // build the passable mask: one thread per (row, word) pair, strided
+    for (int i = tid; i < H * FM_MAXW; i += blockDim.x) {
+        int y = i / FM_MAXW, k = i % FM_MAXW;
+        uint32_t m = 0;
+        if (k < words) {
+            for (int bit = 0; bit < 32; ++bit) {
+                int x = k * 32 + bit;
+                if (x < W) {
+                    float d = ab[((int64_t)y * W + x) * a_stride] * 255.0f - seed;
+                    if (d >= 0.0f && d <= 254.0f) m |= 1u << bit;
+                }
+            }
+        }
+        pass[y][k] = m;
+        reach[y][k] = 0;
+    }
+    __syncthreads();
+    if (tid == 0) { reach[0][0] = 1u; pass[0][0] |= 1u; }
+    __syncthreads();
+    for (int iter = 0; iter < 4096; ++iter) {
+        if (tid == 0) changed = 0;
+        __syncthreads();
+        // ---- rows: fill every passable run that contains a reached bit
+        if (tid < H) {
+            int y = tid;
+            bool ch = false;
+            uint32_t carry = 0;
+            for (int k = 0; k < words; ++k) {  // towards increasing x
+                uint32_t P = pass[y][k], R = reach[y][k];
+                uint32_t x = R & P;
+                if (carry && (P & 1u)) x |= 1u;
+                uint64_t sum = (uint64_t)P + (uint64_t)x;
+                uint32_t f = ((((uint32_t)sum) ^ P) & P) | x;
+                carry = (uint32_t)(sum >> 32) & 1u;
+                if (f & ~R) { reach[y][k] = R | f; ch = true; }
+            }
+            carry = 0;
+            for (int k = words - 1; k >= 0; --k) {  // towards decreasing x (bit-reversed words)
+                uint32_t P = __brev(pass[y][k]), R = __brev(reach[y][k]);
+                uint32_t x = R & P;
+                if (carry && (P & 1u)) x |= 1u;
+                uint64_t sum = (uint64_t)P + (uint64_t)x;
+                uint32_t f = ((((uint32_t)sum) ^ P) & P) | x;
+                carry = (uint32_t)(sum >> 32) & 1u;
+                if (f & ~R) { reach[y][k] = __brev(R | f); ch = true; }
+            }
+            if (ch) changed = 1;
+        }
+        __syncthreads();
+        // ---- columns: sequential sweeps, 32 columns per thread
+        if (tid < words) {
+            int k = tid;
+            bool ch = false;
+            uint32_t prev = reach[0][k];
+            for (int y = 1; y < H; ++y) {
+                uint32_t R = reach[y][k];
+                uint32_t n = R | (prev & pass[y][k]);
+                if (n != R) { reach[y][k] = n; ch = true; }
+                prev = n;
+            }
+            for (int y = H - 2; y >= 0; --y) {
+                uint32_t R = reach[y][k];
+                uint32_t n = R | (prev & pass[y][k]);
+                if (n != R) { reach[y][k] = n; ch = true; }
+                prev = n;
+            }
+            if (ch) changed = 1;
+        }
+        __syncthreads();
+        if (!changed) break;
+        __syncthreads();
+    }
+    // ---- outputs
+    for (int i = tid; i < H * W; i += blockDim.x) {
+        int y = i / W, x = i % W;
+        float a = ab[(int64_t)i * a_stride];
+        bool filled = (reach[y][x >> 5] >> (x & 31)) & 1u;
+        float m = filled ? 0.0f : (255.0f - a * 255.0f) / 255.0f;
+        int64_t o = (int64_t)b * H * W + i;
+        if (mouth) mouth[o] = m;
+        if (full_alpha) full_alpha[o] = fminf(fmaxf(a + m, 0.0f), 1.0f);
+        if (upper_alpha) upper_alpha[o] = fminf(fmaxf(a + (y >= upper_row0 ? m : 0.0f), 0.0f), 1.0f);
+    }
+}
+
+extern "C" int ia_fill_mouth(const float* alpha, int64_t a_stride, int64_t a_batch_stride, int32_t B, int32_t H, int32_t W,
+                             int32_t upper_row0, float* full_alpha, float* mouth, float* upper_alpha, void* stream) {
+    IA_CHECK(alpha, "ia_fill_mouth: null alpha");
+    IA_CHECK(H >= 1 && W >= 1 && H <= 256 && W <= 256, "ia_fill_mouth: image must be at most 256x256 (got %dx%d)", H, W);
+    if (B == 0) return 0;
+    fill_mouth_kernel<<<B, 256, 0, as_stream(stream)>>>(alpha, a_stride, a_batch_stride, H, W, upper_row0, full_alpha, mouth, upper_alpha);
+    IA_LAUNCH_CHECK("ia_fill_mouth");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// grid_sample: bilinear, zeros padding, align_corners=False, NHWC
+// ------------------------------------------------------------------------------------------------
+__global__ void grid_sample_kernel(const float* __restrict__ in, int B, int Hi, int Wi, int C, int64_t in_ld,
+                                   const float* __restrict__ grid, int64_t g_ld, int Ho, int Wo, float* __restrict__ out,
+                                   int64_t out_ld) {
+    const int groups = (C + 3) >> 2;
+    int64_t total = (int64_t)B * Ho * Wo * groups;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int g = i % groups; int64_t pix = i / groups;
+    int b = (int)(pix / ((int64_t)Ho * Wo));
+    const float gx = grid[pix * g_ld + 0], gy = grid[pix * g_ld + 1];
+    const float ix = ((gx + 1.f) * Wi - 1.f) / 2.f;
+    const float iy = ((gy + 1.f) * Hi - 1.f) / 2.f;
+    const float fx = floorf(ix), fy = floorf(iy);
+    const int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;
+    // ATen weights: nw = (x1-ix)(y1-iy), ne = (ix-x0)(y1-iy), sw = (x1-ix)(iy-y0), se = (ix-x0)(iy-y0)
+    const float wnw = ((float)x1 - ix) * ((float)y1 - iy);
+    const float wne = (ix - (float)x0) * ((float)y1 - iy);
+    const float wsw = ((float)x1 - ix) * (iy - (float)y0);
+    const float wse = (ix - (float)x0) * (iy - (float)y0);
+    const bool vx0 = x0 >= 0 && x0 < Wi, vx1 = x1 >= 0 && x1 < Wi, vy0 = y0 >= 0 && y0 < Hi, vy1 = y1 >= 0 && y1 < Hi;
+    const int c0 = g * 4;
+    const int nc = min(4, C - c0);
+    const bool vec = (nc == 4) && ((in_ld & 3) == 0);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* base = in + (int64_t)b * Hi * Wi * in_ld + c0;
+    auto corner = [&](int yy, int xx, float w) {
+        const float* p = base + ((int64_t)yy * Wi + xx) * in_ld;
+        if (vec) {
+            float4 t = *reinterpret_cast<const float4*>(p);
+            acc[0] += t.x * w; acc[1] += t.y * w; acc[2] += t.z * w; acc[3] += t.w * w;
+        } else {
+            for (int k = 0; k < nc; ++k) acc[k] += p[k] * w;
+        }
+    };
+    if (vy0 && vx0) corner(y0, x0, wnw);
+    if (vy0 && vx1) corner(y0, x1, wne);
+    if (vy1 && vx0) corner(y1, x0, wsw);
+    if (vy1 && vx1) corner(y1, x1, wse);
+    float* o = out + pix * out_ld + c0;
+    if (vec && (out_ld & 3) == 0) *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    else for (int k = 0; k < nc; ++k) o[k] = acc[k];
+}
+
+extern "C" int ia_grid_sample(const float* in, int32_t B, int32_t Hi, int32_t Wi, int32_t C, int64_t in_ld, const float* grid,
+                              int64_t g_ld, int32_t Ho, int32_t Wo, float* out, int64_t out_ld, void* stream) {
+    IA_CHECK(in && grid && out, "ia_grid_sample: null tensor");
+    IA_CHECK(C > 0 && in_ld >= C && out_ld >= C && g_ld >= 2, "ia_grid_sample: bad strides");
+    int64_t total = (int64_t)B * Ho * Wo * ((C + 3) >> 2);
+    if (total == 0) return 0;
+    grid_sample_kernel<<<(unsigned)cdiv(total, 256), 256, 0, as_stream(stream)>>>(in, B, Hi, Wi, C, in_ld, grid, g_ld, Ho, Wo, out, out_ld);
+    IA_LAUNCH_CHECK("ia_grid_sample");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// antialiased bilinear resize (separable taps; horizontal pass nested inside the vertical one, matching the
+// width-then-height order of ATen's separable implementation)
+// ------------------------------------------------------------------------------------------------
+__global__ void resize_aa_kernel(ia_resize_params p) {
+    const int groups = (p.C + 3) >> 2;
+    int64_t total = (int64_t)p.B * p.oh * p.ow * groups;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int g = i % groups; int64_t t = i / groups;
+    int ox = t % p.ow; t /= p.ow;
+    int oy = t % p.oh; int b = (int)(t / p.oh);
+    const int c0 = g * 4;
+    const int nc = min(4, p.C - c0);
+    const bool vec = (nc == 4) && ((p.in_ld & 3) == 0);
+    const int ys = p.y_start[oy], yn = p.y_count[oy];
+    const int xs = p.x_start[ox], xn = p.x_count[ox];
+    const float* wy = p.y_w + (int64_t)oy * p.y_max_taps;
+    const float* wx = p.x_w + (int64_t)ox * p.x_max_taps;
+    const float* base = p.in + (int64_t)b * p.in_H * p.in_W * p.in_ld + c0;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int ty = 0; ty < yn; ++ty) {
+        const float* row = base + ((int64_t)(p.in_y0 + ys + ty) * p.in_W + p.in_x0 + xs) * p.in_ld;
+        float r[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int tx = 0; tx < xn; ++tx) {
+            const float w = wx[tx];
+            const float* q = row + (int64_t)tx * p.in_ld;
+            if (vec) {
+                float4 v = *reinterpret_cast<const float4*>(q);
+                r[0] += v.x * w; r[1] += v.y * w; r[2] += v.z * w; r[3] += v.w * w;
+            } else {
+                for (int k = 0; k < nc; ++k) r[k] += q[k] * w;
+            }
+        }
+        const float w = wy[ty];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[k] += r[k] * w;
+    }
+    float* o = p.out + (((int64_t)b * p.out_H + p.out_y0 + oy) * p.out_W + p.out_x0 + ox) * p.out_ld + c0;
+    if (vec && (p.out_ld & 3) == 0) *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    else for (int k = 0; k < nc; ++k) o[k] = acc[k];
+}
+
+extern "C" int ia_resize_aa(const ia_resize_params* p, void* stream) {
+    IA_CHECK(p && p->in && p->out, "ia_resize_aa: null tensor");
+    IA_CHECK(p->y_start && p->y_count && p->y_w && p->x_start && p->x_count && p->x_w, "ia_resize_aa: null tap table");
+    IA_CHECK(p->C > 0 && p->in_ld >= p->C && p->out_ld >= p->C, "ia_resize_aa: bad strides");
+    int64_t total = (int64_t)p->B * p->oh * p->ow * ((p->C + 3) >> 2);
+    if (total == 0) return 0;
+    resize_aa_kernel<<<(unsigned)cdiv(total, 256), 256, 0, as_stream(stream)>>>(*p);
+    IA_LAUNCH_CHECK("ia_resize_aa");
+    return 0;
+}

@@ -1,0 +1,578 @@
+"""Host-side launch layer: torch tensors in, C-ABI calls out.
+
+PyTorch is used for device memory, streams and module/parameter bookkeeping only; every arithmetic step of
+the hot path is a kernel in libinvertavatar_b200.so.  All functions require CUDA tensors and raise
+RuntimeError otherwise -- there is no CPU path in the product (the CPU restatement lives in ``oracle/`` and
+is test infrastructure)."""
+import ctypes as C
+import math
+import threading
+
+import numpy as np
+import torch
+
+from . import _C
+
+ACT_IDS = {'linear': 1, 'relu': 2, 'lrelu': 3, 'tanh': 4, 'sigmoid': 5, 'elu': 6, 'selu': 7, 'softplus': 8, 'swish': 9}
+ACT_DEFAULTS = {  # name -> (def_alpha, def_gain), reference torch_utils/ops/bias_act.py:23-33
+    'linear': (0.0, 1.0), 'relu': (0.0, math.sqrt(2)), 'lrelu': (0.2, math.sqrt(2)), 'tanh': (0.0, 1.0),
+    'sigmoid': (0.0, 1.0), 'elu': (0.0, 1.0), 'selu': (0.0, 1.0), 'softplus': (0.0, 1.0), 'swish': (0.0, math.sqrt(2)),
+}
+
+_tls = threading.local()
+_conv_impl = 'tc'   # 'tc' (tcgen05 tensor cores) | 'simt' (CUDA cores; bring-up / cross-check)
+
+
+def set_conv_impl(name):
+    global _conv_impl
+    assert name in ('tc', 'simt')
+    _conv_impl = name
+
+
+def get_conv_impl():
+    return _conv_impl
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError('invertavatar_b200: CUDA tensors required (no CPU fallback exists for the hot path); '
+                               f'got a tensor on {t.device}')
+
+
+def _enter(t):
+    """Make the tensor's device current for this thread in both torch and the library; return the stream handle."""
+    _require_cuda(t)
+    idx = t.device.index if t.device.index is not None else torch.cuda.current_device()
+    if getattr(_tls, 'device', None) != idx:
+        _C.check(_C.lib().ia_set_device(idx), 'ia_set_device')
+        _tls.device = idx
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _f32c(t):
+    """fp32 + contiguous (no copy when already so)."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def launch_count():
+    return int(_C.lib().ia_launch_count())
+
+
+def reset_launch_count():
+    _C.lib().ia_reset_launch_count()
+
+
+# ---------------------------------------------------------------------------------------------------
+# layout helpers: public tensors are logical NCHW with channels-last strides, kernels see NHWC
+# ---------------------------------------------------------------------------------------------------
+def to_nhwc(x):
+    """[B,C,H,W] (any strides) -> contiguous [B,H,W,C] fp32 view/copy."""
+    if x.dtype != torch.float32:
+        x = x.float()
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def from_nhwc(x):
+    """contiguous [B,H,W,C] -> logical [B,C,H,W] view (channels_last strides, no copy)."""
+    return x.permute(0, 3, 1, 2)
+
+
+# ---------------------------------------------------------------------------------------------------
+# torch_utils/ops equivalents
+# ---------------------------------------------------------------------------------------------------
+def bias_act(x, b=None, dim=1, act='linear', alpha=None, gain=None, clamp=None):
+    _require_cuda(x, b)
+    spec = ACT_DEFAULTS[act]
+    alpha = float(spec[0] if alpha is None else alpha)
+    gain = float(spec[1] if gain is None else gain)
+    clamp = float(-1 if clamp is None else clamp)
+    st = _enter(x)
+    xd = x if x.dtype == torch.float32 else x.float()
+    # dense in either contiguous or channels-last order: operate in memory order
+    if xd.is_contiguous():
+        xm, shape = xd, list(xd.shape)
+        mdim = dim
+    elif xd.ndim == 4 and xd.is_contiguous(memory_format=torch.channels_last):
+        xm = xd.permute(0, 2, 3, 1)
+        shape = list(xm.shape)
+        mdim = {0: 0, 1: 3, 2: 1, 3: 2}[dim % 4]
+    else:
+        xd = xd.contiguous()
+        xm, shape, mdim = xd, list(xd.shape), dim
+    y = torch.empty_like(xd)
+    Cn, inner = 1, 1
+    if b is not None:
+        if b.ndim != 1 or b.shape[0] != shape[mdim]:
+            raise RuntimeError('bias_act: bias must be 1-D and match x.shape[dim]')
+        b = _f32c(b)
+        Cn = shape[mdim]
+        inner = int(np.prod(shape[mdim + 1:])) if mdim + 1 < len(shape) else 1
+    _C.check(_C.lib().ia_bias_act(_p(xd), _p(b), _p(y), xd.numel(), Cn, inner, ACT_IDS[act], alpha, gain, clamp, st), 'ia_bias_act')
+    return y if x.dtype == torch.float32 else y.to(x.dtype)
+
+
+def upfirdn2d(x, f, up=(1, 1), down=(1, 1), padding=(0, 0, 0, 0), flip_filter=False, gain=1.0):
+    """x [N,C,H,W] any strides; f fp32 [fh,fw] | [taps] (separable) | None.  padding = [x0,x1,y0,y1]."""
+    _require_cuda(x, f)
+    st = _enter(x)
+    upx, upy = up
+    downx, downy = down
+    px0, px1, py0, py1 = [int(v) for v in padding]
+    xd = x if x.dtype == torch.float32 else x.float()
+    N, Cc, H, W = xd.shape
+    if f is None:
+        f = torch.ones(1, 1, dtype=torch.float32, device=x.device)
+    f = f.to(torch.float32)
+    passes = []
+    if f.ndim == 2:
+        passes.append((f.contiguous(), gain, (px0, px1, py0, py1), (upx, upy), (downx, downy)))
+    else:  # separable: x pass then y pass, gain split as sqrt per pass (reference upfirdn2d.py:197,206-208)
+        g = float(gain) ** 0.5
+        passes.append((f.reshape(1, -1).contiguous(), g, (px0, px1, 0, 0), (upx, 1), (downx, 1)))
+        passes.append((f.reshape(-1, 1).contiguous(), g, (0, 0, py0, py1), (1, upy), (1, downy)))
+    cur = xd
+    for (ff, g, (a0, a1, b0, b1), (ux, uy), (dx, dy)) in passes:
+        n, c, h, w = cur.shape
+        fh, fw = ff.shape
+        outW = (w * ux + a0 + a1 - fw) // dx + 1
+        outH = (h * uy + b0 + b1 - fh) // dy + 1
+        if outW < 1 or outH < 1:
+            raise RuntimeError('upfirdn2d: upsampled/padded signal is smaller than the filter')
+        cl = cur.ndim == 4 and cur.stride(1) == 1 and c > 1
+        y = torch.empty((n, c, outH, outW), dtype=torch.float32, device=cur.device,
+                        memory_format=torch.channels_last if cl else torch.contiguous_format)
+        p = _C.Upfirdn2dParams(_p(cur), _p(ff), _p(y), n, c, h, w, outH, outW, fh, fw, ux, uy, dx, dy, a0, b0,
+                               1 if flip_filter else 0, float(g),
+                               cur.stride(0), cur.stride(1), cur.stride(2), cur.stride(3),
+                               y.stride(0), y.stride(1), y.stride(2), y.stride(3))
+        _C.check(_C.lib().ia_upfirdn2d(C.byref(p), st), 'ia_upfirdn2d')
+        cur = y
+    return cur if x.dtype == torch.float32 else cur.to(x.dtype)
+
+
+# ---------------------------------------------------------------------------------------------------
+# small dense layers
+# ---------------------------------------------------------------------------------------------------
+def fully_connected(x, weight, bias=None, w_gain=1.0, b_gain=1.0, act='linear', alpha=None, act_gain=None):
+    _require_cuda(x, weight, bias)
+    st = _enter(x)
+    spec = ACT_DEFAULTS[act]
+    alpha = float(spec[0] if alpha is None else alpha)
+    act_gain = float(spec[1] if act_gain is None else act_gain)
+    x2 = _f32c(x.reshape(-1, x.shape[-1]))
+    w = _f32c(weight)
+    b = _f32c(bias) if bias is not None else None
+    B, In = x2.shape
+    Out = w.shape[0]
+    if w.shape[1] != In:
+        raise RuntimeError(f'fully_connected: input features {In} do not match weight {tuple(w.shape)}')
+    y = torch.empty((B, Out), dtype=torch.float32, device=x.device)
+    _C.check(_C.lib().ia_fully_connected(_p(x2), _p(w), _p(b), _p(y), B, In, Out, float(w_gain), float(b_gain),
+                                         ACT_IDS[act], alpha, act_gain, In, Out, st), 'ia_fully_connected')
+    return y.reshape(*x.shape[:-1], Out)
+
+
+def normalize_2nd_moment(x, eps=1e-8):
+    _require_cuda(x)
+    st = _enter(x)
+    x2 = _f32c(x)
+    y = torch.empty_like(x2)
+    _C.check(_C.lib().ia_normalize_2nd_moment(_p(x2), _p(y), x2.shape[0], x2.shape[1], float(eps), x2.shape[1], x2.shape[1], st),
+             'ia_normalize_2nd_moment')
+    return y
+
+
+def broadcast_truncate(w, w_avg, num_ws, psi=1.0, cutoff=None):
+    _require_cuda(w, w_avg)
+    st = _enter(w)
+    w = _f32c(w)
+    B, D = w.shape
+    ws = torch.empty((B, num_ws, D), dtype=torch.float32, device=w.device)
+    cut = num_ws if cutoff is None else int(cutoff)
+    wa = _f32c(w_avg) if w_avg is not None else None
+    _C.check(_C.lib().ia_broadcast_truncate(_p(w), _p(wa), _p(ws), B, num_ws, D, float(psi), cut, st), 'ia_broadcast_truncate')
+    return ws
+
+
+# ---------------------------------------------------------------------------------------------------
+# modulated convolution pieces
+# ---------------------------------------------------------------------------------------------------
+def _pad_to(v, m):
+    return (v + m - 1) // m * m
+
+
+class ConvPack:
+    """GEMM-layout weights of one conv layer: bf16 hi/lo [taps][Cout_pad][Cin_pad] and wsq[Cout][Cin]."""
+
+    def __init__(self, weight, need_wsq=True):
+        _require_cuda(weight)
+        st = _enter(weight)
+        w = _f32c(weight.detach())
+        self.Cout, self.Cin, self.kh, self.kw = w.shape
+        self.taps = self.kh * self.kw
+        self.Cout_pad = _pad_to(self.Cout, 32)
+        self.Cin_pad = _pad_to(self.Cin, 64)
+        dev = w.device
+        self.w_hi = torch.empty((self.taps, self.Cout_pad, self.Cin_pad), dtype=torch.bfloat16, device=dev)
+        self.w_lo = torch.empty_like(self.w_hi)
+        self.wsq = torch.empty((self.Cout, self.Cin), dtype=torch.float32, device=dev) if need_wsq else None
+        _C.check(_C.lib().ia_pack_conv_weight(_p(w), self.Cout, self.Cin, self.kh, self.kw, self.Cout_pad, self.Cin_pad,
+                                              _p(self.w_hi), _p(self.w_lo), _p(self.wsq), st), 'ia_pack_conv_weight')
+        self.key = (weight.data_ptr(), weight._version, str(dev))
+
+    @staticmethod
+    def current(cache_owner, attr, weight, need_wsq=True):
+        """Return the pack cached on ``cache_owner.<attr>``; repack when the parameter changed."""
+        pack = cache_owner.__dict__.get(attr)
+        key = (weight.data_ptr(), weight._version, str(weight.device))
+        if pack is None or pack.key != key:
+            pack = ConvPack(weight, need_wsq)
+            cache_owner.__dict__[attr] = pack
+        return pack
+
+
+class StylePlan:
+    """Device table of ia_style_layer entries + output buffers for a group of layers that share one ws tensor."""
+
+    def __init__(self, entries, device):
+        # entries: list of dict(affine_w, affine_b, wsq|None, Cin, Cout, w_index, style_gain)
+        self.entries = entries
+        self.device = device
+        self.cap = 0
+        self.styles = []
+        self.dcoefs = []
+        self.host = None
+        self.dev = None
+
+    def _build(self, B):
+        n = len(self.entries)
+        self.cap = B
+        self.styles = [torch.empty((B, e['Cin']), dtype=torch.float32, device=self.device) for e in self.entries]
+        self.dcoefs = [torch.empty((B, e['Cout']), dtype=torch.float32, device=self.device) if e['wsq'] is not None else None
+                       for e in self.entries]
+        arr = (_C.StyleLayer * n)()
+        for i, e in enumerate(self.entries):
+            w_dim = e['affine_w'].shape[1]
+            arr[i] = _C.StyleLayer(_p(e['affine_w']), _p(e['affine_b']), _p(e['wsq']), _p(self.styles[i]), _p(self.dcoefs[i]),
+                                   e['Cin'], e['Cout'], e['w_index'], w_dim, 1.0 / math.sqrt(w_dim), float(e['style_gain']))
+        self.host = arr
+        raw = np.frombuffer(bytes(arr), dtype=np.uint8).copy()
+        self.dev = torch.from_numpy(raw).to(self.device)
+
+    def run(self, ws):
+        """ws: [B, n, w_dim] fp32 with unit inner stride (may be a narrow() view of a wider tensor)."""
+        st = _enter(ws)
+        if ws.dtype != torch.float32 or ws.stride(2) != 1 or ws.stride(1) != ws.shape[2] or ws.stride(0) % ws.shape[2] != 0:
+            ws = ws.float().contiguous()
+        B = ws.shape[0]
+        if self.host is None or B != self.cap:
+            self._build(B)
+        num_ws = max(ws.stride(0) // ws.shape[2], ws.shape[1])  # batch stride of a narrow() view, in rows
+        _C.check(_C.lib().ia_styles(_p(self.dev), self.host, len(self.entries), _p(ws), B, num_ws, st), 'ia_styles')
+        return self.styles, self.dcoefs
+
+
+def modsplit(x_nhwc, styles=None, cond=None, cond_alpha=None, C_pad=None):
+    """x [B,H,W,C] fp32 (pixel stride = x.stride(2)) -> (hi, lo) bf16 [B,H,W,C_pad] of x*styles (after optional blend)."""
+    st = _enter(x_nhwc)
+    B, H, W, Cc = x_nhwc.shape
+    assert x_nhwc.stride(3) == 1 and x_nhwc.stride(1) == W * x_nhwc.stride(2) and x_nhwc.stride(0) == H * x_nhwc.stride(1)
+    C_pad = _pad_to(Cc, 64) if C_pad is None else C_pad
+    hi = torch.empty((B, H, W, C_pad), dtype=torch.bfloat16, device=x_nhwc.device)
+    lo = torch.empty_like(hi)
+    cond_ld = 0
+    if cond is not None:
+        assert cond.shape == x_nhwc.shape and cond.stride(3) == 1 and cond_alpha is not None
+        assert cond.stride(1) == W * cond.stride(2) and cond.stride(0) == H * cond.stride(1)
+        assert cond_alpha.is_contiguous() and cond_alpha.numel() == B * H * W
+        cond_ld = cond.stride(2)
+    p = _C.ModsplitParams(_p(x_nhwc), x_nhwc.stride(2), _p(styles), _p(cond), cond_ld, _p(cond_alpha), _p(hi), _p(lo),
+                          B, H * W, Cc, C_pad)
+    _C.check(_C.lib().ia_modsplit(C.byref(p), st), 'ia_modsplit')
+    return hi, lo
+
+
+def _emit(out32=None):
+    e = _C.Emit()
+    if out32 is not None:
+        e.out32 = _p(out32)
+        e.out32_ld = out32.stride(2)
+    return e
+
+
+def _conv_call(p, st, impl=None):
+    impl = impl or _conv_impl
+    fn = _C.lib().ia_conv_tc if impl == 'tc' else _C.lib().ia_conv_simt
+    _C.check(fn(C.byref(p), st), 'ia_conv_' + impl)
+
+
+def _noise_bstride(noise):
+    return 0 if noise is None or noise.ndim < 3 else noise.shape[-1] * noise.shape[-2]
+
+
+def conv_same(hi, lo, pack, Cin_pad, out32, dcoef=None, noise=None, noise_strength=None, bias=None, act='linear',
+              gain=1.0, clamp=None, mode=1, impl=None):
+    """k x k correlation, stride 1, 'same' padding (flip_weight=True branch of conv2d_resample, :134-136)."""
+    st = _enter(hi)
+    B, H, W, _ = hi.shape
+    k = pack.kh
+    pad = k // 2
+    p = _C.ConvParams()
+    p.a_hi, p.a_lo, p.B, p.H, p.W, p.Cin_pad = _p(hi), _p(lo), B, H, W, Cin_pad
+    p.w_hi, p.w_lo, p.Cout, p.Cout_pad, p.n_taps_total = _p(pack.w_hi), _p(pack.w_lo), pack.Cout, pack.Cout_pad, pack.taps
+    p.GH, p.GW, p.ntaps = H, W, k * k
+    t = 0
+    for ky in range(k):
+        for kx in range(k):
+            p.dy[t], p.dx[t], p.wtap[t] = ky - pad, kx - pad, ky * k + kx
+            t += 1
+    p.OH, p.OW, p.sy, p.sx, p.py, p.px = H, W, 1, 1, 0, 0
+    p.mode = mode
+    p.dcoef, p.noise, p.noise_strength, p.bias = _p(dcoef), _p(noise), _p(noise_strength), _p(bias)
+    p.noise_bstride = _noise_bstride(noise)
+    p.act, p.alpha, p.gain, p.clamp = ACT_IDS[act], ACT_DEFAULTS[act][0], float(gain), float(-1 if clamp is None else clamp)
+    p.emit = _emit(out32)
+    _conv_call(p, st, impl)
+
+
+def conv_transpose_up2_raw(hi, lo, pack, Cin_pad, raw, impl=None):
+    """Stride-2 transposed 3x3 convolution (true convolution, conv2d_resample.py:114-127) written as four output-parity
+    phases; raw is [B, 2H+1, 2W+1, Cout] fp32.  Even output row 2m gets ky=0 from input row m and ky=2 from row m-1; odd
+    output row 2m+1 gets ky=1 from row m (same for columns)."""
+    st = _enter(hi)
+    B, H, W, _ = hi.shape
+    assert pack.kh == 3 and pack.kw == 3
+    rowtaps = {0: [(0, 0), (2, -1)], 1: [(1, 0)]}
+    for py in (0, 1):
+        for px in (0, 1):
+            p = _C.ConvParams()
+            p.a_hi, p.a_lo, p.B, p.H, p.W, p.Cin_pad = _p(hi), _p(lo), B, H, W, Cin_pad
+            p.w_hi, p.w_lo, p.Cout, p.Cout_pad, p.n_taps_total = _p(pack.w_hi), _p(pack.w_lo), pack.Cout, pack.Cout_pad, pack.taps
+            p.GH, p.GW = H + 1 - py, W + 1 - px
+            t = 0
+            for (ky, dy) in rowtaps[py]:
+                for (kx, dx) in rowtaps[px]:
+                    p.dy[t], p.dx[t], p.wtap[t] = dy, dx, ky * 3 + kx
+                    t += 1
+            p.ntaps = t
+            p.OH, p.OW, p.sy, p.sx, p.py, p.px = 2 * H + 1, 2 * W + 1, 2, 2, py, px
+            p.mode = 0
+            p.act, p.alpha, p.gain, p.clamp = 1, 0.0, 1.0, -1.0
+            p.emit = _emit(raw)
+            _conv_call(p, st, impl)
+
+
+_FIR_CACHE = {}
+
+
+def fir4x4_gain4(device):
+    """outer([1,3,3,1])/64 * 4 : the resample filter of every synthesis layer times the up**2 gain."""
+    key = str(device)
+    f = _FIR_CACHE.get(key)
+    if f is None:
+        k = torch.tensor([1.0, 3.0, 3.0, 1.0])
+        f2 = torch.outer(k, k)
+        f2 = f2 / f2.sum() * 4.0
+        f = f2.to(device)
+        _FIR_CACHE[key] = f
+    return f
+
+
+def fir_epilogue(raw, fir, out32, dcoef, noise, noise_strength, bias, act, gain, clamp):
+    st = _enter(raw)
+    B, RH, RW, Cc = raw.shape
+    _, OH, OW, _ = out32.shape
+    p = _C.FirParams()
+    p.raw, p.B, p.RH, p.RW, p.C = _p(raw), B, RH, RW, Cc
+    p.fir, p.OH, p.OW = _p(fir), OH, OW
+    p.dcoef, p.noise, p.noise_strength, p.bias = _p(dcoef), _p(noise), _p(noise_strength), _p(bias)
+    p.noise_bstride = _noise_bstride(noise)
+    p.act, p.alpha, p.gain, p.clamp = ACT_IDS[act], ACT_DEFAULTS[act][0], float(gain), float(-1 if clamp is None else clamp)
+    p.emit = _emit(out32)
+    _C.check(_C.lib().ia_fir_epilogue(C.byref(p), st), 'ia_fir_epilogue')
+
+
+def torgb_finish(raw, bias, clamp, img_prev, out_nchw=False):
+    """raw [B,H,W,C]; img_prev [B,H/2,W/2,C] NHWC or None -> img [B,H,W,C] NHWC (or [B,C,H,W] planar)."""
+    st = _enter(raw)
+    B, H, W, Cc = raw.shape
+    if out_nchw:
+        out = torch.empty((B, Cc, H, W), dtype=torch.float32, device=raw.device)
+    else:
+        out = torch.empty((B, H, W, Cc), dtype=torch.float32, device=raw.device)
+    if img_prev is not None:
+        assert img_prev.is_contiguous() and tuple(img_prev.shape) == (B, H // 2, W // 2, Cc), (img_prev.shape, raw.shape)
+    p = _C.TorgbParams(_p(raw), raw.stride(2), _p(bias), float(-1 if clamp is None else clamp), _p(img_prev), _p(out),
+                       B, H, W, Cc, 1 if out_nchw else 0)
+    _C.check(_C.lib().ia_torgb_finish(C.byref(p), st), 'ia_torgb_finish')
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# rasterize / stitch pieces
+# ---------------------------------------------------------------------------------------------------
+def fill_mouth(uv_or_alpha, upper_row0=87):
+    """alpha given either as uvcoords_image [B,H,W,3] (mask in channel 2) or as [B,1,H,W]; returns
+    (full_alpha, mouth, upper_alpha) as contiguous [B,H,W] tensors."""
+    st = _enter(uv_or_alpha)
+    t = uv_or_alpha if uv_or_alpha.dtype == torch.float32 else uv_or_alpha.float()
+    if t.ndim == 4 and t.shape[-1] == 3 and t.shape[1] != 1:
+        t = t.contiguous()
+        B, H, W, _ = t.shape
+        base, a_stride, a_batch = t.data_ptr() + 2 * 4, 3, H * W * 3
+    else:
+        t = t.contiguous()
+        B, _, H, W = t.shape
+        base, a_stride, a_batch = t.data_ptr(), 1, H * W
+    full = torch.empty((B, H, W), dtype=torch.float32, device=t.device)
+    mouth = torch.empty_like(full)
+    upper = torch.empty_like(full)
+    _C.check(_C.lib().ia_fill_mouth(base, a_stride, a_batch, B, H, W, int(upper_row0), _p(full), _p(mouth), _p(upper), st),
+             'ia_fill_mouth')
+    return full, mouth, upper
+
+
+def grid_sample_nhwc(x_nhwc, grid, g_ld=None):
+    """x [B,Hi,Wi,C] contiguous; grid [B,Ho,Wo,>=2] (last-dim stride 1) -> [B,Ho,Wo,C]."""
+    st = _enter(x_nhwc)
+    B, Hi, Wi, Cc = x_nhwc.shape
+    assert x_nhwc.is_contiguous()
+    grid = grid if grid.dtype == torch.float32 else grid.float()
+    if not grid.is_contiguous():
+        grid = grid.contiguous()
+    _, Ho, Wo, gl = grid.shape
+    out = torch.empty((B, Ho, Wo, Cc), dtype=torch.float32, device=x_nhwc.device)
+    _C.check(_C.lib().ia_grid_sample(_p(x_nhwc), B, Hi, Wi, Cc, Cc, _p(grid), gl, Ho, Wo, _p(out), Cc, st), 'ia_grid_sample')
+    return out
+
+
+_AA_CACHE = {}
+
+
+def aa_tables(in_size, out_size, device):
+    """Tap tables of ATen's _upsample_bilinear2d_aa for one axis (float32 arithmetic as in
+    aten/src/ATen/native/cpu/UpSampleKernel.cpp, _compute_indices_min_size_weights_aa)."""
+    key = (in_size, out_size, str(device))
+    hit = _AA_CACHE.get(key)
+    if hit is not None:
+        return hit
+    f32 = np.float32
+    scale = f32(in_size) / f32(out_size)
+    support = f32(1.0) * scale if scale >= 1.0 else f32(1.0)
+    invscale = f32(1.0) / scale if scale >= 1.0 else f32(1.0)
+    max_taps = int(math.ceil(float(support))) * 2 + 1
+    starts = np.zeros(out_size, dtype=np.int32)
+    counts = np.zeros(out_size, dtype=np.int32)
+    weights = np.zeros((out_size, max_taps), dtype=np.float32)
+    for i in range(out_size):
+        center = scale * f32(i + 0.5)
+        xmin = max(int(center - support + f32(0.5)), 0)
+        xsize = min(int(center + support + f32(0.5)), in_size) - xmin
+        xsize = max(min(xsize, max_taps), 0)
+        ws = np.zeros(max_taps, dtype=np.float32)
+        total = f32(0.0)
+        for j in range(xsize):
+            x = (f32(j + xmin) - center + f32(0.5)) * invscale
+            x = -x if x < 0 else x
+            w = f32(1.0) - x if x < 1.0 else f32(0.0)
+            ws[j] = w
+            total = f32(total + w)
+        if total != 0:
+            ws[:xsize] = ws[:xsize] / total
+        starts[i], counts[i] = xmin, xsize
+        weights[i] = ws
+    out = (torch.from_numpy(starts).to(device), torch.from_numpy(counts).to(device),
+           torch.from_numpy(weights).to(device), max_taps)
+    _AA_CACHE[key] = out
+    return out
+
+
+def resize_aa(x_nhwc, oh, ow, crop=None, out=None, out_origin=(0, 0)):
+    """Antialiased bilinear resize of (a crop of) x [B,H,W,C] to [oh,ow], optionally pasted into ``out`` at out_origin."""
+    st = _enter(x_nhwc)
+    B, H, W, Cc = x_nhwc.shape
+    assert x_nhwc.stride(3) == 1 and x_nhwc.stride(1) == W * x_nhwc.stride(2) and x_nhwc.stride(0) == H * x_nhwc.stride(1)
+    y0, y1, x0, x1 = (0, H, 0, W) if crop is None else crop
+    ih, iw = y1 - y0, x1 - x0
+    ys, yc, yw, ymt = aa_tables(ih, oh, x_nhwc.device)
+    xs, xc, xw, xmt = aa_tables(iw, ow, x_nhwc.device)
+    if out is None:
+        out = torch.empty((B, oh, ow, Cc), dtype=torch.float32, device=x_nhwc.device)
+    OB, OHh, OWw, OC = out.shape
+    assert OB == B and out.stride(3) == 1 and out.stride(1) == OWw * out.stride(2) and out.stride(0) == OHh * out.stride(1)
+    p = _C.ResizeParams(_p(x_nhwc), x_nhwc.stride(2), H, W, y0, x0, _p(out), out.stride(2), OHh, OWw, out_origin[0], out_origin[1],
+                        B, Cc, oh, ow, _p(ys), _p(yc), _p(yw), ymt, _p(xs), _p(xc), _p(xw), xmt)
+    _C.check(_C.lib().ia_resize_aa(C.byref(p), st), 'ia_resize_aa')
+    return out
+
+
+def lerp_alpha(a, b, alpha, out=None):
+    """out = a*alpha + b*(1-alpha); a,b,out [B,H,W,C] NHWC views (unit channel stride), alpha [B,H,W] view."""
+    st = _enter(a)
+    B, H, W, Cc = a.shape
+    if out is None:
+        out = torch.empty((B, H, W, Cc), dtype=torch.float32, device=a.device)
+    for t in (a, b, out):
+        assert t.stride(3) == 1 and tuple(t.shape) == (B, H, W, Cc)
+    assert tuple(alpha.shape) == (B, H, W)
+    p = _C.LerpParams(_p(a), a.stride(2), a.stride(1), a.stride(0), _p(b), b.stride(2), b.stride(1), b.stride(0),
+                      _p(alpha), alpha.stride(2), alpha.stride(1), alpha.stride(0),
+                      _p(out), out.stride(2), out.stride(1), out.stride(0), B, H, W, Cc)
+    _C.check(_C.lib().ia_lerp_alpha(C.byref(p), st), 'ia_lerp_alpha')
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# renderer
+# ---------------------------------------------------------------------------------------------------
+def ray_sampler(cam, res):
+    st = _enter(cam)
+    cam = _f32c(cam)
+    B = cam.shape[0]
+    o = torch.empty((B, res * res, 3), dtype=torch.float32, device=cam.device)
+    d = torch.empty_like(o)
+    _C.check(_C.lib().ia_ray_sampler(_p(cam), cam.stride(0), B, res, _p(o), _p(d), st), 'ia_ray_sampler')
+    return o, d
+
+
+def render(planes_nhwc, cam, res, Dc, Df, jitter, u, box_warp, white_back, w1, b1, w2, b2, rays=None):
+    """planes [B,PH,PW,>=96] NHWC fp32 (plane p = channels 32p..32p+31); cam [B,>=25] (or rays=(origins, dirs)
+    [B,res*res,3] with cam=None); returns feat [B,res,res,32], depth [B,res,res] (clamped), wsum [B,res,res]."""
+    st = _enter(planes_nhwc)
+    B, PH, PW, PC = planes_nhwc.shape
+    assert planes_nhwc.is_contiguous() and PC >= 96
+    rays_o = rays_d = None
+    if rays is not None:
+        rays_o, rays_d = _f32c(rays[0]), _f32c(rays[1])
+        assert rays_o.numel() == B * res * res * 3 and rays_d.numel() == rays_o.numel()
+    else:
+        cam = _f32c(cam)
+    jitter = _f32c(jitter)
+    assert jitter.numel() == B * res * res * Dc, (jitter.shape, B, res, Dc)
+    if u is not None:
+        u = _f32c(u)
+        assert u.numel() == B * res * res * Df
+    dev = planes_nhwc.device
+    near_far = torch.empty(4, dtype=torch.float32, device=dev)
+    if rays is not None:
+        _C.check(_C.lib().ia_ray_bounds_from_origins(_p(rays_o), rays_o.numel() // 3, _p(near_far), st), 'ia_ray_bounds_from_origins')
+    else:
+        _C.check(_C.lib().ia_ray_bounds(_p(cam), cam.stride(0), B, _p(near_far), st), 'ia_ray_bounds')
+    feat = torch.empty((B, res, res, 32), dtype=torch.float32, device=dev)
+    depth = torch.empty((B, res, res), dtype=torch.float32, device=dev)
+    wsum = torch.empty_like(depth)
+    mm = torch.empty(2, dtype=torch.float32, device=dev)
+    w1, b1, w2, b2 = _f32c(w1), _f32c(b1), _f32c(w2), _f32c(b2)
+    p = _C.RenderParams(_p(planes_nhwc), PC, B, PH, PW, _p(cam), (cam.stride(0) if cam is not None else 0), _p(rays_o), _p(rays_d), res, Dc, Df, _p(jitter), _p(u),
+                        float(box_warp), 1 if white_back else 0, _p(near_far), _p(w1), _p(b1), _p(w2), _p(b2),
+                        _p(feat), _p(depth), _p(wsum), _p(mm))
+    _C.check(_C.lib().ia_render(C.byref(p), st), 'ia_render')
+    _C.check(_C.lib().ia_depth_clamp(_p(depth), depth.numel(), _p(mm), st), 'ia_depth_clamp')
+    return feat, depth, wsum

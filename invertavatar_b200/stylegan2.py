@@ -1,0 +1,443 @@
+"""StyleGAN2 generator blocks of the Next3D++ generator on the B200 engine.
+
+Same classes, constructor arguments, parameter/buffer names and forward signatures as the reference
+(training_avatar_texture/networks_stylegan2_new.py: FullyConnectedLayer :96, MappingNetwork :193, SynthesisLayer :276,
+ToRGBLayer :340, SynthesisBlock :365, SynthesisNetwork :475, Generator :559; training/networks_stylegan2.py is the same
+arithmetic without the cond/feat hooks), so ``copy_params_and_buffers(require_all=True)`` works in both directions and
+parameters drawn under ``torch.manual_seed`` match the reference's.
+
+Underneath, nothing is shared with the reference: a layer is (styles + demod coefficients) -> (modulate + bf16 hi/lo
+split) -> tcgen05 implicit-GEMM convolution with a fused demod/noise/bias/lrelu/clamp epilogue -- the reference's own
+``fused_modconv=False`` formulation (networks_stylegan2_new.py:70-79), so the batch folds into GEMM-M.  Activations
+stay channels-last between layers; tensors handed to the caller are logical NCHW views of those buffers.
+Forward only (the inference scripts run under no_grad / requires_grad_(False))."""
+import math
+
+import numpy as np
+import torch
+
+from . import persistence
+from . import runtime as rt
+
+SQRT2 = math.sqrt(2.0)
+
+
+def setup_filter(f, device=torch.device('cpu'), normalize=True, flip_filter=False, gain=1, separable=None):
+    """FIR filter setup, reference torch_utils/ops/upfirdn2d.py:72-116."""
+    if f is None:
+        f = 1
+    f = torch.as_tensor(f, dtype=torch.float32)
+    assert f.ndim in [0, 1, 2] and f.numel() > 0
+    if f.ndim == 0:
+        f = f[np.newaxis]
+    if separable is None:
+        separable = (f.ndim == 1 and f.numel() >= 8)
+    if f.ndim == 1 and not separable:
+        f = f.ger(f)
+    assert f.ndim == (1 if separable else 2)
+    if normalize:
+        f = f / f.sum()
+    if flip_filter:
+        f = f.flip(list(range(f.ndim)))
+    f = f * (gain ** (f.ndim / 2))
+    return f.to(device=device)
+
+
+def _is_1331(f):
+    """True when the resample filter is the stock outer([1,3,3,1])/64 the fused kernels assume."""
+    if f is None or f.ndim != 2 or tuple(f.shape) != (4, 4):
+        return False
+    k = torch.tensor([1.0, 3.0, 3.0, 1.0])
+    ref = torch.outer(k, k) / 64.0
+    return bool(torch.allclose(f.detach().float().cpu(), ref, atol=1e-7))
+
+
+@persistence.persistent_class
+class FullyConnectedLayer(torch.nn.Module):
+    def __init__(self, in_features, out_features, bias=True, activation='linear', lr_multiplier=1, bias_init=0):
+        super().__init__()
+        self.in_features = in_features
+        self.out_features = out_features
+        self.activation = activation
+        self.weight = torch.nn.Parameter(torch.randn([out_features, in_features]) / lr_multiplier)
+        self.bias = torch.nn.Parameter(torch.full([out_features], np.float32(bias_init))) if bias else None
+        self.weight_gain = lr_multiplier / np.sqrt(in_features)
+        self.bias_gain = lr_multiplier
+
+    def forward(self, x):
+        return rt.fully_connected(x, self.weight, self.bias, w_gain=self.weight_gain, b_gain=self.bias_gain,
+                                  act=self.activation)
+
+    def extra_repr(self):
+        return f'in_features={self.in_features:d}, out_features={self.out_features:d}, activation={self.activation:s}'
+
+
+@persistence.persistent_class
+class MappingNetwork(torch.nn.Module):
+    def __init__(self, z_dim, c_dim, w_dim, num_ws, num_layers=8, embed_features=None, layer_features=None,
+                 activation='lrelu', lr_multiplier=0.01, w_avg_beta=0.998):
+        super().__init__()
+        self.z_dim, self.c_dim, self.w_dim, self.num_ws = z_dim, c_dim, w_dim, num_ws
+        self.num_layers = num_layers
+        self.w_avg_beta = w_avg_beta
+        if embed_features is None:
+            embed_features = w_dim
+        if c_dim == 0:
+            embed_features = 0
+        if layer_features is None:
+            layer_features = w_dim
+        features = [z_dim + embed_features] + [layer_features] * (num_layers - 1) + [w_dim]
+        if c_dim > 0:
+            self.embed = FullyConnectedLayer(c_dim, embed_features)
+        for idx in range(num_layers):
+            setattr(self, f'fc{idx}', FullyConnectedLayer(features[idx], features[idx + 1], activation=activation,
+                                                          lr_multiplier=lr_multiplier))
+        if num_ws is not None and w_avg_beta is not None:
+            self.register_buffer('w_avg', torch.zeros([w_dim]))
+
+    def forward(self, z, c, truncation_psi=1, truncation_cutoff=None, update_emas=False):
+        x = None
+        if self.z_dim > 0:
+            assert z.shape[1] == self.z_dim
+            x = rt.normalize_2nd_moment(z.to(torch.float32))
+        if self.c_dim > 0:
+            assert c.shape[1] == self.c_dim
+            y = rt.normalize_2nd_moment(self.embed(c.to(torch.float32)))
+            x = torch.cat([x, y], dim=1) if x is not None else y
+        for idx in range(self.num_layers):
+            x = getattr(self, f'fc{idx}')(x)
+        if update_emas and self.w_avg_beta is not None:
+            self.w_avg.copy_(x.detach().mean(dim=0).lerp(self.w_avg, self.w_avg_beta))
+        if self.num_ws is None:
+            if truncation_psi != 1:
+                x = self.w_avg.lerp(x, truncation_psi)
+            return x
+        if truncation_psi != 1:
+            assert self.w_avg_beta is not None
+        return rt.broadcast_truncate(x, getattr(self, 'w_avg', None), self.num_ws, psi=truncation_psi,
+                                     cutoff=truncation_cutoff)
+
+    def extra_repr(self):
+        return f'z_dim={self.z_dim:d}, c_dim={self.c_dim:d}, w_dim={self.w_dim:d}, num_ws={self.num_ws:d}'
+
+
+def _noise_for(layer, noise_mode, batch, device):
+    """Per-layer noise image(s): 'const' -> the registered buffer [R,R]; 'random' -> fresh N(0,1) [B,R,R]
+    (networks_stylegan2_new.py:317-321).  The multiplication by noise_strength happens inside the epilogue."""
+    if not layer.use_noise or noise_mode == 'none':
+        return None
+    if noise_mode == 'const':
+        return layer.noise_const
+    return torch.randn([batch, layer.resolution, layer.resolution], device=device)
+
+
+@persistence.persistent_class
+class SynthesisLayer(torch.nn.Module):
+    def __init__(self, in_channels, out_channels, w_dim, resolution, kernel_size=3, up=1, use_noise=True,
+                 activation='lrelu', resample_filter=[1, 3, 3, 1], conv_clamp=None, channels_last=False):
+        super().__init__()
+        self.in_channels, self.out_channels, self.w_dim = in_channels, out_channels, w_dim
+        self.resolution, self.up, self.use_noise = resolution, up, use_noise
+        self.activation, self.conv_clamp = activation, conv_clamp
+        self.register_buffer('resample_filter', setup_filter(resample_filter))
+        self.padding = kernel_size // 2
+        self.act_gain = rt.ACT_DEFAULTS[activation][1]
+        self.affine = FullyConnectedLayer(w_dim, in_channels, bias_init=1)
+        self.weight = torch.nn.Parameter(torch.randn([out_channels, in_channels, kernel_size, kernel_size]))
+        if use_noise:
+            self.register_buffer('noise_const', torch.randn([resolution, resolution]))
+            self.noise_strength = torch.nn.Parameter(torch.zeros([]))
+        self.bias = torch.nn.Parameter(torch.zeros([out_channels]))
+
+    # ---- engine-facing pieces ----
+    def pack(self):
+        return rt.ConvPack.current(self, '_ia_pack', self.weight, need_wsq=True)
+
+    def style_entry(self, w_index):
+        p = self.pack()
+        return dict(affine_w=self.affine.weight, affine_b=self.affine.bias, wsq=p.wsq, Cin=self.in_channels,
+                    Cout=self.out_channels, w_index=w_index, style_gain=1.0)
+
+    def run_nhwc(self, x, styles, dcoef, noise_mode='const', gain=1, cond=None, cond_alpha=None):
+        """x [B,H,W,Cin] fp32 NHWC -> [B,R,R,Cout] fp32 NHWC."""
+        assert self.up in (1, 2), 'only up=1 and up=2 synthesis layers exist on the hot path'
+        if self.up == 2 and not _layer_filter_ok(self):
+            raise RuntimeError('SynthesisLayer: the fused up=2 path assumes the [1,3,3,1] resample filter')
+        B, H, W, Cin = x.shape
+        assert Cin == self.in_channels and H * self.up == self.resolution, (x.shape, self.in_channels, self.resolution)
+        pack = self.pack()
+        hi, lo = rt.modsplit(x, styles, cond=cond, cond_alpha=cond_alpha, C_pad=pack.Cin_pad)
+        noise = _noise_for(self, noise_mode, B, x.device)
+        strength = self.noise_strength if noise is not None else None
+        act_gain = self.act_gain * gain
+        act_clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
+        R = self.resolution
+        out = torch.empty((B, R, R, self.out_channels), dtype=torch.float32, device=x.device)
+        if self.up == 1:
+            rt.conv_same(hi, lo, pack, pack.Cin_pad, out, dcoef=dcoef, noise=noise, noise_strength=strength, bias=self.bias,
+                         act=self.activation, gain=act_gain, clamp=act_clamp, mode=1)
+        else:
+            raw = torch.empty((B, 2 * H + 1, 2 * W + 1, self.out_channels), dtype=torch.float32, device=x.device)
+            rt.conv_transpose_up2_raw(hi, lo, pack, pack.Cin_pad, raw)
+            rt.fir_epilogue(raw, rt.fir4x4_gain4(x.device), out, dcoef, noise, strength, self.bias, self.activation,
+                            act_gain, act_clamp)
+        return out
+
+    def forward(self, x, w, noise_mode='random', fused_modconv=True, gain=1):
+        assert noise_mode in ['random', 'const', 'none']
+        plan = _plan_for(self, [self.style_entry(0)])
+        styles, dcoefs = plan.run(w.reshape(w.shape[0], 1, -1))
+        y = self.run_nhwc(rt.to_nhwc(x), styles[0], dcoefs[0], noise_mode=noise_mode, gain=gain)
+        return rt.from_nhwc(y)
+
+    def extra_repr(self):
+        return ' '.join([f'in_channels={self.in_channels:d}, out_channels={self.out_channels:d}, w_dim={self.w_dim:d},',
+                         f'resolution={self.resolution:d}, up={self.up}, activation={self.activation:s}'])
+
+
+def _layer_filter_ok(layer):
+    ok = layer.__dict__.get('_ia_filter_ok')
+    if ok is None:
+        ok = _is_1331(layer.resample_filter)
+        layer.__dict__['_ia_filter_ok'] = ok
+    return ok
+
+
+def _plan_for(owner, entries):
+    """StylePlan cached on ``owner``; rebuilt when any referenced tensor moved (new storage / device)."""
+    key = tuple((e['affine_w'].data_ptr(), e['affine_b'].data_ptr(), 0 if e['wsq'] is None else e['wsq'].data_ptr(),
+                 e['w_index']) for e in entries)
+    cached = owner.__dict__.get('_ia_plan')
+    if cached is None or cached[0] != key:
+        cached = (key, rt.StylePlan(entries, entries[0]['affine_w'].device))
+        owner.__dict__['_ia_plan'] = cached
+    return cached[1]
+
+
+@persistence.persistent_class
+class ToRGBLayer(torch.nn.Module):
+    def __init__(self, in_channels, out_channels, w_dim, kernel_size=1, conv_clamp=None, channels_last=False):
+        super().__init__()
+        self.in_channels, self.out_channels, self.w_dim = in_channels, out_channels, w_dim
+        self.conv_clamp = conv_clamp
+        self.affine = FullyConnectedLayer(w_dim, in_channels, bias_init=1)
+        self.weight = torch.nn.Parameter(torch.randn([out_channels, in_channels, kernel_size, kernel_size]))
+        self.bias = torch.nn.Parameter(torch.zeros([out_channels]))
+        self.weight_gain = 1 / np.sqrt(in_channels * (kernel_size ** 2))
+
+    def pack(self):
+        return rt.ConvPack.current(self, '_ia_pack', self.weight, need_wsq=False)
+
+    def style_entry(self, w_index):
+        return dict(affine_w=self.affine.weight, affine_b=self.affine.bias, wsq=None, Cin=self.in_channels,
+                    Cout=self.out_channels, w_index=w_index, style_gain=float(self.weight_gain))
+
+    def run_nhwc(self, x, styles, img_prev=None, out_nchw=False):
+        """x [B,H,W,Cin] -> img = upsample2d(img_prev) + clamp(modconv1x1(x) + bias)  as NHWC (or planar NCHW)."""
+        B, H, W, _ = x.shape
+        pack = self.pack()
+        hi, lo = rt.modsplit(x, styles, C_pad=pack.Cin_pad)
+        raw = torch.empty((B, H, W, self.out_channels), dtype=torch.float32, device=x.device)
+        rt.conv_same(hi, lo, pack, pack.Cin_pad, raw, mode=0)
+        return rt.torgb_finish(raw, self.bias, self.conv_clamp, img_prev, out_nchw=out_nchw)
+
+    def forward(self, x, w, fused_modconv=True):
+        plan = _plan_for(self, [self.style_entry(0)])
+        styles, _ = plan.run(w.reshape(w.shape[0], 1, -1))
+        return rt.from_nhwc(self.run_nhwc(rt.to_nhwc(x), styles[0]))
+
+    def extra_repr(self):
+        return f'in_channels={self.in_channels:d}, out_channels={self.out_channels:d}, w_dim={self.w_dim:d}'
+
+
+@persistence.persistent_class
+class SynthesisBlock(torch.nn.Module):
+    def __init__(self, in_channels, out_channels, w_dim, resolution, img_channels, is_last, architecture='skip',
+                 resample_filter=[1, 3, 3, 1], conv_clamp=256, use_fp16=False, fp16_channels_last=False,
+                 fused_modconv_default=True, **layer_kwargs):
+        assert architecture in ['orig', 'skip', 'resnet']
+        super().__init__()
+        if architecture == 'resnet':
+            raise NotImplementedError('resnet synthesis blocks are not on the generator hot path (skip architecture only)')
+        self.in_channels, self.w_dim, self.resolution = in_channels, w_dim, resolution
+        self.img_channels, self.is_last, self.architecture = img_channels, is_last, architecture
+        self.use_fp16 = use_fp16
+        self.channels_last = (use_fp16 and fp16_channels_last)
+        self.fused_modconv_default = fused_modconv_default
+        self.register_buffer('resample_filter', setup_filter(resample_filter))
+        self.num_conv = 0
+        self.num_torgb = 0
+        if in_channels == 0:
+            self.const = torch.nn.Parameter(torch.randn([out_channels, resolution, resolution]))
+        if in_channels != 0:
+            self.conv0 = SynthesisLayer(in_channels, out_channels, w_dim=w_dim, resolution=resolution, up=2,
+                                        resample_filter=resample_filter, conv_clamp=conv_clamp,
+                                        channels_last=self.channels_last, **layer_kwargs)
+            self.num_conv += 1
+        self.conv1 = SynthesisLayer(out_channels, out_channels, w_dim=w_dim, resolution=resolution, conv_clamp=conv_clamp,
+                                    channels_last=self.channels_last, **layer_kwargs)
+        self.num_conv += 1
+        if is_last or architecture == 'skip':
+            self.torgb = ToRGBLayer(out_channels, img_channels, w_dim=w_dim, conv_clamp=conv_clamp,
+                                    channels_last=self.channels_last)
+            self.num_torgb += 1
+
+    def _plan(self):
+        entries = []
+        if self.in_channels != 0:
+            entries.append(self.conv0.style_entry(len(entries)))
+        entries.append(self.conv1.style_entry(len(entries)))
+        if hasattr(self, 'torgb'):
+            entries.append(self.torgb.style_entry(len(entries)))
+        return _plan_for(self, entries)
+
+    def run_nhwc(self, x, img, ws, condition=None, noise_mode='random', cond=None, cond_alpha=None, img_nchw=False,
+                 gain=1):
+        """Channels-last block: x [B,H/2,W/2,Cin] or None, img [B,H/2,W/2,Cimg] or None, ws [B,n,w_dim].
+        ``cond``/``cond_alpha`` blend the incoming x (face-backbone cond_list) inside the operand preparation."""
+        if self.is_last is False and self.architecture == 'orig':
+            pass
+        styles, dcoefs = self._plan().run(ws)
+        i = 0
+        if self.in_channels == 0:
+            B = ws.shape[0]
+            x = self.const.detach().permute(1, 2, 0).unsqueeze(0).expand(B, -1, -1, -1).contiguous()
+            x = self.conv1.run_nhwc(x, styles[i], dcoefs[i], noise_mode=noise_mode, gain=gain)
+            i += 1
+        else:
+            x = self.conv0.run_nhwc(x, styles[i], dcoefs[i], noise_mode=noise_mode, gain=gain, cond=cond, cond_alpha=cond_alpha)
+            i += 1
+            if condition is not None:
+                # CS-SFT (networks_stylegan2_new.py:448-452): second half of the channels <- x*scale + shift.
+                # Runs once per identity (AR_eval_forward), so plain tensor algebra on the NCHW view is fine here.
+                xv = rt.from_nhwc(x)
+                half = xv.shape[1] // 2
+                xv = torch.cat([xv[:, :half], xv[:, half:] * condition[0] + condition[1]], dim=1)
+                x = rt.to_nhwc(xv)
+            x = self.conv1.run_nhwc(x, styles[i], dcoefs[i], noise_mode=noise_mode, gain=gain)
+            i += 1
+        if hasattr(self, 'torgb'):
+            img = self.torgb.run_nhwc(x, styles[i], img_prev=img, out_nchw=img_nchw)
+        elif img is not None:
+            img = rt.to_nhwc(rt.upfirdn2d(rt.from_nhwc(img), self.resample_filter, up=(2, 2), padding=(2, 1, 2, 1), gain=4.0))
+        return x, img
+
+    def forward(self, x, img, ws, condition=None, force_fp32=False, fused_modconv=None, update_emas=False, **layer_kwargs):
+        assert ws.shape[1] == self.num_conv + self.num_torgb and ws.shape[2] == self.w_dim
+        noise_mode = layer_kwargs.get('noise_mode', 'random')
+        if self.in_channels != 0:
+            assert tuple(x.shape[1:]) == (self.in_channels, self.resolution // 2, self.resolution // 2)
+            x = rt.to_nhwc(x)
+        if img is not None:
+            assert tuple(img.shape[1:]) == (self.img_channels, self.resolution // 2, self.resolution // 2)
+            img = rt.to_nhwc(img)
+        x, img = self.run_nhwc(x, img, ws, condition=condition, noise_mode=noise_mode, gain=layer_kwargs.get('gain', 1))
+        return rt.from_nhwc(x), (rt.from_nhwc(img) if img is not None else None)
+
+    def extra_repr(self):
+        return f'resolution={self.resolution:d}, architecture={self.architecture:s}'
+
+
+@persistence.persistent_class
+class SynthesisNetwork(torch.nn.Module):
+    def __init__(self, w_dim, img_resolution, img_channels, channel_base=32768, channel_max=512, num_fp16_res=4,
+                 **block_kwargs):
+        assert img_resolution >= 4 and img_resolution & (img_resolution - 1) == 0
+        super().__init__()
+        self.w_dim = w_dim
+        self.img_resolution = img_resolution
+        self.img_resolution_log2 = int(np.log2(img_resolution))
+        self.img_channels = img_channels
+        self.num_fp16_res = num_fp16_res
+        self.block_resolutions = [2 ** i for i in range(2, self.img_resolution_log2 + 1)]
+        channels_dict = {res: min(channel_base // res, channel_max) for res in self.block_resolutions}
+        fp16_resolution = max(2 ** (self.img_resolution_log2 + 1 - num_fp16_res), 8)
+        self.num_ws = 0
+        for res in self.block_resolutions:
+            in_channels = channels_dict[res // 2] if res > 4 else 0
+            out_channels = channels_dict[res]
+            use_fp16 = (res >= fp16_resolution)
+            is_last = (res == self.img_resolution)
+            block = SynthesisBlock(in_channels, out_channels, w_dim=w_dim, resolution=res, img_channels=img_channels,
+                                   is_last=is_last, use_fp16=use_fp16, **block_kwargs)
+            self.num_ws += block.num_conv
+            if is_last:
+                self.num_ws += block.num_torgb
+            setattr(self, f'b{res}', block)
+
+    def forward(self, ws, cond_list=None, return_list=False, feat_conditions=None, return_imgs=False, out_res=(32, 256),
+                **block_kwargs):
+        """cond_list / return_list / feat_conditions semantics of networks_stylegan2_new.py:509-548.  (The stock
+        training/networks_stylegan2.SynthesisNetwork.forward(ws, **kw) is the cond_list=None, return_list=False case.)"""
+        assert not (return_list and return_imgs)
+        assert ws.shape[1] == self.num_ws and ws.shape[2] == self.w_dim, (ws.shape, self.num_ws)
+        noise_mode = block_kwargs.get('noise_mode', 'random')
+        ws = ws.to(torch.float32)
+        x = img = None
+        x_list, out_imgs = [], []
+        start_layer = int(np.log2(out_res[0])) - 2
+        end_layer = (self.img_resolution_log2 - 2) if len(out_res) == 1 else (int(np.log2(out_res[1])) - 2)
+        pending_cond = None     # (cond_nhwc, alpha[B,H,W]) to blend into x inside the next block's operand preparation
+        w_idx = 0
+        for index, res in enumerate(self.block_resolutions):
+            block = getattr(self, f'b{res}')
+            cur_ws = ws.narrow(1, w_idx, block.num_conv + block.num_torgb)
+            w_idx += block.num_conv
+            cond_feat = feat_conditions[res] if (feat_conditions is not None and res in feat_conditions.keys()) else None
+            cnd, cal = pending_cond if pending_cond is not None else (None, None)
+            pending_cond = None
+            x, img = block.run_nhwc(x, img, cur_ws, condition=cond_feat, noise_mode=noise_mode, cond=cnd, cond_alpha=cal)
+            if index >= start_layer:
+                if return_list:
+                    if index == start_layer:
+                        x_list.append(rt.from_nhwc(img))
+                    x_list.append(rt.from_nhwc(x))
+                if return_imgs:
+                    if index == start_layer:
+                        out_imgs.append(rt.from_nhwc(x))
+                    out_imgs.append(rt.from_nhwc(img))
+                if cond_list is not None:
+                    if index == start_layer:
+                        c_img, c_a = _split_cond(cond_list[0])
+                        img = rt.lerp_alpha(c_img, img, c_a)
+                    if index < end_layer:
+                        pending_cond = _split_cond(cond_list[1 + index - start_layer])
+        if return_list:
+            x_list.append(rt.from_nhwc(img))
+            return x_list
+        if return_imgs:
+            return out_imgs
+        return rt.from_nhwc(img)
+
+    def extra_repr(self):
+        return ' '.join([f'w_dim={self.w_dim:d}, num_ws={self.num_ws:d},',
+                         f'img_resolution={self.img_resolution:d}, img_channels={self.img_channels:d},',
+                         f'num_fp16_res={self.num_fp16_res:d}'])
+
+
+def _split_cond(c):
+    """A cond_list entry is either the engine's (features NHWC [B,H,W,C], alpha [B,H,W]) pair or the reference's
+    [B,C+1,H,W] tensor whose last channel is the blend alpha (triplane_v20.py:335-337)."""
+    if isinstance(c, (tuple, list)):
+        return c[0], c[1]
+    cn = rt.to_nhwc(c)
+    return cn[..., :-1], cn[..., -1].contiguous()
+
+
+@persistence.persistent_class
+class Generator(torch.nn.Module):
+    def __init__(self, z_dim, c_dim, w_dim, img_resolution, img_channels, mapping_ws=-1, mapping_kwargs={},
+                 **synthesis_kwargs):
+        super().__init__()
+        self.z_dim, self.c_dim, self.w_dim = z_dim, c_dim, w_dim
+        self.img_resolution, self.img_channels = img_resolution, img_channels
+        self.synthesis = SynthesisNetwork(w_dim=w_dim, img_resolution=img_resolution, img_channels=img_channels,
+                                          **synthesis_kwargs)
+        self.num_ws = self.synthesis.num_ws
+        if mapping_ws == -1:
+            mapping_ws = self.num_ws
+        self.mapping = MappingNetwork(z_dim=z_dim, c_dim=c_dim, w_dim=w_dim, num_ws=mapping_ws, **mapping_kwargs)
+
+    def forward(self, z, c, truncation_psi=1, truncation_cutoff=None, update_emas=False, **synthesis_kwargs):
+        ws = self.mapping(z, c, truncation_psi=truncation_psi, truncation_cutoff=truncation_cutoff, update_emas=update_emas)
+        return self.synthesis(ws, update_emas=update_emas, **synthesis_kwargs)

@@ -1,0 +1,176 @@
+"""Synthetic, seeded inputs for the generator-forward hot path.
+
+These are the inputs SURVEY.md section 8(d) specifies: latents from
+``RandomState(i)`` (same rule as reference ``reenact_avatar_next3d.py:172``),
+look-at cameras at a fixed radius (reference
+``training_avatar_texture/camera_utils.py:58-87,105-148``), a UV mesh condition
+with a mouth hole (so ``fill_mouth`` has something to fill), and the explicit
+depth-jitter tensor that replaces ``torch.rand_like`` (reference
+``volumetric_rendering/renderer.py:406``).
+
+Everything here is plain CPU torch/numpy; tests, bench.py and the golden
+generator all draw their inputs from this one place.
+"""
+import math
+
+import numpy as np
+import torch
+
+FOV_DEG = 18.837
+CAM_RADIUS = 2.7
+CAM_PIVOT = (0.0, 0.0, 0.2)
+
+
+def rendering_kwargs(depth_resolution=48, depth_resolution_importance=48):
+    """The ``rendering_kwargs`` dict that travels inside reference pickles
+    (``train_avatar_texture.py:320-348``)."""
+    return {
+        'image_resolution': 512,
+        'disparity_space_sampling': False,
+        'clamp_mode': 'softplus',
+        'superresolution_module': 'training_avatar_texture.superresolution.SuperresolutionHybrid8XDC',
+        'c_gen_conditioning_zero': False,
+        'gpc_reg_prob': None,
+        'c_scale': 1,
+        'superresolution_noise_mode': 'none',
+        'density_reg': 0.25,
+        'density_reg_p_dist': 0.004,
+        'reg_type': 'l1',
+        'decoder_lr_mul': 1,
+        'sr_antialias': True,
+        'depth_resolution': depth_resolution,
+        'depth_resolution_importance': depth_resolution_importance,
+        'ray_start': 2.25,
+        'ray_end': 3.3,
+        'box_warp': 1,
+        'avg_camera_radius': CAM_RADIUS,
+        'avg_camera_pivot': list(CAM_PIVOT),
+    }
+
+
+def generator_kwargs(depth_resolution=48, depth_resolution_importance=48):
+    """Constructor kwargs of the Next3D++ generator at the ``train_avatar_texture.py``
+    defaults (``:256,274-276,304,355,365-367,392-393``)."""
+    return dict(
+        z_dim=512, c_dim=25, w_dim=512, img_resolution=512, img_channels=3,
+        sr_num_fp16_res=4,
+        mapping_kwargs={'num_layers': 2},
+        rendering_kwargs=rendering_kwargs(depth_resolution, depth_resolution_importance),
+        sr_kwargs={'channel_base': 32768, 'channel_max': 512, 'fused_modconv_default': 'inference_only'},
+        channel_base=32768, channel_max=512, fused_modconv_default='inference_only',
+        num_fp16_res=0, conv_clamp=None,
+    )
+
+
+def _normalize(v):
+    return v / torch.linalg.norm(v, dim=-1, keepdim=True)
+
+
+def lookat_cam2world(h, v, pivot=CAM_PIVOT, radius=CAM_RADIUS):
+    """Look-at pose, y-up, no roll (semantics of ``LookAtPoseSampler.sample`` +
+    ``create_cam2world_matrix``, ``camera_utils.py:58-87,119-137``)."""
+    h = torch.as_tensor(h, dtype=torch.float32).reshape(-1, 1)
+    v = torch.as_tensor(v, dtype=torch.float32).reshape(-1, 1)
+    v = torch.clamp(v, 1e-5, math.pi - 1e-5)
+    phi = torch.arccos(1 - 2 * (v / math.pi))
+    origin = torch.zeros(h.shape[0], 3)
+    origin[:, 0:1] = radius * torch.sin(phi) * torch.cos(math.pi - h)
+    origin[:, 2:3] = radius * torch.sin(phi) * torch.sin(math.pi - h)
+    origin[:, 1:2] = radius * torch.cos(phi)
+    fwd = _normalize(torch.tensor(pivot, dtype=torch.float32) - origin)
+    up = torch.tensor([0.0, 1.0, 0.0]).expand_as(fwd)
+    right = -_normalize(torch.cross(up, fwd, dim=-1))
+    up = _normalize(torch.cross(fwd, right, dim=-1))
+    rot = torch.eye(4).repeat(h.shape[0], 1, 1)
+    rot[:, :3, :3] = torch.stack((right, up, fwd), dim=-1)
+    trans = torch.eye(4).repeat(h.shape[0], 1, 1)
+    trans[:, :3, 3] = origin
+    return trans @ rot
+
+
+def fov_to_intrinsics(fov_degrees=FOV_DEG):
+    """Normalised pinhole intrinsics (``camera_utils.py:140-148``; note the
+    reference's 3.14159 / 1.414 constants)."""
+    focal = float(1 / (math.tan(fov_degrees * 3.14159 / 360) * 1.414))
+    return torch.tensor([[focal, 0, 0.5], [0, focal, 0.5], [0, 0, 1]], dtype=torch.float32)
+
+
+def cameras(batch, first=0):
+    """[B,25] labels: c2w(16) | K(9). yaw,pitch ~ U(-0.4,0.4),U(-0.2,0.2) from RandomState(1000+i)."""
+    hs, vs = [], []
+    for i in range(first, first + batch):
+        rs = np.random.RandomState(1000 + i)
+        hs.append(math.pi / 2 + rs.uniform(-0.4, 0.4))
+        vs.append(math.pi / 2 + rs.uniform(-0.2, 0.2))
+    c2w = lookat_cam2world(hs, vs)
+    K = fov_to_intrinsics().reshape(1, 9).repeat(batch, 1)
+    return torch.cat([c2w.reshape(batch, 16), K], dim=1)
+
+
+def frontal_camera(batch=1):
+    c2w = lookat_cam2world([math.pi / 2] * batch, [math.pi / 2] * batch)
+    K = fov_to_intrinsics().reshape(1, 9).repeat(batch, 1)
+    return torch.cat([c2w.reshape(batch, 16), K], dim=1)
+
+
+def latents(batch, first=0, z_dim=512):
+    return torch.from_numpy(np.concatenate(
+        [np.random.RandomState(i).randn(1, z_dim) for i in range(first, first + batch)])).float()
+
+
+def uvcoords_image(batch, first=0, res=256):
+    """[B,res,res,3]: (u,v) in [-1,1] = smooth warp of a normalised grid; mask = face
+    ellipse minus an enclosed mouth ellipse, binarised at 0.5
+    (``reenact_avatar_next3d.py:79``)."""
+    out = []
+    lin = (torch.arange(res, dtype=torch.float32) + 0.5) / res * 2 - 1
+    yy, xx = torch.meshgrid(lin, lin, indexing='ij')
+    for i in range(first, first + batch):
+        rs = np.random.RandomState(2000 + i)
+        ph = rs.uniform(0, 2 * math.pi, size=4).astype(np.float32)
+        u = xx + 0.1 * torch.sin(3.0 * yy + float(ph[0])) * torch.cos(2.0 * xx + float(ph[1]))
+        v = yy + 0.1 * torch.sin(2.5 * xx + float(ph[2])) * torch.cos(3.5 * yy + float(ph[3]))
+        face = ((xx / 0.55) ** 2 + (yy / 0.7) ** 2) < 1
+        mx, my = float(rs.uniform(-0.03, 0.03)), 0.3 + float(rs.uniform(-0.03, 0.03))
+        mouth = (((xx - mx) / 0.12) ** 2 + ((yy - my) / 0.05) ** 2) < 1
+        mask = (face & ~mouth).float()
+        out.append(torch.stack([u.clamp(-1, 1), v.clamp(-1, 1), mask], dim=-1))
+    return torch.stack(out)
+
+
+def depth_jitter(batch, rays, depth_resolution, seed=7):
+    """U[0,1) tensor [B,rays,D,1] that both the oracle and the CUDA renderer consume in
+    place of ``torch.rand_like`` (``renderer.py:406``). One generator per sample so the
+    values of sample i do not depend on the batch size (shard invariance)."""
+    out = []
+    for i in range(batch):
+        g = torch.Generator(device='cpu').manual_seed(seed * 100003 + i)
+        out.append(torch.rand(rays, depth_resolution, 1, generator=g))
+    return torch.stack(out)
+
+
+def importance_u(batch, rays, n_importance, seed=11):
+    """U[0,1) tensor [B*rays, n_importance] replacing ``torch.rand`` when evaluation=False
+    (``renderer.py:453``)."""
+    out = []
+    for i in range(batch):
+        g = torch.Generator(device='cpu').manual_seed(seed * 100003 + i)
+        out.append(torch.rand(rays, n_importance, generator=g))
+    return torch.cat(out)
+
+
+def randomize_noise_and_wavg(module_or_sd, seed=123):
+    """Random init leaves noise_strength=0 and w_avg=0; give them values so the noise and
+    truncation paths are exercised. Accepts a module or a state-dict."""
+    g = torch.Generator(device='cpu').manual_seed(seed)
+    sd = module_or_sd if isinstance(module_or_sd, dict) else module_or_sd.state_dict()
+    with torch.no_grad():
+        for k in sorted(sd.keys()):
+            v = sd[k]
+            if k.endswith('noise_strength'):
+                v.copy_((torch.rand([], generator=g) * 0.1).to(v.device))
+            elif k.endswith('w_avg'):
+                v.copy_(torch.randn(v.shape, generator=g).to(v.device))
+            elif k.endswith('.bias') and ('conv' in k or 'torgb' in k) and 'affine' not in k:
+                v.copy_((torch.randn(v.shape, generator=g) * 0.1).to(v.device))
+    return module_or_sd

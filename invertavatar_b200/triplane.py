@@ -1,0 +1,238 @@
+"""Next3D++ tri-plane generator on the B200 engine (reference training_avatar_texture/triplane_v20.py).
+
+Same constructor, attributes, methods, return dictionaries and state-dict (444 tensors) as the reference
+``TriPlaneGenerator``; every stage underneath is a kernel of libinvertavatar_b200.so (see DESIGN.md for the stage map).
+"""
+import importlib
+
+import torch
+
+from . import persistence
+from . import runtime as rt
+from . import stylegan2 as sg
+from . import superresolution as sr_mod
+from .rendering import ImportanceRenderer_bsMotion, RaySampler_zxc
+from .stylegan2 import FullyConnectedLayer
+from .stylegan2 import Generator as StyleGAN2Backbone_cond
+
+BBOX_256 = [57, 185, 64, 192]   # face region of the frontal plane, triplane_v20.py:114
+
+_KNOWN_SR = {
+    'training_avatar_texture.superresolution.SuperresolutionHybrid8XDC': sr_mod.SuperresolutionHybrid8XDC,
+    'training_avatar_texture.superresolution.SuperresolutionHybrid8X': sr_mod.SuperresolutionHybrid8X,
+}
+
+
+def _construct(class_name, **kwargs):
+    """dnnlib.util.construct_class_by_name for the super-resolution module (triplane_v20.py:56-58)."""
+    cls = _KNOWN_SR.get(class_name)
+    if cls is None:
+        mod, name = class_name.rsplit('.', 1)
+        cls = getattr(importlib.import_module(mod), name)
+    return cls(**kwargs)
+
+
+class OSGDecoder(torch.nn.Module):
+    """triplane_v20.py:415-438.  The forward used by the generator is fused into the render kernel; the module holds the
+    parameters (decoder.net.{0,2}.{weight,bias}) and offers the standalone forward for API parity."""
+
+    def __init__(self, n_features, options):
+        super().__init__()
+        self.hidden_dim = 64
+        self.net = torch.nn.Sequential(
+            FullyConnectedLayer(n_features, self.hidden_dim, lr_multiplier=options['decoder_lr_mul']),
+            torch.nn.Softplus(),
+            FullyConnectedLayer(self.hidden_dim, 1 + options['decoder_output_dim'], lr_multiplier=options['decoder_lr_mul']))
+
+    def forward(self, sampled_features, ray_directions, sampled_embeddings=None):
+        x = sampled_features.mean(1)
+        N, M, Cc = x.shape
+        x = self.net[0](x.reshape(N * M, Cc))
+        x = rt.bias_act(x, act='softplus')
+        x = self.net[2](x).reshape(N, M, -1)
+        rgb = rt.bias_act(x[..., 1:].contiguous(), act='sigmoid') * (1 + 2 * 0.001) - 0.001
+        return {'rgb': rgb, 'sigma': x[..., 0:1]}
+
+
+@persistence.persistent_class
+class TriPlaneGenerator(torch.nn.Module):
+    def __init__(self, z_dim, c_dim, w_dim, img_resolution, img_channels, topology_path=None, sr_num_fp16_res=0,
+                 mapping_kwargs={}, rendering_kwargs={}, sr_kwargs={}, **synthesis_kwargs):
+        super().__init__()
+        self.z_dim, self.c_dim, self.w_dim = z_dim, c_dim, w_dim
+        self.img_resolution, self.img_channels = img_resolution, img_channels
+        self.renderer = ImportanceRenderer_bsMotion()
+        self.ray_sampler = RaySampler_zxc()
+        self.texture_backbone = StyleGAN2Backbone_cond(z_dim, c_dim, w_dim, img_resolution=256, img_channels=32,
+                                                       mapping_kwargs=mapping_kwargs, **synthesis_kwargs)
+        self.face_backbone = StyleGAN2Backbone_cond(z_dim, c_dim, w_dim, img_resolution=256, img_channels=32,
+                                                    mapping_kwargs=mapping_kwargs, **synthesis_kwargs)
+        self.backbone = StyleGAN2Backbone_cond(z_dim, c_dim, w_dim, img_resolution=256, img_channels=32 * 3,
+                                               mapping_ws=self.texture_backbone.num_ws, mapping_kwargs=mapping_kwargs,
+                                               **synthesis_kwargs)
+        self.superresolution = _construct(rendering_kwargs['superresolution_module'], channels=32, img_resolution=img_resolution,
+                                          sr_num_fp16_res=sr_num_fp16_res, sr_antialias=rendering_kwargs['sr_antialias'],
+                                          **sr_kwargs)
+        self.decoder = OSGDecoder(32, {'decoder_lr_mul': rendering_kwargs.get('decoder_lr_mul', 1), 'decoder_output_dim': 32})
+        self.neural_rendering_resolution = 128
+        self.rendering_kwargs = rendering_kwargs
+        self.fill_mouth = True
+
+    # ------------------------------------------------------------------------------------------
+    def mapping(self, z, c, truncation_psi=1, truncation_cutoff=None, update_emas=False):
+        if self.rendering_kwargs['c_gen_conditioning_zero']:
+            c = torch.zeros_like(c)
+        c = c[:, :self.c_dim]
+        return self.backbone.mapping(z, c * self.rendering_kwargs.get('c_scale', 0), truncation_psi=truncation_psi,
+                                     truncation_cutoff=truncation_cutoff, update_emas=update_emas)
+
+    # ------------------------------------------------------------------------------------------
+    def _rasterize_nhwc(self, texture_feats, uvcoords_image, static_feats, bbox_256, levels=None):
+        """Engine rasterizer.  texture_feats/static_feats: lists of NHWC tensors (static entries already reduced to the
+        32 plane-0 channels where the reference slices them).  Returns per-level (cond NHWC [B,r,r,C], alpha [B,r,r]),
+        full_alpha [B,256,256], mouth [B,256,256].  ``levels`` restricts the work to the entries a consumer reads."""
+        uv = uvcoords_image if uvcoords_image.dtype == torch.float32 else uvcoords_image.float()
+        uv = uv.contiguous()
+        B, UH, UW, _ = uv.shape
+        full_alpha, mouth, upper_alpha = rt.fill_mouth(uv, upper_row0=87)
+        alpha = uv[..., 2]                       # strided view [B,H,W]
+        alpha4 = uv[..., 2:3]                    # [B,H,W,1] NHWC view with pixel stride 3
+        upper4 = upper_alpha.unsqueeze(-1)
+        outs = []
+        resized_alpha = {}
+        for idx, tex in enumerate(texture_feats):
+            if levels is not None and idx not in levels:
+                outs.append(None)
+                continue
+            res = tex.shape[1]
+            bbox = [round(i * res / 256) for i in bbox_256]
+            rendering_image = rt.grid_sample_nhwc(tex, uv)                       # [B,256,256,C]
+            rendering_feat = rt.resize_aa(rendering_image, res, res)
+            if res not in resized_alpha:
+                resized_alpha[res] = (rt.resize_aa(alpha4, res, res).squeeze(-1), rt.resize_aa(upper4, res, res).squeeze(-1))
+            a_r, ua_r = resized_alpha[res]
+            st = static_feats[idx]
+            static_feat = rt.resize_aa(st, res, res, crop=(bbox[0], bbox[1], bbox[2], bbox[3]))
+            outs.append((rt.lerp_alpha(rendering_feat, static_feat, a_r), ua_r))
+        return outs, full_alpha, mouth
+
+    def rasterize(self, texture_feats, uvcoords_image, static_feats, bbox_256):
+        """Reference signature (triplane_v20.py:317-339): NCHW lists in, list of [B,C+1,res,res], full_alpha, mouth_masks."""
+        tex = [rt.to_nhwc(t) for t in texture_feats]
+        sta = [rt.to_nhwc(t) for t in static_feats]
+        outs, full_alpha, mouth = self._rasterize_nhwc(tex, uvcoords_image, sta, bbox_256)
+        images = [rt.from_nhwc(torch.cat([o[0], o[1].unsqueeze(-1)], dim=-1)) for o in outs]
+        return images, full_alpha.unsqueeze(1), mouth.unsqueeze(1)
+
+    # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def _static_views(static_feats):
+        """NHWC views of the six static features; entries 0 and 5 (the 96-channel images) reduced to plane 0
+        (triplane_v20.py:109-112)."""
+        sf = [rt.to_nhwc(t) for t in static_feats]
+        plane_img = sf[-1]
+        views = list(sf)
+        if views[0].shape[-1] == 96:
+            views[0] = views[0][..., :32]
+        views[-1] = plane_img[..., :32] if plane_img.shape[-1] == 96 else plane_img
+        return views, plane_img
+
+    def _stitch_render_sr(self, ws, c, mesh_condition, texture_feats, static_feats, neural_rendering_resolution,
+                          evaluation, synthesis_kwargs):
+        cam = c[:, -25:]
+        if neural_rendering_resolution is None:
+            neural_rendering_resolution = self.neural_rendering_resolution
+        else:
+            self.neural_rendering_resolution = neural_rendering_resolution
+        N = ws.shape[0]
+        tex = [rt.to_nhwc(t) for t in texture_feats]
+        static_views, plane_img = self._static_views(static_feats)
+        assert len(static_views) == len(tex)
+        assert plane_img.shape[-1] == 96, 'static backbone must emit 3 x 32 plane channels'
+
+        # UV rasterize: only the four levels the face backbone consumes (cond_list[0..3], networks_stylegan2_new.py:536-540)
+        conds, full_alpha, _ = self._rasterize_nhwc(tex, mesh_condition['uvcoords_image'], static_views, BBOX_256,
+                                                    levels=(0, 1, 2, 3))
+        noise_kwargs = {k: v for k, v in synthesis_kwargs.items() if k in ('noise_mode',)}
+        stitch = self.face_backbone.synthesis(ws, cond_list=conds[:4], return_list=False, **noise_kwargs)   # NCHW view
+        stitch = rt.to_nhwc(stitch)                                                                          # [B,256,256,32]
+
+        # stitch into plane 0 of a copy of the static planes (triplane_v20.py:119-128)
+        b0, b1, b2, b3 = BBOX_256
+        stitch128 = rt.resize_aa(stitch, 128, 128)
+        alpha128 = rt.resize_aa(full_alpha.unsqueeze(-1), 128, 128).squeeze(-1)
+        planes = plane_img.clone()
+        win_out = planes[:, b0:b1, b2:b3, :32]
+        rt.lerp_alpha(stitch128, plane_img[:, b0:b1, b2:b3, :32], alpha128, out=win_out)
+
+        if evaluation:
+            assert synthesis_kwargs.get('noise_mode') == 'const', ('noise_mode' in synthesis_kwargs, synthesis_kwargs.get('noise_mode'))
+        res = int(self.neural_rendering_resolution)
+        feat, depth, wsum = self.renderer.render_nhwc(planes, self.decoder, cam, res, self.rendering_kwargs, evaluation=evaluation)
+        feature_image = rt.from_nhwc(feat)                       # [B,32,res,res] view
+        depth_image = depth.reshape(N, 1, res, res)
+        rgb_image = feature_image[:, :3]
+        sr_kwargs = {k: v for k, v in synthesis_kwargs.items() if k != 'noise_mode' and k not in ('update_emas',)}
+        sr_image = self.superresolution(rgb_image, feature_image, ws, noise_mode=self.rendering_kwargs['superresolution_noise_mode'],
+                                        **sr_kwargs)
+        triplane = rt.from_nhwc(planes).reshape(N, 3, 32, planes.shape[1], planes.shape[2])
+        return {'image': sr_image, 'image_raw': rgb_image, 'image_depth': depth_image, 'feature_image': feature_image,
+                'triplane': triplane}
+
+    def synthesis(self, ws, c, mesh_condition, neural_rendering_resolution=None, update_emas=False, cache_backbone=False,
+                  use_cached_backbone=False, return_featmap=False, evaluation=False, depth_jitter=None, importance_u=None,
+                  **synthesis_kwargs):
+        """triplane_v20.py:89-150.  ``depth_jitter`` / ``importance_u`` optionally pin the renderer's random draws."""
+        if depth_jitter is not None:
+            self.renderer.depth_jitter = depth_jitter
+        if importance_u is not None:
+            self.renderer.importance_u = importance_u
+        noise_kwargs = {k: v for k, v in synthesis_kwargs.items() if k in ('noise_mode',)}
+        texture_feats = self.texture_backbone.synthesis(ws, cond_list=None, return_list=True, **noise_kwargs)
+        static_feats = self.backbone.synthesis(ws, cond_list=None, return_list=True, **noise_kwargs)
+        out = self._stitch_render_sr(ws, c, mesh_condition, texture_feats, static_feats, neural_rendering_resolution,
+                                     evaluation, synthesis_kwargs)
+        if return_featmap:
+            out['texture'] = texture_feats
+            return out
+        return {'image': out['image'], 'image_raw': out['image_raw'], 'image_depth': out['image_depth']}
+
+    def synthesis_withTexture(self, ws, texture_feats, c, mesh_condition, static_feats=None, neural_rendering_resolution=None,
+                              update_emas=False, cache_backbone=False, use_cached_backbone=False, evaluation=False,
+                              depth_jitter=None, importance_u=None, **synthesis_kwargs):
+        """triplane_v20.py:152-244: per-frame driver of eval_seq.py (texture/static features precomputed)."""
+        if depth_jitter is not None:
+            self.renderer.depth_jitter = depth_jitter
+        if importance_u is not None:
+            self.renderer.importance_u = importance_u
+        if static_feats is None:
+            noise_kwargs = {k: v for k, v in synthesis_kwargs.items() if k in ('noise_mode',)}
+            static_feats = self.backbone.synthesis(ws, cond_list=None, return_list=True, **noise_kwargs)
+        return self._stitch_render_sr(ws, c, mesh_condition, texture_feats, static_feats, neural_rendering_resolution,
+                                      evaluation, synthesis_kwargs)
+
+    def synthesis_withCondition(self, ws, c, mesh_condition, gt_texture_feats=None, gt_static_feats=None,
+                                texture_feats_conditions=None, static_feats_conditions=None, neural_rendering_resolution=None,
+                                update_emas=False, cache_backbone=False, use_cached_backbone=False, only_image=False,
+                                return_feats=False, **synthesis_kwargs):
+        """triplane_v20.py:246-315 (called from training code only; kept for signature parity)."""
+        noise_kwargs = {k: v for k, v in synthesis_kwargs.items() if k in ('noise_mode',)}
+        texture_feats = gt_texture_feats if gt_texture_feats is not None else self.texture_backbone.synthesis(
+            ws, cond_list=None, return_list=True, feat_conditions=texture_feats_conditions, **noise_kwargs)
+        static_feats = gt_static_feats if gt_static_feats is not None else self.backbone.synthesis(
+            ws, cond_list=None, return_list=True, feat_conditions=static_feats_conditions, **noise_kwargs)
+        evaluation = synthesis_kwargs.get('noise_mode') == 'const'
+        out = self._stitch_render_sr(ws, c, mesh_condition, texture_feats, static_feats, neural_rendering_resolution,
+                                     evaluation, synthesis_kwargs)
+        if only_image:
+            return {'image': out['image']}
+        if return_feats:
+            out['static'] = static_feats
+            out['texture'] = texture_feats
+        return out
+
+    def forward(self, z, c, v, truncation_psi=1, truncation_cutoff=None, neural_rendering_resolution=None, update_emas=False,
+                cache_backbone=False, use_cached_backbone=False, **synthesis_kwargs):
+        ws = self.mapping(z, c, truncation_psi=truncation_psi, truncation_cutoff=truncation_cutoff, update_emas=update_emas)
+        return self.synthesis(ws, c, v, update_emas=update_emas, neural_rendering_resolution=neural_rendering_resolution,
+                              cache_backbone=cache_backbone, use_cached_backbone=use_cached_backbone, **synthesis_kwargs)
