@@ -1,0 +1,143 @@
+"""GPU parity of the op-level C-ABI entry points (called through invertavatar_b200.runtime, the ctypes layer)
+against the reference-minted golden vectors and the oracle."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from common import T, golden
+from invertavatar_b200 import runtime as rt
+from oracle import ops as o_ops
+from oracle import stylegan2 as o_sg
+from oracle import triplane as o_tp
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def close(a, b, atol, what=''):
+    a = a.detach().cpu().numpy() if hasattr(a, 'detach') else np.asarray(a)
+    b = b.detach().cpu().numpy() if hasattr(b, 'detach') else np.asarray(b)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    err = float(np.abs(a.astype(np.float64) - b.astype(np.float64)).max()) if a.size else 0.0
+    assert err <= atol, f'{what}: max-abs {err:.3e} > {atol:.1e}'
+    return err
+
+
+def test_bias_act_golden():
+    g = golden('ops.npz')
+    x, b = T(g['bias_act/x']).to(DEV), T(g['bias_act/b']).to(DEV)
+    for act in rt.ACT_IDS:
+        close(rt.bias_act(x, b, act=act), g[f'bias_act/{act}'], 2e-6, act)
+    close(rt.bias_act(x, b, act='lrelu', alpha=0.1, gain=1.7, clamp=1.5), g['bias_act/lrelu_gain_clamp'], 1e-6)
+    close(rt.bias_act(x, torch.arange(6.0, device=DEV), dim=3), g['bias_act/linear_dim3'], 1e-6)
+    # channels-last input, no bias, empty tensor
+    xc = x.contiguous(memory_format=torch.channels_last)
+    close(rt.bias_act(xc, b, act='lrelu'), g['bias_act/lrelu'], 1e-6)
+    close(rt.bias_act(x, None, act='relu'), o_ops.bias_act(x.cpu(), None, act='relu'), 1e-6)
+    assert rt.bias_act(torch.empty(0, 5, 2, 2, device=DEV), b).numel() == 0
+    with pytest.raises(RuntimeError):
+        rt.bias_act(x.cpu(), b.cpu())          # no CPU fallback
+
+
+def test_bias_act_large():
+    x = torch.randn(2, 128, 64, 64, device=DEV)
+    b = torch.randn(128, device=DEV)
+    y = rt.bias_act(x, b, act='lrelu', clamp=256)
+    close(y, o_ops.bias_act(x.cpu(), b.cpu(), act='lrelu', clamp=256), 1e-6)
+
+
+def test_upfirdn2d_golden():
+    g = golden('ops.npz')
+    x, f = T(g['upfirdn2d/x']).to(DEV), T(g['upfirdn2d/f']).to(DEV)
+    close(rt.upfirdn2d(x, f, up=(2, 2), padding=(2, 1, 2, 1), gain=4), g['upfirdn2d/up2'], 1e-6)
+    close(rt.upfirdn2d(x, f, down=(2, 2), padding=(1, 1, 1, 1)), g['upfirdn2d/down2'], 1e-6)
+    close(rt.upfirdn2d(x, f, padding=(2, 1, 2, 1)), g['upfirdn2d/filter'], 1e-6)
+    close(rt.upfirdn2d(x, f, padding=(1, 1, 1, 1), gain=4), g['upfirdn2d/pad_fir'], 1e-6)
+    close(rt.upfirdn2d(x, f, up=(3, 3), down=(2, 2), padding=(2, 1, 0, 3), flip_filter=True, gain=2), g['upfirdn2d/up3_down2_pad'], 1e-6)
+    fa = T(g['upfirdn2d/fa']).to(DEV)
+    close(rt.upfirdn2d(x, fa, up=(2, 1), down=(1, 2), padding=(1, 2, 2, 1)), g['upfirdn2d/asym'], 2e-6)
+    close(rt.upfirdn2d(x, fa, up=(2, 1), down=(1, 2), padding=(1, 2, 2, 1), flip_filter=True), g['upfirdn2d/asym_flip'], 2e-6)
+    close(rt.upfirdn2d(x, T(g['upfirdn2d/f_sep']).to(DEV), up=(2, 2), padding=(4, 3, 4, 3), gain=4), g['upfirdn2d/sep_up2'], 1e-6)
+    close(rt.upfirdn2d(x, f, up=(2, 2), padding=(-1, 2, 3, -2)), g['upfirdn2d/negpad'], 1e-6)
+    # channels-last strides are honoured (upfirdn2d.cpp:56-63)
+    xc = x.contiguous(memory_format=torch.channels_last)
+    y = rt.upfirdn2d(xc, f, up=(2, 2), padding=(2, 1, 2, 1), gain=4)
+    close(y, g['upfirdn2d/up2'], 1e-6)
+
+
+def test_mapping_pieces():
+    x = torch.randn(5, 37, device=DEV)
+    w = torch.randn(19, 37, device=DEV)
+    b = torch.randn(19, device=DEV)
+    y = rt.fully_connected(x, w, b, w_gain=0.01 / np.sqrt(37), b_gain=0.01, act='lrelu')
+    close(y, o_sg.fully_connected(x.cpu(), w.cpu(), b.cpu(), activation='lrelu', lr_multiplier=0.01), 1e-6)
+    x = torch.randn(11, 512, device=DEV)      # more than one batch chunk of 8
+    w = torch.randn(512, 512, device=DEV)
+    close(rt.fully_connected(x, w, None, w_gain=1 / np.sqrt(512)), o_sg.fully_connected(x.cpu(), w.cpu()), 2e-5)
+    close(rt.normalize_2nd_moment(x), o_sg.normalize_2nd_moment(x.cpu()), 1e-5)
+    wa = torch.randn(512, device=DEV)
+    ws = rt.broadcast_truncate(x, wa, 14, psi=0.7, cutoff=9)
+    ref = x.cpu().unsqueeze(1).repeat(1, 14, 1)
+    ref[:, :9] = wa.cpu().lerp(ref[:, :9], 0.7)
+    close(ws, ref, 1e-6)
+
+
+def test_fill_mouth_golden():
+    g = golden('stages.npz')
+    a = T(g['fill_mouth/alpha']).to(DEV)
+    full, mouth, upper = rt.fill_mouth(a)
+    close(full.unsqueeze(1), g['fill_mouth/full'], 0)
+    close(mouth.unsqueeze(1), g['fill_mouth/mouth'], 0)
+    up = T(g['fill_mouth/mouth']).clone()
+    up[:, :, :87] = 0
+    close(upper.unsqueeze(1), (T(g['fill_mouth/alpha']) + up).clamp(0, 1), 0)
+    # uvcoords_image layout (mask = channel 2 of [B,H,W,3])
+    uv = torch.cat([torch.zeros(3, 256, 256, 2), T(g['fill_mouth/alpha'])[:, 0].unsqueeze(-1)], -1).to(DEV)
+    full2, mouth2, _ = rt.fill_mouth(uv)
+    close(full2, full, 0)
+    close(mouth2, mouth, 0)
+
+
+def test_fill_mouth_adversarial():
+    """Spiral corridor: the flood has to wind through a long 1-pixel path (many row/column sweep iterations)."""
+    a = torch.ones(1, 1, 64, 64)
+    a[0, 0, 0, :] = 0
+    y0, y1, x0, x1 = 2, 61, 2, 61
+    a[0, 0, 0:3, 63] = 0
+    # carve a serpentine path
+    for r in range(2, 62, 4):
+        a[0, 0, r, 1:63] = 0
+        a[0, 0, r:r + 3, 62 if (r // 4) % 2 == 0 else 1] = 0
+        if r + 2 < 64:
+            a[0, 0, r + 2, 1:63] = 0
+    a[0, 0, 1, 63] = 0
+    a[0, 0, 40:44, 30:34] = 1
+    a[0, 0, 41:43, 31:33] = 0.0    # enclosed 2x2 hole inside a solid 4x4 block sitting in the corridor area
+    full, mouth = o_tp.fill_mouth(a.clone())
+    f2, m2, _ = rt.fill_mouth(a.to(DEV))
+    close(f2.unsqueeze(1), full, 0)
+    close(m2.unsqueeze(1), mouth, 0)
+
+
+def test_grid_sample_resize_lerp():
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 12, 20, 24, generator=g)          # NCHW
+    grid = torch.rand(2, 9, 11, 2, generator=g) * 2.4 - 1.2   # includes out-of-range samples
+    ref = F.grid_sample(x, grid, mode='bilinear', padding_mode='zeros', align_corners=False)
+    y = rt.grid_sample_nhwc(rt.to_nhwc(x.to(DEV)), grid.to(DEV))
+    close(rt.from_nhwc(y), ref, 2e-6)
+    for (ih, iw, oh, ow) in [(256, 256, 32, 32), (256, 256, 64, 64), (64, 64, 64, 64), (16, 16, 32, 32), (128, 128, 128, 128), (40, 24, 17, 31)]:
+        x = torch.randn(2, 5, ih, iw, generator=g)
+        ref = F.interpolate(x, size=(oh, ow), mode='bilinear', antialias=True)
+        y = rt.resize_aa(rt.to_nhwc(x.to(DEV)), oh, ow)
+        close(rt.from_nhwc(y), ref, 2e-6, f'resize {ih}x{iw}->{oh}x{ow}')
+    # crop + paste window
+    x = torch.randn(1, 8, 64, 64, generator=g)
+    ref = F.interpolate(x[:, :, 14:46, 16:48], size=(64, 64), mode='bilinear', antialias=True)
+    y = rt.resize_aa(rt.to_nhwc(x.to(DEV)), 64, 64, crop=(14, 46, 16, 48))
+    close(rt.from_nhwc(y), ref, 2e-6)
+    a, b = torch.randn(2, 6, 7, 5, generator=g), torch.randn(2, 6, 7, 5, generator=g)
+    al = torch.rand(2, 6, 7, generator=g)
+    y = rt.lerp_alpha(a.to(DEV), b.to(DEV), al.to(DEV))
+    close(y, a * al.unsqueeze(-1) + b * (1 - al.unsqueeze(-1)), 1e-6)

@@ -1,0 +1,88 @@
+"""GPU parity of the whole generator forward (TriPlaneGenerator.mapping + synthesis / synthesis_withTexture) against
+the reference-minted fingerprints; tolerance = BASELINE north_star: 1e-3 max-abs on the image (PSNR > 50 dB)."""
+import numpy as np
+import pytest
+import torch
+
+from common import build_generator, golden, psnr
+from fingerprint import compare, unpack
+from invertavatar_b200 import runtime as rt
+from invertavatar_b200 import synth
+from oracle import triplane as o_tp
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+IMAGE_ATOL = 1e-3       # north_star
+STAGE_ATOL = 2e-4       # intermediate feature maps (fp32 3-term split convolutions)
+
+
+def _run(tag, npz, stages=True):
+    g = golden(npz)
+    res, Dc, Df, B, ev = [int(v) for v in g[f'{tag}/meta']]
+    G = build_generator(Dc, Df).to(DEV)
+    z, cond, c, uv = synth.latents(B).to(DEV), synth.frontal_camera(B).to(DEV), synth.cameras(B).to(DEV), synth.uvcoords_image(B).to(DEV)
+    ws = G.mapping(z, cond, truncation_psi=0.7, truncation_cutoff=14)
+    assert float((ws.cpu() - torch.from_numpy(g[f'{tag}/ws'])).abs().max()) <= 1e-5
+    jit = synth.depth_jitter(B, res * res, Dc).to(DEV)
+    out = G.synthesis(ws, c, {'uvcoords_image': uv}, neural_rendering_resolution=res, noise_mode='const', evaluation=bool(ev),
+                      depth_jitter=jit, return_featmap=True)
+    return g, G, ws, out
+
+
+def _check(g, tag, out):
+    errs = {}
+    for i, t in enumerate(out['texture']):
+        errs[f'texture{i}'] = compare(t, unpack(f'{tag}/texture{i}', g), STAGE_ATOL * max(1.0, float(np.abs(g[f'{tag}/texture{i}/sub']).max())), f'texture{i}')[0]
+    errs['triplane'] = compare(out['triplane'], unpack(f'{tag}/triplane', g), STAGE_ATOL * max(1.0, float(np.abs(g[f'{tag}/triplane/sub']).max())), 'triplane')[0]
+    errs['feature_image'] = compare(out['feature_image'], unpack(f'{tag}/feature_image', g), IMAGE_ATOL, 'feature_image')[0]
+    errs['image_raw'] = compare(out['image_raw'], unpack(f'{tag}/image_raw', g), IMAGE_ATOL, 'image_raw')[0]
+    errs['image_depth'] = compare(out['image_depth'], unpack(f'{tag}/image_depth', g), IMAGE_ATOL, 'image_depth')[0]
+    errs['image'] = compare(out['image'], unpack(f'{tag}/image', g), IMAGE_ATOL, 'image')[0]
+    print(tag, {k: f'{v:.2e}' for k, v in errs.items()})
+    return errs
+
+
+def test_synthesis_c1_golden():
+    g, G, ws, out = _run('c1', 'synthesis_c1.npz')
+    _check(g, 'c1', out)
+    assert tuple(out['image'].shape) == (1, 3, 512, 512) and tuple(out['image_raw'].shape) == (1, 3, 64, 64)
+    # per-frame driver of eval_seq.py: synthesis_withTexture, evaluation=False with pinned importance u
+    ws1 = ws[:1]
+    tex = G.texture_backbone.synthesis(ws1, cond_list=None, return_list=True, noise_mode='const')
+    sta = G.backbone.synthesis(ws1, cond_list=None, return_list=True, noise_mode='const')
+    o = G.synthesis_withTexture(ws1, tex, synth.cameras(1, first=3).to(DEV), {'uvcoords_image': synth.uvcoords_image(1, first=3).to(DEV)},
+                                static_feats=sta, noise_mode='const', evaluation=False,
+                                depth_jitter=synth.depth_jitter(1, 64 * 64, 16, seed=8).to(DEV),
+                                importance_u=synth.importance_u(1, 64 * 64, 16, seed=12).to(DEV))
+    for k in ('image', 'image_raw', 'image_depth'):
+        compare(o[k], unpack(f'c1_withtex/{k}', g), IMAGE_ATOL, 'withtex/' + k)
+
+
+def test_synthesis_c1_psnr_vs_oracle():
+    """Full-image max-abs and PSNR against the oracle run on this host (same weights, same inputs)."""
+    g, G, ws, out = _run('c1', 'synthesis_c1.npz')
+    sd = {k: v.cpu() for k, v in G.state_dict().items()}
+    ref = o_tp.synthesis(sd, ws.cpu(), synth.cameras(1), synth.uvcoords_image(1), G.rendering_kwargs, synth.depth_jitter(1, 64 * 64, 16),
+                         evaluation=True, neural_rendering_resolution=64)
+    err = float((out['image'].cpu() - ref['image']).abs().max())
+    p = psnr(out['image'].cpu(), ref['image'])
+    print(f'c1 image max-abs {err:.3e}  PSNR {p:.1f} dB')
+    assert err <= IMAGE_ATOL and p > 50.0
+
+
+def test_synthesis_c2_golden():
+    """Headline shape 128^2 x (48+48), two different frames in one batch."""
+    g, G, ws, out = _run('c2', 'synthesis_c2.npz')
+    _check(g, 'c2', out)
+
+
+def test_synthesis_batch_invariance():
+    """Frames are independent: rendering frame 1 alone equals frame 1 of the batch (fixed camera radius keeps
+    the batch-mean near/far identical)."""
+    g, G, ws, out = _run('c2', 'synthesis_c2.npz')
+    res, Dc = 128, 48
+    c, uv = synth.cameras(2).to(DEV), synth.uvcoords_image(2).to(DEV)
+    jit = synth.depth_jitter(2, res * res, Dc).to(DEV)
+    o1 = G.synthesis(ws[1:2], c[1:2], {'uvcoords_image': uv[1:2]}, neural_rendering_resolution=res, noise_mode='const', evaluation=True,
+                     depth_jitter=jit[1:2])
+    assert float((o1['image'] - out['image'][1:2]).abs().max()) <= 1e-5
