@@ -35,6 +35,12 @@ int ia_set_device(int device);
 /* Number of kernels this library has launched since load / since the last reset (bench.py gpu_launches). */
 int64_t ia_launch_count(void);
 void ia_reset_launch_count(void);
+/* Per-launch timing for bench.py's roofline leg: between ia_profile_begin() and ia_profile_report() every kernel launch
+ * of this library is bracketed by CUDA events on its launching stream.  ia_profile_report synchronises the device, stops
+ * profiling and writes a JSON object {"<entry point>": {"ms": total, "launches": n}, ...} into buf (NUL-terminated,
+ * truncated to buflen); returns the untruncated length, or -1 on error. */
+int ia_profile_begin(void);
+int64_t ia_profile_report(char* buf, int64_t buflen);
 
 /* ---- torch_utils/ops plugin equivalents --------------------------------------------------------- */
 

@@ -101,6 +101,8 @@ SIGNATURES = {
     'ia_set_device': (C.c_int, [C.c_int]),
     'ia_launch_count': (C.c_int64, []),
     'ia_reset_launch_count': (None, []),
+    'ia_profile_begin': (C.c_int, []),
+    'ia_profile_report': (C.c_int64, [C.c_char_p, C.c_int64]),
     'ia_bias_act': (C.c_int, [c_f32p, c_f32p, c_f32p, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_float, C.c_float, C.c_float, C.c_void_p]),
     'ia_upfirdn2d': (C.c_int, [C.POINTER(Upfirdn2dParams), C.c_void_p]),
     'ia_fully_connected': (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float,

@@ -12,6 +12,10 @@ namespace ia {
 
 void set_error(const char* fmt, ...);
 void count_launch();
+// Optional per-launch CUDA-event bracketing (ia_profile_begin/ia_profile_report): prof_begin records the start event on
+// the launching stream, IA_LAUNCH_CHECK closes the bracket.  Both are no-ops unless profiling is enabled.
+void prof_begin(const char* name, cudaStream_t stream);
+void prof_end();
 
 #define IA_CHECK(cond, ...)                                   \
     do {                                                      \
@@ -24,6 +28,7 @@ void count_launch();
 #define IA_LAUNCH_CHECK(name)                                                        \
     do {                                                                             \
         ia::count_launch();                                                          \
+        ia::prof_end();                                                              \
         cudaError_t e__ = cudaGetLastError();                                        \
         if (e__ != cudaSuccess) {                                                    \
             ia::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));   \

@@ -372,6 +372,7 @@ extern "C" int ia_conv_tc(const ia_conv_params* p, void* stream) {
         IA_CHECK(e == cudaSuccess, "ia_conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     }
     dim3 grid((unsigned)(t.tiles_x * t.tiles_y * tiles_n), (unsigned)(p->Cout_pad / n_tile));
+    ia::prof_begin("ia_conv_tc", as_stream(stream));
     conv_tc_kernel<<<grid, kThreads, smem, as_stream(stream)>>>(ma_hi, ma_lo, mw_hi, mw_lo, t);
     IA_LAUNCH_CHECK("ia_conv_tc");
     return 0;

@@ -78,10 +78,12 @@ extern "C" int ia_styles(const ia_style_layer* layers_dev, const ia_style_layer*
         if (layers_host[i].wsq) max_cout = layers_host[i].Cout > max_cout ? layers_host[i].Cout : max_cout;
     }
     dim3 g1((unsigned)cdiv((int64_t)max_cin * 32, 256), n_layers);
+    ia::prof_begin("ia_styles(styles)", as_stream(stream));
     styles_kernel<<<g1, 256, 0, as_stream(stream)>>>(layers_dev, ws, B, num_ws);
     IA_LAUNCH_CHECK("ia_styles(styles)");
     if (max_cout > 0) {
         dim3 g2((unsigned)cdiv((int64_t)max_cout * 32, 256), n_layers);
+        ia::prof_begin("ia_styles(demod)", as_stream(stream));
         demod_kernel<<<g2, 256, 0, as_stream(stream)>>>(layers_dev, B);
         IA_LAUNCH_CHECK("ia_styles(demod)");
     }
@@ -134,6 +136,7 @@ extern "C" int ia_modsplit(const ia_modsplit_params* p, void* stream) {
     IA_CHECK(p->cond == nullptr || p->cond_alpha != nullptr, "ia_modsplit: cond needs cond_alpha");
     int64_t total = (int64_t)p->B * p->HW * (p->C_pad >> 2);
     if (total == 0) return 0;
+    ia::prof_begin("ia_modsplit", as_stream(stream));
     modsplit_kernel<<<(unsigned)cdiv(total, 256), 256, 0, as_stream(stream)>>>(*p);
     IA_LAUNCH_CHECK("ia_modsplit");
     return 0;
@@ -169,9 +172,11 @@ extern "C" int ia_pack_conv_weight(const float* w, int32_t Cout, int32_t Cin, in
     IA_CHECK(Cout_pad >= Cout && Cin_pad >= Cin, "ia_pack_conv_weight: bad padding");
     int taps = kh * kw;
     int64_t total = (int64_t)taps * Cout_pad * Cin_pad;
+    ia::prof_begin("ia_pack_conv_weight", as_stream(stream));
     pack_weight_kernel<<<(unsigned)cdiv(total, 256), 256, 0, as_stream(stream)>>>(w, Cout, Cin, taps, Cout_pad, Cin_pad, w_hi, w_lo);
     IA_LAUNCH_CHECK("ia_pack_conv_weight");
     if (wsq) {
+        ia::prof_begin("ia_pack_conv_weight(wsq)", as_stream(stream));
         wsq_kernel<<<(unsigned)cdiv((int64_t)Cout * Cin, 256), 256, 0, as_stream(stream)>>>(w, Cout, Cin, taps, wsq);
         IA_LAUNCH_CHECK("ia_pack_conv_weight(wsq)");
     }
@@ -235,6 +240,7 @@ extern "C" int ia_fir_epilogue(const ia_fir_params* p, void* stream) {
     IA_CHECK(p->noise == nullptr || p->noise_strength != nullptr, "ia_fir_epilogue: noise needs noise_strength");
     int64_t total = (int64_t)p->B * p->OH * p->OW * (p->C >> 2);
     if (total == 0) return 0;
+    ia::prof_begin("ia_fir_epilogue", as_stream(stream));
     fir_epilogue_kernel<<<(unsigned)cdiv(total, 256), 256, 0, as_stream(stream)>>>(*p);
     IA_LAUNCH_CHECK("ia_fir_epilogue");
     return 0;
@@ -286,6 +292,7 @@ extern "C" int ia_torgb_finish(const ia_torgb_params* p, void* stream) {
     IA_CHECK(p->img_prev == nullptr || ((p->H & 1) == 0 && (p->W & 1) == 0), "ia_torgb_finish: odd size with skip image");
     int64_t total = (int64_t)p->B * p->H * p->W * p->C;
     if (total == 0) return 0;
+    ia::prof_begin("ia_torgb_finish", as_stream(stream));
     torgb_finish_kernel<<<(unsigned)cdiv(total, 256), 256, 0, as_stream(stream)>>>(*p);
     IA_LAUNCH_CHECK("ia_torgb_finish");
     return 0;
@@ -401,6 +408,7 @@ extern "C" int ia_conv_simt(const ia_conv_params* p, void* stream) {
     if (int rc = ia_conv_validate(p, "ia_conv_simt")) return rc;
     int64_t rows = (int64_t)p->B * p->GH * p->GW;
     dim3 grid((unsigned)cdiv(rows, SIMT_TM), (unsigned)cdiv(p->Cout_pad, SIMT_TN));
+    ia::prof_begin("ia_conv_simt", as_stream(stream));
     conv_simt_kernel<<<grid, 256, 0, as_stream(stream)>>>(*p);
     IA_LAUNCH_CHECK("ia_conv_simt");
     return 0;

@@ -3,6 +3,10 @@
 // training_avatar_texture/networks_stylegan2_new.py:96-127,233-268 (written from scratch).
 #include <stdarg.h>
 #include <atomic>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
 
 #include "ia_common.cuh"
 
@@ -16,7 +20,69 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// ---- per-launch event profiler (bench.py's roofline leg) -------------------------------------------
+struct ProfRec { const char* name; cudaEvent_t t0, t1; };
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static thread_local int g_prof_open = -1;
+static thread_local cudaStream_t g_prof_stream = nullptr;
+void prof_begin(const char* name, cudaStream_t stream) {
+    if (!g_prof_on) return;
+    ProfRec r{name, nullptr, nullptr};
+    if (cudaEventCreate(&r.t0) != cudaSuccess || cudaEventCreate(&r.t1) != cudaSuccess) return;
+    cudaEventRecord(r.t0, stream);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof.push_back(r);
+    g_prof_open = (int)g_prof.size() - 1;
+    g_prof_stream = stream;
+}
+void prof_end() {
+    if (g_prof_open < 0) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (g_prof_open < (int)g_prof.size()) cudaEventRecord(g_prof[g_prof_open].t1, g_prof_stream);
+    g_prof_open = -1;
+}
 }  // namespace ia
+
+extern "C" int ia_profile_begin(void) {
+    std::lock_guard<std::mutex> lk(ia::g_prof_mu);
+    for (auto& r : ia::g_prof) { cudaEventDestroy(r.t0); cudaEventDestroy(r.t1); }
+    ia::g_prof.clear();
+    ia::g_prof_on = true;
+    return 0;
+}
+
+extern "C" int64_t ia_profile_report(char* buf, int64_t buflen) {
+    std::lock_guard<std::mutex> lk(ia::g_prof_mu);
+    ia::g_prof_on = false;
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { ia::set_error("ia_profile_report: %s", cudaGetErrorString(e)); return -1; }
+    std::map<std::string, std::pair<double, int64_t>> agg;
+    for (auto& r : ia::g_prof) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.t0, r.t1) == cudaSuccess) { auto& a = agg[r.name]; a.first += ms; a.second += 1; }
+        cudaEventDestroy(r.t0); cudaEventDestroy(r.t1);
+    }
+    ia::g_prof.clear();
+    std::string out = "{";
+    bool first = true;
+    for (auto& kv : agg) {
+        char tmp[256];
+        snprintf(tmp, sizeof(tmp), "%s\"%s\": {\"ms\": %.6f, \"launches\": %lld}", first ? "" : ", ", kv.first.c_str(), kv.second.first,
+                 (long long)kv.second.second);
+        out += tmp;
+        first = false;
+    }
+    out += "}";
+    if (buf && buflen > 0) {
+        size_t n = out.size() < (size_t)buflen - 1 ? out.size() : (size_t)buflen - 1;
+        memcpy(buf, out.data(), n);
+        buf[n] = 0;
+    }
+    return (int64_t)out.size();
+}
 
 using namespace ia;
 
@@ -65,6 +131,7 @@ extern "C" int ia_bias_act(const float* x, const float* b, float* y, int64_t num
     if (numel == 0) return 0;
     int threads = 256;
     int64_t blocks = cdiv(cdiv(numel, 4), threads);
+    ia::prof_begin("ia_bias_act", as_stream(stream));
     bias_act_kernel<<<(unsigned)blocks, threads, 0, as_stream(stream)>>>(x, b, y, numel, C > 0 ? C : 1,
                                                                           inner > 0 ? inner : 1, act, alpha, gain, clamp);
     IA_LAUNCH_CHECK("ia_bias_act");
@@ -120,6 +187,7 @@ extern "C" int ia_upfirdn2d(const ia_upfirdn2d_params* p, void* stream) {
     int64_t total = (int64_t)p->N * p->C * p->outH * p->outW;
     IA_CHECK(total >= 0 && total < (1LL << 40), "ia_upfirdn2d: output too large");
     if (total == 0) return 0;
+    ia::prof_begin("ia_upfirdn2d", as_stream(stream));
     upfirdn2d_kernel<<<(unsigned)cdiv(total, 256), 256, 0, as_stream(stream)>>>(*p);
     IA_LAUNCH_CHECK("ia_upfirdn2d");
     return 0;
@@ -166,6 +234,7 @@ extern "C" int ia_fully_connected(const float* x, const float* w, const float* b
     int threads = 256;
     int blocks = (int)cdiv((int64_t)Out * 32, threads);
     for (int b0 = 0; b0 < B; b0 += 8) {
+        ia::prof_begin("ia_fully_connected", as_stream(stream));
         fc_kernel<8><<<blocks, threads, 0, as_stream(stream)>>>(x, w, bias, y, B, In, Out, w_gain, b_gain, act, alpha,
                                                                   act_gain, x_stride, y_stride, b0);
         IA_LAUNCH_CHECK("ia_fully_connected");
@@ -199,6 +268,7 @@ extern "C" int ia_normalize_2nd_moment(const float* x, float* y, int32_t B, int3
                                        int64_t y_stride, void* stream) {
     IA_CHECK(x && y && D > 0, "ia_normalize_2nd_moment: bad arguments");
     if (B == 0) return 0;
+    ia::prof_begin("ia_normalize_2nd_moment", as_stream(stream));
     normalize_2nd_moment_kernel<<<B, 256, 0, as_stream(stream)>>>(x, y, D, eps, x_stride, y_stride);
     IA_LAUNCH_CHECK("ia_normalize_2nd_moment");
     return 0;
@@ -227,6 +297,7 @@ extern "C" int ia_broadcast_truncate(const float* w, const float* w_avg, float* 
     IA_CHECK(psi == 1.f || w_avg, "ia_broadcast_truncate: truncation needs w_avg");
     int64_t total = (int64_t)B * num_ws * D;
     if (total == 0) return 0;
+    ia::prof_begin("ia_broadcast_truncate", as_stream(stream));
     broadcast_truncate_kernel<<<(unsigned)cdiv(total, 256), 256, 0, as_stream(stream)>>>(w, w_avg, ws, B, num_ws, D,
                                                                                         psi, cutoff);
     IA_LAUNCH_CHECK("ia_broadcast_truncate");
@@ -253,6 +324,7 @@ extern "C" int ia_lerp_alpha(const ia_lerp_params* p, void* stream) {
     IA_CHECK(p && p->a && p->b && p->alpha && p->out, "ia_lerp_alpha: null tensor");
     int64_t total = (int64_t)p->B * p->H * p->W * p->C;
     if (total == 0) return 0;
+    ia::prof_begin("ia_lerp_alpha", as_stream(stream));
     lerp_alpha_kernel<<<(unsigned)cdiv(total, 256), 256, 0, as_stream(stream)>>>(*p);
     IA_LAUNCH_CHECK("ia_lerp_alpha");
     return 0;

@@ -114,6 +114,7 @@ extern "C" int ia_fill_mouth(const float* alpha, int64_t a_stride, int64_t a_bat
     IA_CHECK(alpha, "ia_fill_mouth: null alpha");
     IA_CHECK(H >= 1 && W >= 1 && H <= 256 && W <= 256, "ia_fill_mouth: image must be at most 256x256 (got %dx%d)", H, W);
     if (B == 0) return 0;
+    ia::prof_begin("ia_fill_mouth", as_stream(stream));
     fill_mouth_kernel<<<B, 256, 0, as_stream(stream)>>>(alpha, a_stride, a_batch_stride, H, W, upper_row0, full_alpha, mouth, upper_alpha);
     IA_LAUNCH_CHECK("ia_fill_mouth");
     return 0;
@@ -171,6 +172,7 @@ extern "C" int ia_grid_sample(const float* in, int32_t B, int32_t Hi, int32_t Wi
     IA_CHECK(C > 0 && in_ld >= C && out_ld >= C && g_ld >= 2, "ia_grid_sample: bad strides");
     int64_t total = (int64_t)B * Ho * Wo * ((C + 3) >> 2);
     if (total == 0) return 0;
+    ia::prof_begin("ia_grid_sample", as_stream(stream));
     grid_sample_kernel<<<(unsigned)cdiv(total, 256), 256, 0, as_stream(stream)>>>(in, B, Hi, Wi, C, in_ld, grid, g_ld, Ho, Wo, out, out_ld);
     IA_LAUNCH_CHECK("ia_grid_sample");
     return 0;
@@ -225,6 +227,7 @@ extern "C" int ia_resize_aa(const ia_resize_params* p, void* stream) {
     IA_CHECK(p->C > 0 && p->in_ld >= p->C && p->out_ld >= p->C, "ia_resize_aa: bad strides");
     int64_t total = (int64_t)p->B * p->oh * p->ow * ((p->C + 3) >> 2);
     if (total == 0) return 0;
+    ia::prof_begin("ia_resize_aa", as_stream(stream));
     resize_aa_kernel<<<(unsigned)cdiv(total, 256), 256, 0, as_stream(stream)>>>(*p);
     IA_LAUNCH_CHECK("ia_resize_aa");
     return 0;

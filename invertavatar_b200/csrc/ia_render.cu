@@ -392,6 +392,7 @@ __global__ void ray_sampler_kernel(const float* __restrict__ cam, int64_t cam_ld
 
 extern "C" int ia_ray_bounds(const float* cam, int64_t cam_ld, int32_t B, float* near_far, void* stream) {
     IA_CHECK(cam && near_far && B > 0, "ia_ray_bounds: bad arguments");
+    ia::prof_begin("ia_ray_bounds", as_stream(stream));
     ray_bounds_kernel<<<1, 32, 0, as_stream(stream)>>>(cam, cam_ld, B, near_far);
     IA_LAUNCH_CHECK("ia_ray_bounds");
     return 0;
@@ -399,6 +400,7 @@ extern "C" int ia_ray_bounds(const float* cam, int64_t cam_ld, int32_t B, float*
 
 extern "C" int ia_ray_bounds_from_origins(const float* origins, int64_t n, float* near_far, void* stream) {
     IA_CHECK(origins && near_far && n > 0, "ia_ray_bounds_from_origins: bad arguments");
+    ia::prof_begin("ia_ray_bounds_from_origins", as_stream(stream));
     ray_bounds_origins_kernel<<<1, 1024, 0, as_stream(stream)>>>(origins, n, near_far);
     IA_LAUNCH_CHECK("ia_ray_bounds_from_origins");
     return 0;
@@ -412,6 +414,7 @@ extern "C" int ia_render(const ia_render_params* p, void* stream) {
     IA_CHECK((p->plane_px_ld & 3) == 0 && p->plane_px_ld >= 96, "ia_render: planes need >= 96 channels, pixel stride multiple of 4");
     IA_CHECK(p->res > 0 && p->B > 0, "ia_render: empty batch");
     cudaStream_t st = as_stream(stream);
+    ia::prof_begin("ia_render(decoder_stage)", st);
     decoder_stage_kernel<<<1, 256, 0, st>>>(p->w1, p->b1, p->w2, p->b2);
     IA_LAUNCH_CHECK("ia_render(decoder_stage)");
     void* stage = nullptr;
@@ -423,6 +426,7 @@ extern "C" int ia_render(const ia_render_params* p, void* stream) {
     if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_w2t, sp + kHidden * kFeat + kHidden, sizeof(float) * kHidden * kOut, 0, cudaMemcpyDeviceToDevice, st);
     if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_b2, sp + kHidden * kFeat + kHidden + kHidden * kOut, sizeof(float) * kOut, 0, cudaMemcpyDeviceToDevice, st);
     IA_CHECK(e == cudaSuccess, "ia_render: constant upload: %s", cudaGetErrorString(e));
+    ia::prof_begin("ia_render(minmax_init)", st);
     minmax_init_kernel<<<1, 32, 0, st>>>(p->depth_minmax);
     IA_LAUNCH_CHECK("ia_render(minmax_init)");
 
@@ -441,6 +445,7 @@ extern "C" int ia_render(const ia_render_params* p, void* stream) {
     int64_t want = cdiv(total_rays, kWarpsPerCta);
     int64_t grid = (int64_t)sms * per_sm;
     if (grid > want) grid = want;
+    ia::prof_begin("ia_render", st);
     render_kernel<<<(unsigned)grid, kWarpsPerCta * 32, smem, st>>>(*p);
     IA_LAUNCH_CHECK("ia_render");
     return 0;
@@ -449,6 +454,7 @@ extern "C" int ia_render(const ia_render_params* p, void* stream) {
 extern "C" int ia_depth_clamp(float* depth, int64_t n, const float* depth_minmax, void* stream) {
     IA_CHECK(depth && depth_minmax, "ia_depth_clamp: null argument");
     if (n == 0) return 0;
+    ia::prof_begin("ia_depth_clamp", as_stream(stream));
     depth_clamp_kernel<<<(unsigned)cdiv(n, 256), 256, 0, as_stream(stream)>>>(depth, n, depth_minmax);
     IA_LAUNCH_CHECK("ia_depth_clamp");
     return 0;
@@ -458,6 +464,7 @@ extern "C" int ia_ray_sampler(const float* cam, int64_t cam_ld, int32_t B, int32
     IA_CHECK(cam && origins && dirs, "ia_ray_sampler: null argument");
     int64_t total = (int64_t)B * res * res;
     if (total == 0) return 0;
+    ia::prof_begin("ia_ray_sampler", as_stream(stream));
     ray_sampler_kernel<<<(unsigned)cdiv(total, 256), 256, 0, as_stream(stream)>>>(cam, cam_ld, B, res, origins, dirs);
     IA_LAUNCH_CHECK("ia_ray_sampler");
     return 0;

@@ -69,6 +69,21 @@ def reset_launch_count():
     _C.lib().ia_reset_launch_count()
 
 
+def profile_begin():
+    """Bracket every kernel launch of the library with CUDA events until profile_report()."""
+    _C.check(_C.lib().ia_profile_begin(), 'ia_profile_begin')
+
+
+def profile_report():
+    """-> {entry point: {'ms': total device time, 'launches': n}} since profile_begin(); synchronises the device."""
+    import json
+    buf = C.create_string_buffer(1 << 16)
+    n = _C.lib().ia_profile_report(buf, len(buf))
+    if n < 0:
+        _C.check(1, 'ia_profile_report')
+    return json.loads(buf.value.decode())
+
+
 # ---------------------------------------------------------------------------------------------------
 # layout helpers: public tensors are logical NCHW with channels-last strides, kernels see NHWC
 # ---------------------------------------------------------------------------------------------------
@@ -93,6 +108,8 @@ def bias_act(x, b=None, dim=1, act='linear', alpha=None, gain=None, clamp=None):
     alpha = float(spec[0] if alpha is None else alpha)
     gain = float(spec[1] if gain is None else gain)
     clamp = float(-1 if clamp is None else clamp)
+    if x.numel() == 0:
+        return torch.empty_like(x)
     st = _enter(x)
     xd = x if x.dtype == torch.float32 else x.float()
     # dense in either contiguous or channels-last order: operate in memory order

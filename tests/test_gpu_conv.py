@@ -11,6 +11,9 @@ from oracle import stylegan2 as o_sg
 
 pytestmark = pytest.mark.gpu
 DEV = 'cuda'
+# 3-term bf16 split (hi*hi + hi*lo + lo*hi, fp32 accumulate): operands carry 16 mantissa bits, the dropped lo*lo term is
+# 2^-16 relative per product -> a few 1e-5 relative to the output scale (SURVEY 8d precision budget: 5.6e-5 on the image)
+TOL = 5e-5
 
 
 def maxerr(a, b):
@@ -52,7 +55,7 @@ def test_synthesis_layer(impl, cin, cout, res, up, B):
     assert tuple(y.shape) == tuple(ref.shape)
     scale = float(ref.abs().max())
     err = maxerr(y, ref)
-    assert err <= 2e-5 * max(scale, 1.0), f'{impl}: err {err:.3e} (scale {scale:.2f})'
+    assert err <= TOL * max(scale, 1.0), f'{impl}: err {err:.3e} (scale {scale:.2f})'
 
 
 def test_synthesis_layer_noise_modes(impl):
@@ -61,7 +64,7 @@ def test_synthesis_layer_noise_modes(impl):
     x, w = torch.randn(2, 16, 8, 8, generator=g), torch.randn(2, 64, generator=g)
     ref = o_sg.synthesis_layer(L.state_dict(), x, w, noise_mode='none')
     y = L.to(DEV)(x.to(DEV), w.to(DEV), noise_mode='none')
-    assert maxerr(y, ref) <= 2e-5
+    assert maxerr(y, ref) <= TOL * max(1.0, float(ref.abs().max()))
     y1 = L(x.to(DEV), w.to(DEV), noise_mode='random')
     y2 = L(x.to(DEV), w.to(DEV), noise_mode='random')
     assert maxerr(y1, y2) > 1e-3     # fresh noise each call
@@ -76,7 +79,7 @@ def test_torgb(impl, cin, cimg):
     x, w = torch.randn(2, cin, 16, 16, generator=g), torch.randn(2, 64, generator=g)
     ref = o_sg.torgb_layer(L.state_dict(), x, w, conv_clamp=2.0)
     y = L.to(DEV)(x.to(DEV), w.to(DEV))
-    assert maxerr(y, ref) <= 2e-5
+    assert maxerr(y, ref) <= TOL * max(1.0, float(ref.abs().max()))
 
 
 def test_modconv_golden(impl):
@@ -93,7 +96,7 @@ def test_modconv_golden(impl):
             L.noise_const.copy_(T(g[nz]))
             L.noise_strength.fill_(1.0)
             y = L.to(DEV)(x[b:b + 1].to(DEV), torch.zeros(1, 8, device=DEV), noise_mode='const', gain=1)
-            assert maxerr(y, T(g[key])[b:b + 1]) <= 2e-5, (key, b)
+            assert maxerr(y, T(g[key])[b:b + 1]) <= TOL * max(1.0, float(T(g[key]).abs().max())), (key, b)
 
 
 def test_synthesis_block_skip(impl):
@@ -110,12 +113,12 @@ def test_synthesis_block_skip(impl):
     rx, rimg = o_sg.synthesis_block(blk.state_dict(), x, img, ws, noise_mode='const')
     blk = blk.to(DEV)
     yx, yimg = blk(x.to(DEV), img.to(DEV), ws.to(DEV), noise_mode='const')
-    assert maxerr(yx, rx) <= 3e-5 and maxerr(yimg, rimg) <= 3e-5
+    assert maxerr(yx, rx) <= TOL * max(1.0, float(rx.abs().max())) and maxerr(yimg, rimg) <= TOL * max(1.0, float(rimg.abs().max()))
     # CS-SFT condition on the second half of the channels (:448-452)
     cond = torch.stack([torch.randn(2, 16, 16, 16, generator=g), torch.randn(2, 16, 16, 16, generator=g)])
     rx, rimg = o_sg.synthesis_block(blk.cpu().state_dict(), x, img, ws, condition=cond, noise_mode='const')
     yx, yimg = blk.to(DEV)(x.to(DEV), img.to(DEV), ws.to(DEV), condition=cond.to(DEV), noise_mode='const')
-    assert maxerr(yx, rx) <= 3e-5 and maxerr(yimg, rimg) <= 3e-5
+    assert maxerr(yx, rx) <= TOL * max(1.0, float(rx.abs().max())) and maxerr(yimg, rimg) <= TOL * max(1.0, float(rimg.abs().max()))
 
 
 def test_tc_matches_simt_large():
@@ -127,4 +130,4 @@ def test_tc_matches_simt_large():
     a = L(x, w, noise_mode='const')
     rt.set_conv_impl('tc')
     b = L(x, w, noise_mode='const')
-    assert maxerr(a, b) <= 2e-5 * max(1.0, float(a.abs().max()))
+    assert maxerr(a, b) <= TOL * max(1.0, float(a.abs().max()))

@@ -85,4 +85,6 @@ def test_synthesis_batch_invariance():
     jit = synth.depth_jitter(2, res * res, Dc).to(DEV)
     o1 = G.synthesis(ws[1:2], c[1:2], {'uvcoords_image': uv[1:2]}, neural_rendering_resolution=res, noise_mode='const', evaluation=True,
                      depth_jitter=jit[1:2])
-    assert float((o1['image'] - out['image'][1:2]).abs().max()) <= 1e-5
+    # not bit-identical: the batch-mean ray distance (renderer.py:311) rounds differently for 1 and 2 cameras (last ulp of
+    # near/far), which moves every depth sample by ~1e-7 -- the reference has the same property (SURVEY 8e hazard 1)
+    assert float((o1['image'] - out['image'][1:2]).abs().max()) <= 1e-4
