@@ -340,9 +340,15 @@ extern "C" int ia_conv_tc(const ia_conv_params* p, void* stream) {
     const int tiles_n = (int)cdiv(p->B, t.nb);
     t.Cin_blocks = p->Cin_pad / kBlockK;
     t.Cout = p->Cout; t.Cout_pad = p->Cout_pad;
-    // N tile: the largest of {256,128,64,32}-multiples that divides Cout_pad, capped at 256
-    int n_tile = p->Cout_pad <= 256 ? p->Cout_pad : 256;
-    while (p->Cout_pad % n_tile) n_tile -= 32;
+    // N tile: the largest multiple of 32 (<= 256) dividing Cout_pad that still yields a grid of at least ~one wave;
+    // low-resolution layers have few M tiles and are bound by the serial MMA chain of a CTA, so they take narrow tiles.
+    const int64_t m_tiles = (int64_t)t.tiles_x * t.tiles_y * tiles_n;
+    int n_tile = 32;
+    for (int cand = 256; cand >= 32; cand -= 32) {
+        if (p->Cout_pad % cand) continue;
+        n_tile = cand;
+        if (m_tiles * (p->Cout_pad / cand) >= 128) break;
+    }
     t.n_tile = n_tile;
     t.tmem_cols = 32; while (t.tmem_cols < n_tile) t.tmem_cols <<= 1;
     const uint32_t stage_bytes = 2u * kABytes + 2u * (uint32_t)n_tile * 128u;

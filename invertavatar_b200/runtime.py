@@ -316,11 +316,35 @@ def modsplit(x_nhwc, styles=None, cond=None, cond_alpha=None, C_pad=None):
     return hi, lo
 
 
-def _emit(out32=None):
+class Split:
+    """A tensor-core A operand: bf16 hi/lo pair [B,H,W,C_pad] holding x * styles of the consuming layer."""
+    __slots__ = ('hi', 'lo', 'C_pad')
+
+    def __init__(self, hi, lo):
+        self.hi, self.lo, self.C_pad = hi, lo, hi.shape[-1]
+
+
+def new_split(B, H, W, C_pad, device, C=None):
+    """Uninitialised operand buffers; zero-filled when the producer leaves padding channels (C < C_pad) untouched."""
+    make = torch.zeros if (C is not None and C != C_pad) else torch.empty
+    hi = make((B, H, W, C_pad), dtype=torch.bfloat16, device=device)
+    lo = make((B, H, W, C_pad), dtype=torch.bfloat16, device=device)
+    return Split(hi, lo)
+
+
+def _emit(out32=None, e1=None, e2=None):
+    """out32: fp32 NHWC tensor or None; e1/e2: (Split, styles [B,Cout] or None) pairs filled by the epilogue with
+    split(v * styles) -- the operand of the next convolution / the ToRGB layer."""
     e = _C.Emit()
     if out32 is not None:
         e.out32 = _p(out32)
         e.out32_ld = out32.stride(2)
+    if e1 is not None:
+        sp, st = e1
+        e.hi1, e.lo1, e.s1, e.c1_pad = _p(sp.hi), _p(sp.lo), _p(st), sp.C_pad
+    if e2 is not None:
+        sp, st = e2
+        e.hi2, e.lo2, e.s2, e.c2_pad = _p(sp.hi), _p(sp.lo), _p(st), sp.C_pad
     return e
 
 
@@ -335,7 +359,7 @@ def _noise_bstride(noise):
 
 
 def conv_same(hi, lo, pack, Cin_pad, out32, dcoef=None, noise=None, noise_strength=None, bias=None, act='linear',
-              gain=1.0, clamp=None, mode=1, impl=None):
+              gain=1.0, clamp=None, mode=1, impl=None, e1=None, e2=None):
     """k x k correlation, stride 1, 'same' padding (flip_weight=True branch of conv2d_resample, :134-136)."""
     st = _enter(hi)
     B, H, W, _ = hi.shape
@@ -355,7 +379,7 @@ def conv_same(hi, lo, pack, Cin_pad, out32, dcoef=None, noise=None, noise_streng
     p.dcoef, p.noise, p.noise_strength, p.bias = _p(dcoef), _p(noise), _p(noise_strength), _p(bias)
     p.noise_bstride = _noise_bstride(noise)
     p.act, p.alpha, p.gain, p.clamp = ACT_IDS[act], ACT_DEFAULTS[act][0], float(gain), float(-1 if clamp is None else clamp)
-    p.emit = _emit(out32)
+    p.emit = _emit(out32, e1, e2)
     _conv_call(p, st, impl)
 
 
@@ -402,17 +426,17 @@ def fir4x4_gain4(device):
     return f
 
 
-def fir_epilogue(raw, fir, out32, dcoef, noise, noise_strength, bias, act, gain, clamp):
+def fir_epilogue(raw, fir, out32, dcoef, noise, noise_strength, bias, act, gain, clamp, e1=None, e2=None):
     st = _enter(raw)
     B, RH, RW, Cc = raw.shape
-    _, OH, OW, _ = out32.shape
+    OH, OW = RH - 1, RW - 1
     p = _C.FirParams()
     p.raw, p.B, p.RH, p.RW, p.C = _p(raw), B, RH, RW, Cc
     p.fir, p.OH, p.OW = _p(fir), OH, OW
     p.dcoef, p.noise, p.noise_strength, p.bias = _p(dcoef), _p(noise), _p(noise_strength), _p(bias)
     p.noise_bstride = _noise_bstride(noise)
     p.act, p.alpha, p.gain, p.clamp = ACT_IDS[act], ACT_DEFAULTS[act][0], float(gain), float(-1 if clamp is None else clamp)
-    p.emit = _emit(out32)
+    p.emit = _emit(out32, e1, e2)
     _C.check(_C.lib().ia_fir_epilogue(C.byref(p), st), 'ia_fir_epilogue')
 
 

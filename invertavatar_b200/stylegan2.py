@@ -183,6 +183,31 @@ class SynthesisLayer(torch.nn.Module):
                             act_gain, act_clamp)
         return out
 
+    def run_split(self, a, dcoef, noise_mode='const', gain=1, want32=False, e1=None, e2=None):
+        """Fused-chain entry: ``a`` is an rt.Split already holding x*styles of THIS layer; the epilogue writes any of
+        the fp32 NHWC result (want32) and the pre-modulated operands of the consumers (e1/e2 = (Split, styles))."""
+        assert self.up in (1, 2)
+        if self.up == 2 and not _layer_filter_ok(self):
+            raise RuntimeError('SynthesisLayer: the fused up=2 path assumes the [1,3,3,1] resample filter')
+        B, H, W, _ = a.hi.shape
+        pack = self.pack()
+        assert a.C_pad == pack.Cin_pad and H * self.up == self.resolution
+        noise = _noise_for(self, noise_mode, B, a.hi.device)
+        strength = self.noise_strength if noise is not None else None
+        act_gain = self.act_gain * gain
+        act_clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
+        R = self.resolution
+        out = torch.empty((B, R, R, self.out_channels), dtype=torch.float32, device=a.hi.device) if want32 else None
+        if self.up == 1:
+            rt.conv_same(a.hi, a.lo, pack, pack.Cin_pad, out, dcoef=dcoef, noise=noise, noise_strength=strength, bias=self.bias,
+                         act=self.activation, gain=act_gain, clamp=act_clamp, mode=1, e1=e1, e2=e2)
+        else:
+            raw = torch.empty((B, 2 * H + 1, 2 * W + 1, self.out_channels), dtype=torch.float32, device=a.hi.device)
+            rt.conv_transpose_up2_raw(a.hi, a.lo, pack, pack.Cin_pad, raw)
+            rt.fir_epilogue(raw, rt.fir4x4_gain4(a.hi.device), out, dcoef, noise, strength, self.bias, self.activation,
+                            act_gain, act_clamp, e1=e1, e2=e2)
+        return out
+
     def forward(self, x, w, noise_mode='random', fused_modconv=True, gain=1):
         assert noise_mode in ['random', 'const', 'none']
         plan = _plan_for(self, [self.style_entry(0)])
@@ -239,6 +264,14 @@ class ToRGBLayer(torch.nn.Module):
         hi, lo = rt.modsplit(x, styles, C_pad=pack.Cin_pad)
         raw = torch.empty((B, H, W, self.out_channels), dtype=torch.float32, device=x.device)
         rt.conv_same(hi, lo, pack, pack.Cin_pad, raw, mode=0)
+        return rt.torgb_finish(raw, self.bias, self.conv_clamp, img_prev, out_nchw=out_nchw)
+
+    def run_split(self, a, img_prev=None, out_nchw=False):
+        """``a``: rt.Split holding x*styles of this layer (emitted by the producing convolution's epilogue)."""
+        B, H, W, _ = a.hi.shape
+        pack = self.pack()
+        raw = torch.empty((B, H, W, self.out_channels), dtype=torch.float32, device=a.hi.device)
+        rt.conv_same(a.hi, a.lo, pack, pack.Cin_pad, raw, mode=0)
         return rt.torgb_finish(raw, self.bias, self.conv_clamp, img_prev, out_nchw=out_nchw)
 
     def forward(self, x, w, fused_modconv=True):
@@ -322,6 +355,54 @@ class SynthesisBlock(torch.nn.Module):
             img = rt.to_nhwc(rt.upfirdn2d(rt.from_nhwc(img), self.resample_filter, up=(2, 2), padding=(2, 1, 2, 1), gain=4.0))
         return x, img
 
+    def layers(self):
+        """[(kind, layer)] in evaluation order."""
+        out = []
+        if self.in_channels != 0:
+            out.append(('conv', self.conv0))
+        out.append(('conv', self.conv1))
+        if hasattr(self, 'torgb'):
+            out.append(('torgb', self.torgb))
+        return out
+
+    def run_chain(self, a_in, img, styles, dcoefs, B, noise_mode='const', condition=None, want_x32=False, next_conv=None,
+                  next_styles=None, img_nchw=False, gain=1):
+        """Fused block: every convolution epilogue writes the operand(s) of its consumer(s) directly.
+        a_in: rt.Split for conv0 (None for the const block); styles/dcoefs: this block's entries in layers() order;
+        next_conv/next_styles: the following block's conv0 and its styles (None -> no operand emitted for it).
+        Returns (x32 or None, img, a_next or None)."""
+        dev = styles[0].device
+        R = self.resolution
+        i = 0
+        if self.in_channels == 0:
+            x0 = self.const.detach().permute(1, 2, 0).unsqueeze(0).expand(B, -1, -1, -1).contiguous()
+            hi, lo = rt.modsplit(x0, styles[0], C_pad=self.conv1.pack().Cin_pad)
+            a1 = rt.Split(hi, lo)
+        else:
+            a1 = rt.new_split(B, R, R, self.conv1.pack().Cin_pad, dev, C=self.conv1.in_channels)
+            if condition is None:
+                self.conv0.run_split(a_in, dcoefs[0], noise_mode=noise_mode, gain=gain, e1=(a1, styles[1]))
+            else:
+                # CS-SFT (networks_stylegan2_new.py:448-452) needs the fp32 activation: once per identity, not per frame
+                x = self.conv0.run_split(a_in, dcoefs[0], noise_mode=noise_mode, gain=gain, want32=True)
+                xv = rt.from_nhwc(x)
+                half = xv.shape[1] // 2
+                xv = torch.cat([xv[:, :half], xv[:, half:] * condition[0] + condition[1]], dim=1)
+                hi, lo = rt.modsplit(rt.to_nhwc(xv), styles[1], C_pad=self.conv1.pack().Cin_pad)
+                a1 = rt.Split(hi, lo)
+            i = 1
+        has_rgb = hasattr(self, 'torgb')
+        a_rgb = rt.new_split(B, R, R, self.torgb.pack().Cin_pad, dev, C=self.torgb.in_channels) if has_rgb else None
+        a_next = rt.new_split(B, R, R, next_conv.pack().Cin_pad, dev, C=next_conv.in_channels) if next_conv is not None else None
+        x32 = self.conv1.run_split(a1, dcoefs[i], noise_mode=noise_mode, gain=gain, want32=want_x32,
+                                   e1=(a_next, next_styles) if a_next is not None else None,
+                                   e2=(a_rgb, styles[i + 1]) if has_rgb else None)
+        if has_rgb:
+            img = self.torgb.run_split(a_rgb, img_prev=img, out_nchw=img_nchw)
+        elif img is not None:
+            img = rt.to_nhwc(rt.upfirdn2d(rt.from_nhwc(img), self.resample_filter, up=(2, 2), padding=(2, 1, 2, 1), gain=4.0))
+        return x32, img, a_next
+
     def forward(self, x, img, ws, condition=None, force_fp32=False, fused_modconv=None, update_emas=False, **layer_kwargs):
         assert ws.shape[1] == self.num_conv + self.num_torgb and ws.shape[2] == self.w_dim
         noise_mode = layer_kwargs.get('noise_mode', 'random')
@@ -373,35 +454,53 @@ class SynthesisNetwork(torch.nn.Module):
         assert ws.shape[1] == self.num_ws and ws.shape[2] == self.w_dim, (ws.shape, self.num_ws)
         noise_mode = block_kwargs.get('noise_mode', 'random')
         ws = ws.to(torch.float32)
-        x = img = None
+        B = ws.shape[0]
+        blocks = [getattr(self, f'b{res}') for res in self.block_resolutions]
+        # one style/demod pass for the whole network (2 launches instead of 2 per block)
+        entries, spans, w_idx = [], [], 0
+        for block in blocks:
+            lay = block.layers()
+            first = len(entries)
+            for j, (kind, layer) in enumerate(lay):
+                entries.append(layer.style_entry(w_idx + j))
+            spans.append((first, len(entries)))
+            w_idx += block.num_conv
+        styles, dcoefs = _plan_for(self, entries).run(ws)
         x_list, out_imgs = [], []
         start_layer = int(np.log2(out_res[0])) - 2
         end_layer = (self.img_resolution_log2 - 2) if len(out_res) == 1 else (int(np.log2(out_res[1])) - 2)
-        pending_cond = None     # (cond_nhwc, alpha[B,H,W]) to blend into x inside the next block's operand preparation
-        w_idx = 0
-        for index, res in enumerate(self.block_resolutions):
-            block = getattr(self, f'b{res}')
-            cur_ws = ws.narrow(1, w_idx, block.num_conv + block.num_torgb)
-            w_idx += block.num_conv
+        a = img = None
+        for index, (res, block) in enumerate(zip(self.block_resolutions, blocks)):
+            lo_i, hi_i = spans[index]
             cond_feat = feat_conditions[res] if (feat_conditions is not None and res in feat_conditions.keys()) else None
-            cnd, cal = pending_cond if pending_cond is not None else (None, None)
-            pending_cond = None
-            x, img = block.run_nhwc(x, img, cur_ws, condition=cond_feat, noise_mode=noise_mode, cond=cnd, cond_alpha=cal)
-            if index >= start_layer:
+            emitting = index >= start_layer
+            # the blend x <- cond*alpha + x*(1-alpha) (:538-540) happens between this block and the next one: then the next
+            # operand cannot come straight out of this block's epilogue
+            blend_next = cond_list is not None and emitting and index < end_layer
+            want_x32 = (emitting and (return_list or return_imgs)) or blend_next
+            has_next = index + 1 < len(blocks)
+            next_conv = blocks[index + 1].conv0 if (has_next and not blend_next) else None
+            next_styles = styles[spans[index + 1][0]] if next_conv is not None else None
+            x32, img, a = block.run_chain(a, img, styles[lo_i:hi_i], dcoefs[lo_i:hi_i], B, noise_mode=noise_mode, condition=cond_feat,
+                                          want_x32=want_x32, next_conv=next_conv, next_styles=next_styles)
+            if emitting:
                 if return_list:
                     if index == start_layer:
                         x_list.append(rt.from_nhwc(img))
-                    x_list.append(rt.from_nhwc(x))
+                    x_list.append(rt.from_nhwc(x32))
                 if return_imgs:
                     if index == start_layer:
-                        out_imgs.append(rt.from_nhwc(x))
+                        out_imgs.append(rt.from_nhwc(x32))
                     out_imgs.append(rt.from_nhwc(img))
                 if cond_list is not None:
                     if index == start_layer:
                         c_img, c_a = _split_cond(cond_list[0])
                         img = rt.lerp_alpha(c_img, img, c_a)
-                    if index < end_layer:
-                        pending_cond = _split_cond(cond_list[1 + index - start_layer])
+                    if blend_next and has_next:
+                        cnd, cal = _split_cond(cond_list[1 + index - start_layer])
+                        nxt = blocks[index + 1].conv0
+                        hi, lo = rt.modsplit(x32, styles[spans[index + 1][0]], cond=cnd, cond_alpha=cal, C_pad=nxt.pack().Cin_pad)
+                        a = rt.Split(hi, lo)
         if return_list:
             x_list.append(rt.from_nhwc(img))
             return x_list

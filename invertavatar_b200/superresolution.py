@@ -6,7 +6,7 @@ import torch
 
 from . import persistence
 from . import runtime as rt
-from .stylegan2 import SynthesisBlock
+from .stylegan2 import SynthesisBlock, _plan_for
 
 
 class _SuperresolutionBase(torch.nn.Module):
@@ -27,8 +27,16 @@ class _SuperresolutionBase(torch.nn.Module):
         ws = ws[:, -1:, :].repeat(1, 3, 1)
         noise_mode = block_kwargs.get('noise_mode', 'random')
         rgb, x = self._prepare(rgb, x)
-        x, rgb = self.block0.run_nhwc(x, rgb, ws, noise_mode=noise_mode)
-        x, rgb = self.block1.run_nhwc(x, rgb, ws, noise_mode=noise_mode, img_nchw=True)
+        B = x.shape[0]
+        b0, b1 = self.block0, self.block1
+        entries = [layer.style_entry(j) for j, (_, layer) in enumerate(b0.layers())] + \
+                  [layer.style_entry(j) for j, (_, layer) in enumerate(b1.layers())]
+        styles, dcoefs = _plan_for(self, entries).run(ws.to(torch.float32))
+        n0 = len(b0.layers())
+        hi, lo = rt.modsplit(x, styles[0], C_pad=b0.conv0.pack().Cin_pad)
+        _, rgb, a = b0.run_chain(rt.Split(hi, lo), rgb, styles[:n0], dcoefs[:n0], B, noise_mode=noise_mode, next_conv=b1.conv0,
+                                 next_styles=styles[n0])
+        _, rgb, _ = b1.run_chain(a, rgb, styles[n0:], dcoefs[n0:], B, noise_mode=noise_mode, img_nchw=True)
         return rgb
 
 

@@ -131,3 +131,35 @@ def test_tc_matches_simt_large():
     rt.set_conv_impl('tc')
     b = L(x, w, noise_mode='const')
     assert maxerr(a, b) <= TOL * max(1.0, float(a.abs().max()))
+
+
+def _small_network(seed=5):
+    torch.manual_seed(seed)
+    net = sg.SynthesisNetwork(w_dim=64, img_resolution=32, img_channels=8, channel_base=1280, channel_max=40, num_fp16_res=0,
+                              conv_clamp=None).requires_grad_(False)
+    for n, p in net.named_parameters():
+        if n.endswith('noise_strength'):
+            p.fill_(0.2)
+        if n.endswith('.bias') and 'affine' not in n:
+            p.copy_(torch.randn_like(p) * 0.1)
+    return net
+
+
+def test_synthesis_network_fused_chain(impl):
+    """Whole-network fused chain (epilogues emit the next layer's operands) with channel counts that need zero padding
+    (40 -> 64), return_list and cond_list semantics of networks_stylegan2_new.py:509-548."""
+    net = _small_network()
+    g = torch.Generator().manual_seed(6)
+    ws = torch.randn(3, net.num_ws, 64, generator=g)
+    sd = net.state_dict()
+    ref = o_sg.synthesis_network(sd, ws, return_list=True, out_res=(8, 32))
+    net = net.to(DEV)
+    got = net(ws.to(DEV), return_list=True, out_res=(8, 32), noise_mode='const')
+    assert len(got) == len(ref)
+    for a, b in zip(got, ref):
+        assert maxerr(a, b) <= TOL * max(1.0, float(b.abs().max()))
+    # cond_list: img blended at res 8, x blended at res 8 and 16 (index < end_layer)
+    conds = [torch.cat([torch.randn(3, c, r, r, generator=g), torch.rand(3, 1, r, r, generator=g)], 1) for (c, r) in ((8, 8), (40, 8), (40, 16))]
+    ref = o_sg.synthesis_network(sd, ws, cond_list=conds, return_list=False, out_res=(8, 32))
+    got = net(ws.to(DEV), cond_list=[c.to(DEV) for c in conds], return_list=False, out_res=(8, 32), noise_mode='const')
+    assert maxerr(got, ref) <= TOL * max(1.0, float(ref.abs().max()))
