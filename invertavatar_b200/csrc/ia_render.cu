@@ -19,35 +19,75 @@ namespace {
 constexpr int kHidden = 64;
 constexpr int kFeat = 32;
 constexpr int kOut = 33;
-constexpr int kRowLd = 33;          // padded row of the per-sample feature/colour scratch
+constexpr int kRowLd = 36;          // colour scratch row pitch: even (float2 stores) and 4g+2t bank spread -> conflict-free
 constexpr int kWarpsPerCta = 4;
 constexpr int kMaxS = 192;          // Dc + Df
+constexpr int kOutPad = 40;         // layer-2 columns: 0..31 = rgb, 32 = sigma, 33..39 = zero padding (5 n-tiles of 8)
 
-// decoder weights with the FullyConnectedLayer runtime gains folded in (networks_stylegan2.py:111-115)
-__constant__ float c_w1[kHidden * kFeat];   // [j][i]
-__constant__ float c_b1[kHidden];
-__constant__ float c_w2t[kHidden * kOut];   // [j][k]  (transposed second layer)
-__constant__ float c_b2[kOut];
-__device__ float g_dec_stage[kHidden * kFeat + kHidden + kHidden * kOut + kOut];
+// OSG decoder in mma.sync.m16n8k16 B-fragment order, fp16 hi/lo split (3-term product hi*hi + hi*lo + lo*hi with fp32
+// accumulation reproduces the fp32 MLP to ~1e-6), FullyConnectedLayer runtime gains folded in
+// (networks_stylegan2.py:111-115).  Built by decoder_stage_kernel, copied to shared memory by every render CTA.
+//   w1f[((nt*2 + ks)*2 + hl)*32 + lane] : layer 1, n-tile nt (8 hidden units), k-step ks (16 input channels)
+//   w2f[((nt*4 + ks)*2 + hl)*32 + lane] : layer 2, n-tile nt (8 outputs),     k-step ks (16 hidden units)
+// Input channel order inside a k-step follows the gather: lane quad member t owns physical channels 4t..4t+3 (k-step 0)
+// and 16+4t..16+4t+3 (k-step 1), which sit at logical k positions {2t, 2t+1, 2t+8, 2t+9}.
+struct DecoderFrags {
+    uint2 w1f[8 * 2 * 2 * 32];
+    uint2 w2f[5 * 4 * 2 * 32];
+    float b1[kHidden];
+    float b2[kOutPad];
+};
+__device__ DecoderFrags g_dec;
+
+__device__ __forceinline__ uint32_t pack_half2(__half lo16, __half hi16) {
+    return (uint32_t)__half_as_ushort(lo16) | ((uint32_t)__half_as_ushort(hi16) << 16);
+}
+__device__ __forceinline__ void split_half(float v, __half& hi, __half& lo) {
+    hi = __float2half_rn(v);
+    lo = __float2half_rn(v - __half2float(hi));
+}
+__device__ __forceinline__ int phys_channel(int k) {   // logical layer-1 k index -> physical feature channel
+    const int ks = k >> 4, r = k & 15;
+    return (r < 8) ? 16 * ks + 4 * (r >> 1) + (r & 1) : 16 * ks + 4 * ((r - 8) >> 1) + 2 + ((r - 8) & 1);
+}
 
 __global__ void decoder_stage_kernel(const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
                                      const float* __restrict__ b2) {
     const float g1 = 1.0f / sqrtf((float)kFeat), g2 = 1.0f / sqrtf((float)kHidden);
-    float* s_w1 = g_dec_stage;
-    float* s_b1 = s_w1 + kHidden * kFeat;
-    float* s_w2t = s_b1 + kHidden;
-    float* s_b2 = s_w2t + kHidden * kOut;
-    for (int i = threadIdx.x; i < kHidden * kFeat; i += blockDim.x) s_w1[i] = w1[i] * g1;
-    for (int i = threadIdx.x; i < kHidden; i += blockDim.x) s_b1[i] = b1[i];
-    for (int i = threadIdx.x; i < kHidden * kOut; i += blockDim.x) {
-        int j = i / kOut, k = i % kOut;
-        s_w2t[i] = w2[k * kHidden + j] * g2;
+    // layer 1: B[k][n] = W1[n][phys(k)] * g1
+    for (int i = threadIdx.x; i < 8 * 2 * 32; i += blockDim.x) {
+        const int lane = i & 31, ks = (i >> 5) & 1, nt = i >> 6;
+        const int g = lane >> 2, t = lane & 3, n = nt * 8 + g;
+        float v[4];
+        const int kk[4] = {16 * ks + 2 * t, 16 * ks + 2 * t + 1, 16 * ks + 2 * t + 8, 16 * ks + 2 * t + 9};
+        __half h[4], l[4];
+        for (int q = 0; q < 4; ++q) { v[q] = w1[n * kFeat + phys_channel(kk[q])] * g1; split_half(v[q], h[q], l[q]); }
+        g_dec.w1f[((nt * 2 + ks) * 2 + 0) * 32 + lane] = make_uint2(pack_half2(h[0], h[1]), pack_half2(h[2], h[3]));
+        g_dec.w1f[((nt * 2 + ks) * 2 + 1) * 32 + lane] = make_uint2(pack_half2(l[0], l[1]), pack_half2(l[2], l[3]));
     }
-    for (int i = threadIdx.x; i < kOut; i += blockDim.x) s_b2[i] = b2[i];
+    // layer 2: column o' < 32 -> rgb channel o' (W2 row 1+o'), o' == 32 -> sigma (W2 row 0), else zero
+    for (int i = threadIdx.x; i < 5 * 4 * 32; i += blockDim.x) {
+        const int lane = i & 31, ks = (i >> 5) & 3, nt = i >> 7;
+        const int g = lane >> 2, t = lane & 3, col = nt * 8 + g;
+        const int row = col < 32 ? col + 1 : (col == 32 ? 0 : -1);
+        const int kk[4] = {16 * ks + 2 * t, 16 * ks + 2 * t + 1, 16 * ks + 2 * t + 8, 16 * ks + 2 * t + 9};
+        __half h[4], l[4];
+        for (int q = 0; q < 4; ++q) { const float v = row >= 0 ? w2[row * kHidden + kk[q]] * g2 : 0.f; split_half(v, h[q], l[q]); }
+        g_dec.w2f[((nt * 4 + ks) * 2 + 0) * 32 + lane] = make_uint2(pack_half2(h[0], h[1]), pack_half2(h[2], h[3]));
+        g_dec.w2f[((nt * 4 + ks) * 2 + 1) * 32 + lane] = make_uint2(pack_half2(l[0], l[1]), pack_half2(l[2], l[3]));
+    }
+    for (int i = threadIdx.x; i < kHidden; i += blockDim.x) g_dec.b1[i] = b1[i];
+    for (int i = threadIdx.x; i < kOutPad; i += blockDim.x) g_dec.b2[i] = i < 32 ? b2[i + 1] : (i == 32 ? b2[0] : 0.f);
 }
 
 __device__ __forceinline__ float softplus_fast(float x) { return x > 20.f ? x : __logf(1.f + __expf(x)); }
 __device__ __forceinline__ float softplus_acc(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+
+__device__ __forceinline__ void mma_f16(float (&c)[4], const uint32_t (&a)[4], const uint2 b) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y));
+}
 
 // torch.linspace(start, end, steps) for float32 (ATen RangeFactories: symmetric around the midpoint)
 __device__ __forceinline__ float linspace_at(float start, float end, int steps, int i) {
@@ -81,9 +121,10 @@ __device__ __forceinline__ Ray make_ray(const float* __restrict__ cam, int res, 
     return r;
 }
 
-// One bilinear tap set of a plane for the 8-lane group: accumulate 4 channels (sub*4..sub*4+3).
-__device__ __forceinline__ void plane_gather(const float* __restrict__ plane_base, int64_t px_ld, int PH, int PW, float gx, float gy,
-                                             int sub, float acc[4]) {
+// Bilinear taps of one plane for this lane's 8 channels (physical 4t..4t+3 and 16+4t..16+4t+3) of one sample:
+// F.grid_sample(bilinear, zeros, align_corners=False) arithmetic, accumulated nw, ne, sw, se.
+__device__ __forceinline__ void plane_gather8(const float* __restrict__ plane_base, int64_t px_ld, int PH, int PW, float gx, float gy,
+                                              float acc[8]) {
     const float ix = ((gx + 1.f) * PW - 1.f) / 2.f;
     const float iy = ((gy + 1.f) * PH - 1.f) / 2.f;
     const float fx = floorf(ix), fy = floorf(iy);
@@ -93,59 +134,123 @@ __device__ __forceinline__ void plane_gather(const float* __restrict__ plane_bas
     const float wsw = ((float)x1 - ix) * (iy - (float)y0);
     const float wse = (ix - (float)x0) * (iy - (float)y0);
     const bool vx0 = x0 >= 0 && x0 < PW, vx1 = x1 >= 0 && x1 < PW, vy0 = y0 >= 0 && y0 < PH, vy1 = y1 >= 0 && y1 < PH;
-    float s[4] = {0.f, 0.f, 0.f, 0.f};
-    const float* b = plane_base + sub * 4;
-    if (vy0 && vx0) { float4 t = __ldg(reinterpret_cast<const float4*>(b + ((int64_t)y0 * PW + x0) * px_ld)); s[0] += t.x * wnw; s[1] += t.y * wnw; s[2] += t.z * wnw; s[3] += t.w * wnw; }
-    if (vy0 && vx1) { float4 t = __ldg(reinterpret_cast<const float4*>(b + ((int64_t)y0 * PW + x1) * px_ld)); s[0] += t.x * wne; s[1] += t.y * wne; s[2] += t.z * wne; s[3] += t.w * wne; }
-    if (vy1 && vx0) { float4 t = __ldg(reinterpret_cast<const float4*>(b + ((int64_t)y1 * PW + x0) * px_ld)); s[0] += t.x * wsw; s[1] += t.y * wsw; s[2] += t.z * wsw; s[3] += t.w * wsw; }
-    if (vy1 && vx1) { float4 t = __ldg(reinterpret_cast<const float4*>(b + ((int64_t)y1 * PW + x1) * px_ld)); s[0] += t.x * wse; s[1] += t.y * wse; s[2] += t.z * wse; s[3] += t.w * wse; }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) acc[k] += s[k];
-}
-
-// Gather the mean tri-plane feature of samples [s0, s0+n) of this warp's ray into rows of `col`.
-__device__ __forceinline__ void gather_pass(const ia_render_params& p, const float* __restrict__ planes_b, const Ray& r,
-                                            const float* dep, float* col, int s0, int n, int lane) {
-    const int grp = lane >> 3, sub = lane & 7;
-    const float scale = 2.0f / p.box_warp;
-    for (int s = grp; s < n; s += 4) {
-        const float t = dep[s0 + s];
-        const float qx = (r.ox + t * r.dx) * scale;
-        const float qy = (r.oy + t * r.dy) * scale;
-        const float qz = (r.oz + t * r.dz) * scale;
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        plane_gather(planes_b + 0, p.plane_px_ld, p.PH, p.PW, qx, qy, sub, acc);    // plane 0: (x, y)
-        plane_gather(planes_b + 32, p.plane_px_ld, p.PH, p.PW, qx, qz, sub, acc);   // plane 1: (x, z)
-        plane_gather(planes_b + 64, p.plane_px_ld, p.PH, p.PW, qz, qx, sub, acc);   // plane 2: (z, x)
-        float* o = col + (s0 + s) * kRowLd + sub * 4;
-        o[0] = acc[0] / 3.0f; o[1] = acc[1] / 3.0f; o[2] = acc[2] / 3.0f; o[3] = acc[3] / 3.0f;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    // issue all eight 16-byte loads before using any (memory-level parallelism)
+    const float* p00 = plane_base + ((int64_t)y0 * PW + x0) * px_ld;
+    const float* p01 = plane_base + ((int64_t)y0 * PW + x1) * px_ld;
+    const float* p10 = plane_base + ((int64_t)y1 * PW + x0) * px_ld;
+    const float* p11 = plane_base + ((int64_t)y1 * PW + x1) * px_ld;
+    const bool v00 = vy0 && vx0, v01 = vy0 && vx1, v10 = vy1 && vx0, v11 = vy1 && vx1;
+    const float4 a0 = v00 ? __ldg(reinterpret_cast<const float4*>(p00)) : z, a1 = v00 ? __ldg(reinterpret_cast<const float4*>(p00 + 16)) : z;
+    const float4 b0 = v01 ? __ldg(reinterpret_cast<const float4*>(p01)) : z, b1 = v01 ? __ldg(reinterpret_cast<const float4*>(p01 + 16)) : z;
+    const float4 c0 = v10 ? __ldg(reinterpret_cast<const float4*>(p10)) : z, c1 = v10 ? __ldg(reinterpret_cast<const float4*>(p10 + 16)) : z;
+    const float4 d0 = v11 ? __ldg(reinterpret_cast<const float4*>(p11)) : z, d1 = v11 ? __ldg(reinterpret_cast<const float4*>(p11 + 16)) : z;
+    float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#define IA_TAP(ok_, lo4_, hi4_, wt_)                                                                          \
+    if (ok_) {                                                                                                    \
+        s[0] += lo4_.x * wt_; s[1] += lo4_.y * wt_; s[2] += lo4_.z * wt_; s[3] += lo4_.w * wt_;                   \
+        s[4] += hi4_.x * wt_; s[5] += hi4_.y * wt_; s[6] += hi4_.z * wt_; s[7] += hi4_.w * wt_;                   \
     }
+    IA_TAP(v00, a0, a1, wnw) IA_TAP(v01, b0, b1, wne) IA_TAP(v10, c0, c1, wsw) IA_TAP(v11, d0, d1, wse)
+#undef IA_TAP
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] += s[k];
 }
 
-// OSG decoder on samples [s0, s0+n): one sample per lane; features in, colours out (same rows), sigma to sig[].
-__device__ __forceinline__ void mlp_pass(float* col, float* sig, int s0, int n, int lane) {
-    for (int s = lane; s < n; s += 32) {
-        float* row = col + (s0 + s) * kRowLd;
-        float x[kFeat];
+// Tri-plane gather + OSG decoder for samples [s0, s0+n) of this warp's ray, 16 samples per step on the tensor cores
+// (mma.sync m16n8k16, fp16 hi/lo split operands, fp32 accumulate).  Lane (g = lane/4, t = lane%4) gathers 8 channels of
+// samples 16m+g and 16m+g+8 straight into its A fragment; layer 1's C fragments become layer 2's A fragments in
+// registers.  Colours go to col[sample][channel], sigma to sig[sample].
+__device__ __forceinline__ void gather_mlp_pass(const ia_render_params& p, const float* __restrict__ planes_b, const Ray& r,
+                                                const float* dep, float* col, float* sig, int s0, int n, int lane,
+                                                const DecoderFrags* __restrict__ dec) {
+    const int g = lane >> 2, t = lane & 3;
+    const float scale = 2.0f / p.box_warp;
+    const float* pb = planes_b + 4 * t;
+    for (int m0 = 0; m0 < n; m0 += 16) {
+        float feat[2][8];
 #pragma unroll
-        for (int i = 0; i < kFeat; ++i) x[i] = row[i];
-        float out[kOut];
+        for (int rr = 0; rr < 2; ++rr) {
+            const int sidx = min(m0 + g + 8 * rr, n - 1);      // rows past the end repeat the last sample; results are dropped
+            const float tt = dep[s0 + sidx];
+            const float qx = (r.ox + tt * r.dx) * scale;
+            const float qy = (r.oy + tt * r.dy) * scale;
+            const float qz = (r.oz + tt * r.dz) * scale;
+            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            plane_gather8(pb + 0, p.plane_px_ld, p.PH, p.PW, qx, qy, acc);    // plane 0: (x, y)
+            plane_gather8(pb + 32, p.plane_px_ld, p.PH, p.PW, qx, qz, acc);   // plane 1: (x, z)
+            plane_gather8(pb + 64, p.plane_px_ld, p.PH, p.PW, qz, qx, acc);   // plane 2: (z, x)
 #pragma unroll
-        for (int k = 0; k < kOut; ++k) out[k] = c_b2[k];
-#pragma unroll
-        for (int j = 0; j < kHidden; ++j) {
-            float h = c_b1[j];
-#pragma unroll
-            for (int i = 0; i < kFeat; ++i) h = fmaf(x[i], c_w1[j * kFeat + i], h);
-            const float a = softplus_fast(h);
-#pragma unroll
-            for (int k = 0; k < kOut; ++k) out[k] = fmaf(a, c_w2t[j * kOut + k], out[k]);
+            for (int k = 0; k < 8; ++k) feat[rr][k] = acc[k] / 3.0f;           // mean over the three planes
         }
-        sig[s0 + s] = out[0];
+        // ---- layer 1: [16 x 32] x [32 x 64] ----
+        uint32_t ah[2][4], al[2][4];
 #pragma unroll
-        for (int k = 0; k < kFeat; ++k) {
-            const float sg = 1.0f / (1.0f + __expf(-out[1 + k]));
-            row[k] = sg * (1.0f + 2.0f * 0.001f) - 0.001f;
+        for (int ks = 0; ks < 2; ++ks) {
+            __half h[2][4], l[2][4];
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) split_half(feat[rr][4 * ks + q], h[rr][q], l[rr][q]);
+            ah[ks][0] = pack_half2(h[0][0], h[0][1]); ah[ks][1] = pack_half2(h[1][0], h[1][1]);
+            ah[ks][2] = pack_half2(h[0][2], h[0][3]); ah[ks][3] = pack_half2(h[1][2], h[1][3]);
+            al[ks][0] = pack_half2(l[0][0], l[0][1]); al[ks][1] = pack_half2(l[1][0], l[1][1]);
+            al[ks][2] = pack_half2(l[0][2], l[0][3]); al[ks][3] = pack_half2(l[1][2], l[1][3]);
+        }
+        float hid[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const float bb0 = dec->b1[nt * 8 + 2 * t], bb1 = dec->b1[nt * 8 + 2 * t + 1];
+            float c[4] = {bb0, bb1, bb0, bb1};
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+                const uint2 bh = dec->w1f[((nt * 2 + ks) * 2 + 0) * 32 + lane];
+                const uint2 bl = dec->w1f[((nt * 2 + ks) * 2 + 1) * 32 + lane];
+                mma_f16(c, ah[ks], bh);
+                mma_f16(c, ah[ks], bl);
+                mma_f16(c, al[ks], bh);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) hid[nt][q] = softplus_fast(c[q]);
+        }
+        // ---- layer 2: [16 x 64] x [64 x 40] ----
+        float out[5][4];
+#pragma unroll
+        for (int nt = 0; nt < 5; ++nt) {
+            const float bb0 = dec->b2[nt * 8 + 2 * t], bb1 = dec->b2[nt * 8 + 2 * t + 1];
+            out[nt][0] = bb0; out[nt][1] = bb1; out[nt][2] = bb0; out[nt][3] = bb1;
+        }
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            __half h[8], l[8];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { split_half(hid[2 * ks][q], h[q], l[q]); split_half(hid[2 * ks + 1][q], h[4 + q], l[4 + q]); }
+            const uint32_t a2h[4] = {pack_half2(h[0], h[1]), pack_half2(h[2], h[3]), pack_half2(h[4], h[5]), pack_half2(h[6], h[7])};
+            const uint32_t a2l[4] = {pack_half2(l[0], l[1]), pack_half2(l[2], l[3]), pack_half2(l[4], l[5]), pack_half2(l[6], l[7])};
+#pragma unroll
+            for (int nt = 0; nt < 5; ++nt) {
+                const uint2 bh = dec->w2f[((nt * 4 + ks) * 2 + 0) * 32 + lane];
+                const uint2 bl = dec->w2f[((nt * 4 + ks) * 2 + 1) * 32 + lane];
+                mma_f16(out[nt], a2h, bh);
+                mma_f16(out[nt], a2h, bl);
+                mma_f16(out[nt], a2l, bh);
+            }
+        }
+        // ---- write back: rows g (c0,c1) and g+8 (c2,c3); columns nt*8 + 2t, +1 ----
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            const int sidx = m0 + g + 8 * rr;
+            if (sidx < n) {
+                float* row = col + (s0 + sidx) * kRowLd;
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    const float v0 = 1.0f / (1.0f + __expf(-out[nt][2 * rr + 0]));
+                    const float v1 = 1.0f / (1.0f + __expf(-out[nt][2 * rr + 1]));
+                    *reinterpret_cast<float2*>(row + nt * 8 + 2 * t) =
+                        make_float2(v0 * (1.0f + 2.0f * 0.001f) - 0.001f, v1 * (1.0f + 2.0f * 0.001f) - 0.001f);
+                }
+                if (t == 0) sig[s0 + sidx] = out[4][2 * rr];
+            }
         }
     }
 }
@@ -185,12 +290,19 @@ __device__ __forceinline__ void march_weights(const float* d, const float* sg, f
 }
 
 __global__ void __launch_bounds__(kWarpsPerCta * 32) render_kernel(const ia_render_params p) {
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = p.Dc + p.Df;
-    // per-warp scratch
-    const int per_warp = S * kRowLd + 6 * S + 2 * (p.Dc + 2);
-    float* base = smem + (size_t)warp * per_warp;
+    // decoder fragments (shared by the CTA), then per-warp scratch
+    DecoderFrags* dec = reinterpret_cast<DecoderFrags*>(smem);
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(&g_dec);
+        uint4* dst = reinterpret_cast<uint4*>(dec);
+        for (int i = threadIdx.x; i < (int)(sizeof(DecoderFrags) / 16); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const int per_warp = S * kRowLd + 6 * S + 2 * (p.Dc + 2) + ((S * kRowLd + 6 * S + 2 * (p.Dc + 2)) & 1);
+    float* base = smem + sizeof(DecoderFrags) / 4 + (size_t)warp * per_warp;
     float* col = base;                      // [S][33] features -> colours
     float* dep = col + S * kRowLd;          // [S] depths (coarse then fine)
     float* sig = dep + S;                   // [S]
@@ -227,9 +339,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) render_kernel(const ia_rend
             dmin = fminf(dmin, t); dmax = fmaxf(dmax, t);
         }
         __syncwarp();
-        gather_pass(p, planes_b, r, dep, col, 0, p.Dc, lane);
-        __syncwarp();
-        mlp_pass(col, sig, 0, p.Dc, lane);
+        gather_mlp_pass(p, planes_b, r, dep, col, sig, 0, p.Dc, lane, dec);
         __syncwarp();
 
         int n_all = p.Dc;
@@ -250,12 +360,25 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) render_kernel(const ia_rend
                 sd[k] = ((m0 + m1) * 0.5f + 0.01f) + 1e-5f;   // pdf numerators (sample_pdf adds eps)
             }
             __syncwarp();
-            if (lane == 0) {
+            {   // pdf = w / sum(w); cdf = [0, cumsum(pdf)]  (warp-parallel sum and scan, 32 bins per round)
                 float tot = 0.f;
-                for (int k = 0; k < nb; ++k) tot += sd[k];
-                float c = 0.f;
-                cdf[0] = 0.f;
-                for (int k = 0; k < nb; ++k) { c += sd[k] / tot; cdf[k + 1] = c; }
+                for (int k = lane; k < nb; k += 32) tot += sd[k];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+                float carry_c = 0.f;
+                if (lane == 0) cdf[0] = 0.f;
+                for (int base_k = 0; base_k < nb; base_k += 32) {
+                    const int k = base_k + lane;
+                    float v = (k < nb) ? sd[k] / tot : 0.f;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const float up = __shfl_up_sync(0xffffffffu, v, o);
+                        if (lane >= o) v += up;
+                    }
+                    v += carry_c;
+                    if (k < nb) cdf[k + 1] = v;
+                    carry_c = __shfl_sync(0xffffffffu, v, 31);
+                }
             }
             __syncwarp();
             for (int f = lane; f < p.Df; f += 32) {
@@ -273,9 +396,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) render_kernel(const ia_rend
                 dmin = fminf(dmin, t); dmax = fmaxf(dmax, t);
             }
             __syncwarp();
-            gather_pass(p, planes_b, r, dep, col, p.Dc, p.Df, lane);
-            __syncwarp();
-            mlp_pass(col, sig, p.Dc, p.Df, lane);
+            gather_mlp_pass(p, planes_b, r, dep, col, sig, p.Dc, p.Df, lane, dec);
             __syncwarp();
             // ---- merge: stable rank of every sample among all S (unify_samples, renderer.py:372-382) ----
             for (int s = lane; s < S; s += 32) {
@@ -417,22 +538,15 @@ extern "C" int ia_render(const ia_render_params* p, void* stream) {
     ia::prof_begin("ia_render(decoder_stage)", st);
     decoder_stage_kernel<<<1, 256, 0, st>>>(p->w1, p->b1, p->w2, p->b2);
     IA_LAUNCH_CHECK("ia_render(decoder_stage)");
-    void* stage = nullptr;
-    cudaError_t e = cudaGetSymbolAddress(&stage, g_dec_stage);
-    IA_CHECK(e == cudaSuccess, "ia_render: cudaGetSymbolAddress: %s", cudaGetErrorString(e));
-    const float* sp = static_cast<const float*>(stage);
-    e = cudaMemcpyToSymbolAsync(c_w1, sp, sizeof(float) * kHidden * kFeat, 0, cudaMemcpyDeviceToDevice, st);
-    if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_b1, sp + kHidden * kFeat, sizeof(float) * kHidden, 0, cudaMemcpyDeviceToDevice, st);
-    if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_w2t, sp + kHidden * kFeat + kHidden, sizeof(float) * kHidden * kOut, 0, cudaMemcpyDeviceToDevice, st);
-    if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_b2, sp + kHidden * kFeat + kHidden + kHidden * kOut, sizeof(float) * kOut, 0, cudaMemcpyDeviceToDevice, st);
-    IA_CHECK(e == cudaSuccess, "ia_render: constant upload: %s", cudaGetErrorString(e));
+    cudaError_t e = cudaSuccess;
     ia::prof_begin("ia_render(minmax_init)", st);
     minmax_init_kernel<<<1, 32, 0, st>>>(p->depth_minmax);
     IA_LAUNCH_CHECK("ia_render(minmax_init)");
 
     const int S = p->Dc + p->Df;
-    const size_t per_warp = (size_t)S * kRowLd + 6 * (size_t)S + 2 * (size_t)(p->Dc + 2);
-    const size_t smem = per_warp * kWarpsPerCta * sizeof(float);
+    size_t per_warp = (size_t)S * kRowLd + 6 * (size_t)S + 2 * (size_t)(p->Dc + 2);
+    per_warp += per_warp & 1;   // keep every warp's scratch 8-byte aligned (float2 colour stores)
+    const size_t smem = sizeof(DecoderFrags) + per_warp * kWarpsPerCta * sizeof(float);
     IA_CHECK(smem <= 227 * 1024, "ia_render: shared memory request too large");
     e = cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     IA_CHECK(e == cudaSuccess, "ia_render: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
