@@ -16,6 +16,7 @@
 // torch_utils/ops/conv2d_gradfix.py:127-129 <- conv2d_resample.py:31-43 <- modulated_conv2d
 // (training_avatar_texture/networks_stylegan2_new.py:34-91) together with the bias_act that follows it.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "ia_common.cuh"
 
@@ -325,6 +326,363 @@ void choose_patch(int B, int GH, int GW, int& nb, int& th, int& tw) {
     }
 }
 
+
+// =============================================================================================================
+// v2: persistent, 256-pixel tiles, double-buffered TMEM accumulators, row-halo reuse of the activation tile
+// =============================================================================================================
+// One CTA per SM loops over (pixel tile, cout tile) pairs.  A pixel tile is TH x tw pixels of one image (256 pixels =
+// two M=128 halves sharing every weight tile).  Per 32/64-channel k-block and per horizontal tap offset dx the activation
+// tile is loaded ONCE with its vertical halo ((TH+halo) x tw pixels); the taps (dy, dx) of that column group read it
+// through UMMA descriptors whose start address is shifted by (dy - dy_min) * tw rows -- a multiple of the 8-row swizzle
+// atom because tw is a multiple of 8.  Weights stream through their own ring, one (tap, k-block) tile per slot.
+// The accumulators of tile i are drained by the epilogue warps while the MMA warp already works on tile i+1.
+template <int BK> struct SwzTraits;
+template <> struct SwzTraits<64> { static constexpr uint64_t kLayout = 2; static constexpr uint32_t kSbo = 1024; static constexpr CUtensorMapSwizzle kTma = CU_TENSOR_MAP_SWIZZLE_128B; };
+template <> struct SwzTraits<32> { static constexpr uint64_t kLayout = 4; static constexpr uint32_t kSbo = 512; static constexpr CUtensorMapSwizzle kTma = CU_TENSOR_MAP_SWIZZLE_64B; };
+
+template <int BK>
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(SwzTraits<BK>::kSbo >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= SwzTraits<BK>::kLayout << 61;
+    return d;
+}
+
+constexpr int kV2MaxASlots = 4, kV2MaxBSlots = 8;
+
+struct Tc2Params {
+    int B, GH, GW, TH, tw, tiles_x, tiles_y, m_tiles, n_tiles, total_tiles;
+    int Cin_blocks, Cout, Cout_pad, n_tile, acc_stride;
+    int ntaps, ngroups;
+    int g_dx[4], g_first[5];
+    int t_dyoff[9], t_wtap[9];
+    int dy_min;
+    uint32_t a_bytes, b_bytes;     // slot stride of ONE (hi or lo) tile, 1024-byte aligned
+    uint32_t a_tx, b_tx;           // bytes one TMA box actually delivers
+    int a_slots, b_slots;
+    int OH, OW, sy, sx, py, px;
+    int mode; const float* dcoef; const float* noise; const float* noise_strength; const float* bias;
+    long long noise_bstride;
+    int act; float alpha, gain, clamp;
+    ia_emit emit;
+};
+
+template <int BK>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
+                const Tc2Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t a_slot_bytes = 2u * p.a_bytes, b_slot_bytes = 2u * p.b_bytes;
+    const uint32_t a_base = smem_base;
+    const uint32_t b_base = a_base + (uint32_t)p.a_slots * a_slot_bytes;
+    const uint32_t bar_base = b_base + (uint32_t)p.b_slots * b_slot_bytes;
+    auto a_full = [&](int s) { return bar_base + 8u * (uint32_t)s; };
+    auto a_empty = [&](int s) { return bar_base + 8u * (uint32_t)(kV2MaxASlots + s); };
+    auto b_full = [&](int s) { return bar_base + 8u * (uint32_t)(2 * kV2MaxASlots + s); };
+    auto b_empty = [&](int s) { return bar_base + 8u * (uint32_t)(2 * kV2MaxASlots + kV2MaxBSlots + s); };
+    auto t_full = [&](int s) { return bar_base + 8u * (uint32_t)(2 * kV2MaxASlots + 2 * kV2MaxBSlots + s); };
+    auto t_empty = [&](int s) { return bar_base + 8u * (uint32_t)(2 * kV2MaxASlots + 2 * kV2MaxBSlots + 2 + s); };
+    const uint32_t tmem_slot = bar_base + 8u * (uint32_t)(2 * kV2MaxASlots + 2 * kV2MaxBSlots + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.a_slots; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
+        for (int s = 0; s < p.b_slots; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(t_full(s), 1); mbar_init(t_empty(s), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tm_a_hi); prefetch_tmap(&tm_a_lo); prefetch_tmap(&tm_w_hi); prefetch_tmap(&tm_w_lo);
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    const int th_half = p.TH >> 1;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t a_it = 0, b_it = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const int n_idx = tile / p.m_tiles;
+                int m = tile - n_idx * p.m_tiles;
+                const int txi = m % p.tiles_x; m /= p.tiles_x;
+                const int tyi = m % p.tiles_y; const int img = m / p.tiles_y;
+                const int x0 = txi * p.tw, y0 = tyi * p.TH, col0 = n_idx * p.n_tile;
+                for (int kc = 0; kc < p.Cin_blocks; ++kc) {
+                    for (int g = 0; g < p.ngroups; ++g) {
+                        const int as = (int)(a_it % (uint32_t)p.a_slots);
+                        mbar_wait(a_empty(as), ((a_it / (uint32_t)p.a_slots) & 1u) ^ 1u);
+                        const uint32_t sa = a_base + (uint32_t)as * a_slot_bytes;
+                        mbar_expect_tx(a_full(as), 2u * p.a_tx);
+                        tma_load_4d(sa, &tm_a_hi, a_full(as), kc * BK, x0 + p.g_dx[g], y0 + p.dy_min, img);
+                        tma_load_4d(sa + p.a_bytes, &tm_a_lo, a_full(as), kc * BK, x0 + p.g_dx[g], y0 + p.dy_min, img);
+                        ++a_it;
+                        for (int t = p.g_first[g]; t < p.g_first[g + 1]; ++t) {
+                            const int bs = (int)(b_it % (uint32_t)p.b_slots);
+                            mbar_wait(b_empty(bs), ((b_it / (uint32_t)p.b_slots) & 1u) ^ 1u);
+                            const uint32_t sb = b_base + (uint32_t)bs * b_slot_bytes;
+                            mbar_expect_tx(b_full(bs), 2u * p.b_tx);
+                            const int wrow = p.t_wtap[t] * p.Cout_pad + col0;
+                            tma_load_2d(sb, &tm_w_hi, b_full(bs), kc * BK, wrow);
+                            tma_load_2d(sb + p.b_bytes, &tm_w_lo, b_full(bs), kc * BK, wrow);
+                            ++b_it;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+            uint32_t a_it = 0, b_it = 0, j = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++j) {
+                const uint32_t acc = j & 1u;
+                mbar_wait(t_empty(acc), ((j >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t d0 = tmem_base + (acc * 2u + 0u) * (uint32_t)p.acc_stride;
+                const uint32_t d1 = tmem_base + (acc * 2u + 1u) * (uint32_t)p.acc_stride;
+                bool first = true;
+                for (int kc = 0; kc < p.Cin_blocks; ++kc) {
+                    for (int g = 0; g < p.ngroups; ++g) {
+                        const int as = (int)(a_it % (uint32_t)p.a_slots);
+                        mbar_wait(a_full(as), (a_it / (uint32_t)p.a_slots) & 1u);
+                        const uint32_t sa = a_base + (uint32_t)as * a_slot_bytes;
+                        for (int t = p.g_first[g]; t < p.g_first[g + 1]; ++t) {
+                            const int bs = (int)(b_it % (uint32_t)p.b_slots);
+                            mbar_wait(b_full(bs), (b_it / (uint32_t)p.b_slots) & 1u);
+                            tc_fence_after();
+                            const uint32_t sb = b_base + (uint32_t)bs * b_slot_bytes;
+                            const uint64_t b_hi = make_kmajor_desc<BK>(sb);
+                            const uint64_t b_lo = make_kmajor_desc<BK>(sb + p.b_bytes);
+                            const uint32_t row_bytes = (uint32_t)BK * 2u;
+                            const uint32_t off0 = (uint32_t)(p.t_dyoff[t] * p.tw) * row_bytes;
+                            const uint32_t off1 = (uint32_t)((th_half + p.t_dyoff[t]) * p.tw) * row_bytes;
+                            const uint64_t a0_hi = make_kmajor_desc<BK>(sa + off0), a0_lo = make_kmajor_desc<BK>(sa + p.a_bytes + off0);
+                            const uint64_t a1_hi = make_kmajor_desc<BK>(sa + off1), a1_lo = make_kmajor_desc<BK>(sa + p.a_bytes + off1);
+#pragma unroll
+                            for (int k = 0; k < BK / 16; ++k) {
+                                const uint64_t koff = (uint64_t)((k * 32) >> 4);
+                                const uint32_t accum = first ? 0u : 1u;
+                                umma_bf16(d0, a0_hi + koff, b_hi + koff, idesc, accum);
+                                umma_bf16(d0, a0_hi + koff, b_lo + koff, idesc, 1u);
+                                umma_bf16(d0, a0_lo + koff, b_hi + koff, idesc, 1u);
+                                umma_bf16(d1, a1_hi + koff, b_hi + koff, idesc, accum);
+                                umma_bf16(d1, a1_hi + koff, b_lo + koff, idesc, 1u);
+                                umma_bf16(d1, a1_lo + koff, b_hi + koff, idesc, 1u);
+                                first = false;
+                            }
+                            umma_commit(b_empty(bs));
+                            ++b_it;
+                        }
+                        umma_commit(a_empty(as));
+                        ++a_it;
+                    }
+                }
+                umma_commit(t_full(acc));
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int lg = warp & 3;
+        uint32_t j = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++j) {
+            const uint32_t acc = j & 1u;
+            const int n_idx = tile / p.m_tiles;
+            int m = tile - n_idx * p.m_tiles;
+            const int txi = m % p.tiles_x; m /= p.tiles_x;
+            const int tyi = m % p.tiles_y; const int img = m / p.tiles_y;
+            const int x0 = txi * p.tw, y0 = tyi * p.TH, col0 = n_idx * p.n_tile;
+            mbar_wait(t_full(acc), (j >> 1) & 1u);
+            tc_fence_after();
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                const int row = lg * 32 + lane;
+                const int w_l = row % p.tw;
+                const int h_l = row / p.tw + half * th_half;
+                const int gy = y0 + h_l, gx = x0 + w_l;
+                const int oy = gy * p.sy + p.py, ox = gx * p.sx + p.px;
+                const bool valid = gy < p.GH && gx < p.GW && oy < p.OH && ox < p.OW;
+                const int64_t pix = ((int64_t)img * p.OH + oy) * p.OW + ox;
+                float nz = 0.f;
+                if (valid && p.mode == 1 && p.noise) nz = p.noise[(int64_t)img * p.noise_bstride + (int64_t)oy * p.OW + ox] * p.noise_strength[0];
+                const uint32_t tcol = (acc * 2u + (uint32_t)half) * (uint32_t)p.acc_stride;
+                for (int c = 0; c < p.n_tile; c += 32) {
+                    uint32_t r[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + tcol + (uint32_t)c, r);
+                    if (!valid) continue;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int co = col0 + c + q * 4;
+                        if (co >= p.Cout) break;
+                        float v[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            float a = __uint_as_float(r[q * 4 + k]);
+                            if (p.mode == 1 && co + k < p.Cout) {
+                                if (p.dcoef) a = fmaf(a, p.dcoef[(int64_t)img * p.Cout + co + k], nz); else a += nz;
+                                if (p.bias) a += p.bias[co + k];
+                                a = act_gain_clamp(a, p.act, p.alpha, p.gain, p.clamp);
+                            }
+                            v[k] = a;
+                        }
+                        emit4(p.emit, img, pix, co, p.Cout, v);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(t_empty(acc)) : "memory");
+        }
+    }
+
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+template <int BK>
+int make_act_map2(CUtensorMap* m, const void* ptr, int B, int H, int W, int C_pad, int rows, int tw) {
+    EncodeTiledFn enc = get_encode_fn();
+    IA_CHECK(enc, "ia_conv_tc: cuTensorMapEncodeTiled unavailable");
+    cuuint64_t dims[4] = {(cuuint64_t)C_pad, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)C_pad * 2, (cuuint64_t)W * C_pad * 2, (cuuint64_t)H * W * C_pad * 2};
+    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)tw, (cuuint32_t)rows, 1u};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, SwzTraits<BK>::kTma, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    IA_CHECK(r == CUDA_SUCCESS, "ia_conv_tc(v2): activation tensor map encode failed (CUresult %d; B=%d H=%d W=%d C=%d box %d x %d)",
+             (int)r, B, H, W, C_pad, rows, tw);
+    return 0;
+}
+
+template <int BK>
+int make_weight_map2(CUtensorMap* m, const void* ptr, int rows, int Cin_pad, int n_tile) {
+    EncodeTiledFn enc = get_encode_fn();
+    IA_CHECK(enc, "ia_conv_tc: cuTensorMapEncodeTiled unavailable");
+    cuuint64_t dims[2] = {(cuuint64_t)Cin_pad, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)Cin_pad * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)n_tile};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, SwzTraits<BK>::kTma, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    IA_CHECK(r == CUDA_SUCCESS, "ia_conv_tc(v2): weight tensor map encode failed (CUresult %d)", (int)r);
+    return 0;
+}
+
+int g_sm_count = 0;
+
+template <int BK>
+int launch_v2(const ia_conv_params* p, void* stream) {
+    Tc2Params t;
+    memset(&t, 0, sizeof(t));
+    t.B = p->B; t.GH = p->GH; t.GW = p->GW;
+    // tile geometry: 256 pixels as TH x tw with tw in {8,16,32}; fewest tiles wins, ties -> taller tiles (smaller halo share)
+    {
+        int64_t best = -1;
+        const int cand[3][2] = {{32, 8}, {16, 16}, {8, 32}};
+        for (int i = 0; i < 3; ++i) {
+            int64_t tiles = cdiv(p->GH, cand[i][0]) * cdiv(p->GW, cand[i][1]);
+            if (best < 0 || tiles < best) { best = tiles; t.TH = cand[i][0]; t.tw = cand[i][1]; }
+        }
+    }
+    t.tiles_x = (int)cdiv(p->GW, t.tw); t.tiles_y = (int)cdiv(p->GH, t.TH);
+    t.m_tiles = t.tiles_x * t.tiles_y * p->B;
+    t.Cin_blocks = p->Cin_pad / BK;
+    t.Cout = p->Cout; t.Cout_pad = p->Cout_pad;
+    int n_tile = 32;
+    for (int cand = 128; cand >= 32; cand -= 32) {
+        if (p->Cout_pad % cand) continue;
+        n_tile = cand;
+        if ((int64_t)t.m_tiles * (p->Cout_pad / cand) >= 120) break;
+    }
+    t.n_tile = n_tile; t.acc_stride = 128;
+    t.n_tiles = p->Cout_pad / n_tile;
+    t.total_tiles = t.m_tiles * t.n_tiles;
+    // group the taps by dx
+    int dy_min = 1 << 30, dy_max = -(1 << 30);
+    for (int i = 0; i < p->ntaps; ++i) { dy_min = p->dy[i] < dy_min ? p->dy[i] : dy_min; dy_max = p->dy[i] > dy_max ? p->dy[i] : dy_max; }
+    t.dy_min = dy_min;
+    const int halo = dy_max - dy_min;
+    t.ntaps = p->ntaps; t.ngroups = 0;
+    int nt = 0;
+    bool used[9] = {false, false, false, false, false, false, false, false, false};
+    for (int i = 0; i < p->ntaps; ++i) {
+        if (used[i]) continue;
+        IA_CHECK(t.ngroups < 4, "ia_conv_tc(v2): more than 4 distinct horizontal tap offsets");
+        t.g_dx[t.ngroups] = p->dx[i];
+        t.g_first[t.ngroups] = nt;
+        for (int k = i; k < p->ntaps; ++k)
+            if (!used[k] && p->dx[k] == p->dx[i]) { used[k] = true; t.t_dyoff[nt] = p->dy[k] - dy_min; t.t_wtap[nt] = p->wtap[k]; ++nt; }
+        ++t.ngroups;
+    }
+    t.g_first[t.ngroups] = nt;
+    const int a_rows = (t.TH + halo) * t.tw;
+    t.a_tx = (uint32_t)a_rows * BK * 2u;
+    t.a_bytes = (t.a_tx + 1023u) & ~1023u;
+    t.b_tx = (uint32_t)n_tile * BK * 2u;
+    t.b_bytes = (t.b_tx + 1023u) & ~1023u;
+    const uint32_t budget = 227u * 1024u - 1024u - 512u;
+    // at least 2 + 2 slots; then spend the rest alternately (weights first: they turn over once per tap)
+    t.a_slots = 2; t.b_slots = 2;
+    IA_CHECK(2u * (2u * t.a_bytes + 2u * t.b_bytes) <= budget, "ia_conv_tc(v2): tile does not fit shared memory");
+    for (;;) {
+        uint32_t used_b = 2u * ((uint32_t)t.a_slots * t.a_bytes + (uint32_t)t.b_slots * t.b_bytes);
+        bool grew = false;
+        if (t.b_slots < kV2MaxBSlots && t.b_slots < 3 * t.a_slots && used_b + 2u * t.b_bytes <= budget) { ++t.b_slots; grew = true; }
+        else if (t.a_slots < kV2MaxASlots && used_b + 2u * t.a_bytes <= budget) { ++t.a_slots; grew = true; }
+        else if (t.b_slots < kV2MaxBSlots && used_b + 2u * t.b_bytes <= budget) { ++t.b_slots; grew = true; }
+        if (!grew) break;
+    }
+    t.OH = p->OH; t.OW = p->OW; t.sy = p->sy; t.sx = p->sx; t.py = p->py; t.px = p->px;
+    t.mode = p->mode; t.dcoef = p->dcoef; t.noise = p->noise; t.noise_strength = p->noise_strength; t.bias = p->bias;
+    t.noise_bstride = p->noise_bstride;
+    t.act = p->act; t.alpha = p->alpha; t.gain = p->gain; t.clamp = p->clamp;
+    t.emit = p->emit;
+
+    CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
+    if (int rc = make_act_map2<BK>(&ma_hi, p->a_hi, p->B, p->H, p->W, p->Cin_pad, t.TH + halo, t.tw)) return rc;
+    if (int rc = make_act_map2<BK>(&ma_lo, p->a_lo, p->B, p->H, p->W, p->Cin_pad, t.TH + halo, t.tw)) return rc;
+    const int wrows = p->n_taps_total * p->Cout_pad;
+    if (int rc = make_weight_map2<BK>(&mw_hi, p->w_hi, wrows, p->Cin_pad, n_tile)) return rc;
+    if (int rc = make_weight_map2<BK>(&mw_lo, p->w_lo, wrows, p->Cin_pad, n_tile)) return rc;
+
+    const size_t smem = 2u * ((size_t)t.a_slots * t.a_bytes + (size_t)t.b_slots * t.b_bytes) + 1024 + 512;
+    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    IA_CHECK(e == cudaSuccess, "ia_conv_tc(v2): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    if (g_sm_count == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+        if (g_sm_count <= 0) g_sm_count = 148;
+    }
+    const int grid = t.total_tiles < g_sm_count ? t.total_tiles : g_sm_count;
+    ia::prof_begin("ia_conv_tc", as_stream(stream));
+    conv_tc2_kernel<BK><<<grid, kThreads, smem, as_stream(stream)>>>(ma_hi, ma_lo, mw_hi, mw_lo, t);
+    IA_LAUNCH_CHECK("ia_conv_tc");
+    return 0;
+}
+
 }  // namespace
 
 extern "C" int ia_conv_tc(const ia_conv_params* p, void* stream) {
@@ -332,6 +690,13 @@ extern "C" int ia_conv_tc(const ia_conv_params* p, void* stream) {
     IA_CHECK((reinterpret_cast<uintptr_t>(p->a_hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->a_lo) & 15) == 0 &&
              (reinterpret_cast<uintptr_t>(p->w_hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->w_lo) & 15) == 0,
              "ia_conv_tc: operands must be 16-byte aligned");
+    // v2 (persistent, 256-pixel tiles, halo reuse) needs images of at least one 128-pixel half tile; the low-resolution
+    // layers (4x4, 8x8 and their transposed-conv phase grids) pack several images into a tile with the v1 kernel below.
+    {
+        static int mode = -1;   // IA_CONV_TC: 0 = v1 only, 32 / 64 = v2 with that k-block (default 32)
+        if (mode < 0) { const char* e = getenv("IA_CONV_TC"); mode = e ? atoi(e) : 32; }
+        if (mode != 0 && p->GH * p->GW >= 128 && p->GW >= 8) return mode == 64 ? launch_v2<64>(p, stream) : launch_v2<32>(p, stream);
+    }
     TcParams t;
     memset(&t, 0, sizeof(t));
     t.B = p->B; t.GH = p->GH; t.GW = p->GW;

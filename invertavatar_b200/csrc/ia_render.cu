@@ -20,7 +20,7 @@ constexpr int kHidden = 64;
 constexpr int kFeat = 32;
 constexpr int kOut = 33;
 constexpr int kRowLd = 36;          // colour scratch row pitch: even (float2 stores) and 4g+2t bank spread -> conflict-free
-constexpr int kWarpsPerCta = 4;
+constexpr int kMaxWarpsPerCta = 12;   // one CTA per SM, as many ray-warps as the shared-memory scratch allows
 constexpr int kMaxS = 192;          // Dc + Df
 constexpr int kOutPad = 40;         // layer-2 columns: 0..31 = rgb, 32 = sigma, 33..39 = zero padding (5 n-tiles of 8)
 
@@ -289,7 +289,8 @@ __device__ __forceinline__ void march_weights(const float* d, const float* sg, f
     wsum = ws; dnum = dn;
 }
 
-__global__ void __launch_bounds__(kWarpsPerCta * 32) render_kernel(const ia_render_params p) {
+__global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1) render_kernel(const ia_render_params p) {
+    const int kWarpsPerCta = blockDim.x >> 5;
     extern __shared__ __align__(16) float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = p.Dc + p.Df;
@@ -546,8 +547,10 @@ extern "C" int ia_render(const ia_render_params* p, void* stream) {
     const int S = p->Dc + p->Df;
     size_t per_warp = (size_t)S * kRowLd + 6 * (size_t)S + 2 * (size_t)(p->Dc + 2);
     per_warp += per_warp & 1;   // keep every warp's scratch 8-byte aligned (float2 colour stores)
+    int kWarpsPerCta = (int)((227 * 1024 - sizeof(DecoderFrags)) / (per_warp * sizeof(float)));
+    if (kWarpsPerCta > kMaxWarpsPerCta) kWarpsPerCta = kMaxWarpsPerCta;
+    IA_CHECK(kWarpsPerCta >= 1, "ia_render: shared memory request too large");
     const size_t smem = sizeof(DecoderFrags) + per_warp * kWarpsPerCta * sizeof(float);
-    IA_CHECK(smem <= 227 * 1024, "ia_render: shared memory request too large");
     e = cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     IA_CHECK(e == cudaSuccess, "ia_render: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     int dev = 0, sms = 148, per_sm = 1;
