@@ -370,8 +370,56 @@ struct Tc2Params {
     ia_emit emit;
 };
 
+
+// Inner epilogue loop of one [32 rows][32 channels] chunk: lane = channel.  ACT: 0 = raw accumulator (mode 0),
+// IA_ACT_LINEAR / IA_ACT_LRELU specialised, -1 = any activation through the generic switch.
+template <int ACT>
+__device__ __forceinline__ void epilogue_chunk(const Tc2Params& p, const float* tsm, int lane, uint32_t vmask, int my_pix, float my_nz,
+                                               int64_t img_pix0, int co, bool cvalid, float dc, float bs, float s1v, float s2v) {
+    float* o32 = p.emit.out32 ? p.emit.out32 + img_pix0 * p.emit.out32_ld + co : nullptr;
+    uint16_t* h1 = p.emit.hi1 ? p.emit.hi1 + img_pix0 * p.emit.c1_pad + co : nullptr;
+    uint16_t* l1 = p.emit.hi1 ? p.emit.lo1 + img_pix0 * p.emit.c1_pad + co : nullptr;
+    uint16_t* h2 = p.emit.hi2 ? p.emit.hi2 + img_pix0 * p.emit.c2_pad + co : nullptr;
+    uint16_t* l2 = p.emit.hi2 ? p.emit.lo2 + img_pix0 * p.emit.c2_pad + co : nullptr;
+    const bool has_dc = p.dcoef != nullptr;
+    const float gain = p.gain, alpha = p.alpha, clampv = p.clamp;
+    const bool do_clamp = clampv >= 0.f;
+#pragma unroll 4
+    for (int rr = 0; rr < 32; ++rr) {
+        if (!((vmask >> rr) & 1u)) continue;
+        float a = tsm[rr * 33 + lane];
+        const int pix_r = __shfl_sync(0xffffffffu, my_pix, rr);
+        if (ACT != 0) {
+            const float nz = __shfl_sync(0xffffffffu, my_nz, rr);
+            a = has_dc ? fmaf(a, dc, nz) : a + nz;
+            a += bs;
+            if (ACT == IA_ACT_LRELU) a = (a > 0.f ? a : a * alpha) * gain;
+            else if (ACT == IA_ACT_LINEAR) a = a * gain;
+            else a = apply_act(a, p.act, alpha) * gain;
+            if (do_clamp) a = fminf(fmaxf(a, -clampv), clampv);
+        }
+        if (!cvalid) continue;
+        if (o32) o32[(int64_t)pix_r * p.emit.out32_ld] = a;
+        if (h1) {
+            uint16_t h, l;
+            split_bf16(a * s1v, h, l);
+            const int64_t o = (int64_t)pix_r * p.emit.c1_pad;
+            h1[o] = h; l1[o] = l;
+        }
+        if (h2) {
+            uint16_t h, l;
+            split_bf16(a * s2v, h, l);
+            const int64_t o = (int64_t)pix_r * p.emit.c2_pad;
+            h2[o] = h; l2[o] = l;
+        }
+    }
+}
+
+constexpr int kEpiWarps2 = 8;                       // epilogue warps of the v2 kernel: 2 per TMEM lane quarter (one per half tile)
+constexpr int kThreads2 = (2 + kEpiWarps2) * 32;
+
 template <int BK>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads2, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                 const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
                 const Tc2Params p) {
@@ -388,6 +436,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     auto t_full = [&](int s) { return bar_base + 8u * (uint32_t)(2 * kV2MaxASlots + 2 * kV2MaxBSlots + s); };
     auto t_empty = [&](int s) { return bar_base + 8u * (uint32_t)(2 * kV2MaxASlots + 2 * kV2MaxBSlots + 2 + s); };
     const uint32_t tmem_slot = bar_base + 8u * (uint32_t)(2 * kV2MaxASlots + 2 * kV2MaxBSlots + 4);
+    const uint32_t epi_base = bar_base + 512u;   // 4 x [32][33] fp32 transpose tiles of the epilogue warps
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -395,7 +444,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.a_slots; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
         for (int s = 0; s < p.b_slots; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(t_full(s), 1); mbar_init(t_empty(s), 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(t_full(s), 1); mbar_init(t_empty(s), kEpiWarps2); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -500,7 +549,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         }
     } else {
         // ===================== epilogue (warps 2..5) =====================
+        // TMEM -> registers (thread = pixel row) -> per-warp shared-memory transpose -> lane = output channel, so that the
+        // per-channel epilogue operands (demod coefficient, bias, next-layer styles) live in registers and every global
+        // store instruction writes one contiguous run (128 B of fp32 or 64 B of bf16) of a single pixel.
         const int lg = warp & 3;
+        const int half = (warp - 2) >> 2;           // which 128-pixel half of the tile this warp drains
+        float* tsm = reinterpret_cast<float*>(smem_raw + (epi_base - smem_u32(smem_raw))) + (warp - 2) * (32 * 33);
+        const int tw_shift = p.tw == 8 ? 3 : (p.tw == 16 ? 4 : 5);
         uint32_t j = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++j) {
             const uint32_t acc = j & 1u;
@@ -511,39 +566,40 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
             const int x0 = txi * p.tw, y0 = tyi * p.TH, col0 = n_idx * p.n_tile;
             mbar_wait(t_full(acc), (j >> 1) & 1u);
             tc_fence_after();
-#pragma unroll 1
-            for (int half = 0; half < 2; ++half) {
+            {
                 const int row = lg * 32 + lane;
-                const int w_l = row % p.tw;
-                const int h_l = row / p.tw + half * th_half;
+                const int w_l = row & (p.tw - 1);
+                const int h_l = (row >> tw_shift) + half * th_half;
                 const int gy = y0 + h_l, gx = x0 + w_l;
                 const int oy = gy * p.sy + p.py, ox = gx * p.sx + p.px;
                 const bool valid = gy < p.GH && gx < p.GW && oy < p.OH && ox < p.OW;
-                const int64_t pix = ((int64_t)img * p.OH + oy) * p.OW + ox;
-                float nz = 0.f;
-                if (valid && p.mode == 1 && p.noise) nz = p.noise[(int64_t)img * p.noise_bstride + (int64_t)oy * p.OW + ox] * p.noise_strength[0];
+                const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+                const int my_pix = oy * p.OW + ox;                     // pixel index inside the image (fits in int)
+                float my_nz = 0.f;
+                if (valid && p.mode == 1 && p.noise) my_nz = p.noise[(int64_t)img * p.noise_bstride + my_pix] * p.noise_strength[0];
+                const int64_t img_pix0 = (int64_t)img * p.OH * p.OW;
                 const uint32_t tcol = (acc * 2u + (uint32_t)half) * (uint32_t)p.acc_stride;
+#pragma unroll 1
                 for (int c = 0; c < p.n_tile; c += 32) {
                     uint32_t r[32];
                     tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + tcol + (uint32_t)c, r);
-                    if (!valid) continue;
+                    if (vmask == 0u) continue;
+                    __syncwarp();
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const int co = col0 + c + q * 4;
-                        if (co >= p.Cout) break;
-                        float v[4];
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            float a = __uint_as_float(r[q * 4 + k]);
-                            if (p.mode == 1 && co + k < p.Cout) {
-                                if (p.dcoef) a = fmaf(a, p.dcoef[(int64_t)img * p.Cout + co + k], nz); else a += nz;
-                                if (p.bias) a += p.bias[co + k];
-                                a = act_gain_clamp(a, p.act, p.alpha, p.gain, p.clamp);
-                            }
-                            v[k] = a;
-                        }
-                        emit4(p.emit, img, pix, co, p.Cout, v);
+                    for (int q = 0; q < 32; ++q) tsm[lane * 33 + q] = __uint_as_float(r[q]);
+                    __syncwarp();
+                    const int co = col0 + c + lane;
+                    const bool cvalid = co < p.Cout;
+                    float dc = 1.f, bs = 0.f, s1v = 1.f, s2v = 1.f;
+                    if (cvalid) {
+                        if (p.mode == 1) { if (p.dcoef) dc = p.dcoef[(int64_t)img * p.Cout + co]; if (p.bias) bs = p.bias[co]; }
+                        if (p.emit.hi1 && p.emit.s1) s1v = p.emit.s1[(int64_t)img * p.Cout + co];
+                        if (p.emit.hi2 && p.emit.s2) s2v = p.emit.s2[(int64_t)img * p.Cout + co];
                     }
+                    if (p.mode == 0) epilogue_chunk<0>(p, tsm, lane, vmask, my_pix, my_nz, img_pix0, co, cvalid, dc, bs, s1v, s2v);
+                    else if (p.act == IA_ACT_LRELU) epilogue_chunk<IA_ACT_LRELU>(p, tsm, lane, vmask, my_pix, my_nz, img_pix0, co, cvalid, dc, bs, s1v, s2v);
+                    else if (p.act == IA_ACT_LINEAR) epilogue_chunk<IA_ACT_LINEAR>(p, tsm, lane, vmask, my_pix, my_nz, img_pix0, co, cvalid, dc, bs, s1v, s2v);
+                    else epilogue_chunk<-1>(p, tsm, lane, vmask, my_pix, my_nz, img_pix0, co, cvalid, dc, bs, s1v, s2v);
                 }
             }
             tc_fence_before();
@@ -642,7 +698,8 @@ int launch_v2(const ia_conv_params* p, void* stream) {
     t.a_bytes = (t.a_tx + 1023u) & ~1023u;
     t.b_tx = (uint32_t)n_tile * BK * 2u;
     t.b_bytes = (t.b_tx + 1023u) & ~1023u;
-    const uint32_t budget = 227u * 1024u - 1024u - 512u;
+    const uint32_t kEpiBytes = (uint32_t)kEpiWarps2 * 32u * 33u * 4u;
+    const uint32_t budget = 227u * 1024u - 1024u - 512u - kEpiBytes;
     // at least 2 + 2 slots; then spend the rest alternately (weights first: they turn over once per tap)
     t.a_slots = 2; t.b_slots = 2;
     IA_CHECK(2u * (2u * t.a_bytes + 2u * t.b_bytes) <= budget, "ia_conv_tc(v2): tile does not fit shared memory");
@@ -667,7 +724,7 @@ int launch_v2(const ia_conv_params* p, void* stream) {
     if (int rc = make_weight_map2<BK>(&mw_hi, p->w_hi, wrows, p->Cin_pad, n_tile)) return rc;
     if (int rc = make_weight_map2<BK>(&mw_lo, p->w_lo, wrows, p->Cin_pad, n_tile)) return rc;
 
-    const size_t smem = 2u * ((size_t)t.a_slots * t.a_bytes + (size_t)t.b_slots * t.b_bytes) + 1024 + 512;
+    const size_t smem = 2u * ((size_t)t.a_slots * t.a_bytes + (size_t)t.b_slots * t.b_bytes) + 1024 + 512 + kEpiBytes;
     cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     IA_CHECK(e == cudaSuccess, "ia_conv_tc(v2): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     if (g_sm_count == 0) {
@@ -678,7 +735,7 @@ int launch_v2(const ia_conv_params* p, void* stream) {
     }
     const int grid = t.total_tiles < g_sm_count ? t.total_tiles : g_sm_count;
     ia::prof_begin("ia_conv_tc", as_stream(stream));
-    conv_tc2_kernel<BK><<<grid, kThreads, smem, as_stream(stream)>>>(ma_hi, ma_lo, mw_hi, mw_lo, t);
+    conv_tc2_kernel<BK><<<grid, kThreads2, smem, as_stream(stream)>>>(ma_hi, ma_lo, mw_hi, mw_lo, t);
     IA_LAUNCH_CHECK("ia_conv_tc");
     return 0;
 }
