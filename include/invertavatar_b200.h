@@ -230,6 +230,76 @@ int ia_depth_clamp(float* depth, int64_t n, const float* depth_minmax, void* str
 /* Ray generation only (RaySampler_zxc API): origins/dirs [B][rays][3]. */
 int ia_ray_sampler(const float* cam, int64_t cam_ld, int32_t B, int32_t res, float* origins, float* dirs, void* stream);
 
+/* ---- inversion encoder (encoder_inversion/models/{helpers,e4e,unet_encoders,uvnet}.py) -------------------------
+ * The IR-SE50 trunks, FPN/GradualStyleBlocks, DoubleConv/ConvGRU decoders and SFT heads are built from ia_conv_tc
+ * (mode 0: raw fp32 accumulators) plus the layout / normalisation / gating kernels below.  A view addresses element
+ * (b, y, x, c) of a logical [B][H][W][C] tensor as
+ *     p[b*s_img + (y/ps)*s_row + (x/ps)*s_pix + (c*ps*ps + (y%ps)*ps + (x%ps))*s_c]
+ * so NCHW inputs, channel slices, stride-2 subsampling (MaxPool2d(1,2), the output of a stride-2 convolution computed
+ * at full resolution), batch broadcast (s_img = 0, the `expand(T)` of unet_encoders.py:219) and
+ * torch.nn.PixelShuffle(ps) (unet_encoders.py:74,89,282) are all plain views -- nothing is materialised. */
+typedef struct {
+    const float* p; int32_t C; int32_t ps;
+    int64_t s_c, s_pix, s_row, s_img;
+} ia_view;
+
+/* Per-channel sum and sum of squares over [B][H][W] in float64 (sums[0..C) = sum, sums[C..2C) = sum of squares); the
+ * callee zeroes `sums` first.  Feeds train-mode BatchNorm (eval_seq.py:92 leaves e4e and the UNet decoders in train
+ * mode) and the squeeze of SEModule. */
+int ia_enc_chan_stats(const ia_view* x, int32_t B, int32_t H, int32_t W, double* sums, void* stream);
+/* torch.nn.BatchNorm2d folded to y = x*scale[c] + shift[c].  training != 0: batch statistics from `sums` over `count`
+ * elements (biased variance), and running_mean / running_var (may be NULL) updated with `momentum` (unbiased variance) as
+ * torch does; training == 0: running statistics.  gamma/beta may be NULL (1 / 0). */
+int ia_enc_bn_fold(const double* sums, int64_t count, const float* gamma, const float* beta, float* running_mean,
+                   float* running_var, int32_t training, float momentum, float eps, int32_t C, float* scale, float* shift,
+                   void* stream);
+/* Operand builder of an encoder convolution: concatenates up to 4 views along channels (torch.cat of
+ * unet_encoders.py:78,96, uvnet.py:121,183), applies the per-channel affine of a preceding BatchNorm (scale/shift over
+ * the concatenated channel index, may be NULL), an optional bias-free activation -- PReLU with per-channel `slope`, or
+ * leaky ReLU with the scalar `lrelu` when slope is NULL and lrelu != 1 -- and writes the bf16 hi/lo split
+ * [B][H][W][C_pad] (zero padded) that ia_conv_tc consumes, and/or the fp32 NHWC tensor out32 [B][H][W][sum C]. */
+typedef struct {
+    ia_view src[4]; int32_t nsrc;
+    const float* scale; const float* shift; const float* slope; float lrelu;
+    uint16_t* hi; uint16_t* lo; float* out32;
+    int32_t B, H, W, C_pad;
+} ia_enc_prep_params;
+int ia_enc_prep(const ia_enc_prep_params* p, void* stream);
+/* y = gate[b][c] * act2(act1(x*scale[c] + shift[c])) + (res*res_scale[c] + res_shift[c]).
+ * act1: PReLU with per-channel slope1 when given, else IA_ACT_* `act` with `alpha`; act2: optional second PReLU (slope2;
+ * DoubleConv ends in two PReLUs, unet_encoders.py:62-63).  Every pointer except x.p and y may be NULL.  Covers
+ * conv+bias, BatchNorm+PReLU (helpers.py:113-118), the SE scale + shortcut add of bottleneck_IR_SE (helpers.py:120-124),
+ * LeakyReLU heads, feature offsets (uvnet.py:187) and image differences (uvnet.py:181).  y is [B][H][W][C] with pixel
+ * stride y_ld (>= C). */
+typedef struct {
+    ia_view x; const float* scale; const float* shift; const float* slope1; const float* slope2;
+    int32_t act; float alpha;
+    const float* gate;
+    ia_view res; const float* res_scale; const float* res_shift;
+    float* y; int64_t y_ld;
+    int32_t B, H, W, C;
+} ia_enc_affine_params;
+int ia_enc_affine_act(const ia_enc_affine_params* p, void* stream);
+/* pooled[b][c] = mean over H,W of x*scale[c] + shift[c] (AdaptiveAvgPool2d(1) of SEModule, helpers.py:65,74). */
+int ia_enc_global_pool(const ia_view* x, const float* scale, const float* shift, int32_t B, int32_t H, int32_t W,
+                       float* pooled, void* stream);
+/* k x k box average, NHWC out [B][H/k][W/k][C] (AdaptiveAvgPool2d((256,256)) on 512^2 inputs, uvnet.py:108-109,
+ * unet_encoders.py:199-200; only integer ratios occur). */
+int ia_enc_avgpool(const ia_view* x, int32_t B, int32_t H, int32_t W, int32_t k, float* y, void* stream);
+/* y = bilinear_upsample(x -> [H][W], align_corners=True) + lateral  (FPN _upsample_add, e4e.py:48-65).
+ * x [B][h][w][C] and lateral/y [B][H][W][C] contiguous NHWC. */
+int ia_enc_upsample_add(const float* x, int32_t B, int32_t h, int32_t w, int32_t C, const float* lateral, int32_t H,
+                        int32_t W, float* y, void* stream);
+/* ConvGRU gating (unet_encoders.py:27-32).  stage 0: raw [n][2C] = ih conv accumulators; writes rh = sigmoid(raw[:C] +
+ * bias[:C]) * h and z = sigmoid(raw[C:] + bias[C:]).  stage 1: raw [n][C] = hh conv accumulators;
+ * h_out = (1 - z)*h + z*tanh(raw + bias).  n = B*H*W pixels, all tensors contiguous NHWC; h may be NULL (zero state). */
+int ia_enc_gru_gate(int32_t stage, const float* raw, const float* bias, const float* h, float* rh, float* z,
+                    float* h_out, int64_t n, int32_t C, void* stream);
+/* CS-SFT of the static backbone (networks_stylegan2_new.py:448-452): x[..., C/2:] = x[..., C/2:]*scale + shift, in
+ * place on the fp32 NHWC activation x [B][HW][C]; scale/shift are views of [1|B][HW][C/2]. */
+int ia_sft_half(float* x, int64_t x_ld, const ia_view* scale, const ia_view* shift, int32_t B, int32_t H, int32_t W,
+                int32_t C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -94,6 +94,27 @@ class RenderParams(C.Structure):
                 ('feat', c_f32p), ('depth', c_f32p), ('wsum', c_f32p), ('depth_minmax', c_f32p)]
 
 
+class View(C.Structure):
+    _fields_ = [('p', c_f32p), ('C', C.c_int32), ('ps', C.c_int32),
+                ('s_c', C.c_int64), ('s_pix', C.c_int64), ('s_row', C.c_int64), ('s_img', C.c_int64)]
+
+
+class EncPrepParams(C.Structure):
+    _fields_ = [('src', View * 4), ('nsrc', C.c_int32),
+                ('scale', c_f32p), ('shift', c_f32p), ('slope', c_f32p), ('lrelu', C.c_float),
+                ('hi', c_u16p), ('lo', c_u16p), ('out32', c_f32p),
+                ('B', C.c_int32), ('H', C.c_int32), ('W', C.c_int32), ('C_pad', C.c_int32)]
+
+
+class EncAffineParams(C.Structure):
+    _fields_ = [('x', View), ('scale', c_f32p), ('shift', c_f32p), ('slope1', c_f32p), ('slope2', c_f32p),
+                ('act', C.c_int32), ('alpha', C.c_float),
+                ('gate', c_f32p),
+                ('res', View), ('res_scale', c_f32p), ('res_shift', c_f32p),
+                ('y', c_f32p), ('y_ld', C.c_int64),
+                ('B', C.c_int32), ('H', C.c_int32), ('W', C.c_int32), ('C', C.c_int32)]
+
+
 # name -> (restype, argtypes); every symbol include/invertavatar_b200.h declares
 SIGNATURES = {
     'ia_abi_version': (C.c_int, []),
@@ -125,6 +146,16 @@ SIGNATURES = {
     'ia_render': (C.c_int, [C.POINTER(RenderParams), C.c_void_p]),
     'ia_depth_clamp': (C.c_int, [c_f32p, C.c_int64, c_f32p, C.c_void_p]),
     'ia_ray_sampler': (C.c_int, [c_f32p, C.c_int64, C.c_int32, C.c_int32, c_f32p, c_f32p, C.c_void_p]),
+    'ia_enc_chan_stats': (C.c_int, [C.POINTER(View), C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    'ia_enc_bn_fold': (C.c_int, [C.c_void_p, C.c_int64, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int32, C.c_float, C.c_float, C.c_int32,
+                                c_f32p, c_f32p, C.c_void_p]),
+    'ia_enc_prep': (C.c_int, [C.POINTER(EncPrepParams), C.c_void_p]),
+    'ia_enc_affine_act': (C.c_int, [C.POINTER(EncAffineParams), C.c_void_p]),
+    'ia_enc_global_pool': (C.c_int, [C.POINTER(View), c_f32p, c_f32p, C.c_int32, C.c_int32, C.c_int32, c_f32p, C.c_void_p]),
+    'ia_enc_avgpool': (C.c_int, [C.POINTER(View), C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_f32p, C.c_void_p]),
+    'ia_enc_upsample_add': (C.c_int, [c_f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_f32p, C.c_int32, C.c_int32, c_f32p, C.c_void_p]),
+    'ia_enc_gru_gate': (C.c_int, [C.c_int32, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int64, C.c_int32, C.c_void_p]),
+    'ia_sft_half': (C.c_int, [c_f32p, C.c_int64, C.POINTER(View), C.POINTER(View), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
 }
 
 ABI_VERSION = 1

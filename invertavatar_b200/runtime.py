@@ -617,3 +617,201 @@ def render(planes_nhwc, cam, res, Dc, Df, jitter, u, box_warp, white_back, w1, b
     _C.check(_C.lib().ia_render(C.byref(p), st), 'ia_render')
     _C.check(_C.lib().ia_depth_clamp(_p(depth), depth.numel(), _p(mm), st), 'ia_depth_clamp')
     return feat, depth, wsum
+
+
+# ---------------------------------------------------------------------------------------------------
+# inversion-encoder pieces (csrc/ia_encoder.cu): everything reads through ia_view, so torch views (permute, slicing,
+# expand) describe NCHW inputs, channel slices, stride-2 subsampling and batch broadcast without copies
+# ---------------------------------------------------------------------------------------------------
+def make_view(t, ps=1):
+    """t: fp32 CUDA tensor indexed [B,H,W,C] (any strides, e.g. an NCHW tensor permuted) -> (_C.View, (B, H*ps, W*ps, C/ps^2)).
+    ps > 1 reads it through torch.nn.PixelShuffle(ps)."""
+    _require_cuda(t)
+    if t.dtype != torch.float32:
+        t = t.float()
+    B, H, W, Cc = t.shape
+    assert Cc % (ps * ps) == 0
+    v = _C.View(t.data_ptr(), Cc // (ps * ps), ps, t.stride(3), t.stride(2), t.stride(1), t.stride(0))
+    v._keep = t   # keep a converted temporary alive until the launch is enqueued
+    return v, (B, H * ps, W * ps, Cc // (ps * ps))
+
+
+def _as_view(src):
+    """src: tensor [B,H,W,C] or (tensor, ps)."""
+    return make_view(src[0], src[1]) if isinstance(src, (tuple, list)) else make_view(src, 1)
+
+
+def enc_chan_stats(src):
+    v, (B, H, W, Cc) = _as_view(src)
+    st = _enter(v._keep)
+    sums = torch.empty(2 * Cc, dtype=torch.float64, device=v._keep.device)
+    _C.check(_C.lib().ia_enc_chan_stats(C.byref(v), B, H, W, _p(sums), st), 'ia_enc_chan_stats')
+    return sums, B * H * W
+
+
+def enc_bn_fold(bn, srcs):
+    """torch.nn.BatchNorm2d ``bn`` applied to cat(srcs, channel) -> per-channel (scale, shift) fp32 [C].
+    Train mode (or no running statistics): batch statistics of the sources, running statistics updated as torch does."""
+    dev = bn.weight.device if bn.weight is not None else srcs[0].device
+    Cn = bn.num_features
+    training = bn.training or not bn.track_running_stats
+    scale = torch.empty(Cn, dtype=torch.float32, device=dev)
+    shift = torch.empty_like(scale)
+    sums, count = None, 0
+    if training:
+        if len(srcs) == 1:
+            sums, count = enc_chan_stats(srcs[0])
+        else:
+            sums = torch.empty(2, Cn, dtype=torch.float64, device=dev)
+            c0 = 0
+            for s in srcs:
+                part, count = enc_chan_stats(s)
+                cs = part.numel() // 2
+                sums[:, c0:c0 + cs] = part.view(2, cs)
+                c0 += cs
+            assert c0 == Cn
+        assert sums.numel() == 2 * Cn, (sums.numel(), Cn)
+    st = _enter(scale)
+    track = bn.track_running_stats and bn.running_mean is not None
+    momentum = 0.1 if bn.momentum is None else float(bn.momentum)
+    if training and track and bn.momentum is None:   # cumulative moving average
+        momentum = 1.0 / float(int(bn.num_batches_tracked) + 1)
+    _C.check(_C.lib().ia_enc_bn_fold(_p(sums), int(count), _p(bn.weight), _p(bn.bias), _p(bn.running_mean) if track else None,
+                                     _p(bn.running_var) if track else None, 1 if training else 0, momentum, float(bn.eps), Cn,
+                                     _p(scale), _p(shift), st), 'ia_enc_bn_fold')
+    if training and track and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked += 1
+    return scale, shift
+
+
+def enc_prep(srcs, scale=None, shift=None, slope=None, lrelu=1.0, C_pad=None, want_split=True, want32=False):
+    """cat(srcs) -> affine -> PReLU/leaky -> (Split [B,H,W,C_pad] bf16 hi/lo or None, fp32 NHWC [B,H,W,Ctot] or None)."""
+    views = [_as_view(s) for s in srcs]
+    B, H, W, _ = views[0][1]
+    for _, shp in views:
+        assert shp[:3] == (B, H, W), ('enc_prep: sources disagree', [s for _, s in views])
+    Ctot = sum(shp[3] for _, shp in views)
+    dev = views[0][0]._keep.device
+    st = _enter(views[0][0]._keep)
+    p = _C.EncPrepParams()
+    for i, (v, _) in enumerate(views):
+        p.src[i] = v
+    p.nsrc = len(views)
+    p.scale, p.shift, p.slope, p.lrelu = _p(scale), _p(shift), _p(slope), float(lrelu)
+    sp = out32 = None
+    if want_split:
+        C_pad = _pad_to(Ctot, 64) if C_pad is None else C_pad
+        sp = Split(torch.empty((B, H, W, C_pad), dtype=torch.bfloat16, device=dev), torch.empty((B, H, W, C_pad), dtype=torch.bfloat16, device=dev))
+        p.hi, p.lo, p.C_pad = _p(sp.hi), _p(sp.lo), C_pad
+    if want32:
+        out32 = torch.empty((B, H, W, Ctot), dtype=torch.float32, device=dev)
+        p.out32 = _p(out32)
+    p.B, p.H, p.W = B, H, W
+    _C.check(_C.lib().ia_enc_prep(C.byref(p), st), 'ia_enc_prep')
+    return sp, out32
+
+
+def enc_conv(a, conv):
+    """a: Split; conv: torch.nn.Conv2d holder (3x3 pad 1 or 1x1, stride applied by the caller as a [::s, ::s] view of the
+    result) -> raw fp32 accumulators [B,H,W,Cout] (bias not added)."""
+    pack = ConvPack.current(conv, '_ia_pack', conv.weight, need_wsq=False)
+    assert (pack.kh, pack.kw) in ((1, 1), (3, 3)) and a.C_pad == pack.Cin_pad, (pack.kh, a.C_pad, pack.Cin_pad)
+    B, H, W, _ = a.hi.shape
+    raw = torch.empty((B, H, W, pack.Cout), dtype=torch.float32, device=a.hi.device)
+    conv_same(a.hi, a.lo, pack, pack.Cin_pad, raw, mode=0)
+    return raw
+
+
+def enc_affine_act(x, scale=None, shift=None, slope1=None, slope2=None, act='linear', alpha=0.0, gate=None, res=None,
+                   res_scale=None, res_shift=None, out=None):
+    """y = gate * act2(act1(x*scale + shift)) + (res*res_scale + res_shift); x/res: tensors [B,H,W,C] (any strides) or
+    (tensor, ps).  out: optional [B,H,W,C] destination with unit channel stride and dense rows (a column slice of a
+    wider NHWC buffer is fine)."""
+    xv, (B, H, W, Cc) = _as_view(x)
+    st = _enter(xv._keep)
+    p = _C.EncAffineParams()
+    p.x = xv
+    p.scale, p.shift, p.slope1, p.slope2 = _p(scale), _p(shift), _p(slope1), _p(slope2)
+    p.act, p.alpha, p.gate = ACT_IDS[act], float(alpha), _p(gate)
+    if res is not None:
+        rv, rshape = _as_view(res)
+        if rshape[0] == 1 and B > 1:
+            rv.s_img = 0
+        assert rshape[1:] == (H, W, Cc), (rshape, (B, H, W, Cc))
+        p.res = rv
+    p.res_scale, p.res_shift = _p(res_scale), _p(res_shift)
+    if out is None:
+        out = torch.empty((B, H, W, Cc), dtype=torch.float32, device=xv._keep.device)
+    assert tuple(out.shape) == (B, H, W, Cc) and (Cc == 1 or out.stride(3) == 1), (out.shape, out.stride())
+    # the destination must be pixel-linear: address(b, y, x) = ((b*H + y)*W + x) * y_ld  (size-1 dims carry no constraint)
+    y_ld = out.stride(2) if W > 1 else (out.stride(1) if H > 1 else (out.stride(0) if B > 1 else Cc))
+    assert (W == 1 or H == 1 or out.stride(1) == W * y_ld) and (B == 1 or H * W == 1 or out.stride(0) == H * W * y_ld), (out.shape, out.stride())
+    p.y, p.y_ld = _p(out), y_ld
+    p.B, p.H, p.W, p.C = B, H, W, Cc
+    _C.check(_C.lib().ia_enc_affine_act(C.byref(p), st), 'ia_enc_affine_act')
+    return out
+
+
+def enc_global_pool(x, scale=None, shift=None):
+    xv, (B, H, W, Cc) = _as_view(x)
+    st = _enter(xv._keep)
+    pooled = torch.empty((B, Cc), dtype=torch.float32, device=xv._keep.device)
+    _C.check(_C.lib().ia_enc_global_pool(C.byref(xv), _p(scale), _p(shift), B, H, W, _p(pooled), st), 'ia_enc_global_pool')
+    return pooled
+
+
+def enc_avgpool(x, k):
+    xv, (B, H, W, Cc) = _as_view(x)
+    st = _enter(xv._keep)
+    y = torch.empty((B, H // k, W // k, Cc), dtype=torch.float32, device=xv._keep.device)
+    _C.check(_C.lib().ia_enc_avgpool(C.byref(xv), B, H, W, int(k), _p(y), st), 'ia_enc_avgpool')
+    return y
+
+
+def enc_upsample_add(x, lateral):
+    """bilinear(align_corners=True) upsample of x [B,h,w,C] to lateral's size, plus lateral (both contiguous NHWC)."""
+    st = _enter(x)
+    x, lateral = _f32c(x), _f32c(lateral)
+    B, h, w, Cc = x.shape
+    _, H, W, _ = lateral.shape
+    y = torch.empty_like(lateral)
+    _C.check(_C.lib().ia_enc_upsample_add(_p(x), B, h, w, Cc, _p(lateral), H, W, _p(y), st), 'ia_enc_upsample_add')
+    return y
+
+
+def enc_gru_gate0(raw, bias, h):
+    """raw [B,H,W,2C] (ih accumulators) -> (r*h, z) each [B,H,W,C]."""
+    st = _enter(raw)
+    B, H, W, C2 = raw.shape
+    Cc = C2 // 2
+    rh = torch.empty((B, H, W, Cc), dtype=torch.float32, device=raw.device)
+    z = torch.empty_like(rh)
+    assert raw.is_contiguous() and (h is None or h.is_contiguous())
+    _C.check(_C.lib().ia_enc_gru_gate(0, _p(raw), _p(bias), _p(h), _p(rh), _p(z), None, B * H * W, Cc, st), 'ia_enc_gru_gate')
+    return rh, z
+
+
+def enc_gru_gate1(raw, bias, h, z):
+    st = _enter(raw)
+    B, H, W, Cc = raw.shape
+    h_out = torch.empty_like(raw)
+    assert raw.is_contiguous() and z.is_contiguous() and (h is None or h.is_contiguous())
+    _C.check(_C.lib().ia_enc_gru_gate(1, _p(raw), _p(bias), _p(h), None, _p(z), _p(h_out), B * H * W, Cc, st), 'ia_enc_gru_gate')
+    return h_out
+
+
+def sft_half(x_nhwc, scale, shift):
+    """In place CS-SFT on the second half of the channels of x [B,H,W,C] (networks_stylegan2_new.py:448-452);
+    scale/shift: [1|B,H,W,C/2]-indexed tensors (any strides)."""
+    st = _enter(x_nhwc)
+    B, H, W, Cc = x_nhwc.shape
+    assert x_nhwc.stride(3) == 1 and x_nhwc.stride(1) == W * x_nhwc.stride(2) and x_nhwc.stride(0) == H * x_nhwc.stride(1)
+    sv, sshape = make_view(scale)
+    hv, hshape = make_view(shift)
+    assert sshape[1:] == (H, W, Cc // 2) and hshape[1:] == (H, W, Cc // 2), (sshape, hshape, x_nhwc.shape)
+    if sshape[0] == 1:
+        sv.s_img = 0
+    if hshape[0] == 1:
+        hv.s_img = 0
+    _C.check(_C.lib().ia_sft_half(_p(x_nhwc), x_nhwc.stride(2), C.byref(sv), C.byref(hv), B, H, W, Cc, st), 'ia_sft_half')
+    return x_nhwc

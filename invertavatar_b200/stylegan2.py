@@ -342,11 +342,8 @@ class SynthesisBlock(torch.nn.Module):
             i += 1
             if condition is not None:
                 # CS-SFT (networks_stylegan2_new.py:448-452): second half of the channels <- x*scale + shift.
-                # Runs once per identity (AR_eval_forward), so plain tensor algebra on the NCHW view is fine here.
-                xv = rt.from_nhwc(x)
-                half = xv.shape[1] // 2
-                xv = torch.cat([xv[:, :half], xv[:, half:] * condition[0] + condition[1]], dim=1)
-                x = rt.to_nhwc(xv)
+                # In place on the fp32 NHWC activation (ia_sft_half).
+                rt.sft_half(x, condition[0].permute(0, 2, 3, 1), condition[1].permute(0, 2, 3, 1))
             x = self.conv1.run_nhwc(x, styles[i], dcoefs[i], noise_mode=noise_mode, gain=gain)
             i += 1
         if hasattr(self, 'torgb'):
@@ -385,10 +382,8 @@ class SynthesisBlock(torch.nn.Module):
             else:
                 # CS-SFT (networks_stylegan2_new.py:448-452) needs the fp32 activation: once per identity, not per frame
                 x = self.conv0.run_split(a_in, dcoefs[0], noise_mode=noise_mode, gain=gain, want32=True)
-                xv = rt.from_nhwc(x)
-                half = xv.shape[1] // 2
-                xv = torch.cat([xv[:, :half], xv[:, half:] * condition[0] + condition[1]], dim=1)
-                hi, lo = rt.modsplit(rt.to_nhwc(xv), styles[1], C_pad=self.conv1.pack().Cin_pad)
+                rt.sft_half(x, condition[0].permute(0, 2, 3, 1), condition[1].permute(0, 2, 3, 1))
+                hi, lo = rt.modsplit(x, styles[1], C_pad=self.conv1.pack().Cin_pad)
                 a1 = rt.Split(hi, lo)
             i = 1
         has_rgb = hasattr(self, 'torgb')

@@ -174,3 +174,31 @@ def randomize_noise_and_wavg(module_or_sd, seed=123):
             elif k.endswith('.bias') and ('conv' in k or 'torgb' in k) and 'affine' not in k:
                 v.copy_((torch.randn(v.shape, generator=g) * 0.1).to(v.device))
     return module_or_sd
+
+
+def randomize_encoder(net, seed=321):
+    """Random init leaves every BatchNorm at identity (weight 1, bias 0, running mean 0 / var 1) and every PReLU at
+    0.25; give them values so that the normalisation and activation paths of the inversion encoder are exercised.
+    Works on the reference modules and on this package's (both keep torch.nn.BatchNorm2d / PReLU parameter holders)."""
+    g = torch.Generator(device='cpu').manual_seed(seed)
+    with torch.no_grad():
+        for m in net.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.weight.copy_((0.8 + 0.4 * torch.rand(m.weight.shape, generator=g)).to(m.weight.device))
+                m.bias.copy_((0.1 * torch.randn(m.bias.shape, generator=g)).to(m.bias.device))
+                m.running_mean.copy_((0.1 * torch.randn(m.running_mean.shape, generator=g)).to(m.running_mean.device))
+                m.running_var.copy_((0.5 + torch.rand(m.running_var.shape, generator=g)).to(m.running_var.device))
+            elif isinstance(m, torch.nn.PReLU):
+                m.weight.copy_((0.1 + 0.3 * torch.rand(m.weight.shape, generator=g)).to(m.weight.device))
+    return net
+
+
+def encoder_inputs(T, seed=31):
+    """SURVEY 8(d) encoder config: images clamp(N(0,0.5),-1,1) [T,3,512,512]; uv [T,6,256,256] = (random texture 3 ch,
+    the UV mesh condition image 3 ch); cameras and mesh conditions of frames 0..T-1."""
+    g = torch.Generator(device='cpu').manual_seed(seed)
+    image = (0.5 * torch.randn(T, 3, 512, 512, generator=g)).clamp(-1, 1)
+    tex = (0.5 * torch.randn(T, 3, 256, 256, generator=g)).clamp(-1, 1)
+    uvimg = uvcoords_image(T)
+    uv = torch.cat([tex, uvimg.permute(0, 3, 1, 2)], dim=1)
+    return {'image': image, 'uv': uv}, cameras(T), {'uvcoords_image': uvimg}

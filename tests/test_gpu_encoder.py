@@ -1,0 +1,132 @@
+"""GPU parity of the inversion encoder through the C-ABI: block-level against the CPU oracle,
+whole ``encode`` / ``AR_eval_forward`` against golden vectors minted from the unmodified reference."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from common import build_inversion_net, golden
+from golden.fingerprint import compare, unpack
+from invertavatar_b200 import synth
+from oracle import encoder as o_enc
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+RTOL = 1e-3   # north_star tolerance: 1e-3 max-abs (relative to the tensor's magnitude where that exceeds 1)
+
+
+def rel_err(got, ref):
+    ref = ref.float().cpu()
+    return float((got.float().cpu() - ref).abs().max()) / max(1.0, float(ref.abs().max()))
+
+
+@pytest.fixture(scope='module')
+def net():
+    g = golden('encoder.npz')
+    T, res, Dc, Df = [int(v) for v in g['enc/meta']]
+    n = copy.deepcopy(build_inversion_net(Dc, Df, res)).to(DEV)
+    return n
+
+
+def _sd(module):
+    return {k: v.detach().cpu().clone() for k, v in module.state_dict().items()}
+
+
+@pytest.mark.parametrize('idx,res,training', [(0, 32, False), (1, 24, True), (3, 16, True), (7, 16, False), (21, 8, True)])
+def test_bottleneck_vs_oracle(net, idx, res, training):
+    """IR-SE50 unit: stride 1 / 2, identity / projected shortcut, BatchNorm in eval and in train (batch statistics) mode."""
+    blk = copy.deepcopy(net.encoder.body[idx]).train(training)
+    in_c, depth, stride = o_enc.get_blocks50()[idx]
+    g = torch.Generator().manual_seed(idx)
+    x = torch.randn(2, in_c, res, res, generator=g)
+    sd = _sd(blk)
+    with torch.no_grad():
+        want = o_enc.bottleneck_ir_se(sd, x, in_c, depth, stride, training)
+        got = blk(x.to(DEV))
+    assert tuple(got.shape) == tuple(want.shape)
+    assert rel_err(got, want) < 2e-4
+    if training:   # running statistics follow torch's update rule (momentum 0.1, unbiased variance)
+        bn = blk.res_layer[0]
+        m = x.mean(dim=(0, 2, 3))
+        v = x.var(dim=(0, 2, 3), unbiased=True)
+        assert torch.allclose(bn.running_mean.cpu(), 0.9 * sd['res_layer.0.running_mean'] + 0.1 * m, atol=1e-5)
+        assert torch.allclose(bn.running_var.cpu(), 0.9 * sd['res_layer.0.running_var'] + 0.1 * v, atol=1e-5)
+        assert int(bn.num_batches_tracked) == int(sd['res_layer.0.num_batches_tracked']) + 1
+
+
+@pytest.mark.parametrize('i', [0, 3, 7])
+def test_gradual_style_block_vs_oracle(net, i):
+    blk = net.encoder.styles[i]
+    sp = blk.spatial
+    x = torch.randn(2, 512, sp, sp, generator=torch.Generator().manual_seed(i))
+    with torch.no_grad():
+        want = o_enc.gradual_style_block(_sd(blk), x, sp)
+        got = blk(x.to(DEV))
+    assert rel_err(got, want) < 2e-4
+
+
+def test_recurrent_up_and_gru_vs_oracle(net):
+    """PixelShuffle + concat + train-mode BatchNorm + DoubleConv + ConvGRU over T steps, with and without a carried state."""
+    up = net.unet_encoder.texture_unet.up3   # recurrent_Up(224, 256): x1 384ch (PixelShuffle 2 -> 96), x2 128ch
+    T = 3
+    g = torch.Generator().manual_seed(4)
+    x1 = torch.randn(T, 384, 8, 8, generator=g)
+    x2 = torch.randn(T, 128, 16, 16, generator=g)
+    r0 = torch.randn(1, 256, 16, 16, generator=g) * 0.5
+    sd = _sd(up)
+    with torch.no_grad():
+        for r in (None, r0):
+            want, want_r = o_enc.recurrent_up(sd, x1, x2, T, r, 2, training=True)
+            got, got_r = up(x1.to(DEV), x2.to(DEV), T, None if r is None else r.to(DEV))
+            assert rel_err(got, want) < 2e-4 and rel_err(got_r, want_r) < 2e-4
+
+
+def test_encode_golden(net):
+    g = golden('encoder.npz')
+    x, _, _ = synth.encoder_inputs(int(g['enc/meta'][0]))
+    img = x['image'][:1].to(DEV)
+    n = copy.deepcopy(net)
+    with torch.no_grad():
+        n.encoder.eval()
+        ws_eval = n.encode(img)
+        n.encoder.train()
+        ws_train = n.encode(img)
+    assert rel_err(ws_eval, torch.from_numpy(g['enc/ws_eval'])) < RTOL
+    assert rel_err(ws_train, torch.from_numpy(g['enc/ws_train'])) < RTOL
+
+
+def test_ar_eval_forward_golden(net):
+    """eval_seq.py:164-190: e4e features, then two AR_eval_forward calls (the second carries the ConvGRU states)."""
+    g = golden('encoder.npz')
+    T, res, Dc, Df = [int(v) for v in g['enc/meta']]
+    n = copy.deepcopy(net)
+    x, c, v = synth.encoder_inputs(T)
+    x = {k: t.to(DEV) for k, t in x.items()}
+    c = c.to(DEV)
+    v = {k: t.to(DEV) for k, t in v.items()}
+    ws = torch.from_numpy(g['enc/ws_train']).to(DEV)
+    G = n.generator
+    with torch.no_grad():
+        tex = G.texture_backbone.synthesis(ws, cond_list=None, return_list=True, update_emas=False, noise_mode='const')
+        sta = G.backbone.synthesis(ws, cond_list=None, return_list=True, update_emas=False, noise_mode='const')
+        e4e = {'w': ws, 'texture': tex, 'static': sta}
+        r_list = [None, None]
+        for call in range(2):
+            G.renderer.depth_jitter = synth.depth_jitter(T, res * res, Dc, seed=20 + call).to(DEV)
+            G.renderer.importance_u = synth.importance_u(T, res * res, Df, seed=30 + call).to(DEV)
+            upd, fake, r_list = n.AR_eval_forward(x, c, v, ws, r_list, e4e_results=e4e, return_fake=True)
+            tag = f'enc/ar{call}'
+            worst = 0.0
+            compare(fake['x_input'].unsqueeze(0), unpack(f'{tag}/x_input', g), 1e-3, 'x_input')
+            for i, t in enumerate(upd['texture']):
+                fp = unpack(f'{tag}/texture{i}', g)
+                worst = max(worst, compare(t, fp, RTOL * max(1.0, float(np.abs(fp['sub']).max())), f'texture{i}')[0])
+            for i, t in enumerate(upd['static']):
+                fp = unpack(f'{tag}/static{i}', g)
+                worst = max(worst, compare(t, fp, RTOL * max(1.0, float(np.abs(fp['sub']).max())), f'static{i}')[0])
+            for k in range(2):
+                for i, t in enumerate(r_list[k]):
+                    compare(t, unpack(f'{tag}/r{k}_{i}', g), RTOL, f'r{k}_{i}')
+            assert fake['image'].shape == (T, 3, 512, 512) and bool(torch.isfinite(fake['image']).all())
+            print(f'AR_eval_forward call {call}: worst feature error {worst:.2e}')
