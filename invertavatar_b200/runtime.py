@@ -286,7 +286,8 @@ class StylePlan:
     def run(self, ws):
         """ws: [B, n, w_dim] fp32 with unit inner stride (may be a narrow() view of a wider tensor)."""
         st = _enter(ws)
-        if ws.dtype != torch.float32 or ws.stride(2) != 1 or ws.stride(1) != ws.shape[2] or ws.stride(0) % ws.shape[2] != 0:
+        if ws.dtype != torch.float32 or ws.stride(2) != 1 or ws.stride(1) != ws.shape[2] or ws.stride(0) % ws.shape[2] != 0 or \
+                ws.stride(0) < ws.shape[1] * ws.shape[2]:   # (an expand()ed batch has stride 0: materialise it)
             ws = ws.float().contiguous()
         B = ws.shape[0]
         if self.host is None or B != self.cap:
