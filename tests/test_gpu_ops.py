@@ -141,3 +141,35 @@ def test_grid_sample_resize_lerp():
     al = torch.rand(2, 6, 7, generator=g)
     y = rt.lerp_alpha(a.to(DEV), b.to(DEV), al.to(DEV))
     close(y, a * al.unsqueeze(-1) + b * (1 - al.unsqueeze(-1)), 1e-6)
+
+
+def test_reference_python_api_golden():
+    """The function-level mirror of torch_utils.ops (invertavatar_b200.ops, what the drop-in tree exports) against the
+    reference-minted vectors: upsample2d / downsample2d / filter2d, filtered_lrelu, conv2d_resample, modulated_conv2d, fma,
+    grid_sample."""
+    from invertavatar_b200 import ops
+    g = golden('ops.npz')
+    x, f = T(g['upfirdn2d/x']).to(DEV), T(g['upfirdn2d/f']).to(DEV)
+    close(ops.upsample2d(x, f), g['upfirdn2d/up2'], 1e-6)
+    close(ops.downsample2d(x, f), g['upfirdn2d/down2'], 1e-6)
+    close(ops.filter2d(x, f), g['upfirdn2d/filter'], 1e-6)
+    close(ops.upsample2d(x, T(g['upfirdn2d/f_sep']).to(DEV)), g['upfirdn2d/sep_up2'], 1e-6)
+    close(ops.upfirdn2d(x, T(g['upfirdn2d/fa']).to(DEV), up=[2, 1], down=[1, 2], padding=[1, 2, 2, 1]), g['upfirdn2d/asym'], 2e-6)
+    xb, bb, ff = T(g['filtered_lrelu/x']).to(DEV), T(g['filtered_lrelu/b']).to(DEV), T(g['filtered_lrelu/f']).to(DEV)
+    close(ops.filtered_lrelu(xb, fu=ff, fd=ff, b=bb, up=2, down=2, padding=3, clamp=0.9), g['filtered_lrelu/up2_down2'], 2e-6)
+    close(ops.filtered_lrelu(xb, b=bb), g['filtered_lrelu/plain'], 1e-6)
+    xm, w, s = T(g['modconv/x']).to(DEV), T(g['modconv/w']).to(DEV), T(g['modconv/s']).to(DEV)
+    tol = 2e-4
+    close(ops.conv2d_resample(xm, w, f=f, up=2, padding=1, flip_weight=False), g['conv2d_resample/up2'], tol * float(np.abs(g['conv2d_resample/up2']).max()))
+    close(ops.conv2d_resample(xm, w, padding=1), g['conv2d_resample/same'], tol * float(np.abs(g['conv2d_resample/same']).max()))
+    close(ops.conv2d(xm, w, padding=1), g['conv2d_resample/same'], tol * float(np.abs(g['conv2d_resample/same']).max()))
+    close(ops.modulated_conv2d(xm, w, s, noise=T(g['modconv/noise']).to(DEV), padding=1), g['modconv/same'], tol * max(1.0, float(np.abs(g['modconv/same']).max())))
+    close(ops.modulated_conv2d(xm, w, s, noise=T(g['modconv/noise2']).to(DEV), up=2, padding=1, resample_filter=f, flip_weight=False),
+          g['modconv/up2'], tol * max(1.0, float(np.abs(g['modconv/up2']).max())))
+    close(ops.modulated_conv2d(xm, T(g['modconv/w1']).to(DEV), s, demodulate=False), g['modconv/torgb'], tol * max(1.0, float(np.abs(g['modconv/torgb']).max())))
+    a, b, c = torch.randn(3, 1, 5, device=DEV), torch.randn(1, 4, 5, device=DEV), torch.randn(3, 4, 1, device=DEV)
+    close(ops.fma(a, b, c), (a * b + c), 1e-6)
+    inp, grid = torch.randn(2, 5, 9, 7, device=DEV), torch.rand(2, 6, 4, 2, device=DEV) * 2.4 - 1.2
+    close(ops.grid_sample(inp, grid), F.grid_sample(inp.cpu(), grid.cpu(), mode='bilinear', padding_mode='zeros', align_corners=False), 2e-6)
+    with pytest.raises(NotImplementedError):
+        ops.conv2d_resample(xm, w, f=f, down=2, padding=1)
