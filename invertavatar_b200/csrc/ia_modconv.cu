@@ -201,47 +201,128 @@ __device__ __forceinline__ float epi_value(float acc, const EpiArgs& e, int b, i
 // ------------------------------------------------------------------------------------------------
 // FIR epilogue for up=2 layers
 // ------------------------------------------------------------------------------------------------
-__global__ void fir_epilogue_kernel(ia_fir_params p) {
-    const int groups = p.C >> 2;
-    int64_t total = (int64_t)p.B * p.OH * p.OW * groups;
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    int g = i % groups; int64_t t = i / groups;
-    int ox = t % p.OW; t /= p.OW;
-    int oy = t % p.OH; int b = (int)(t / p.OH);
-    int c0 = g * 4;
-    // out[oy][ox] = sum_{ty,tx} F[ty][tx] * raw[oy+ty-1][ox+tx-1]   (pad [1,1,1,1]; F symmetric, gain folded in)
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+// Strip-mined: a thread owns 4 channels of one output column and walks FIR_YT consecutive output rows.  Each raw row it
+// reads (4 neighbouring float4, of which the next-column thread of the same block re-reads 3 -> L1 hits) is filtered
+// horizontally once and then contributes to the 4 output rows whose window covers it, held as 4 running accumulators;
+// every raw element comes from DRAM once (plus a 3/FIR_YT row halo) -- measured traffic = algorithmic bytes
+// (profiles/r1_fir_full.txt).  The 4x4 filter must be separable (rank 1), which the resample filter
+// outer([1,3,3,1]) of every synthesis layer is: its row/column factors are recovered from the row and column sums.
+constexpr int FIR_YT = 32;
+
+template <int ACT>
+__global__ void __launch_bounds__(256) fir_epilogue_kernel(ia_fir_params p, int cg, int xt, int cchunks) {
+    const int c4 = threadIdx.x % cg;
+    const int xl = threadIdx.x / cg;
+    const int ox = blockIdx.x * xt + xl;
+    const int oy0 = blockIdx.y * FIR_YT;
+    const int b = blockIdx.z / cchunks;
+    const int c0 = ((blockIdx.z % cchunks) * cg + c4) * 4;
+    if (ox >= p.OW || c0 >= p.C) return;
+    // out[oy][ox] = sum_{ty,tx} F[3-ty][3-tx] * raw[oy+ty-1][ox+tx-1]  (pad [1,1,1,1], gain folded in); F = fy (x) fx
+    float fy[4], fx[4];
+    {
+        float tot = 0.f, rs[4] = {0.f, 0.f, 0.f, 0.f}, cs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int ty = 0; ty < 4; ++ty) {
-        int ry = oy + ty - 1;
-        if (ry < 0 || ry >= p.RH) continue;
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int tx = 0; tx < 4; ++tx) {
-            int rx = ox + tx - 1;
-            if (rx < 0 || rx >= p.RW) continue;
-            float f = p.fir[(3 - ty) * 4 + (3 - tx)];
-            float4 r = *reinterpret_cast<const float4*>(p.raw + (((int64_t)b * p.RH + ry) * p.RW + rx) * p.C + c0);
-            acc[0] = fmaf(f, r.x, acc[0]); acc[1] = fmaf(f, r.y, acc[1]);
-            acc[2] = fmaf(f, r.z, acc[2]); acc[3] = fmaf(f, r.w, acc[3]);
-        }
+            for (int j = 0; j < 4; ++j) { const float f = p.fir[i * 4 + j]; rs[i] += f; cs[j] += f; tot += f; }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) { fy[t] = rs[3 - t]; fx[t] = cs[3 - t] / tot; }
     }
-    EpiArgs e{p.dcoef, p.noise, p.noise_strength, p.bias, p.act, p.alpha, p.gain, p.clamp};
-    float nz = p.noise ? p.noise[(int64_t)b * p.noise_bstride + (int64_t)oy * p.OW + ox] * p.noise_strength[0] : 0.f;
-    float v[4];
+    const int oy1 = min(oy0 + FIR_YT, p.OH);
+    float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0, acc2 = acc0, acc3 = acc0;   // output rows ry-2 .. ry+1
+    float dc[4], bs[4], s1[4], s2[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) v[k] = epi_value(acc[k], e, b, c0 + k, p.C, nz);
-    emit4(p.emit, b, ((int64_t)b * p.OH + oy) * p.OW + ox, c0, p.C, v);
+    for (int k = 0; k < 4; ++k) {
+        dc[k] = p.dcoef ? p.dcoef[(int64_t)b * p.C + c0 + k] : 1.f;
+        bs[k] = p.bias ? p.bias[c0 + k] : 0.f;
+        s1[k] = (p.emit.hi1 && p.emit.s1) ? p.emit.s1[(int64_t)b * p.C + c0 + k] : 1.f;
+        s2[k] = (p.emit.hi2 && p.emit.s2) ? p.emit.s2[(int64_t)b * p.C + c0 + k] : 1.f;
+    }
+    const float nstr = p.noise ? p.noise_strength[0] : 0.f;
+    const float* nptr = p.noise ? p.noise + (int64_t)b * p.noise_bstride + (int64_t)oy0 * p.OW + ox : nullptr;
+    const int64_t row_f = (int64_t)p.RW * p.C;
+    const float* rp = p.raw + (int64_t)b * p.RH * row_f + (int64_t)(oy0 - 1) * row_f + (int64_t)(ox - 1) * p.C + c0;
+    const bool v0 = ox - 1 >= 0, v3 = ox + 2 < p.RW;      // ox, ox+1 always valid (ox < OW = RW-1)
+    const int C = p.C;
+    int64_t opix = ((int64_t)b * p.OH + oy0) * p.OW + ox;
+    const float gain = p.gain, alpha = p.alpha, clampv = p.clamp;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    // raw row ry feeds output rows oy = ry+1-ty, ty = 0..3.  Walk ry from oy0-1 to oy1+1.
+    for (int ry = oy0 - 1; ry <= oy1 + 1; ++ry, rp += row_f) {
+        float4 r0 = z4, r1 = z4, r2 = z4, r3 = z4;
+        if (ry >= 0 && ry < p.RH) {
+            if (v0) r0 = __ldg(reinterpret_cast<const float4*>(rp));
+            r1 = __ldg(reinterpret_cast<const float4*>(rp + C));
+            r2 = __ldg(reinterpret_cast<const float4*>(rp + 2 * C));
+            if (v3) r3 = __ldg(reinterpret_cast<const float4*>(rp + 3 * C));
+        }
+        float4 h;
+        h.x = fmaf(fx[3], r3.x, fmaf(fx[2], r2.x, fmaf(fx[1], r1.x, fx[0] * r0.x)));
+        h.y = fmaf(fx[3], r3.y, fmaf(fx[2], r2.y, fmaf(fx[1], r1.y, fx[0] * r0.y)));
+        h.z = fmaf(fx[3], r3.z, fmaf(fx[2], r2.z, fmaf(fx[1], r1.z, fx[0] * r0.z)));
+        h.w = fmaf(fx[3], r3.w, fmaf(fx[2], r2.w, fmaf(fx[1], r1.w, fx[0] * r0.w)));
+        // acc_j accumulates output row (ry - 2 + j): raw row ry is its tap ty = 3 - j
+        acc0.x = fmaf(fy[3], h.x, acc0.x); acc0.y = fmaf(fy[3], h.y, acc0.y); acc0.z = fmaf(fy[3], h.z, acc0.z); acc0.w = fmaf(fy[3], h.w, acc0.w);
+        acc1.x = fmaf(fy[2], h.x, acc1.x); acc1.y = fmaf(fy[2], h.y, acc1.y); acc1.z = fmaf(fy[2], h.z, acc1.z); acc1.w = fmaf(fy[2], h.w, acc1.w);
+        acc2.x = fmaf(fy[1], h.x, acc2.x); acc2.y = fmaf(fy[1], h.y, acc2.y); acc2.z = fmaf(fy[1], h.z, acc2.z); acc2.w = fmaf(fy[1], h.w, acc2.w);
+        acc3.x = fy[0] * h.x; acc3.y = fy[0] * h.y; acc3.z = fy[0] * h.z; acc3.w = fy[0] * h.w;
+        if (ry - 2 >= oy0) {      // output row ry-2 (< oy1 by the loop bound) is complete
+            float nz = 0.f;
+            if (nptr) { nz = nptr[0] * nstr; nptr += p.OW; }
+            const float a4[4] = {acc0.x, acc0.y, acc0.z, acc0.w};
+            float v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float t = p.dcoef ? fmaf(a4[k], dc[k], nz) : a4[k] + nz;     // fma(x, dcoef, noise), networks_stylegan2_new.py:74
+                t += bs[k];
+                if (ACT == IA_ACT_LRELU) t = (t > 0.f ? t : t * alpha) * gain;
+                else if (ACT == IA_ACT_LINEAR) t = t * gain;
+                else t = apply_act(t, p.act, alpha) * gain;
+                if (clampv >= 0.f) t = fminf(fmaxf(t, -clampv), clampv);
+                v[k] = t;
+            }
+            if (p.emit.out32) {
+                float* o = p.emit.out32 + opix * p.emit.out32_ld + c0;
+                if ((p.emit.out32_ld & 3) == 0) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+                else { o[0] = v[0]; o[1] = v[1]; o[2] = v[2]; o[3] = v[3]; }
+            }
+            if (p.emit.hi1) {
+                uint16_t h16[4], l16[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) split_bf16(v[k] * s1[k], h16[k], l16[k]);
+                *reinterpret_cast<uint2*>(p.emit.hi1 + opix * p.emit.c1_pad + c0) = make_uint2(h16[0] | ((uint32_t)h16[1] << 16), h16[2] | ((uint32_t)h16[3] << 16));
+                *reinterpret_cast<uint2*>(p.emit.lo1 + opix * p.emit.c1_pad + c0) = make_uint2(l16[0] | ((uint32_t)l16[1] << 16), l16[2] | ((uint32_t)l16[3] << 16));
+            }
+            if (p.emit.hi2) {
+                uint16_t h16[4], l16[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) split_bf16(v[k] * s2[k], h16[k], l16[k]);
+                *reinterpret_cast<uint2*>(p.emit.hi2 + opix * p.emit.c2_pad + c0) = make_uint2(h16[0] | ((uint32_t)h16[1] << 16), h16[2] | ((uint32_t)h16[3] << 16));
+                *reinterpret_cast<uint2*>(p.emit.lo2 + opix * p.emit.c2_pad + c0) = make_uint2(l16[0] | ((uint32_t)l16[1] << 16), l16[2] | ((uint32_t)l16[3] << 16));
+            }
+            opix += p.OW;
+        }
+        acc0 = acc1; acc1 = acc2; acc2 = acc3;
+    }
 }
 
 extern "C" int ia_fir_epilogue(const ia_fir_params* p, void* stream) {
     IA_CHECK(p && p->raw && p->fir, "ia_fir_epilogue: null tensor");
     IA_CHECK((p->C & 3) == 0, "ia_fir_epilogue: C must be a multiple of 4");
+    IA_CHECK(p->RH == p->OH + 1 && p->RW == p->OW + 1, "ia_fir_epilogue: raw must be (OH+1) x (OW+1)");
     IA_CHECK(p->noise == nullptr || p->noise_strength != nullptr, "ia_fir_epilogue: noise needs noise_strength");
-    int64_t total = (int64_t)p->B * p->OH * p->OW * (p->C >> 2);
-    if (total == 0) return 0;
+    if ((int64_t)p->B * p->OH * p->OW * p->C == 0) return 0;
+    const int groups = p->C >> 2;
+    int cg = groups < 32 ? groups : 32;                 // channel groups (of 4) per block row; 32 -> one warp = 512 contiguous bytes
+    while (256 % cg) --cg;                              // block is 256 threads = cg x xt
+    const int xt = 256 / cg;
+    const int cchunks = (int)cdiv(groups, cg);
+    dim3 grid((unsigned)cdiv(p->OW, xt), (unsigned)cdiv(p->OH, FIR_YT), (unsigned)(p->B * cchunks));
     ia::prof_begin("ia_fir_epilogue", as_stream(stream));
-    fir_epilogue_kernel<<<(unsigned)cdiv(total, 256), 256, 0, as_stream(stream)>>>(*p);
+    if (p->act == IA_ACT_LRELU) fir_epilogue_kernel<IA_ACT_LRELU><<<grid, 256, 0, as_stream(stream)>>>(*p, cg, xt, cchunks);
+    else if (p->act == IA_ACT_LINEAR) fir_epilogue_kernel<IA_ACT_LINEAR><<<grid, 256, 0, as_stream(stream)>>>(*p, cg, xt, cchunks);
+    else fir_epilogue_kernel<-1><<<grid, 256, 0, as_stream(stream)>>>(*p, cg, xt, cchunks);
     IA_LAUNCH_CHECK("ia_fir_epilogue");
     return 0;
 }
