@@ -203,6 +203,26 @@ typedef struct {
 } ia_lerp_params;
 int ia_lerp_alpha(const ia_lerp_params* p, void* stream);
 
+/* One pyramid level of TriPlaneGenerator.rasterize (triplane_v20.py:328-338) without the [B][256][256][C] intermediate:
+ *   out = aa_resize(grid_sample(tex, uv))*alpha + aa_resize(static[crop])*(1 - alpha)
+ * as two passes: (1) grid_sample fused with the horizontal antialias taps -> tmp [B][UH][r][C]; (2) vertical taps + the
+ * (up-sampling) resize of the static crop + the alpha blend.  Tap tables as in ia_resize_aa: (ux_*) UW -> r, (uy_*) UH -> r,
+ * (sx_*) sw -> r, (sy_*) sh -> r.  tex is contiguous NHWC; C must be a multiple of 4. */
+typedef struct {
+    const float* tex; int32_t Ht, Wt, C;
+    const float* uv; int64_t uv_ld; int32_t UH, UW;
+    float* tmp;
+    const float* stat; int64_t stat_ld; int32_t SH, SW, sy0, sx0;
+    const float* alpha;
+    float* out; int64_t out_ld;
+    int32_t B, r;
+    const int32_t* ux_start; const int32_t* ux_count; const float* ux_w; int32_t ux_max_taps;
+    const int32_t* uy_start; const int32_t* uy_count; const float* uy_w; int32_t uy_max_taps;
+    const int32_t* sx_start; const int32_t* sx_count; const float* sx_w; int32_t sx_max_taps;
+    const int32_t* sy_start; const int32_t* sy_count; const float* sy_w; int32_t sy_max_taps;
+} ia_raster_level_params;
+int ia_raster_level(const ia_raster_level_params* p, void* stream);
+
 /* ---- volume renderer (renderer.py:309-469, ray_sampler.py:70-107, ray_marcher.py:25-57, triplane_v20.py:415-438) */
 typedef struct {
     const float* planes; int64_t plane_px_ld;    /* [B][PH][PW][>=96]: plane p = channels [32p, 32p+32) */

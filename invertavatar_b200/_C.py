@@ -94,6 +94,20 @@ class RenderParams(C.Structure):
                 ('feat', c_f32p), ('depth', c_f32p), ('wsum', c_f32p), ('depth_minmax', c_f32p)]
 
 
+class RasterLevelParams(C.Structure):
+    _fields_ = [('tex', c_f32p), ('Ht', C.c_int32), ('Wt', C.c_int32), ('C', C.c_int32),
+                ('uv', c_f32p), ('uv_ld', C.c_int64), ('UH', C.c_int32), ('UW', C.c_int32),
+                ('tmp', c_f32p),
+                ('stat', c_f32p), ('stat_ld', C.c_int64), ('SH', C.c_int32), ('SW', C.c_int32), ('sy0', C.c_int32), ('sx0', C.c_int32),
+                ('alpha', c_f32p),
+                ('out', c_f32p), ('out_ld', C.c_int64),
+                ('B', C.c_int32), ('r', C.c_int32),
+                ('ux_start', c_i32p), ('ux_count', c_i32p), ('ux_w', c_f32p), ('ux_max_taps', C.c_int32),
+                ('uy_start', c_i32p), ('uy_count', c_i32p), ('uy_w', c_f32p), ('uy_max_taps', C.c_int32),
+                ('sx_start', c_i32p), ('sx_count', c_i32p), ('sx_w', c_f32p), ('sx_max_taps', C.c_int32),
+                ('sy_start', c_i32p), ('sy_count', c_i32p), ('sy_w', c_f32p), ('sy_max_taps', C.c_int32)]
+
+
 class View(C.Structure):
     _fields_ = [('p', c_f32p), ('C', C.c_int32), ('ps', C.c_int32),
                 ('s_c', C.c_int64), ('s_pix', C.c_int64), ('s_row', C.c_int64), ('s_img', C.c_int64)]
@@ -141,6 +155,7 @@ SIGNATURES = {
     'ia_grid_sample': (C.c_int, [c_f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, c_f32p, C.c_int64, C.c_int32, C.c_int32, c_f32p, C.c_int64, C.c_void_p]),
     'ia_resize_aa': (C.c_int, [C.POINTER(ResizeParams), C.c_void_p]),
     'ia_lerp_alpha': (C.c_int, [C.POINTER(LerpParams), C.c_void_p]),
+    'ia_raster_level': (C.c_int, [C.POINTER(RasterLevelParams), C.c_void_p]),
     'ia_ray_bounds': (C.c_int, [c_f32p, C.c_int64, C.c_int32, c_f32p, C.c_void_p]),
     'ia_ray_bounds_from_origins': (C.c_int, [c_f32p, C.c_int64, c_f32p, C.c_void_p]),
     'ia_render': (C.c_int, [C.POINTER(RenderParams), C.c_void_p]),

@@ -232,3 +232,143 @@ extern "C" int ia_resize_aa(const ia_resize_params* p, void* stream) {
     IA_LAUNCH_CHECK("ia_resize_aa");
     return 0;
 }
+
+
+// ------------------------------------------------------------------------------------------------
+// fused rasterize level: grid_sample (+) horizontal antialias taps, then vertical taps + static resize + alpha blend
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+// pass 1: thread = (pixel (b, y, x'), lane); lane owns channel groups c4 = lane + LPP*k, k < KC (LPP lanes per pixel), so
+// every LDG.128 of a warp covers contiguous 16*LPP bytes of one texel and the coordinate / weight arithmetic of a tap is
+// done once per KC*4 loads.
+template <int KC>
+__global__ void __launch_bounds__(256) raster_hpass_kernel(ia_raster_level_params p, int lpp) {
+    const int64_t total = (int64_t)p.B * p.UH * p.r * lpp;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int lane = (int)(i % lpp);
+    int64_t t = i / lpp;
+    const int ox = (int)(t % p.r); t /= p.r;
+    const int y = (int)(t % p.UH); const int b = (int)(t / p.UH);
+    const int xs = p.ux_start[ox], xn = p.ux_count[ox];
+    const float* wx = p.ux_w + (int64_t)ox * p.ux_max_taps;
+    const float* uvrow = p.uv + ((int64_t)(b * p.UH + y) * p.UW + xs) * p.uv_ld;
+    const float* tbase = p.tex + (int64_t)b * p.Ht * p.Wt * p.C + lane * 4;
+    float4 acc[KC];
+#pragma unroll
+    for (int k = 0; k < KC; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int Wi = p.Wt, Hi = p.Ht;
+    const int kstride = lpp * 4;
+    for (int tx = 0; tx < xn; ++tx) {
+        const float gx = uvrow[(int64_t)tx * p.uv_ld + 0], gy = uvrow[(int64_t)tx * p.uv_ld + 1];
+        const float w = wx[tx];
+        // grid_sample(bilinear, zeros, align_corners=False), same arithmetic as grid_sample_kernel
+        const float ix = ((gx + 1.f) * Wi - 1.f) / 2.f;
+        const float iy = ((gy + 1.f) * Hi - 1.f) / 2.f;
+        const float fx = floorf(ix), fy = floorf(iy);
+        const int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;
+        const float wnw = ((float)x1 - ix) * ((float)y1 - iy);
+        const float wne = (ix - (float)x0) * ((float)y1 - iy);
+        const float wsw = ((float)x1 - ix) * (iy - (float)y0);
+        const float wse = (ix - (float)x0) * (iy - (float)y0);
+        const bool vx0 = x0 >= 0 && x0 < Wi, vx1 = x1 >= 0 && x1 < Wi, vy0 = y0 >= 0 && y0 < Hi, vy1 = y1 >= 0 && y1 < Hi;
+        float4 s[KC];
+#pragma unroll
+        for (int k = 0; k < KC; ++k) s[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        auto corner = [&](int yy, int xx, float cw) {
+            const float* q = tbase + ((int64_t)yy * Wi + xx) * p.C;
+#pragma unroll
+            for (int k = 0; k < KC; ++k) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(q + k * kstride));
+                s[k].x += v.x * cw; s[k].y += v.y * cw; s[k].z += v.z * cw; s[k].w += v.w * cw;
+            }
+        };
+        if (vy0 && vx0) corner(y0, x0, wnw);
+        if (vy0 && vx1) corner(y0, x1, wne);
+        if (vy1 && vx0) corner(y1, x0, wsw);
+        if (vy1 && vx1) corner(y1, x1, wse);
+#pragma unroll
+        for (int k = 0; k < KC; ++k) { acc[k].x += s[k].x * w; acc[k].y += s[k].y * w; acc[k].z += s[k].z * w; acc[k].w += s[k].w * w; }
+    }
+    float* o = p.tmp + ((int64_t)(b * p.UH + y) * p.r + ox) * p.C + lane * 4;
+#pragma unroll
+    for (int k = 0; k < KC; ++k) *reinterpret_cast<float4*>(o + k * kstride) = acc[k];
+}
+
+__global__ void __launch_bounds__(256) raster_vpass_kernel(ia_raster_level_params p) {
+    const int groups = p.C >> 2;
+    const int64_t total = (int64_t)p.B * p.r * p.r * groups;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c0 = (int)(i % groups) * 4;
+    int64_t t = i / groups;
+    const int ox = (int)(t % p.r); t /= p.r;
+    const int oy = (int)(t % p.r); const int b = (int)(t / p.r);
+    // vertical antialias taps over the horizontally filtered samples
+    float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+    {
+        const int ys = p.uy_start[oy], yn = p.uy_count[oy];
+        const float* wy = p.uy_w + (int64_t)oy * p.uy_max_taps;
+        const float* q = p.tmp + ((int64_t)(b * p.UH + ys) * p.r + ox) * p.C + c0;
+        for (int ty = 0; ty < yn; ++ty, q += (int64_t)p.r * p.C) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(q));
+            const float w = wy[ty];
+            f.x += v.x * w; f.y += v.y * w; f.z += v.z * w; f.w += v.w * w;
+        }
+    }
+    // static crop resized to r x r (rows of horizontal taps, then the vertical weight: ATen's pass order)
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    {
+        const int ys = p.sy_start[oy], yn = p.sy_count[oy], xs = p.sx_start[ox], xn = p.sx_count[ox];
+        const float* wy = p.sy_w + (int64_t)oy * p.sy_max_taps;
+        const float* wx = p.sx_w + (int64_t)ox * p.sx_max_taps;
+        const bool vec = (p.stat_ld & 3) == 0;
+        for (int ty = 0; ty < yn; ++ty) {
+            const float* row = p.stat + (((int64_t)b * p.SH + p.sy0 + ys + ty) * p.SW + p.sx0 + xs) * p.stat_ld + c0;
+            float4 rr = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int tx = 0; tx < xn; ++tx) {
+                const float* q = row + (int64_t)tx * p.stat_ld;
+                float4 v;
+                if (vec) v = __ldg(reinterpret_cast<const float4*>(q));
+                else v = make_float4(q[0], q[1], q[2], q[3]);
+                const float w = wx[tx];
+                rr.x += v.x * w; rr.y += v.y * w; rr.z += v.z * w; rr.w += v.w * w;
+            }
+            const float w = wy[ty];
+            s.x += rr.x * w; s.y += rr.y * w; s.z += rr.z * w; s.w += rr.w * w;
+        }
+    }
+    const float al = p.alpha[((int64_t)b * p.r + oy) * p.r + ox];
+    const float bl = 1.f - al;
+    float* o = p.out + (((int64_t)b * p.r + oy) * p.r + ox) * p.out_ld + c0;
+    const float4 res = make_float4(f.x * al + s.x * bl, f.y * al + s.y * bl, f.z * al + s.z * bl, f.w * al + s.w * bl);
+    if ((p.out_ld & 3) == 0) *reinterpret_cast<float4*>(o) = res;
+    else { o[0] = res.x; o[1] = res.y; o[2] = res.z; o[3] = res.w; }
+}
+
+}  // namespace
+
+extern "C" int ia_raster_level(const ia_raster_level_params* p, void* stream) {
+    IA_CHECK(p && p->tex && p->uv && p->tmp && p->stat && p->alpha && p->out, "ia_raster_level: null tensor");
+    IA_CHECK(p->C > 0 && (p->C & 3) == 0 && p->uv_ld >= 2 && p->stat_ld >= p->C && p->out_ld >= p->C, "ia_raster_level: bad channel count / strides");
+    IA_CHECK(p->ux_start && p->uy_start && p->sx_start && p->sy_start, "ia_raster_level: null tap table");
+    if ((int64_t)p->B * p->r * p->r == 0) return 0;
+    const int groups = p->C >> 2;
+    int kc = 1;
+    if (groups % 128 == 0) kc = 4; else if (groups % 64 == 0) kc = 2;
+    while (groups / kc > 32 && kc < 4) kc *= 2;
+    IA_CHECK(groups % kc == 0 && groups / kc <= 32, "ia_raster_level: unsupported channel count %d", p->C);
+    const int lpp = groups / kc;
+    const int64_t total1 = (int64_t)p->B * p->UH * p->r * lpp;
+    ia::prof_begin("ia_raster_level(hpass)", as_stream(stream));
+    if (kc == 4) raster_hpass_kernel<4><<<(unsigned)cdiv(total1, 256), 256, 0, as_stream(stream)>>>(*p, lpp);
+    else if (kc == 2) raster_hpass_kernel<2><<<(unsigned)cdiv(total1, 256), 256, 0, as_stream(stream)>>>(*p, lpp);
+    else raster_hpass_kernel<1><<<(unsigned)cdiv(total1, 256), 256, 0, as_stream(stream)>>>(*p, lpp);
+    IA_LAUNCH_CHECK("ia_raster_level(hpass)");
+    const int64_t total2 = (int64_t)p->B * p->r * p->r * groups;
+    ia::prof_begin("ia_raster_level(vpass)", as_stream(stream));
+    raster_vpass_kernel<<<(unsigned)cdiv(total2, 256), 256, 0, as_stream(stream)>>>(*p);
+    IA_LAUNCH_CHECK("ia_raster_level(vpass)");
+    return 0;
+}

@@ -571,6 +571,32 @@ def lerp_alpha(a, b, alpha, out=None):
     return out
 
 
+def raster_level(tex_nhwc, uv, stat_nhwc, crop, alpha_r, res):
+    """One rasterize pyramid level (triplane_v20.py:328-338) fused: aa_resize(grid_sample(tex, uv))*alpha +
+    aa_resize(static[crop])*(1-alpha) -> [B,res,res,C] without the 256^2 x C intermediate.
+    tex [B,Ht,Wt,C] contiguous; uv [B,UH,UW,>=2] contiguous; stat [B,SH,SW,>=C] NHWC view; crop = (y0,y1,x0,x1); alpha_r [B,res,res]."""
+    st = _enter(tex_nhwc)
+    B, Ht, Wt, Cc = tex_nhwc.shape
+    assert tex_nhwc.is_contiguous() and uv.is_contiguous() and alpha_r.is_contiguous() and Cc % 4 == 0
+    _, UH, UW, ul = uv.shape
+    SB, SH, SW, SC = stat_nhwc.shape
+    assert SC >= Cc and stat_nhwc.stride(3) == 1 and stat_nhwc.stride(1) == SW * stat_nhwc.stride(2) and stat_nhwc.stride(0) == SH * stat_nhwc.stride(1)
+    y0, y1, x0, x1 = crop
+    dev = tex_nhwc.device
+    uxs, uxc, uxw, uxm = aa_tables(UW, res, dev)
+    uys, uyc, uyw, uym = aa_tables(UH, res, dev)
+    sxs, sxc, sxw, sxm = aa_tables(x1 - x0, res, dev)
+    sys_, syc, syw, sym = aa_tables(y1 - y0, res, dev)
+    tmp = torch.empty((B, UH, res, Cc), dtype=torch.float32, device=dev)
+    out = torch.empty((B, res, res, Cc), dtype=torch.float32, device=dev)
+    p = _C.RasterLevelParams(_p(tex_nhwc), Ht, Wt, Cc, _p(uv), ul, UH, UW, _p(tmp), _p(stat_nhwc), stat_nhwc.stride(2), SH, SW, y0, x0,
+                             _p(alpha_r), _p(out), Cc, B, res,
+                             _p(uxs), _p(uxc), _p(uxw), uxm, _p(uys), _p(uyc), _p(uyw), uym,
+                             _p(sxs), _p(sxc), _p(sxw), sxm, _p(sys_), _p(syc), _p(syw), sym)
+    _C.check(_C.lib().ia_raster_level(C.byref(p), st), 'ia_raster_level')
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------
 # renderer
 # ---------------------------------------------------------------------------------------------------

@@ -106,14 +106,11 @@ class TriPlaneGenerator(torch.nn.Module):
                 continue
             res = tex.shape[1]
             bbox = [round(i * res / 256) for i in bbox_256]
-            rendering_image = rt.grid_sample_nhwc(tex, uv)                       # [B,256,256,C]
-            rendering_feat = rt.resize_aa(rendering_image, res, res)
             if res not in resized_alpha:
                 resized_alpha[res] = (rt.resize_aa(alpha4, res, res).squeeze(-1), rt.resize_aa(upper4, res, res).squeeze(-1))
             a_r, ua_r = resized_alpha[res]
-            st = static_feats[idx]
-            static_feat = rt.resize_aa(st, res, res, crop=(bbox[0], bbox[1], bbox[2], bbox[3]))
-            outs.append((rt.lerp_alpha(rendering_feat, static_feat, a_r), ua_r))
+            # grid_sample @256^2 -> aa-resize to res -> blend with the resized static crop, fused (no [B,256,256,C] tensor)
+            outs.append((rt.raster_level(tex, uv, static_feats[idx], (bbox[0], bbox[1], bbox[2], bbox[3]), a_r, res), ua_r))
         return outs, full_alpha, mouth
 
     def rasterize(self, texture_feats, uvcoords_image, static_feats, bbox_256):

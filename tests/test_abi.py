@@ -63,7 +63,7 @@ def _struct_fields(name):
                                           ('ia_modsplit_params', 'ModsplitParams'), ('ia_emit', 'Emit'), ('ia_conv_params', 'ConvParams'),
                                           ('ia_fir_params', 'FirParams'), ('ia_torgb_params', 'TorgbParams'),
                                           ('ia_resize_params', 'ResizeParams'), ('ia_lerp_params', 'LerpParams'),
-                                          ('ia_render_params', 'RenderParams'), ('ia_view', 'View'),
+                                          ('ia_render_params', 'RenderParams'), ('ia_view', 'View'), ('ia_raster_level_params', 'RasterLevelParams'),
                                           ('ia_enc_prep_params', 'EncPrepParams'), ('ia_enc_affine_params', 'EncAffineParams')])
 def test_ctypes_structs_follow_header(cname, pyname):
     from invertavatar_b200 import _C

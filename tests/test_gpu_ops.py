@@ -173,3 +173,29 @@ def test_reference_python_api_golden():
     close(ops.grid_sample(inp, grid), F.grid_sample(inp.cpu(), grid.cpu(), mode='bilinear', padding_mode='zeros', align_corners=False), 2e-6)
     with pytest.raises(NotImplementedError):
         ops.conv2d_resample(xm, w, f=f, down=2, padding=1)
+
+
+@pytest.mark.parametrize('Cc,tr,res', [(32, 32, 32), (512, 32, 32), (512, 64, 64), (256, 128, 128), (128, 256, 256), (24, 16, 64)])
+def test_raster_level_fused(Cc, tr, res):
+    """One rasterize level (triplane_v20.py:328-338), fused two-pass kernel vs torch on CPU and vs the reference's rasterize golden
+    path (grid_sample @256^2 -> antialiased resize -> alpha blend with the resized static crop)."""
+    g = torch.Generator().manual_seed(Cc + res)
+    B = 2
+    tex = torch.randn(B, Cc, tr, tr, generator=g)
+    uv = synth_uv(B)
+    stat = torch.randn(B, Cc + 8, tr, tr, generator=g)        # wider than C: the kernel reads a channel slice
+    bbox = [round(i * res / 256) for i in (57, 185, 64, 192)]
+    sb = [round(i * tr / 256) for i in (57, 185, 64, 192)]
+    alpha = F.interpolate(uv[..., 2].unsqueeze(1), size=(res, res), mode='bilinear', antialias=True)
+    ri = F.grid_sample(tex, uv[..., :2], mode='bilinear', padding_mode='zeros', align_corners=False)
+    rf = F.interpolate(ri, size=(res, res), mode='bilinear', antialias=True)
+    sf = F.interpolate(stat[:, :Cc, sb[0]:sb[1], sb[2]:sb[3]], size=(res, res), mode='bilinear', antialias=True)
+    want = rf * alpha + sf * (1 - alpha)
+    got = rt.raster_level(rt.to_nhwc(tex.to(DEV)), uv.to(DEV).contiguous(), rt.to_nhwc(stat.to(DEV))[..., :Cc], (sb[0], sb[1], sb[2], sb[3]),
+                          alpha[:, 0].contiguous().to(DEV), res)
+    close(rt.from_nhwc(got), want, 5e-6 * max(1.0, float(want.abs().max())), f'raster_level C={Cc} r={res}')
+
+
+def synth_uv(B):
+    from invertavatar_b200 import synth
+    return synth.uvcoords_image(B)
