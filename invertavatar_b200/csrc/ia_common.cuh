@@ -16,6 +16,7 @@ void count_launch();
 // the launching stream, IA_LAUNCH_CHECK closes the bracket.  Both are no-ops unless profiling is enabled.
 void prof_begin(const char* name, cudaStream_t stream);
 void prof_end();
+const char* prof_detail_name(const char* base, int ntaps, int gh, int gw, int cin, int cout);
 
 #define IA_CHECK(cond, ...)                                   \
     do {                                                      \

@@ -702,6 +702,15 @@ int launch_v2(const ia_conv_params* p, void* stream) {
     const uint32_t budget = 227u * 1024u - 1024u - 512u - kEpiBytes;
     // at least 2 + 2 slots; then spend the rest alternately (weights first: they turn over once per tap)
     t.a_slots = 2; t.b_slots = 2;
+    // a wide k-block with a tall halo tile may not leave room for 2 + 2 slots at the widest N tile: narrow the N tile
+    while (2u * (2u * t.a_bytes + 2u * t.b_bytes) > budget && n_tile > 32) {
+        int next = n_tile - 32;
+        while (next > 32 && p->Cout_pad % next) next -= 32;
+        n_tile = next;
+        t.n_tile = n_tile; t.n_tiles = p->Cout_pad / n_tile; t.total_tiles = t.m_tiles * t.n_tiles;
+        t.b_tx = (uint32_t)n_tile * BK * 2u;
+        t.b_bytes = (t.b_tx + 1023u) & ~1023u;
+    }
     IA_CHECK(2u * (2u * t.a_bytes + 2u * t.b_bytes) <= budget, "ia_conv_tc(v2): tile does not fit shared memory");
     for (;;) {
         uint32_t used_b = 2u * ((uint32_t)t.a_slots * t.a_bytes + (uint32_t)t.b_slots * t.b_bytes);
@@ -734,7 +743,7 @@ int launch_v2(const ia_conv_params* p, void* stream) {
         if (g_sm_count <= 0) g_sm_count = 148;
     }
     const int grid = t.total_tiles < g_sm_count ? t.total_tiles : g_sm_count;
-    ia::prof_begin("ia_conv_tc", as_stream(stream));
+    ia::prof_begin(ia::prof_detail_name("ia_conv_tc", p->ntaps, p->GH, p->GW, p->Cin_pad, p->Cout), as_stream(stream));
     conv_tc2_kernel<BK><<<grid, kThreads2, smem, as_stream(stream)>>>(ma_hi, ma_lo, mw_hi, mw_lo, t);
     IA_LAUNCH_CHECK("ia_conv_tc");
     return 0;
@@ -751,8 +760,15 @@ extern "C" int ia_conv_tc(const ia_conv_params* p, void* stream) {
     // layers (4x4, 8x8 and their transposed-conv phase grids) pack several images into a tile with the v1 kernel below.
     {
         static int mode = -1;   // IA_CONV_TC: 0 = v1 only, 32 / 64 = v2 with that k-block (default 32)
+        static int mode_few = -1;   // IA_CONV_TC_FEW: k-block for launches with <= 4 taps (transposed-conv phases, 1x1): these
+                                    // issue few MMAs per activation tile, so the TMA row rate (one request per 64/128-byte
+                                    // row) bounds them and 128-byte rows (k-block 64) halve the request count
         if (mode < 0) { const char* e = getenv("IA_CONV_TC"); mode = e ? atoi(e) : 32; }
-        if (mode != 0 && p->GH * p->GW >= 128 && p->GW >= 8) return mode == 64 ? launch_v2<64>(p, stream) : launch_v2<32>(p, stream);
+        if (mode_few < 0) { const char* e = getenv("IA_CONV_TC_FEW"); mode_few = e ? atoi(e) : 32; }
+        if (mode != 0 && p->GH * p->GW >= 128 && p->GW >= 8) {
+            const int bk = (p->ntaps <= 4) ? mode_few : mode;
+            return bk == 64 ? launch_v2<64>(p, stream) : launch_v2<32>(p, stream);
+        }
     }
     TcParams t;
     memset(&t, 0, sizeof(t));
@@ -800,7 +816,7 @@ extern "C" int ia_conv_tc(const ia_conv_params* p, void* stream) {
         IA_CHECK(e == cudaSuccess, "ia_conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     }
     dim3 grid((unsigned)(t.tiles_x * t.tiles_y * tiles_n), (unsigned)(p->Cout_pad / n_tile));
-    ia::prof_begin("ia_conv_tc", as_stream(stream));
+    ia::prof_begin(ia::prof_detail_name("ia_conv_tc", p->ntaps, p->GH, p->GW, p->Cin_pad, p->Cout), as_stream(stream));
     conv_tc_kernel<<<grid, kThreads, smem, as_stream(stream)>>>(ma_hi, ma_lo, mw_hi, mw_lo, t);
     IA_LAUNCH_CHECK("ia_conv_tc");
     return 0;

@@ -368,13 +368,57 @@ __global__ void torgb_finish_kernel(ia_torgb_params p) {
     else p.img_out[(((int64_t)b * p.H + y) * p.W + x) * p.C + c] = v;
 }
 
+// 4 channels per thread, 32-bit index arithmetic (NHWC output, C % 4 == 0): the element-per-thread kernel above spends its
+// time in 64-bit divisions, not in memory.
+__global__ void __launch_bounds__(256) torgb_finish_vec4_kernel(ia_torgb_params p) {
+    const int groups = p.C >> 2;
+    const unsigned total = (unsigned)p.B * p.H * p.W * groups;
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)(i % groups) * 4;
+    unsigned t = i / groups;
+    const int x = (int)(t % p.W); t /= p.W;
+    const int y = (int)(t % p.H); const int b = (int)(t / p.H);
+    const int64_t pix = ((int64_t)b * p.H + y) * p.W + x;
+    float4 v;
+    if ((p.raw_ld & 3) == 0) v = __ldg(reinterpret_cast<const float4*>(p.raw + pix * p.raw_ld + c));
+    else { const float* q = p.raw + pix * p.raw_ld + c; v = make_float4(q[0], q[1], q[2], q[3]); }
+    if (p.bias) { const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + c)); v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w; }
+    if (p.clamp >= 0.f) {
+        v.x = fminf(fmaxf(v.x, -p.clamp), p.clamp); v.y = fminf(fmaxf(v.y, -p.clamp), p.clamp);
+        v.z = fminf(fmaxf(v.z, -p.clamp), p.clamp); v.w = fminf(fmaxf(v.w, -p.clamp), p.clamp);
+    }
+    if (p.img_prev) {
+        const int h2 = p.H >> 1, w2 = p.W >> 1;
+        const int my = y >> 1, mx = x >> 1;
+        int y0, y1, x0, x1; float wy0, wy1, wx0, wx1;
+        if (y & 1) { y0 = my; y1 = my + 1; wy0 = 0.75f; wy1 = 0.25f; } else { y0 = my - 1; y1 = my; wy0 = 0.25f; wy1 = 0.75f; }
+        if (x & 1) { x0 = mx; x1 = mx + 1; wx0 = 0.75f; wx1 = 0.25f; } else { x0 = mx - 1; x1 = mx; wx0 = 0.25f; wx1 = 0.75f; }
+        const float* ip = p.img_prev + (int64_t)b * h2 * w2 * p.C + c;
+        float4 up = make_float4(0.f, 0.f, 0.f, 0.f);
+        auto tap = [&](int yy, int xx, float w) {
+            if (yy < 0 || yy >= h2 || xx < 0 || xx >= w2) return;
+            const float4 q = __ldg(reinterpret_cast<const float4*>(ip + ((int64_t)yy * w2 + xx) * p.C));
+            up.x = fmaf(w, q.x, up.x); up.y = fmaf(w, q.y, up.y); up.z = fmaf(w, q.z, up.z); up.w = fmaf(w, q.w, up.w);
+        };
+        tap(y0, x0, wy0 * wx0); tap(y0, x1, wy0 * wx1); tap(y1, x0, wy1 * wx0); tap(y1, x1, wy1 * wx1);
+        v.x += up.x; v.y += up.y; v.z += up.z; v.w += up.w;
+    }
+    *reinterpret_cast<float4*>(p.img_out + pix * p.C + c) = v;
+}
+
 extern "C" int ia_torgb_finish(const ia_torgb_params* p, void* stream) {
     IA_CHECK(p && p->raw && p->img_out, "ia_torgb_finish: null tensor");
     IA_CHECK(p->img_prev == nullptr || ((p->H & 1) == 0 && (p->W & 1) == 0), "ia_torgb_finish: odd size with skip image");
     int64_t total = (int64_t)p->B * p->H * p->W * p->C;
     if (total == 0) return 0;
     ia::prof_begin("ia_torgb_finish", as_stream(stream));
-    torgb_finish_kernel<<<(unsigned)cdiv(total, 256), 256, 0, as_stream(stream)>>>(*p);
+    if (!p->out_nchw && (p->C & 3) == 0 && total / 4 < (int64_t)0x7fffffff &&
+        (reinterpret_cast<uintptr_t>(p->img_out) & 15) == 0 && (p->bias == nullptr || (reinterpret_cast<uintptr_t>(p->bias) & 15) == 0) &&
+        (p->img_prev == nullptr || (reinterpret_cast<uintptr_t>(p->img_prev) & 15) == 0) && (reinterpret_cast<uintptr_t>(p->raw) & 15) == 0)
+        torgb_finish_vec4_kernel<<<(unsigned)cdiv(total / 4, 256), 256, 0, as_stream(stream)>>>(*p);
+    else
+        torgb_finish_kernel<<<(unsigned)cdiv(total, 256), 256, 0, as_stream(stream)>>>(*p);
     IA_LAUNCH_CHECK("ia_torgb_finish");
     return 0;
 }

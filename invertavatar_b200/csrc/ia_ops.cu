@@ -8,6 +8,7 @@
 #include <string>
 #include <vector>
 
+#include <stdlib.h>
 #include "ia_common.cuh"
 
 namespace ia {
@@ -37,6 +38,19 @@ void prof_begin(const char* name, cudaStream_t stream) {
     g_prof.push_back(r);
     g_prof_open = (int)g_prof.size() - 1;
     g_prof_stream = stream;
+}
+// IA_PROF_DETAIL=1: per-shape names for the convolution launches (tools/prof_layers.py); interned, never freed.
+const char* prof_detail_name(const char* base, int ntaps, int gh, int gw, int cin, int cout) {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("IA_PROF_DETAIL"); on = (e && atoi(e)) ? 1 : 0; }
+    if (!on || !g_prof_on) return base;
+    static std::map<std::string, std::string*> names;
+    char tmp[160];
+    snprintf(tmp, sizeof(tmp), "%s[t%d %dx%d %d->%d]", base, ntaps, gh, gw, cin, cout);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    auto it = names.find(tmp);
+    if (it == names.end()) it = names.emplace(tmp, new std::string(tmp)).first;
+    return it->second->c_str();
 }
 void prof_end() {
     if (g_prof_open < 0) return;
