@@ -174,7 +174,8 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
+        import datetime
+        dist.init_process_group('nccl', device_id=dev, timeout=datetime.timedelta(seconds=180))
 
     B, res, D = args.batch, args.res, args.depth
     torch.manual_seed(0)
@@ -231,24 +232,27 @@ def run_b200(args):
             step_resident()
         clocks = ClockSampler(local)
         if rank == 0:
-            clocks.start()
+            clocks.start()   # samples every 200 ms across both timed regions (resident + end-to-end)
         rt.reset_launch_count()
         ms = timed(step_resident, args.steps)
         launches = rt.launch_count()
-        clk = clocks.stop() if rank == 0 else None
         for _ in range(2):
             step_e2e()
         ms_e2e = timed(step_e2e, args.steps)
+        clk = clocks.stop() if rank == 0 else None
 
         roofline = None
         breakdown = None
-        if rank == 0 and not args.no_roofline:
-            # same steps again with every launch bracketed by CUDA events on the launching stream
-            torch.cuda.synchronize()
+        if not args.no_roofline:
+            # same steps again with every launch bracketed by CUDA events on the launching stream (every rank runs them so
+            # that the image all-gather stays matched; rank 0 reports)
+            barrier()
             rt.profile_begin()
             for _ in range(args.steps):
                 step_resident()
             rep = rt.profile_report()
+            barrier()
+        if rank == 0 and not args.no_roofline:
             conv = rep.get('ia_conv_tc', {'ms': 0.0, 'launches': 0})
             flops = conv_flops_per_frame(G) * B * args.steps
             peaks = {}
