@@ -134,24 +134,30 @@ __device__ __forceinline__ void plane_gather8(const float* __restrict__ plane_ba
     const float wsw = ((float)x1 - ix) * (iy - (float)y0);
     const float wse = (ix - (float)x0) * (iy - (float)y0);
     const bool vx0 = x0 >= 0 && x0 < PW, vx1 = x1 >= 0 && x1 < PW, vy0 = y0 >= 0 && y0 < PH, vy1 = y1 >= 0 && y1 < PH;
-    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    // issue all eight 16-byte loads before using any (memory-level parallelism)
-    const float* p00 = plane_base + ((int64_t)y0 * PW + x0) * px_ld;
-    const float* p01 = plane_base + ((int64_t)y0 * PW + x1) * px_ld;
-    const float* p10 = plane_base + ((int64_t)y1 * PW + x0) * px_ld;
-    const float* p11 = plane_base + ((int64_t)y1 * PW + x1) * px_ld;
-    const bool v00 = vy0 && vx0, v01 = vy0 && vx1, v10 = vy1 && vx0, v11 = vy1 && vx1;
-    const float4 a0 = v00 ? __ldg(reinterpret_cast<const float4*>(p00)) : z, a1 = v00 ? __ldg(reinterpret_cast<const float4*>(p00 + 16)) : z;
-    const float4 b0 = v01 ? __ldg(reinterpret_cast<const float4*>(p01)) : z, b1 = v01 ? __ldg(reinterpret_cast<const float4*>(p01 + 16)) : z;
-    const float4 c0 = v10 ? __ldg(reinterpret_cast<const float4*>(p10)) : z, c1 = v10 ? __ldg(reinterpret_cast<const float4*>(p10 + 16)) : z;
-    const float4 d0 = v11 ? __ldg(reinterpret_cast<const float4*>(p11)) : z, d1 = v11 ? __ldg(reinterpret_cast<const float4*>(p11 + 16)) : z;
-    float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#define IA_TAP(ok_, lo4_, hi4_, wt_)                                                                          \
-    if (ok_) {                                                                                                    \
-        s[0] += lo4_.x * wt_; s[1] += lo4_.y * wt_; s[2] += lo4_.z * wt_; s[3] += lo4_.w * wt_;                   \
-        s[4] += hi4_.x * wt_; s[5] += hi4_.y * wt_; s[6] += hi4_.z * wt_; s[7] += hi4_.w * wt_;                   \
-    }
-    IA_TAP(v00, a0, a1, wnw) IA_TAP(v01, b0, b1, wne) IA_TAP(v10, c0, c1, wsw) IA_TAP(v11, d0, d1, wse)
+    // Branch-free zero padding: an out-of-range corner reads a clamped (valid) texel with weight 0, so all eight 16-byte
+    // loads are issued unconditionally and back to back (memory-level parallelism, no divergence bookkeeping); adding
+    // v*0 leaves the sum unchanged, so the result equals the skip-the-corner formulation bit for bit.
+    const int x0c = min(max(x0, 0), PW - 1), x1c = min(max(x1, 0), PW - 1);
+    const int y0c = min(max(y0, 0), PH - 1), y1c = min(max(y1, 0), PH - 1);
+    const float w00 = (vy0 && vx0) ? wnw : 0.f, w01 = (vy0 && vx1) ? wne : 0.f;
+    const float w10 = (vy1 && vx0) ? wsw : 0.f, w11 = (vy1 && vx1) ? wse : 0.f;
+    const float* r0 = plane_base + (int64_t)(y0c * PW) * px_ld;
+    const float* r1 = plane_base + (int64_t)(y1c * PW) * px_ld;
+    const float* p00 = r0 + (int64_t)x0c * px_ld;
+    const float* p01 = r0 + (int64_t)x1c * px_ld;
+    const float* p10 = r1 + (int64_t)x0c * px_ld;
+    const float* p11 = r1 + (int64_t)x1c * px_ld;
+    const float4 a0 = __ldg(reinterpret_cast<const float4*>(p00)), a1 = __ldg(reinterpret_cast<const float4*>(p00 + 16));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p01)), b1 = __ldg(reinterpret_cast<const float4*>(p01 + 16));
+    const float4 c0 = __ldg(reinterpret_cast<const float4*>(p10)), c1 = __ldg(reinterpret_cast<const float4*>(p10 + 16));
+    const float4 d0 = __ldg(reinterpret_cast<const float4*>(p11)), d1 = __ldg(reinterpret_cast<const float4*>(p11 + 16));
+    float s[8];
+    s[0] = a0.x * w00; s[1] = a0.y * w00; s[2] = a0.z * w00; s[3] = a0.w * w00;
+    s[4] = a1.x * w00; s[5] = a1.y * w00; s[6] = a1.z * w00; s[7] = a1.w * w00;
+#define IA_TAP(lo4_, hi4_, wt_)                                                                                   \
+    s[0] += lo4_.x * wt_; s[1] += lo4_.y * wt_; s[2] += lo4_.z * wt_; s[3] += lo4_.w * wt_;                       \
+    s[4] += hi4_.x * wt_; s[5] += hi4_.y * wt_; s[6] += hi4_.z * wt_; s[7] += hi4_.w * wt_;
+    IA_TAP(b0, b1, w01) IA_TAP(c0, c1, w10) IA_TAP(d0, d1, w11)
 #undef IA_TAP
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k] += s[k];
@@ -181,7 +187,7 @@ __device__ __forceinline__ void gather_mlp_pass(const ia_render_params& p, const
             plane_gather8(pb + 32, p.plane_px_ld, p.PH, p.PW, qx, qz, acc);   // plane 1: (x, z)
             plane_gather8(pb + 64, p.plane_px_ld, p.PH, p.PW, qz, qx, acc);   // plane 2: (z, x)
 #pragma unroll
-            for (int k = 0; k < 8; ++k) feat[rr][k] = acc[k] / 3.0f;           // mean over the three planes
+            for (int k = 0; k < 8; ++k) feat[rr][k] = acc[k] * (1.0f / 3.0f);  // mean over the three planes (<= 1 ulp from the division)
         }
         // ---- layer 1: [16 x 32] x [32 x 64] ----
         uint32_t ah[2][4], al[2][4];
@@ -244,8 +250,8 @@ __device__ __forceinline__ void gather_mlp_pass(const ia_render_params& p, const
                 float* row = col + (s0 + sidx) * kRowLd;
 #pragma unroll
                 for (int nt = 0; nt < 4; ++nt) {
-                    const float v0 = 1.0f / (1.0f + __expf(-out[nt][2 * rr + 0]));
-                    const float v1 = 1.0f / (1.0f + __expf(-out[nt][2 * rr + 1]));
+                    const float v0 = __fdividef(1.0f, 1.0f + __expf(-out[nt][2 * rr + 0]));
+                    const float v1 = __fdividef(1.0f, 1.0f + __expf(-out[nt][2 * rr + 1]));
                     *reinterpret_cast<float2*>(row + nt * 8 + 2 * t) =
                         make_float2(v0 * (1.0f + 2.0f * 0.001f) - 0.001f, v1 * (1.0f + 2.0f * 0.001f) - 0.001f);
                 }
@@ -384,8 +390,12 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1) render_kernel(const i
             __syncwarp();
             for (int f = lane; f < p.Df; f += 32) {
                 const float u = p.u ? p.u[ray * p.Df + f] : linspace_at(0.0f, 1.0f, p.Df, f);
-                int inds = 0;   // searchsorted(cdf, u, right=True) over nb+1 entries
-                for (int k = 0; k <= nb; ++k) inds += (cdf[k] <= u) ? 1 : 0;
+                int inds = 0;   // searchsorted(cdf, u, right=True) over the nb+1 non-decreasing entries: #{k : cdf[k] <= u}
+                {
+                    int lo_i = 0, hi_i = nb + 1;
+                    while (lo_i < hi_i) { const int mid = (lo_i + hi_i) >> 1; if (cdf[mid] <= u) lo_i = mid + 1; else hi_i = mid; }
+                    inds = lo_i;
+                }
                 const int below = max(inds - 1, 0);
                 const int above = min(inds, nb);
                 const float c0 = cdf[below], c1 = cdf[above];
@@ -400,14 +410,38 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1) render_kernel(const i
             gather_mlp_pass(p, planes_b, r, dep, col, sig, p.Dc, p.Df, lane, dec);
             __syncwarp();
             // ---- merge: stable rank of every sample among all S (unify_samples, renderer.py:372-382) ----
-            for (int s = lane; s < S; s += 32) {
-                const float ds = dep[s];
-                int rank = 0;
-                for (int j = 0; j < S; ++j) {
-                    const float dj = dep[j];
-                    rank += (dj < ds || (dj == ds && j < s)) ? 1 : 0;
+            // Both lists are normally already sorted (coarse: jitter < bin width; fine: deterministic u), in which case the
+            // stable rank is a 2-way merge: coarse s -> s + #{fine < d_s}, fine f -> f + #{coarse <= d_f} (binary searches).
+            // Anything else (random u, or a rounding inversion at a bin edge) takes the exact O(S^2) rank.
+            bool sorted_ok = true;
+            for (int s = lane; s < S - 1; s += 32)
+                if (s != p.Dc - 1 && dep[s] > dep[s + 1]) sorted_ok = false;
+            sorted_ok = __all_sync(0xffffffffu, sorted_ok);
+            if (sorted_ok) {
+                for (int s = lane; s < S; s += 32) {
+                    const float ds = dep[s];
+                    int lo_i, hi_i, rank;
+                    if (s < p.Dc) {      // lower_bound over the fine list
+                        lo_i = p.Dc; hi_i = S;
+                        while (lo_i < hi_i) { const int mid = (lo_i + hi_i) >> 1; if (dep[mid] < ds) lo_i = mid + 1; else hi_i = mid; }
+                        rank = s + (lo_i - p.Dc);
+                    } else {             // upper_bound over the coarse list
+                        lo_i = 0; hi_i = p.Dc;
+                        while (lo_i < hi_i) { const int mid = (lo_i + hi_i) >> 1; if (dep[mid] <= ds) lo_i = mid + 1; else hi_i = mid; }
+                        rank = (s - p.Dc) + lo_i;
+                    }
+                    sd[rank] = ds; ssg[rank] = sig[s]; perm[rank] = s;
                 }
-                sd[rank] = ds; ssg[rank] = sig[s]; perm[rank] = s;
+            } else {
+                for (int s = lane; s < S; s += 32) {
+                    const float ds = dep[s];
+                    int rank = 0;
+                    for (int j = 0; j < S; ++j) {
+                        const float dj = dep[j];
+                        rank += (dj < ds || (dj == ds && j < s)) ? 1 : 0;
+                    }
+                    sd[rank] = ds; ssg[rank] = sig[s]; perm[rank] = s;
+                }
             }
             n_all = S;
             __syncwarp();
