@@ -351,7 +351,7 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr) {
     return d;
 }
 
-constexpr int kV2MaxASlots = 4, kV2MaxBSlots = 8;
+constexpr int kV2MaxASlots = 6, kV2MaxBSlots = 8;
 
 struct Tc2Params {
     int B, GH, GW, TH, tw, tiles_x, tiles_y, m_tiles, n_tiles, total_tiles;
@@ -368,6 +368,7 @@ struct Tc2Params {
     long long noise_bstride;
     int act; float alpha, gain, clamp;
     ia_emit emit;
+    int epi_vec4;                  // 1: Cout % 4 == 0 and every output pointer / pitch is 16-byte friendly -> epilogue_chunk_v4
 };
 
 
@@ -413,6 +414,82 @@ __device__ __forceinline__ void epilogue_chunk(const Tc2Params& p, const float* 
             h2[o] = h; l2[o] = l;
         }
     }
+}
+
+// Vectorised variant (Cout % 4 == 0, 16-byte aligned outputs): lane = (row_sub = lane/8, c4 = lane%8) owns 4 consecutive
+// channels of row 4*i + row_sub, so one pass over a [32 rows][32 channels] chunk is 8 iterations of {LDS.128, 2 shuffles,
+// 4-wide epilogue math, 16-byte fp32 / 8-byte bf16 stores} instead of 32 iterations of scalar work -- the scalar loop
+// costs ~80 instructions per row and bounds every few-tap launch (profiles/r1_conv_up_phase.txt).  tsm is [32][36] floats.
+constexpr int kTsmLd = 36;
+template <int ACT, bool O32, bool E1, bool E2>
+__device__ __forceinline__ void epilogue_chunk_v4(const Tc2Params& p, const float* tsm, int lane, uint32_t vmask, int my_pix, float my_nz,
+                                                  float* o32, uint16_t* h1, uint16_t* l1, uint16_t* h2, uint16_t* l2,
+                                                  const float4 dc, const float4 bs, const float4 s1, const float4 s2) {
+    const int rs = lane >> 3, c4 = lane & 7;
+    const float gain = p.gain, alpha = p.alpha, clampv = p.clamp;
+    const bool do_clamp = clampv >= 0.f;
+#pragma unroll 2
+    for (int i = 0; i < 8; ++i) {
+        const int rr = 4 * i + rs;
+        const int pix_r = __shfl_sync(0xffffffffu, my_pix, rr);
+        float nz = 0.f;
+        if (ACT != 0) nz = __shfl_sync(0xffffffffu, my_nz, rr);
+        if (!((vmask >> rr) & 1u)) continue;
+        float4 a = *reinterpret_cast<const float4*>(tsm + rr * kTsmLd + c4 * 4);
+        if (ACT != 0) {
+            a.x = fmaf(a.x, dc.x, nz) + bs.x; a.y = fmaf(a.y, dc.y, nz) + bs.y;
+            a.z = fmaf(a.z, dc.z, nz) + bs.z; a.w = fmaf(a.w, dc.w, nz) + bs.w;
+            if (ACT == IA_ACT_LRELU) {
+                a.x = (a.x > 0.f ? a.x : a.x * alpha) * gain; a.y = (a.y > 0.f ? a.y : a.y * alpha) * gain;
+                a.z = (a.z > 0.f ? a.z : a.z * alpha) * gain; a.w = (a.w > 0.f ? a.w : a.w * alpha) * gain;
+            } else if (ACT == IA_ACT_LINEAR) {
+                a.x *= gain; a.y *= gain; a.z *= gain; a.w *= gain;
+            } else {
+                a.x = apply_act(a.x, p.act, alpha) * gain; a.y = apply_act(a.y, p.act, alpha) * gain;
+                a.z = apply_act(a.z, p.act, alpha) * gain; a.w = apply_act(a.w, p.act, alpha) * gain;
+            }
+            if (do_clamp) {
+                a.x = fminf(fmaxf(a.x, -clampv), clampv); a.y = fminf(fmaxf(a.y, -clampv), clampv);
+                a.z = fminf(fmaxf(a.z, -clampv), clampv); a.w = fminf(fmaxf(a.w, -clampv), clampv);
+            }
+        }
+        if (O32) *reinterpret_cast<float4*>(o32 + (int64_t)pix_r * p.emit.out32_ld) = a;
+        if (E1) {
+            uint16_t h[4], l[4];
+            split_bf16(a.x * s1.x, h[0], l[0]); split_bf16(a.y * s1.y, h[1], l[1]);
+            split_bf16(a.z * s1.z, h[2], l[2]); split_bf16(a.w * s1.w, h[3], l[3]);
+            const int64_t o = (int64_t)pix_r * p.emit.c1_pad;
+            *reinterpret_cast<uint2*>(h1 + o) = make_uint2(h[0] | ((uint32_t)h[1] << 16), h[2] | ((uint32_t)h[3] << 16));
+            *reinterpret_cast<uint2*>(l1 + o) = make_uint2(l[0] | ((uint32_t)l[1] << 16), l[2] | ((uint32_t)l[3] << 16));
+        }
+        if (E2) {
+            uint16_t h[4], l[4];
+            split_bf16(a.x * s2.x, h[0], l[0]); split_bf16(a.y * s2.y, h[1], l[1]);
+            split_bf16(a.z * s2.z, h[2], l[2]); split_bf16(a.w * s2.w, h[3], l[3]);
+            const int64_t o = (int64_t)pix_r * p.emit.c2_pad;
+            *reinterpret_cast<uint2*>(h2 + o) = make_uint2(h[0] | ((uint32_t)h[1] << 16), h[2] | ((uint32_t)h[3] << 16));
+            *reinterpret_cast<uint2*>(l2 + o) = make_uint2(l[0] | ((uint32_t)l[1] << 16), l[2] | ((uint32_t)l[3] << 16));
+        }
+    }
+}
+
+template <int ACT>
+__device__ __forceinline__ void epilogue_chunk_v4_dispatch(const Tc2Params& p, const float* tsm, int lane, uint32_t vmask, int my_pix, float my_nz,
+                                                           float* o32, uint16_t* h1, uint16_t* l1, uint16_t* h2, uint16_t* l2,
+                                                           const float4 dc, const float4 bs, const float4 s1, const float4 s2) {
+    const int sel = (o32 ? 1 : 0) | (h1 ? 2 : 0) | (h2 ? 4 : 0);
+#define IA_EPI(O, A, B) epilogue_chunk_v4<ACT, O, A, B>(p, tsm, lane, vmask, my_pix, my_nz, o32, h1, l1, h2, l2, dc, bs, s1, s2)
+    switch (sel) {
+        case 1: IA_EPI(true, false, false); break;
+        case 2: IA_EPI(false, true, false); break;
+        case 3: IA_EPI(true, true, false); break;
+        case 4: IA_EPI(false, false, true); break;
+        case 5: IA_EPI(true, false, true); break;
+        case 6: IA_EPI(false, true, true); break;
+        case 7: IA_EPI(true, true, true); break;
+        default: break;
+    }
+#undef IA_EPI
 }
 
 constexpr int kEpiWarps2 = 8;                       // epilogue warps of the v2 kernel: 2 per TMEM lane quarter (one per half tile)
@@ -554,7 +631,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         // store instruction writes one contiguous run (128 B of fp32 or 64 B of bf16) of a single pixel.
         const int lg = warp & 3;
         const int half = (warp - 2) >> 2;           // which 128-pixel half of the tile this warp drains
-        float* tsm = reinterpret_cast<float*>(smem_raw + (epi_base - smem_u32(smem_raw))) + (warp - 2) * (32 * 33);
+        float* tsm = reinterpret_cast<float*>(smem_raw + (epi_base - smem_u32(smem_raw))) + (warp - 2) * (32 * kTsmLd);
         const int tw_shift = p.tw == 8 ? 3 : (p.tw == 16 ? 4 : 5);
         uint32_t j = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++j) {
@@ -585,6 +662,36 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                     tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + tcol + (uint32_t)c, r);
                     if (vmask == 0u) continue;
                     __syncwarp();
+                    if (p.epi_vec4) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            *reinterpret_cast<float4*>(tsm + lane * kTsmLd + 4 * q) =
+                                make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+                        __syncwarp();
+                        const int co0 = col0 + c + 4 * (lane & 7);
+                        const bool cval = co0 < p.Cout;
+                        float4 dc4 = make_float4(1.f, 1.f, 1.f, 1.f), bs4 = make_float4(0.f, 0.f, 0.f, 0.f), s14 = dc4, s24 = dc4;
+                        if (cval) {
+                            if (p.mode == 1) {
+                                if (p.dcoef) dc4 = *reinterpret_cast<const float4*>(p.dcoef + (int64_t)img * p.Cout + co0);
+                                if (p.bias) bs4 = *reinterpret_cast<const float4*>(p.bias + co0);
+                            }
+                            if (p.emit.hi1 && p.emit.s1) s14 = *reinterpret_cast<const float4*>(p.emit.s1 + (int64_t)img * p.Cout + co0);
+                            if (p.emit.hi2 && p.emit.s2) s24 = *reinterpret_cast<const float4*>(p.emit.s2 + (int64_t)img * p.Cout + co0);
+                        }
+                        // rows of lanes whose channel group is past Cout are masked out, the shuffles inside stay warp-wide
+                        const uint32_t vm = cval ? vmask : 0u;
+                        float* o32 = p.emit.out32 ? p.emit.out32 + img_pix0 * p.emit.out32_ld + co0 : nullptr;
+                        uint16_t* h1 = p.emit.hi1 ? p.emit.hi1 + img_pix0 * p.emit.c1_pad + co0 : nullptr;
+                        uint16_t* l1 = p.emit.hi1 ? p.emit.lo1 + img_pix0 * p.emit.c1_pad + co0 : nullptr;
+                        uint16_t* h2 = p.emit.hi2 ? p.emit.hi2 + img_pix0 * p.emit.c2_pad + co0 : nullptr;
+                        uint16_t* l2 = p.emit.hi2 ? p.emit.lo2 + img_pix0 * p.emit.c2_pad + co0 : nullptr;
+                        if (p.mode == 0) epilogue_chunk_v4_dispatch<0>(p, tsm, lane, vm, my_pix, my_nz, o32, h1, l1, h2, l2, dc4, bs4, s14, s24);
+                        else if (p.act == IA_ACT_LRELU) epilogue_chunk_v4_dispatch<IA_ACT_LRELU>(p, tsm, lane, vm, my_pix, my_nz, o32, h1, l1, h2, l2, dc4, bs4, s14, s24);
+                        else if (p.act == IA_ACT_LINEAR) epilogue_chunk_v4_dispatch<IA_ACT_LINEAR>(p, tsm, lane, vm, my_pix, my_nz, o32, h1, l1, h2, l2, dc4, bs4, s14, s24);
+                        else epilogue_chunk_v4_dispatch<-1>(p, tsm, lane, vm, my_pix, my_nz, o32, h1, l1, h2, l2, dc4, bs4, s14, s24);
+                        continue;
+                    }
 #pragma unroll
                     for (int q = 0; q < 32; ++q) tsm[lane * 33 + q] = __uint_as_float(r[q]);
                     __syncwarp();
@@ -698,7 +805,7 @@ int launch_v2(const ia_conv_params* p, void* stream) {
     t.a_bytes = (t.a_tx + 1023u) & ~1023u;
     t.b_tx = (uint32_t)n_tile * BK * 2u;
     t.b_bytes = (t.b_tx + 1023u) & ~1023u;
-    const uint32_t kEpiBytes = (uint32_t)kEpiWarps2 * 32u * 33u * 4u;
+    const uint32_t kEpiBytes = (uint32_t)kEpiWarps2 * 32u * (uint32_t)kTsmLd * 4u;
     const uint32_t budget = 227u * 1024u - 1024u - 512u - kEpiBytes;
     // at least 2 + 2 slots; then spend the rest alternately (weights first: they turn over once per tap)
     t.a_slots = 2; t.b_slots = 2;
@@ -712,19 +819,34 @@ int launch_v2(const ia_conv_params* p, void* stream) {
         t.b_bytes = (t.b_tx + 1023u) & ~1023u;
     }
     IA_CHECK(2u * (2u * t.a_bytes + 2u * t.b_bytes) <= budget, "ia_conv_tc(v2): tile does not fit shared memory");
+    // Spend the rest so that both rings hold about the same number of k-blocks of work: a k-block consumes `ngroups`
+    // activation slots and `ntaps` weight slots.  Few-tap launches (transposed-conv phases, 1x1) therefore get a deep
+    // activation ring -- their activation tiles stream from DRAM and two slots in flight bound them by latency
+    // (measured: 3.85 TB/s aggregate with 2 slots) -- while 3x3 layers keep the deep weight ring.
     for (;;) {
-        uint32_t used_b = 2u * ((uint32_t)t.a_slots * t.a_bytes + (uint32_t)t.b_slots * t.b_bytes);
-        bool grew = false;
-        if (t.b_slots < kV2MaxBSlots && t.b_slots < 3 * t.a_slots && used_b + 2u * t.b_bytes <= budget) { ++t.b_slots; grew = true; }
-        else if (t.a_slots < kV2MaxASlots && used_b + 2u * t.a_bytes <= budget) { ++t.a_slots; grew = true; }
-        else if (t.b_slots < kV2MaxBSlots && used_b + 2u * t.b_bytes <= budget) { ++t.b_slots; grew = true; }
-        if (!grew) break;
+        const uint32_t used_b = 2u * ((uint32_t)t.a_slots * t.a_bytes + (uint32_t)t.b_slots * t.b_bytes);
+        const bool a_fits = t.a_slots < kV2MaxASlots && used_b + 2u * t.a_bytes <= budget;
+        const bool b_fits = t.b_slots < kV2MaxBSlots && used_b + 2u * t.b_bytes <= budget;
+        if (!a_fits && !b_fits) break;
+        // depth_a = a_slots / ngroups, depth_b = b_slots / ntaps; grow the shallower ring (ties -> activations)
+        const bool want_a = (int64_t)t.a_slots * t.ntaps <= (int64_t)t.b_slots * t.ngroups;
+        if ((want_a && a_fits) || !b_fits) ++t.a_slots; else ++t.b_slots;
     }
     t.OH = p->OH; t.OW = p->OW; t.sy = p->sy; t.sx = p->sx; t.py = p->py; t.px = p->px;
     t.mode = p->mode; t.dcoef = p->dcoef; t.noise = p->noise; t.noise_strength = p->noise_strength; t.bias = p->bias;
     t.noise_bstride = p->noise_bstride;
     t.act = p->act; t.alpha = p->alpha; t.gain = p->gain; t.clamp = p->clamp;
     t.emit = p->emit;
+    {
+        auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+        const ia_emit& e = p->emit;
+        t.epi_vec4 = (p->Cout % 4 == 0) && (!e.out32 || (al16(e.out32) && e.out32_ld % 4 == 0)) &&
+                     (!e.hi1 || (al16(e.hi1) && al16(e.lo1) && e.c1_pad % 8 == 0)) && (!e.hi2 || (al16(e.hi2) && al16(e.lo2) && e.c2_pad % 8 == 0)) &&
+                     (!p->dcoef || al16(p->dcoef)) && (!p->bias || al16(p->bias)) && (!e.s1 || al16(e.s1)) && (!e.s2 || al16(e.s2));
+        static int force_scalar = -1;
+        if (force_scalar < 0) { const char* ev = getenv("IA_CONV_EPI_SCALAR"); force_scalar = (ev && atoi(ev)) ? 1 : 0; }
+        if (force_scalar) t.epi_vec4 = 0;
+    }
 
     CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
     if (int rc = make_act_map2<BK>(&ma_hi, p->a_hi, p->B, p->H, p->W, p->Cin_pad, t.TH + halo, t.tw)) return rc;

@@ -210,7 +210,7 @@ __device__ __forceinline__ float epi_value(float acc, const EpiArgs& e, int b, i
 constexpr int FIR_YT = 32;
 
 template <int ACT>
-__global__ void __launch_bounds__(256) fir_epilogue_kernel(ia_fir_params p, int cg, int xt, int cchunks) {
+__global__ void __launch_bounds__(256, 4) fir_epilogue_kernel(ia_fir_params p, int cg, int xt, int cchunks) {
     const int c4 = threadIdx.x % cg;
     const int xl = threadIdx.x / cg;
     const int ox = blockIdx.x * xt + xl;

@@ -1,4 +1,5 @@
-"""Profiling driver: a few representative modulated-convolution launches (used under ncu)."""
+"""Profiling driver: a few representative modulated-convolution layers (used under ncu, or stand-alone for per-phase times:
+IA_PROF_DETAIL=1 python tools/prof_conv.py 1)."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -6,7 +7,7 @@ from invertavatar_b200 import runtime as rt
 from invertavatar_b200 import stylegan2 as sg
 
 dev = 'cuda'
-cases = [(128, 128, 512, 1, 8), (256, 128, 512, 2, 8), (512, 512, 64, 1, 8), (256, 256, 128, 1, 8)]
+cases = [(128, 128, 512, 1, 8), (256, 128, 512, 2, 8), (512, 512, 64, 1, 8), (256, 256, 128, 1, 8), (512, 256, 128, 2, 8), (256, 128, 256, 2, 8)]
 if len(sys.argv) > 1:
     cases = [cases[int(a)] for a in sys.argv[1:]]
 for (cin, cout, res, up, B) in cases:
@@ -29,3 +30,9 @@ for (cin, cout, res, up, B) in cases:
     ms = e0.elapsed_time(e1) / 5
     fl = 2 * (res // up) ** 2 * cin * cout * 9 * B
     print(f'{cin}->{cout} @{res} up{up} B{B}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s algorithmic')
+    if os.environ.get('IA_PROF_DETAIL'):
+        rt.profile_begin()
+        for it in range(5):
+            L.run_split(a, dc, noise_mode='const', e1=(nxt, dc))
+        for k, v in sorted(rt.profile_report().items()):
+            print(f'    {k:44s} {v["ms"] / 5 * 1000:8.1f} us')
