@@ -320,6 +320,13 @@ int ia_enc_gru_gate(int32_t stage, const float* raw, const float* bias, const fl
 int ia_sft_half(float* x, int64_t x_ld, const ia_view* scale, const ia_view* shift, int32_t B, int32_t H, int32_t W,
                 int32_t C, void* stream);
 
+/* ---- output stage (the step after the path) ------------------------------------------------------------
+ * layout_grid (reenact_avatar_next3d.py:117-131) with float_to_uint8 and chw_to_hwc: frame g = gy*grid_w + gx of the
+ * [B][C][H][W]-indexed image (element strides s_b, s_c, s_h, s_w -- the generator's channels-last output or a planar
+ * tensor) goes to out[(gy*H + y)][(gx*W + x)][c] = (uint8) clamp(img*127.5 + 128, 0, 255) (truncation, as .to(torch.uint8)). */
+int ia_layout_grid_u8(const float* img, int64_t s_b, int64_t s_c, int64_t s_h, int64_t s_w, int32_t grid_h, int32_t grid_w,
+                      int32_t C, int32_t H, int32_t W, uint8_t* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -170,6 +170,8 @@ SIGNATURES = {
     'ia_enc_avgpool': (C.c_int, [C.POINTER(View), C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_f32p, C.c_void_p]),
     'ia_enc_upsample_add': (C.c_int, [c_f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_f32p, C.c_int32, C.c_int32, c_f32p, C.c_void_p]),
     'ia_enc_gru_gate': (C.c_int, [C.c_int32, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int64, C.c_int32, C.c_void_p]),
+    'ia_layout_grid_u8': (C.c_int, [c_f32p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                   C.c_void_p, C.c_void_p]),
     'ia_sft_half': (C.c_int, [c_f32p, C.c_int64, C.POINTER(View), C.POINTER(View), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
 }
 

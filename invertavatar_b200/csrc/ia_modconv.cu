@@ -210,7 +210,7 @@ __device__ __forceinline__ float epi_value(float acc, const EpiArgs& e, int b, i
 constexpr int FIR_YT = 32;
 
 template <int ACT>
-__global__ void __launch_bounds__(256, 4) fir_epilogue_kernel(ia_fir_params p, int cg, int xt, int cchunks) {
+__global__ void __launch_bounds__(256, 3) fir_epilogue_kernel(ia_fir_params p, int cg, int xt, int cchunks) {
     const int c4 = threadIdx.x % cg;
     const int xl = threadIdx.x / cg;
     const int ox = blockIdx.x * xt + xl;
@@ -249,14 +249,20 @@ __global__ void __launch_bounds__(256, 4) fir_epilogue_kernel(ia_fir_params p, i
     const float gain = p.gain, alpha = p.alpha, clampv = p.clamp;
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     // raw row ry feeds output rows oy = ry+1-ty, ty = 0..3.  Walk ry from oy0-1 to oy1+1.
-    for (int ry = oy0 - 1; ry <= oy1 + 1; ++ry, rp += row_f) {
-        float4 r0 = z4, r1 = z4, r2 = z4, r3 = z4;
+    float4 n0 = z4, n1 = z4, n2 = z4, n3 = z4;      // next raw row, in flight while the current one is consumed
+    auto load_row = [&](int ry, const float* q) {
+        n0 = z4; n1 = z4; n2 = z4; n3 = z4;
         if (ry >= 0 && ry < p.RH) {
-            if (v0) r0 = __ldg(reinterpret_cast<const float4*>(rp));
-            r1 = __ldg(reinterpret_cast<const float4*>(rp + C));
-            r2 = __ldg(reinterpret_cast<const float4*>(rp + 2 * C));
-            if (v3) r3 = __ldg(reinterpret_cast<const float4*>(rp + 3 * C));
+            if (v0) n0 = __ldg(reinterpret_cast<const float4*>(q));
+            n1 = __ldg(reinterpret_cast<const float4*>(q + C));
+            n2 = __ldg(reinterpret_cast<const float4*>(q + 2 * C));
+            if (v3) n3 = __ldg(reinterpret_cast<const float4*>(q + 3 * C));
         }
+    };
+    load_row(oy0 - 1, rp);
+    for (int ry = oy0 - 1; ry <= oy1 + 1; ++ry, rp += row_f) {
+        const float4 r0 = n0, r1 = n1, r2 = n2, r3 = n3;
+        if (ry < oy1 + 1) load_row(ry + 1, rp + row_f);
         float4 h;
         h.x = fmaf(fx[3], r3.x, fmaf(fx[2], r2.x, fmaf(fx[1], r1.x, fx[0] * r0.x)));
         h.y = fmaf(fx[3], r3.y, fmaf(fx[2], r2.y, fmaf(fx[1], r1.y, fx[0] * r0.y)));

@@ -343,3 +343,34 @@ extern "C" int ia_lerp_alpha(const ia_lerp_params* p, void* stream) {
     IA_LAUNCH_CHECK("ia_lerp_alpha");
     return 0;
 }
+
+
+// ------------------------------------------------------------------------------------------------
+// output stage: layout_grid with uint8 quantisation, HWC
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) layout_grid_u8_kernel(const float* __restrict__ img, int64_t s_b, int64_t s_c, int64_t s_h, int64_t s_w,
+                                                             int grid_h, int grid_w, int C, int H, int W, uint8_t* __restrict__ out) {
+    const int64_t total = (int64_t)grid_h * H * grid_w * W;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int X = (int)(i % ((int64_t)grid_w * W));
+    const int Y = (int)(i / ((int64_t)grid_w * W));
+    const int gx = X / W, x = X - gx * W, gy = Y / H, y = Y - gy * H;
+    const float* p = img + (int64_t)(gy * grid_w + gx) * s_b + (int64_t)y * s_h + (int64_t)x * s_w;
+    uint8_t* o = out + i * C;
+    for (int c = 0; c < C; ++c) {
+        float v = p[(int64_t)c * s_c] * 127.5f + 128.0f;
+        v = fminf(fmaxf(v, 0.0f), 255.0f);
+        o[c] = (uint8_t)v;      // truncation toward zero, like tensor.to(torch.uint8)
+    }
+}
+
+extern "C" int ia_layout_grid_u8(const float* img, int64_t s_b, int64_t s_c, int64_t s_h, int64_t s_w, int32_t grid_h, int32_t grid_w,
+                                 int32_t C, int32_t H, int32_t W, uint8_t* out, void* stream) {
+    IA_CHECK(img && out && grid_h > 0 && grid_w > 0 && C > 0 && H > 0 && W > 0, "ia_layout_grid_u8: bad arguments");
+    const int64_t total = (int64_t)grid_h * H * grid_w * W;
+    ia::prof_begin("ia_layout_grid_u8", as_stream(stream));
+    layout_grid_u8_kernel<<<(unsigned)cdiv(total, 256), 256, 0, as_stream(stream)>>>(img, s_b, s_c, s_h, s_w, grid_h, grid_w, C, H, W, out);
+    IA_LAUNCH_CHECK("ia_layout_grid_u8");
+    return 0;
+}

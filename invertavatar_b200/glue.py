@@ -237,3 +237,13 @@ class UniformCameraPoseSampler:
 
 def FOV_to_intrinsics(fov_degrees, device='cpu'):
     return synth.fov_to_intrinsics(fov_degrees).to(device)
+
+
+# ---- reenact_avatar_next3d.py:117-131 ------------------------------------------------------------------------------------
+def layout_grid(img, grid_w=None, grid_h=1, float_to_uint8=True, chw_to_hwc=True, to_numpy=True):
+    """Output stage of the inference scripts.  The common configuration (uint8 + HWC) is one fused kernel on the device."""
+    from . import runtime as rt
+    if float_to_uint8 and chw_to_hwc:
+        out = rt.layout_grid_u8(img, grid_w=grid_w, grid_h=grid_h)
+        return out.cpu().numpy() if to_numpy else out
+    raise NotImplementedError('layout_grid: only float_to_uint8=True, chw_to_hwc=True (the configuration the scripts use) is implemented')

@@ -842,3 +842,22 @@ def sft_half(x_nhwc, scale, shift):
         hv.s_img = 0
     _C.check(_C.lib().ia_sft_half(_p(x_nhwc), x_nhwc.stride(2), C.byref(sv), C.byref(hv), B, H, W, Cc, st), 'ia_sft_half')
     return x_nhwc
+
+
+# ---------------------------------------------------------------------------------------------------
+# output stage
+# ---------------------------------------------------------------------------------------------------
+def layout_grid_u8(img, grid_w=None, grid_h=1):
+    """[B,C,H,W] float image batch (any strides) -> uint8 [grid_h*H, grid_w*W, C] (reenact_avatar_next3d.py:117-131 with
+    float_to_uint8=True, chw_to_hwc=True), one kernel; the D2H copy that follows moves 1 byte per value instead of 4."""
+    _require_cuda(img)
+    st = _enter(img)
+    img = img if img.dtype == torch.float32 else img.float()
+    B, Cc, H, W = img.shape
+    if grid_w is None:
+        grid_w = B // grid_h
+    assert B == grid_w * grid_h
+    out = torch.empty((grid_h * H, grid_w * W, Cc), dtype=torch.uint8, device=img.device)
+    _C.check(_C.lib().ia_layout_grid_u8(_p(img), img.stride(0), img.stride(1), img.stride(2), img.stride(3), grid_h, grid_w, Cc, H, W,
+                                        _p(out), st), 'ia_layout_grid_u8')
+    return out

@@ -199,3 +199,17 @@ def test_raster_level_fused(Cc, tr, res):
 def synth_uv(B):
     from invertavatar_b200 import synth
     return synth.uvcoords_image(B)
+
+
+def test_layout_grid_u8():
+    """Output stage (reenact_avatar_next3d.py:117-131): fused quantise + tile + HWC against the reference expression."""
+    from invertavatar_b200 import glue
+    g = torch.Generator().manual_seed(5)
+    img = torch.randn(6, 3, 20, 12, generator=g) * 0.8
+    img[0, 0, 0, :4] = torch.tensor([-1.0, 1.0, 0.99607843, -1.00392157])   # quantisation edges
+    for gw, gh in ((6, 1), (3, 2), (2, 3)):
+        ref = (img * 127.5 + 128).clamp(0, 255).to(torch.uint8).reshape(gh, gw, 3, 20, 12).permute(2, 0, 3, 1, 4).reshape(3, gh * 20, gw * 12).permute(1, 2, 0)
+        for x in (img.to(DEV), img.to(DEV).contiguous(memory_format=torch.channels_last)):
+            out = glue.layout_grid(x, grid_w=gw, grid_h=gh)
+            assert out.dtype == np.uint8 and out.shape == (gh * 20, gw * 12, 3)
+            assert np.array_equal(out, ref.numpy())
