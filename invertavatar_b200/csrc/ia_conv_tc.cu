@@ -107,6 +107,25 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// Cluster-of-2 variant: one CTA loads a weight tile for both (TMA multicast), and every CTA's MMA warp releases a weight
+// slot in both CTAs (commit with a multicast arrive), so a slot is refilled only after both consumers are done with it.
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
+        ::"r"(dst), "l"(map), "r"(bar), "h"(mask), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -368,6 +387,7 @@ struct Tc2Params {
     long long noise_bstride;
     int act; float alpha, gain, clamp;
     ia_emit emit;
+    int m_tiles_p, total_pairs;    // cluster variant: m_tiles rounded up to even; (m_tiles_p * n_tiles) / 2 tile pairs
     int epi_vec4;                  // 1: Cout % 4 == 0 and every output pointer / pitch is 16-byte friendly -> epilogue_chunk_v4
 };
 
@@ -495,7 +515,7 @@ __device__ __forceinline__ void epilogue_chunk_v4_dispatch(const Tc2Params& p, c
 constexpr int kEpiWarps2 = 8;                       // epilogue warps of the v2 kernel: 2 per TMEM lane quarter (one per half tile)
 constexpr int kThreads2 = (2 + kEpiWarps2) * 32;
 
-template <int BK>
+template <int BK, bool CL>
 __global__ void __launch_bounds__(kThreads2, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                 const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
@@ -520,7 +540,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.a_slots; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
-        for (int s = 0; s < p.b_slots; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+        for (int s = 0; s < p.b_slots; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), CL ? 2 : 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(t_full(s), 1); mbar_init(t_empty(s), kEpiWarps2); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -534,19 +554,40 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     }
     tc_fence_before();
     __syncthreads();
+    if (CL) cluster_sync_all();      // the peer's barriers are initialised before anything arrives on them
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
     const int th_half = p.TH >> 1;
+    // tile schedule.  Plain: CTA b takes tiles b, b+grid, ...  Cluster: the pair (2q, 2q+1) takes tile pairs q, q+grid/2, ...;
+    // both tiles of a pair share the N tile (m_tiles is padded to even: a padding tile recomputes the last M tile and
+    // stores nothing), so the weight tiles of the pair are identical and are loaded once.
+    const uint32_t crank = CL ? cluster_ctarank() : 0u;
+    const int it_first = CL ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int it_step = CL ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int it_end = CL ? p.total_pairs : p.total_tiles;
+    auto decode = [&](int it, int& n_idx, int& m, bool& null_tile) {
+        if (CL) {
+            const int lin = 2 * it + (int)crank;
+            n_idx = lin / p.m_tiles_p;
+            m = lin - n_idx * p.m_tiles_p;
+            null_tile = m >= p.m_tiles;
+            if (null_tile) m = p.m_tiles - 1;
+        } else {
+            n_idx = it / p.m_tiles;
+            m = it - n_idx * p.m_tiles;
+            null_tile = false;
+        }
+    };
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             uint32_t a_it = 0, b_it = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-                const int n_idx = tile / p.m_tiles;
-                int m = tile - n_idx * p.m_tiles;
+            for (int it = it_first; it < it_end; it += it_step) {
+                int n_idx, m; bool null_tile;
+                decode(it, n_idx, m, null_tile);
                 const int txi = m % p.tiles_x; m /= p.tiles_x;
                 const int tyi = m % p.tiles_y; const int img = m / p.tiles_y;
                 const int x0 = txi * p.tw, y0 = tyi * p.TH, col0 = n_idx * p.n_tile;
@@ -565,8 +606,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                             const uint32_t sb = b_base + (uint32_t)bs * b_slot_bytes;
                             mbar_expect_tx(b_full(bs), 2u * p.b_tx);
                             const int wrow = p.t_wtap[t] * p.Cout_pad + col0;
-                            tma_load_2d(sb, &tm_w_hi, b_full(bs), kc * BK, wrow);
-                            tma_load_2d(sb + p.b_bytes, &tm_w_lo, b_full(bs), kc * BK, wrow);
+                            if (CL) {     // both CTAs armed their own barrier above; rank 0 fetches the tile for both
+                                if (crank == 0) {
+                                    tma_load_2d_mc(sb, &tm_w_hi, b_full(bs), kc * BK, wrow, (uint16_t)3);
+                                    tma_load_2d_mc(sb + p.b_bytes, &tm_w_lo, b_full(bs), kc * BK, wrow, (uint16_t)3);
+                                }
+                            } else {
+                                tma_load_2d(sb, &tm_w_hi, b_full(bs), kc * BK, wrow);
+                                tma_load_2d(sb + p.b_bytes, &tm_w_lo, b_full(bs), kc * BK, wrow);
+                            }
                             ++b_it;
                         }
                     }
@@ -578,7 +626,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         if (lane == 0) {
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
             uint32_t a_it = 0, b_it = 0, j = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++j) {
+            for (int it = it_first; it < it_end; it += it_step, ++j) {
                 const uint32_t acc = j & 1u;
                 mbar_wait(t_empty(acc), ((j >> 1) & 1u) ^ 1u);
                 tc_fence_after();
@@ -614,7 +662,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                                 umma_bf16(d1, a1_lo + koff, b_hi + koff, idesc, 1u);
                                 first = false;
                             }
-                            umma_commit(b_empty(bs));
+                            if (CL) umma_commit_mc(b_empty(bs), (uint16_t)3); else umma_commit(b_empty(bs));
                             ++b_it;
                         }
                         umma_commit(a_empty(as));
@@ -634,10 +682,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         float* tsm = reinterpret_cast<float*>(smem_raw + (epi_base - smem_u32(smem_raw))) + (warp - 2) * (32 * kTsmLd);
         const int tw_shift = p.tw == 8 ? 3 : (p.tw == 16 ? 4 : 5);
         uint32_t j = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++j) {
+        for (int it = it_first; it < it_end; it += it_step, ++j) {
             const uint32_t acc = j & 1u;
-            const int n_idx = tile / p.m_tiles;
-            int m = tile - n_idx * p.m_tiles;
+            int n_idx, m; bool null_tile;
+            decode(it, n_idx, m, null_tile);
             const int txi = m % p.tiles_x; m /= p.tiles_x;
             const int tyi = m % p.tiles_y; const int img = m / p.tiles_y;
             const int x0 = txi * p.tw, y0 = tyi * p.TH, col0 = n_idx * p.n_tile;
@@ -649,7 +697,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                 const int h_l = (row >> tw_shift) + half * th_half;
                 const int gy = y0 + h_l, gx = x0 + w_l;
                 const int oy = gy * p.sy + p.py, ox = gx * p.sx + p.px;
-                const bool valid = gy < p.GH && gx < p.GW && oy < p.OH && ox < p.OW;
+                const bool valid = !null_tile && gy < p.GH && gx < p.GW && oy < p.OH && ox < p.OW;
                 const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
                 const int my_pix = oy * p.OW + ox;                     // pixel index inside the image (fits in int)
                 float my_nz = 0.f;
@@ -716,6 +764,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     }
 
     __syncthreads();
+    if (CL) cluster_sync_all();      // no CTA leaves while its peer may still multicast into it or arrive on its barriers
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -856,7 +905,9 @@ int launch_v2(const ia_conv_params* p, void* stream) {
     if (int rc = make_weight_map2<BK>(&mw_lo, p->w_lo, wrows, p->Cin_pad, n_tile)) return rc;
 
     const size_t smem = 2u * ((size_t)t.a_slots * t.a_bytes + (size_t)t.b_slots * t.b_bytes) + 1024 + 512 + kEpiBytes;
-    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    IA_CHECK(e == cudaSuccess, "ia_conv_tc(v2): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    e = cudaFuncSetAttribute(conv_tc2_kernel<BK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     IA_CHECK(e == cudaSuccess, "ia_conv_tc(v2): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     if (g_sm_count == 0) {
         int dev = 0;
@@ -864,9 +915,34 @@ int launch_v2(const ia_conv_params* p, void* stream) {
         cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
         if (g_sm_count <= 0) g_sm_count = 148;
     }
+    // Cluster-of-2 weight multicast (IA_CONV_CLUSTER=1 enables).
+    static int use_cluster = -1;
+    // Measured on B200: 367 (cluster) vs 396 (plain) TF/s algorithmic on the 128->128 @512^2 layer -- the lock-step
+    // coupling of the pair costs more than the halved weight traffic saves, so the variant is off by default.
+    if (use_cluster < 0) { const char* ev = getenv("IA_CONV_CLUSTER"); use_cluster = ev ? atoi(ev) : 0; }
+    t.m_tiles_p = (t.m_tiles + 1) & ~1;
+    t.total_pairs = (t.m_tiles_p * t.n_tiles) / 2;
+    const int sm_even = g_sm_count & ~1;
+    if (use_cluster && t.total_pairs >= sm_even / 2) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)sm_even, 1, 1);
+        cfg.blockDim = dim3(kThreads2, 1, 1);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = as_stream(stream);
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        ia::prof_begin(ia::prof_detail_name("ia_conv_tc", p->ntaps, p->GH, p->GW, p->Cin_pad, p->Cout), as_stream(stream));
+        cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tc2_kernel<BK, true>, ma_hi, ma_lo, mw_hi, mw_lo, t);
+        IA_CHECK(le == cudaSuccess, "ia_conv_tc(v2): cluster launch failed: %s", cudaGetErrorString(le));
+        IA_LAUNCH_CHECK("ia_conv_tc");
+        return 0;
+    }
     const int grid = t.total_tiles < g_sm_count ? t.total_tiles : g_sm_count;
     ia::prof_begin(ia::prof_detail_name("ia_conv_tc", p->ntaps, p->GH, p->GW, p->Cin_pad, p->Cout), as_stream(stream));
-    conv_tc2_kernel<BK><<<grid, kThreads2, smem, as_stream(stream)>>>(ma_hi, ma_lo, mw_hi, mw_lo, t);
+    conv_tc2_kernel<BK, false><<<grid, kThreads2, smem, as_stream(stream)>>>(ma_hi, ma_lo, mw_hi, mw_lo, t);
     IA_LAUNCH_CHECK("ia_conv_tc");
     return 0;
 }
