@@ -134,26 +134,36 @@ __global__ void __launch_bounds__(256) enc_affine_kernel(ia_enc_affine_params p)
     p.y[pix * p.y_ld + c] = a;
 }
 
-// ---- global average pool of an affine'd view: grid (B, ceil(C/32)), block 32 x 8 ---------------------------------
-__global__ void __launch_bounds__(256) global_pool_kernel(ia_view v, const float* __restrict__ scale, const float* __restrict__ shift,
-                                                          int H, int W, float* __restrict__ pooled) {
+// ---- global average pool of an affine'd view: grid (B, ceil(C/32), pixel chunks), block 32 x 8; partial sums are added
+// atomically into `pooled` (zeroed by the host wrapper), a second tiny kernel turns the sums into scale*mean + shift ------
+__global__ void __launch_bounds__(256) global_pool_kernel(ia_view v, int H, int W, int pix_per_block, float* __restrict__ pooled) {
     const int b = blockIdx.x;
     const int c = blockIdx.y * 32 + (threadIdx.x & 31);
     const int lane_p = threadIdx.x >> 5;
     const int npix = H * W;
+    const int p0 = blockIdx.z * pix_per_block;
+    const int p1 = min(p0 + pix_per_block, npix);
     float s = 0.f;
     if (c < v.C) {
-        for (int p = lane_p; p < npix; p += 8) s += view_at(v, b, p / W, p % W, c);
+        for (int p = p0 + lane_p; p < p1; p += 8) s += view_at(v, b, p / W, p % W, c);
     }
     __shared__ float sh[8][32];
     sh[lane_p][threadIdx.x & 31] = s;
     __syncthreads();
     if (lane_p == 0 && c < v.C) {
         for (int k = 1; k < 8; ++k) s += sh[k][threadIdx.x & 31];
-        float m = s / (float)npix;
-        if (scale) m = fmaf(m, scale[c], shift ? shift[c] : 0.f);
-        pooled[(int64_t)b * v.C + c] = m;
+        atomicAdd(&pooled[(int64_t)b * v.C + c], s);
     }
+}
+
+__global__ void global_pool_finish_kernel(float* __restrict__ pooled, const float* __restrict__ scale, const float* __restrict__ shift, int B, int C,
+                                          float inv_npix) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * C) return;
+    const int c = i % C;
+    float m = pooled[i] * inv_npix;
+    if (scale) m = fmaf(m, scale[c], shift ? shift[c] : 0.f);
+    pooled[i] = m;
 }
 
 __global__ void __launch_bounds__(256) avgpool_kernel(ia_view v, int B, int OH, int OW, int k, float* __restrict__ y) {
@@ -305,9 +315,20 @@ extern "C" int ia_enc_global_pool(const ia_view* x, const float* scale, const fl
                                   float* pooled, void* stream) {
     if (int rc = check_view(x, "ia_enc_global_pool")) return rc;
     IA_CHECK(pooled && B > 0 && H > 0 && W > 0, "ia_enc_global_pool: bad arguments");
-    dim3 grid((unsigned)B, (unsigned)cdiv(x->C, 32));
+    cudaError_t e = cudaMemsetAsync(pooled, 0, sizeof(float) * (size_t)B * x->C, as_stream(stream));
+    IA_CHECK(e == cudaSuccess, "ia_enc_global_pool: memset: %s", cudaGetErrorString(e));
+    const int npix = H * W;
+    const int cblocks = (int)cdiv(x->C, 32);
+    int chunks = (int)cdiv(148 * 4, (int64_t)B * cblocks);
+    int ppb = (int)cdiv(npix, chunks);
+    if (ppb < 64) ppb = 64;
+    chunks = (int)cdiv(npix, ppb);
+    dim3 grid((unsigned)B, (unsigned)cblocks, (unsigned)chunks);
     ia::prof_begin("ia_enc_global_pool", as_stream(stream));
-    global_pool_kernel<<<grid, 256, 0, as_stream(stream)>>>(*x, scale, shift, H, W, pooled);
+    global_pool_kernel<<<grid, 256, 0, as_stream(stream)>>>(*x, H, W, ppb, pooled);
+    IA_LAUNCH_CHECK("ia_enc_global_pool");
+    ia::prof_begin("ia_enc_global_pool", as_stream(stream));
+    global_pool_finish_kernel<<<(unsigned)cdiv((int64_t)B * x->C, 128), 128, 0, as_stream(stream)>>>(pooled, scale, shift, B, x->C, 1.0f / (float)npix);
     IA_LAUNCH_CHECK("ia_enc_global_pool");
     return 0;
 }
