@@ -137,6 +137,10 @@ typedef struct {
     int64_t noise_bstride;   /* 0: one [OH][OW] noise image shared by the batch ('const'); OH*OW: per-sample ('random') */
     int32_t act; float alpha; float gain; float clamp;
     ia_emit emit;
+    /* Grouped launch (several networks with identical layer shapes evaluated as one batch, e.g. the low-resolution blocks of
+     * the three backbones): image b belongs to group g = b / imgs_per_group and uses weight taps [g*n_taps_total, ...),
+     * bias[g*Cout + co], noise_strength[g] and noise + g*noise_gstride.  groups <= 1: a single set (fields may be 0). */
+    int32_t groups; int32_t imgs_per_group; int64_t noise_gstride;
 } ia_conv_params;
 /* Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05.mma, TMEM accumulators, TMA-fed). */
 int ia_conv_tc(const ia_conv_params* p, void* stream);
@@ -153,6 +157,7 @@ typedef struct {
     int64_t noise_bstride;
     int32_t act; float alpha; float gain; float clamp;
     ia_emit emit;
+    int32_t groups; int32_t imgs_per_group; int64_t noise_gstride;   /* as in ia_conv_params */
 } ia_fir_params;
 int ia_fir_epilogue(const ia_fir_params* p, void* stream);
 
@@ -163,6 +168,7 @@ typedef struct {
     const float* bias; float clamp;
     const float* img_prev;                       /* [B][H/2][W/2][C] or NULL */
     float* img_out; int32_t B, H, W, C; int32_t out_nchw;
+    int32_t groups; int32_t imgs_per_group;      /* bias[g*C + c] with g = b / imgs_per_group (groups <= 1: one bias) */
 } ia_torgb_params;
 int ia_torgb_finish(const ia_torgb_params* p, void* stream);
 

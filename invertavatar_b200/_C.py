@@ -50,7 +50,8 @@ class ConvParams(C.Structure):
                 ('mode', C.c_int32), ('dcoef', c_f32p), ('noise', c_f32p), ('noise_strength', c_f32p), ('bias', c_f32p),
                 ('noise_bstride', C.c_int64),
                 ('act', C.c_int32), ('alpha', C.c_float), ('gain', C.c_float), ('clamp', C.c_float),
-                ('emit', Emit)]
+                ('emit', Emit),
+                ('groups', C.c_int32), ('imgs_per_group', C.c_int32), ('noise_gstride', C.c_int64)]
 
 
 class FirParams(C.Structure):
@@ -59,13 +60,14 @@ class FirParams(C.Structure):
                 ('dcoef', c_f32p), ('noise', c_f32p), ('noise_strength', c_f32p), ('bias', c_f32p),
                 ('noise_bstride', C.c_int64),
                 ('act', C.c_int32), ('alpha', C.c_float), ('gain', C.c_float), ('clamp', C.c_float),
-                ('emit', Emit)]
+                ('emit', Emit),
+                ('groups', C.c_int32), ('imgs_per_group', C.c_int32), ('noise_gstride', C.c_int64)]
 
 
 class TorgbParams(C.Structure):
     _fields_ = [('raw', c_f32p), ('raw_ld', C.c_int64), ('bias', c_f32p), ('clamp', C.c_float), ('img_prev', c_f32p),
                 ('img_out', c_f32p), ('B', C.c_int32), ('H', C.c_int32), ('W', C.c_int32), ('C', C.c_int32),
-                ('out_nchw', C.c_int32)]
+                ('out_nchw', C.c_int32), ('groups', C.c_int32), ('imgs_per_group', C.c_int32)]
 
 
 class ResizeParams(C.Structure):

@@ -43,6 +43,7 @@ struct TcParams {
     long long noise_bstride;
     int act; float alpha, gain, clamp;
     ia_emit emit;
+    int groups, ipg, n_taps_total; long long noise_gstride;   // grouped launch (see ia_conv_params)
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------
@@ -203,7 +204,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                 mbar_expect_tx(full_bar(stage), stage_bytes);
                 tma_load_4d(sa, &tm_a_hi, full_bar(stage), kc * kBlockK, x0 + p.dx[t], y0 + p.dy[t], n0);
                 tma_load_4d(sa + kABytes, &tm_a_lo, full_bar(stage), kc * kBlockK, x0 + p.dx[t], y0 + p.dy[t], n0);
-                const int wrow = p.wtap[t] * p.Cout_pad + col0;
+                const int wrow = ((n0 / p.ipg) * p.n_taps_total + p.wtap[t]) * p.Cout_pad + col0;   // a tile never spans two groups
                 tma_load_2d(sa + 2u * kABytes, &tm_w_hi, full_bar(stage), kc * kBlockK, wrow);
                 tma_load_2d(sa + 2u * kABytes + b_bytes, &tm_w_lo, full_bar(stage), kc * kBlockK, wrow);
                 if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -246,8 +247,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         const int oy = gy * p.sy + p.py, ox = gx * p.sx + p.px;
         const bool valid = gy < p.GH && gx < p.GW && img < p.B && oy < p.OH && ox < p.OW;
         const int64_t pix = ((int64_t)img * p.OH + oy) * p.OW + ox;
+        const int grp = img / p.ipg;
         float nz = 0.f;
-        if (valid && p.mode == 1 && p.noise) nz = p.noise[(int64_t)img * p.noise_bstride + (int64_t)oy * p.OW + ox] * p.noise_strength[0];
+        if (valid && p.mode == 1 && p.noise)
+            nz = p.noise[(int64_t)grp * p.noise_gstride + (int64_t)img * p.noise_bstride + (int64_t)oy * p.OW + ox] * p.noise_strength[grp];
+        const float* bias_g = p.bias ? p.bias + (int64_t)grp * p.Cout : nullptr;
 
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
@@ -265,7 +269,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                     float a = __uint_as_float(r[q * 4 + k]);
                     if (p.mode == 1 && co + k < p.Cout) {
                         if (p.dcoef) a = fmaf(a, p.dcoef[(int64_t)img * p.Cout + co + k], nz); else a += nz;
-                        if (p.bias) a += p.bias[co + k];
+                        if (bias_g) a += bias_g[co + k];
                         a = act_gain_clamp(a, p.act, p.alpha, p.gain, p.clamp);
                     }
                     v[k] = a;
@@ -330,14 +334,21 @@ int make_weight_map(CUtensorMap* m, const void* ptr, int rows, int Cin_pad, int 
 }
 
 // Choose the 128-row patch {nb, th, tw} (powers of two) that covers the [B][GH][GW] grid with the fewest tiles.
-void choose_patch(int B, int GH, int GW, int& nb, int& th, int& tw) {
+// nb_cap > 0 (grouped launch): a tile may not span two groups, so nb must divide nb_cap (= images per group).
+void choose_patch(int B, int GH, int GW, int& nb, int& th, int& tw, int nb_cap = 0) {
     int64_t best = -1;
     int wmax = 1, hmax = 1;
     while (wmax < GW && wmax < 128) wmax <<= 1;
     while (hmax < GH && hmax < 128) hmax <<= 1;
+    if (nb_cap > 0) {
+        // the patch may have to be larger than the image so that it holds few enough images (out-of-range rows are zero-filled
+        // by TMA and masked in the epilogue): let the search run over every power-of-two patch shape
+        wmax = 128; hmax = 128;
+    }
     for (int w = 1; w <= wmax; w <<= 1) {
         for (int h = 1; h <= hmax && h * w <= 128; h <<= 1) {
             int n = 128 / (w * h);
+            if (nb_cap > 0 && (n > nb_cap || nb_cap % n != 0)) continue;
             int64_t tiles = cdiv(GW, w) * cdiv(GH, h) * cdiv(B, n);
             // prefer fewer tiles, then wider rows (longer contiguous runs per TMA box row)
             if (best < 0 || tiles < best || (tiles == best && w > tw)) { best = tiles; nb = n; th = h; tw = w; }
@@ -387,6 +398,7 @@ struct Tc2Params {
     long long noise_bstride;
     int act; float alpha, gain, clamp;
     ia_emit emit;
+    int groups, ipg, n_taps_total; long long noise_gstride;   // grouped launch (see ia_conv_params)
     int m_tiles_p, total_pairs;    // cluster variant: m_tiles rounded up to even; (m_tiles_p * n_tiles) / 2 tile pairs
     int epi_vec4;                  // 1: Cout % 4 == 0 and every output pointer / pitch is 16-byte friendly -> epilogue_chunk_v4
 };
@@ -605,7 +617,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                             mbar_wait(b_empty(bs), ((b_it / (uint32_t)p.b_slots) & 1u) ^ 1u);
                             const uint32_t sb = b_base + (uint32_t)bs * b_slot_bytes;
                             mbar_expect_tx(b_full(bs), 2u * p.b_tx);
-                            const int wrow = p.t_wtap[t] * p.Cout_pad + col0;
+                            const int wrow = ((img / p.ipg) * p.n_taps_total + p.t_wtap[t]) * p.Cout_pad + col0;
                             if (CL) {     // both CTAs armed their own barrier above; rank 0 fetches the tile for both
                                 if (crank == 0) {
                                     tma_load_2d_mc(sb, &tm_w_hi, b_full(bs), kc * BK, wrow, (uint16_t)3);
@@ -701,7 +713,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                 const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
                 const int my_pix = oy * p.OW + ox;                     // pixel index inside the image (fits in int)
                 float my_nz = 0.f;
-                if (valid && p.mode == 1 && p.noise) my_nz = p.noise[(int64_t)img * p.noise_bstride + my_pix] * p.noise_strength[0];
+                const int grp = img / p.ipg;
+                if (valid && p.mode == 1 && p.noise)
+                    my_nz = p.noise[(int64_t)grp * p.noise_gstride + (int64_t)img * p.noise_bstride + my_pix] * p.noise_strength[grp];
+                const float* bias_g = p.bias ? p.bias + (int64_t)grp * p.Cout : nullptr;
                 const int64_t img_pix0 = (int64_t)img * p.OH * p.OW;
                 const uint32_t tcol = (acc * 2u + (uint32_t)half) * (uint32_t)p.acc_stride;
 #pragma unroll 1
@@ -722,7 +737,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                         if (cval) {
                             if (p.mode == 1) {
                                 if (p.dcoef) dc4 = *reinterpret_cast<const float4*>(p.dcoef + (int64_t)img * p.Cout + co0);
-                                if (p.bias) bs4 = *reinterpret_cast<const float4*>(p.bias + co0);
+                                if (bias_g) bs4 = *reinterpret_cast<const float4*>(bias_g + co0);
                             }
                             if (p.emit.hi1 && p.emit.s1) s14 = *reinterpret_cast<const float4*>(p.emit.s1 + (int64_t)img * p.Cout + co0);
                             if (p.emit.hi2 && p.emit.s2) s24 = *reinterpret_cast<const float4*>(p.emit.s2 + (int64_t)img * p.Cout + co0);
@@ -747,7 +762,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                     const bool cvalid = co < p.Cout;
                     float dc = 1.f, bs = 0.f, s1v = 1.f, s2v = 1.f;
                     if (cvalid) {
-                        if (p.mode == 1) { if (p.dcoef) dc = p.dcoef[(int64_t)img * p.Cout + co]; if (p.bias) bs = p.bias[co]; }
+                        if (p.mode == 1) { if (p.dcoef) dc = p.dcoef[(int64_t)img * p.Cout + co]; if (bias_g) bs = bias_g[co]; }
                         if (p.emit.hi1 && p.emit.s1) s1v = p.emit.s1[(int64_t)img * p.Cout + co];
                         if (p.emit.hi2 && p.emit.s2) s2v = p.emit.s2[(int64_t)img * p.Cout + co];
                     }
@@ -886,6 +901,8 @@ int launch_v2(const ia_conv_params* p, void* stream) {
     t.noise_bstride = p->noise_bstride;
     t.act = p->act; t.alpha = p->alpha; t.gain = p->gain; t.clamp = p->clamp;
     t.emit = p->emit;
+    t.groups = p->groups > 1 ? p->groups : 1; t.ipg = p->groups > 1 ? p->imgs_per_group : (p->B > 0 ? p->B : 1);
+    t.n_taps_total = p->n_taps_total; t.noise_gstride = p->groups > 1 ? p->noise_gstride : 0;
     {
         auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
         const ia_emit& e = p->emit;
@@ -900,7 +917,7 @@ int launch_v2(const ia_conv_params* p, void* stream) {
     CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
     if (int rc = make_act_map2<BK>(&ma_hi, p->a_hi, p->B, p->H, p->W, p->Cin_pad, t.TH + halo, t.tw)) return rc;
     if (int rc = make_act_map2<BK>(&ma_lo, p->a_lo, p->B, p->H, p->W, p->Cin_pad, t.TH + halo, t.tw)) return rc;
-    const int wrows = p->n_taps_total * p->Cout_pad;
+    const int wrows = t.groups * p->n_taps_total * p->Cout_pad;
     if (int rc = make_weight_map2<BK>(&mw_hi, p->w_hi, wrows, p->Cin_pad, n_tile)) return rc;
     if (int rc = make_weight_map2<BK>(&mw_lo, p->w_lo, wrows, p->Cin_pad, n_tile)) return rc;
 
@@ -923,7 +940,7 @@ int launch_v2(const ia_conv_params* p, void* stream) {
     t.m_tiles_p = (t.m_tiles + 1) & ~1;
     t.total_pairs = (t.m_tiles_p * t.n_tiles) / 2;
     const int sm_even = g_sm_count & ~1;
-    if (use_cluster && t.total_pairs >= sm_even / 2) {
+    if (use_cluster && p->groups <= 1 && t.total_pairs >= sm_even / 2) {
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
         cfg.gridDim = dim3((unsigned)sm_even, 1, 1);
@@ -971,7 +988,9 @@ extern "C" int ia_conv_tc(const ia_conv_params* p, void* stream) {
     TcParams t;
     memset(&t, 0, sizeof(t));
     t.B = p->B; t.GH = p->GH; t.GW = p->GW;
-    choose_patch(p->B, p->GH, p->GW, t.nb, t.th, t.tw);
+    t.groups = p->groups > 1 ? p->groups : 1; t.ipg = p->groups > 1 ? p->imgs_per_group : (p->B > 0 ? p->B : 1);
+    t.n_taps_total = p->n_taps_total; t.noise_gstride = p->groups > 1 ? p->noise_gstride : 0;
+    choose_patch(p->B, p->GH, p->GW, t.nb, t.th, t.tw, t.groups > 1 ? t.ipg : 0);
     t.tiles_x = (int)cdiv(p->GW, t.tw); t.tiles_y = (int)cdiv(p->GH, t.th);
     const int tiles_n = (int)cdiv(p->B, t.nb);
     t.Cin_blocks = p->Cin_pad / kBlockK;
@@ -1004,7 +1023,7 @@ extern "C" int ia_conv_tc(const ia_conv_params* p, void* stream) {
     CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
     if (int rc = make_act_map(&ma_hi, p->a_hi, p->B, p->H, p->W, p->Cin_pad, t.nb, t.th, t.tw)) return rc;
     if (int rc = make_act_map(&ma_lo, p->a_lo, p->B, p->H, p->W, p->Cin_pad, t.nb, t.th, t.tw)) return rc;
-    const int wrows = p->n_taps_total * p->Cout_pad;
+    const int wrows = t.groups * p->n_taps_total * p->Cout_pad;
     if (int rc = make_weight_map(&mw_hi, p->w_hi, wrows, p->Cin_pad, n_tile)) return rc;
     if (int rc = make_weight_map(&mw_lo, p->w_lo, wrows, p->Cin_pad, n_tile)) return rc;
 

@@ -231,16 +231,17 @@ __global__ void __launch_bounds__(256, 3) fir_epilogue_kernel(ia_fir_params p, i
     }
     const int oy1 = min(oy0 + FIR_YT, p.OH);
     float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0, acc2 = acc0, acc3 = acc0;   // output rows ry-2 .. ry+1
+    const int grp = p.groups > 1 ? b / p.imgs_per_group : 0;
     float dc[4], bs[4], s1[4], s2[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         dc[k] = p.dcoef ? p.dcoef[(int64_t)b * p.C + c0 + k] : 1.f;
-        bs[k] = p.bias ? p.bias[c0 + k] : 0.f;
+        bs[k] = p.bias ? p.bias[(int64_t)grp * p.C + c0 + k] : 0.f;
         s1[k] = (p.emit.hi1 && p.emit.s1) ? p.emit.s1[(int64_t)b * p.C + c0 + k] : 1.f;
         s2[k] = (p.emit.hi2 && p.emit.s2) ? p.emit.s2[(int64_t)b * p.C + c0 + k] : 1.f;
     }
-    const float nstr = p.noise ? p.noise_strength[0] : 0.f;
-    const float* nptr = p.noise ? p.noise + (int64_t)b * p.noise_bstride + (int64_t)oy0 * p.OW + ox : nullptr;
+    const float nstr = p.noise ? p.noise_strength[grp] : 0.f;
+    const float* nptr = p.noise ? p.noise + (int64_t)grp * p.noise_gstride + (int64_t)b * p.noise_bstride + (int64_t)oy0 * p.OW + ox : nullptr;
     const int64_t row_f = (int64_t)p.RW * p.C;
     const float* rp = p.raw + (int64_t)b * p.RH * row_f + (int64_t)(oy0 - 1) * row_f + (int64_t)(ox - 1) * p.C + c0;
     const bool v0 = ox - 1 >= 0, v3 = ox + 2 < p.RW;      // ox, ox+1 always valid (ox < OW = RW-1)
@@ -347,7 +348,7 @@ __global__ void torgb_finish_kernel(ia_torgb_params p) {
         c = i % p.C; int64_t t = i / p.C; x = t % p.W; t /= p.W; y = t % p.H; b = (int)(t / p.H);
     }
     float v = p.raw[(((int64_t)b * p.H + y) * p.W + x) * p.raw_ld + c];
-    if (p.bias) v += p.bias[c];
+    if (p.bias) v += p.bias[(p.groups > 1 ? b / p.imgs_per_group : 0) * p.C + c];
     if (p.clamp >= 0.f) v = fminf(fmaxf(v, -p.clamp), p.clamp);
     if (p.img_prev) {
         // upsample2d: zero-stuff x2, pad (2,1), 4-tap [1,3,3,1]/8 * 2 per axis.  Even output 2m: .25*x[m-1] + .75*x[m];
@@ -389,7 +390,7 @@ __global__ void __launch_bounds__(256) torgb_finish_vec4_kernel(ia_torgb_params 
     float4 v;
     if ((p.raw_ld & 3) == 0) v = __ldg(reinterpret_cast<const float4*>(p.raw + pix * p.raw_ld + c));
     else { const float* q = p.raw + pix * p.raw_ld + c; v = make_float4(q[0], q[1], q[2], q[3]); }
-    if (p.bias) { const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + c)); v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w; }
+    if (p.bias) { const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + (p.groups > 1 ? b / p.imgs_per_group : 0) * p.C + c)); v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w; }
     if (p.clamp >= 0.f) {
         v.x = fminf(fmaxf(v.x, -p.clamp), p.clamp); v.y = fminf(fmaxf(v.y, -p.clamp), p.clamp);
         v.z = fminf(fmaxf(v.z, -p.clamp), p.clamp); v.w = fminf(fmaxf(v.w, -p.clamp), p.clamp);
@@ -530,6 +531,7 @@ int ia_conv_validate(const ia_conv_params* p, const char* who) {
     IA_CHECK(p->mode == 0 || p->mode == 1, "%s: bad epilogue mode", who);
     IA_CHECK(p->noise == nullptr || p->noise_strength != nullptr, "%s: noise needs noise_strength", who);
     IA_CHECK(p->emit.out32 || p->emit.hi1 || p->emit.hi2, "%s: nothing to emit", who);
+    IA_CHECK(p->groups <= 1 || (p->imgs_per_group > 0 && p->B == p->groups * p->imgs_per_group), "%s: grouped launch needs B == groups * imgs_per_group", who);
     IA_CHECK(!p->emit.hi1 || (p->emit.lo1 && p->emit.c1_pad >= p->Cout && (p->emit.c1_pad & 3) == 0), "%s: bad emit 1", who);
     IA_CHECK(!p->emit.hi2 || (p->emit.lo2 && p->emit.c2_pad >= p->Cout && (p->emit.c2_pad & 3) == 0), "%s: bad emit 2", who);
     return 0;
@@ -537,6 +539,7 @@ int ia_conv_validate(const ia_conv_params* p, const char* who) {
 
 extern "C" int ia_conv_simt(const ia_conv_params* p, void* stream) {
     if (int rc = ia_conv_validate(p, "ia_conv_simt")) return rc;
+    IA_CHECK(p->groups <= 1, "ia_conv_simt: grouped launches are implemented by ia_conv_tc only");
     int64_t rows = (int64_t)p->B * p->GH * p->GW;
     dim3 grid((unsigned)cdiv(rows, SIMT_TM), (unsigned)cdiv(p->Cout_pad, SIMT_TN));
     ia::prof_begin("ia_conv_simt", as_stream(stream));

@@ -255,6 +255,40 @@ class ConvPack:
         return pack
 
 
+class ConvPackGroup:
+    """Packed weights of the same layer of several networks, stacked along the tap axis ([G*taps][Cout_pad][Cin_pad]) for a
+    grouped launch (ia_conv_params.groups).  Output channels are zero-padded to the widest member (ToRGB layers of the
+    32- and 96-channel backbones)."""
+
+    def __init__(self, weights, need_wsq=True):
+        Cout = max(int(w.shape[0]) for w in weights)
+        packs = []
+        for w in weights:
+            w = w.detach()
+            if w.shape[0] != Cout:
+                wp = torch.zeros((Cout,) + tuple(w.shape[1:]), dtype=w.dtype, device=w.device)
+                wp[:w.shape[0]] = w
+                w = wp
+            packs.append(ConvPack(w, need_wsq))
+        p0 = packs[0]
+        self.G = len(packs)
+        self.Cout, self.Cin, self.kh, self.kw, self.taps = Cout, p0.Cin, p0.kh, p0.kw, p0.taps
+        self.Cout_pad, self.Cin_pad = p0.Cout_pad, p0.Cin_pad
+        self.w_hi = torch.cat([q.w_hi for q in packs], dim=0).contiguous()
+        self.w_lo = torch.cat([q.w_lo for q in packs], dim=0).contiguous()
+        self.wsq = [q.wsq for q in packs]
+        self.key = tuple((w.data_ptr(), w._version, str(w.device)) for w in weights)
+
+    @staticmethod
+    def current(cache_owner, attr, weights, need_wsq=True):
+        pack = cache_owner.__dict__.get(attr)
+        key = tuple((w.data_ptr(), w._version, str(w.device)) for w in weights)
+        if pack is None or pack.key != key:
+            pack = ConvPackGroup(weights, need_wsq)
+            cache_owner.__dict__[attr] = pack
+        return pack
+
+
 class StylePlan:
     """Device table of ia_style_layer entries + output buffers for a group of layers that share one ws tensor."""
 
@@ -359,8 +393,14 @@ def _noise_bstride(noise):
     return 0 if noise is None or noise.ndim < 3 else noise.shape[-1] * noise.shape[-2]
 
 
+def _set_group(p, group):
+    """group = (G, imgs_per_group, noise_gstride) or None."""
+    if group is not None:
+        p.groups, p.imgs_per_group, p.noise_gstride = int(group[0]), int(group[1]), int(group[2])
+
+
 def conv_same(hi, lo, pack, Cin_pad, out32, dcoef=None, noise=None, noise_strength=None, bias=None, act='linear',
-              gain=1.0, clamp=None, mode=1, impl=None, e1=None, e2=None):
+              gain=1.0, clamp=None, mode=1, impl=None, e1=None, e2=None, group=None):
     """k x k correlation, stride 1, 'same' padding (flip_weight=True branch of conv2d_resample, :134-136)."""
     st = _enter(hi)
     B, H, W, _ = hi.shape
@@ -381,10 +421,11 @@ def conv_same(hi, lo, pack, Cin_pad, out32, dcoef=None, noise=None, noise_streng
     p.noise_bstride = _noise_bstride(noise)
     p.act, p.alpha, p.gain, p.clamp = ACT_IDS[act], ACT_DEFAULTS[act][0], float(gain), float(-1 if clamp is None else clamp)
     p.emit = _emit(out32, e1, e2)
+    _set_group(p, group)
     _conv_call(p, st, impl)
 
 
-def conv_transpose_up2_raw(hi, lo, pack, Cin_pad, raw, impl=None):
+def conv_transpose_up2_raw(hi, lo, pack, Cin_pad, raw, impl=None, group=None):
     """Stride-2 transposed 3x3 convolution (true convolution, conv2d_resample.py:114-127) written as four output-parity
     phases; raw is [B, 2H+1, 2W+1, Cout] fp32.  Even output row 2m gets ky=0 from input row m and ky=2 from row m-1; odd
     output row 2m+1 gets ky=1 from row m (same for columns)."""
@@ -408,6 +449,7 @@ def conv_transpose_up2_raw(hi, lo, pack, Cin_pad, raw, impl=None):
             p.mode = 0
             p.act, p.alpha, p.gain, p.clamp = 1, 0.0, 1.0, -1.0
             p.emit = _emit(raw)
+            _set_group(p, group)
             _conv_call(p, st, impl)
 
 
@@ -427,7 +469,7 @@ def fir4x4_gain4(device):
     return f
 
 
-def fir_epilogue(raw, fir, out32, dcoef, noise, noise_strength, bias, act, gain, clamp, e1=None, e2=None):
+def fir_epilogue(raw, fir, out32, dcoef, noise, noise_strength, bias, act, gain, clamp, e1=None, e2=None, group=None):
     st = _enter(raw)
     B, RH, RW, Cc = raw.shape
     OH, OW = RH - 1, RW - 1
@@ -438,10 +480,11 @@ def fir_epilogue(raw, fir, out32, dcoef, noise, noise_strength, bias, act, gain,
     p.noise_bstride = _noise_bstride(noise)
     p.act, p.alpha, p.gain, p.clamp = ACT_IDS[act], ACT_DEFAULTS[act][0], float(gain), float(-1 if clamp is None else clamp)
     p.emit = _emit(out32, e1, e2)
+    _set_group(p, group)
     _C.check(_C.lib().ia_fir_epilogue(C.byref(p), st), 'ia_fir_epilogue')
 
 
-def torgb_finish(raw, bias, clamp, img_prev, out_nchw=False):
+def torgb_finish(raw, bias, clamp, img_prev, out_nchw=False, group=None):
     """raw [B,H,W,C]; img_prev [B,H/2,W/2,C] NHWC or None -> img [B,H,W,C] NHWC (or [B,C,H,W] planar)."""
     st = _enter(raw)
     B, H, W, Cc = raw.shape
@@ -453,6 +496,8 @@ def torgb_finish(raw, bias, clamp, img_prev, out_nchw=False):
         assert img_prev.is_contiguous() and tuple(img_prev.shape) == (B, H // 2, W // 2, Cc), (img_prev.shape, raw.shape)
     p = _C.TorgbParams(_p(raw), raw.stride(2), _p(bias), float(-1 if clamp is None else clamp), _p(img_prev), _p(out),
                        B, H, W, Cc, 1 if out_nchw else 0)
+    if group is not None:
+        p.groups, p.imgs_per_group = int(group[0]), int(group[1])
     _C.check(_C.lib().ia_torgb_finish(C.byref(p), st), 'ia_torgb_finish')
     return out
 

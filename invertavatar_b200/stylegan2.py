@@ -441,6 +441,21 @@ class SynthesisNetwork(torch.nn.Module):
                 self.num_ws += block.num_torgb
             setattr(self, f'b{res}', block)
 
+    def style_pass(self, ws):
+        """One style/demod pass for the whole network (2 launches instead of 2 per block) -> (styles, dcoefs, spans):
+        per-layer lists in evaluation order and the [first, last) span of every block."""
+        blocks = [getattr(self, f'b{res}') for res in self.block_resolutions]
+        entries, spans, w_idx = [], [], 0
+        for block in blocks:
+            lay = block.layers()
+            first = len(entries)
+            for j, (kind, layer) in enumerate(lay):
+                entries.append(layer.style_entry(w_idx + j))
+            spans.append((first, len(entries)))
+            w_idx += block.num_conv
+        styles, dcoefs = _plan_for(self, entries).run(ws)
+        return styles, dcoefs, spans
+
     def forward(self, ws, cond_list=None, return_list=False, feat_conditions=None, return_imgs=False, out_res=(32, 256),
                 **block_kwargs):
         """cond_list / return_list / feat_conditions semantics of networks_stylegan2_new.py:509-548.  (The stock
@@ -451,16 +466,11 @@ class SynthesisNetwork(torch.nn.Module):
         ws = ws.to(torch.float32)
         B = ws.shape[0]
         blocks = [getattr(self, f'b{res}') for res in self.block_resolutions]
-        # one style/demod pass for the whole network (2 launches instead of 2 per block)
-        entries, spans, w_idx = [], [], 0
-        for block in blocks:
-            lay = block.layers()
-            first = len(entries)
-            for j, (kind, layer) in enumerate(lay):
-                entries.append(layer.style_entry(w_idx + j))
-            spans.append((first, len(entries)))
-            w_idx += block.num_conv
-        styles, dcoefs = _plan_for(self, entries).run(ws)
+        prefix = block_kwargs.pop('prefix', None)     # engine-internal: result of synthesis_prefix_grouped for this network
+        if prefix is not None:
+            styles, dcoefs, spans = prefix['styles'], prefix['dcoefs'], prefix['spans']
+        else:
+            styles, dcoefs, spans = self.style_pass(ws)
         x_list, out_imgs = [], []
         start_layer = int(np.log2(out_res[0])) - 2
         end_layer = (self.img_resolution_log2 - 2) if len(out_res) == 1 else (int(np.log2(out_res[1])) - 2)
@@ -476,8 +486,14 @@ class SynthesisNetwork(torch.nn.Module):
             has_next = index + 1 < len(blocks)
             next_conv = blocks[index + 1].conv0 if (has_next and not blend_next) else None
             next_styles = styles[spans[index + 1][0]] if next_conv is not None else None
-            x32, img, a = block.run_chain(a, img, styles[lo_i:hi_i], dcoefs[lo_i:hi_i], B, noise_mode=noise_mode, condition=cond_feat,
-                                          want_x32=want_x32, next_conv=next_conv, next_styles=next_styles)
+            if prefix is not None and index < prefix['index']:
+                continue                                  # evaluated by the grouped prefix
+            if prefix is not None and index == prefix['index']:
+                assert cond_feat is None and index <= start_layer
+                x32, img, a = prefix['x32'], prefix['img'], prefix['a_next']
+            else:
+                x32, img, a = block.run_chain(a, img, styles[lo_i:hi_i], dcoefs[lo_i:hi_i], B, noise_mode=noise_mode, condition=cond_feat,
+                                              want_x32=want_x32, next_conv=next_conv, next_styles=next_styles)
             if emitting:
                 if return_list:
                     if index == start_layer:
@@ -516,6 +532,126 @@ def _split_cond(c):
         return c[0], c[1]
     cn = rt.to_nhwc(c)
     return cn[..., :-1], cn[..., -1].contiguous()
+
+
+def _stack_cached(owner, attr, tensors, flatten_from=None, pad_to=None):
+    """torch.stack of small per-network tensors (bias, noise image, noise strength), cached on ``owner`` until one changes;
+    1-D members are zero-padded to ``pad_to`` entries first."""
+    key = tuple((t.data_ptr(), t._version) for t in tensors) + (pad_to,)
+    hit = owner.__dict__.get(attr)
+    if hit is None or hit[0] != key:
+        members = [t.detach().float() for t in tensors]
+        if pad_to is not None:
+            members = [torch.nn.functional.pad(t, (0, pad_to - t.shape[0])) for t in members]
+        st = torch.stack(members)
+        if flatten_from is not None:
+            st = st.reshape(*st.shape[:flatten_from], -1)
+        hit = (key, st.contiguous())
+        owner.__dict__[attr] = hit
+    return hit[1]
+
+
+def can_group_prefix(nets, upto_res=32):
+    """True when the networks have identical layer shapes up to ``upto_res`` (image channels may differ) and the fused
+    up-sampling path applies, i.e. synthesis_prefix_grouped may evaluate their low-resolution blocks as one batch."""
+    n0 = nets[0]
+    for n in nets:
+        if n.block_resolutions != n0.block_resolutions or n.w_dim != n0.w_dim:
+            return False
+        for res in n.block_resolutions:
+            if res > upto_res:
+                break
+            b, b0 = getattr(n, f'b{res}'), getattr(n0, f'b{res}')
+            if b.architecture != 'skip' or not hasattr(b, 'torgb') or b.in_channels != b0.in_channels:
+                return False
+            for (k, l), (k0, l0) in zip(b.layers(), b0.layers()):
+                if k != k0 or l.in_channels != l0.in_channels or (k == 'conv' and (l.out_channels != l0.out_channels or l.up != l0.up or
+                                                                                 l.activation != l0.activation or l.conv_clamp != l0.conv_clamp or
+                                                                                 l.use_noise != l0.use_noise or (l.up == 2 and not _layer_filter_ok(l)))):
+                    return False
+                if k == 'torgb' and l.conv_clamp != l0.conv_clamp:
+                    return False
+    return upto_res in n0.block_resolutions and n0.block_resolutions[-1] > upto_res
+
+
+def synthesis_prefix_grouped(nets, ws, noise_mode='const', upto_res=32):
+    """Blocks b4..b{upto_res} of several SynthesisNetworks evaluated as ONE grouped batch (ia_conv_params.groups): the
+    low-resolution layers are latency-bound (a few CTAs, a long serial k-loop), so running the three backbones' copies side by
+    side costs about the same time as one of them.  Arithmetic per network is unchanged (same kernels, same operand order).
+    Returns one ``prefix`` dict per network for ``SynthesisNetwork.forward(..., prefix=...)``."""
+    G = len(nets)
+    ws = ws.to(torch.float32)
+    B = ws.shape[0]
+    dev = ws.device
+    passes = [n.style_pass(ws) for n in nets]
+    spans = passes[0][2]
+    k_last = nets[0].block_resolutions.index(upto_res)
+    group = lambda gstride: (G, B, gstride)
+
+    def cat_layer(idx, which):       # per-layer styles / dcoefs of all networks, group-major
+        return torch.cat([ps[which][idx] for ps in passes], dim=0)
+
+    def layer_noise(layers):
+        l0 = layers[0]
+        if not l0.use_noise or noise_mode == 'none':
+            return None, None, 0
+        strength = _stack_cached(l0, '_ia_g_strength', [l.noise_strength for l in layers])
+        R = l0.resolution
+        if noise_mode == 'const':
+            return _stack_cached(l0, '_ia_g_noise', [l.noise_const for l in layers], flatten_from=1), strength, R * R
+        return torch.randn([G * B, R, R], device=dev), strength, 0
+
+    a = img = x32 = None
+    a_next = None
+    for index in range(k_last + 1):
+        res = nets[0].block_resolutions[index]
+        blocks = [getattr(n, f'b{res}') for n in nets]
+        b0 = blocks[0]
+        lo_i = spans[index][0]
+        i = 0
+        conv1s = [b.conv1 for b in blocks]
+        pack1 = rt.ConvPackGroup.current(conv1s[0], '_ia_gpack', [c.weight for c in conv1s])
+        if b0.in_channels == 0:
+            x0 = torch.cat([b.const.detach().permute(1, 2, 0).unsqueeze(0).expand(B, -1, -1, -1) for b in blocks], dim=0).contiguous()
+            hi, lo = rt.modsplit(x0, cat_layer(lo_i, 0), C_pad=pack1.Cin_pad)
+            a1 = rt.Split(hi, lo)
+        else:
+            conv0s = [b.conv0 for b in blocks]
+            pack0 = rt.ConvPackGroup.current(conv0s[0], '_ia_gpack', [c.weight for c in conv0s])
+            a1 = rt.new_split(G * B, res, res, pack1.Cin_pad, dev, C=conv1s[0].in_channels)
+            H = res // 2
+            raw = torch.empty((G * B, 2 * H + 1, 2 * H + 1, pack0.Cout), dtype=torch.float32, device=dev)
+            rt.conv_transpose_up2_raw(a.hi, a.lo, pack0, pack0.Cin_pad, raw, group=group(0))
+            nz, ns, gs = layer_noise(conv0s)
+            rt.fir_epilogue(raw, rt.fir4x4_gain4(dev), None, cat_layer(lo_i, 1), nz, ns, _stack_cached(conv0s[0], '_ia_g_bias', [c.bias for c in conv0s]),
+                            conv0s[0].activation, conv0s[0].act_gain, conv0s[0].conv_clamp, e1=(a1, cat_layer(lo_i + 1, 0)), group=group(gs))
+            i = 1
+        last = index == k_last
+        rgbs = [b.torgb for b in blocks]
+        packr = rt.ConvPackGroup.current(rgbs[0], '_ia_gpack', [t.weight for t in rgbs], need_wsq=False)
+        a_rgb = rt.new_split(G * B, res, res, packr.Cin_pad, dev, C=rgbs[0].in_channels)
+        nxt = [getattr(n, f'b{nets[0].block_resolutions[index + 1]}').conv0 for n in nets]
+        a_next = rt.new_split(G * B, res, res, nxt[0].pack().Cin_pad, dev, C=nxt[0].in_channels)
+        x32 = torch.empty((G * B, res, res, pack1.Cout), dtype=torch.float32, device=dev) if last else None
+        nz, ns, gs = layer_noise(conv1s)
+        rt.conv_same(a1.hi, a1.lo, pack1, pack1.Cin_pad, x32, dcoef=cat_layer(lo_i + i, 1), noise=nz, noise_strength=ns,
+                     bias=_stack_cached(conv1s[0], '_ia_g_bias', [c.bias for c in conv1s]), act=conv1s[0].activation, gain=conv1s[0].act_gain,
+                     clamp=conv1s[0].conv_clamp, mode=1, e1=(a_next, cat_layer(spans[index + 1][0], 0)), e2=(a_rgb, cat_layer(lo_i + i + 1, 0)),
+                     group=group(gs))
+        rawc = torch.empty((G * B, res, res, packr.Cout), dtype=torch.float32, device=dev)
+        rt.conv_same(a_rgb.hi, a_rgb.lo, packr, packr.Cin_pad, rawc, mode=0, group=group(0))
+        bias_rgb = _stack_cached(rgbs[0], '_ia_g_bias', [t.bias for t in rgbs], pad_to=packr.Cout)
+        img = rt.torgb_finish(rawc, bias_rgb, rgbs[0].conv_clamp, img, group=(G, B))
+        a = a_next
+    out = []
+    for g, n in enumerate(nets):
+        sl = slice(g * B, (g + 1) * B)
+        im = img[sl]
+        if n.img_channels != im.shape[-1]:
+            im = im[..., :n.img_channels].contiguous()
+        out.append(dict(index=k_last, x32=x32[sl], img=im, a_next=rt.Split(a_next.hi[sl], a_next.lo[sl]),
+                        styles=passes[g][0], dcoefs=passes[g][1], spans=passes[g][2]))
+    return out
 
 
 @persistence.persistent_class

@@ -23,6 +23,12 @@ _KNOWN_SR = {
 }
 
 
+def _grouped_prefix_enabled():
+    """IA_GROUPED_PREFIX=0 evaluates the three backbones one after the other (cross-check / profiling)."""
+    import os
+    return os.environ.get('IA_GROUPED_PREFIX', '1') != '0'
+
+
 def _construct(class_name, **kwargs):
     """dnnlib.util.construct_class_by_name for the super-resolution module (triplane_v20.py:56-58)."""
     cls = _KNOWN_SR.get(class_name)
@@ -135,7 +141,7 @@ class TriPlaneGenerator(torch.nn.Module):
         return views, plane_img
 
     def _stitch_render_sr(self, ws, c, mesh_condition, texture_feats, static_feats, neural_rendering_resolution,
-                          evaluation, synthesis_kwargs):
+                          evaluation, synthesis_kwargs, face_prefix=None):
         cam = c[:, -25:]
         if neural_rendering_resolution is None:
             neural_rendering_resolution = self.neural_rendering_resolution
@@ -151,7 +157,7 @@ class TriPlaneGenerator(torch.nn.Module):
         conds, full_alpha, _ = self._rasterize_nhwc(tex, mesh_condition['uvcoords_image'], static_views, BBOX_256,
                                                     levels=(0, 1, 2, 3))
         noise_kwargs = {k: v for k, v in synthesis_kwargs.items() if k in ('noise_mode',)}
-        stitch = self.face_backbone.synthesis(ws, cond_list=conds[:4], return_list=False, **noise_kwargs)   # NCHW view
+        stitch = self.face_backbone.synthesis(ws, cond_list=conds[:4], return_list=False, prefix=face_prefix, **noise_kwargs)   # NCHW view
         stitch = rt.to_nhwc(stitch)                                                                          # [B,256,256,32]
 
         # stitch into plane 0 of a copy of the static planes (triplane_v20.py:119-128)
@@ -185,10 +191,16 @@ class TriPlaneGenerator(torch.nn.Module):
         if importance_u is not None:
             self.renderer.importance_u = importance_u
         noise_kwargs = {k: v for k, v in synthesis_kwargs.items() if k in ('noise_mode',)}
-        texture_feats = self.texture_backbone.synthesis(ws, cond_list=None, return_list=True, **noise_kwargs)
-        static_feats = self.backbone.synthesis(ws, cond_list=None, return_list=True, **noise_kwargs)
+        # The blocks up to 32^2 of the three backbones do not depend on each other (the face backbone receives its
+        # conditions after its own 32^2 block) and are latency-bound: evaluate them as one grouped batch.
+        nets = [self.texture_backbone.synthesis, self.backbone.synthesis, self.face_backbone.synthesis]
+        pre = [None, None, None]
+        if _grouped_prefix_enabled() and sg.can_group_prefix(nets):
+            pre = sg.synthesis_prefix_grouped(nets, ws, noise_mode=noise_kwargs.get('noise_mode', 'random'))
+        texture_feats = self.texture_backbone.synthesis(ws, cond_list=None, return_list=True, prefix=pre[0], **noise_kwargs)
+        static_feats = self.backbone.synthesis(ws, cond_list=None, return_list=True, prefix=pre[1], **noise_kwargs)
         out = self._stitch_render_sr(ws, c, mesh_condition, texture_feats, static_feats, neural_rendering_resolution,
-                                     evaluation, synthesis_kwargs)
+                                     evaluation, synthesis_kwargs, face_prefix=pre[2])
         if return_featmap:
             out['texture'] = texture_feats
             return out

@@ -19,3 +19,25 @@ def test_expanded_ws_batch():
     for x, y in zip(a, b):
         assert torch.equal(x, y)
         assert torch.equal(x[0], x[2])
+
+
+def test_grouped_prefix_matches_sequential(monkeypatch):
+    """The grouped evaluation of the three backbones' low-resolution blocks (ia_conv_params.groups) must reproduce the
+    one-network-at-a-time path: same kernels, same operands, different tiling only."""
+    import copy
+    G = copy.deepcopy(build_generator(16, 16)).to('cuda')
+    B = 3
+    z, cond, c, uv = synth.latents(B).cuda(), synth.frontal_camera(B).cuda(), synth.cameras(B).cuda(), synth.uvcoords_image(B).cuda()
+    jit = synth.depth_jitter(B, 64 * 64, 16).cuda()
+    outs = {}
+    with torch.no_grad():
+        ws = G.mapping(z, cond, truncation_psi=0.7, truncation_cutoff=14)
+        for flag in ('1', '0'):
+            monkeypatch.setenv('IA_GROUPED_PREFIX', flag)
+            outs[flag] = G.synthesis(ws, c, {'uvcoords_image': uv}, neural_rendering_resolution=64, noise_mode='const', evaluation=True,
+                                     depth_jitter=jit.clone(), return_featmap=True)
+    for k in ('image', 'image_raw', 'feature_image', 'triplane'):
+        d = float((outs['1'][k].float() - outs['0'][k].float()).abs().max())
+        assert d <= 2e-5 * max(1.0, float(outs['0'][k].abs().max())), (k, d)
+    for a, b in zip(outs['1']['texture'], outs['0']['texture']):
+        assert float((a - b).abs().max()) <= 2e-5 * max(1.0, float(b.abs().max()))
