@@ -284,7 +284,11 @@ def run_b200(args):
             achieved = flops / (conv['ms'] * 1e-3) / 1e12 if conv['ms'] > 0 else 0.0
             roofline = {'kernel': 'conv_tc_kernel (tcgen05 implicit-GEMM modulated convolution)', 'bound': 'tensor', 'achieved': achieved,
                         'peak': peak, 'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained (of measured)' if peaks else 'fallback 1.4 PFLOP/s sustained (of fallback)',
-                        'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': None,
+                        'unit': 'TFLOP/s', 'frac': achieved / peak,
+                        # DRAM bytes of one launch from the committed `ncu --set full` capture (profiles/r1_conv_same_full_v4.txt):
+                        # the 128->128 @512^2 layer at batch 8 reads 1.085 GB and writes 1.030 GB; its algorithmic bytes are the
+                        # bf16 hi/lo operand in (1.074 GB) and the next layer's operand out (1.074 GB) -- no re-reads
+                        'traffic': 2.115e9, 'traffic_launch': 'conv_tc2 128->128 @512x512, batch 8 (algorithmic 2.147e9 B)',
                         'algorithmic_flops_per_frame': conv_flops_per_frame(G), 'launches_per_step': conv['launches'] / args.steps,
                         'avg_launch_ms': conv['ms'] / max(1, conv['launches']),
                         'note': 'algorithmic FLOPs (fp32 semantics); the 3-term bf16 split issues 3x these MMAs, so frac <= 1/3 in parity mode'}
