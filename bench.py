@@ -48,7 +48,7 @@ def workload_config(args, n_gpus):
                         f'(BASELINE configs[1]), random-init generator, synthetic latents/cameras/UV',
             'frames_per_gpu_per_step': args.batch, 'global_frames_per_step': args.batch * n_gpus,
             'neural_res': args.res, 'depth_samples': [args.depth, args.depth], 'parallelism': f'dp{n_gpus} (frames sharded, weights replicated)',
-            'conv_precision': 'bf16x3 split operands (hi*hi+hi*lo+lo*hi), fp32 accumulate in TMEM',
+            'conv_precision': 'bf16x3 split operands (hi*hi+hi*lo+lo*hi), fp32 accumulate in TMEM', 'gather': getattr(args, 'gather_kind', 'none'),
             'l2': 'working set per step (>10 GB of activations) exceeds the 126 MB L2; no explicit flush'}
 
 
@@ -190,11 +190,32 @@ def run_b200(args):
     z, cond, c, uv = z_h.to(dev), cond_h.to(dev), c_h.to(dev), uv_h.to(dev)
     img_h = torch.empty((B, 3, 512, 512), dtype=torch.float32).pin_memory()
     gathered = torch.empty((world * B, 3, 512, 512), dtype=torch.float32, device=dev) if world > 1 else None
+    # The one exchange step of the path: gather the final images.  Preferred: the last ToRGB kernel stores its
+    # frames straight into every rank's gathered buffer over NVLink (symmetric memory, NVSwitch multicast when available) and a
+    # cross-rank barrier closes the step; fallback (IA_GATHER=nccl or no symmetric memory): one NCCL all-gather.
+    peer = None
+    gather_kind = 'none'
+    if world > 1:
+        gather_kind = 'nccl all_gather_into_tensor'
+        if os.environ.get('IA_GATHER', 'p2p') != 'nccl':
+            try:
+                from invertavatar_b200.parallel import PeerFrameGather
+                peer = PeerFrameGather(B, (3, 512, 512), device=dev)
+                gather_kind = 'fused into the last ToRGB kernel: ' + ('multimem.st over the NVSwitch multicast mapping' if peer.mc_ptr else
+                                                                      'stores to peer-mapped symmetric memory') + ' + barrier'
+            except Exception as ex:   # symmetric memory unavailable on this box / build
+                peer = None
+                gather_kind += f' (symmetric memory unavailable: {type(ex).__name__})'
 
     def frame_batch(z, cond, c, uv):
         ws = G.mapping(z, cond, truncation_psi=0.7, truncation_cutoff=14)
+        if peer is not None:
+            with peer.sink():
+                img = G.synthesis(ws, c, {'uvcoords_image': uv}, neural_rendering_resolution=res, noise_mode='const', evaluation=True)['image']
+            peer.barrier()
+            return img
         img = G.synthesis(ws, c, {'uvcoords_image': uv}, neural_rendering_resolution=res, noise_mode='const', evaluation=True)['image']
-        if world > 1:   # the one collective of the path: gather the final images
+        if world > 1:
             dist.all_gather_into_tensor(gathered, img.contiguous())
         return img
 
@@ -250,6 +271,13 @@ def run_b200(args):
     with torch.no_grad():
         for _ in range(max(args.warmup, 3)):
             step_resident()
+        if peer is not None:   # the fused gather must reproduce the NCCL gather bit for bit
+            img = step_resident()
+            dist.all_gather_into_tensor(gathered, img.contiguous())
+            torch.cuda.synchronize()
+            ok = torch.tensor([1 if torch.equal(gathered, peer.tensor) else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            assert int(ok.item()) == 1, 'fused peer-memory gather differs from the NCCL all-gather'
         clocks = ClockSampler(local)
         if rank == 0:
             clocks.start()   # samples every 200 ms across both timed regions (resident + end-to-end)
@@ -307,6 +335,7 @@ def run_b200(args):
         dist.destroy_process_group()
     if rank != 0:
         return
+    args.gather_kind = gather_kind
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
             'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
             'data': 'synthetic', 'config': workload_config(args, world), 'clocks': clk,

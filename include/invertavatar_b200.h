@@ -169,6 +169,11 @@ typedef struct {
     const float* img_prev;                       /* [B][H/2][W/2][C] or NULL */
     float* img_out; int32_t B, H, W, C; int32_t out_nchw;
     int32_t groups; int32_t imgs_per_group;      /* bias[g*C + c] with g = b / imgs_per_group (groups <= 1: one bias) */
+    /* Fused image gather (the one exchange step of the path).  With out_nchw=1 every value is also stored at
+     * element offset peer_offset + (its index in img_out) of the gathered [world*B][C][H][W] buffer of every rank: either one
+     * multimem.st to mc_out (NVSwitch multicast address of the symmetric buffer) or n_peers plain stores to the peer-mapped
+     * pointers peer_out[0..n_peers).  All NULL / 0: no gather. */
+    float* peer_out[8]; int32_t n_peers; int64_t peer_offset; float* mc_out;
 } ia_torgb_params;
 int ia_torgb_finish(const ia_torgb_params* p, void* stream);
 

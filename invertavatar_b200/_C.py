@@ -67,7 +67,8 @@ class FirParams(C.Structure):
 class TorgbParams(C.Structure):
     _fields_ = [('raw', c_f32p), ('raw_ld', C.c_int64), ('bias', c_f32p), ('clamp', C.c_float), ('img_prev', c_f32p),
                 ('img_out', c_f32p), ('B', C.c_int32), ('H', C.c_int32), ('W', C.c_int32), ('C', C.c_int32),
-                ('out_nchw', C.c_int32), ('groups', C.c_int32), ('imgs_per_group', C.c_int32)]
+                ('out_nchw', C.c_int32), ('groups', C.c_int32), ('imgs_per_group', C.c_int32),
+                ('peer_out', c_f32p * 8), ('n_peers', C.c_int32), ('peer_offset', C.c_int64), ('mc_out', c_f32p)]
 
 
 class ResizeParams(C.Structure):

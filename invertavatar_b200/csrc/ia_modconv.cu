@@ -371,8 +371,19 @@ __global__ void torgb_finish_kernel(ia_torgb_params p) {
         }
         v = up + v;
     }
-    if (p.out_nchw) p.img_out[(((int64_t)b * p.C + c) * p.H + y) * p.W + x] = v;
-    else p.img_out[(((int64_t)b * p.H + y) * p.W + x) * p.C + c] = v;
+    if (p.out_nchw) {
+        const int64_t o = (((int64_t)b * p.C + c) * p.H + y) * p.W + x;
+        p.img_out[o] = v;
+        // fused gather of the final frames: the same value goes to this rank's slot of every rank's gathered buffer, through
+        // the NVSwitch multicast mapping when there is one (one store, replicated by the switch), else over the peer mappings
+        if (p.mc_out) {
+            asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p.mc_out + p.peer_offset + o), "f"(v) : "memory");
+        } else {
+            for (int k = 0; k < p.n_peers; ++k) p.peer_out[k][p.peer_offset + o] = v;
+        }
+    } else {
+        p.img_out[(((int64_t)b * p.H + y) * p.W + x) * p.C + c] = v;
+    }
 }
 
 // 4 channels per thread, 32-bit index arithmetic (NHWC output, C % 4 == 0): the element-per-thread kernel above spends its
@@ -417,6 +428,8 @@ __global__ void __launch_bounds__(256) torgb_finish_vec4_kernel(ia_torgb_params 
 extern "C" int ia_torgb_finish(const ia_torgb_params* p, void* stream) {
     IA_CHECK(p && p->raw && p->img_out, "ia_torgb_finish: null tensor");
     IA_CHECK(p->img_prev == nullptr || ((p->H & 1) == 0 && (p->W & 1) == 0), "ia_torgb_finish: odd size with skip image");
+    IA_CHECK(p->n_peers >= 0 && p->n_peers <= 8, "ia_torgb_finish: at most 8 peers");
+    IA_CHECK((p->n_peers == 0 && p->mc_out == nullptr) || p->out_nchw, "ia_torgb_finish: the fused gather needs the planar (out_nchw) output");
     int64_t total = (int64_t)p->B * p->H * p->W * p->C;
     if (total == 0) return 0;
     ia::prof_begin("ia_torgb_finish", as_stream(stream));

@@ -45,3 +45,36 @@ def render_sharded(render_fn, z, cond, c, uv, group=None):
     sl = slice(first, first + cnt)
     img = render_fn(z[sl], cond[sl], c[sl], uv[sl])
     return gather_frames(img, counts, group)
+
+
+class PeerFrameGather:
+    """Gathered frame buffer [world*B,3,H,W] in symmetric (peer-mapped) memory: every rank's last ToRGB kernel writes its
+    frames straight into slot ``rank`` of every rank's copy (``runtime.frame_sink``), so the image gather of SURVEY 8(e) is
+    the epilogue of the producing kernel plus one cross-rank barrier, not a separate NCCL collective.  Uses the NVSwitch
+    multicast mapping (multimem.st: one store, replicated in the switch) when the allocation has one, plain stores to the
+    peer mappings otherwise.  ``available()`` is False when symmetric memory cannot be set up; callers then fall back to
+    ``gather_frames`` (NCCL)."""
+
+    def __init__(self, frames_per_rank, shape=(3, 512, 512), device=None, group=None, multicast=True):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.per_rank = int(frames_per_rank) * int(shape[0]) * int(shape[1]) * int(shape[2])
+        self.tensor = symm_mem.empty((self.world * frames_per_rank,) + tuple(shape), dtype=torch.float32, device=device)
+        self.handle = symm_mem.rendezvous(self.tensor, self.group)
+        self.peer_ptrs = [int(q) for q in self.handle.buffer_ptrs]
+        mc = 0
+        try:
+            if multicast and self.handle.has_multicast_support:
+                mc = int(self.handle.multicast_ptr or 0)
+        except Exception:
+            mc = 0
+        self.mc_ptr = mc
+
+    def sink(self):
+        from . import runtime as rt
+        return rt.frame_sink(self.peer_ptrs, self.rank * self.per_rank, self.mc_ptr)
+
+    def barrier(self):
+        """All ranks' frame writes are visible in every copy after this (enqueued on the current stream)."""
+        self.handle.barrier(channel=0)

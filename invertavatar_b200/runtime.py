@@ -484,6 +484,27 @@ def fir_epilogue(raw, fir, out32, dcoef, noise, noise_strength, bias, act, gain,
     _C.check(_C.lib().ia_fir_epilogue(C.byref(p), st), 'ia_fir_epilogue')
 
 
+_frame_sink = None   # (peer_ptrs [int], element offset, multicast ptr or 0): consumed by the planar (final image) ToRGB tail
+
+
+class frame_sink:
+    """Context manager: while active, the ToRGB tail that writes the final planar image (out_nchw) also stores every value
+    into this rank's slot of every rank's gathered frame buffer (peer-mapped / multicast symmetric memory)."""
+
+    def __init__(self, peer_ptrs, offset, mc_ptr=0):
+        self.sink = (list(peer_ptrs), int(offset), int(mc_ptr or 0))
+
+    def __enter__(self):
+        global _frame_sink
+        self.prev, _frame_sink = _frame_sink, self.sink
+        return self
+
+    def __exit__(self, *exc):
+        global _frame_sink
+        _frame_sink = self.prev
+        return False
+
+
 def torgb_finish(raw, bias, clamp, img_prev, out_nchw=False, group=None):
     """raw [B,H,W,C]; img_prev [B,H/2,W/2,C] NHWC or None -> img [B,H,W,C] NHWC (or [B,C,H,W] planar)."""
     st = _enter(raw)
@@ -498,6 +519,15 @@ def torgb_finish(raw, bias, clamp, img_prev, out_nchw=False, group=None):
                        B, H, W, Cc, 1 if out_nchw else 0)
     if group is not None:
         p.groups, p.imgs_per_group = int(group[0]), int(group[1])
+    if out_nchw and _frame_sink is not None:
+        ptrs, off, mc = _frame_sink
+        if mc:
+            p.mc_out = mc
+        else:
+            for k, q in enumerate(ptrs):
+                p.peer_out[k] = q
+            p.n_peers = len(ptrs)
+        p.peer_offset = off
     _C.check(_C.lib().ia_torgb_finish(C.byref(p), st), 'ia_torgb_finish')
     return out
 
