@@ -225,7 +225,22 @@ def _pad_to(v, m):
     return (v + m - 1) // m * m
 
 
-class ConvPack:
+def _none():
+    return None
+
+
+class _EngineCache:
+    """Engine-side caches hung on modules (packed weights, style plans) are derived data keyed by the parameters' storage:
+    they are dropped, not copied, when the owning module is deep-copied or pickled (copy.deepcopy(G), persistence pickles)."""
+
+    def __deepcopy__(self, memo):
+        return None
+
+    def __reduce__(self):
+        return (_none, ())
+
+
+class ConvPack(_EngineCache):
     """GEMM-layout weights of one conv layer: bf16 hi/lo [taps][Cout_pad][Cin_pad] and wsq[Cout][Cin]."""
 
     def __init__(self, weight, need_wsq=True):
@@ -255,7 +270,7 @@ class ConvPack:
         return pack
 
 
-class ConvPackGroup:
+class ConvPackGroup(_EngineCache):
     """Packed weights of the same layer of several networks, stacked along the tap axis ([G*taps][Cout_pad][Cin_pad]) for a
     grouped launch (ia_conv_params.groups).  Output channels are zero-padded to the widest member (ToRGB layers of the
     32- and 96-channel backbones)."""
@@ -289,7 +304,7 @@ class ConvPackGroup:
         return pack
 
 
-class StylePlan:
+class StylePlan(_EngineCache):
     """Device table of ia_style_layer entries + output buffers for a group of layers that share one ws tensor."""
 
     def __init__(self, entries, device):

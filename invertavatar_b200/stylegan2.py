@@ -233,7 +233,7 @@ def _plan_for(owner, entries):
     key = tuple((e['affine_w'].data_ptr(), e['affine_b'].data_ptr(), 0 if e['wsq'] is None else e['wsq'].data_ptr(),
                  e['w_index']) for e in entries)
     cached = owner.__dict__.get('_ia_plan')
-    if cached is None or cached[0] != key:
+    if cached is None or cached[1] is None or cached[0] != key:
         cached = (key, rt.StylePlan(entries, entries[0]['affine_w'].device))
         owner.__dict__['_ia_plan'] = cached
     return cached[1]

@@ -82,3 +82,19 @@ def test_reload_idiom_and_cpu_inputs_fail_loudly():
         ops.bias_act(torch.zeros(1, 2, 3, 3), torch.zeros(2))
     with pytest.raises(RuntimeError):
         ops.upfirdn2d(torch.zeros(1, 2, 4, 4), ops.setup_filter([1, 3, 3, 1]), up=2)
+
+
+def test_engine_caches_do_not_block_copy_or_pickle():
+    """copy.deepcopy / pickle of a module that carries engine-side caches (ctypes tables, packed weights) drops the caches."""
+    import copy
+    import pickle
+    from invertavatar_b200 import runtime as rt
+    lin = torch.nn.Linear(2, 2)
+    plan = rt.StylePlan([], torch.device('cpu'))
+    import ctypes
+    plan.host = (ctypes.c_void_p * 2)()        # what a used plan holds
+    lin.__dict__['_ia_plan'] = (('k',), plan)
+    lin2 = copy.deepcopy(lin)
+    assert lin2.__dict__['_ia_plan'][1] is None
+    lin3 = pickle.loads(pickle.dumps(lin))
+    assert lin3.__dict__['_ia_plan'][1] is None and torch.equal(lin3.weight, lin.weight)

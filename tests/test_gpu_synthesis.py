@@ -88,3 +88,26 @@ def test_synthesis_batch_invariance():
     # not bit-identical: the batch-mean ray distance (renderer.py:311) rounds differently for 1 and 2 cameras (last ulp of
     # near/far), which moves every depth sample by ~1e-7 -- the reference has the same property (SURVEY 8e hazard 1)
     assert float((o1['image'] - out['image'][1:2]).abs().max()) <= 1e-4
+
+
+@pytest.mark.parametrize('res,D', [(256, 16), (64, 96)])
+def test_synthesis_sweep_vs_oracle(res, D):
+    """BASELINE configs[4] corners (neural resolution 64..256, 16..96 depth samples): full frame against the oracle run on
+    this host.  Resolution 256 exercises the antialiased 256 -> 128 resize in front of the super-resolution blocks
+    (superresolution.py:281-285); 96+96 samples the largest per-ray scratch of the renderer."""
+    import copy
+    G = copy.deepcopy(build_generator(D, D)).to(DEV)
+    z, cond, c, uv = synth.latents(1), synth.frontal_camera(1), synth.cameras(1), synth.uvcoords_image(1)
+    jit = synth.depth_jitter(1, res * res, D)
+    with torch.no_grad():
+        ws = G.mapping(z.to(DEV), cond.to(DEV), truncation_psi=0.7, truncation_cutoff=14)
+        out = G.synthesis(ws, c.to(DEV), {'uvcoords_image': uv.to(DEV)}, neural_rendering_resolution=res, noise_mode='const', evaluation=True,
+                          depth_jitter=jit.to(DEV))
+        sd = {k: v.cpu() for k, v in G.state_dict().items()}
+        ref = o_tp.synthesis(sd, ws.cpu(), c, uv, G.rendering_kwargs, jit, evaluation=True, neural_rendering_resolution=res)
+    err = float((out['image'].cpu() - ref['image']).abs().max())
+    p = psnr(out['image'].cpu(), ref['image'])
+    print(f'sweep res {res} D {D}: image max-abs {err:.3e}  PSNR {p:.1f} dB')
+    assert tuple(out['image_raw'].shape) == (1, 3, res, res)
+    assert err <= IMAGE_ATOL and p > 50.0
+    assert float((out['image_depth'].cpu() - ref['image_depth']).abs().max()) <= 1e-3
