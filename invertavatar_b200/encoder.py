@@ -500,6 +500,13 @@ class inversionNet(nn.Module):
         xn = _face_pool(_nhwc(x.float()), 256)
         return self.encoder.run_nhwc(xn, w_offset=self.latent_avg.reshape(-1))
 
+    def _side_streams(self, device):
+        st = self.__dict__.get('_ia_streams')
+        if st is None or st[0] != str(device):
+            st = (str(device), torch.cuda.Stream(device=device), torch.cuda.Stream(device=device))
+            self.__dict__['_ia_streams'] = st
+        return st[1], st[2]
+
     def _delta(self, y_hat, image):
         """y_hat - image[:, :3] as fp32 NHWC [T,H,W,3] (uvnet.py:181)."""
         neg = self.__dict__.get('_ia_neg1')
@@ -546,9 +553,21 @@ class inversionNet(nn.Module):
         _, tri_in = rt.enc_prep([_nhwc(x['image'][:, :3].float()), delta], want_split=False, want32=True)
 
         r_list = [None, None] if r_list is None else list(r_list)
-        texture_offsets, r_list[0] = self.unet_encoder.texture_unet(_nchw(x_input).unsqueeze(0), r_list=r_list[0], return_list=True)
+        # The two UNets are independent and made of small, latency-bound launches (few CTAs each): run them side by side on
+        # two streams and join before their results are consumed.
+        cur = torch.cuda.current_stream(x_input.device)
+        s_tex, s_tri = self._side_streams(x_input.device)
+        s_tex.wait_stream(cur)
+        s_tri.wait_stream(cur)
+        with torch.cuda.stream(s_tex):
+            texture_offsets, r_list[0] = self.unet_encoder.texture_unet(_nchw(x_input).unsqueeze(0), r_list=r_list[0], return_list=True)
+        with torch.cuda.stream(s_tri):
+            triplane_feat_offsets, r_list[1] = self.unet_encoder.triplane_unet(_nchw(tri_in).unsqueeze(0), r_list=r_list[1])
+        cur.wait_stream(s_tex)
+        cur.wait_stream(s_tri)
+        for t in list(texture_offsets) + list(r_list[0]) + list(r_list[1]) + list(triplane_feat_offsets.values()):
+            t.record_stream(cur)      # produced on a side stream, consumed (and eventually freed) on the caller's stream
         texture_feats = self._add_offsets(texture_feats, texture_offsets)
-        triplane_feat_offsets, r_list[1] = self.unet_encoder.triplane_unet(_nchw(tri_in).unsqueeze(0), r_list=r_list[1])
         static_feats = G.backbone.synthesis(ws, cond_list=None, return_list=True, feat_conditions=triplane_feat_offsets,
                                             update_emas=False, noise_mode='const')
         updated = {'w': ws, 'texture': texture_feats, 'static': static_feats}
