@@ -144,6 +144,11 @@ typedef struct {
 } ia_conv_params;
 /* Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05.mma, TMEM accumulators, TMA-fed). */
 int ia_conv_tc(const ia_conv_params* p, void* stream);
+/* n (<= 4) launches that share operands, epilogue and emitted tensors and differ only in taps / grid / output parity -- the four
+ * phases of the stride-2 transposed convolution of conv2d_resample.py:114-127 -- executed as ONE persistent launch (the phases
+ * share the ramp/tail and, tiles being interleaved phase-minor, the activation tile in L2).  Falls back to n ia_conv_tc calls
+ * when a sub-problem is too small for the persistent kernel. */
+int ia_conv_tc_phases(const ia_conv_params* p, int32_t n, void* stream);
 /* Same contract on CUDA cores (fp32 FMA over hi+lo); cross-check and bring-up path. */
 int ia_conv_simt(const ia_conv_params* p, void* stream);
 

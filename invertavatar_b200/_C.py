@@ -151,6 +151,7 @@ SIGNATURES = {
     'ia_modsplit': (C.c_int, [C.POINTER(ModsplitParams), C.c_void_p]),
     'ia_pack_conv_weight': (C.c_int, [c_f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_u16p, c_u16p, c_f32p, C.c_void_p]),
     'ia_conv_tc': (C.c_int, [C.POINTER(ConvParams), C.c_void_p]),
+    'ia_conv_tc_phases': (C.c_int, [C.POINTER(ConvParams), C.c_int32, C.c_void_p]),
     'ia_conv_simt': (C.c_int, [C.POINTER(ConvParams), C.c_void_p]),
     'ia_fir_epilogue': (C.c_int, [C.POINTER(FirParams), C.c_void_p]),
     'ia_torgb_finish': (C.c_int, [C.POINTER(TorgbParams), C.c_void_p]),

@@ -383,7 +383,18 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr) {
 
 constexpr int kV2MaxASlots = 6, kV2MaxBSlots = 8;
 
+// One sub-problem of a launch: its taps (grouped by horizontal offset), its grid and where its outputs go.  A plain launch has
+// one; a stride-2 transposed convolution runs its four output-parity phases as four sub-problems of ONE persistent launch, so the
+// phases share the launch, the ramp/tail and -- tiles being interleaved phase-minor -- the activation tile in L2.
+struct Tc2Phase {
+    int GH, GW, py, px, tiles_x, tiles_y, ngroups;
+    int g_dx[4], g_first[5];
+    int t_dyoff[9], t_wtap[9];
+};
+
 struct Tc2Params {
+    int nph, S_tx, S_ty;           // sub-problems; common tile grid = the largest sub-problem grid
+    Tc2Phase ph[4];
     int B, GH, GW, TH, tw, tiles_x, tiles_y, m_tiles, n_tiles, total_tiles;
     int Cin_blocks, Cout, Cout_pad, n_tile, acc_stride;
     int ntaps, ngroups;
@@ -579,7 +590,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     const int it_first = CL ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     const int it_step = CL ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     const int it_end = CL ? p.total_pairs : p.total_tiles;
-    auto decode = [&](int it, int& n_idx, int& m, bool& null_tile) {
+    // -> N tile, image, tile origin, sub-problem; `null_tile` (cluster padding) computes but stores nothing, `skip` (a tile
+    // position outside this sub-problem's grid) is not executed at all -- every role takes the same decision.
+    auto decode = [&](int it, int& n_idx, int& img, int& txi, int& tyi, int& pi, bool& null_tile, bool& skip) {
+        int m;
         if (CL) {
             const int lin = 2 * it + (int)crank;
             n_idx = lin / p.m_tiles_p;
@@ -591,6 +605,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
             m = it - n_idx * p.m_tiles;
             null_tile = false;
         }
+        pi = m % p.nph; m /= p.nph;
+        pi = (pi + m) % p.nph;     // rotate the sub-problem with the tile position: with a grid stride that is a multiple of nph
+                                   // a CTA would otherwise always draw the same sub-problem (the 4-tap phase costs 4x the 1-tap one)
+        txi = m % p.S_tx; m /= p.S_tx;
+        tyi = m % p.S_ty; img = m / p.S_ty;
+        skip = txi >= p.ph[pi].tiles_x || tyi >= p.ph[pi].tiles_y;
     };
 
     if (warp == 0) {
@@ -598,26 +618,26 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         if (lane == 0) {
             uint32_t a_it = 0, b_it = 0;
             for (int it = it_first; it < it_end; it += it_step) {
-                int n_idx, m; bool null_tile;
-                decode(it, n_idx, m, null_tile);
-                const int txi = m % p.tiles_x; m /= p.tiles_x;
-                const int tyi = m % p.tiles_y; const int img = m / p.tiles_y;
+                int n_idx, img, txi, tyi, pi; bool null_tile, skip;
+                decode(it, n_idx, img, txi, tyi, pi, null_tile, skip);
+                if (skip) continue;
+                const Tc2Phase& ph = p.ph[pi];
                 const int x0 = txi * p.tw, y0 = tyi * p.TH, col0 = n_idx * p.n_tile;
                 for (int kc = 0; kc < p.Cin_blocks; ++kc) {
-                    for (int g = 0; g < p.ngroups; ++g) {
+                    for (int g = 0; g < ph.ngroups; ++g) {
                         const int as = (int)(a_it % (uint32_t)p.a_slots);
                         mbar_wait(a_empty(as), ((a_it / (uint32_t)p.a_slots) & 1u) ^ 1u);
                         const uint32_t sa = a_base + (uint32_t)as * a_slot_bytes;
                         mbar_expect_tx(a_full(as), 2u * p.a_tx);
-                        tma_load_4d(sa, &tm_a_hi, a_full(as), kc * BK, x0 + p.g_dx[g], y0 + p.dy_min, img);
-                        tma_load_4d(sa + p.a_bytes, &tm_a_lo, a_full(as), kc * BK, x0 + p.g_dx[g], y0 + p.dy_min, img);
+                        tma_load_4d(sa, &tm_a_hi, a_full(as), kc * BK, x0 + ph.g_dx[g], y0 + p.dy_min, img);
+                        tma_load_4d(sa + p.a_bytes, &tm_a_lo, a_full(as), kc * BK, x0 + ph.g_dx[g], y0 + p.dy_min, img);
                         ++a_it;
-                        for (int t = p.g_first[g]; t < p.g_first[g + 1]; ++t) {
+                        for (int t = ph.g_first[g]; t < ph.g_first[g + 1]; ++t) {
                             const int bs = (int)(b_it % (uint32_t)p.b_slots);
                             mbar_wait(b_empty(bs), ((b_it / (uint32_t)p.b_slots) & 1u) ^ 1u);
                             const uint32_t sb = b_base + (uint32_t)bs * b_slot_bytes;
                             mbar_expect_tx(b_full(bs), 2u * p.b_tx);
-                            const int wrow = ((img / p.ipg) * p.n_taps_total + p.t_wtap[t]) * p.Cout_pad + col0;
+                            const int wrow = ((img / p.ipg) * p.n_taps_total + ph.t_wtap[t]) * p.Cout_pad + col0;
                             if (CL) {     // both CTAs armed their own barrier above; rank 0 fetches the tile for both
                                 if (crank == 0) {
                                     tma_load_2d_mc(sb, &tm_w_hi, b_full(bs), kc * BK, wrow, (uint16_t)3);
@@ -638,7 +658,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         if (lane == 0) {
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
             uint32_t a_it = 0, b_it = 0, j = 0;
-            for (int it = it_first; it < it_end; it += it_step, ++j) {
+            int mma_pi = 0;
+            for (int it = it_first; it < it_end; it += it_step) {
+                {
+                    int n_idx, img, txi, tyi, pi_; bool null_tile, skip;
+                    decode(it, n_idx, img, txi, tyi, pi_, null_tile, skip);
+                    if (skip) continue;
+                    mma_pi = pi_;
+                }
+                const Tc2Phase& ph = p.ph[mma_pi];
                 const uint32_t acc = j & 1u;
                 mbar_wait(t_empty(acc), ((j >> 1) & 1u) ^ 1u);
                 tc_fence_after();
@@ -646,11 +674,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                 const uint32_t d1 = tmem_base + (acc * 2u + 1u) * (uint32_t)p.acc_stride;
                 bool first = true;
                 for (int kc = 0; kc < p.Cin_blocks; ++kc) {
-                    for (int g = 0; g < p.ngroups; ++g) {
+                    for (int g = 0; g < ph.ngroups; ++g) {
                         const int as = (int)(a_it % (uint32_t)p.a_slots);
                         mbar_wait(a_full(as), (a_it / (uint32_t)p.a_slots) & 1u);
                         const uint32_t sa = a_base + (uint32_t)as * a_slot_bytes;
-                        for (int t = p.g_first[g]; t < p.g_first[g + 1]; ++t) {
+                        for (int t = ph.g_first[g]; t < ph.g_first[g + 1]; ++t) {
                             const int bs = (int)(b_it % (uint32_t)p.b_slots);
                             mbar_wait(b_full(bs), (b_it / (uint32_t)p.b_slots) & 1u);
                             tc_fence_after();
@@ -658,8 +686,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                             const uint64_t b_hi = make_kmajor_desc<BK>(sb);
                             const uint64_t b_lo = make_kmajor_desc<BK>(sb + p.b_bytes);
                             const uint32_t row_bytes = (uint32_t)BK * 2u;
-                            const uint32_t off0 = (uint32_t)(p.t_dyoff[t] * p.tw) * row_bytes;
-                            const uint32_t off1 = (uint32_t)((th_half + p.t_dyoff[t]) * p.tw) * row_bytes;
+                            const uint32_t off0 = (uint32_t)(ph.t_dyoff[t] * p.tw) * row_bytes;
+                            const uint32_t off1 = (uint32_t)((th_half + ph.t_dyoff[t]) * p.tw) * row_bytes;
                             const uint64_t a0_hi = make_kmajor_desc<BK>(sa + off0), a0_lo = make_kmajor_desc<BK>(sa + p.a_bytes + off0);
                             const uint64_t a1_hi = make_kmajor_desc<BK>(sa + off1), a1_lo = make_kmajor_desc<BK>(sa + p.a_bytes + off1);
 #pragma unroll
@@ -682,6 +710,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                     }
                 }
                 umma_commit(t_full(acc));
+                ++j;
             }
         }
     } else {
@@ -694,12 +723,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         float* tsm = reinterpret_cast<float*>(smem_raw + (epi_base - smem_u32(smem_raw))) + (warp - 2) * (32 * kTsmLd);
         const int tw_shift = p.tw == 8 ? 3 : (p.tw == 16 ? 4 : 5);
         uint32_t j = 0;
-        for (int it = it_first; it < it_end; it += it_step, ++j) {
+        for (int it = it_first; it < it_end; it += it_step) {
+            int n_idx, img, txi, tyi, pi; bool null_tile, skip;
+            decode(it, n_idx, img, txi, tyi, pi, null_tile, skip);
+            if (skip) continue;
+            const Tc2Phase& ph = p.ph[pi];
             const uint32_t acc = j & 1u;
-            int n_idx, m; bool null_tile;
-            decode(it, n_idx, m, null_tile);
-            const int txi = m % p.tiles_x; m /= p.tiles_x;
-            const int tyi = m % p.tiles_y; const int img = m / p.tiles_y;
             const int x0 = txi * p.tw, y0 = tyi * p.TH, col0 = n_idx * p.n_tile;
             mbar_wait(t_full(acc), (j >> 1) & 1u);
             tc_fence_after();
@@ -708,8 +737,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                 const int w_l = row & (p.tw - 1);
                 const int h_l = (row >> tw_shift) + half * th_half;
                 const int gy = y0 + h_l, gx = x0 + w_l;
-                const int oy = gy * p.sy + p.py, ox = gx * p.sx + p.px;
-                const bool valid = !null_tile && gy < p.GH && gx < p.GW && oy < p.OH && ox < p.OW;
+                const int oy = gy * p.sy + ph.py, ox = gx * p.sx + ph.px;
+                const bool valid = !null_tile && gy < ph.GH && gx < ph.GW && oy < p.OH && ox < p.OW;
                 const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
                 const int my_pix = oy * p.OW + ox;                     // pixel index inside the image (fits in int)
                 float my_nz = 0.f;
@@ -775,6 +804,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
             tc_fence_before();
             __syncwarp();
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(t_empty(acc)) : "memory");
+            ++j;
         }
     }
 
@@ -820,50 +850,72 @@ int make_weight_map2(CUtensorMap* m, const void* ptr, int rows, int Cin_pad, int
 int g_sm_count = 0;
 
 template <int BK>
-int launch_v2(const ia_conv_params* p, void* stream) {
+int launch_v2(const ia_conv_params* const* ps, int nph, void* stream) {
+    const ia_conv_params* p = ps[0];       // operands, epilogue and emitted tensors are shared by all sub-problems
     Tc2Params t;
     memset(&t, 0, sizeof(t));
-    t.B = p->B; t.GH = p->GH; t.GW = p->GW;
+    t.B = p->B;
+    int GHm = 0, GWm = 0;
+    for (int i = 0; i < nph; ++i) { GHm = ps[i]->GH > GHm ? ps[i]->GH : GHm; GWm = ps[i]->GW > GWm ? ps[i]->GW : GWm; }
+    t.GH = GHm; t.GW = GWm;
     // tile geometry: 256 pixels as TH x tw with tw in {8,16,32}; fewest tiles wins, ties -> taller tiles (smaller halo share)
     {
         int64_t best = -1;
         const int cand[3][2] = {{32, 8}, {16, 16}, {8, 32}};
         for (int i = 0; i < 3; ++i) {
-            int64_t tiles = cdiv(p->GH, cand[i][0]) * cdiv(p->GW, cand[i][1]);
+            int64_t tiles = 0;
+            for (int q = 0; q < nph; ++q) tiles += cdiv(ps[q]->GH, cand[i][0]) * cdiv(ps[q]->GW, cand[i][1]);
             if (best < 0 || tiles < best) { best = tiles; t.TH = cand[i][0]; t.tw = cand[i][1]; }
         }
     }
-    t.tiles_x = (int)cdiv(p->GW, t.tw); t.tiles_y = (int)cdiv(p->GH, t.TH);
-    t.m_tiles = t.tiles_x * t.tiles_y * p->B;
+    t.nph = nph;
+    t.S_tx = (int)cdiv(GWm, t.tw); t.S_ty = (int)cdiv(GHm, t.TH);
+    t.tiles_x = t.S_tx; t.tiles_y = t.S_ty;
+    t.m_tiles = t.S_tx * t.S_ty * nph * p->B;          // schedule entries (positions outside a sub-problem's grid are skipped)
+    int64_t real_tiles = 0;
+    for (int q = 0; q < nph; ++q) real_tiles += cdiv(ps[q]->GH, t.TH) * cdiv(ps[q]->GW, t.tw) * p->B;
     t.Cin_blocks = p->Cin_pad / BK;
     t.Cout = p->Cout; t.Cout_pad = p->Cout_pad;
     int n_tile = 32;
     for (int cand = 128; cand >= 32; cand -= 32) {
         if (p->Cout_pad % cand) continue;
         n_tile = cand;
-        if ((int64_t)t.m_tiles * (p->Cout_pad / cand) >= 120) break;
+        if (real_tiles * (p->Cout_pad / cand) >= 120) break;
     }
     t.n_tile = n_tile; t.acc_stride = 128;
     t.n_tiles = p->Cout_pad / n_tile;
     t.total_tiles = t.m_tiles * t.n_tiles;
-    // group the taps by dx
+    // taps of every sub-problem grouped by dx; one activation box (common dy range) serves all of them
     int dy_min = 1 << 30, dy_max = -(1 << 30);
-    for (int i = 0; i < p->ntaps; ++i) { dy_min = p->dy[i] < dy_min ? p->dy[i] : dy_min; dy_max = p->dy[i] > dy_max ? p->dy[i] : dy_max; }
+    for (int q = 0; q < nph; ++q)
+        for (int i = 0; i < ps[q]->ntaps; ++i) {
+            dy_min = ps[q]->dy[i] < dy_min ? ps[q]->dy[i] : dy_min;
+            dy_max = ps[q]->dy[i] > dy_max ? ps[q]->dy[i] : dy_max;
+        }
     t.dy_min = dy_min;
     const int halo = dy_max - dy_min;
-    t.ntaps = p->ntaps; t.ngroups = 0;
-    int nt = 0;
-    bool used[9] = {false, false, false, false, false, false, false, false, false};
-    for (int i = 0; i < p->ntaps; ++i) {
-        if (used[i]) continue;
-        IA_CHECK(t.ngroups < 4, "ia_conv_tc(v2): more than 4 distinct horizontal tap offsets");
-        t.g_dx[t.ngroups] = p->dx[i];
-        t.g_first[t.ngroups] = nt;
-        for (int k = i; k < p->ntaps; ++k)
-            if (!used[k] && p->dx[k] == p->dx[i]) { used[k] = true; t.t_dyoff[nt] = p->dy[k] - dy_min; t.t_wtap[nt] = p->wtap[k]; ++nt; }
-        ++t.ngroups;
+    int taps_sum = 0, groups_sum = 0;
+    for (int q = 0; q < nph; ++q) {
+        const ia_conv_params* pq = ps[q];
+        Tc2Phase& ph = t.ph[q];
+        ph.GH = pq->GH; ph.GW = pq->GW; ph.py = pq->py; ph.px = pq->px;
+        ph.tiles_x = (int)cdiv(pq->GW, t.tw); ph.tiles_y = (int)cdiv(pq->GH, t.TH);
+        ph.ngroups = 0;
+        int nt = 0;
+        bool used[9] = {false, false, false, false, false, false, false, false, false};
+        for (int i = 0; i < pq->ntaps; ++i) {
+            if (used[i]) continue;
+            IA_CHECK(ph.ngroups < 4, "ia_conv_tc(v2): more than 4 distinct horizontal tap offsets");
+            ph.g_dx[ph.ngroups] = pq->dx[i];
+            ph.g_first[ph.ngroups] = nt;
+            for (int k = i; k < pq->ntaps; ++k)
+                if (!used[k] && pq->dx[k] == pq->dx[i]) { used[k] = true; ph.t_dyoff[nt] = pq->dy[k] - dy_min; ph.t_wtap[nt] = pq->wtap[k]; ++nt; }
+            ++ph.ngroups;
+        }
+        ph.g_first[ph.ngroups] = nt;
+        taps_sum += pq->ntaps; groups_sum += ph.ngroups;
     }
-    t.g_first[t.ngroups] = nt;
+    t.ntaps = taps_sum; t.ngroups = groups_sum;      // (ring-depth balance below; the kernel reads the per-phase tables)
     const int a_rows = (t.TH + halo) * t.tw;
     t.a_tx = (uint32_t)a_rows * BK * 2u;
     t.a_bytes = (t.a_tx + 1023u) & ~1023u;
@@ -940,7 +992,7 @@ int launch_v2(const ia_conv_params* p, void* stream) {
     t.m_tiles_p = (t.m_tiles + 1) & ~1;
     t.total_pairs = (t.m_tiles_p * t.n_tiles) / 2;
     const int sm_even = g_sm_count & ~1;
-    if (use_cluster && p->groups <= 1 && t.total_pairs >= sm_even / 2) {
+    if (use_cluster && nph == 1 && p->groups <= 1 && t.total_pairs >= sm_even / 2) {
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
         cfg.gridDim = dim3((unsigned)sm_even, 1, 1);
@@ -951,14 +1003,15 @@ int launch_v2(const ia_conv_params* p, void* stream) {
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        ia::prof_begin(ia::prof_detail_name("ia_conv_tc", p->ntaps, p->GH, p->GW, p->Cin_pad, p->Cout), as_stream(stream));
+        ia::prof_begin(ia::prof_detail_name("ia_conv_tc", taps_sum, GHm, GWm, p->Cin_pad, p->Cout), as_stream(stream));
         cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tc2_kernel<BK, true>, ma_hi, ma_lo, mw_hi, mw_lo, t);
         IA_CHECK(le == cudaSuccess, "ia_conv_tc(v2): cluster launch failed: %s", cudaGetErrorString(le));
         IA_LAUNCH_CHECK("ia_conv_tc");
         return 0;
     }
-    const int grid = t.total_tiles < g_sm_count ? t.total_tiles : g_sm_count;
-    ia::prof_begin(ia::prof_detail_name("ia_conv_tc", p->ntaps, p->GH, p->GW, p->Cin_pad, p->Cout), as_stream(stream));
+    const int64_t real_total = real_tiles * t.n_tiles;
+    const int grid = real_total < g_sm_count ? (int)real_total : g_sm_count;
+    ia::prof_begin(ia::prof_detail_name("ia_conv_tc", taps_sum, GHm, GWm, p->Cin_pad, p->Cout), as_stream(stream));
     conv_tc2_kernel<BK, false><<<grid, kThreads2, smem, as_stream(stream)>>>(ma_hi, ma_lo, mw_hi, mw_lo, t);
     IA_LAUNCH_CHECK("ia_conv_tc");
     return 0;
@@ -982,7 +1035,7 @@ extern "C" int ia_conv_tc(const ia_conv_params* p, void* stream) {
         if (mode_few < 0) { const char* e = getenv("IA_CONV_TC_FEW"); mode_few = e ? atoi(e) : 32; }
         if (mode != 0 && p->GH * p->GW >= 128 && p->GW >= 8) {
             const int bk = (p->ntaps <= 4) ? mode_few : mode;
-            return bk == 64 ? launch_v2<64>(p, stream) : launch_v2<32>(p, stream);
+            return bk == 64 ? launch_v2<64>(&p, 1, stream) : launch_v2<32>(&p, 1, stream);
         }
     }
     TcParams t;
@@ -1037,4 +1090,43 @@ extern "C" int ia_conv_tc(const ia_conv_params* p, void* stream) {
     conv_tc_kernel<<<grid, kThreads, smem, as_stream(stream)>>>(ma_hi, ma_lo, mw_hi, mw_lo, t);
     IA_LAUNCH_CHECK("ia_conv_tc");
     return 0;
+}
+
+
+// n launches that share operands, epilogue and emitted tensors and differ only in taps / grid / output parity (the four phases
+// of a stride-2 transposed convolution, conv2d_resample.py:114-127) executed as ONE persistent launch.
+extern "C" int ia_conv_tc_phases(const ia_conv_params* p, int32_t n, void* stream) {
+    IA_CHECK(p && n >= 1 && n <= 4, "ia_conv_tc_phases: 1..4 sub-problems");
+    bool merged = n > 1;
+    {
+        static int on = -1;
+        if (on < 0) { const char* e = getenv("IA_CONV_MERGE_PHASES"); on = e ? atoi(e) : 1; }
+        if (!on) merged = false;
+        static int mode = -1;
+        if (mode < 0) { const char* e = getenv("IA_CONV_TC"); mode = e ? atoi(e) : 32; }
+        if (mode == 0) merged = false;
+    }
+    for (int i = 0; i < n && merged; ++i) {
+        if (int rc = ia_conv_validate(&p[i], "ia_conv_tc_phases")) return rc;
+        const ia_conv_params& a = p[0]; const ia_conv_params& b = p[i];
+        // every sub-problem must be eligible for the persistent kernel and share everything but its geometry
+        if (!(b.GH * b.GW >= 128 && b.GW >= 8)) merged = false;
+        if (a.a_hi != b.a_hi || a.a_lo != b.a_lo || a.w_hi != b.w_hi || a.w_lo != b.w_lo || a.B != b.B || a.H != b.H || a.W != b.W ||
+            a.Cin_pad != b.Cin_pad || a.Cout != b.Cout || a.Cout_pad != b.Cout_pad || a.n_taps_total != b.n_taps_total || a.OH != b.OH ||
+            a.OW != b.OW || a.sy != b.sy || a.sx != b.sx || a.mode != b.mode || a.dcoef != b.dcoef || a.noise != b.noise || a.bias != b.bias ||
+            a.act != b.act || a.gain != b.gain || a.clamp != b.clamp || a.emit.out32 != b.emit.out32 || a.emit.hi1 != b.emit.hi1 ||
+            a.emit.hi2 != b.emit.hi2 || a.groups != b.groups || a.imgs_per_group != b.imgs_per_group)
+            merged = false;
+    }
+    if (!merged) {
+        for (int i = 0; i < n; ++i)
+            if (int rc = ia_conv_tc(&p[i], stream)) return rc;
+        return 0;
+    }
+    IA_CHECK((reinterpret_cast<uintptr_t>(p->a_hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->a_lo) & 15) == 0 &&
+             (reinterpret_cast<uintptr_t>(p->w_hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->w_lo) & 15) == 0,
+             "ia_conv_tc_phases: operands must be 16-byte aligned");
+    const ia_conv_params* ps[4];
+    for (int i = 0; i < n; ++i) ps[i] = &p[i];
+    return launch_v2<32>(ps, n, stream);
 }

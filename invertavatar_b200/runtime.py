@@ -448,9 +448,12 @@ def conv_transpose_up2_raw(hi, lo, pack, Cin_pad, raw, impl=None, group=None):
     B, H, W, _ = hi.shape
     assert pack.kh == 3 and pack.kw == 3
     rowtaps = {0: [(0, 0), (2, -1)], 1: [(1, 0)]}
+    phases = (_C.ConvParams * 4)()
+    k = 0
     for py in (0, 1):
         for px in (0, 1):
-            p = _C.ConvParams()
+            p = phases[k]
+            k += 1
             p.a_hi, p.a_lo, p.B, p.H, p.W, p.Cin_pad = _p(hi), _p(lo), B, H, W, Cin_pad
             p.w_hi, p.w_lo, p.Cout, p.Cout_pad, p.n_taps_total = _p(pack.w_hi), _p(pack.w_lo), pack.Cout, pack.Cout_pad, pack.taps
             p.GH, p.GW = H + 1 - py, W + 1 - px
@@ -465,7 +468,11 @@ def conv_transpose_up2_raw(hi, lo, pack, Cin_pad, raw, impl=None, group=None):
             p.act, p.alpha, p.gain, p.clamp = 1, 0.0, 1.0, -1.0
             p.emit = _emit(raw)
             _set_group(p, group)
-            _conv_call(p, st, impl)
+    if (impl or _conv_impl) == 'tc':
+        _C.check(_C.lib().ia_conv_tc_phases(phases, 4, st), 'ia_conv_tc_phases')     # one persistent launch for the four phases
+    else:
+        for k in range(4):
+            _conv_call(phases[k], st, impl)
 
 
 _FIR_CACHE = {}
