@@ -295,10 +295,13 @@ def run_b200(args):
             # same steps again with every launch bracketed by CUDA events on the launching stream (every rank runs them so
             # that the image all-gather stays matched; rank 0 reports)
             barrier()
+            from invertavatar_b200 import triplane as _tp
+            _tp.set_backbone_streams(False)      # per-kernel durations are taken with one kernel at a time on the device
             rt.profile_begin()
             for _ in range(args.steps):
                 step_resident()
             rep = rt.profile_report()
+            _tp.set_backbone_streams(None)
             barrier()
         if rank == 0 and not args.no_roofline:
             conv = rep.get('ia_conv_tc', {'ms': 0.0, 'launches': 0})

@@ -501,11 +501,7 @@ class inversionNet(nn.Module):
         return self.encoder.run_nhwc(xn, w_offset=self.latent_avg.reshape(-1))
 
     def _side_streams(self, device):
-        st = self.__dict__.get('_ia_streams')
-        if st is None or st[0] != str(device):
-            st = (str(device), torch.cuda.Stream(device=device), torch.cuda.Stream(device=device))
-            self.__dict__['_ia_streams'] = st
-        return st[1], st[2]
+        return rt.side_streams(device)
 
     def _delta(self, y_hat, image):
         """y_hat - image[:, :3] as fp32 NHWC [T,H,W,3] (uvnet.py:181)."""

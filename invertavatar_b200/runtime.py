@@ -958,3 +958,16 @@ def layout_grid_u8(img, grid_w=None, grid_h=1):
     _C.check(_C.lib().ia_layout_grid_u8(_p(img), img.stride(0), img.stride(1), img.stride(2), img.stride(3), grid_h, grid_w, Cc, H, W,
                                         _p(out), st), 'ia_layout_grid_u8')
     return out
+
+
+_SIDE_STREAMS = {}
+
+
+def side_streams(device):
+    """Two auxiliary CUDA streams per device (process-wide; kept off the modules so that they stay deep-copyable/picklable)."""
+    key = str(torch.device(device))
+    st = _SIDE_STREAMS.get(key)
+    if st is None:
+        st = (torch.cuda.Stream(device=device), torch.cuda.Stream(device=device))
+        _SIDE_STREAMS[key] = st
+    return st

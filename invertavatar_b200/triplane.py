@@ -29,6 +29,23 @@ def _grouped_prefix_enabled():
     return os.environ.get('IA_GROUPED_PREFIX', '1') != '0'
 
 
+_backbone_streams = None
+
+
+def set_backbone_streams(enabled):
+    """Issue the texture and static backbones on two streams (True, default) or one after the other on the caller's stream
+    (False; used when kernels are timed one by one).  None restores the IA_BACKBONE_STREAMS environment default."""
+    global _backbone_streams
+    _backbone_streams = enabled
+
+
+def _backbone_streams_enabled():
+    if _backbone_streams is not None:
+        return bool(_backbone_streams)
+    import os
+    return os.environ.get('IA_BACKBONE_STREAMS', '1') != '0'
+
+
 def _construct(class_name, **kwargs):
     """dnnlib.util.construct_class_by_name for the super-resolution module (triplane_v20.py:56-58)."""
     cls = _KNOWN_SR.get(class_name)
@@ -83,6 +100,9 @@ class TriPlaneGenerator(torch.nn.Module):
         self.neural_rendering_resolution = 128
         self.rendering_kwargs = rendering_kwargs
         self.fill_mouth = True
+
+    def _side_streams(self, device):
+        return rt.side_streams(device)
 
     # ------------------------------------------------------------------------------------------
     def mapping(self, z, c, truncation_psi=1, truncation_cutoff=None, update_emas=False):
@@ -197,8 +217,25 @@ class TriPlaneGenerator(torch.nn.Module):
         pre = [None, None, None]
         if _grouped_prefix_enabled() and sg.can_group_prefix(nets):
             pre = sg.synthesis_prefix_grouped(nets, ws, noise_mode=noise_kwargs.get('noise_mode', 'random'))
-        texture_feats = self.texture_backbone.synthesis(ws, cond_list=None, return_list=True, prefix=pre[0], **noise_kwargs)
-        static_feats = self.backbone.synthesis(ws, cond_list=None, return_list=True, prefix=pre[1], **noise_kwargs)
+        if _backbone_streams_enabled() and ws.is_cuda:
+            # The texture and static backbones are independent: issue them on two streams so that the HBM-bound kernels of one
+            # (FIR epilogues, ToRGB tails, operand preparation: no shared memory, few registers) run on the SMs next to the
+            # tensor-core convolutions of the other; join before the rasterizer consumes both.
+            cur = torch.cuda.current_stream(ws.device)
+            s_a, s_b = self._side_streams(ws.device)
+            s_a.wait_stream(cur)
+            s_b.wait_stream(cur)
+            with torch.cuda.stream(s_a):
+                texture_feats = self.texture_backbone.synthesis(ws, cond_list=None, return_list=True, prefix=pre[0], **noise_kwargs)
+            with torch.cuda.stream(s_b):
+                static_feats = self.backbone.synthesis(ws, cond_list=None, return_list=True, prefix=pre[1], **noise_kwargs)
+            cur.wait_stream(s_a)
+            cur.wait_stream(s_b)
+            for t in list(texture_feats) + list(static_feats):
+                t.record_stream(cur)
+        else:
+            texture_feats = self.texture_backbone.synthesis(ws, cond_list=None, return_list=True, prefix=pre[0], **noise_kwargs)
+            static_feats = self.backbone.synthesis(ws, cond_list=None, return_list=True, prefix=pre[1], **noise_kwargs)
         out = self._stitch_render_sr(ws, c, mesh_condition, texture_feats, static_feats, neural_rendering_resolution,
                                      evaluation, synthesis_kwargs, face_prefix=pre[2])
         if return_featmap:
