@@ -1,0 +1,55 @@
+"""Whole-frame CUDA graphs for the per-frame drivers of the inference scripts.
+
+``reenact_avatar_next3d.py:214`` and ``eval_seq.py:212`` call ``G.synthesis`` / ``G.synthesis_withTexture`` once per video
+frame at batch 1; at that size a frame is ~170 short launches and the host (Python + ctypes) issues them more slowly than the
+GPU runs them.  ``GraphedSynthesis`` captures one call into a CUDA graph (every kernel of libinvertavatar_b200.so is launched
+on the capturing stream with static buffers; tensor maps are encoded on the host at capture time) and replays it per frame:
+
+    gs = GraphedSynthesis(G, ws, c, uv)                  # or (..., texture_feats=..., static_feats=...) for the eval_seq driver
+    img = gs(c_t, uv_t)['image']                         # per frame: two small copies + one graph launch
+
+The numbers are those of the eager call (same kernels, same order).  Inputs keep the shapes they had at capture."""
+import torch
+
+
+class GraphedSynthesis:
+    def __init__(self, G, ws, c, uvcoords_image, texture_feats=None, static_feats=None, neural_rendering_resolution=None,
+                 evaluation=True, warmup=3):
+        assert ws.is_cuda, 'GraphedSynthesis needs CUDA tensors'
+        self.G = G
+        self.ws = ws.detach().clone()
+        self.c = c.detach().clone()
+        self.uv = uvcoords_image.detach().clone().float()
+        self.tex = None if texture_feats is None else [t.detach().clone() for t in texture_feats]
+        self.sta = None if static_feats is None else [t.detach().clone() for t in static_feats]
+        self.res = neural_rendering_resolution
+        self.evaluation = evaluation
+        side = torch.cuda.Stream(device=ws.device)
+        side.wait_stream(torch.cuda.current_stream(ws.device))
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(warmup):          # builds every cache (packed weights, style plans, tap tables) outside the capture
+                self._call()
+        torch.cuda.current_stream(ws.device).wait_stream(side)
+        torch.cuda.synchronize(ws.device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            self.out = self._call()
+
+    def _call(self):
+        mc = {'uvcoords_image': self.uv}
+        if self.tex is not None:
+            return self.G.synthesis_withTexture(self.ws, self.tex, self.c, mc, static_feats=self.sta, neural_rendering_resolution=self.res,
+                                                noise_mode='const', evaluation=self.evaluation)
+        return self.G.synthesis(self.ws, self.c, mc, neural_rendering_resolution=self.res, noise_mode='const', evaluation=self.evaluation)
+
+    def __call__(self, c=None, uvcoords_image=None, ws=None):
+        """Replay with new camera / mesh condition / latent (any of them may be omitted); returns the dict of the captured call
+        (static output tensors: copy what must outlive the next replay)."""
+        if ws is not None:
+            self.ws.copy_(ws, non_blocking=True)
+        if c is not None:
+            self.c.copy_(c, non_blocking=True)
+        if uvcoords_image is not None:
+            self.uv.copy_(uvcoords_image, non_blocking=True)
+        self.graph.replay()
+        return self.out

@@ -94,10 +94,13 @@ class ImportanceRenderer_bsMotion(torch.nn.Module):
         self.plane_axes = generate_planes()
         self.depth_jitter = None     # [B, rays, Dc(,1)] U[0,1); consumed by the next forward
         self.importance_u = None     # [B*rays, Df] U[0,1); consumed by the next forward when evaluation=False
+        self.fixed_jitter = None     # [B, rays, Dc] used by every forward while set (depth_jitter takes precedence)
 
     def _draws(self, B, rays, Dc, Df, evaluation, device):
         jit, u = self.depth_jitter, self.importance_u
         self.depth_jitter = self.importance_u = None
+        if jit is None:
+            jit = getattr(self, 'fixed_jitter', None)     # persistent (not consumed) jitter tensor: reproducible video / tests
         if jit is None:
             jit = torch.rand((B, rays, Dc), device=device)
         if evaluation or Df == 0:

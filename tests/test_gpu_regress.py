@@ -41,3 +41,24 @@ def test_grouped_prefix_matches_sequential(monkeypatch):
         assert d <= 2e-5 * max(1.0, float(outs['0'][k].abs().max())), (k, d)
     for a, b in zip(outs['1']['texture'], outs['0']['texture']):
         assert float((a - b).abs().max()) <= 2e-5 * max(1.0, float(b.abs().max()))
+
+
+def test_graphed_synthesis_matches_eager():
+    """Whole-frame CUDA graph (invertavatar_b200.graphs) of the batch-1 per-frame call == the eager call, also after the
+    camera and mesh condition are swapped between replays."""
+    import copy
+    from invertavatar_b200.graphs import GraphedSynthesis
+    G = copy.deepcopy(build_generator(16, 16)).to('cuda')
+    z, cond = synth.latents(1).cuda(), synth.frontal_camera(1).cuda()
+    cams, uvs = synth.cameras(3).cuda(), synth.uvcoords_image(3).cuda()
+    with torch.no_grad():
+        ws = G.mapping(z, cond, truncation_psi=0.7, truncation_cutoff=14)
+        jit = synth.depth_jitter(1, 64 * 64, 16).cuda()
+        G.renderer.fixed_jitter = jit            # deterministic depth jitter for the comparison (see rendering.py)
+        gs = GraphedSynthesis(G, ws, cams[:1], uvs[:1], neural_rendering_resolution=64)
+        for i in (1, 2, 0):
+            got = gs(cams[i:i + 1], uvs[i:i + 1])['image'].clone()
+            want = G.synthesis(ws, cams[i:i + 1], {'uvcoords_image': uvs[i:i + 1]}, neural_rendering_resolution=64, noise_mode='const',
+                               evaluation=True)['image']
+            assert float((got - want).abs().max()) <= 1e-6, i
+        G.renderer.fixed_jitter = None
