@@ -411,6 +411,10 @@ struct Tc2Params {
     ia_emit emit;
     int groups, ipg, n_taps_total; long long noise_gstride;   // grouped launch (see ia_conv_params)
     int m_tiles_p, total_pairs;    // cluster variant: m_tiles rounded up to even; (m_tiles_p * n_tiles) / 2 tile pairs
+    // balanced schedule (plain variant): tiles ordered (image chunk, sub-problem, N tile, image, tile) with the sub-problems by
+    // descending tap count, only real tiles enumerated -- see decode()
+    int ic, chunk_tiles;           // images per chunk; schedule entries of one chunk = ic * n_tiles * ph_cum[nph]
+    int ph_cum[5];                 // ph_cum[q] = sum_{k<q} tiles_x[k] * tiles_y[k]
     int epi_vec4;                  // 1: Cout % 4 == 0 and every output pointer / pitch is 16-byte friendly -> epilogue_chunk_v4
 };
 
@@ -593,24 +597,35 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     // -> N tile, image, tile origin, sub-problem; `null_tile` (cluster padding) computes but stores nothing, `skip` (a tile
     // position outside this sub-problem's grid) is not executed at all -- every role takes the same decision.
     auto decode = [&](int it, int& n_idx, int& img, int& txi, int& tyi, int& pi, bool& null_tile, bool& skip) {
-        int m;
         if (CL) {
             const int lin = 2 * it + (int)crank;
             n_idx = lin / p.m_tiles_p;
-            m = lin - n_idx * p.m_tiles_p;
+            int m = lin - n_idx * p.m_tiles_p;
             null_tile = m >= p.m_tiles;
             if (null_tile) m = p.m_tiles - 1;
-        } else {
-            n_idx = it / p.m_tiles;
-            m = it - n_idx * p.m_tiles;
-            null_tile = false;
+            pi = 0;                                   // (the cluster variant is launched for single sub-problems only)
+            txi = m % p.S_tx; m /= p.S_tx;
+            tyi = m % p.S_ty; img = m / p.S_ty;
+            skip = false;
+            return;
         }
-        pi = m % p.nph; m /= p.nph;
-        pi = (pi + m) % p.nph;     // rotate the sub-problem with the tile position: with a grid stride that is a multiple of nph
-                                   // a CTA would otherwise always draw the same sub-problem (the 4-tap phase costs 4x the 1-tap one)
-        txi = m % p.S_tx; m /= p.S_tx;
-        tyi = m % p.S_ty; img = m / p.S_ty;
-        skip = txi >= p.ph[pi].tiles_x || tyi >= p.ph[pi].tiles_y;
+        // Static round-robin over a cost-sorted tile list: inside a chunk of p.ic images all tiles of the 4-tap sub-problem come
+        // first, then the 2-tap ones, then the 1-tap one, so consecutive schedule entries -- which go to consecutive CTAs -- cost
+        // the same and every CTA draws (within one tile) the same number of tiles of each cost.  (An interleaved order gives a
+        // CTA a random mix: max/mean load 1.2-1.5 on the (H+1)^2 phase grids of the 32^2..128^2 transposed convolutions.)
+        null_tile = false; skip = false;
+        const int ch = it / p.chunk_tiles;
+        int r = it - ch * p.chunk_tiles;
+        const int per_ph = p.ic * p.n_tiles;
+        pi = 0;
+        while (pi + 1 < p.nph && r >= per_ph * p.ph_cum[pi + 1]) ++pi;
+        r -= per_ph * p.ph_cum[pi];
+        const int T = p.ph_cum[pi + 1] - p.ph_cum[pi];
+        const int per_n = p.ic * T;
+        n_idx = r / per_n; r -= n_idx * per_n;
+        const int il = r / T; r -= il * T;
+        img = ch * p.ic + il;
+        tyi = r / p.ph[pi].tiles_x; txi = r - tyi * p.ph[pi].tiles_x;
     };
 
     if (warp == 0) {
@@ -947,6 +962,48 @@ int launch_v2(const ia_conv_params* const* ps, int nph, void* stream) {
         // depth_a = a_slots / ngroups, depth_b = b_slots / ntaps; grow the shallower ring (ties -> activations)
         const bool want_a = (int64_t)t.a_slots * t.ntaps <= (int64_t)t.b_slots * t.ngroups;
         if ((want_a && a_fits) || !b_fits) ++t.a_slots; else ++t.b_slots;
+    }
+    if (g_sm_count == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+        if (g_sm_count <= 0) g_sm_count = 148;
+    }
+    // Balanced schedule of the plain variant (decode()).  Images per chunk: a chunk's activations should stay in L2 while its
+    // sub-problems are swept one after the other (each sweep re-reads them), so only chunk sizes up to ~72 MB of operand bytes
+    // are considered (always at least one image); among those the one with the smallest maximum per-CTA load (in tap units,
+    // evaluated exactly for the round-robin assignment) wins, ties go to the smaller chunk.
+    {
+        t.ph_cum[0] = 0;
+        for (int q = 0; q < nph; ++q) t.ph_cum[q + 1] = t.ph_cum[q] + t.ph[q].tiles_x * t.ph[q].tiles_y;
+        const int64_t total = (int64_t)t.ph_cum[nph] * p->B * t.n_tiles;
+        const int g = total < g_sm_count ? (int)total : g_sm_count;
+        const double img_bytes = (double)p->H * p->W * p->Cin_pad * 4.0;
+        int best_ic = 1; int64_t best_max = -1;
+        for (int ic = 1; ic <= p->B && nph > 1; ++ic) {
+            if (p->B % ic) continue;
+            if (ic > 1 && ic * img_bytes > 72e6) break;
+            int64_t load[1024];
+            const int gg = g < 1024 ? g : 1024;
+            for (int i = 0; i < gg; ++i) load[i] = 0;
+            int64_t pos = 0;
+            for (int ch = 0; ch < p->B / ic; ++ch)
+                for (int q = 0; q < nph; ++q) {
+                    const int64_t L = (int64_t)ic * t.n_tiles * (t.ph_cum[q + 1] - t.ph_cum[q]);
+                    const int64_t full = L / gg, rem = L % gg;
+                    const int64_t w = ps[q]->ntaps;
+                    for (int i = 0; i < gg; ++i) load[i] += full * w;
+                    for (int64_t i = 0; i < rem; ++i) load[(pos + i) % gg] += w;
+                    pos += L;
+                }
+            int64_t mx = 0;
+            for (int i = 0; i < gg; ++i) mx = load[i] > mx ? load[i] : mx;
+            if (best_max < 0 || mx < best_max) { best_max = mx; best_ic = ic; }
+        }
+        if (nph == 1) best_ic = 1;
+        t.ic = best_ic;
+        t.chunk_tiles = t.ic * t.n_tiles * t.ph_cum[nph];
+        t.total_tiles = (int)total;
     }
     t.OH = p->OH; t.OW = p->OW; t.sy = p->sy; t.sx = p->sx; t.py = p->py; t.px = p->px;
     t.mode = p->mode; t.dcoef = p->dcoef; t.noise = p->noise; t.noise_strength = p->noise_strength; t.bias = p->bias;

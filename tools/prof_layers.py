@@ -5,7 +5,8 @@ os.environ.setdefault('IA_PROF_DETAIL', '1')
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from invertavatar_b200 import synth, runtime as rt
-from invertavatar_b200.triplane import TriPlaneGenerator
+from invertavatar_b200.triplane import TriPlaneGenerator, set_backbone_streams
+set_backbone_streams(False)      # one stream: per-launch event times must not overlap
 B = 8
 torch.manual_seed(0)
 G = TriPlaneGenerator(**synth.generator_kwargs(48, 48)).eval().requires_grad_(False)
