@@ -48,6 +48,17 @@ __device__ __forceinline__ void split_bf16(float v, uint16_t& hi, uint16_t& lo) 
     hi = __bfloat16_as_ushort(h);
     lo = __bfloat16_as_ushort(l);
 }
+// Two values at once (packed cvt.rn.bf16x2.f32: same rounding as above, half the instructions): hi / lo hold a in their
+// low and b in their high 16 bits -- the in-memory order of two consecutive channels.
+__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    uint32_t h;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(b), "f"(a));
+    const float ra = a - __uint_as_float(h << 16);
+    const float rb = b - __uint_as_float(h & 0xffff0000u);
+    uint32_t l;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l) : "f"(rb), "f"(ra));
+    hi = h; lo = l;
+}
 __device__ __forceinline__ float bf16_bits_to_float(uint16_t b) { return __uint_as_float(((uint32_t)b) << 16); }
 
 // activation + gain + clamp shared by every epilogue (reference bias_act.cu:27-151 forward path; only the

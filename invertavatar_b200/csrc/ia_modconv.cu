@@ -314,6 +314,133 @@ __global__ void __launch_bounds__(256, 3) fir_epilogue_kernel(ia_fir_params p, i
     }
 }
 
+// Two output columns per thread and two raw rows in flight.  The one-column kernel above keeps a single row of 4 x 16 B per
+// thread in flight, of which only 16 B are unique DRAM bytes (the neighbours re-read the rest through L1): ~12 KB of unique
+// reads in flight per SM, about a third of what the HBM latency-bandwidth product asks for -- it ran at 3.3 TB/s, issue- and
+// latency-bound rather than bandwidth-bound (profiles/r1_fir_full_v3.txt).  Here a thread reads 5 neighbouring float4 per
+// raw row for 2 outputs (2.5 loads per output instead of 4) and prefetches two rows ahead (64 B unique per thread in flight).
+template <int ACT>
+__global__ void __launch_bounds__(256, 2) fir_epilogue_x2_kernel(ia_fir_params p, int cg, int xt, int cchunks) {
+    const int c4 = threadIdx.x % cg;
+    const int xl = threadIdx.x / cg;
+    const int ox = (blockIdx.x * xt + xl) * 2;            // even output column; this thread owns ox and ox + 1 (OW is even)
+    const int oy0 = blockIdx.y * FIR_YT;
+    const int b = blockIdx.z / cchunks;
+    const int c0 = ((blockIdx.z % cchunks) * cg + c4) * 4;
+    if (ox >= p.OW || c0 >= p.C) return;
+    float fy[4], fx[4];
+    {
+        float tot = 0.f, rs[4] = {0.f, 0.f, 0.f, 0.f}, cs[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { const float f = p.fir[i * 4 + j]; rs[i] += f; cs[j] += f; tot += f; }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) { fy[t] = rs[3 - t]; fx[t] = cs[3 - t] / tot; }
+    }
+    const int oy1 = min(oy0 + FIR_YT, p.OH);
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 acc[2][3];                                     // [column][output rows ry-2, ry-1, ry]
+#pragma unroll
+    for (int j = 0; j < 2; ++j) { acc[j][0] = z4; acc[j][1] = z4; acc[j][2] = z4; }
+    const int grp = p.groups > 1 ? b / p.imgs_per_group : 0;
+    float dc[4], bs[4], s1[4], s2[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        dc[k] = p.dcoef ? p.dcoef[(int64_t)b * p.C + c0 + k] : 1.f;
+        bs[k] = p.bias ? p.bias[(int64_t)grp * p.C + c0 + k] : 0.f;
+        s1[k] = (p.emit.hi1 && p.emit.s1) ? p.emit.s1[(int64_t)b * p.C + c0 + k] : 1.f;
+        s2[k] = (p.emit.hi2 && p.emit.s2) ? p.emit.s2[(int64_t)b * p.C + c0 + k] : 1.f;
+    }
+    const float nstr = p.noise ? p.noise_strength[grp] : 0.f;
+    const float* nptr = p.noise ? p.noise + (int64_t)grp * p.noise_gstride + (int64_t)b * p.noise_bstride + (int64_t)oy0 * p.OW + ox : nullptr;
+    const int64_t row_f = (int64_t)p.RW * p.C;
+    const float* rp = p.raw + (int64_t)b * p.RH * row_f + (int64_t)(oy0 - 1) * row_f + (int64_t)(ox - 1) * p.C + c0;
+    const bool v0 = ox - 1 >= 0, v4 = ox + 3 < p.RW;      // raw columns ox, ox+1, ox+2 always exist (ox + 1 < OW = RW - 1)
+    const int C = p.C;
+    // running 32-bit element offsets (the launcher checks that every emitted tensor has < 2^31 elements) instead of 64-bit
+    // index products per pixel
+    const int64_t opix = ((int64_t)b * p.OH + oy0) * p.OW + ox;
+    const uint32_t o32ld = (uint32_t)p.emit.out32_ld, c1p = (uint32_t)p.emit.c1_pad, c2p = (uint32_t)p.emit.c2_pad;
+    uint32_t o32 = (uint32_t)(opix * o32ld + c0), o1 = (uint32_t)(opix * c1p + c0), o2 = (uint32_t)(opix * c2p + c0);
+    const uint32_t o32row = (uint32_t)p.OW * o32ld, r1row = (uint32_t)p.OW * c1p, r2row = (uint32_t)p.OW * c2p;
+    const bool has32 = p.emit.out32 != nullptr, has1 = p.emit.hi1 != nullptr, has2 = p.emit.hi2 != nullptr;
+    const float gain = p.gain, alpha = p.alpha, clampv = p.clamp;
+    float4 ra[5], rb[5];                                  // the next two raw rows, in flight while the current one is consumed
+    auto load_row = [&](float4 (&r)[5], int ry, const float* q) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) r[k] = z4;
+        if (ry >= 0 && ry < p.RH) {
+            if (v0) r[0] = __ldg(reinterpret_cast<const float4*>(q));
+            r[1] = __ldg(reinterpret_cast<const float4*>(q + C));
+            r[2] = __ldg(reinterpret_cast<const float4*>(q + 2 * C));
+            r[3] = __ldg(reinterpret_cast<const float4*>(q + 3 * C));
+            if (v4) r[4] = __ldg(reinterpret_cast<const float4*>(q + 4 * C));
+        }
+    };
+    load_row(ra, oy0 - 1, rp);
+    load_row(rb, oy0, rp + row_f);
+#pragma unroll 3
+    for (int ry = oy0 - 1; ry <= oy1 + 1; ++ry, rp += row_f) {
+        float4 r[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) { r[k] = ra[k]; ra[k] = rb[k]; }
+        if (ry + 2 <= oy1 + 1) load_row(rb, ry + 2, rp + 2 * row_f);
+        float nz0 = 0.f, nz1 = 0.f;
+        const bool emit_row = ry - 2 >= oy0;              // output row ry-2 (< oy1 by the loop bound) completes with this raw row
+        if (emit_row && nptr) { nz0 = nptr[0] * nstr; nz1 = nptr[1] * nstr; nptr += p.OW; }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            float4 h;
+            h.x = fmaf(fx[3], r[j + 3].x, fmaf(fx[2], r[j + 2].x, fmaf(fx[1], r[j + 1].x, fx[0] * r[j].x)));
+            h.y = fmaf(fx[3], r[j + 3].y, fmaf(fx[2], r[j + 2].y, fmaf(fx[1], r[j + 1].y, fx[0] * r[j].y)));
+            h.z = fmaf(fx[3], r[j + 3].z, fmaf(fx[2], r[j + 2].z, fmaf(fx[1], r[j + 1].z, fx[0] * r[j].z)));
+            h.w = fmaf(fx[3], r[j + 3].w, fmaf(fx[2], r[j + 2].w, fmaf(fx[1], r[j + 1].w, fx[0] * r[j].w)));
+            float4& a0 = acc[j][0]; float4& a1 = acc[j][1]; float4& a2 = acc[j][2];
+            a0.x = fmaf(fy[3], h.x, a0.x); a0.y = fmaf(fy[3], h.y, a0.y); a0.z = fmaf(fy[3], h.z, a0.z); a0.w = fmaf(fy[3], h.w, a0.w);
+            a1.x = fmaf(fy[2], h.x, a1.x); a1.y = fmaf(fy[2], h.y, a1.y); a1.z = fmaf(fy[2], h.z, a1.z); a1.w = fmaf(fy[2], h.w, a1.w);
+            a2.x = fmaf(fy[1], h.x, a2.x); a2.y = fmaf(fy[1], h.y, a2.y); a2.z = fmaf(fy[1], h.z, a2.z); a2.w = fmaf(fy[1], h.w, a2.w);
+            const float4 a3 = make_float4(fy[0] * h.x, fy[0] * h.y, fy[0] * h.z, fy[0] * h.w);
+            if (emit_row) {
+                const float nz = j ? nz1 : nz0;
+                const float a4[4] = {a0.x, a0.y, a0.z, a0.w};
+                float v[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float t = p.dcoef ? fmaf(a4[k], dc[k], nz) : a4[k] + nz;     // fma(x, dcoef, noise), networks_stylegan2_new.py:74
+                    t += bs[k];
+                    if (ACT == IA_ACT_LRELU) t = (t > 0.f ? t : t * alpha) * gain;
+                    else if (ACT == IA_ACT_LINEAR) t = t * gain;
+                    else t = apply_act(t, p.act, alpha) * gain;
+                    if (clampv >= 0.f) t = fminf(fmaxf(t, -clampv), clampv);
+                    v[k] = t;
+                }
+                if (has32) {
+                    float* o = p.emit.out32 + (o32 + j * o32ld);
+                    if ((o32ld & 3) == 0) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+                    else { o[0] = v[0]; o[1] = v[1]; o[2] = v[2]; o[3] = v[3]; }
+                }
+                if (has1) {
+                    uint2 hv, lv;
+                    split_bf16x2(v[0] * s1[0], v[1] * s1[1], hv.x, lv.x);
+                    split_bf16x2(v[2] * s1[2], v[3] * s1[3], hv.y, lv.y);
+                    *reinterpret_cast<uint2*>(p.emit.hi1 + (o1 + j * c1p)) = hv;
+                    *reinterpret_cast<uint2*>(p.emit.lo1 + (o1 + j * c1p)) = lv;
+                }
+                if (has2) {
+                    uint2 hv, lv;
+                    split_bf16x2(v[0] * s2[0], v[1] * s2[1], hv.x, lv.x);
+                    split_bf16x2(v[2] * s2[2], v[3] * s2[3], hv.y, lv.y);
+                    *reinterpret_cast<uint2*>(p.emit.hi2 + (o2 + j * c2p)) = hv;
+                    *reinterpret_cast<uint2*>(p.emit.lo2 + (o2 + j * c2p)) = lv;
+                }
+            }
+            a0 = a1; a1 = a2; a2 = a3;
+        }
+        if (emit_row) { o32 += o32row; o1 += r1row; o2 += r2row; }
+    }
+}
+
 extern "C" int ia_fir_epilogue(const ia_fir_params* p, void* stream) {
     IA_CHECK(p && p->raw && p->fir, "ia_fir_epilogue: null tensor");
     IA_CHECK((p->C & 3) == 0, "ia_fir_epilogue: C must be a multiple of 4");
@@ -325,8 +452,21 @@ extern "C" int ia_fir_epilogue(const ia_fir_params* p, void* stream) {
     while (256 % cg) --cg;                              // block is 256 threads = cg x xt
     const int xt = 256 / cg;
     const int cchunks = (int)cdiv(groups, cg);
-    dim3 grid((unsigned)cdiv(p->OW, xt), (unsigned)cdiv(p->OH, FIR_YT), (unsigned)(p->B * cchunks));
+    static int x2 = -1;                                 // IA_FIR_X2=0 selects the one-column kernel (cross-check / profiling)
+    if (x2 < 0) { const char* e = getenv("IA_FIR_X2"); x2 = e ? atoi(e) : 1; }
     ia::prof_begin("ia_fir_epilogue", as_stream(stream));
+    const int64_t out_pix = (int64_t)p->B * p->OH * p->OW;
+    const bool small = out_pix * (p->emit.out32 ? p->emit.out32_ld : 0) < (1ll << 31) && out_pix * (p->emit.hi1 ? p->emit.c1_pad : 0) < (1ll << 31) &&
+                       out_pix * (p->emit.hi2 ? p->emit.c2_pad : 0) < (1ll << 31);
+    if (x2 && (p->OW & 1) == 0 && small) {
+        dim3 grid((unsigned)cdiv(p->OW / 2, xt), (unsigned)cdiv(p->OH, FIR_YT), (unsigned)(p->B * cchunks));
+        if (p->act == IA_ACT_LRELU) fir_epilogue_x2_kernel<IA_ACT_LRELU><<<grid, 256, 0, as_stream(stream)>>>(*p, cg, xt, cchunks);
+        else if (p->act == IA_ACT_LINEAR) fir_epilogue_x2_kernel<IA_ACT_LINEAR><<<grid, 256, 0, as_stream(stream)>>>(*p, cg, xt, cchunks);
+        else fir_epilogue_x2_kernel<-1><<<grid, 256, 0, as_stream(stream)>>>(*p, cg, xt, cchunks);
+        IA_LAUNCH_CHECK("ia_fir_epilogue");
+        return 0;
+    }
+    dim3 grid((unsigned)cdiv(p->OW, xt), (unsigned)cdiv(p->OH, FIR_YT), (unsigned)(p->B * cchunks));
     if (p->act == IA_ACT_LRELU) fir_epilogue_kernel<IA_ACT_LRELU><<<grid, 256, 0, as_stream(stream)>>>(*p, cg, xt, cchunks);
     else if (p->act == IA_ACT_LINEAR) fir_epilogue_kernel<IA_ACT_LINEAR><<<grid, 256, 0, as_stream(stream)>>>(*p, cg, xt, cchunks);
     else fir_epilogue_kernel<-1><<<grid, 256, 0, as_stream(stream)>>>(*p, cg, xt, cchunks);
