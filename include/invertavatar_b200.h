@@ -122,6 +122,11 @@ typedef struct {
     float* out32; int64_t out32_ld;                       /* fp32 NHWC */
     uint16_t* hi1; uint16_t* lo1; const float* s1; int32_t c1_pad;   /* split of v*s1[b][co] (next conv) */
     uint16_t* hi2; uint16_t* lo2; const float* s2; int32_t c2_pad;   /* split of v*s2[b][co] (ToRGB) */
+    /* Fused ToRGB contraction (networks_stylegan2_new.py:354-356: 1x1 modulated convolution without demodulation, few output
+     * channels): rgb_out[b][pixel][j] += sum_co (v*rgb_s[b][co]) * rgb_w[j][co], j < rgb_n <= 4, accumulated in fp32 with
+     * atomic adds (one per N tile of the launch) into a buffer the caller zero-filled.  ia_conv_tc only, persistent kernel,
+     * mode 1, Cout % 4 == 0; NULL: not used. */
+    float* rgb_out; const float* rgb_w; const float* rgb_s; int32_t rgb_n;
 } ia_emit;
 
 typedef struct {

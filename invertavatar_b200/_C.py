@@ -38,7 +38,8 @@ class ModsplitParams(C.Structure):
 class Emit(C.Structure):
     _fields_ = [('out32', c_f32p), ('out32_ld', C.c_int64),
                 ('hi1', c_u16p), ('lo1', c_u16p), ('s1', c_f32p), ('c1_pad', C.c_int32),
-                ('hi2', c_u16p), ('lo2', c_u16p), ('s2', c_f32p), ('c2_pad', C.c_int32)]
+                ('hi2', c_u16p), ('lo2', c_u16p), ('s2', c_f32p), ('c2_pad', C.c_int32),
+                ('rgb_out', c_f32p), ('rgb_w', c_f32p), ('rgb_s', c_f32p), ('rgb_n', C.c_int32)]
 
 
 class ConvParams(C.Structure):

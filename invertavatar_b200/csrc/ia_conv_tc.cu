@@ -468,14 +468,17 @@ __device__ __forceinline__ void epilogue_chunk(const Tc2Params& p, const float* 
 // 4-wide epilogue math, 16-byte fp32 / 8-byte bf16 stores} instead of 32 iterations of scalar work -- the scalar loop
 // costs ~80 instructions per row and bounds every few-tap launch (profiles/r1_conv_up_phase.txt).  tsm is [32][36] floats.
 constexpr int kTsmLd = 36;
-template <int ACT, bool O32, bool E1, bool E2>
+// Per-chunk operands of the fused ToRGB contraction: styles and weight rows of this lane's 4 channels, running sums of its 8 rows.
+struct RgbLane { float4 s; float4 w[4]; };
+template <int ACT, bool O32, bool E1, bool E2, bool RGB = false>
 __device__ __forceinline__ void epilogue_chunk_v4(const Tc2Params& p, const float* tsm, int lane, uint32_t vmask, int my_pix, float my_nz,
                                                   float* o32, uint16_t* h1, uint16_t* l1, uint16_t* h2, uint16_t* l2,
-                                                  const float4 dc, const float4 bs, const float4 s1, const float4 s2) {
+                                                  const float4 dc, const float4 bs, const float4 s1, const float4 s2,
+                                                  const RgbLane& rg, float (&racc)[8][4]) {
     const int rs = lane >> 3, c4 = lane & 7;
     const float gain = p.gain, alpha = p.alpha, clampv = p.clamp;
     const bool do_clamp = clampv >= 0.f;
-#pragma unroll 2
+#pragma unroll(RGB ? 8 : 2)
     for (int i = 0; i < 8; ++i) {
         const int rr = 4 * i + rs;
         const int pix_r = __shfl_sync(0xffffffffu, my_pix, rr);
@@ -501,6 +504,13 @@ __device__ __forceinline__ void epilogue_chunk_v4(const Tc2Params& p, const floa
             }
         }
         if (O32) *reinterpret_cast<float4*>(o32 + (int64_t)pix_r * p.emit.out32_ld) = a;
+        if (RGB) {
+            // (v * style) * weight, channel by channel, as the modulated 1x1 convolution does (networks_stylegan2_new.py:70-79)
+            const float mx = a.x * rg.s.x, my = a.y * rg.s.y, mz = a.z * rg.s.z, mw = a.w * rg.s.w;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                racc[i][j] = fmaf(mw, rg.w[j].w, fmaf(mz, rg.w[j].z, fmaf(my, rg.w[j].y, fmaf(mx, rg.w[j].x, racc[i][j]))));
+        }
         if (E1) {
             uint16_t h[4], l[4];
             split_bf16(a.x * s1.x, h[0], l[0]); split_bf16(a.y * s1.y, h[1], l[1]);
@@ -523,9 +533,15 @@ __device__ __forceinline__ void epilogue_chunk_v4(const Tc2Params& p, const floa
 template <int ACT>
 __device__ __forceinline__ void epilogue_chunk_v4_dispatch(const Tc2Params& p, const float* tsm, int lane, uint32_t vmask, int my_pix, float my_nz,
                                                            float* o32, uint16_t* h1, uint16_t* l1, uint16_t* h2, uint16_t* l2,
-                                                           const float4 dc, const float4 bs, const float4 s1, const float4 s2) {
+                                                           const float4 dc, const float4 bs, const float4 s1, const float4 s2,
+                                                           const RgbLane& rg, float (&racc)[8][4], bool rgb) {
+    if (ACT != 0 && rgb) {      // fused ToRGB: only with (optionally) the next convolution's operand -- checked by the launcher
+        if (h1) epilogue_chunk_v4<ACT, false, true, false, true>(p, tsm, lane, vmask, my_pix, my_nz, o32, h1, l1, h2, l2, dc, bs, s1, s2, rg, racc);
+        else epilogue_chunk_v4<ACT, false, false, false, true>(p, tsm, lane, vmask, my_pix, my_nz, o32, h1, l1, h2, l2, dc, bs, s1, s2, rg, racc);
+        return;
+    }
     const int sel = (o32 ? 1 : 0) | (h1 ? 2 : 0) | (h2 ? 4 : 0);
-#define IA_EPI(O, A, B) epilogue_chunk_v4<ACT, O, A, B>(p, tsm, lane, vmask, my_pix, my_nz, o32, h1, l1, h2, l2, dc, bs, s1, s2)
+#define IA_EPI(O, A, B) epilogue_chunk_v4<ACT, O, A, B>(p, tsm, lane, vmask, my_pix, my_nz, o32, h1, l1, h2, l2, dc, bs, s1, s2, rg, racc)
     switch (sel) {
         case 1: IA_EPI(true, false, false); break;
         case 2: IA_EPI(false, true, false); break;
@@ -763,6 +779,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                 const float* bias_g = p.bias ? p.bias + (int64_t)grp * p.Cout : nullptr;
                 const int64_t img_pix0 = (int64_t)img * p.OH * p.OW;
                 const uint32_t tcol = (acc * 2u + (uint32_t)half) * (uint32_t)p.acc_stride;
+                const bool rgb = p.emit.rgb_out != nullptr;
+                float racc[8][4];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { racc[i][0] = 0.f; racc[i][1] = 0.f; racc[i][2] = 0.f; racc[i][3] = 0.f; }
 #pragma unroll 1
                 for (int c = 0; c < p.n_tile; c += 32) {
                     uint32_t r[32];
@@ -793,10 +813,20 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                         uint16_t* l1 = p.emit.hi1 ? p.emit.lo1 + img_pix0 * p.emit.c1_pad + co0 : nullptr;
                         uint16_t* h2 = p.emit.hi2 ? p.emit.hi2 + img_pix0 * p.emit.c2_pad + co0 : nullptr;
                         uint16_t* l2 = p.emit.hi2 ? p.emit.lo2 + img_pix0 * p.emit.c2_pad + co0 : nullptr;
-                        if (p.mode == 0) epilogue_chunk_v4_dispatch<0>(p, tsm, lane, vm, my_pix, my_nz, o32, h1, l1, h2, l2, dc4, bs4, s14, s24);
-                        else if (p.act == IA_ACT_LRELU) epilogue_chunk_v4_dispatch<IA_ACT_LRELU>(p, tsm, lane, vm, my_pix, my_nz, o32, h1, l1, h2, l2, dc4, bs4, s14, s24);
-                        else if (p.act == IA_ACT_LINEAR) epilogue_chunk_v4_dispatch<IA_ACT_LINEAR>(p, tsm, lane, vm, my_pix, my_nz, o32, h1, l1, h2, l2, dc4, bs4, s14, s24);
-                        else epilogue_chunk_v4_dispatch<-1>(p, tsm, lane, vm, my_pix, my_nz, o32, h1, l1, h2, l2, dc4, bs4, s14, s24);
+                        RgbLane rg;
+                        rg.s = make_float4(1.f, 1.f, 1.f, 1.f);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) rg.w[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (rgb && cval) {
+                            if (p.emit.rgb_s) rg.s = *reinterpret_cast<const float4*>(p.emit.rgb_s + (int64_t)img * p.Cout + co0);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                if (j < p.emit.rgb_n) rg.w[j] = *reinterpret_cast<const float4*>(p.emit.rgb_w + (int64_t)j * p.Cout + co0);
+                        }
+                        if (p.mode == 0) epilogue_chunk_v4_dispatch<0>(p, tsm, lane, vm, my_pix, my_nz, o32, h1, l1, h2, l2, dc4, bs4, s14, s24, rg, racc, false);
+                        else if (p.act == IA_ACT_LRELU) epilogue_chunk_v4_dispatch<IA_ACT_LRELU>(p, tsm, lane, vm, my_pix, my_nz, o32, h1, l1, h2, l2, dc4, bs4, s14, s24, rg, racc, rgb);
+                        else if (p.act == IA_ACT_LINEAR && !rgb) epilogue_chunk_v4_dispatch<IA_ACT_LINEAR>(p, tsm, lane, vm, my_pix, my_nz, o32, h1, l1, h2, l2, dc4, bs4, s14, s24, rg, racc, false);
+                        else epilogue_chunk_v4_dispatch<-1>(p, tsm, lane, vm, my_pix, my_nz, o32, h1, l1, h2, l2, dc4, bs4, s14, s24, rg, racc, rgb);
                         continue;
                     }
 #pragma unroll
@@ -814,6 +844,30 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                     else if (p.act == IA_ACT_LRELU) epilogue_chunk<IA_ACT_LRELU>(p, tsm, lane, vmask, my_pix, my_nz, img_pix0, co, cvalid, dc, bs, s1v, s2v);
                     else if (p.act == IA_ACT_LINEAR) epilogue_chunk<IA_ACT_LINEAR>(p, tsm, lane, vmask, my_pix, my_nz, img_pix0, co, cvalid, dc, bs, s1v, s2v);
                     else epilogue_chunk<-1>(p, tsm, lane, vmask, my_pix, my_nz, img_pix0, co, cvalid, dc, bs, s1v, s2v);
+                }
+                if (rgb && vmask != 0u) {
+                    // sum the partial contractions of the 8 lanes that share a row (their 4-channel groups), then lane c4 == 0 adds
+                    // this N tile's share into the zero-filled output (one add per N tile: two tiles commute, the result is exact)
+                    const int rs = lane >> 3;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            float v = racc[i][j];
+                            v += __shfl_xor_sync(0xffffffffu, v, 1);
+                            v += __shfl_xor_sync(0xffffffffu, v, 2);
+                            v += __shfl_xor_sync(0xffffffffu, v, 4);
+                            racc[i][j] = v;
+                        }
+                        const int rr = 4 * i + rs;
+                        const int pix_r = __shfl_sync(0xffffffffu, my_pix, rr);
+                        if ((lane & 7) == 0 && ((vmask >> rr) & 1u)) {
+                            float* o = p.emit.rgb_out + (img_pix0 + pix_r) * p.emit.rgb_n;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                if (j < p.emit.rgb_n) atomicAdd(o + j, racc[i][j]);
+                        }
+                    }
                 }
             }
             tc_fence_before();
@@ -1018,9 +1072,11 @@ int launch_v2(const ia_conv_params* const* ps, int nph, void* stream) {
         t.epi_vec4 = (p->Cout % 4 == 0) && (!e.out32 || (al16(e.out32) && e.out32_ld % 4 == 0)) &&
                      (!e.hi1 || (al16(e.hi1) && al16(e.lo1) && e.c1_pad % 8 == 0)) && (!e.hi2 || (al16(e.hi2) && al16(e.lo2) && e.c2_pad % 8 == 0)) &&
                      (!p->dcoef || al16(p->dcoef)) && (!p->bias || al16(p->bias)) && (!e.s1 || al16(e.s1)) && (!e.s2 || al16(e.s2));
+        IA_CHECK(!e.rgb_out || (t.epi_vec4 && (!e.rgb_s || al16(e.rgb_s)) && al16(e.rgb_w)),
+                 "ia_conv_tc: the fused ToRGB contraction needs the vectorised epilogue (aligned operands, Cout %% 4 == 0)");
         static int force_scalar = -1;
         if (force_scalar < 0) { const char* ev = getenv("IA_CONV_EPI_SCALAR"); force_scalar = (ev && atoi(ev)) ? 1 : 0; }
-        if (force_scalar) t.epi_vec4 = 0;
+        if (force_scalar && !e.rgb_out) t.epi_vec4 = 0;
     }
 
     CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
@@ -1095,6 +1151,7 @@ extern "C" int ia_conv_tc(const ia_conv_params* p, void* stream) {
             return bk == 64 ? launch_v2<64>(&p, 1, stream) : launch_v2<32>(&p, 1, stream);
         }
     }
+    IA_CHECK(!p->emit.rgb_out, "ia_conv_tc: the fused ToRGB contraction needs the persistent kernel (images of >= 128 pixels, width >= 8)");
     TcParams t;
     memset(&t, 0, sizeof(t));
     t.B = p->B; t.GH = p->GH; t.GW = p->GW;

@@ -441,19 +441,25 @@ __global__ void __launch_bounds__(256, 2) fir_epilogue_x2_kernel(ia_fir_params p
     }
 }
 
+namespace ia {
+bool fir_tma_eligible(const ia_fir_params* p);      // ia_fir_tma.cu: TMA-fed streaming variant
+int fir_tma_launch(const ia_fir_params* p, void* stream);
+}
+
 extern "C" int ia_fir_epilogue(const ia_fir_params* p, void* stream) {
     IA_CHECK(p && p->raw && p->fir, "ia_fir_epilogue: null tensor");
     IA_CHECK((p->C & 3) == 0, "ia_fir_epilogue: C must be a multiple of 4");
     IA_CHECK(p->RH == p->OH + 1 && p->RW == p->OW + 1, "ia_fir_epilogue: raw must be (OH+1) x (OW+1)");
     IA_CHECK(p->noise == nullptr || p->noise_strength != nullptr, "ia_fir_epilogue: noise needs noise_strength");
     if ((int64_t)p->B * p->OH * p->OW * p->C == 0) return 0;
+    if (ia::fir_tma_eligible(p)) return ia::fir_tma_launch(p, stream);
     const int groups = p->C >> 2;
     int cg = groups < 32 ? groups : 32;                 // channel groups (of 4) per block row; 32 -> one warp = 512 contiguous bytes
     while (256 % cg) --cg;                              // block is 256 threads = cg x xt
     const int xt = 256 / cg;
     const int cchunks = (int)cdiv(groups, cg);
-    static int x2 = -1;                                 // IA_FIR_X2=0 selects the one-column kernel (cross-check / profiling)
-    if (x2 < 0) { const char* e = getenv("IA_FIR_X2"); x2 = e ? atoi(e) : 1; }
+    int x2 = 1;                                         // IA_FIR_X2=0 selects the one-column kernel (cross-check / profiling)
+    { const char* e = getenv("IA_FIR_X2"); if (e) x2 = atoi(e); }
     ia::prof_begin("ia_fir_epilogue", as_stream(stream));
     const int64_t out_pix = (int64_t)p->B * p->OH * p->OW;
     const bool small = out_pix * (p->emit.out32 ? p->emit.out32_ld : 0) < (1ll << 31) && out_pix * (p->emit.hi1 ? p->emit.c1_pad : 0) < (1ll << 31) &&
@@ -683,7 +689,10 @@ int ia_conv_validate(const ia_conv_params* p, const char* who) {
     IA_CHECK(p->sy >= 1 && p->sx >= 1, "%s: bad output stride", who);
     IA_CHECK(p->mode == 0 || p->mode == 1, "%s: bad epilogue mode", who);
     IA_CHECK(p->noise == nullptr || p->noise_strength != nullptr, "%s: noise needs noise_strength", who);
-    IA_CHECK(p->emit.out32 || p->emit.hi1 || p->emit.hi2, "%s: nothing to emit", who);
+    IA_CHECK(p->emit.out32 || p->emit.hi1 || p->emit.hi2 || p->emit.rgb_out, "%s: nothing to emit", who);
+    IA_CHECK(!p->emit.rgb_out || (p->emit.rgb_w && p->emit.rgb_n >= 1 && p->emit.rgb_n <= 4 && p->mode == 1 && (p->Cout & 3) == 0 &&
+                                  !p->emit.out32 && !p->emit.hi2),
+             "%s: fused ToRGB needs rgb_w, 1..4 outputs, mode 1, Cout %% 4 == 0 and neither out32 nor emit 2", who);
     IA_CHECK(p->groups <= 1 || (p->imgs_per_group > 0 && p->B == p->groups * p->imgs_per_group), "%s: grouped launch needs B == groups * imgs_per_group", who);
     IA_CHECK(!p->emit.hi1 || (p->emit.lo1 && p->emit.c1_pad >= p->Cout && (p->emit.c1_pad & 3) == 0), "%s: bad emit 1", who);
     IA_CHECK(!p->emit.hi2 || (p->emit.lo2 && p->emit.c2_pad >= p->Cout && (p->emit.c2_pad & 3) == 0), "%s: bad emit 2", who);
@@ -693,6 +702,7 @@ int ia_conv_validate(const ia_conv_params* p, const char* who) {
 extern "C" int ia_conv_simt(const ia_conv_params* p, void* stream) {
     if (int rc = ia_conv_validate(p, "ia_conv_simt")) return rc;
     IA_CHECK(p->groups <= 1, "ia_conv_simt: grouped launches are implemented by ia_conv_tc only");
+    IA_CHECK(!p->emit.rgb_out, "ia_conv_simt: the fused ToRGB contraction is implemented by ia_conv_tc only");
     int64_t rows = (int64_t)p->B * p->GH * p->GW;
     dim3 grid((unsigned)cdiv(rows, SIMT_TM), (unsigned)cdiv(p->Cout_pad, SIMT_TN));
     ia::prof_begin("ia_conv_simt", as_stream(stream));

@@ -9,6 +9,7 @@ import math
 import threading
 
 import numpy as np
+import os
 import torch
 
 from . import _C
@@ -382,10 +383,15 @@ def new_split(B, H, W, C_pad, device, C=None):
     return Split(hi, lo)
 
 
-def _emit(out32=None, e1=None, e2=None):
+def _emit(out32=None, e1=None, e2=None, rgb=None):
     """out32: fp32 NHWC tensor or None; e1/e2: (Split, styles [B,Cout] or None) pairs filled by the epilogue with
-    split(v * styles) -- the operand of the next convolution / the ToRGB layer."""
+    split(v * styles) -- the operand of the next convolution / the ToRGB layer.  rgb = (raw [B,H,W,n] zero-filled fp32,
+    weight [n,Cout] fp32, styles [B,Cout]): the ToRGB contraction itself, accumulated by the epilogue (n <= 4)."""
     e = _C.Emit()
+    if rgb is not None:
+        raw, w2d, st = rgb
+        assert raw.is_contiguous() and w2d.is_contiguous() and st.is_contiguous() and w2d.shape[0] == raw.shape[-1] <= 4
+        e.rgb_out, e.rgb_w, e.rgb_s, e.rgb_n = _p(raw), _p(w2d), _p(st), int(raw.shape[-1])
     if out32 is not None:
         e.out32 = _p(out32)
         e.out32_ld = out32.stride(2)
@@ -415,7 +421,7 @@ def _set_group(p, group):
 
 
 def conv_same(hi, lo, pack, Cin_pad, out32, dcoef=None, noise=None, noise_strength=None, bias=None, act='linear',
-              gain=1.0, clamp=None, mode=1, impl=None, e1=None, e2=None, group=None):
+              gain=1.0, clamp=None, mode=1, impl=None, e1=None, e2=None, group=None, rgb=None):
     """k x k correlation, stride 1, 'same' padding (flip_weight=True branch of conv2d_resample, :134-136)."""
     st = _enter(hi)
     B, H, W, _ = hi.shape
@@ -435,9 +441,16 @@ def conv_same(hi, lo, pack, Cin_pad, out32, dcoef=None, noise=None, noise_streng
     p.dcoef, p.noise, p.noise_strength, p.bias = _p(dcoef), _p(noise), _p(noise_strength), _p(bias)
     p.noise_bstride = _noise_bstride(noise)
     p.act, p.alpha, p.gain, p.clamp = ACT_IDS[act], ACT_DEFAULTS[act][0], float(gain), float(-1 if clamp is None else clamp)
-    p.emit = _emit(out32, e1, e2)
+    p.emit = _emit(out32, e1, e2, rgb)
     _set_group(p, group)
     _conv_call(p, st, impl)
+
+
+def can_fuse_torgb(H, W, Cout, n_img, impl=None):
+    """Whether conv_same(..., rgb=...) is available for this layer: tensor-core path, persistent kernel (>= 128 pixels per image,
+    width >= 8), <= 4 image channels, and at most two N tiles of 128 (two partial sums commute: the result stays exact)."""
+    return ((impl or _conv_impl) == 'tc' and H * W >= 128 and W >= 8 and n_img <= 4 and Cout % 4 == 0 and Cout <= 256
+            and os.environ.get('IA_FUSE_TORGB', '1') != '0')
 
 
 def conv_transpose_up2_raw(hi, lo, pack, Cin_pad, raw, impl=None, group=None):

@@ -183,7 +183,7 @@ class SynthesisLayer(torch.nn.Module):
                             act_gain, act_clamp)
         return out
 
-    def run_split(self, a, dcoef, noise_mode='const', gain=1, want32=False, e1=None, e2=None):
+    def run_split(self, a, dcoef, noise_mode='const', gain=1, want32=False, e1=None, e2=None, rgb=None):
         """Fused-chain entry: ``a`` is an rt.Split already holding x*styles of THIS layer; the epilogue writes any of
         the fp32 NHWC result (want32) and the pre-modulated operands of the consumers (e1/e2 = (Split, styles))."""
         assert self.up in (1, 2)
@@ -200,8 +200,9 @@ class SynthesisLayer(torch.nn.Module):
         out = torch.empty((B, R, R, self.out_channels), dtype=torch.float32, device=a.hi.device) if want32 else None
         if self.up == 1:
             rt.conv_same(a.hi, a.lo, pack, pack.Cin_pad, out, dcoef=dcoef, noise=noise, noise_strength=strength, bias=self.bias,
-                         act=self.activation, gain=act_gain, clamp=act_clamp, mode=1, e1=e1, e2=e2)
+                         act=self.activation, gain=act_gain, clamp=act_clamp, mode=1, e1=e1, e2=e2, rgb=rgb)
         else:
+            assert rgb is None
             raw = torch.empty((B, 2 * H + 1, 2 * W + 1, self.out_channels), dtype=torch.float32, device=a.hi.device)
             rt.conv_transpose_up2_raw(a.hi, a.lo, pack, pack.Cin_pad, raw)
             rt.fir_epilogue(raw, rt.fir4x4_gain4(a.hi.device), out, dcoef, noise, strength, self.bias, self.activation,
@@ -256,6 +257,10 @@ class ToRGBLayer(torch.nn.Module):
     def style_entry(self, w_index):
         return dict(affine_w=self.affine.weight, affine_b=self.affine.bias, wsq=None, Cin=self.in_channels,
                     Cout=self.out_channels, w_index=w_index, style_gain=float(self.weight_gain))
+
+    def weight2d(self):
+        """[out_channels, in_channels] fp32 view of the 1x1 kernel (operand of the fused ToRGB contraction)."""
+        return self.weight.detach().reshape(self.out_channels, self.in_channels)
 
     def run_nhwc(self, x, styles, img_prev=None, out_nchw=False):
         """x [B,H,W,Cin] -> img = upsample2d(img_prev) + clamp(modconv1x1(x) + bias)  as NHWC (or planar NCHW)."""
@@ -387,12 +392,20 @@ class SynthesisBlock(torch.nn.Module):
                 a1 = rt.Split(hi, lo)
             i = 1
         has_rgb = hasattr(self, 'torgb')
-        a_rgb = rt.new_split(B, R, R, self.torgb.pack().Cin_pad, dev, C=self.torgb.in_channels) if has_rgb else None
+        # ToRGB with few image channels (the super-resolution blocks: 3) is contracted inside conv1's epilogue: no ToRGB operand is
+        # written and re-read, no 1x1 convolution launch
+        fuse_rgb = (has_rgb and not want_x32 and self.torgb.weight.shape[2] == 1 and
+                    rt.can_fuse_torgb(R, R, self.conv1.out_channels, self.torgb.out_channels))
+        a_rgb = rt.new_split(B, R, R, self.torgb.pack().Cin_pad, dev, C=self.torgb.in_channels) if (has_rgb and not fuse_rgb) else None
         a_next = rt.new_split(B, R, R, next_conv.pack().Cin_pad, dev, C=next_conv.in_channels) if next_conv is not None else None
+        rgb_raw = torch.zeros((B, R, R, self.torgb.out_channels), dtype=torch.float32, device=dev) if fuse_rgb else None
         x32 = self.conv1.run_split(a1, dcoefs[i], noise_mode=noise_mode, gain=gain, want32=want_x32,
                                    e1=(a_next, next_styles) if a_next is not None else None,
-                                   e2=(a_rgb, styles[i + 1]) if has_rgb else None)
-        if has_rgb:
+                                   e2=(a_rgb, styles[i + 1]) if a_rgb is not None else None,
+                                   rgb=(rgb_raw, self.torgb.weight2d(), styles[i + 1]) if fuse_rgb else None)
+        if fuse_rgb:
+            img = rt.torgb_finish(rgb_raw, self.torgb.bias, self.torgb.conv_clamp, img, out_nchw=img_nchw)
+        elif has_rgb:
             img = self.torgb.run_split(a_rgb, img_prev=img, out_nchw=img_nchw)
         elif img is not None:
             img = rt.to_nhwc(rt.upfirdn2d(rt.from_nhwc(img), self.resample_filter, up=(2, 2), padding=(2, 1, 2, 1), gain=4.0))

@@ -163,3 +163,28 @@ def test_synthesis_network_fused_chain(impl):
     ref = o_sg.synthesis_network(sd, ws, cond_list=conds, return_list=False, out_res=(8, 32))
     got = net(ws.to(DEV), cond_list=[c.to(DEV) for c in conds], return_list=False, out_res=(8, 32), noise_mode='const')
     assert maxerr(got, ref) <= TOL * max(1.0, float(ref.abs().max()))
+
+
+def test_fused_torgb_matches_oracle(monkeypatch):
+    """3-channel ToRGB contracted inside conv1's epilogue (ia_emit.rgb_*; 256 channels = two N tiles adding into the same
+    pixels) against the oracle, and bit-for-bit reproducible; IA_FUSE_TORGB=0 (separate 1x1 convolution) agrees to tolerance."""
+    torch.manual_seed(9)
+    net = sg.SynthesisNetwork(w_dim=64, img_resolution=32, img_channels=3, channel_base=8192, channel_max=256, num_fp16_res=0,
+                              conv_clamp=None).requires_grad_(False)
+    for n, p in net.named_parameters():
+        if n.endswith('noise_strength'):
+            p.fill_(0.2)
+        if n.endswith('.bias') and 'affine' not in n:
+            p.copy_(torch.randn_like(p) * 0.1)
+    g = torch.Generator().manual_seed(3)
+    ws = torch.randn(2, net.num_ws, 64, generator=g)
+    ref = o_sg.synthesis_network(net.state_dict(), ws)
+    net = net.to(DEV)
+    assert rt.can_fuse_torgb(32, 32, 256, 3) and not rt.can_fuse_torgb(8, 8, 256, 3)
+    a = net(ws.to(DEV), noise_mode='const')
+    b = net(ws.to(DEV), noise_mode='const')
+    assert torch.equal(a, b)
+    assert maxerr(a, ref) <= TOL * max(1.0, float(ref.abs().max()))
+    monkeypatch.setenv('IA_FUSE_TORGB', '0')
+    c = net(ws.to(DEV), noise_mode='const')
+    assert maxerr(c, ref) <= TOL * max(1.0, float(ref.abs().max()))

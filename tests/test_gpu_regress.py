@@ -62,3 +62,29 @@ def test_graphed_synthesis_matches_eager():
                                evaluation=True)['image']
             assert float((got - want).abs().max()) <= 1e-6, i
         G.renderer.fixed_jitter = None
+
+
+@pytest.mark.parametrize('B,OH,C,use32,use1,use2', [(2, 128, 64, True, True, True), (1, 64, 128, False, True, False), (3, 32, 32, True, False, True)])
+def test_fir_epilogue_variants_agree(monkeypatch, B, OH, C, use32, use1, use2):
+    """The three FIR-epilogue kernels (TMA-fed ring, two-column register kernel, one-column register kernel) perform the same
+    arithmetic in the same order: bit-identical outputs (fp32 copy and both emitted bf16 hi/lo operands)."""
+    from invertavatar_b200 import runtime as rt
+    g = torch.Generator().manual_seed(B * 1000 + OH + C)
+    raw = torch.randn(B, OH + 1, OH + 1, C, generator=g).cuda()
+    dcoef, bias = torch.rand(B, C, generator=g).cuda() + 0.5, torch.randn(C, generator=g).cuda()
+    noise, strength = torch.randn(OH, OH, generator=g).cuda(), torch.tensor(0.3).cuda()
+    s1, s2 = torch.randn(B, C, generator=g).cuda(), torch.randn(B, C, generator=g).cuda()
+    outs = {}
+    for name, env in (('tma', {'IA_FIR_TMA': '1'}), ('x2', {'IA_FIR_TMA': '0', 'IA_FIR_X2': '1'}), ('x1', {'IA_FIR_TMA': '0', 'IA_FIR_X2': '0'})):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        out = torch.zeros(B, OH, OH, C, device='cuda') if use32 else None
+        e1 = rt.new_split(B, OH, OH, max(64, C), 'cuda', C=C) if use1 else None
+        e2 = rt.new_split(B, OH, OH, max(64, C), 'cuda', C=C) if use2 else None
+        rt.fir_epilogue(raw, rt.fir4x4_gain4('cuda'), out, dcoef, noise, strength, bias, 'lrelu', 1.3, 2.0,
+                        e1=(e1, s1) if use1 else None, e2=(e2, s2) if use2 else None)
+        torch.cuda.synchronize()
+        outs[name] = [t.clone() for t in ([out] if use32 else []) + ([e1.hi, e1.lo] if use1 else []) + ([e2.hi, e2.lo] if use2 else [])]
+    for name in ('x2', 'x1'):
+        for a, b in zip(outs['tma'], outs[name]):
+            assert torch.equal(a, b), name
