@@ -950,6 +950,9 @@ int launch_v2(const ia_conv_params* const* ps, int nph, void* stream) {
         if (p->Cout_pad % cand) continue;
         n_tile = cand;
         if (real_tiles * (p->Cout_pad / cand) >= 120) break;
+        // fused ToRGB: every N tile adds its share into the same pixels; with at most two tiles the two adds commute and the
+        // result does not depend on their order -> take the widest tile whatever the grid size
+        if (p->emit.rgb_out) break;
     }
     t.n_tile = n_tile; t.acc_stride = 128;
     t.n_tiles = p->Cout_pad / n_tile;
@@ -1072,6 +1075,7 @@ int launch_v2(const ia_conv_params* const* ps, int nph, void* stream) {
         t.epi_vec4 = (p->Cout % 4 == 0) && (!e.out32 || (al16(e.out32) && e.out32_ld % 4 == 0)) &&
                      (!e.hi1 || (al16(e.hi1) && al16(e.lo1) && e.c1_pad % 8 == 0)) && (!e.hi2 || (al16(e.hi2) && al16(e.lo2) && e.c2_pad % 8 == 0)) &&
                      (!p->dcoef || al16(p->dcoef)) && (!p->bias || al16(p->bias)) && (!e.s1 || al16(e.s1)) && (!e.s2 || al16(e.s2));
+        IA_CHECK(!e.rgb_out || t.n_tiles <= 2, "ia_conv_tc: the fused ToRGB contraction allows at most two N tiles (Cout_pad %d, N tile %d)", p->Cout_pad, t.n_tile);
         IA_CHECK(!e.rgb_out || (t.epi_vec4 && (!e.rgb_s || al16(e.rgb_s)) && al16(e.rgb_w)),
                  "ia_conv_tc: the fused ToRGB contraction needs the vectorised epilogue (aligned operands, Cout %% 4 == 0)");
         static int force_scalar = -1;

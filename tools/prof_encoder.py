@@ -5,7 +5,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from invertavatar_b200 import synth, runtime as rt
 from invertavatar_b200.encoder import inversionNet
-from invertavatar_b200.triplane import TriPlaneGenerator
+from invertavatar_b200.triplane import TriPlaneGenerator, set_backbone_streams
+set_backbone_streams(False)                                   # one stream: per-launch event times must not overlap
+rt.side_streams = lambda device: (torch.cuda.current_stream(device),) * 2
 T = 4
 torch.manual_seed(0)
 G = TriPlaneGenerator(**synth.generator_kwargs(48, 48)).eval().requires_grad_(False)
@@ -35,5 +37,10 @@ with torch.no_grad():
     rep = rt.profile_report()
 tot = sum(q['ms'] for q in rep.values())
 print(f'{which}: total {tot:.3f} ms, {sum(q["launches"] for q in rep.values())} launches')
-for k, q in sorted(rep.items(), key=lambda kv: -kv[1]['ms'])[:40]:
-    print(f'{k:48s} {q["ms"]:8.3f} ms  x{q["launches"]:4d}')
+for k, q in sorted(rep.items(), key=lambda kv: -kv[1]['ms'])[:60]:
+    extra = ''
+    m = re.match(r'ia_conv_tc\[t(\d+) (\d+)x(\d+) (\d+)->(\d+)\]', k)
+    if m:
+        t, gh, gw, ci, co = map(int, m.groups())
+        extra = f'  {2.0 * gh * gw * ci * co * t * q["launches"] / (q["ms"] * 1e-3) / 1e12:7.1f} TF/s per image (x batch; padded Cin)'
+    print(f'{k:48s} {q["ms"]:8.3f} ms  x{q["launches"]:4d}{extra}')
