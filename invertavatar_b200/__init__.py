@@ -3,3 +3,9 @@
 Host side: Python modules mirroring the reference's classes (``TriPlaneGenerator`` etc.); device side: hand-written CUDA
 behind the C-ABI in ``include/invertavatar_b200.h`` (``libinvertavatar_b200.so``).  There is no CPU fallback."""
 __version__ = '0.1.0'
+
+
+def prepack(module):
+    """Pack every convolution weight of ``module`` (already on the GPU) into the tensor-core layout now (see runtime.prepack)."""
+    from . import runtime
+    return runtime.prepack(module)

@@ -271,6 +271,20 @@ class ConvPack(_EngineCache):
         return pack
 
 
+def prepack(module):
+    """One-time weight packing at load: build the GEMM-layout bf16 hi/lo weights (+ the demodulation table
+    sum w^2) of every convolution / ToRGB layer of ``module`` now instead of at first use.  Call after ``module.to('cuda')``
+    (e.g. right after ``legacy.load_network_pkl``); returns the packed bytes.  Packs are keyed on the parameter's storage and
+    version, so a later in-place update (PTI fine-tuning, ``copy_params_and_buffers``) repacks that layer transparently."""
+    total = 0
+    for m in module.modules():
+        fn = getattr(m, 'pack', None)
+        if callable(fn) and isinstance(getattr(m, 'weight', None), torch.Tensor) and m.weight.is_cuda and m.weight.ndim == 4:
+            pk = fn()
+            total += pk.w_hi.numel() * 4 + (pk.wsq.numel() * 4 if pk.wsq is not None else 0)
+    return total
+
+
 class ConvPackGroup(_EngineCache):
     """Packed weights of the same layer of several networks, stacked along the tap axis ([G*taps][Cout_pad][Cin_pad]) for a
     grouped launch (ia_conv_params.groups).  Output channels are zero-padded to the widest member (ToRGB layers of the

@@ -88,3 +88,22 @@ def test_fir_epilogue_variants_agree(monkeypatch, B, OH, C, use32, use1, use2):
     for name in ('x2', 'x1'):
         for a, b in zip(outs['tma'], outs[name]):
             assert torch.equal(a, b), name
+
+
+def test_prepack_builds_every_pack_once():
+    """invertavatar_b200.prepack packs all conv / ToRGB weights at load; the first synthesis afterwards reuses them."""
+    import copy
+    import invertavatar_b200
+    from invertavatar_b200 import runtime as rt
+    G = copy.deepcopy(build_generator(16, 16)).to('cuda')
+    nbytes = invertavatar_b200.prepack(G)
+    assert nbytes > 300e6                       # 88 M parameters -> ~353 MB of bf16 hi/lo pairs
+    packs = {id(m): m.__dict__['_ia_pack'] for m in G.modules() if '_ia_pack' in m.__dict__}
+    assert len(packs) >= 3 * 25
+    z, cond, c, uv = synth.latents(1).cuda(), synth.frontal_camera(1).cuda(), synth.cameras(1).cuda(), synth.uvcoords_image(1).cuda()
+    with torch.no_grad():
+        ws = G.mapping(z, cond, truncation_psi=0.7, truncation_cutoff=14)
+        G.synthesis(ws, c, {'uvcoords_image': uv}, neural_rendering_resolution=64, noise_mode='const', evaluation=True)
+    for m in G.modules():
+        if id(m) in packs:
+            assert m.__dict__['_ia_pack'] is packs[id(m)]
