@@ -278,10 +278,17 @@ def prepack(module):
     version, so a later in-place update (PTI fine-tuning, ``copy_params_and_buffers``) repacks that layer transparently."""
     total = 0
     for m in module.modules():
+        w = getattr(m, 'weight', None)
+        if not (isinstance(w, torch.Tensor) and w.is_cuda and w.ndim == 4):
+            continue
         fn = getattr(m, 'pack', None)
-        if callable(fn) and isinstance(getattr(m, 'weight', None), torch.Tensor) and m.weight.is_cuda and m.weight.ndim == 4:
+        if callable(fn):
             pk = fn()
-            total += pk.w_hi.numel() * 4 + (pk.wsq.numel() * 4 if pk.wsq is not None else 0)
+        elif isinstance(m, torch.nn.Conv2d) and m.groups == 1:      # encoder convolutions (plain nn.Conv2d parameters)
+            pk = ConvPack.current(m, '_ia_pack', w, need_wsq=False)
+        else:
+            continue
+        total += pk.w_hi.numel() * 4 + (pk.wsq.numel() * 4 if pk.wsq is not None else 0)
     return total
 
 

@@ -99,7 +99,7 @@ def test_prepack_builds_every_pack_once():
     nbytes = invertavatar_b200.prepack(G)
     assert nbytes > 300e6                       # 88 M parameters -> ~353 MB of bf16 hi/lo pairs
     packs = {id(m): m.__dict__['_ia_pack'] for m in G.modules() if '_ia_pack' in m.__dict__}
-    assert len(packs) >= 3 * 25
+    assert len(packs) == 3 * 20 + 6             # per backbone: b4 conv1+torgb, b8..b256 conv0+conv1+torgb; SR: 2 blocks x 3
     z, cond, c, uv = synth.latents(1).cuda(), synth.frontal_camera(1).cuda(), synth.cameras(1).cuda(), synth.uvcoords_image(1).cuda()
     with torch.no_grad():
         ws = G.mapping(z, cond, truncation_psi=0.7, truncation_cutoff=14)
