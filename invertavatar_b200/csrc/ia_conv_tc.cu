@@ -949,7 +949,12 @@ int launch_v2(const ia_conv_params* const* ps, int nph, void* stream) {
     for (int cand = 128; cand >= 32; cand -= 32) {
         if (p->Cout_pad % cand) continue;
         n_tile = cand;
-        if (real_tiles * (p->Cout_pad / cand) >= 120) break;
+        // widest N tile that still gives at least `min_tiles` CTAs: a narrow tile amortises every activation tile over few
+        // output channels and leaves too little MMA work per pipeline stage to cover the TMA latency (measured, 512->512 at
+        // 16x16 x 24 images: 96 CTAs of N=128 take 126 us, 384 CTAs of N=32 take 213 us); IA_CONV_MIN_TILES overrides
+        static int min_tiles = -1;
+        if (min_tiles < 0) { const char* ev = getenv("IA_CONV_MIN_TILES"); min_tiles = ev ? atoi(ev) : 48; }
+        if (real_tiles * (p->Cout_pad / cand) >= min_tiles) break;
         // fused ToRGB: every N tile adds its share into the same pixels; with at most two tiles the two adds commute and the
         // result does not depend on their order -> take the widest tile whatever the grid size
         if (p->emit.rgb_out) break;
@@ -1173,7 +1178,9 @@ extern "C" int ia_conv_tc(const ia_conv_params* p, void* stream) {
     for (int cand = 256; cand >= 32; cand -= 32) {
         if (p->Cout_pad % cand) continue;
         n_tile = cand;
-        if (m_tiles * (p->Cout_pad / cand) >= 128) break;
+        static int min_tiles1 = -1;
+        if (min_tiles1 < 0) { const char* ev = getenv("IA_CONV_MIN_TILES_V1"); min_tiles1 = ev ? atoi(ev) : 128; }
+        if (m_tiles * (p->Cout_pad / cand) >= min_tiles1) break;
     }
     t.n_tile = n_tile;
     t.tmem_cols = 32; while (t.tmem_cols < n_tile) t.tmem_cols <<= 1;

@@ -997,11 +997,11 @@ def layout_grid_u8(img, grid_w=None, grid_h=1):
 _SIDE_STREAMS = {}
 
 
-def side_streams(device):
-    """Two auxiliary CUDA streams per device (process-wide; kept off the modules so that they stay deep-copyable/picklable)."""
+def side_streams(device, n=2):
+    """``n`` auxiliary CUDA streams per device (process-wide; kept off the modules so that they stay deep-copyable/picklable)."""
     key = str(torch.device(device))
-    st = _SIDE_STREAMS.get(key)
-    if st is None:
-        st = (torch.cuda.Stream(device=device), torch.cuda.Stream(device=device))
+    st = _SIDE_STREAMS.get(key, ())
+    if len(st) < n:
+        st = tuple(st) + tuple(torch.cuda.Stream(device=device) for _ in range(n - len(st)))
         _SIDE_STREAMS[key] = st
-    return st
+    return st[:n]

@@ -113,27 +113,52 @@ class TriPlaneGenerator(torch.nn.Module):
                                      truncation_cutoff=truncation_cutoff, update_emas=update_emas)
 
     # ------------------------------------------------------------------------------------------
-    def _rasterize_nhwc(self, texture_feats, uvcoords_image, static_feats, bbox_256, levels=None):
-        """Engine rasterizer.  texture_feats/static_feats: lists of NHWC tensors (static entries already reduced to the
-        32 plane-0 channels where the reference slices them).  Returns per-level (cond NHWC [B,r,r,C], alpha [B,r,r]),
-        full_alpha [B,256,256], mouth [B,256,256].  ``levels`` restricts the work to the entries a consumer reads."""
+    @staticmethod
+    def _uv_prep(uvcoords_image, resolutions, want_alpha128=False):
+        """Everything the rasterizer / stitcher derives from the mesh condition alone: the flood-filled masks
+        (renderer.py:716-741) and the antialias-resized alpha / upper-face alpha of every level (triplane_v20.py:331-337).
+        Independent of the backbones, so ``synthesis`` issues it on a side stream while they run."""
         uv = uvcoords_image if uvcoords_image.dtype == torch.float32 else uvcoords_image.float()
         uv = uv.contiguous()
-        B, UH, UW, _ = uv.shape
         full_alpha, mouth, upper_alpha = rt.fill_mouth(uv, upper_row0=87)
-        alpha = uv[..., 2]                       # strided view [B,H,W]
         alpha4 = uv[..., 2:3]                    # [B,H,W,1] NHWC view with pixel stride 3
         upper4 = upper_alpha.unsqueeze(-1)
+        resized = {}
+        for res in resolutions:
+            if res not in resized:
+                resized[res] = (rt.resize_aa(alpha4, res, res).squeeze(-1), rt.resize_aa(upper4, res, res).squeeze(-1))
+        prep = {'uv': uv, 'full_alpha': full_alpha, 'mouth': mouth, 'resized': resized}
+        if want_alpha128:
+            prep['alpha128'] = rt.resize_aa(full_alpha.unsqueeze(-1), 128, 128).squeeze(-1)
+        return prep
+
+    @staticmethod
+    def _prep_tensors(prep):
+        out = [prep['uv'], prep['full_alpha'], prep['mouth']] + [t for pair in prep['resized'].values() for t in pair]
+        if 'alpha128' in prep:
+            out.append(prep['alpha128'])
+        return out
+
+    def _rasterize_nhwc(self, texture_feats, uvcoords_image, static_feats, bbox_256, levels=None, prep=None):
+        """Engine rasterizer.  texture_feats/static_feats: lists of NHWC tensors (static entries already reduced to the
+        32 plane-0 channels where the reference slices them).  Returns per-level (cond NHWC [B,r,r,C], alpha [B,r,r]),
+        full_alpha [B,256,256], mouth [B,256,256].  ``levels`` restricts the work to the entries a consumer reads;
+        ``prep`` is the result of ``_uv_prep`` when the caller already has it."""
+        idxs = [i for i in range(len(texture_feats)) if levels is None or i in levels]
+        if prep is None:
+            prep = self._uv_prep(uvcoords_image, [texture_feats[i].shape[1] for i in idxs])
+        uv, full_alpha, mouth, resized_alpha = prep['uv'], prep['full_alpha'], prep['mouth'], prep['resized']
+        for i in idxs:
+            res = texture_feats[i].shape[1]
+            if res not in resized_alpha:         # a level the caller's prep did not cover
+                resized_alpha[res] = self._uv_prep(uvcoords_image, [res])['resized'][res]
         outs = []
-        resized_alpha = {}
         for idx, tex in enumerate(texture_feats):
-            if levels is not None and idx not in levels:
+            if idx not in idxs:
                 outs.append(None)
                 continue
             res = tex.shape[1]
             bbox = [round(i * res / 256) for i in bbox_256]
-            if res not in resized_alpha:
-                resized_alpha[res] = (rt.resize_aa(alpha4, res, res).squeeze(-1), rt.resize_aa(upper4, res, res).squeeze(-1))
             a_r, ua_r = resized_alpha[res]
             # grid_sample @256^2 -> aa-resize to res -> blend with the resized static crop, fused (no [B,256,256,C] tensor)
             outs.append((rt.raster_level(tex, uv, static_feats[idx], (bbox[0], bbox[1], bbox[2], bbox[3]), a_r, res), ua_r))
@@ -161,7 +186,7 @@ class TriPlaneGenerator(torch.nn.Module):
         return views, plane_img
 
     def _stitch_render_sr(self, ws, c, mesh_condition, texture_feats, static_feats, neural_rendering_resolution,
-                          evaluation, synthesis_kwargs, face_prefix=None):
+                          evaluation, synthesis_kwargs, face_prefix=None, uv_prep=None):
         cam = c[:, -25:]
         if neural_rendering_resolution is None:
             neural_rendering_resolution = self.neural_rendering_resolution
@@ -175,7 +200,7 @@ class TriPlaneGenerator(torch.nn.Module):
 
         # UV rasterize: only the four levels the face backbone consumes (cond_list[0..3], networks_stylegan2_new.py:536-540)
         conds, full_alpha, _ = self._rasterize_nhwc(tex, mesh_condition['uvcoords_image'], static_views, BBOX_256,
-                                                    levels=(0, 1, 2, 3))
+                                                    levels=(0, 1, 2, 3), prep=uv_prep)
         noise_kwargs = {k: v for k, v in synthesis_kwargs.items() if k in ('noise_mode',)}
         stitch = self.face_backbone.synthesis(ws, cond_list=conds[:4], return_list=False, prefix=face_prefix, **noise_kwargs)   # NCHW view
         stitch = rt.to_nhwc(stitch)                                                                          # [B,256,256,32]
@@ -183,7 +208,8 @@ class TriPlaneGenerator(torch.nn.Module):
         # stitch into plane 0 of a copy of the static planes (triplane_v20.py:119-128)
         b0, b1, b2, b3 = BBOX_256
         stitch128 = rt.resize_aa(stitch, 128, 128)
-        alpha128 = rt.resize_aa(full_alpha.unsqueeze(-1), 128, 128).squeeze(-1)
+        alpha128 = uv_prep['alpha128'] if (uv_prep is not None and 'alpha128' in uv_prep) else \
+            rt.resize_aa(full_alpha.unsqueeze(-1), 128, 128).squeeze(-1)
         planes = plane_img.clone()
         win_out = planes[:, b0:b1, b2:b3, :32]
         rt.lerp_alpha(stitch128, plane_img[:, b0:b1, b2:b3, :32], alpha128, out=win_out)
@@ -222,22 +248,29 @@ class TriPlaneGenerator(torch.nn.Module):
             # (FIR epilogues, ToRGB tails, operand preparation: no shared memory, few registers) run on the SMs next to the
             # tensor-core convolutions of the other; join before the rasterizer consumes both.
             cur = torch.cuda.current_stream(ws.device)
-            s_a, s_b = self._side_streams(ws.device)
+            s_a, s_b, s_c = rt.side_streams(ws.device, 3)
             s_a.wait_stream(cur)
             s_b.wait_stream(cur)
+            # third stream: what the rasterizer / stitcher derives from the mesh condition alone (flood fill, alpha resizes) --
+            # small latency-bound launches that fit next to the convolutions
+            s_c.wait_stream(cur)
+            with torch.cuda.stream(s_c):
+                uv_prep = self._uv_prep(mesh_condition['uvcoords_image'], (32, 64, 128), want_alpha128=True)   # levels 0..3 of the texture list
             with torch.cuda.stream(s_a):
                 texture_feats = self.texture_backbone.synthesis(ws, cond_list=None, return_list=True, prefix=pre[0], **noise_kwargs)
             with torch.cuda.stream(s_b):
                 static_feats = self.backbone.synthesis(ws, cond_list=None, return_list=True, prefix=pre[1], **noise_kwargs)
             cur.wait_stream(s_a)
             cur.wait_stream(s_b)
-            for t in list(texture_feats) + list(static_feats):
+            cur.wait_stream(s_c)
+            for t in list(texture_feats) + list(static_feats) + self._prep_tensors(uv_prep):
                 t.record_stream(cur)
         else:
+            uv_prep = None
             texture_feats = self.texture_backbone.synthesis(ws, cond_list=None, return_list=True, prefix=pre[0], **noise_kwargs)
             static_feats = self.backbone.synthesis(ws, cond_list=None, return_list=True, prefix=pre[1], **noise_kwargs)
         out = self._stitch_render_sr(ws, c, mesh_condition, texture_feats, static_feats, neural_rendering_resolution,
-                                     evaluation, synthesis_kwargs, face_prefix=pre[2])
+                                     evaluation, synthesis_kwargs, face_prefix=pre[2], uv_prep=uv_prep)
         if return_featmap:
             out['texture'] = texture_feats
             return out
