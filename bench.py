@@ -155,7 +155,7 @@ def run_reference(args):
             'data': 'synthetic', 'config': workload_config(args, args.gpus),
             'cpu_baseline': {'value': fps, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
             'e2e': {'value': fps, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
-    print(json.dumps(line), flush=True)
+    _emit_line(line)
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -351,11 +351,26 @@ def run_b200(args):
         fps, cores, times = cpu_frames_per_s(args, 1, 2, warmup=1)
         line['cpu_baseline'] = {'value': fps, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                                 'sample': f'1 frame/step x 2 steps of the same workload after 1 warm-up (oracle port of the reference, torch CPU fp32, {cores} threads)'}
-    print(json.dumps(line), flush=True)
+    _emit_line(line)
+
+
+_JSON_OUT = None
+
+
+def _emit_line(line):
+    """The ONE JSON line goes to the process's original stdout; everything else written to fd 1 meanwhile (the NCCL version
+    banner, library chatter) has been routed to stderr by main()."""
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + '\n')
+    out.flush()
 
 
 def main():
+    global _JSON_OUT
     args = parse_args()
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
     if args.impl == 'reference':
         run_reference(args)
     else:
