@@ -137,7 +137,8 @@ typedef struct {
     int32_t GH, GW, ntaps; int32_t dy[9]; int32_t dx[9]; int32_t wtap[9];
     /* output pixel = (gy*sy+py, gx*sx+px) of an [B][OH][OW] image */
     int32_t OH, OW, sy, sx, py, px;
-    /* epilogue: mode 0 = raw accumulator; mode 1 = v = acc*dcoef + noise*strength; v = act(v+bias)*gain, clamp */
+    /* epilogue: mode 0 = raw accumulator; mode 1 = v = acc*dcoef + noise*strength; v = act(v+bias)*gain, clamp;
+     * mode 2 = ToRGB tail (see img_prev below) */
     int32_t mode; const float* dcoef; const float* noise; const float* noise_strength; const float* bias;
     int64_t noise_bstride;   /* 0: one [OH][OW] noise image shared by the batch ('const'); OH*OW: per-sample ('random') */
     int32_t act; float alpha; float gain; float clamp;
@@ -146,6 +147,10 @@ typedef struct {
      * the three backbones): image b belongs to group g = b / imgs_per_group and uses weight taps [g*n_taps_total, ...),
      * bias[g*Cout + co], noise_strength[g] and noise + g*noise_gstride.  groups <= 1: a single set (fields may be 0). */
     int32_t groups; int32_t imgs_per_group; int64_t noise_gstride;
+    /* mode 2 (ia_conv_tc, persistent kernel, emit.out32 only): ToRGB tail fused into the 1x1 convolution --
+     * out = upsample2d(img_prev) + clamp(acc + bias)  (networks_stylegan2_new.py:354-363,456-463; the arithmetic of
+     * ia_torgb_finish, bit for bit).  img_prev: [B][OH/2][OW/2][Cout] fp32 NHWC or NULL. */
+    const float* img_prev;
 } ia_conv_params;
 /* Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05.mma, TMEM accumulators, TMA-fed). */
 int ia_conv_tc(const ia_conv_params* p, void* stream);

@@ -52,7 +52,8 @@ class ConvParams(C.Structure):
                 ('noise_bstride', C.c_int64),
                 ('act', C.c_int32), ('alpha', C.c_float), ('gain', C.c_float), ('clamp', C.c_float),
                 ('emit', Emit),
-                ('groups', C.c_int32), ('imgs_per_group', C.c_int32), ('noise_gstride', C.c_int64)]
+                ('groups', C.c_int32), ('imgs_per_group', C.c_int32), ('noise_gstride', C.c_int64),
+                ('img_prev', c_f32p)]
 
 
 class FirParams(C.Structure):

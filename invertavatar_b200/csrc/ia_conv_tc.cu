@@ -416,6 +416,7 @@ struct Tc2Params {
     int ic, chunk_tiles;           // images per chunk; schedule entries of one chunk = ic * n_tiles * ph_cum[nph]
     int ph_cum[5];                 // ph_cum[q] = sum_{k<q} tiles_x[k] * tiles_y[k]
     int epi_vec4;                  // 1: Cout % 4 == 0 and every output pointer / pitch is 16-byte friendly -> epilogue_chunk_v4
+    const float* img_prev;         // mode 2: previous-resolution image [B][OH/2][OW/2][Cout] (or null)
 };
 
 
@@ -527,6 +528,43 @@ __device__ __forceinline__ void epilogue_chunk_v4(const Tc2Params& p, const floa
             *reinterpret_cast<uint2*>(h2 + o) = make_uint2(h[0] | ((uint32_t)h[1] << 16), h[2] | ((uint32_t)h[3] << 16));
             *reinterpret_cast<uint2*>(l2 + o) = make_uint2(l[0] | ((uint32_t)l[1] << 16), l[2] | ((uint32_t)l[3] << 16));
         }
+    }
+}
+
+// mode 2: ToRGB tail on a [32 rows][32 channels] chunk -- out = upsample2d(img_prev) + clamp(acc + bias), the arithmetic (and
+// the order of operations) of torgb_finish_vec4_kernel in ia_modconv.cu.  `prev` points at this image's img_prev, channel co0.
+__device__ __forceinline__ void epilogue_chunk_v4_torgb(const Tc2Params& p, const float* tsm, int lane, uint32_t vmask, int my_pix,
+                                                        float* o32, const float4 bs, const float* prev) {
+    const int rs = lane >> 3, c4 = lane & 7;
+    const float clampv = p.clamp;
+    const int h2 = p.OH >> 1, w2 = p.OW >> 1;
+#pragma unroll 2
+    for (int i = 0; i < 8; ++i) {
+        const int rr = 4 * i + rs;
+        const int pix_r = __shfl_sync(0xffffffffu, my_pix, rr);
+        if (!((vmask >> rr) & 1u)) continue;
+        float4 v = *reinterpret_cast<const float4*>(tsm + rr * kTsmLd + c4 * 4);
+        v.x += bs.x; v.y += bs.y; v.z += bs.z; v.w += bs.w;
+        if (clampv >= 0.f) {
+            v.x = fminf(fmaxf(v.x, -clampv), clampv); v.y = fminf(fmaxf(v.y, -clampv), clampv);
+            v.z = fminf(fmaxf(v.z, -clampv), clampv); v.w = fminf(fmaxf(v.w, -clampv), clampv);
+        }
+        if (prev) {
+            const int y = pix_r / p.OW, x = pix_r - y * p.OW;
+            const int my = y >> 1, mx = x >> 1;
+            int y0, y1, x0, x1; float wy0, wy1, wx0, wx1;
+            if (y & 1) { y0 = my; y1 = my + 1; wy0 = 0.75f; wy1 = 0.25f; } else { y0 = my - 1; y1 = my; wy0 = 0.25f; wy1 = 0.75f; }
+            if (x & 1) { x0 = mx; x1 = mx + 1; wx0 = 0.75f; wx1 = 0.25f; } else { x0 = mx - 1; x1 = mx; wx0 = 0.25f; wx1 = 0.75f; }
+            float4 up = make_float4(0.f, 0.f, 0.f, 0.f);
+            auto tap = [&](int yy, int xx, float w) {
+                if (yy < 0 || yy >= h2 || xx < 0 || xx >= w2) return;
+                const float4 q = __ldg(reinterpret_cast<const float4*>(prev + ((int64_t)yy * w2 + xx) * p.Cout));
+                up.x = fmaf(w, q.x, up.x); up.y = fmaf(w, q.y, up.y); up.z = fmaf(w, q.z, up.z); up.w = fmaf(w, q.w, up.w);
+            };
+            tap(y0, x0, wy0 * wx0); tap(y0, x1, wy0 * wx1); tap(y1, x0, wy1 * wx0); tap(y1, x1, wy1 * wx1);
+            v.x += up.x; v.y += up.y; v.z += up.z; v.w += up.w;
+        }
+        *reinterpret_cast<float4*>(o32 + (int64_t)pix_r * p.emit.out32_ld) = v;
     }
 }
 
@@ -802,6 +840,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                             if (p.mode == 1) {
                                 if (p.dcoef) dc4 = *reinterpret_cast<const float4*>(p.dcoef + (int64_t)img * p.Cout + co0);
                                 if (bias_g) bs4 = *reinterpret_cast<const float4*>(bias_g + co0);
+                            } else if (p.mode == 2) {
+                                if (bias_g) bs4 = *reinterpret_cast<const float4*>(bias_g + co0);
                             }
                             if (p.emit.hi1 && p.emit.s1) s14 = *reinterpret_cast<const float4*>(p.emit.s1 + (int64_t)img * p.Cout + co0);
                             if (p.emit.hi2 && p.emit.s2) s24 = *reinterpret_cast<const float4*>(p.emit.s2 + (int64_t)img * p.Cout + co0);
@@ -823,7 +863,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                             for (int j = 0; j < 4; ++j)
                                 if (j < p.emit.rgb_n) rg.w[j] = *reinterpret_cast<const float4*>(p.emit.rgb_w + (int64_t)j * p.Cout + co0);
                         }
-                        if (p.mode == 0) epilogue_chunk_v4_dispatch<0>(p, tsm, lane, vm, my_pix, my_nz, o32, h1, l1, h2, l2, dc4, bs4, s14, s24, rg, racc, false);
+                        if (p.mode == 2) {
+                            const float* prev = p.img_prev ? p.img_prev + (int64_t)img * (p.OH >> 1) * (p.OW >> 1) * p.Cout + co0 : nullptr;
+                            epilogue_chunk_v4_torgb(p, tsm, lane, vm, my_pix, o32, bs4, prev);
+                        }
+                        else if (p.mode == 0) epilogue_chunk_v4_dispatch<0>(p, tsm, lane, vm, my_pix, my_nz, o32, h1, l1, h2, l2, dc4, bs4, s14, s24, rg, racc, false);
                         else if (p.act == IA_ACT_LRELU) epilogue_chunk_v4_dispatch<IA_ACT_LRELU>(p, tsm, lane, vm, my_pix, my_nz, o32, h1, l1, h2, l2, dc4, bs4, s14, s24, rg, racc, rgb);
                         else if (p.act == IA_ACT_LINEAR && !rgb) epilogue_chunk_v4_dispatch<IA_ACT_LINEAR>(p, tsm, lane, vm, my_pix, my_nz, o32, h1, l1, h2, l2, dc4, bs4, s14, s24, rg, racc, false);
                         else epilogue_chunk_v4_dispatch<-1>(p, tsm, lane, vm, my_pix, my_nz, o32, h1, l1, h2, l2, dc4, bs4, s14, s24, rg, racc, rgb);
@@ -1080,12 +1124,15 @@ int launch_v2(const ia_conv_params* const* ps, int nph, void* stream) {
         t.epi_vec4 = (p->Cout % 4 == 0) && (!e.out32 || (al16(e.out32) && e.out32_ld % 4 == 0)) &&
                      (!e.hi1 || (al16(e.hi1) && al16(e.lo1) && e.c1_pad % 8 == 0)) && (!e.hi2 || (al16(e.hi2) && al16(e.lo2) && e.c2_pad % 8 == 0)) &&
                      (!p->dcoef || al16(p->dcoef)) && (!p->bias || al16(p->bias)) && (!e.s1 || al16(e.s1)) && (!e.s2 || al16(e.s2));
+        IA_CHECK(p->mode != 2 || (t.epi_vec4 && (!p->img_prev || al16(p->img_prev))),
+                 "ia_conv_tc: the fused ToRGB tail (mode 2) needs the vectorised epilogue (aligned operands, Cout %% 4 == 0)");
+        t.img_prev = p->img_prev;
         IA_CHECK(!e.rgb_out || t.n_tiles <= 2, "ia_conv_tc: the fused ToRGB contraction allows at most two N tiles (Cout_pad %d, N tile %d)", p->Cout_pad, t.n_tile);
         IA_CHECK(!e.rgb_out || (t.epi_vec4 && (!e.rgb_s || al16(e.rgb_s)) && al16(e.rgb_w)),
                  "ia_conv_tc: the fused ToRGB contraction needs the vectorised epilogue (aligned operands, Cout %% 4 == 0)");
         static int force_scalar = -1;
         if (force_scalar < 0) { const char* ev = getenv("IA_CONV_EPI_SCALAR"); force_scalar = (ev && atoi(ev)) ? 1 : 0; }
-        if (force_scalar && !e.rgb_out) t.epi_vec4 = 0;
+        if (force_scalar && !e.rgb_out && p->mode != 2) t.epi_vec4 = 0;
     }
 
     CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
@@ -1161,6 +1208,7 @@ extern "C" int ia_conv_tc(const ia_conv_params* p, void* stream) {
         }
     }
     IA_CHECK(!p->emit.rgb_out, "ia_conv_tc: the fused ToRGB contraction needs the persistent kernel (images of >= 128 pixels, width >= 8)");
+    IA_CHECK(p->mode != 2, "ia_conv_tc: the fused ToRGB tail (mode 2) needs the persistent kernel (images of >= 128 pixels, width >= 8)");
     TcParams t;
     memset(&t, 0, sizeof(t));
     t.B = p->B; t.GH = p->GH; t.GW = p->GW;

@@ -687,7 +687,10 @@ int ia_conv_validate(const ia_conv_params* p, const char* who) {
         IA_CHECK(p->wtap[t] >= 0 && p->wtap[t] < p->n_taps_total, "%s: tap %d weight index out of range", who, t);
     IA_CHECK(p->GH > 0 && p->GW > 0 && p->B > 0 && p->H > 0 && p->W > 0, "%s: empty geometry", who);
     IA_CHECK(p->sy >= 1 && p->sx >= 1, "%s: bad output stride", who);
-    IA_CHECK(p->mode == 0 || p->mode == 1, "%s: bad epilogue mode", who);
+    IA_CHECK(p->mode == 0 || p->mode == 1 || p->mode == 2, "%s: bad epilogue mode", who);
+    IA_CHECK(p->mode != 2 || (p->emit.out32 && !p->emit.hi1 && !p->emit.hi2 && !p->emit.rgb_out && p->sy == 1 && p->sx == 1 && (p->Cout & 3) == 0 &&
+                              (!p->img_prev || ((p->OH & 1) == 0 && (p->OW & 1) == 0))),
+             "%s: mode 2 (ToRGB tail) writes out32 only, stride 1, Cout %% 4 == 0, even output size with img_prev", who);
     IA_CHECK(p->noise == nullptr || p->noise_strength != nullptr, "%s: noise needs noise_strength", who);
     IA_CHECK(p->emit.out32 || p->emit.hi1 || p->emit.hi2 || p->emit.rgb_out, "%s: nothing to emit", who);
     IA_CHECK(!p->emit.rgb_out || (p->emit.rgb_w && p->emit.rgb_n >= 1 && p->emit.rgb_n <= 4 && p->mode == 1 && (p->Cout & 3) == 0 &&
@@ -703,6 +706,7 @@ extern "C" int ia_conv_simt(const ia_conv_params* p, void* stream) {
     if (int rc = ia_conv_validate(p, "ia_conv_simt")) return rc;
     IA_CHECK(p->groups <= 1, "ia_conv_simt: grouped launches are implemented by ia_conv_tc only");
     IA_CHECK(!p->emit.rgb_out, "ia_conv_simt: the fused ToRGB contraction is implemented by ia_conv_tc only");
+    IA_CHECK(p->mode != 2, "ia_conv_simt: the fused ToRGB tail (mode 2) is implemented by ia_conv_tc only");
     int64_t rows = (int64_t)p->B * p->GH * p->GW;
     dim3 grid((unsigned)cdiv(rows, SIMT_TM), (unsigned)cdiv(p->Cout_pad, SIMT_TN));
     ia::prof_begin("ia_conv_simt", as_stream(stream));

@@ -442,7 +442,7 @@ def _set_group(p, group):
 
 
 def conv_same(hi, lo, pack, Cin_pad, out32, dcoef=None, noise=None, noise_strength=None, bias=None, act='linear',
-              gain=1.0, clamp=None, mode=1, impl=None, e1=None, e2=None, group=None, rgb=None):
+              gain=1.0, clamp=None, mode=1, impl=None, e1=None, e2=None, group=None, rgb=None, img_prev=None):
     """k x k correlation, stride 1, 'same' padding (flip_weight=True branch of conv2d_resample, :134-136)."""
     st = _enter(hi)
     B, H, W, _ = hi.shape
@@ -463,8 +463,18 @@ def conv_same(hi, lo, pack, Cin_pad, out32, dcoef=None, noise=None, noise_streng
     p.noise_bstride = _noise_bstride(noise)
     p.act, p.alpha, p.gain, p.clamp = ACT_IDS[act], ACT_DEFAULTS[act][0], float(gain), float(-1 if clamp is None else clamp)
     p.emit = _emit(out32, e1, e2, rgb)
+    if img_prev is not None:
+        assert mode == 2 and img_prev.is_contiguous() and tuple(img_prev.shape) == (B, H // 2, W // 2, pack.Cout), (img_prev.shape, hi.shape)
+        p.img_prev = _p(img_prev)
     _set_group(p, group)
     _conv_call(p, st, impl)
+
+
+def can_fuse_torgb_tail(H, W, Cout, impl=None):
+    """Whether conv_same(..., mode=2) -- ToRGB tail (bias, clamp, + upsampled previous image) inside the 1x1 convolution's
+    epilogue -- is available: tensor-core path, persistent kernel, Cout % 4 == 0."""
+    return ((impl or _conv_impl) == 'tc' and H * W >= 128 and W >= 8 and Cout % 4 == 0 and H % 2 == 0 and W % 2 == 0
+            and os.environ.get('IA_FUSE_TORGB_TAIL', '1') != '0')
 
 
 def can_fuse_torgb(H, W, Cout, n_img, impl=None):

@@ -275,6 +275,12 @@ class ToRGBLayer(torch.nn.Module):
         """``a``: rt.Split holding x*styles of this layer (emitted by the producing convolution's epilogue)."""
         B, H, W, _ = a.hi.shape
         pack = self.pack()
+        if not out_nchw and rt.can_fuse_torgb_tail(H, W, self.out_channels):
+            # bias, clamp and the upsampled previous image are applied by the 1x1 convolution's epilogue (mode 2): no raw
+            # round trip, no ToRGB-tail launch; same arithmetic as ia_torgb_finish
+            img = torch.empty((B, H, W, self.out_channels), dtype=torch.float32, device=a.hi.device)
+            rt.conv_same(a.hi, a.lo, pack, pack.Cin_pad, img, bias=self.bias, clamp=self.conv_clamp, mode=2, img_prev=img_prev)
+            return img
         raw = torch.empty((B, H, W, self.out_channels), dtype=torch.float32, device=a.hi.device)
         rt.conv_same(a.hi, a.lo, pack, pack.Cin_pad, raw, mode=0)
         return rt.torgb_finish(raw, self.bias, self.conv_clamp, img_prev, out_nchw=out_nchw)

@@ -188,3 +188,24 @@ def test_fused_torgb_matches_oracle(monkeypatch):
     monkeypatch.setenv('IA_FUSE_TORGB', '0')
     c = net(ws.to(DEV), noise_mode='const')
     assert maxerr(c, ref) <= TOL * max(1.0, float(ref.abs().max()))
+
+
+def test_fused_torgb_tail_bit_identical(monkeypatch):
+    """ToRGB tail inside the 1x1 convolution's epilogue (mode 2) == 1x1 convolution + ia_torgb_finish, bit for bit (with and
+    without a previous image, 32 and 96 image channels)."""
+    for cin, cimg, res, with_prev in ((128, 32, 32, True), (256, 96, 16, True), (128, 32, 16, False)):
+        torch.manual_seed(cin + cimg)
+        L = sg.ToRGBLayer(cin, cimg, w_dim=64, conv_clamp=0.8).requires_grad_(False)
+        L.bias.copy_(torch.randn(cimg) * 0.3)
+        L = L.to(DEV)
+        B = 3
+        x = torch.randn(B, res, res, cin, device=DEV)
+        st = torch.randn(B, cin, device=DEV)
+        prev = torch.randn(B, res // 2, res // 2, cimg, device=DEV) if with_prev else None
+        hi, lo = rt.modsplit(x, st, C_pad=L.pack().Cin_pad)
+        outs = []
+        for flag in ('1', '0'):
+            monkeypatch.setenv('IA_FUSE_TORGB_TAIL', flag)
+            assert rt.can_fuse_torgb_tail(res, res, cimg) == (flag == '1')
+            outs.append(L.run_split(rt.Split(hi, lo), img_prev=prev).clone())
+        assert torch.equal(outs[0], outs[1]), (cin, cimg, res, with_prev)
