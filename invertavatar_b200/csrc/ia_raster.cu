@@ -1,6 +1,8 @@
 // UV rasterize / stitch kernels: GPU flood fill replacing cv2.floodFill, bilinear grid_sample, antialiased
 // bilinear resize.  Semantics follow reference training_avatar_texture/volumetric_rendering/renderer.py:716-741
 // (fill_mouth), triplane_v20.py:317-339 (rasterize) and the ATen ops they call.
+#include <stdlib.h>
+
 #include "ia_common.cuh"
 
 using namespace ia;
@@ -239,30 +241,42 @@ extern "C" int ia_resize_aa(const ia_resize_params* p, void* stream) {
 // ------------------------------------------------------------------------------------------------
 namespace {
 
-// pass 1: thread = (pixel (b, y, x'), lane); lane owns channel groups c4 = lane + LPP*k, k < KC (LPP lanes per pixel), so
-// every LDG.128 of a warp covers contiguous 16*LPP bytes of one texel and the coordinate / weight arithmetic of a tap is
-// done once per KC*4 loads.
-template <int KC>
+// pass 1: thread = (NX adjacent output pixels (b, y, x'..x'+NX-1), lane); lane owns channel groups c4 = lane + LPP*k, k < KC
+// (LPP lanes per pixel), so every LDG.128 of a warp covers contiguous 16*LPP bytes of one texel and the coordinate / weight
+// arithmetic of a tap is done once per KC*4 loads.  The antialias (triangle) filter of a down-scaling level makes every
+// 256^2 sample a tap of two neighbouring outputs: a thread that owns NX neighbours gathers each sample of their union once
+// (NX = 4: 40 instead of 64 gathers at scale 8) and adds it to each output whose window holds it, in the same ascending-tap
+// order as before -- results are bit-identical to NX = 1.
+template <int KC, int NX>
 __global__ void __launch_bounds__(256) raster_hpass_kernel(ia_raster_level_params p, int lpp) {
-    const int64_t total = (int64_t)p.B * p.UH * p.r * lpp;
+    const int rg = (p.r + NX - 1) / NX;
+    const int64_t total = (int64_t)p.B * p.UH * rg * lpp;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int lane = (int)(i % lpp);
     int64_t t = i / lpp;
-    const int ox = (int)(t % p.r); t /= p.r;
+    const int ox0 = (int)(t % rg) * NX; t /= rg;
     const int y = (int)(t % p.UH); const int b = (int)(t / p.UH);
-    const int xs = p.ux_start[ox], xn = p.ux_count[ox];
-    const float* wx = p.ux_w + (int64_t)ox * p.ux_max_taps;
-    const float* uvrow = p.uv + ((int64_t)(b * p.UH + y) * p.UW + xs) * p.uv_ld;
-    const float* tbase = p.tex + (int64_t)b * p.Ht * p.Wt * p.C + lane * 4;
-    float4 acc[KC];
+    int xs[NX], xn[NX];
+    int x_lo = 1 << 30, x_hi = -(1 << 30);
 #pragma unroll
-    for (int k = 0; k < KC; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < NX; ++j) {
+        const bool on = ox0 + j < p.r;
+        xs[j] = on ? p.ux_start[ox0 + j] : 0;
+        xn[j] = on ? p.ux_count[ox0 + j] : 0;
+        if (on) { x_lo = min(x_lo, xs[j]); x_hi = max(x_hi, xs[j] + xn[j]); }
+    }
+    const float* uvrow = p.uv + (int64_t)(b * p.UH + y) * p.UW * p.uv_ld;
+    const float* tbase = p.tex + (int64_t)b * p.Ht * p.Wt * p.C + lane * 4;
+    float4 acc[NX][KC];
+#pragma unroll
+    for (int j = 0; j < NX; ++j)
+#pragma unroll
+        for (int k = 0; k < KC; ++k) acc[j][k] = make_float4(0.f, 0.f, 0.f, 0.f);
     const int Wi = p.Wt, Hi = p.Ht;
     const int kstride = lpp * 4;
-    for (int tx = 0; tx < xn; ++tx) {
-        const float gx = uvrow[(int64_t)tx * p.uv_ld + 0], gy = uvrow[(int64_t)tx * p.uv_ld + 1];
-        const float w = wx[tx];
+    for (int x = x_lo; x < x_hi; ++x) {
+        const float gx = uvrow[(int64_t)x * p.uv_ld + 0], gy = uvrow[(int64_t)x * p.uv_ld + 1];
         // grid_sample(bilinear, zeros, align_corners=False), same arithmetic as grid_sample_kernel
         const float ix = ((gx + 1.f) * Wi - 1.f) / 2.f;
         const float iy = ((gy + 1.f) * Hi - 1.f) / 2.f;
@@ -289,11 +303,22 @@ __global__ void __launch_bounds__(256) raster_hpass_kernel(ia_raster_level_param
         if (vy1 && vx0) corner(y1, x0, wsw);
         if (vy1 && vx1) corner(y1, x1, wse);
 #pragma unroll
-        for (int k = 0; k < KC; ++k) { acc[k].x += s[k].x * w; acc[k].y += s[k].y * w; acc[k].z += s[k].z * w; acc[k].w += s[k].w * w; }
-    }
-    float* o = p.tmp + ((int64_t)(b * p.UH + y) * p.r + ox) * p.C + lane * 4;
+        for (int j = 0; j < NX; ++j) {
+            const int tx = x - xs[j];
+            if (tx >= 0 && tx < xn[j]) {
+                const float w = p.ux_w[(int64_t)(ox0 + j) * p.ux_max_taps + tx];
 #pragma unroll
-    for (int k = 0; k < KC; ++k) *reinterpret_cast<float4*>(o + k * kstride) = acc[k];
+                for (int k = 0; k < KC; ++k) { acc[j][k].x += s[k].x * w; acc[j][k].y += s[k].y * w; acc[j][k].z += s[k].z * w; acc[j][k].w += s[k].w * w; }
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NX; ++j) {
+        if (ox0 + j >= p.r) continue;
+        float* o = p.tmp + ((int64_t)(b * p.UH + y) * p.r + ox0 + j) * p.C + lane * 4;
+#pragma unroll
+        for (int k = 0; k < KC; ++k) *reinterpret_cast<float4*>(o + k * kstride) = acc[j][k];
+    }
 }
 
 __global__ void __launch_bounds__(256) raster_vpass_kernel(ia_raster_level_params p) {
@@ -358,13 +383,22 @@ extern "C" int ia_raster_level(const ia_raster_level_params* p, void* stream) {
     int kc = 1;
     if (groups % 128 == 0) kc = 4; else if (groups % 64 == 0) kc = 2;
     while (groups / kc > 32 && kc < 4) kc *= 2;
-    IA_CHECK(groups % kc == 0 && groups / kc <= 32, "ia_raster_level: unsupported channel count %d", p->C);
+    { const char* e = getenv("IA_RASTER_KC"); if (e) { const int v = atoi(e); if ((v == 1 || v == 2 || v == 4) && groups % v == 0 && groups / v <= 64) kc = v; } }
+    IA_CHECK(groups % kc == 0 && groups / kc <= 64, "ia_raster_level: unsupported channel count %d", p->C);
     const int lpp = groups / kc;
-    const int64_t total1 = (int64_t)p->B * p->UH * p->r * lpp;
+    // outputs per thread: 4 when the level shrinks the 256^2 samples by >= 4 (neighbouring windows overlap by half), 2 at
+    // scale 2, 1 when every output has its own sample(s); IA_RASTER_NX overrides (1 = the one-output kernel)
+    int nx = p->UW >= 4 * p->r ? 4 : (p->UW >= 2 * p->r ? 2 : 1);
+    { const char* e = getenv("IA_RASTER_NX"); if (e) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) nx = v; } }
+    if (kc == 4 && nx == 4) nx = 2;      // 4 x 4 float4 accumulators + the sample would not fit the register budget
+    const int64_t total1 = (int64_t)p->B * p->UH * cdiv(p->r, nx) * lpp;
+    const unsigned grid1 = (unsigned)cdiv(total1, 256);
     ia::prof_begin("ia_raster_level(hpass)", as_stream(stream));
-    if (kc == 4) raster_hpass_kernel<4><<<(unsigned)cdiv(total1, 256), 256, 0, as_stream(stream)>>>(*p, lpp);
-    else if (kc == 2) raster_hpass_kernel<2><<<(unsigned)cdiv(total1, 256), 256, 0, as_stream(stream)>>>(*p, lpp);
-    else raster_hpass_kernel<1><<<(unsigned)cdiv(total1, 256), 256, 0, as_stream(stream)>>>(*p, lpp);
+#define IA_HPASS(K, N) raster_hpass_kernel<K, N><<<grid1, 256, 0, as_stream(stream)>>>(*p, lpp)
+    if (kc == 4) { if (nx == 2) IA_HPASS(4, 2); else IA_HPASS(4, 1); }
+    else if (kc == 2) { if (nx == 4) IA_HPASS(2, 4); else if (nx == 2) IA_HPASS(2, 2); else IA_HPASS(2, 1); }
+    else { if (nx == 4) IA_HPASS(1, 4); else if (nx == 2) IA_HPASS(1, 2); else IA_HPASS(1, 1); }
+#undef IA_HPASS
     IA_LAUNCH_CHECK("ia_raster_level(hpass)");
     const int64_t total2 = (int64_t)p->B * p->r * p->r * groups;
     ia::prof_begin("ia_raster_level(vpass)", as_stream(stream));
