@@ -110,6 +110,7 @@ typedef struct {
     const float* cond_alpha;                  /* [B][HW] */
     uint16_t* hi; uint16_t* lo;               /* bf16 [B][HW][C_pad] */
     int32_t B, HW, C, C_pad;
+    int64_t out_img_pix;                      /* pixel stride between images of hi / lo (0: HW, dense) */
 } ia_modsplit_params;
 int ia_modsplit(const ia_modsplit_params* p, void* stream);
 
@@ -127,6 +128,9 @@ typedef struct {
      * atomic adds (one per N tile of the launch) into a buffer the caller zero-filled.  ia_conv_tc only, persistent kernel,
      * mode 1, Cout % 4 == 0; NULL: not used. */
     float* rgb_out; const float* rgb_w; const float* rgb_s; int32_t rgb_n;
+    /* Pixel stride between consecutive images of the emit-1 tensors (0: OH*OW, dense).  A consumer that is a stride-2 transposed
+     * convolution takes its operand as [B][H+1][W][C] with a zero row after every image (ia_conv_params.a_img_rows). */
+    int64_t e1_img_pix;
 } ia_emit;
 
 typedef struct {
@@ -151,6 +155,10 @@ typedef struct {
      * out = upsample2d(img_prev) + clamp(acc + bias)  (networks_stylegan2_new.py:354-363,456-463; the arithmetic of
      * ia_torgb_finish, bit for bit).  img_prev: [B][OH/2][OW/2][Cout] fp32 NHWC or NULL. */
     const float* img_prev;
+    /* Rows per image of the A tensors (0: H, dense).  H+1 = every image is followed by one all-zero row: ia_conv_tc_phases then
+     * tiles the [B*(H+1)] x W concatenation of the images instead of every (H+1)-row phase grid on its own (a tile may span two
+     * images; the zero row is the padding between them) -- fewer, fuller tiles.  mode 0, groups <= 1 only. */
+    int32_t a_img_rows;
 } ia_conv_params;
 /* Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05.mma, TMEM accumulators, TMA-fed). */
 int ia_conv_tc(const ia_conv_params* p, void* stream);

@@ -32,14 +32,15 @@ class Upfirdn2dParams(C.Structure):
 class ModsplitParams(C.Structure):
     _fields_ = [('x', c_f32p), ('x_ld', C.c_int64), ('styles', c_f32p), ('cond', c_f32p), ('cond_ld', C.c_int64),
                 ('cond_alpha', c_f32p), ('hi', c_u16p), ('lo', c_u16p),
-                ('B', C.c_int32), ('HW', C.c_int32), ('C', C.c_int32), ('C_pad', C.c_int32)]
+                ('B', C.c_int32), ('HW', C.c_int32), ('C', C.c_int32), ('C_pad', C.c_int32), ('out_img_pix', C.c_int64)]
 
 
 class Emit(C.Structure):
     _fields_ = [('out32', c_f32p), ('out32_ld', C.c_int64),
                 ('hi1', c_u16p), ('lo1', c_u16p), ('s1', c_f32p), ('c1_pad', C.c_int32),
                 ('hi2', c_u16p), ('lo2', c_u16p), ('s2', c_f32p), ('c2_pad', C.c_int32),
-                ('rgb_out', c_f32p), ('rgb_w', c_f32p), ('rgb_s', c_f32p), ('rgb_n', C.c_int32)]
+                ('rgb_out', c_f32p), ('rgb_w', c_f32p), ('rgb_s', c_f32p), ('rgb_n', C.c_int32),
+                ('e1_img_pix', C.c_int64)]
 
 
 class ConvParams(C.Structure):
@@ -53,7 +54,7 @@ class ConvParams(C.Structure):
                 ('act', C.c_int32), ('alpha', C.c_float), ('gain', C.c_float), ('clamp', C.c_float),
                 ('emit', Emit),
                 ('groups', C.c_int32), ('imgs_per_group', C.c_int32), ('noise_gstride', C.c_int64),
-                ('img_prev', c_f32p)]
+                ('img_prev', c_f32p), ('a_img_rows', C.c_int32)]
 
 
 class FirParams(C.Structure):

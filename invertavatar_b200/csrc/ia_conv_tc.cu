@@ -303,11 +303,12 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-int make_act_map(CUtensorMap* m, const void* ptr, int B, int H, int W, int C_pad, int nb, int th, int tw) {
+int make_act_map(CUtensorMap* m, const void* ptr, int B, int H, int W, int C_pad, int nb, int th, int tw, int img_rows = 0) {
     EncodeTiledFn enc = get_encode_fn();
     IA_CHECK(enc, "ia_conv_tc: cuTensorMapEncodeTiled unavailable");
+    if (img_rows < H) img_rows = H;
     cuuint64_t dims[4] = {(cuuint64_t)C_pad, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-    cuuint64_t strides[3] = {(cuuint64_t)C_pad * 2, (cuuint64_t)W * C_pad * 2, (cuuint64_t)H * W * C_pad * 2};
+    cuuint64_t strides[3] = {(cuuint64_t)C_pad * 2, (cuuint64_t)W * C_pad * 2, (cuuint64_t)img_rows * W * C_pad * 2};
     cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)nb};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
@@ -417,6 +418,7 @@ struct Tc2Params {
     int ph_cum[5];                 // ph_cum[q] = sum_{k<q} tiles_x[k] * tiles_y[k]
     int epi_vec4;                  // 1: Cout % 4 == 0 and every output pointer / pitch is 16-byte friendly -> epilogue_chunk_v4
     const float* img_prev;         // mode 2: previous-resolution image [B][OH/2][OW/2][Cout] (or null)
+    int cat_rows, cat_B;           // > 0: the grid rows are the concatenation of cat_B images of cat_rows rows each (see launch_v2)
 };
 
 
@@ -424,10 +426,10 @@ struct Tc2Params {
 // IA_ACT_LINEAR / IA_ACT_LRELU specialised, -1 = any activation through the generic switch.
 template <int ACT>
 __device__ __forceinline__ void epilogue_chunk(const Tc2Params& p, const float* tsm, int lane, uint32_t vmask, int my_pix, float my_nz,
-                                               int64_t img_pix0, int co, bool cvalid, float dc, float bs, float s1v, float s2v) {
+                                               int64_t img_pix0, int64_t img_pix1, int co, bool cvalid, float dc, float bs, float s1v, float s2v) {
     float* o32 = p.emit.out32 ? p.emit.out32 + img_pix0 * p.emit.out32_ld + co : nullptr;
-    uint16_t* h1 = p.emit.hi1 ? p.emit.hi1 + img_pix0 * p.emit.c1_pad + co : nullptr;
-    uint16_t* l1 = p.emit.hi1 ? p.emit.lo1 + img_pix0 * p.emit.c1_pad + co : nullptr;
+    uint16_t* h1 = p.emit.hi1 ? p.emit.hi1 + img_pix1 * p.emit.c1_pad + co : nullptr;
+    uint16_t* l1 = p.emit.hi1 ? p.emit.lo1 + img_pix1 * p.emit.c1_pad + co : nullptr;
     uint16_t* h2 = p.emit.hi2 ? p.emit.hi2 + img_pix0 * p.emit.c2_pad + co : nullptr;
     uint16_t* l2 = p.emit.hi2 ? p.emit.lo2 + img_pix0 * p.emit.c2_pad + co : nullptr;
     const bool has_dc = p.dcoef != nullptr;
@@ -805,17 +807,23 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                 const int row = lg * 32 + lane;
                 const int w_l = row & (p.tw - 1);
                 const int h_l = (row >> tw_shift) + half * th_half;
-                const int gy = y0 + h_l, gx = x0 + w_l;
+                int gy = y0 + h_l;
+                const int gx = x0 + w_l;
+                // concatenated-rows launch: grid row -> (image, row inside the image); the pixel index then carries the image
+                // offset (mode 0 only: no per-image epilogue operand is read) and `img` stays 0
+                int cat_img = 0;
+                if (p.cat_rows > 0) { cat_img = gy / p.cat_rows; gy -= cat_img * p.cat_rows; }
                 const int oy = gy * p.sy + ph.py, ox = gx * p.sx + ph.px;
-                const bool valid = !null_tile && gy < ph.GH && gx < ph.GW && oy < p.OH && ox < p.OW;
+                const bool valid = !null_tile && cat_img < p.cat_B && gy < ph.GH && gx < ph.GW && oy < p.OH && ox < p.OW;
                 const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
-                const int my_pix = oy * p.OW + ox;                     // pixel index inside the image (fits in int)
+                const int my_pix = (cat_img * p.OH + oy) * p.OW + ox;  // pixel index inside the image (fits in int)
                 float my_nz = 0.f;
                 const int grp = img / p.ipg;
                 if (valid && p.mode == 1 && p.noise)
                     my_nz = p.noise[(int64_t)grp * p.noise_gstride + (int64_t)img * p.noise_bstride + my_pix] * p.noise_strength[grp];
                 const float* bias_g = p.bias ? p.bias + (int64_t)grp * p.Cout : nullptr;
                 const int64_t img_pix0 = (int64_t)img * p.OH * p.OW;
+                const int64_t img_pix1 = p.emit.e1_img_pix ? (int64_t)img * p.emit.e1_img_pix : img_pix0;   // emit 1 may be row-padded
                 const uint32_t tcol = (acc * 2u + (uint32_t)half) * (uint32_t)p.acc_stride;
                 const bool rgb = p.emit.rgb_out != nullptr;
                 float racc[8][4];
@@ -849,8 +857,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                         // rows of lanes whose channel group is past Cout are masked out, the shuffles inside stay warp-wide
                         const uint32_t vm = cval ? vmask : 0u;
                         float* o32 = p.emit.out32 ? p.emit.out32 + img_pix0 * p.emit.out32_ld + co0 : nullptr;
-                        uint16_t* h1 = p.emit.hi1 ? p.emit.hi1 + img_pix0 * p.emit.c1_pad + co0 : nullptr;
-                        uint16_t* l1 = p.emit.hi1 ? p.emit.lo1 + img_pix0 * p.emit.c1_pad + co0 : nullptr;
+                        uint16_t* h1 = p.emit.hi1 ? p.emit.hi1 + img_pix1 * p.emit.c1_pad + co0 : nullptr;
+                        uint16_t* l1 = p.emit.hi1 ? p.emit.lo1 + img_pix1 * p.emit.c1_pad + co0 : nullptr;
                         uint16_t* h2 = p.emit.hi2 ? p.emit.hi2 + img_pix0 * p.emit.c2_pad + co0 : nullptr;
                         uint16_t* l2 = p.emit.hi2 ? p.emit.lo2 + img_pix0 * p.emit.c2_pad + co0 : nullptr;
                         RgbLane rg;
@@ -884,10 +892,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                         if (p.emit.hi1 && p.emit.s1) s1v = p.emit.s1[(int64_t)img * p.Cout + co];
                         if (p.emit.hi2 && p.emit.s2) s2v = p.emit.s2[(int64_t)img * p.Cout + co];
                     }
-                    if (p.mode == 0) epilogue_chunk<0>(p, tsm, lane, vmask, my_pix, my_nz, img_pix0, co, cvalid, dc, bs, s1v, s2v);
-                    else if (p.act == IA_ACT_LRELU) epilogue_chunk<IA_ACT_LRELU>(p, tsm, lane, vmask, my_pix, my_nz, img_pix0, co, cvalid, dc, bs, s1v, s2v);
-                    else if (p.act == IA_ACT_LINEAR) epilogue_chunk<IA_ACT_LINEAR>(p, tsm, lane, vmask, my_pix, my_nz, img_pix0, co, cvalid, dc, bs, s1v, s2v);
-                    else epilogue_chunk<-1>(p, tsm, lane, vmask, my_pix, my_nz, img_pix0, co, cvalid, dc, bs, s1v, s2v);
+                    if (p.mode == 0) epilogue_chunk<0>(p, tsm, lane, vmask, my_pix, my_nz, img_pix0, img_pix1, co, cvalid, dc, bs, s1v, s2v);
+                    else if (p.act == IA_ACT_LRELU) epilogue_chunk<IA_ACT_LRELU>(p, tsm, lane, vmask, my_pix, my_nz, img_pix0, img_pix1, co, cvalid, dc, bs, s1v, s2v);
+                    else if (p.act == IA_ACT_LINEAR) epilogue_chunk<IA_ACT_LINEAR>(p, tsm, lane, vmask, my_pix, my_nz, img_pix0, img_pix1, co, cvalid, dc, bs, s1v, s2v);
+                    else epilogue_chunk<-1>(p, tsm, lane, vmask, my_pix, my_nz, img_pix0, img_pix1, co, cvalid, dc, bs, s1v, s2v);
                 }
                 if (rgb && vmask != 0u) {
                     // sum the partial contractions of the 8 lanes that share a row (their 4-channel groups), then lane c4 == 0 adds
@@ -930,11 +938,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
 }
 
 template <int BK>
-int make_act_map2(CUtensorMap* m, const void* ptr, int B, int H, int W, int C_pad, int rows, int tw) {
+int make_act_map2(CUtensorMap* m, const void* ptr, int B, int H, int W, int C_pad, int rows, int tw, int img_rows = 0) {
     EncodeTiledFn enc = get_encode_fn();
     IA_CHECK(enc, "ia_conv_tc: cuTensorMapEncodeTiled unavailable");
+    if (img_rows < H) img_rows = H;      // rows between the starts of consecutive images (row-padded operand layouts)
     cuuint64_t dims[4] = {(cuuint64_t)C_pad, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-    cuuint64_t strides[3] = {(cuuint64_t)C_pad * 2, (cuuint64_t)W * C_pad * 2, (cuuint64_t)H * W * C_pad * 2};
+    cuuint64_t strides[3] = {(cuuint64_t)C_pad * 2, (cuuint64_t)W * C_pad * 2, (cuuint64_t)img_rows * W * C_pad * 2};
     cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)tw, (cuuint32_t)rows, 1u};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
@@ -971,22 +980,30 @@ int launch_v2(const ia_conv_params* const* ps, int nph, void* stream) {
     int GHm = 0, GWm = 0;
     for (int i = 0; i < nph; ++i) { GHm = ps[i]->GH > GHm ? ps[i]->GH : GHm; GWm = ps[i]->GW > GWm ? ps[i]->GW : GWm; }
     t.GH = GHm; t.GW = GWm;
+    // Concatenated rows (ia_conv_params.a_img_rows == H + 1): the operand is [B][H+1][W][C] with a zero row after every image,
+    // so the B phase grids of (H+1) rows each form one tall grid of B*(H+1) rows whose taps never see a neighbouring image's
+    // data (row -1 / row H of an image is a zero row, or outside the tensor).  Tiles then run across image boundaries:
+    // ceil(B*(H+1)/TH) tile rows instead of B*ceil((H+1)/TH).
+    const bool cat = nph > 1 && p->a_img_rows == p->H + 1 && p->mode == 0 && p->groups <= 1 && GHm == p->H + 1;
+    const int rowsB = cat ? p->B * (p->H + 1) : 0;           // rows of the concatenated grid
+    t.cat_rows = cat ? p->H + 1 : 0; t.cat_B = cat ? p->B : 1;
+    if (cat) t.B = 1;
     // tile geometry: 256 pixels as TH x tw with tw in {8,16,32}; fewest tiles wins, ties -> taller tiles (smaller halo share)
     {
         int64_t best = -1;
         const int cand[3][2] = {{32, 8}, {16, 16}, {8, 32}};
         for (int i = 0; i < 3; ++i) {
             int64_t tiles = 0;
-            for (int q = 0; q < nph; ++q) tiles += cdiv(ps[q]->GH, cand[i][0]) * cdiv(ps[q]->GW, cand[i][1]);
+            for (int q = 0; q < nph; ++q) tiles += cdiv(cat ? rowsB : ps[q]->GH, cand[i][0]) * cdiv(ps[q]->GW, cand[i][1]);
             if (best < 0 || tiles < best) { best = tiles; t.TH = cand[i][0]; t.tw = cand[i][1]; }
         }
     }
     t.nph = nph;
-    t.S_tx = (int)cdiv(GWm, t.tw); t.S_ty = (int)cdiv(GHm, t.TH);
+    t.S_tx = (int)cdiv(GWm, t.tw); t.S_ty = (int)cdiv(cat ? rowsB : GHm, t.TH);
     t.tiles_x = t.S_tx; t.tiles_y = t.S_ty;
-    t.m_tiles = t.S_tx * t.S_ty * nph * p->B;          // schedule entries (positions outside a sub-problem's grid are skipped)
+    t.m_tiles = t.S_tx * t.S_ty * nph * t.B;           // schedule entries (positions outside a sub-problem's grid are skipped)
     int64_t real_tiles = 0;
-    for (int q = 0; q < nph; ++q) real_tiles += cdiv(ps[q]->GH, t.TH) * cdiv(ps[q]->GW, t.tw) * p->B;
+    for (int q = 0; q < nph; ++q) real_tiles += cdiv(cat ? rowsB : ps[q]->GH, t.TH) * cdiv(ps[q]->GW, t.tw) * t.B;
     t.Cin_blocks = p->Cin_pad / BK;
     t.Cout = p->Cout; t.Cout_pad = p->Cout_pad;
     int n_tile = 32;
@@ -1020,7 +1037,7 @@ int launch_v2(const ia_conv_params* const* ps, int nph, void* stream) {
         const ia_conv_params* pq = ps[q];
         Tc2Phase& ph = t.ph[q];
         ph.GH = pq->GH; ph.GW = pq->GW; ph.py = pq->py; ph.px = pq->px;
-        ph.tiles_x = (int)cdiv(pq->GW, t.tw); ph.tiles_y = (int)cdiv(pq->GH, t.TH);
+        ph.tiles_x = (int)cdiv(pq->GW, t.tw); ph.tiles_y = (int)cdiv(cat ? rowsB : pq->GH, t.TH);
         ph.ngroups = 0;
         int nt = 0;
         bool used[9] = {false, false, false, false, false, false, false, false, false};
@@ -1082,18 +1099,18 @@ int launch_v2(const ia_conv_params* const* ps, int nph, void* stream) {
     {
         t.ph_cum[0] = 0;
         for (int q = 0; q < nph; ++q) t.ph_cum[q + 1] = t.ph_cum[q] + t.ph[q].tiles_x * t.ph[q].tiles_y;
-        const int64_t total = (int64_t)t.ph_cum[nph] * p->B * t.n_tiles;
+        const int64_t total = (int64_t)t.ph_cum[nph] * t.B * t.n_tiles;
         const int g = total < g_sm_count ? (int)total : g_sm_count;
         const double img_bytes = (double)p->H * p->W * p->Cin_pad * 4.0;
         int best_ic = 1; int64_t best_max = -1;
-        for (int ic = 1; ic <= p->B && nph > 1; ++ic) {
-            if (p->B % ic) continue;
+        for (int ic = 1; ic <= t.B && nph > 1; ++ic) {
+            if (t.B % ic) continue;
             if (ic > 1 && ic * img_bytes > 72e6) break;
             int64_t load[1024];
             const int gg = g < 1024 ? g : 1024;
             for (int i = 0; i < gg; ++i) load[i] = 0;
             int64_t pos = 0;
-            for (int ch = 0; ch < p->B / ic; ++ch)
+            for (int ch = 0; ch < t.B / ic; ++ch)
                 for (int q = 0; q < nph; ++q) {
                     const int64_t L = (int64_t)ic * t.n_tiles * (t.ph_cum[q + 1] - t.ph_cum[q]);
                     const int64_t full = L / gg, rem = L % gg;
@@ -1136,8 +1153,11 @@ int launch_v2(const ia_conv_params* const* ps, int nph, void* stream) {
     }
 
     CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
-    if (int rc = make_act_map2<BK>(&ma_hi, p->a_hi, p->B, p->H, p->W, p->Cin_pad, t.TH + halo, t.tw)) return rc;
-    if (int rc = make_act_map2<BK>(&ma_lo, p->a_lo, p->B, p->H, p->W, p->Cin_pad, t.TH + halo, t.tw)) return rc;
+    // concatenated rows: one image of B*(H+1) rows (the trailing zero row of the last image included); else B images whose
+    // starts are a_img_rows rows apart
+    const int mapB = cat ? 1 : p->B, mapH = cat ? rowsB : p->H, mapR = cat ? rowsB : p->a_img_rows;
+    if (int rc = make_act_map2<BK>(&ma_hi, p->a_hi, mapB, mapH, p->W, p->Cin_pad, t.TH + halo, t.tw, mapR)) return rc;
+    if (int rc = make_act_map2<BK>(&ma_lo, p->a_lo, mapB, mapH, p->W, p->Cin_pad, t.TH + halo, t.tw, mapR)) return rc;
     const int wrows = t.groups * p->n_taps_total * p->Cout_pad;
     if (int rc = make_weight_map2<BK>(&mw_hi, p->w_hi, wrows, p->Cin_pad, n_tile)) return rc;
     if (int rc = make_weight_map2<BK>(&mw_lo, p->w_lo, wrows, p->Cin_pad, n_tile)) return rc;
@@ -1209,6 +1229,7 @@ extern "C" int ia_conv_tc(const ia_conv_params* p, void* stream) {
     }
     IA_CHECK(!p->emit.rgb_out, "ia_conv_tc: the fused ToRGB contraction needs the persistent kernel (images of >= 128 pixels, width >= 8)");
     IA_CHECK(p->mode != 2, "ia_conv_tc: the fused ToRGB tail (mode 2) needs the persistent kernel (images of >= 128 pixels, width >= 8)");
+    IA_CHECK(p->emit.e1_img_pix == 0, "ia_conv_tc: a row-padded emit-1 layout needs the persistent kernel (images of >= 128 pixels, width >= 8)");
     TcParams t;
     memset(&t, 0, sizeof(t));
     t.B = p->B; t.GH = p->GH; t.GW = p->GW;
@@ -1247,8 +1268,8 @@ extern "C" int ia_conv_tc(const ia_conv_params* p, void* stream) {
     t.emit = p->emit;
 
     CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
-    if (int rc = make_act_map(&ma_hi, p->a_hi, p->B, p->H, p->W, p->Cin_pad, t.nb, t.th, t.tw)) return rc;
-    if (int rc = make_act_map(&ma_lo, p->a_lo, p->B, p->H, p->W, p->Cin_pad, t.nb, t.th, t.tw)) return rc;
+    if (int rc = make_act_map(&ma_hi, p->a_hi, p->B, p->H, p->W, p->Cin_pad, t.nb, t.th, t.tw, p->a_img_rows)) return rc;
+    if (int rc = make_act_map(&ma_lo, p->a_lo, p->B, p->H, p->W, p->Cin_pad, t.nb, t.th, t.tw, p->a_img_rows)) return rc;
     const int wrows = t.groups * p->n_taps_total * p->Cout_pad;
     if (int rc = make_weight_map(&mw_hi, p->w_hi, wrows, p->Cin_pad, n_tile)) return rc;
     if (int rc = make_weight_map(&mw_lo, p->w_lo, wrows, p->Cin_pad, n_tile)) return rc;
@@ -1288,7 +1309,7 @@ extern "C" int ia_conv_tc_phases(const ia_conv_params* p, int32_t n, void* strea
             a.Cin_pad != b.Cin_pad || a.Cout != b.Cout || a.Cout_pad != b.Cout_pad || a.n_taps_total != b.n_taps_total || a.OH != b.OH ||
             a.OW != b.OW || a.sy != b.sy || a.sx != b.sx || a.mode != b.mode || a.dcoef != b.dcoef || a.noise != b.noise || a.bias != b.bias ||
             a.act != b.act || a.gain != b.gain || a.clamp != b.clamp || a.emit.out32 != b.emit.out32 || a.emit.hi1 != b.emit.hi1 ||
-            a.emit.hi2 != b.emit.hi2 || a.groups != b.groups || a.imgs_per_group != b.imgs_per_group)
+            a.emit.hi2 != b.emit.hi2 || a.groups != b.groups || a.imgs_per_group != b.imgs_per_group || a.a_img_rows != b.a_img_rows)
             merged = false;
     }
     if (!merged) {

@@ -126,8 +126,9 @@ __global__ void modsplit_kernel(ia_modsplit_params p) {
     uint16_t h[4], l[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) split_bf16(v[k], h[k], l[k]);
-    *reinterpret_cast<uint2*>(p.hi + pix * p.C_pad + c0) = make_uint2(h[0] | ((uint32_t)h[1] << 16), h[2] | ((uint32_t)h[3] << 16));
-    *reinterpret_cast<uint2*>(p.lo + pix * p.C_pad + c0) = make_uint2(l[0] | ((uint32_t)l[1] << 16), l[2] | ((uint32_t)l[3] << 16));
+    const int64_t opix = p.out_img_pix ? (int64_t)b * p.out_img_pix + (pix - (int64_t)b * p.HW) : pix;   // padded image stride
+    *reinterpret_cast<uint2*>(p.hi + opix * p.C_pad + c0) = make_uint2(h[0] | ((uint32_t)h[1] << 16), h[2] | ((uint32_t)h[3] << 16));
+    *reinterpret_cast<uint2*>(p.lo + opix * p.C_pad + c0) = make_uint2(l[0] | ((uint32_t)l[1] << 16), l[2] | ((uint32_t)l[3] << 16));
 }
 
 extern "C" int ia_modsplit(const ia_modsplit_params* p, void* stream) {
@@ -688,6 +689,9 @@ int ia_conv_validate(const ia_conv_params* p, const char* who) {
     IA_CHECK(p->GH > 0 && p->GW > 0 && p->B > 0 && p->H > 0 && p->W > 0, "%s: empty geometry", who);
     IA_CHECK(p->sy >= 1 && p->sx >= 1, "%s: bad output stride", who);
     IA_CHECK(p->mode == 0 || p->mode == 1 || p->mode == 2, "%s: bad epilogue mode", who);
+    IA_CHECK(p->a_img_rows == 0 || p->a_img_rows == p->H || (p->a_img_rows == p->H + 1 && p->mode == 0 && p->groups <= 1),
+             "%s: a_img_rows must be H, or H+1 (zero row after every image) with mode 0 and no groups", who);
+    IA_CHECK(p->emit.e1_img_pix == 0 || p->emit.e1_img_pix >= (int64_t)p->OH * p->OW, "%s: emit-1 image stride smaller than the image", who);
     IA_CHECK(p->mode != 2 || (p->emit.out32 && !p->emit.hi1 && !p->emit.hi2 && !p->emit.rgb_out && p->sy == 1 && p->sx == 1 && (p->Cout & 3) == 0 &&
                               (!p->img_prev || ((p->OH & 1) == 0 && (p->OW & 1) == 0))),
              "%s: mode 2 (ToRGB tail) writes out32 only, stride 1, Cout %% 4 == 0, even output size with img_prev", who);
@@ -707,6 +711,7 @@ extern "C" int ia_conv_simt(const ia_conv_params* p, void* stream) {
     IA_CHECK(p->groups <= 1, "ia_conv_simt: grouped launches are implemented by ia_conv_tc only");
     IA_CHECK(!p->emit.rgb_out, "ia_conv_simt: the fused ToRGB contraction is implemented by ia_conv_tc only");
     IA_CHECK(p->mode != 2, "ia_conv_simt: the fused ToRGB tail (mode 2) is implemented by ia_conv_tc only");
+    IA_CHECK(p->a_img_rows <= p->H && p->emit.e1_img_pix == 0, "ia_conv_simt: padded operand layouts are implemented by ia_conv_tc only");
     int64_t rows = (int64_t)p->B * p->GH * p->GW;
     dim3 grid((unsigned)cdiv(rows, SIMT_TM), (unsigned)cdiv(p->Cout_pad, SIMT_TN));
     ia::prof_begin("ia_conv_simt", as_stream(stream));

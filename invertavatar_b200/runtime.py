@@ -370,37 +370,63 @@ class StylePlan(_EngineCache):
 
 def modsplit(x_nhwc, styles=None, cond=None, cond_alpha=None, C_pad=None):
     """x [B,H,W,C] fp32 (pixel stride = x.stride(2)) -> (hi, lo) bf16 [B,H,W,C_pad] of x*styles (after optional blend)."""
+    sp = modsplit_split(x_nhwc, styles, cond, cond_alpha, C_pad)
+    return sp.hi, sp.lo
+
+
+def modsplit_split(x_nhwc, styles=None, cond=None, cond_alpha=None, C_pad=None, pad_row=False):
+    """modsplit into a Split; pad_row: the row-padded layout of new_split(pad_row=True)."""
     st = _enter(x_nhwc)
     B, H, W, Cc = x_nhwc.shape
     assert x_nhwc.stride(3) == 1 and x_nhwc.stride(1) == W * x_nhwc.stride(2) and x_nhwc.stride(0) == H * x_nhwc.stride(1)
     C_pad = _pad_to(Cc, 64) if C_pad is None else C_pad
-    hi = torch.empty((B, H, W, C_pad), dtype=torch.bfloat16, device=x_nhwc.device)
-    lo = torch.empty_like(hi)
+    sp = new_split(B, H, W, C_pad, x_nhwc.device, pad_row=pad_row)
     cond_ld = 0
     if cond is not None:
         assert cond.shape == x_nhwc.shape and cond.stride(3) == 1 and cond_alpha is not None
         assert cond.stride(1) == W * cond.stride(2) and cond.stride(0) == H * cond.stride(1)
         assert cond_alpha.is_contiguous() and cond_alpha.numel() == B * H * W
         cond_ld = cond.stride(2)
-    p = _C.ModsplitParams(_p(x_nhwc), x_nhwc.stride(2), _p(styles), _p(cond), cond_ld, _p(cond_alpha), _p(hi), _p(lo),
-                          B, H * W, Cc, C_pad)
+    p = _C.ModsplitParams(_p(x_nhwc), x_nhwc.stride(2), _p(styles), _p(cond), cond_ld, _p(cond_alpha), _p(sp.hi), _p(sp.lo),
+                          B, H * W, Cc, C_pad, sp.img_pix)
     _C.check(_C.lib().ia_modsplit(C.byref(p), st), 'ia_modsplit')
-    return hi, lo
+    return sp
 
 
 class Split:
-    """A tensor-core A operand: bf16 hi/lo pair [B,H,W,C_pad] holding x * styles of the consuming layer."""
-    __slots__ = ('hi', 'lo', 'C_pad')
+    """A tensor-core A operand: bf16 hi/lo pair [B,H,W,C_pad] holding x * styles of the consuming layer.  ``img_rows`` > H: the
+    images are ``img_rows`` rows apart in memory and the extra rows are zero (hi / lo are views of the padded buffers) -- the
+    layout a stride-2 transposed convolution tiles across image boundaries (ia_conv_params.a_img_rows)."""
+    __slots__ = ('hi', 'lo', 'C_pad', 'img_rows')
 
-    def __init__(self, hi, lo):
+    def __init__(self, hi, lo, img_rows=None):
         self.hi, self.lo, self.C_pad = hi, lo, hi.shape[-1]
+        self.img_rows = int(hi.shape[1] if img_rows is None else img_rows)
+
+    @property
+    def img_pix(self):
+        """Pixel stride between images (ia_emit.e1_img_pix / ia_modsplit_params.out_img_pix); 0 = dense."""
+        return 0 if self.img_rows == self.hi.shape[1] else self.img_rows * self.hi.shape[2]
 
 
-def new_split(B, H, W, C_pad, device, C=None):
-    """Uninitialised operand buffers; zero-filled when the producer leaves padding channels (C < C_pad) untouched."""
+def pad_row_wanted(H, W, impl=None):
+    """Whether the operand of a stride-2 transposed convolution with H x W input should carry a zero row after every image:
+    tensor-core path and both the consumer's phase grids and the producer are handled by the persistent kernel."""
+    return ((impl or _conv_impl) == 'tc' and H >= 32 and W >= 32 and os.environ.get('IA_CONV_CAT_ROWS', '1') != '0')
+
+
+def new_split(B, H, W, C_pad, device, C=None, pad_row=False):
+    """Uninitialised operand buffers; zero-filled when the producer leaves padding channels (C < C_pad) untouched.
+    pad_row: [B, H+1, W, C_pad] buffers with row H zeroed, exposed as [B, H, W, C_pad] views (see Split)."""
     make = torch.zeros if (C is not None and C != C_pad) else torch.empty
-    hi = make((B, H, W, C_pad), dtype=torch.bfloat16, device=device)
-    lo = make((B, H, W, C_pad), dtype=torch.bfloat16, device=device)
+    rows = H + 1 if pad_row else H
+    hi = make((B, rows, W, C_pad), dtype=torch.bfloat16, device=device)
+    lo = make((B, rows, W, C_pad), dtype=torch.bfloat16, device=device)
+    if pad_row:
+        if make is torch.empty:
+            hi[:, H].zero_()
+            lo[:, H].zero_()
+        return Split(hi[:, :H], lo[:, :H], img_rows=rows)
     return Split(hi, lo)
 
 
@@ -419,6 +445,7 @@ def _emit(out32=None, e1=None, e2=None, rgb=None):
     if e1 is not None:
         sp, st = e1
         e.hi1, e.lo1, e.s1, e.c1_pad = _p(sp.hi), _p(sp.lo), _p(st), sp.C_pad
+        e.e1_img_pix = sp.img_pix
     if e2 is not None:
         sp, st = e2
         e.hi2, e.lo2, e.s2, e.c2_pad = _p(sp.hi), _p(sp.lo), _p(st), sp.C_pad
@@ -484,7 +511,7 @@ def can_fuse_torgb(H, W, Cout, n_img, impl=None):
             and os.environ.get('IA_FUSE_TORGB', '1') != '0')
 
 
-def conv_transpose_up2_raw(hi, lo, pack, Cin_pad, raw, impl=None, group=None):
+def conv_transpose_up2_raw(hi, lo, pack, Cin_pad, raw, impl=None, group=None, img_rows=0):
     """Stride-2 transposed 3x3 convolution (true convolution, conv2d_resample.py:114-127) written as four output-parity
     phases; raw is [B, 2H+1, 2W+1, Cout] fp32.  Even output row 2m gets ky=0 from input row m and ky=2 from row m-1; odd
     output row 2m+1 gets ky=1 from row m (same for columns)."""
@@ -511,6 +538,7 @@ def conv_transpose_up2_raw(hi, lo, pack, Cin_pad, raw, impl=None, group=None):
             p.mode = 0
             p.act, p.alpha, p.gain, p.clamp = 1, 0.0, 1.0, -1.0
             p.emit = _emit(raw)
+            p.a_img_rows = int(img_rows) if img_rows and img_rows != H else 0
             _set_group(p, group)
     if (impl or _conv_impl) == 'tc':
         _C.check(_C.lib().ia_conv_tc_phases(phases, 4, st), 'ia_conv_tc_phases')     # one persistent launch for the four phases
@@ -536,6 +564,7 @@ def fir4x4_gain4(device):
 
 
 def fir_epilogue(raw, fir, out32, dcoef, noise, noise_strength, bias, act, gain, clamp, e1=None, e2=None, group=None):
+    assert e1 is None or e1[0].img_pix == 0, 'fir_epilogue writes dense operands only'
     st = _enter(raw)
     B, RH, RW, Cc = raw.shape
     OH, OW = RH - 1, RW - 1

@@ -199,12 +199,13 @@ class SynthesisLayer(torch.nn.Module):
         R = self.resolution
         out = torch.empty((B, R, R, self.out_channels), dtype=torch.float32, device=a.hi.device) if want32 else None
         if self.up == 1:
+            assert a.img_pix == 0, 'a row-padded operand feeds transposed convolutions only'
             rt.conv_same(a.hi, a.lo, pack, pack.Cin_pad, out, dcoef=dcoef, noise=noise, noise_strength=strength, bias=self.bias,
                          act=self.activation, gain=act_gain, clamp=act_clamp, mode=1, e1=e1, e2=e2, rgb=rgb)
         else:
             assert rgb is None
             raw = torch.empty((B, 2 * H + 1, 2 * W + 1, self.out_channels), dtype=torch.float32, device=a.hi.device)
-            rt.conv_transpose_up2_raw(a.hi, a.lo, pack, pack.Cin_pad, raw)
+            rt.conv_transpose_up2_raw(a.hi, a.lo, pack, pack.Cin_pad, raw, img_rows=a.img_rows)
             rt.fir_epilogue(raw, rt.fir4x4_gain4(a.hi.device), out, dcoef, noise, strength, self.bias, self.activation,
                             act_gain, act_clamp, e1=e1, e2=e2)
         return out
@@ -403,7 +404,8 @@ class SynthesisBlock(torch.nn.Module):
         fuse_rgb = (has_rgb and not want_x32 and self.torgb.weight.shape[2] == 1 and
                     rt.can_fuse_torgb(R, R, self.conv1.out_channels, self.torgb.out_channels))
         a_rgb = rt.new_split(B, R, R, self.torgb.pack().Cin_pad, dev, C=self.torgb.in_channels) if (has_rgb and not fuse_rgb) else None
-        a_next = rt.new_split(B, R, R, next_conv.pack().Cin_pad, dev, C=next_conv.in_channels) if next_conv is not None else None
+        a_next = rt.new_split(B, R, R, next_conv.pack().Cin_pad, dev, C=next_conv.in_channels,
+                              pad_row=next_conv.up == 2 and rt.pad_row_wanted(R, R)) if next_conv is not None else None
         rgb_raw = torch.zeros((B, R, R, self.torgb.out_channels), dtype=torch.float32, device=dev) if fuse_rgb else None
         x32 = self.conv1.run_split(a1, dcoefs[i], noise_mode=noise_mode, gain=gain, want32=want_x32,
                                    e1=(a_next, next_styles) if a_next is not None else None,
@@ -529,8 +531,8 @@ class SynthesisNetwork(torch.nn.Module):
                     if blend_next and has_next:
                         cnd, cal = _split_cond(cond_list[1 + index - start_layer])
                         nxt = blocks[index + 1].conv0
-                        hi, lo = rt.modsplit(x32, styles[spans[index + 1][0]], cond=cnd, cond_alpha=cal, C_pad=nxt.pack().Cin_pad)
-                        a = rt.Split(hi, lo)
+                        a = rt.modsplit_split(x32, styles[spans[index + 1][0]], cond=cnd, cond_alpha=cal, C_pad=nxt.pack().Cin_pad,
+                                              pad_row=nxt.up == 2 and rt.pad_row_wanted(x32.shape[1], x32.shape[2]))
         if return_list:
             x_list.append(rt.from_nhwc(img))
             return x_list
@@ -650,7 +652,9 @@ def synthesis_prefix_grouped(nets, ws, noise_mode='const', upto_res=32):
         packr = rt.ConvPackGroup.current(rgbs[0], '_ia_gpack', [t.weight for t in rgbs], need_wsq=False)
         a_rgb = rt.new_split(G * B, res, res, packr.Cin_pad, dev, C=rgbs[0].in_channels)
         nxt = [getattr(n, f'b{nets[0].block_resolutions[index + 1]}').conv0 for n in nets]
-        a_next = rt.new_split(G * B, res, res, nxt[0].pack().Cin_pad, dev, C=nxt[0].in_channels)
+        # the operand that leaves the prefix feeds each network's own (ungrouped) transposed convolution: row-padded layout
+        a_next = rt.new_split(G * B, res, res, nxt[0].pack().Cin_pad, dev, C=nxt[0].in_channels,
+                              pad_row=last and nxt[0].up == 2 and rt.pad_row_wanted(res, res))
         x32 = torch.empty((G * B, res, res, pack1.Cout), dtype=torch.float32, device=dev) if last else None
         nz, ns, gs = layer_noise(conv1s)
         rt.conv_same(a1.hi, a1.lo, pack1, pack1.Cin_pad, x32, dcoef=cat_layer(lo_i + i, 1), noise=nz, noise_strength=ns,
@@ -668,7 +672,7 @@ def synthesis_prefix_grouped(nets, ws, noise_mode='const', upto_res=32):
         im = img[sl]
         if n.img_channels != im.shape[-1]:
             im = im[..., :n.img_channels].contiguous()
-        out.append(dict(index=k_last, x32=x32[sl], img=im, a_next=rt.Split(a_next.hi[sl], a_next.lo[sl]),
+        out.append(dict(index=k_last, x32=x32[sl], img=im, a_next=rt.Split(a_next.hi[sl], a_next.lo[sl], img_rows=a_next.img_rows),
                         styles=passes[g][0], dcoefs=passes[g][1], spans=passes[g][2]))
     return out
 

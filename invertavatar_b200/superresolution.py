@@ -33,8 +33,8 @@ class _SuperresolutionBase(torch.nn.Module):
                   [layer.style_entry(j) for j, (_, layer) in enumerate(b1.layers())]
         styles, dcoefs = _plan_for(self, entries).run(ws.to(torch.float32))
         n0 = len(b0.layers())
-        hi, lo = rt.modsplit(x, styles[0], C_pad=b0.conv0.pack().Cin_pad)
-        _, rgb, a = b0.run_chain(rt.Split(hi, lo), rgb, styles[:n0], dcoefs[:n0], B, noise_mode=noise_mode, next_conv=b1.conv0,
+        a0 = rt.modsplit_split(x, styles[0], C_pad=b0.conv0.pack().Cin_pad, pad_row=rt.pad_row_wanted(x.shape[1], x.shape[2]))
+        _, rgb, a = b0.run_chain(a0, rgb, styles[:n0], dcoefs[:n0], B, noise_mode=noise_mode, next_conv=b1.conv0,
                                  next_styles=styles[n0])
         _, rgb, _ = b1.run_chain(a, rgb, styles[n0:], dcoefs[n0:], B, noise_mode=noise_mode, img_nchw=True)
         return rgb

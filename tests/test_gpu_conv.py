@@ -209,3 +209,29 @@ def test_fused_torgb_tail_bit_identical(monkeypatch):
             assert rt.can_fuse_torgb_tail(res, res, cimg) == (flag == '1')
             outs.append(L.run_split(rt.Split(hi, lo), img_prev=prev).clone())
         assert torch.equal(outs[0], outs[1]), (cin, cimg, res, with_prev)
+
+
+def test_row_padded_operand_layout_bit_identical(monkeypatch):
+    """Transposed convolutions fed with the row-padded operand layout ([B][H+1][W][C], zero row after every image: tiles of the
+    phase grids run across image boundaries) give bit-identical results to the dense layout -- producers: conv epilogue (emit 1
+    image stride), grouped-free chain, modsplit with blend; 3 images so that tiles straddle two images."""
+    torch.manual_seed(21)
+    net = sg.SynthesisNetwork(w_dim=64, img_resolution=128, img_channels=8, channel_base=2560, channel_max=40, num_fp16_res=0,
+                              conv_clamp=None).requires_grad_(False)
+    for n, p in net.named_parameters():
+        if n.endswith('noise_strength'):
+            p.fill_(0.2)
+    g = torch.Generator().manual_seed(4)
+    ws = torch.randn(3, net.num_ws, 64, generator=g).to(DEV)
+    conds = [torch.cat([torch.randn(3, c, r, r, generator=g), torch.rand(3, 1, r, r, generator=g)], 1).to(DEV)
+             for (c, r) in ((8, 32), (40, 32), (40, 64))]
+    net = net.to(DEV)
+    outs = {}
+    for flag in ('1', '0'):
+        monkeypatch.setenv('IA_CONV_CAT_ROWS', flag)
+        assert rt.pad_row_wanted(32, 32) == (flag == '1') and not rt.pad_row_wanted(16, 16)
+        a = net(ws, return_list=True, out_res=(32, 128), noise_mode='const')
+        b = net(ws, cond_list=conds, return_list=False, out_res=(32, 128), noise_mode='const')
+        outs[flag] = [t.clone() for t in a] + [b.clone()]
+    for x, y in zip(outs['1'], outs['0']):
+        assert torch.equal(x, y)
