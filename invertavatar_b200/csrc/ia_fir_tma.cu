@@ -66,7 +66,7 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 
-template <int ACT>
+template <int ACT, bool NPF>     // NPF: noise loaded one emission ahead (see fir_epilogue_x2_kernel)
 __global__ void __launch_bounds__(FT_THREADS, 3) fir_tma_kernel(const __grid_constant__ CUtensorMap tm_raw, const ia_fir_params p, int cchunks) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
@@ -143,6 +143,9 @@ __global__ void __launch_bounds__(FT_THREADS, 3) fir_tma_kernel(const __grid_con
     const uint32_t o32row = (uint32_t)p.OW * o32ld, r1row = (uint32_t)p.OW * c1p, r2row = (uint32_t)p.OW * c2p;
     const bool has32 = p.emit.out32 != nullptr, has1 = p.emit.hi1 != nullptr, has2 = p.emit.hi2 != nullptr;
 
+    float nq = 0.f;                                       // NPF: noise of the next output row to be emitted
+    int nrows_left = oy1 - oy0;
+    if (NPF && nptr) { nq = nptr[0]; nptr += p.OW; --nrows_left; }
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     float4 acc0 = z4, acc1 = z4, acc2 = z4;               // output rows ry-2, ry-1, ry
     const float* my = ring + xl * FT_CC + c4 * 4;         // column ox-1 of the box = raw column ox0-1+xl
@@ -171,7 +174,14 @@ __global__ void __launch_bounds__(FT_THREADS, 3) fir_tma_kernel(const __grid_con
             if (ry - 2 >= oy0 && ry - 2 < oy1) {          // output row ry-2 is complete
                 if (active) {
                     float nz = 0.f;
-                    if (nptr) { nz = nptr[0] * nstr; nptr += p.OW; }
+                    if (nptr) {
+                        if (NPF) {
+                            nz = nq * nstr;
+                            if (nrows_left > 0) { nq = nptr[0]; nptr += p.OW; --nrows_left; }
+                        } else {
+                            nz = nptr[0] * nstr; nptr += p.OW;
+                        }
+                    }
                     const float a4[4] = {acc0.x, acc0.y, acc0.z, acc0.w};
                     float v[4];
 #pragma unroll
@@ -266,14 +276,22 @@ int fir_tma_launch(const ia_fir_params* p, void* stream) {
     const size_t smem = (size_t)FT_STAGES * FT_STAGE_BYTES + 128 + 8 * 2 * FT_STAGES;
     dim3 grid((unsigned)(p->OW / FT_XT), (unsigned)cdiv(p->OH, FT_YT), (unsigned)(p->B * cchunks));
     cudaError_t e;
-#define IA_FIR_LAUNCH(A)                                                                                                     \
-    e = cudaFuncSetAttribute(fir_tma_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                     \
+    bool npf = false;
+    { const char* ev = getenv("IA_FIR_NOISE_PREFETCH"); if (ev && atoi(ev) != 0) npf = true; }
+#define IA_FIR_LAUNCH(A, N)                                                                                                  \
+    e = cudaFuncSetAttribute(fir_tma_kernel<A, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                  \
     IA_CHECK(e == cudaSuccess, "ia_fir_epilogue: cudaFuncSetAttribute: %s", cudaGetErrorString(e));                          \
     ia::prof_begin("ia_fir_epilogue", as_stream(stream));                                                                    \
-    fir_tma_kernel<A><<<grid, FT_THREADS, smem, as_stream(stream)>>>(tm, *p, cchunks)
-    if (p->act == IA_ACT_LRELU) { IA_FIR_LAUNCH(IA_ACT_LRELU); }
-    else if (p->act == IA_ACT_LINEAR) { IA_FIR_LAUNCH(IA_ACT_LINEAR); }
-    else { IA_FIR_LAUNCH(-1); }
+    fir_tma_kernel<A, N><<<grid, FT_THREADS, smem, as_stream(stream)>>>(tm, *p, cchunks)
+    if (npf) {
+        if (p->act == IA_ACT_LRELU) { IA_FIR_LAUNCH(IA_ACT_LRELU, true); }
+        else if (p->act == IA_ACT_LINEAR) { IA_FIR_LAUNCH(IA_ACT_LINEAR, true); }
+        else { IA_FIR_LAUNCH(-1, true); }
+    } else {
+        if (p->act == IA_ACT_LRELU) { IA_FIR_LAUNCH(IA_ACT_LRELU, false); }
+        else if (p->act == IA_ACT_LINEAR) { IA_FIR_LAUNCH(IA_ACT_LINEAR, false); }
+        else { IA_FIR_LAUNCH(-1, false); }
+    }
 #undef IA_FIR_LAUNCH
     IA_LAUNCH_CHECK("ia_fir_epilogue");
     return 0;

@@ -320,7 +320,10 @@ __global__ void __launch_bounds__(256, 3) fir_epilogue_kernel(ia_fir_params p, i
 // reads in flight per SM, about a third of what the HBM latency-bandwidth product asks for -- it ran at 3.3 TB/s, issue- and
 // latency-bound rather than bandwidth-bound (profiles/r1_fir_full_v3.txt).  Here a thread reads 5 neighbouring float4 per
 // raw row for 2 outputs (2.5 loads per output instead of 4) and prefetches two rows ahead (64 B unique per thread in flight).
-template <int ACT>
+// NPF (opt-in, IA_FIR_NOISE_PREFETCH=1): the noise value of an output row is loaded one emission ahead instead of in the iteration
+// that consumes it (ncu: 34 % of this kernel's stall samples sit on that consumer, profiles/r1_fir_x2_full_v6.txt); same values,
+// same arithmetic.  Off by default until it has been run against the test-suite on hardware.
+template <int ACT, bool NPF>
 __global__ void __launch_bounds__(256, 2) fir_epilogue_x2_kernel(ia_fir_params p, int cg, int xt, int cchunks) {
     const int c4 = threadIdx.x % cg;
     const int xl = threadIdx.x / cg;
@@ -367,6 +370,9 @@ __global__ void __launch_bounds__(256, 2) fir_epilogue_x2_kernel(ia_fir_params p
     const uint32_t o32row = (uint32_t)p.OW * o32ld, r1row = (uint32_t)p.OW * c1p, r2row = (uint32_t)p.OW * c2p;
     const bool has32 = p.emit.out32 != nullptr, has1 = p.emit.hi1 != nullptr, has2 = p.emit.hi2 != nullptr;
     const float gain = p.gain, alpha = p.alpha, clampv = p.clamp;
+    float nq0 = 0.f, nq1 = 0.f;                           // NPF: noise of the next output row to be emitted
+    int nrows_left = oy1 - oy0;                           // NPF: output rows whose noise has not been requested yet
+    if (NPF && nptr) { nq0 = nptr[0]; nq1 = nptr[1]; nptr += p.OW; --nrows_left; }
     float4 ra[5], rb[5];                                  // the next two raw rows, in flight while the current one is consumed
     auto load_row = [&](float4 (&r)[5], int ry, const float* q) {
 #pragma unroll
@@ -389,7 +395,14 @@ __global__ void __launch_bounds__(256, 2) fir_epilogue_x2_kernel(ia_fir_params p
         if (ry + 2 <= oy1 + 1) load_row(rb, ry + 2, rp + 2 * row_f);
         float nz0 = 0.f, nz1 = 0.f;
         const bool emit_row = ry - 2 >= oy0;              // output row ry-2 (< oy1 by the loop bound) completes with this raw row
-        if (emit_row && nptr) { nz0 = nptr[0] * nstr; nz1 = nptr[1] * nstr; nptr += p.OW; }
+        if (emit_row && nptr) {
+            if (NPF) {
+                nz0 = nq0 * nstr; nz1 = nq1 * nstr;
+                if (nrows_left > 0) { nq0 = nptr[0]; nq1 = nptr[1]; nptr += p.OW; --nrows_left; }
+            } else {
+                nz0 = nptr[0] * nstr; nz1 = nptr[1] * nstr; nptr += p.OW;
+            }
+        }
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             float4 h;
@@ -467,9 +480,17 @@ extern "C" int ia_fir_epilogue(const ia_fir_params* p, void* stream) {
                        out_pix * (p->emit.hi2 ? p->emit.c2_pad : 0) < (1ll << 31);
     if (x2 && (p->OW & 1) == 0 && small) {
         dim3 grid((unsigned)cdiv(p->OW / 2, xt), (unsigned)cdiv(p->OH, FIR_YT), (unsigned)(p->B * cchunks));
-        if (p->act == IA_ACT_LRELU) fir_epilogue_x2_kernel<IA_ACT_LRELU><<<grid, 256, 0, as_stream(stream)>>>(*p, cg, xt, cchunks);
-        else if (p->act == IA_ACT_LINEAR) fir_epilogue_x2_kernel<IA_ACT_LINEAR><<<grid, 256, 0, as_stream(stream)>>>(*p, cg, xt, cchunks);
-        else fir_epilogue_x2_kernel<-1><<<grid, 256, 0, as_stream(stream)>>>(*p, cg, xt, cchunks);
+        bool npf = false;
+        { const char* e = getenv("IA_FIR_NOISE_PREFETCH"); if (e && atoi(e) != 0) npf = true; }
+        if (npf) {
+            if (p->act == IA_ACT_LRELU) fir_epilogue_x2_kernel<IA_ACT_LRELU, true><<<grid, 256, 0, as_stream(stream)>>>(*p, cg, xt, cchunks);
+            else if (p->act == IA_ACT_LINEAR) fir_epilogue_x2_kernel<IA_ACT_LINEAR, true><<<grid, 256, 0, as_stream(stream)>>>(*p, cg, xt, cchunks);
+            else fir_epilogue_x2_kernel<-1, true><<<grid, 256, 0, as_stream(stream)>>>(*p, cg, xt, cchunks);
+        } else {
+            if (p->act == IA_ACT_LRELU) fir_epilogue_x2_kernel<IA_ACT_LRELU, false><<<grid, 256, 0, as_stream(stream)>>>(*p, cg, xt, cchunks);
+            else if (p->act == IA_ACT_LINEAR) fir_epilogue_x2_kernel<IA_ACT_LINEAR, false><<<grid, 256, 0, as_stream(stream)>>>(*p, cg, xt, cchunks);
+            else fir_epilogue_x2_kernel<-1, false><<<grid, 256, 0, as_stream(stream)>>>(*p, cg, xt, cchunks);
+        }
         IA_LAUNCH_CHECK("ia_fir_epilogue");
         return 0;
     }

@@ -1,4 +1,6 @@
 """Regressions found on the GPU."""
+import os
+
 import pytest
 import torch
 
@@ -75,7 +77,12 @@ def test_fir_epilogue_variants_agree(monkeypatch, B, OH, C, use32, use1, use2):
     noise, strength = torch.randn(OH, OH, generator=g).cuda(), torch.tensor(0.3).cuda()
     s1, s2 = torch.randn(B, C, generator=g).cuda(), torch.randn(B, C, generator=g).cuda()
     outs = {}
-    for name, env in (('tma', {'IA_FIR_TMA': '1'}), ('x2', {'IA_FIR_TMA': '0', 'IA_FIR_X2': '1'}), ('x1', {'IA_FIR_TMA': '0', 'IA_FIR_X2': '0'})):
+    variants = [('tma', {'IA_FIR_TMA': '1'}), ('x2', {'IA_FIR_TMA': '0', 'IA_FIR_X2': '1'}), ('x1', {'IA_FIR_TMA': '0', 'IA_FIR_X2': '0'})]
+    if os.environ.get('IA_TEST_OPTIN'):      # opt-in code paths that have not been through the suite on hardware yet
+        variants += [('x2_npf', {'IA_FIR_TMA': '0', 'IA_FIR_X2': '1', 'IA_FIR_NOISE_PREFETCH': '1'}),
+                     ('tma_npf', {'IA_FIR_TMA': '1', 'IA_FIR_NOISE_PREFETCH': '1'})]
+    for name, env in variants:
+        monkeypatch.setenv('IA_FIR_NOISE_PREFETCH', '0')
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         out = torch.zeros(B, OH, OH, C, device='cuda') if use32 else None
@@ -85,7 +92,7 @@ def test_fir_epilogue_variants_agree(monkeypatch, B, OH, C, use32, use1, use2):
                         e1=(e1, s1) if use1 else None, e2=(e2, s2) if use2 else None)
         torch.cuda.synchronize()
         outs[name] = [t.clone() for t in ([out] if use32 else []) + ([e1.hi, e1.lo] if use1 else []) + ([e2.hi, e2.lo] if use2 else [])]
-    for name in ('x2', 'x1'):
+    for name in outs:
         for a, b in zip(outs['tma'], outs[name]):
             assert torch.equal(a, b), name
 
