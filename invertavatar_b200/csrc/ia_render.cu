@@ -9,6 +9,7 @@
 // (project_onto_planes / sample_from_planes), ray_sampler.py:70-107 (RaySampler_zxc), ray_marcher.py:25-57
 // (MipRayMarcher2) and triplane_v20.py:415-438 (OSGDecoder).
 #include <math_constants.h>
+#include <stdlib.h>
 
 #include "ia_common.cuh"
 
@@ -167,6 +168,11 @@ __device__ __forceinline__ void plane_gather8(const float* __restrict__ plane_ba
 // (mma.sync m16n8k16, fp16 hi/lo split operands, fp32 accumulate).  Lane (g = lane/4, t = lane%4) gathers 8 channels of
 // samples 16m+g and 16m+g+8 straight into its A fragment; layer 1's C fragments become layer 2's A fragments in
 // registers.  Colours go to col[sample][channel], sigma to sig[sample].
+// MLP1 (opt-in, IA_RENDER_MLP=fp16): both decoder layers as single-pass fp16 products (fp32 accumulate) instead of the 3-term
+// hi/lo split -- a third of the mma.sync and none of the lo-fragment arithmetic.  CPU probe with the oracle
+// (tools/probe_render_precision.py): 1.2e-4 max-abs / 94 dB on the final image, inside the 1e-3 bar but outside the 2e-5 the
+// op-level renderer tests hold the feature image to; off by default, not yet run on hardware.
+template <bool MLP1>
 __device__ __forceinline__ void gather_mlp_pass(const ia_render_params& p, const float* __restrict__ planes_b, const Ray& r,
                                                 const float* dep, float* col, float* sig, int s0, int n, int lane,
                                                 const DecoderFrags* __restrict__ dec) {
@@ -200,8 +206,10 @@ __device__ __forceinline__ void gather_mlp_pass(const ia_render_params& p, const
                 for (int q = 0; q < 4; ++q) split_half(feat[rr][4 * ks + q], h[rr][q], l[rr][q]);
             ah[ks][0] = pack_half2(h[0][0], h[0][1]); ah[ks][1] = pack_half2(h[1][0], h[1][1]);
             ah[ks][2] = pack_half2(h[0][2], h[0][3]); ah[ks][3] = pack_half2(h[1][2], h[1][3]);
-            al[ks][0] = pack_half2(l[0][0], l[0][1]); al[ks][1] = pack_half2(l[1][0], l[1][1]);
-            al[ks][2] = pack_half2(l[0][2], l[0][3]); al[ks][3] = pack_half2(l[1][2], l[1][3]);
+            if (!MLP1) {
+                al[ks][0] = pack_half2(l[0][0], l[0][1]); al[ks][1] = pack_half2(l[1][0], l[1][1]);
+                al[ks][2] = pack_half2(l[0][2], l[0][3]); al[ks][3] = pack_half2(l[1][2], l[1][3]);
+            }
         }
         float hid[8][4];
 #pragma unroll
@@ -210,11 +218,15 @@ __device__ __forceinline__ void gather_mlp_pass(const ia_render_params& p, const
             float c[4] = {bb0, bb1, bb0, bb1};
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
-                const uint2 bh = dec->w1f[((nt * 2 + ks) * 2 + 0) * 32 + lane];
-                const uint2 bl = dec->w1f[((nt * 2 + ks) * 2 + 1) * 32 + lane];
-                mma_f16(c, ah[ks], bh);
-                mma_f16(c, ah[ks], bl);
-                mma_f16(c, al[ks], bh);
+                if (MLP1) {
+                    mma_f16(c, ah[ks], dec->w1f[((nt * 2 + ks) * 2 + 0) * 32 + lane]);
+                } else {
+                    const uint2 bh = dec->w1f[((nt * 2 + ks) * 2 + 0) * 32 + lane];
+                    const uint2 bl = dec->w1f[((nt * 2 + ks) * 2 + 1) * 32 + lane];
+                    mma_f16(c, ah[ks], bh);
+                    mma_f16(c, ah[ks], bl);
+                    mma_f16(c, al[ks], bh);
+                }
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) hid[nt][q] = softplus_fast(c[q]);
@@ -235,11 +247,15 @@ __device__ __forceinline__ void gather_mlp_pass(const ia_render_params& p, const
             const uint32_t a2l[4] = {pack_half2(l[0], l[1]), pack_half2(l[2], l[3]), pack_half2(l[4], l[5]), pack_half2(l[6], l[7])};
 #pragma unroll
             for (int nt = 0; nt < 5; ++nt) {
-                const uint2 bh = dec->w2f[((nt * 4 + ks) * 2 + 0) * 32 + lane];
-                const uint2 bl = dec->w2f[((nt * 4 + ks) * 2 + 1) * 32 + lane];
-                mma_f16(out[nt], a2h, bh);
-                mma_f16(out[nt], a2h, bl);
-                mma_f16(out[nt], a2l, bh);
+                if (MLP1) {
+                    mma_f16(out[nt], a2h, dec->w2f[((nt * 4 + ks) * 2 + 0) * 32 + lane]);
+                } else {
+                    const uint2 bh = dec->w2f[((nt * 4 + ks) * 2 + 0) * 32 + lane];
+                    const uint2 bl = dec->w2f[((nt * 4 + ks) * 2 + 1) * 32 + lane];
+                    mma_f16(out[nt], a2h, bh);
+                    mma_f16(out[nt], a2h, bl);
+                    mma_f16(out[nt], a2l, bh);
+                }
             }
         }
         // ---- write back: rows g (c0,c1) and g+8 (c2,c3); columns nt*8 + 2t, +1 ----
@@ -295,6 +311,7 @@ __device__ __forceinline__ void march_weights(const float* d, const float* sg, f
     wsum = ws; dnum = dn;
 }
 
+template <bool MLP1>
 __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1) render_kernel(const ia_render_params p) {
     const int kWarpsPerCta = blockDim.x >> 5;
     extern __shared__ __align__(16) float smem[];
@@ -346,7 +363,7 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1) render_kernel(const i
             dmin = fminf(dmin, t); dmax = fmaxf(dmax, t);
         }
         __syncwarp();
-        gather_mlp_pass(p, planes_b, r, dep, col, sig, 0, p.Dc, lane, dec);
+        gather_mlp_pass<MLP1>(p, planes_b, r, dep, col, sig, 0, p.Dc, lane, dec);
         __syncwarp();
 
         int n_all = p.Dc;
@@ -407,7 +424,7 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1) render_kernel(const i
                 dmin = fminf(dmin, t); dmax = fmaxf(dmax, t);
             }
             __syncwarp();
-            gather_mlp_pass(p, planes_b, r, dep, col, sig, p.Dc, p.Df, lane, dec);
+            gather_mlp_pass<MLP1>(p, planes_b, r, dep, col, sig, p.Dc, p.Df, lane, dec);
             __syncwarp();
             // ---- merge: stable rank of every sample among all S (unify_samples, renderer.py:372-382) ----
             // Both lists are normally already sorted (coarse: jitter < bin width; fine: deterministic u), in which case the
@@ -585,19 +602,24 @@ extern "C" int ia_render(const ia_render_params* p, void* stream) {
     if (kWarpsPerCta > kMaxWarpsPerCta) kWarpsPerCta = kMaxWarpsPerCta;
     IA_CHECK(kWarpsPerCta >= 1, "ia_render: shared memory request too large");
     const size_t smem = sizeof(DecoderFrags) + per_warp * kWarpsPerCta * sizeof(float);
-    e = cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    bool mlp1 = false;      // IA_RENDER_MLP=fp16: single-pass fp16 decoder (opt-in, see gather_mlp_pass)
+    { const char* ev = getenv("IA_RENDER_MLP"); if (ev && strcmp(ev, "fp16") == 0) mlp1 = true; }
+    e = mlp1 ? cudaFuncSetAttribute(render_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+             : cudaFuncSetAttribute(render_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     IA_CHECK(e == cudaSuccess, "ia_render: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     int dev = 0, sms = 148, per_sm = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_kernel, kWarpsPerCta * 32, smem);
+    if (mlp1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_kernel<true>, kWarpsPerCta * 32, smem);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_kernel<false>, kWarpsPerCta * 32, smem);
     if (per_sm < 1) per_sm = 1;
     int64_t total_rays = (int64_t)p->B * p->res * p->res;
     int64_t want = cdiv(total_rays, kWarpsPerCta);
     int64_t grid = (int64_t)sms * per_sm;
     if (grid > want) grid = want;
     ia::prof_begin("ia_render", st);
-    render_kernel<<<(unsigned)grid, kWarpsPerCta * 32, smem, st>>>(*p);
+    if (mlp1) render_kernel<true><<<(unsigned)grid, kWarpsPerCta * 32, smem, st>>>(*p);
+    else render_kernel<false><<<(unsigned)grid, kWarpsPerCta * 32, smem, st>>>(*p);
     IA_LAUNCH_CHECK("ia_render");
     return 0;
 }

@@ -114,3 +114,22 @@ def test_prepack_builds_every_pack_once():
     for m in G.modules():
         if id(m) in packs:
             assert m.__dict__['_ia_pack'] is packs[id(m)]
+
+
+@pytest.mark.skipif(not os.environ.get('IA_TEST_OPTIN'), reason='opt-in code path (IA_RENDER_MLP=fp16), not yet validated on hardware')
+def test_single_pass_decoder_within_north_star(monkeypatch):
+    """IA_RENDER_MLP=fp16 (decoder MLP as single-pass fp16 MMAs): the final image stays within the north-star tolerance of the default
+    3-term path (CPU probe: 1.2e-4 max-abs, tools/probe_render_precision.py)."""
+    import copy
+    G = copy.deepcopy(build_generator(16, 16)).to('cuda')
+    z, cond, c, uv = synth.latents(2).cuda(), synth.frontal_camera(2).cuda(), synth.cameras(2).cuda(), synth.uvcoords_image(2).cuda()
+    jit = synth.depth_jitter(2, 64 * 64, 16).cuda()
+    outs = {}
+    with torch.no_grad():
+        ws = G.mapping(z, cond, truncation_psi=0.7, truncation_cutoff=14)
+        for mode in ('fp32x3', 'fp16'):
+            monkeypatch.setenv('IA_RENDER_MLP', mode)
+            outs[mode] = G.synthesis(ws, c, {'uvcoords_image': uv}, neural_rendering_resolution=64, noise_mode='const', evaluation=True,
+                                     depth_jitter=jit)['image'].clone()
+    err = float((outs['fp16'] - outs['fp32x3']).abs().max())
+    assert 0 < err <= 5e-4, err
