@@ -271,7 +271,8 @@ def main():
             print('synthesis_c1.npz', len(out))
         if 'c2' in want:  # headline shape: 128^2 x (48+48), two different frames
             out = {}
-            golden_synthesis(out, 'c2', 128, 48, 48, 2)
+            G, ws, _ = golden_synthesis(out, 'c2', 128, 48, 48, 2)
+            golden_with_texture(out, 'c2_withtex', G, ws, 128, 48, 48)   # eval_seq.py per-frame driver at the headline size
             np.savez_compressed(os.path.join(HERE, 'synthesis_c2.npz'), **out)
             print('synthesis_c2.npz', len(out))
 

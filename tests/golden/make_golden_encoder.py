@@ -1,7 +1,9 @@
 """Mint golden vectors of the inversion encoder by executing the UNMODIFIED reference
 ``encoder_inversion.models.uvnet.inversionNet`` (read-only tree at /root/reference) on CPU.
 
-    python tests/golden/make_golden_encoder.py     # writes tests/golden/encoder.npz  (build container only)
+    python tests/golden/make_golden_encoder.py        # writes tests/golden/encoder.npz     (T=2, 64^2 x 16+16: small, fast)
+    python tests/golden/make_golden_encoder.py c3     # writes tests/golden/encoder_c3.npz  (BASELINE configs[2]: T=4, 128^2 x 48+48)
+(build container only)
 
 Mode flags follow eval_seq.py:91-97: the whole inversionNet in train mode, then ``input_layer`` / ``body`` of the two
 UNets back to eval -- e4e and the UNet decoders normalise with batch statistics.  The two random draws of the T-frame
@@ -21,6 +23,10 @@ from fingerprint import fingerprint, pack  # noqa: E402
 from invertavatar_b200 import synth  # noqa: E402
 
 T, RES, DC, DF = 2, 64, 16, 16
+NAME = 'encoder.npz'
+if 'c3' in sys.argv[1:]:      # BASELINE configs[2] at its stated size (train-mode BatchNorm over 4 frames, 48 random-u importance samples)
+    T, RES, DC, DF = 4, 128, 48, 48
+    NAME = 'encoder_c3.npz'
 
 
 def build_reference_inversion_net():
@@ -71,8 +77,8 @@ def main():
             for n in range(2):
                 for i, t in enumerate(r_list[n]):
                     pack(f'{tag}/r{n}_{i}', fingerprint(t), out)
-    np.savez_compressed(os.path.join(HERE, 'encoder.npz'), **out)
-    print('encoder.npz', len(out))
+    np.savez_compressed(os.path.join(HERE, NAME), **out)
+    print(NAME, len(out))
 
 
 if __name__ == '__main__':

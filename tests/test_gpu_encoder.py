@@ -21,12 +21,19 @@ def rel_err(got, ref):
     return float((got.float().cpu() - ref).abs().max()) / max(1.0, float(ref.abs().max()))
 
 
+# encoder.npz: T=2, 64^2 x 16+16; encoder_c3.npz: BASELINE configs[2] at its stated size (T=4, 128^2 x 48+48)
+NPZ = ['encoder.npz', 'encoder_c3.npz']
+
+
+def _net_for(npz):
+    g = golden(npz)
+    T, res, Dc, Df = [int(v) for v in g['enc/meta']]
+    return copy.deepcopy(build_inversion_net(Dc, Df, res)).to(DEV)
+
+
 @pytest.fixture(scope='module')
 def net():
-    g = golden('encoder.npz')
-    T, res, Dc, Df = [int(v) for v in g['enc/meta']]
-    n = copy.deepcopy(build_inversion_net(Dc, Df, res)).to(DEV)
-    return n
+    return _net_for('encoder.npz')
 
 
 def _sd(module):
@@ -82,11 +89,12 @@ def test_recurrent_up_and_gru_vs_oracle(net):
             assert rel_err(got, want) < 2e-4 and rel_err(got_r, want_r) < 2e-4
 
 
-def test_encode_golden(net):
-    g = golden('encoder.npz')
+@pytest.mark.parametrize('npz', NPZ)
+def test_encode_golden(npz):
+    g = golden(npz)
     x, _, _ = synth.encoder_inputs(int(g['enc/meta'][0]))
     img = x['image'][:1].to(DEV)
-    n = copy.deepcopy(net)
+    n = _net_for(npz)
     with torch.no_grad():
         n.encoder.eval()
         ws_eval = n.encode(img)
@@ -96,11 +104,14 @@ def test_encode_golden(net):
     assert rel_err(ws_train, torch.from_numpy(g['enc/ws_train'])) < RTOL
 
 
-def test_ar_eval_forward_golden(net):
-    """eval_seq.py:164-190: e4e features, then two AR_eval_forward calls (the second carries the ConvGRU states)."""
-    g = golden('encoder.npz')
+@pytest.mark.parametrize('npz', NPZ)
+def test_ar_eval_forward_golden(npz):
+    """eval_seq.py:164-190: e4e features, then two AR_eval_forward calls (the second carries the ConvGRU states).
+    encoder_c3.npz is BASELINE configs[2] at its stated size: train-mode BatchNorm statistics over T=4 frames and the
+    evaluation=False random-u sort of 48 importance samples per ray."""
+    g = golden(npz)
     T, res, Dc, Df = [int(v) for v in g['enc/meta']]
-    n = copy.deepcopy(net)
+    n = _net_for(npz)
     x, c, v = synth.encoder_inputs(T)
     x = {k: t.to(DEV) for k, t in x.items()}
     c = c.to(DEV)

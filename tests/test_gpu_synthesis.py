@@ -24,8 +24,23 @@ def _run(tag, npz, stages=True):
     ws = G.mapping(z, cond, truncation_psi=0.7, truncation_cutoff=14)
     assert float((ws.cpu() - torch.from_numpy(g[f'{tag}/ws'])).abs().max()) <= 1e-5
     jit = synth.depth_jitter(B, res * res, Dc).to(DEV)
-    out = G.synthesis(ws, c, {'uvcoords_image': uv}, neural_rendering_resolution=res, noise_mode='const', evaluation=bool(ev),
-                      depth_jitter=jit, return_featmap=True)
+    # the stage boundaries the reference does not return are taken the way make_golden.py takes them from the reference:
+    # forward hooks on the static / face backbones, and the public rasterize() for the six rendering images
+    cap = {}
+    h1 = G.face_backbone.synthesis.register_forward_hook(lambda m, i, o: cap.__setitem__('stitch', o))
+    h2 = G.backbone.synthesis.register_forward_hook(lambda m, i, o: cap.__setitem__('static', list(o)))
+    try:
+        out = G.synthesis(ws, c, {'uvcoords_image': uv}, neural_rendering_resolution=res, noise_mode='const', evaluation=bool(ev),
+                          depth_jitter=jit, return_featmap=True)
+    finally:
+        h1.remove(); h2.remove()
+    if stages:
+        sta = list(cap['static'])
+        out['static'] = sta
+        out['stitch'] = cap['stitch']
+        sf = list(sta)
+        sf[0], sf[-1] = sf[0][:, :32], sf[-1][:, :32]          # plane 0 of the 96-channel images (triplane_v20.py:109-112)
+        out['rendering_images'], out['full_alpha'], _ = G.rasterize(out['texture'], uv, sf, [57, 185, 64, 192])
     return g, G, ws, out
 
 
@@ -33,6 +48,15 @@ def _check(g, tag, out):
     errs = {}
     for i, t in enumerate(out['texture']):
         errs[f'texture{i}'] = compare(t, unpack(f'{tag}/texture{i}', g), STAGE_ATOL * max(1.0, float(np.abs(g[f'{tag}/texture{i}/sub']).max())), f'texture{i}')[0]
+    def scaled(name):
+        return STAGE_ATOL * max(1.0, float(np.abs(g[f'{tag}/{name}/sub']).max()))
+    for i, t in enumerate(out.get('static', [])):
+        errs[f'static{i}'] = compare(t, unpack(f'{tag}/static{i}', g), scaled(f'static{i}'), f'static{i}')[0]
+    for i, t in enumerate(out.get('rendering_images', [])):
+        errs[f'rendering_image{i}'] = compare(t, unpack(f'{tag}/rendering_image{i}', g), scaled(f'rendering_image{i}'), f'rendering_image{i}')[0]
+    if 'full_alpha' in out:
+        errs['full_alpha'] = compare(out['full_alpha'], unpack(f'{tag}/full_alpha', g), 1e-6, 'full_alpha')[0]
+        errs['stitch'] = compare(out['stitch'], unpack(f'{tag}/stitch', g), scaled('stitch'), 'stitch')[0]
     errs['triplane'] = compare(out['triplane'], unpack(f'{tag}/triplane', g), STAGE_ATOL * max(1.0, float(np.abs(g[f'{tag}/triplane/sub']).max())), 'triplane')[0]
     errs['feature_image'] = compare(out['feature_image'], unpack(f'{tag}/feature_image', g), IMAGE_ATOL, 'feature_image')[0]
     errs['image_raw'] = compare(out['image_raw'], unpack(f'{tag}/image_raw', g), IMAGE_ATOL, 'image_raw')[0]
@@ -71,9 +95,45 @@ def test_synthesis_c1_psnr_vs_oracle():
 
 
 def test_synthesis_c2_golden():
-    """Headline shape 128^2 x (48+48), two different frames in one batch."""
+    """Headline shape 128^2 x (48+48), two different frames in one batch; then the per-frame driver of eval_seq.py
+    (synthesis_withTexture, evaluation=False with pinned u) at the same size."""
     g, G, ws, out = _run('c2', 'synthesis_c2.npz')
     _check(g, 'c2', out)
+    ws1 = ws[:1]
+    tex = G.texture_backbone.synthesis(ws1, cond_list=None, return_list=True, noise_mode='const')
+    sta = G.backbone.synthesis(ws1, cond_list=None, return_list=True, noise_mode='const')
+    o = G.synthesis_withTexture(ws1, tex, synth.cameras(1, first=3).to(DEV), {'uvcoords_image': synth.uvcoords_image(1, first=3).to(DEV)},
+                                static_feats=sta, noise_mode='const', evaluation=False,
+                                depth_jitter=synth.depth_jitter(1, 128 * 128, 48, seed=8).to(DEV),
+                                importance_u=synth.importance_u(1, 128 * 128, 48, seed=12).to(DEV))
+    for k in ('image', 'image_raw', 'image_depth'):
+        e = compare(o[k], unpack(f'c2_withtex/{k}', g), IMAGE_ATOL, 'c2_withtex/' + k)[0]
+        print(f'c2_withtex {k}: {e:.2e}')
+
+
+def test_synthesis_c2_batch8_full_image_vs_oracle():
+    """BASELINE configs[1] exactly as bench.py runs it (batch 8, 128^2 x 48+48): every pixel of all 8 frames against the
+    oracle run on this host -- max-abs <= 1e-3 and PSNR > 50 dB (north_star), per frame and over the batch."""
+    B, res, D = 8, 128, 48
+    G = build_generator(D, D).to(DEV)
+    z, cond, c, uv = synth.latents(B), synth.frontal_camera(B), synth.cameras(B), synth.uvcoords_image(B)
+    jit = synth.depth_jitter(B, res * res, D)
+    with torch.no_grad():
+        ws = G.mapping(z.to(DEV), cond.to(DEV), truncation_psi=0.7, truncation_cutoff=14)
+        out = G.synthesis(ws, c.to(DEV), {'uvcoords_image': uv.to(DEV)}, neural_rendering_resolution=res, noise_mode='const',
+                          evaluation=True, depth_jitter=jit.to(DEV))
+        img = out['image'].float().cpu()
+        sd = {k: v.cpu() for k, v in G.state_dict().items()}
+        ws_ref = o_tp.mapping(sd, z, cond, G.rendering_kwargs, truncation_psi=0.7, truncation_cutoff=14)
+        ref = o_tp.synthesis(sd, ws_ref, c, uv, G.rendering_kwargs, jit, evaluation=True, neural_rendering_resolution=res)
+    assert tuple(img.shape) == (B, 3, 512, 512)
+    per_frame = [(float((img[i] - ref['image'][i]).abs().max()), psnr(img[i], ref['image'][i])) for i in range(B)]
+    err = max(e for e, _ in per_frame)
+    p = psnr(img, ref['image'])
+    print(f'c2 batch 8 full image: max-abs {err:.3e}  PSNR {p:.1f} dB  per frame ' + ' '.join(f'{e:.1e}/{q:.0f}' for e, q in per_frame))
+    assert err <= IMAGE_ATOL and min(q for _, q in per_frame) > 50.0
+    assert float((out['image_raw'].float().cpu() - ref['image_raw']).abs().max()) <= IMAGE_ATOL
+    assert float((out['image_depth'].float().cpu() - ref['image_depth']).abs().max()) <= IMAGE_ATOL
 
 
 def test_synthesis_batch_invariance():

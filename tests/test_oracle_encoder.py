@@ -1,6 +1,7 @@
 """CPU: the encoder oracle (oracle/encoder.py) against golden vectors minted from the unmodified reference
 (tests/golden/make_golden_encoder.py), and the product modules' state-dict against the reference's."""
 import numpy as np
+import pytest
 import torch
 
 from common import build_inversion_net, golden, state_hash
@@ -12,8 +13,12 @@ from oracle import stylegan2 as o_sg
 ATOL = 2e-4   # fp32 reassociation across ~60 stacked convolutions (the reference itself moves by this much between thread counts)
 
 
-def _setup():
-    g = golden('encoder.npz')
+# encoder.npz: T=2, 64^2 x 16+16 (small); encoder_c3.npz: BASELINE configs[2] at its stated size (T=4, 128^2 x 48+48)
+NPZ = ['encoder.npz', 'encoder_c3.npz']
+
+
+def _setup(npz='encoder.npz'):
+    g = golden(npz)
     T, res, Dc, Df = [int(v) for v in g['enc/meta']]
     net = build_inversion_net(Dc, Df, res)
     return g, net, T, res, Dc, Df
@@ -25,8 +30,9 @@ def test_state_dict_matches_reference():
         'inversionNet construction does not reproduce the reference parameters (names, order or values differ)'
 
 
-def test_encode_golden():
-    g, net, T, res, Dc, Df = _setup()
+@pytest.mark.parametrize('npz', NPZ)
+def test_encode_golden(npz):
+    g, net, T, res, Dc, Df = _setup(npz)
     sd = net.state_dict()
     x, c, v = synth.encoder_inputs(T)
     with torch.no_grad():
@@ -37,8 +43,9 @@ def test_encode_golden():
     assert np.abs(ws_eval.numpy() - g['enc/ws_eval']).max() <= ATOL * max(1.0, float(np.abs(g['enc/ws_eval']).max()))
 
 
-def test_ar_eval_forward_golden():
-    g, net, T, res, Dc, Df = _setup()
+@pytest.mark.parametrize('npz', NPZ)
+def test_ar_eval_forward_golden(npz):
+    g, net, T, res, Dc, Df = _setup(npz)
     sd = net.state_dict()
     x, c, v = synth.encoder_inputs(T)
     ws = torch.from_numpy(g['enc/ws_train'])

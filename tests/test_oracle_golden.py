@@ -152,3 +152,12 @@ def test_synthesis_c2_golden():
     """Headline shape: 128^2 x (48+48), two frames with different latents / cameras / UV conditions."""
     g, G, sd, ws, out = _oracle_synthesis('c2', 'synthesis_c2.npz')
     _check_stages(g, 'c2', out, 5e-5)
+    # eval_seq.py per-frame driver at the headline size (synthesis_withTexture, evaluation=False -> 48 random-u importance samples)
+    ws1 = ws[:1]
+    tex = o_sg.synthesis_network(o_sg.sub(sd, 'texture_backbone.synthesis'), ws1, return_list=True)
+    sta = o_sg.synthesis_network(o_sg.sub(sd, 'backbone.synthesis'), ws1, return_list=True)
+    o = o_tp.synthesis_with_texture(sd, ws1, tex, synth.cameras(1, first=3), synth.uvcoords_image(1, first=3), G.rendering_kwargs,
+                                    synth.depth_jitter(1, 128 * 128, 48, seed=8), static_feats=sta, evaluation=False,
+                                    u=synth.importance_u(1, 128 * 128, 48, seed=12), neural_rendering_resolution=128)
+    for k in ('image', 'image_raw', 'image_depth'):
+        compare(o[k], unpack(f'c2_withtex/{k}', g), 5e-5, 'c2_withtex/' + k)
