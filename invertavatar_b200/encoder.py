@@ -124,7 +124,7 @@ class bottleneck_IR_SE(Module):
         if isinstance(self.shortcut_layer, Sequential):
             conv_s, bn_s = self.shortcut_layer
             a, _ = rt.enc_prep([xs], C_pad=rt.ConvPack.current(conv_s, '_ia_pack', conv_s.weight, need_wsq=False).Cin_pad)
-            raw_s = rt.enc_conv(a, conv_s)
+            raw_s = rt.enc_conv(a, conv_s, alg_stride=1)      # operand already sub-sampled
             rs, rsh = rt.enc_bn_fold(bn_s, [raw_s])
             return rt.enc_affine_act(raw2, scale=sc4, shift=sh4, gate=gate, res=raw_s, res_scale=rs, res_shift=rsh)
         return rt.enc_affine_act(raw2, scale=sc4, shift=sh4, gate=gate, res=xs)

@@ -52,16 +52,25 @@ class PeerFrameGather:
     frames straight into slot ``rank`` of every rank's copy (``runtime.frame_sink``), so the image gather of SURVEY 8(e) is
     the epilogue of the producing kernel plus one cross-rank barrier, not a separate NCCL collective.  Uses the NVSwitch
     multicast mapping (multimem.st: one store, replicated in the switch) when the allocation has one, plain stores to the
-    peer mappings otherwise.  ``available()`` is False when symmetric memory cannot be set up; callers then fall back to
-    ``gather_frames`` (NCCL)."""
+    peer mappings otherwise.  Symmetric memory that cannot be set up raises; callers then fall back to ``gather_frames``
+    (NCCL).
+
+    The allocation is DOUBLE-BUFFERED: step i writes buffer i & 1 and ``barrier()`` flips.  Contract: after ``barrier()``
+    returns, ``tensor`` is the gathered batch of the step just closed; it stays intact until this rank's stream reaches the
+    NEXT ``barrier()`` -- a consumer (D2H copy, encoder) must be enqueued on the stream that calls ``barrier()``, or be waited
+    for by it, before that next call.  Why that is enough: the buffer of step i is overwritten by the producing kernels of
+    step i+2, which rank A launches after it passed barrier i+1 on the device, and a barrier completes only when every rank's
+    stream has reached it -- i.e. after everything those ranks enqueued before it, their reads of step i included.  (With a
+    single buffer, A's step i+1 kernel, ordered only after barrier i, could overwrite slot A in B's copy while B -- which
+    enqueues its reads of step i AFTER barrier i -- is still reading.)"""
 
     def __init__(self, frames_per_rank, shape=(3, 512, 512), device=None, group=None, multicast=True):
         import torch.distributed._symmetric_memory as symm_mem
         self.group = group if group is not None else dist.group.WORLD
         self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
         self.per_rank = int(frames_per_rank) * int(shape[0]) * int(shape[1]) * int(shape[2])
-        self.tensor = symm_mem.empty((self.world * frames_per_rank,) + tuple(shape), dtype=torch.float32, device=device)
-        self.handle = symm_mem.rendezvous(self.tensor, self.group)
+        self.buffers = symm_mem.empty((2, self.world * frames_per_rank) + tuple(shape), dtype=torch.float32, device=device)
+        self.handle = symm_mem.rendezvous(self.buffers, self.group)
         self.peer_ptrs = [int(q) for q in self.handle.buffer_ptrs]
         mc = 0
         try:
@@ -70,11 +79,22 @@ class PeerFrameGather:
         except Exception:
             mc = 0
         self.mc_ptr = mc
+        self.buf_elems = self.world * self.per_rank
+        self.cur = 0          # buffer the next sink() writes
+        self.last = 0         # buffer closed by the most recent barrier()
+
+    @property
+    def tensor(self):
+        """[world*B,3,H,W] gathered frames of the step closed by the most recent ``barrier()``."""
+        return self.buffers[self.last]
 
     def sink(self):
         from . import runtime as rt
-        return rt.frame_sink(self.peer_ptrs, self.rank * self.per_rank, self.mc_ptr)
+        off = self.cur * self.buf_elems + self.rank * self.per_rank
+        return rt.frame_sink(self.peer_ptrs, off, self.mc_ptr, capacity=self.per_rank)
 
     def barrier(self):
-        """All ranks' frame writes are visible in every copy after this (enqueued on the current stream)."""
+        """All ranks' frame writes of this step are visible in every copy after this (enqueued on the current stream); the
+        next ``sink()`` targets the other buffer."""
         self.handle.barrier(channel=0)
+        self.last, self.cur = self.cur, self.cur ^ 1

@@ -8,9 +8,11 @@ pickles use the same record layout (``type='class'``, ``version``, ``module_src`
 persistence.py:120-128,181-206), so ``legacy.load_network_pkl`` can load them through this module, and the
 scripts' "reload" idiom ``Cls(*obj.init_args, **obj.init_kwargs)`` + ``copy_params_and_buffers`` works."""
 import copy
+import importlib
 import inspect
 import io
 import pickle
+import re
 import sys
 import types
 import uuid
@@ -61,16 +63,42 @@ def _module_source(module):
     return src
 
 
-def _module_from_source(src):
+def _module_from_source(src, package=None):
     module = _module_by_src.get(src)
     if module is None:
         name = '_imported_module_' + uuid.uuid4().hex
         module = types.ModuleType(name)
+        if package:
+            # the engine's own modules use relative imports (``from . import runtime``): give the rebuilt module the package
+            # they resolve against, otherwise exec() fails with "attempted relative import with no known parent package"
+            importlib.import_module(package)
+            module.__package__ = package
         sys.modules[name] = module
         _src_by_module[module] = src
         _module_by_src[src] = module
         exec(src, module.__dict__)  # the pickled module text (reference behaviour, persistence.py:216-229)
     return module
+
+
+def _class_by_name(module_name, class_name, src):
+    """The class as importable in THIS process (a fresh process that never imported the defining module included).  Used when
+    the recorded module is one of this package's and its source is the one that was pickled -- otherwise the pickled source
+    text is authoritative (reference behaviour)."""
+    if not module_name or not module_name.split('.')[0] == __name__.split('.')[0]:
+        return None
+    try:
+        module = importlib.import_module(module_name)
+    except Exception:
+        return None
+    cls = getattr(module, class_name, None)
+    if not isinstance(cls, type):
+        return None
+    try:
+        if src and _module_source(module) != src:
+            return None            # the module changed since the pickle was written: rebuild from the pickled text
+    except (OSError, TypeError):
+        pass
+    return cls
 
 
 def _assert_pickleable(obj):
@@ -104,6 +132,7 @@ def persistent_class(orig_class):
     class Decorator(orig_class):
         _orig_module_src = orig_src
         _orig_class_name = orig_class.__name__
+        _orig_module_name = orig_class.__module__
 
         def __init__(self, *args, **kwargs):
             super().__init__(*args, **kwargs)
@@ -122,8 +151,10 @@ def persistent_class(orig_class):
             fields = list(super().__reduce__())
             fields += [None] * max(3 - len(fields), 0)
             if fields[0] is not _reconstruct_persistent_obj:
+                # module_name is an addition to the reference's record (ignored by the reference's loader): lets a fresh
+                # process find the class by import before falling back to the source text
                 meta = dict(type='class', version=_VERSION, module_src=self._orig_module_src,
-                            class_name=self._orig_class_name, state=fields[2])
+                            class_name=self._orig_class_name, state=fields[2], module_name=self._orig_module_name)
                 fields[0] = _reconstruct_persistent_obj
                 fields[1] = (meta,)
                 fields[2] = None
@@ -143,9 +174,15 @@ def _reconstruct_persistent_obj(meta):
         meta = hook(meta)
         assert meta is not None
     assert meta.version == _VERSION
-    module = _module_from_source(meta.module_src)
     assert meta.type == 'class'
-    orig_class = module.__dict__[meta.class_name]
+    module_name = meta.get('module_name')
+    orig_class = _class_by_name(module_name, meta.class_name, meta.module_src)
+    if orig_class is None:
+        pkg = module_name.rsplit('.', 1)[0] if (module_name and '.' in module_name and module_name.split('.')[0] == __name__.split('.')[0]) else None
+        if pkg is None and not module_name and re.search(r'^from \.+ ?import |^from \.\w', meta.module_src or '', re.M):
+            pkg = __name__.rsplit('.', 1)[0]      # a pickle of this engine written before module_name was recorded
+        module = _module_from_source(meta.module_src, package=pkg)
+        orig_class = module.__dict__[meta.class_name]
     decorator_class = persistent_class(orig_class)
     obj = decorator_class.__new__(decorator_class)
     setstate = getattr(obj, '__setstate__', None)

@@ -41,14 +41,48 @@ def _require_cuda(*tensors):
                                f'got a tensor on {t.device}')
 
 
+class _WrongDevice(Exception):
+    """Raised by _enter when the tensor's device is not the thread's current CUDA device; _device_guarded re-runs the call
+    under torch.cuda.device(idx) and restores the caller's device afterwards."""
+
+    def __init__(self, idx):
+        super().__init__(idx)
+        self.idx = idx
+
+
 def _enter(t):
-    """Make the tensor's device current for this thread in both torch and the library; return the stream handle."""
+    """Check that the tensor's device is the thread's current device (in torch and in the library's own runtime instance) and
+    return the handle of torch's current stream on it.  The comparison is made on every call -- the current device may have
+    been changed by anybody since the last one -- and a mismatch is resolved by the _device_guarded wrapper of the public
+    entry points, which switches for the duration of the call and restores the caller's device (the OptionalCUDAGuard of
+    the reference plugins, bias_act.cpp:58)."""
     _require_cuda(t)
     idx = t.device.index if t.device.index is not None else torch.cuda.current_device()
+    if torch.cuda.current_device() != idx:
+        raise _WrongDevice(idx)
     if getattr(_tls, 'device', None) != idx:
         _C.check(_C.lib().ia_set_device(idx), 'ia_set_device')
         _tls.device = idx
     return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _device_guarded(fn):
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        try:
+            return fn(*args, **kwargs)
+        except _WrongDevice as e:
+            prev = torch.cuda.current_device()
+            try:
+                with torch.cuda.device(e.idx):
+                    return fn(*args, **kwargs)
+            finally:
+                # torch restored its own current device; bring the library's runtime instance back as well
+                _C.check(_C.lib().ia_set_device(prev), 'ia_set_device')
+                _tls.device = prev
+    return wrapper
 
 
 def _p(t):
@@ -83,6 +117,34 @@ def profile_report():
     if n < 0:
         _C.check(1, 'ia_profile_report')
     return json.loads(buf.value.decode())
+
+
+# ---------------------------------------------------------------------------------------------------
+# algorithmic-work counter (bench.py roofline leg): 2*MAC of every convolution launched between flop_count_begin() and
+# flop_count_end(), counted as SURVEY 8(d) does -- true (unpadded) channel counts, transposed convolutions at their input
+# resolution, strided encoder convolutions at their output resolution ('computed' is what the device really evaluates)
+# ---------------------------------------------------------------------------------------------------
+_flops = None
+
+
+def flop_count_begin():
+    global _flops
+    _flops = {'algorithmic': 0, 'computed': 0, 'issued_mma': 0, 'launches': 0}
+
+
+def flop_count_end():
+    global _flops
+    out, _flops = _flops, None
+    return out
+
+
+def _count_conv(B, H, W, pack, taps, stride=1, terms=3):
+    if _flops is not None:
+        f = 2 * B * H * W * pack.Cin * pack.Cout * taps
+        _flops['computed'] += f
+        _flops['algorithmic'] += f // (stride * stride)
+        _flops['issued_mma'] += 2 * B * H * W * pack.Cin_pad * pack.Cout_pad * taps * terms
+        _flops['launches'] += 1
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -469,7 +531,7 @@ def _set_group(p, group):
 
 
 def conv_same(hi, lo, pack, Cin_pad, out32, dcoef=None, noise=None, noise_strength=None, bias=None, act='linear',
-              gain=1.0, clamp=None, mode=1, impl=None, e1=None, e2=None, group=None, rgb=None, img_prev=None):
+              gain=1.0, clamp=None, mode=1, impl=None, e1=None, e2=None, group=None, rgb=None, img_prev=None, alg_stride=1):
     """k x k correlation, stride 1, 'same' padding (flip_weight=True branch of conv2d_resample, :134-136)."""
     st = _enter(hi)
     B, H, W, _ = hi.shape
@@ -494,6 +556,7 @@ def conv_same(hi, lo, pack, Cin_pad, out32, dcoef=None, noise=None, noise_streng
         assert mode == 2 and img_prev.is_contiguous() and tuple(img_prev.shape) == (B, H // 2, W // 2, pack.Cout), (img_prev.shape, hi.shape)
         p.img_prev = _p(img_prev)
     _set_group(p, group)
+    _count_conv(B, H, W, pack, k * k, stride=alg_stride)
     _conv_call(p, st, impl)
 
 
@@ -540,6 +603,7 @@ def conv_transpose_up2_raw(hi, lo, pack, Cin_pad, raw, impl=None, group=None, im
             p.emit = _emit(raw)
             p.a_img_rows = int(img_rows) if img_rows and img_rows != H else 0
             _set_group(p, group)
+    _count_conv(B, H, W, pack, 9)
     if (impl or _conv_impl) == 'tc':
         _C.check(_C.lib().ia_conv_tc_phases(phases, 4, st), 'ia_conv_tc_phases')     # one persistent launch for the four phases
     else:
@@ -579,25 +643,27 @@ def fir_epilogue(raw, fir, out32, dcoef, noise, noise_strength, bias, act, gain,
     _C.check(_C.lib().ia_fir_epilogue(C.byref(p), st), 'ia_fir_epilogue')
 
 
-_frame_sink = None   # (peer_ptrs [int], element offset, multicast ptr or 0): consumed by the planar (final image) ToRGB tail
-
-
 class frame_sink:
-    """Context manager: while active, the ToRGB tail that writes the final planar image (out_nchw) also stores every value
-    into this rank's slot of every rank's gathered frame buffer (peer-mapped / multicast symmetric memory)."""
+    """Context manager: while active (on THIS host thread), the ToRGB tail that writes the final planar image (out_nchw) also
+    stores every value into this rank's slot of every rank's gathered frame buffer (peer-mapped / multicast symmetric
+    memory).  ``capacity`` = elements of the slot: an image batch of any other size raises instead of writing
+    past the slot into the neighbouring ranks' frames."""
 
-    def __init__(self, peer_ptrs, offset, mc_ptr=0):
-        self.sink = (list(peer_ptrs), int(offset), int(mc_ptr or 0))
+    def __init__(self, peer_ptrs, offset, mc_ptr=0, capacity=None):
+        self.sink = (list(peer_ptrs), int(offset), int(mc_ptr or 0), None if capacity is None else int(capacity))
 
     def __enter__(self):
-        global _frame_sink
-        self.prev, _frame_sink = _frame_sink, self.sink
+        self.prev = getattr(_tls, 'frame_sink', None)
+        _tls.frame_sink = self.sink
         return self
 
     def __exit__(self, *exc):
-        global _frame_sink
-        _frame_sink = self.prev
+        _tls.frame_sink = self.prev
         return False
+
+
+def _current_frame_sink():
+    return getattr(_tls, 'frame_sink', None)
 
 
 def torgb_finish(raw, bias, clamp, img_prev, out_nchw=False, group=None):
@@ -614,8 +680,12 @@ def torgb_finish(raw, bias, clamp, img_prev, out_nchw=False, group=None):
                        B, H, W, Cc, 1 if out_nchw else 0)
     if group is not None:
         p.groups, p.imgs_per_group = int(group[0]), int(group[1])
-    if out_nchw and _frame_sink is not None:
-        ptrs, off, mc = _frame_sink
+    sink = _current_frame_sink() if out_nchw else None
+    if sink is not None:
+        ptrs, off, mc, cap = sink
+        if cap is not None and out.numel() != cap:
+            raise RuntimeError(f'frame_sink: this call produces {out.numel()} image elements but the gathered buffer has slots of {cap} '
+                               '(batch or resolution differs from the PeerFrameGather it was built for)')
         if mc:
             p.mc_out = mc
         else:
@@ -908,14 +978,16 @@ def enc_prep(srcs, scale=None, shift=None, slope=None, lrelu=1.0, C_pad=None, wa
     return sp, out32
 
 
-def enc_conv(a, conv):
+def enc_conv(a, conv, alg_stride=None):
     """a: Split; conv: torch.nn.Conv2d holder (3x3 pad 1 or 1x1, stride applied by the caller as a [::s, ::s] view of the
-    result) -> raw fp32 accumulators [B,H,W,Cout] (bias not added)."""
+    result) -> raw fp32 accumulators [B,H,W,Cout] (bias not added).  alg_stride: stride used by the algorithmic-FLOP counter
+    (default conv.stride; 1 when the caller already sub-sampled the operand)."""
     pack = ConvPack.current(conv, '_ia_pack', conv.weight, need_wsq=False)
     assert (pack.kh, pack.kw) in ((1, 1), (3, 3)) and a.C_pad == pack.Cin_pad, (pack.kh, a.C_pad, pack.Cin_pad)
     B, H, W, _ = a.hi.shape
     raw = torch.empty((B, H, W, pack.Cout), dtype=torch.float32, device=a.hi.device)
-    conv_same(a.hi, a.lo, pack, pack.Cin_pad, raw, mode=0)
+    stride = alg_stride if alg_stride is not None else (conv.stride[0] if isinstance(conv.stride, (tuple, list)) else int(conv.stride))
+    conv_same(a.hi, a.lo, pack, pack.Cin_pad, raw, mode=0, alg_stride=stride)
     return raw
 
 
@@ -1044,3 +1116,17 @@ def side_streams(device, n=2):
         st = tuple(st) + tuple(torch.cuda.Stream(device=device) for _ in range(n - len(st)))
         _SIDE_STREAMS[key] = st
     return st[:n]
+
+
+def _guard_public_entry_points():
+    """Wrap every public function / method of this module that talks to the library in _device_guarded (see _enter)."""
+    import inspect
+    g = globals()
+    for name, obj in list(g.items()):
+        if inspect.isfunction(obj) and obj.__module__ == __name__ and not name.startswith('_') and '_enter' in obj.__code__.co_names:
+            g[name] = _device_guarded(obj)
+    ConvPack.__init__ = _device_guarded(ConvPack.__init__)
+    StylePlan.run = _device_guarded(StylePlan.run)
+
+
+_guard_public_entry_points()

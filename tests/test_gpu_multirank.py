@@ -21,16 +21,37 @@ def _worker(rank, world, port, q):
         B, Cc, H, W = 2, 3, 16, 16
         peer = PeerFrameGather(B, (Cc, H, W), device=dev)
         g = torch.Generator().manual_seed(100 + rank)
-        raw = torch.randn(B, H, W, Cc, generator=g).to(dev)
-        bias = torch.randn(Cc, generator=g).to(dev)
-        prev = torch.randn(B, H // 2, W // 2, Cc, generator=g).to(dev)
-        with peer.sink():
-            img = rt.torgb_finish(raw, bias, 256.0, prev, out_nchw=True)
-        peer.barrier()
-        want = torch.empty((world * B, Cc, H, W), device=dev)
-        dist.all_gather_into_tensor(want, img.contiguous())
+        ok = True
+        consumed, wanted = [], []
+        side = torch.cuda.Stream(device=dev)
+        for step in range(5):
+            # several steps, a consumer reading the gathered frames of step i on a SIDE stream while step i+1 is produced: the
+            # double-buffered slots keep step i intact until the barrier after next (the consumer is joined before it)
+            raw = torch.randn(B, H, W, Cc, generator=g).to(dev)
+            bias = torch.randn(Cc, generator=g).to(dev)
+            prev = torch.randn(B, H // 2, W // 2, Cc, generator=g).to(dev)
+            torch.cuda.current_stream().wait_stream(side)          # consumer of step i-1 joined before barrier i closes
+            with peer.sink():
+                img = rt.torgb_finish(raw, bias, 256.0, prev, out_nchw=True)
+            peer.barrier()
+            want = torch.empty((world * B, Cc, H, W), device=dev)
+            dist.all_gather_into_tensor(want, img.contiguous())
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                if rank == 1:
+                    torch.cuda._sleep(20_000_000)                   # a slow consumer on one rank (~10 ms)
+                consumed.append(peer.tensor.clone())
+            wanted.append(want)
         torch.cuda.synchronize()
-        q.put((rank, bool(torch.equal(want, peer.tensor)), bool(peer.mc_ptr)))
+        ok = all(torch.equal(a, b) for a, b in zip(consumed, wanted))
+        # a batch that does not match the slot size must raise instead of writing past the slot
+        raised = False
+        try:
+            with peer.sink():
+                rt.torgb_finish(torch.zeros(B + 1, H, W, Cc, device=dev), torch.zeros(Cc, device=dev), 256.0, None, out_nchw=True)
+        except RuntimeError:
+            raised = True
+        q.put((rank, bool(ok and raised), bool(peer.mc_ptr)))
     finally:
         dist.destroy_process_group()
 

@@ -66,3 +66,45 @@ def test_bench_stdout_is_one_json_line():
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d['impl'] == 'reference' and d['unit'] == 'frames/s' and d['cpu_baseline']['kind'] == 'port' and d['e2e']['h2d_bytes_per_step'] == 0
+
+
+def test_persistent_pickle_loads_in_a_fresh_process(tmp_path):
+    """A pickle of an engine @persistent_class object loads in a process that has not imported the defining module
+    (class found by its recorded module name), and still loads when the module text differs from the pickled one (rebuilt
+    from the pickled source, whose relative imports resolve against the package)."""
+    import pickle
+    from invertavatar_b200 import persistence
+    from invertavatar_b200.stylegan2 import FullyConnectedLayer
+    torch.manual_seed(0)
+    fc = FullyConnectedLayer(4, 3, lr_multiplier=0.5)
+    path = tmp_path / 'fc.pkl'
+    with open(path, 'wb') as f:
+        pickle.dump(fc, f)
+    # same record, but with a module text that no importable module has (as after an upgrade of the package) and -- second
+    # variant -- without the module_name field (a pickle written by the previous version of the engine)
+    fields = fc.__reduce__()
+    meta = dict(fields[1][0])
+    meta['module_src'] = meta['module_src'] + '\n# edited after the pickle was written\n'
+    path2 = tmp_path / 'fc_changed.pkl'
+    with open(path2, 'wb') as f:
+        pickle.dump((meta, {k: v for k, v in meta.items() if k != 'module_name'}), f)
+    code = '''
+import pickle, sys
+sys.path.insert(0, %r)
+import torch
+assert 'invertavatar_b200.stylegan2' not in sys.modules
+with open(%r, 'rb') as f:
+    fc = pickle.load(f)
+assert type(fc).__name__ == 'FullyConnectedLayer' and tuple(fc.weight.shape) == (3, 4), type(fc)
+assert fc.init_args == (4, 3) and fc.init_kwargs['lr_multiplier'] == 0.5
+from invertavatar_b200 import persistence
+with open(%r, 'rb') as f:
+    metas = pickle.load(f)
+for meta in metas:
+    obj = persistence._reconstruct_persistent_obj(meta)
+    assert type(obj).__name__ == 'FullyConnectedLayer' and type(obj).__module__.startswith('_imported_module_'), type(obj).__module__
+    assert torch.equal(obj.weight, fc.weight)
+print('ok')
+''' % (ROOT, str(path), str(path2))
+    r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith('ok'), r.stdout + r.stderr
