@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define IA_ABI_VERSION 1
+#define IA_ABI_VERSION 2
 
 /* ---- library management ------------------------------------------------------------------------ */
 int ia_abi_version(void);
@@ -48,27 +48,65 @@ int64_t ia_profile_report(char* buf, int64_t buflen);
 enum { IA_ACT_LINEAR = 1, IA_ACT_RELU = 2, IA_ACT_LRELU = 3, IA_ACT_TANH = 4, IA_ACT_SIGMOID = 5,
        IA_ACT_ELU = 6, IA_ACT_SELU = 7, IA_ACT_SOFTPLUS = 8, IA_ACT_SWISH = 9 };
 
+/* Element types of the three plugin-level entry points.  The reference dispatches bias_act / upfirdn2d over double, float
+ * and half (AT_DISPATCH_FLOATING_TYPES_AND_HALF, bias_act.cpp:81, upfirdn2d.cpp:67) and filtered_lrelu over float / half
+ * (filtered_lrelu.cpp:33); arithmetic is float for half/float and double for double (bias_act.cu:18-21).  Everything else
+ * in this header is fp32. */
+enum { IA_DTYPE_F32 = 0, IA_DTYPE_F16 = 1, IA_DTYPE_F64 = 2 };
+
 /* y = clamp(act(x + b[c]) * gain).  Replaces bias_act_plugin.bias_act(x,b,xref,yref,dy,grad=0,dim,act,alpha,
  * gain,clamp) (torch_utils/ops/bias_act.cpp:36-94, kernel bias_act.cu:27-151), forward only.
  * x is a dense tensor viewed as [outer][C][inner]; channel of element i is (i / inner) % C.
- * b may be NULL (no bias).  clamp < 0 disables clamping. */
-int ia_bias_act(const float* x, const float* b, float* y, int64_t numel, int64_t C, int64_t inner,
-                int act, float alpha, float gain, float clamp, void* stream);
+ * x, b, y have element type `dtype` (bias_act.cpp:41: b.dtype == x.dtype).  b may be NULL (no bias).  clamp < 0 disables
+ * clamping. */
+int ia_bias_act(const void* x, const void* b, void* y, int64_t numel, int64_t C, int64_t inner,
+                int act, float alpha, float gain, float clamp, int dtype, void* stream);
 
 /* Generic upfirdn2d: zero-insert x(up), pad/crop, 2-D FIR, decimate.  Replaces
  * upfirdn2d_plugin.upfirdn2d(x,f,upx,upy,downx,downy,padx0,padx1,pady0,pady1,flip,gain)
  * (torch_utils/ops/upfirdn2d.cpp:20-102, kernels upfirdn2d.cu:33-204).  Arbitrary element strides for x and y
  * (covers contiguous and channels-last, like upfirdn2d.cpp:56-63); f is a dense fp32 [fh][fw] filter. */
 typedef struct {
-    const float* x; const float* f; float* y;
+    const void* x; const float* f; void* y;      /* x, y: element type `dtype`; f: fp32 (upfirdn2d.cpp:26) */
     int32_t N, C, inH, inW, outH, outW, fh, fw;
     int32_t upx, upy, downx, downy, padx0, pady0;
     int32_t flip;              /* reference semantics: flip=0 -> true convolution (filter is flipped) */
     float gain;
     int64_t xs_n, xs_c, xs_h, xs_w;   /* element strides of x */
     int64_t ys_n, ys_c, ys_h, ys_w;   /* element strides of y */
+    int32_t dtype;                    /* IA_DTYPE_* of x and y */
 } ia_upfirdn2d_params;
 int ia_upfirdn2d(const ia_upfirdn2d_params* p, void* stream);
+
+/* filtered_lrelu: y = downFIR(clamp(lrelu(upFIR(x + b) * up^2) * gain)).  Replaces
+ * filtered_lrelu_plugin.filtered_lrelu(x,fu,fd,b,si,up,down,px0,px1,py0,py1,sx,sy,gain,slope,clamp,flip_filters,writeSigns)
+ * -> (y, so, rc) (torch_utils/ops/filtered_lrelu.cpp:20-214), forward only, as two kernels through a caller-provided fp32
+ * workspace of ia_filtered_lrelu_workspace(p) bytes.  fu / fd: fp32 2-D [fh][fw], or separable 1-D [fw] with fh = 0
+ * (filtered_lrelu.cpp:52-53), or NULL (identity).  x / y: element strides, element type `dtype` (F32 or F16); b [C] of the
+ * same type or NULL.  outH / outW must equal the reference's output size (filtered_lrelu.cpp:77-86).
+ * Return value: 0 = done; -1 = "no specialised kernel" exactly like the reference's rc (filtered_lrelu.cpp:56-60): given when
+ * sign tensors are requested (si / so / write_signs: they only serve the backward pass) -- the caller then takes the
+ * bias_act / upfirdn2d composition as filtered_lrelu.py:225-231 does; > 0 = invalid arguments (ia_last_error). */
+typedef struct {
+    const void* x; void* y; const void* b;
+    const float* fu; const float* fd;
+    int32_t N, C, inH, inW, outH, outW;
+    int32_t fuw, fuh, fdw, fdh;
+    int32_t up, down, px0, px1, py0, py1;
+    float gain, slope, clamp;         /* clamp < 0: none */
+    int32_t flip;                     /* flip_filters */
+    int64_t xs_n, xs_c, xs_h, xs_w;
+    int64_t ys_n, ys_c, ys_h, ys_w;
+    int32_t dtype;
+    void* workspace; int64_t workspace_bytes;
+    const uint8_t* si; int32_t sx, sy; int32_t write_signs; uint8_t* so;
+} ia_filtered_lrelu_params;
+int64_t ia_filtered_lrelu_workspace(const ia_filtered_lrelu_params* p);   /* bytes, or -1 (ia_last_error) */
+int ia_filtered_lrelu(const ia_filtered_lrelu_params* p, void* stream);
+/* In place x = clamp(lrelu(x) * gain).  Replaces filtered_lrelu_plugin.filtered_lrelu_act_(x,si,sx,sy,gain,slope,clamp,
+ * writeSigns) (filtered_lrelu.cpp:217-296), the one entry point that mutates its input.  Sign tensors: -1 as above. */
+int ia_filtered_lrelu_act(void* x, int64_t numel, int dtype, const uint8_t* si, int32_t sx, int32_t sy, float gain, float slope,
+                          float clamp, int32_t write_signs, uint8_t* so, void* stream);
 
 /* ---- small dense layers (MappingNetwork, style affines; networks_stylegan2_new.py:96-127,233-268) ------- */
 
@@ -274,7 +312,13 @@ typedef struct {
     float* depth;                                 /* out [B][res][res] unclamped composite depth */
     float* wsum;                                  /* out [B][res][res] */
     float* depth_minmax;                          /* device [2] global min/max of all sample depths (init by callee) */
+    /* Device scratch of ia_render_scratch_bytes() bytes, 16-byte aligned, owned by the caller for the duration of the call's
+     * stream work: the decoder weights are staged into it in tensor-core fragment order by a small kernel in front of the
+     * render kernel.  Per call, so that the library keeps no mutable device state: concurrent renders on different streams
+     * (two generators, a graph replay next to an eager call) cannot race. */
+    void* scratch;
 } ia_render_params;
+int64_t ia_render_scratch_bytes(void);
 /* near/far = mean_b ||c2w_b[:3,3]|| - 0.45 / + 0.6 (renderer.py:311-313), computed on device (no host sync). */
 int ia_ray_bounds(const float* cam, int64_t cam_ld, int32_t B, float* near_far, void* stream);
 int ia_ray_bounds_from_origins(const float* origins, int64_t n, float* near_far, void* stream);

@@ -26,7 +26,19 @@ class Upfirdn2dParams(C.Structure):
                 ('upx', C.c_int32), ('upy', C.c_int32), ('downx', C.c_int32), ('downy', C.c_int32),
                 ('padx0', C.c_int32), ('pady0', C.c_int32), ('flip', C.c_int32), ('gain', C.c_float),
                 ('xs_n', C.c_int64), ('xs_c', C.c_int64), ('xs_h', C.c_int64), ('xs_w', C.c_int64),
-                ('ys_n', C.c_int64), ('ys_c', C.c_int64), ('ys_h', C.c_int64), ('ys_w', C.c_int64)]
+                ('ys_n', C.c_int64), ('ys_c', C.c_int64), ('ys_h', C.c_int64), ('ys_w', C.c_int64), ('dtype', C.c_int32)]
+
+
+class FilteredLreluParams(C.Structure):
+    _fields_ = [('x', C.c_void_p), ('y', C.c_void_p), ('b', C.c_void_p), ('fu', c_f32p), ('fd', c_f32p),
+                ('N', C.c_int32), ('C', C.c_int32), ('inH', C.c_int32), ('inW', C.c_int32), ('outH', C.c_int32), ('outW', C.c_int32),
+                ('fuw', C.c_int32), ('fuh', C.c_int32), ('fdw', C.c_int32), ('fdh', C.c_int32),
+                ('up', C.c_int32), ('down', C.c_int32), ('px0', C.c_int32), ('px1', C.c_int32), ('py0', C.c_int32), ('py1', C.c_int32),
+                ('gain', C.c_float), ('slope', C.c_float), ('clamp', C.c_float), ('flip', C.c_int32),
+                ('xs_n', C.c_int64), ('xs_c', C.c_int64), ('xs_h', C.c_int64), ('xs_w', C.c_int64),
+                ('ys_n', C.c_int64), ('ys_c', C.c_int64), ('ys_h', C.c_int64), ('ys_w', C.c_int64),
+                ('dtype', C.c_int32), ('workspace', C.c_void_p), ('workspace_bytes', C.c_int64),
+                ('si', C.c_void_p), ('sx', C.c_int32), ('sy', C.c_int32), ('write_signs', C.c_int32), ('so', C.c_void_p)]
 
 
 class ModsplitParams(C.Structure):
@@ -97,7 +109,7 @@ class RenderParams(C.Structure):
                 ('cam', c_f32p), ('cam_ld', C.c_int64), ('rays_o', c_f32p), ('rays_d', c_f32p), ('res', C.c_int32), ('Dc', C.c_int32), ('Df', C.c_int32),
                 ('jitter', c_f32p), ('u', c_f32p), ('box_warp', C.c_float), ('white_back', C.c_int32),
                 ('near_far', c_f32p), ('w1', c_f32p), ('b1', c_f32p), ('w2', c_f32p), ('b2', c_f32p),
-                ('feat', c_f32p), ('depth', c_f32p), ('wsum', c_f32p), ('depth_minmax', c_f32p)]
+                ('feat', c_f32p), ('depth', c_f32p), ('wsum', c_f32p), ('depth_minmax', c_f32p), ('scratch', C.c_void_p)]
 
 
 class RasterLevelParams(C.Structure):
@@ -144,8 +156,11 @@ SIGNATURES = {
     'ia_reset_launch_count': (None, []),
     'ia_profile_begin': (C.c_int, []),
     'ia_profile_report': (C.c_int64, [C.c_char_p, C.c_int64]),
-    'ia_bias_act': (C.c_int, [c_f32p, c_f32p, c_f32p, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_float, C.c_float, C.c_float, C.c_void_p]),
+    'ia_bias_act': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_void_p]),
     'ia_upfirdn2d': (C.c_int, [C.POINTER(Upfirdn2dParams), C.c_void_p]),
+    'ia_filtered_lrelu_workspace': (C.c_int64, [C.POINTER(FilteredLreluParams)]),
+    'ia_filtered_lrelu': (C.c_int, [C.POINTER(FilteredLreluParams), C.c_void_p]),
+    'ia_filtered_lrelu_act': (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_int32, C.c_void_p, C.c_void_p]),
     'ia_fully_connected': (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float,
                                     C.c_int, C.c_float, C.c_float, C.c_int64, C.c_int64, C.c_void_p]),
     'ia_normalize_2nd_moment': (C.c_int, [c_f32p, c_f32p, C.c_int32, C.c_int32, C.c_float, C.c_int64, C.c_int64, C.c_void_p]),
@@ -166,6 +181,7 @@ SIGNATURES = {
     'ia_ray_bounds': (C.c_int, [c_f32p, C.c_int64, C.c_int32, c_f32p, C.c_void_p]),
     'ia_ray_bounds_from_origins': (C.c_int, [c_f32p, C.c_int64, c_f32p, C.c_void_p]),
     'ia_render': (C.c_int, [C.POINTER(RenderParams), C.c_void_p]),
+    'ia_render_scratch_bytes': (C.c_int64, []),
     'ia_depth_clamp': (C.c_int, [c_f32p, C.c_int64, c_f32p, C.c_void_p]),
     'ia_ray_sampler': (C.c_int, [c_f32p, C.c_int64, C.c_int32, C.c_int32, c_f32p, c_f32p, C.c_void_p]),
     'ia_enc_chan_stats': (C.c_int, [C.POINTER(View), C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
@@ -182,7 +198,7 @@ SIGNATURES = {
     'ia_sft_half': (C.c_int, [c_f32p, C.c_int64, C.POINTER(View), C.POINTER(View), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
 }
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 _lib = None
 
 

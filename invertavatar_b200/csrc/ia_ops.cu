@@ -111,6 +111,40 @@ extern "C" int ia_set_device(int device) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// element types of the plugin-level entry points: the reference dispatches bias_act / upfirdn2d over double, float and half
+// (AT_DISPATCH_FLOATING_TYPES_AND_HALF, bias_act.cpp:81, upfirdn2d.cpp:67) with float arithmetic for half/float and double
+// arithmetic for double (InternalType<T>, bias_act.cu:18-21)
+// ------------------------------------------------------------------------------------------------
+#include <cuda_fp16.h>
+template <typename T> struct Internal { typedef float type; };
+template <> struct Internal<double> { typedef double type; };
+template <typename T, typename S> __device__ __forceinline__ S ld_as(const T* p) { return (S)(*p); }
+template <> __device__ __forceinline__ float ld_as<__half, float>(const __half* p) { return __half2float(*p); }
+template <typename T, typename S> __device__ __forceinline__ void st_as(T* p, S v) { *p = (T)v; }
+template <> __device__ __forceinline__ void st_as<__half, float>(__half* p, float v) { *p = __float2half_rn(v); }
+
+__device__ __forceinline__ double apply_act_f64(double x, int act, double alpha) {
+    switch (act) {
+        case IA_ACT_LINEAR: return x;
+        case IA_ACT_RELU: return x > 0. ? x : 0.;
+        case IA_ACT_LRELU: return x > 0. ? x : x * alpha;
+        case IA_ACT_TANH: return tanh(x);
+        case IA_ACT_SIGMOID: return 1. / (1. + exp(-x));
+        case IA_ACT_ELU: return x > 0. ? x : expm1(x);
+        case IA_ACT_SELU: return x > 0. ? 1.0507009873554805 * x : 1.0507009873554805 * 1.6732632423543772 * expm1(x);
+        case IA_ACT_SOFTPLUS: return x > 20. ? x : log1p(exp(x));
+        case IA_ACT_SWISH: return x / (1. + exp(-x));
+    }
+    return x;
+}
+__device__ __forceinline__ float act_gc(float x, int act, float alpha, float gain, float clamp) { return act_gain_clamp(x, act, alpha, gain, clamp); }
+__device__ __forceinline__ double act_gc(double x, int act, float alpha, float gain, float clamp) {
+    x = apply_act_f64(x, act, (double)alpha) * (double)gain;
+    if (clamp >= 0.f) x = fmin(fmax(x, -(double)clamp), (double)clamp);
+    return x;
+}
+
+// ------------------------------------------------------------------------------------------------
 // bias_act
 // ------------------------------------------------------------------------------------------------
 __global__ void bias_act_kernel(const float* __restrict__ x, const float* __restrict__ b, float* __restrict__ y,
@@ -136,18 +170,37 @@ __global__ void bias_act_kernel(const float* __restrict__ x, const float* __rest
     }
 }
 
-extern "C" int ia_bias_act(const float* x, const float* b, float* y, int64_t numel, int64_t C, int64_t inner,
-                           int act, float alpha, float gain, float clamp, void* stream) {
+// half / double I/O (the fp32 kernel above is the vectorised hot variant)
+template <typename T>
+__global__ void bias_act_any_kernel(const T* __restrict__ x, const T* __restrict__ b, T* __restrict__ y, int64_t numel, int64_t C,
+                                    int64_t inner, int act, float alpha, float gain, float clamp) {
+    typedef typename Internal<T>::type S;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= numel) return;
+    S t = ld_as<T, S>(x + i);
+    if (b) t += ld_as<T, S>(b + (i / inner) % C);
+    st_as<T, S>(y + i, act_gc(t, act, alpha, gain, clamp));
+}
+
+extern "C" int ia_bias_act(const void* x, const void* b, void* y, int64_t numel, int64_t C, int64_t inner,
+                           int act, float alpha, float gain, float clamp, int dtype, void* stream) {
     IA_CHECK(x && y, "ia_bias_act: null tensor");
     IA_CHECK(act >= IA_ACT_LINEAR && act <= IA_ACT_SWISH, "ia_bias_act: bad activation id %d", act);
+    IA_CHECK(dtype == IA_DTYPE_F32 || dtype == IA_DTYPE_F16 || dtype == IA_DTYPE_F64, "ia_bias_act: x must be float16, float32 or float64 (dtype id %d)", dtype);
     IA_CHECK(numel >= 0 && numel <= 0x7fffffffLL * 4, "ia_bias_act: numel too large");
     IA_CHECK(b == nullptr || (C > 0 && inner > 0), "ia_bias_act: bias needs C>0 and inner>0");
     if (numel == 0) return 0;
     int threads = 256;
-    int64_t blocks = cdiv(cdiv(numel, 4), threads);
+    const int64_t Cc = C > 0 ? C : 1, in = inner > 0 ? inner : 1;
     ia::prof_begin("ia_bias_act", as_stream(stream));
-    bias_act_kernel<<<(unsigned)blocks, threads, 0, as_stream(stream)>>>(x, b, y, numel, C > 0 ? C : 1,
-                                                                          inner > 0 ? inner : 1, act, alpha, gain, clamp);
+    if (dtype == IA_DTYPE_F32) {
+        int64_t blocks = cdiv(cdiv(numel, 4), threads);
+        bias_act_kernel<<<(unsigned)blocks, threads, 0, as_stream(stream)>>>((const float*)x, (const float*)b, (float*)y, numel, Cc, in, act, alpha, gain, clamp);
+    } else if (dtype == IA_DTYPE_F16) {
+        bias_act_any_kernel<__half><<<(unsigned)cdiv(numel, threads), threads, 0, as_stream(stream)>>>((const __half*)x, (const __half*)b, (__half*)y, numel, Cc, in, act, alpha, gain, clamp);
+    } else {
+        bias_act_any_kernel<double><<<(unsigned)cdiv(numel, threads), threads, 0, as_stream(stream)>>>((const double*)x, (const double*)b, (double*)y, numel, Cc, in, act, alpha, gain, clamp);
+    }
     IA_LAUNCH_CHECK("ia_bias_act");
     return 0;
 }
@@ -155,7 +208,38 @@ extern "C" int ia_bias_act(const float* x, const float* b, float* y, int64_t num
 // ------------------------------------------------------------------------------------------------
 // upfirdn2d (generic, strided)
 // ------------------------------------------------------------------------------------------------
+// One output element: sum over the filter window of the zero-stuffed, padded input.  BIAS/ACT (filtered_lrelu's first stage):
+// `bias` is added to every real input sample before filtering and leaky-ReLU * act_gain, clamp are applied to the result.
+// fh == 0 marks a separable filter: f holds fw taps applied along both axes (weight f[ky]*f[kx]).
+template <typename T, typename S, bool FUSED>
+__device__ __forceinline__ S upfirdn2d_point(const T* __restrict__ xb, int64_t xs_h, int64_t xs_w, int inH, int inW, const float* __restrict__ f,
+                                             int fh, int fw, int upx, int upy, int uy0, int ux0, int flip, S bias) {
+    const int fhh = fh > 0 ? fh : fw;
+    S acc = (S)0;
+    for (int fy = 0; fy < fhh; ++fy) {
+        const int uy = uy0 + fy;
+        if (uy < 0 || uy % upy != 0) continue;
+        const int iy = uy / upy;
+        if (iy >= inH) continue;
+        const int ky = flip ? fy : (fhh - 1 - fy);   // reference: correlate with the flipped filter unless flip_filter is set
+        for (int fx = 0; fx < fw; ++fx) {
+            const int ux = ux0 + fx;
+            if (ux < 0 || ux % upx != 0) continue;
+            const int ix = ux / upx;
+            if (ix >= inW) continue;
+            const int kx = flip ? fx : (fw - 1 - fx);
+            const S w = fh > 0 ? (S)f[ky * fw + kx] : (S)f[ky] * (S)f[kx];
+            S v = ld_as<T, S>(xb + iy * xs_h + ix * xs_w);
+            if (FUSED) v += bias;
+            acc += w * v;
+        }
+    }
+    return acc;
+}
+
+template <typename T>
 __global__ void upfirdn2d_kernel(ia_upfirdn2d_params p) {
+    typedef typename Internal<T>::type S;
     int64_t total = (int64_t)p.N * p.C * p.outH * p.outW;
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
@@ -170,40 +254,155 @@ __global__ void upfirdn2d_kernel(ia_upfirdn2d_params p) {
         oy = t % p.outH; t /= p.outH;
         c = t % p.C; n = (int)(t / p.C);
     }
-    // position in the zero-stuffed, padded signal
-    const int uy0 = oy * p.downy - p.pady0;  // top-left of the filter window in upsampled coordinates
-    const int ux0 = ox * p.downx - p.padx0;
-    const float* xb = p.x + n * p.xs_n + c * p.xs_c;
-    float acc = 0.f;
-    for (int fy = 0; fy < p.fh; ++fy) {
-        int uy = uy0 + fy;
-        if (uy < 0 || uy % p.upy != 0) continue;
-        int iy = uy / p.upy;
-        if (iy >= p.inH) continue;
-        for (int fx = 0; fx < p.fw; ++fx) {
-            int ux = ux0 + fx;
-            if (ux < 0 || ux % p.upx != 0) continue;
-            int ix = ux / p.upx;
-            if (ix >= p.inW) continue;
-            // reference: correlate with the flipped filter unless flip_filter is set
-            int ky = p.flip ? fy : (p.fh - 1 - fy);
-            int kx = p.flip ? fx : (p.fw - 1 - fx);
-            acc += p.f[ky * p.fw + kx] * xb[iy * p.xs_h + ix * p.xs_w];
-        }
-    }
-    p.y[n * p.ys_n + c * p.ys_c + oy * p.ys_h + ox * p.ys_w] = acc * p.gain;
+    // position in the zero-stuffed, padded signal: top-left of the filter window in upsampled coordinates
+    const T* xb = reinterpret_cast<const T*>(p.x) + n * p.xs_n + c * p.xs_c;
+    const S acc = upfirdn2d_point<T, S, false>(xb, p.xs_h, p.xs_w, p.inH, p.inW, p.f, p.fh, p.fw, p.upx, p.upy, oy * p.downy - p.pady0,
+                                               ox * p.downx - p.padx0, p.flip, (S)0);
+    st_as<T, S>(reinterpret_cast<T*>(p.y) + n * p.ys_n + c * p.ys_c + oy * p.ys_h + ox * p.ys_w, acc * (S)p.gain);
 }
 
 extern "C" int ia_upfirdn2d(const ia_upfirdn2d_params* p, void* stream) {
     IA_CHECK(p && p->x && p->y && p->f, "ia_upfirdn2d: null tensor");
     IA_CHECK(p->upx >= 1 && p->upy >= 1 && p->downx >= 1 && p->downy >= 1, "ia_upfirdn2d: bad up/down factors");
     IA_CHECK(p->fh >= 1 && p->fw >= 1 && p->fh <= 64 && p->fw <= 64, "ia_upfirdn2d: bad filter size");
+    IA_CHECK(p->dtype == IA_DTYPE_F32 || p->dtype == IA_DTYPE_F16 || p->dtype == IA_DTYPE_F64, "ia_upfirdn2d: x must be float16, float32 or float64 (dtype id %d)", p->dtype);
     int64_t total = (int64_t)p->N * p->C * p->outH * p->outW;
     IA_CHECK(total >= 0 && total < (1LL << 40), "ia_upfirdn2d: output too large");
     if (total == 0) return 0;
     ia::prof_begin("ia_upfirdn2d", as_stream(stream));
-    upfirdn2d_kernel<<<(unsigned)cdiv(total, 256), 256, 0, as_stream(stream)>>>(*p);
+    const unsigned blocks = (unsigned)cdiv(total, 256);
+    if (p->dtype == IA_DTYPE_F32) upfirdn2d_kernel<float><<<blocks, 256, 0, as_stream(stream)>>>(*p);
+    else if (p->dtype == IA_DTYPE_F16) upfirdn2d_kernel<__half><<<blocks, 256, 0, as_stream(stream)>>>(*p);
+    else upfirdn2d_kernel<double><<<blocks, 256, 0, as_stream(stream)>>>(*p);
     IA_LAUNCH_CHECK("ia_upfirdn2d");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// filtered_lrelu (third plugin of the reference's boundary, filtered_lrelu.cpp:20,217): bias -> up-FIR -> leaky ReLU * gain,
+// clamp -> down-FIR as two kernels through an fp32 workspace.  Forward only: the sign tensors that the reference's backward
+// pass reads/writes are not produced -- a call that asks for them answers -1, the reference's own "no specialised kernel"
+// code, on which its Python falls back to the bias_act / upfirdn2d composition (filtered_lrelu.py:225-231).
+// ------------------------------------------------------------------------------------------------
+struct FluGeom { int cw, ch; };
+static int flu_geometry(const ia_filtered_lrelu_params* p, FluGeom* g) {
+    const int fuw = p->fu ? p->fuw : 1, fuh = p->fu ? (p->fuh > 0 ? p->fuh : p->fuw) : 1;
+    const int fdw = p->fd ? p->fdw : 1, fdh = p->fd ? (p->fdh > 0 ? p->fdh : p->fdw) : 1;
+    const int64_t cw = (int64_t)p->inW * p->up + (p->px0 + p->px1) - (fuw - 1);
+    const int64_t ch = (int64_t)p->inH * p->up + (p->py0 + p->py1) - (fuh - 1);
+    IA_CHECK(cw > fdw - 1 && ch > fdh - 1, "ia_filtered_lrelu: upsampled buffer must be at least the size of downsampling filter");
+    IA_CHECK(cw <= 0x7fffffff && ch <= 0x7fffffff, "ia_filtered_lrelu: upsampled buffer is too large");
+    const int64_t yw = (cw - (fdw - 1) + (p->down - 1)) / p->down, yh = (ch - (fdh - 1) + (p->down - 1)) / p->down;
+    IA_CHECK(yw > 0 && yh > 0, "ia_filtered_lrelu: output must be at least 1x1");
+    IA_CHECK(yw == p->outW && yh == p->outH, "ia_filtered_lrelu: output is %lld x %lld for these arguments, caller allocated %d x %d",
+             (long long)yh, (long long)yw, p->outH, p->outW);
+    g->cw = (int)cw; g->ch = (int)ch;
+    return 0;
+}
+static int flu_validate(const ia_filtered_lrelu_params* p) {
+    IA_CHECK(p && p->x && p->y, "ia_filtered_lrelu: null tensor");
+    IA_CHECK(p->dtype == IA_DTYPE_F32 || p->dtype == IA_DTYPE_F16, "ia_filtered_lrelu: x and b must be float16 or float32");
+    IA_CHECK(p->N > 0 && p->C > 0 && p->inH > 0 && p->inW > 0, "ia_filtered_lrelu: x is empty");
+    IA_CHECK(p->up >= 1 && p->down >= 1, "ia_filtered_lrelu: up and down must be at least 1");
+    IA_CHECK(!p->fu || (p->fuw >= 1 && p->fuw <= 64 && p->fuh >= 0 && p->fuh <= 64), "ia_filtered_lrelu: bad fu shape");
+    IA_CHECK(!p->fd || (p->fdw >= 1 && p->fdw <= 64 && p->fdh >= 0 && p->fdh <= 64), "ia_filtered_lrelu: bad fd shape");
+    return 0;
+}
+
+template <typename T>
+__global__ void flu_up_kernel(ia_filtered_lrelu_params p, int cw, int ch, const float* __restrict__ one) {
+    const int64_t total = (int64_t)p.N * p.C * ch * cw;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int ux = (int)(idx % cw); int64_t t = idx / cw;
+    const int uy = (int)(t % ch); t /= ch;
+    const int c = (int)(t % p.C), n = (int)(t / p.C);
+    const T* xb = reinterpret_cast<const T*>(p.x) + n * p.xs_n + c * p.xs_c;
+    const float bias = p.b ? ld_as<T, float>(reinterpret_cast<const T*>(p.b) + c) : 0.f;
+    const float* f = p.fu ? p.fu : one;
+    const int fw = p.fu ? p.fuw : 1, fh = p.fu ? p.fuh : 1;
+    float v = upfirdn2d_point<T, float, true>(xb, p.xs_h, p.xs_w, p.inH, p.inW, f, fh, fw, p.up, p.up, uy - p.py0, ux - p.px0, p.flip, bias);
+    v *= (float)(p.up * p.up);
+    v = (v > 0.f ? v : v * p.slope) * p.gain;
+    if (p.clamp >= 0.f) v = fminf(fmaxf(v, -p.clamp), p.clamp);
+    reinterpret_cast<float*>(p.workspace)[idx] = v;
+}
+
+template <typename T>
+__global__ void flu_down_kernel(ia_filtered_lrelu_params p, int cw, int ch, const float* __restrict__ one) {
+    const int64_t total = (int64_t)p.N * p.C * p.outH * p.outW;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int ox = (int)(idx % p.outW); int64_t t = idx / p.outW;
+    const int oy = (int)(t % p.outH); t /= p.outH;
+    const int c = (int)(t % p.C), n = (int)(t / p.C);
+    const float* wb = reinterpret_cast<const float*>(p.workspace) + ((int64_t)n * p.C + c) * ch * cw;
+    const float* f = p.fd ? p.fd : one;
+    const int fw = p.fd ? p.fdw : 1, fh = p.fd ? p.fdh : 1;
+    const float v = upfirdn2d_point<float, float, false>(wb, cw, 1, ch, cw, f, fh, fw, 1, 1, oy * p.down, ox * p.down, p.flip, 0.f);
+    st_as<T, float>(reinterpret_cast<T*>(p.y) + n * p.ys_n + c * p.ys_c + oy * p.ys_h + ox * p.ys_w, v);
+}
+
+__device__ float g_flu_one = 1.0f;     // identity filter (read-only)
+
+extern "C" int64_t ia_filtered_lrelu_workspace(const ia_filtered_lrelu_params* p) {
+    if (flu_validate(p)) return -1;
+    FluGeom g;
+    if (flu_geometry(p, &g)) return -1;
+    return (int64_t)p->N * p->C * g.ch * g.cw * (int64_t)sizeof(float);
+}
+
+extern "C" int ia_filtered_lrelu(const ia_filtered_lrelu_params* p, void* stream) {
+    if (int rc = flu_validate(p)) return rc;
+    if (p->si || p->so || p->write_signs) {
+        ia::set_error("ia_filtered_lrelu: sign tensors (backward pass) are not produced by this forward-only library; -1 = no specialised kernel");
+        return -1;
+    }
+    FluGeom g;
+    if (int rc = flu_geometry(p, &g)) return rc;
+    const int64_t need = (int64_t)p->N * p->C * g.ch * g.cw * (int64_t)sizeof(float);
+    IA_CHECK(p->workspace && p->workspace_bytes >= need, "ia_filtered_lrelu: workspace of %lld bytes needed (ia_filtered_lrelu_workspace)", (long long)need);
+    float* one = nullptr;
+    cudaError_t e = cudaGetSymbolAddress((void**)&one, g_flu_one);
+    IA_CHECK(e == cudaSuccess, "ia_filtered_lrelu: %s", cudaGetErrorString(e));
+    const int64_t tot_up = (int64_t)p->N * p->C * g.ch * g.cw, tot_dn = (int64_t)p->N * p->C * p->outH * p->outW;
+    ia::prof_begin("ia_filtered_lrelu(up)", as_stream(stream));
+    if (p->dtype == IA_DTYPE_F32) flu_up_kernel<float><<<(unsigned)cdiv(tot_up, 256), 256, 0, as_stream(stream)>>>(*p, g.cw, g.ch, one);
+    else flu_up_kernel<__half><<<(unsigned)cdiv(tot_up, 256), 256, 0, as_stream(stream)>>>(*p, g.cw, g.ch, one);
+    IA_LAUNCH_CHECK("ia_filtered_lrelu(up)");
+    ia::prof_begin("ia_filtered_lrelu(down)", as_stream(stream));
+    if (p->dtype == IA_DTYPE_F32) flu_down_kernel<float><<<(unsigned)cdiv(tot_dn, 256), 256, 0, as_stream(stream)>>>(*p, g.cw, g.ch, one);
+    else flu_down_kernel<__half><<<(unsigned)cdiv(tot_dn, 256), 256, 0, as_stream(stream)>>>(*p, g.cw, g.ch, one);
+    IA_LAUNCH_CHECK("ia_filtered_lrelu(down)");
+    return 0;
+}
+
+template <typename T>
+__global__ void flu_act_kernel(T* __restrict__ x, int64_t numel, float gain, float slope, float clamp) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= numel) return;
+    float v = ld_as<T, float>(x + i);
+    v = (v > 0.f ? v : v * slope) * gain;
+    if (clamp >= 0.f) v = fminf(fmaxf(v, -clamp), clamp);
+    st_as<T, float>(x + i, v);
+}
+
+extern "C" int ia_filtered_lrelu_act(void* x, int64_t numel, int dtype, const uint8_t* si, int32_t sx, int32_t sy, float gain, float slope,
+                                     float clamp, int32_t write_signs, uint8_t* so, void* stream) {
+    (void)sx; (void)sy;
+    IA_CHECK(x, "ia_filtered_lrelu_act: null tensor");
+    IA_CHECK(dtype == IA_DTYPE_F32 || dtype == IA_DTYPE_F16 || dtype == IA_DTYPE_F64, "ia_filtered_lrelu_act: x must be float16, float32 or float64");
+    if (si || so || write_signs) {
+        ia::set_error("ia_filtered_lrelu_act: sign tensors (backward pass) are not supported by this forward-only library");
+        return -1;
+    }
+    if (numel == 0) return 0;
+    ia::prof_begin("ia_filtered_lrelu_act", as_stream(stream));
+    const unsigned blocks = (unsigned)cdiv(numel, 256);
+    if (dtype == IA_DTYPE_F32) flu_act_kernel<float><<<blocks, 256, 0, as_stream(stream)>>>((float*)x, numel, gain, slope, clamp);
+    else if (dtype == IA_DTYPE_F16) flu_act_kernel<__half><<<blocks, 256, 0, as_stream(stream)>>>((__half*)x, numel, gain, slope, clamp);
+    else flu_act_kernel<double><<<blocks, 256, 0, as_stream(stream)>>>((double*)x, numel, gain, slope, clamp);
+    IA_LAUNCH_CHECK("ia_filtered_lrelu_act");
     return 0;
 }
 

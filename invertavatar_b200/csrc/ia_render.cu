@@ -38,7 +38,6 @@ struct DecoderFrags {
     float b1[kHidden];
     float b2[kOutPad];
 };
-__device__ DecoderFrags g_dec;
 
 __device__ __forceinline__ uint32_t pack_half2(__half lo16, __half hi16) {
     return (uint32_t)__half_as_ushort(lo16) | ((uint32_t)__half_as_ushort(hi16) << 16);
@@ -53,7 +52,8 @@ __device__ __forceinline__ int phys_channel(int k) {   // logical layer-1 k inde
 }
 
 __global__ void decoder_stage_kernel(const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
-                                     const float* __restrict__ b2) {
+                                     const float* __restrict__ b2, DecoderFrags* __restrict__ out) {
+    DecoderFrags& g_dec = *out;
     const float g1 = 1.0f / sqrtf((float)kFeat), g2 = 1.0f / sqrtf((float)kHidden);
     // layer 1: B[k][n] = W1[n][phys(k)] * g1
     for (int i = threadIdx.x; i < 8 * 2 * 32; i += blockDim.x) {
@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1) render_kernel(const i
     // decoder fragments (shared by the CTA), then per-warp scratch
     DecoderFrags* dec = reinterpret_cast<DecoderFrags*>(smem);
     {
-        const uint4* src = reinterpret_cast<const uint4*>(&g_dec);
+        const uint4* src = reinterpret_cast<const uint4*>(p.scratch);
         uint4* dst = reinterpret_cast<uint4*>(dec);
         for (int i = threadIdx.x; i < (int)(sizeof(DecoderFrags) / 16); i += blockDim.x) dst[i] = src[i];
     }
@@ -563,6 +563,8 @@ __global__ void ray_sampler_kernel(const float* __restrict__ cam, int64_t cam_ld
 
 }  // namespace
 
+extern "C" int64_t ia_render_scratch_bytes(void) { return (int64_t)sizeof(DecoderFrags); }
+
 extern "C" int ia_ray_bounds(const float* cam, int64_t cam_ld, int32_t B, float* near_far, void* stream) {
     IA_CHECK(cam && near_far && B > 0, "ia_ray_bounds: bad arguments");
     ia::prof_begin("ia_ray_bounds", as_stream(stream));
@@ -583,12 +585,13 @@ extern "C" int ia_render(const ia_render_params* p, void* stream) {
     IA_CHECK(p && p->planes && (p->cam || (p->rays_o && p->rays_d)) && p->jitter && p->near_far && p->feat && p->depth && p->wsum && p->depth_minmax,
              "ia_render: null argument");
     IA_CHECK(p->w1 && p->b1 && p->w2 && p->b2, "ia_render: null decoder weights");
+    IA_CHECK(p->scratch && (reinterpret_cast<uintptr_t>(p->scratch) & 15) == 0, "ia_render: scratch of ia_render_scratch_bytes() bytes (16-byte aligned) required");
     IA_CHECK(p->Dc >= 4 && p->Dc <= 96 && p->Df >= 0 && p->Df <= 96, "ia_render: depth resolutions must be in [4,96] / [0,96]");
     IA_CHECK((p->plane_px_ld & 3) == 0 && p->plane_px_ld >= 96, "ia_render: planes need >= 96 channels, pixel stride multiple of 4");
     IA_CHECK(p->res > 0 && p->B > 0, "ia_render: empty batch");
     cudaStream_t st = as_stream(stream);
     ia::prof_begin("ia_render(decoder_stage)", st);
-    decoder_stage_kernel<<<1, 256, 0, st>>>(p->w1, p->b1, p->w2, p->b2);
+    decoder_stage_kernel<<<1, 256, 0, st>>>(p->w1, p->b1, p->w2, p->b2, reinterpret_cast<DecoderFrags*>(p->scratch));
     IA_LAUNCH_CHECK("ia_render(decoder_stage)");
     cudaError_t e = cudaSuccess;
     ia::prof_begin("ia_render(minmax_init)", st);

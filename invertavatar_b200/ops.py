@@ -102,9 +102,11 @@ def downsample2d(x, f, down=2, padding=0, flip_filter=False, gain=1, impl='cuda'
 # ---- filtered_lrelu.py ---------------------------------------------------------------------------------------------
 def filtered_lrelu(x, fu=None, fd=None, b=None, up=1, down=1, padding=0, gain=np.sqrt(2), slope=0.2, clamp=None, flip_filter=False,
                    impl='cuda'):
-    """bias -> upsample FIR -> leaky ReLU * gain, clamp -> downsample FIR (filtered_lrelu.py:58-121), as a composition of
-    the bias_act and upfirdn2d kernels -- the generic path the reference itself takes when no specialised kernel exists
-    (filtered_lrelu.py:225-231).  Only StyleGAN3 calls this op and no inference script instantiates StyleGAN3."""
+    """bias -> upsample FIR -> leaky ReLU * gain, clamp -> downsample FIR (filtered_lrelu.py:58-121).  impl='cuda': the
+    library's ia_filtered_lrelu (two kernels through an fp32 workspace, the replacement of
+    filtered_lrelu_plugin.filtered_lrelu, filtered_lrelu.cpp:20); impl='ref': the composition of the bias_act and upfirdn2d
+    kernels -- the generic path the reference itself takes when its plugin answers rc = -1 (filtered_lrelu.py:225-231).
+    Only StyleGAN3 calls this op and no inference script instantiates StyleGAN3."""
     assert isinstance(x, torch.Tensor) and x.ndim == 4
     _check_impl(impl)
     fu_w, fu_h = _get_filter_size(fu)
@@ -120,6 +122,11 @@ def filtered_lrelu(x, fu=None, fd=None, b=None, up=1, down=1, padding=0, gain=np
     in_dtype = x.dtype
     out_w = (in_w * up + (px0 + px1) - (fu_w - 1) - (fd_w - 1) + (down - 1)) // down
     out_h = (in_h * up + (py0 + py1) - (fu_h - 1) - (fd_h - 1) + (down - 1)) // down
+    if impl == 'cuda' and x.dtype in (torch.float16, torch.float32):
+        y = rt.filtered_lrelu(x, fu, fd, b, up=up, down=down, padding=[px0, px1, py0, py1], gain=gain, slope=slope, clamp=clamp,
+                              flip_filter=flip_filter)
+        assert tuple(y.shape) == (B, Cc, out_h, out_w) and y.dtype == in_dtype
+        return y
     x = bias_act(x=x, b=b)
     x = upfirdn2d(x=x, f=fu, up=up, padding=[px0, px1, py0, py1], gain=up ** 2, flip_filter=flip_filter)
     x = bias_act(x=x, act='lrelu', alpha=slope, gain=gain, clamp=clamp)

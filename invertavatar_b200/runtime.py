@@ -165,6 +165,9 @@ def from_nhwc(x):
 # ---------------------------------------------------------------------------------------------------
 # torch_utils/ops equivalents
 # ---------------------------------------------------------------------------------------------------
+DTYPE_IDS = {torch.float32: 0, torch.float16: 1, torch.float64: 2}     # IA_DTYPE_* (the element types the reference plugins dispatch)
+
+
 def bias_act(x, b=None, dim=1, act='linear', alpha=None, gain=None, clamp=None):
     _require_cuda(x, b)
     spec = ACT_DEFAULTS[act]
@@ -174,7 +177,7 @@ def bias_act(x, b=None, dim=1, act='linear', alpha=None, gain=None, clamp=None):
     if x.numel() == 0:
         return torch.empty_like(x)
     st = _enter(x)
-    xd = x if x.dtype == torch.float32 else x.float()
+    xd = x if x.dtype in DTYPE_IDS else x.float()      # f16 / f32 / f64 run natively (bias_act.cpp:81); anything else via fp32
     # dense in either contiguous or channels-last order: operate in memory order
     if xd.is_contiguous():
         xm, shape = xd, list(xd.shape)
@@ -191,11 +194,11 @@ def bias_act(x, b=None, dim=1, act='linear', alpha=None, gain=None, clamp=None):
     if b is not None:
         if b.ndim != 1 or b.shape[0] != shape[mdim]:
             raise RuntimeError('bias_act: bias must be 1-D and match x.shape[dim]')
-        b = _f32c(b)
+        b = b.to(xd.dtype).contiguous()
         Cn = shape[mdim]
         inner = int(np.prod(shape[mdim + 1:])) if mdim + 1 < len(shape) else 1
-    _C.check(_C.lib().ia_bias_act(_p(xd), _p(b), _p(y), xd.numel(), Cn, inner, ACT_IDS[act], alpha, gain, clamp, st), 'ia_bias_act')
-    return y if x.dtype == torch.float32 else y.to(x.dtype)
+    _C.check(_C.lib().ia_bias_act(_p(xd), _p(b), _p(y), xd.numel(), Cn, inner, ACT_IDS[act], alpha, gain, clamp, DTYPE_IDS[xd.dtype], st), 'ia_bias_act')
+    return y if y.dtype == x.dtype else y.to(x.dtype)
 
 
 def upfirdn2d(x, f, up=(1, 1), down=(1, 1), padding=(0, 0, 0, 0), flip_filter=False, gain=1.0):
@@ -205,7 +208,7 @@ def upfirdn2d(x, f, up=(1, 1), down=(1, 1), padding=(0, 0, 0, 0), flip_filter=Fa
     upx, upy = up
     downx, downy = down
     px0, px1, py0, py1 = [int(v) for v in padding]
-    xd = x if x.dtype == torch.float32 else x.float()
+    xd = x if x.dtype in DTYPE_IDS else x.float()      # f16 / f32 / f64 run natively (upfirdn2d.cpp:67)
     N, Cc, H, W = xd.shape
     if f is None:
         f = torch.ones(1, 1, dtype=torch.float32, device=x.device)
@@ -226,15 +229,72 @@ def upfirdn2d(x, f, up=(1, 1), down=(1, 1), padding=(0, 0, 0, 0), flip_filter=Fa
         if outW < 1 or outH < 1:
             raise RuntimeError('upfirdn2d: upsampled/padded signal is smaller than the filter')
         cl = cur.ndim == 4 and cur.stride(1) == 1 and c > 1
-        y = torch.empty((n, c, outH, outW), dtype=torch.float32, device=cur.device,
+        y = torch.empty((n, c, outH, outW), dtype=cur.dtype, device=cur.device,
                         memory_format=torch.channels_last if cl else torch.contiguous_format)
         p = _C.Upfirdn2dParams(_p(cur), _p(ff), _p(y), n, c, h, w, outH, outW, fh, fw, ux, uy, dx, dy, a0, b0,
                                1 if flip_filter else 0, float(g),
                                cur.stride(0), cur.stride(1), cur.stride(2), cur.stride(3),
-                               y.stride(0), y.stride(1), y.stride(2), y.stride(3))
+                               y.stride(0), y.stride(1), y.stride(2), y.stride(3), DTYPE_IDS[cur.dtype])
         _C.check(_C.lib().ia_upfirdn2d(C.byref(p), st), 'ia_upfirdn2d')
         cur = y
-    return cur if x.dtype == torch.float32 else cur.to(x.dtype)
+    return cur if cur.dtype == x.dtype else cur.to(x.dtype)
+
+
+def filtered_lrelu(x, fu=None, fd=None, b=None, up=1, down=1, padding=(0, 0, 0, 0), gain=math.sqrt(2), slope=0.2, clamp=None, flip_filter=False):
+    """filtered_lrelu_plugin.filtered_lrelu forward (filtered_lrelu.cpp:20): x [N,C,H,W] f16/f32 (any strides), fu/fd fp32 1-D
+    (separable) / 2-D / None, b [C] or None, padding = [px0,px1,py0,py1] -> y [N,C,outH,outW] in x's dtype and memory format."""
+    _require_cuda(x, fu, fd, b)
+    st = _enter(x)
+    if x.dtype not in (torch.float32, torch.float16):
+        raise RuntimeError('filtered_lrelu: x and b must be float16 or float32')       # filtered_lrelu.cpp:33
+    px0, px1, py0, py1 = [int(v) for v in padding]
+    N, Cc, H, W = x.shape
+
+    def fshape(f):
+        if f is None:
+            return None, 1, 1, 0
+        f = f.to(torch.float32).contiguous()
+        assert f.ndim in (1, 2)
+        return f, int(f.shape[-1]), (int(f.shape[0]) if f.ndim == 2 else int(f.shape[-1])), (int(f.shape[0]) if f.ndim == 2 else 0)
+    fu_t, fuw, fuh, fuh_field = fshape(fu)
+    fd_t, fdw, fdh, fdh_field = fshape(fd)
+    cw = W * up + px0 + px1 - (fuw - 1)
+    ch = H * up + py0 + py1 - (fuh - 1)
+    outW = (cw - (fdw - 1) + (down - 1)) // down
+    outH = (ch - (fdh - 1) + (down - 1)) // down
+    if outW < 1 or outH < 1:
+        raise RuntimeError('filtered_lrelu: output must be at least 1x1')
+    cl = x.stride(1) == 1 and Cc > 1
+    y = torch.empty((N, Cc, outH, outW), dtype=x.dtype, device=x.device, memory_format=torch.channels_last if cl else torch.contiguous_format)
+    if b is not None:
+        b = b.to(x.dtype).contiguous()
+    p = _C.FilteredLreluParams()
+    p.x, p.y, p.b, p.fu, p.fd = _p(x), _p(y), _p(b), _p(fu_t), _p(fd_t)
+    p.N, p.C, p.inH, p.inW, p.outH, p.outW = N, Cc, H, W, outH, outW
+    p.fuw, p.fuh, p.fdw, p.fdh = fuw, fuh_field, fdw, fdh_field
+    p.up, p.down, p.px0, p.px1, p.py0, p.py1 = int(up), int(down), px0, px1, py0, py1
+    p.gain, p.slope, p.clamp, p.flip = float(gain), float(slope), float(-1 if clamp is None else clamp), 1 if flip_filter else 0
+    p.xs_n, p.xs_c, p.xs_h, p.xs_w = x.stride()
+    p.ys_n, p.ys_c, p.ys_h, p.ys_w = y.stride()
+    p.dtype = DTYPE_IDS[x.dtype]
+    need = int(_C.lib().ia_filtered_lrelu_workspace(C.byref(p)))
+    if need < 0:
+        _C.check(1, 'ia_filtered_lrelu_workspace')
+    ws = torch.empty(max(need, 4), dtype=torch.uint8, device=x.device)
+    p.workspace, p.workspace_bytes = _p(ws), need
+    _C.check(_C.lib().ia_filtered_lrelu(C.byref(p), st), 'ia_filtered_lrelu')
+    return y
+
+
+def filtered_lrelu_act_(x, gain=math.sqrt(2), slope=0.2, clamp=None):
+    """In place clamp(lrelu(x) * gain) (filtered_lrelu_plugin.filtered_lrelu_act_, filtered_lrelu.cpp:217, without sign tensors)."""
+    _require_cuda(x)
+    st = _enter(x)
+    if x.dtype not in DTYPE_IDS or not (x.is_contiguous() or (x.ndim == 4 and x.is_contiguous(memory_format=torch.channels_last))):
+        raise RuntimeError('filtered_lrelu_act_: x must be a dense float16 / float32 / float64 tensor')
+    _C.check(_C.lib().ia_filtered_lrelu_act(_p(x), x.numel(), DTYPE_IDS[x.dtype], None, 0, 0, float(gain), float(slope),
+                                            float(-1 if clamp is None else clamp), 0, None, st), 'ia_filtered_lrelu_act')
+    return x
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -877,10 +937,13 @@ def render(planes_nhwc, cam, res, Dc, Df, jitter, u, box_warp, white_back, w1, b
     depth = torch.empty((B, res, res), dtype=torch.float32, device=dev)
     wsum = torch.empty_like(depth)
     mm = torch.empty(2, dtype=torch.float32, device=dev)
+    # per-call scratch for the staged decoder fragments (allocated on the launching stream by torch's caching allocator:
+    # the library keeps no mutable device state, so renders on different streams cannot race)
+    scratch = torch.empty(int(_C.lib().ia_render_scratch_bytes()), dtype=torch.uint8, device=dev)
     w1, b1, w2, b2 = _f32c(w1), _f32c(b1), _f32c(w2), _f32c(b2)
     p = _C.RenderParams(_p(planes_nhwc), PC, B, PH, PW, _p(cam), (cam.stride(0) if cam is not None else 0), _p(rays_o), _p(rays_d), res, Dc, Df, _p(jitter), _p(u),
                         float(box_warp), 1 if white_back else 0, _p(near_far), _p(w1), _p(b1), _p(w2), _p(b2),
-                        _p(feat), _p(depth), _p(wsum), _p(mm))
+                        _p(feat), _p(depth), _p(wsum), _p(mm), _p(scratch))
     _C.check(_C.lib().ia_render(C.byref(p), st), 'ia_render')
     _C.check(_C.lib().ia_depth_clamp(_p(depth), depth.numel(), _p(mm), st), 'ia_depth_clamp')
     return feat, depth, wsum

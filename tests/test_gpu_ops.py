@@ -213,3 +213,65 @@ def test_layout_grid_u8():
             out = glue.layout_grid(x, grid_w=gw, grid_h=gh)
             assert out.dtype == np.uint8 and out.shape == (gh * 20, gw * 12, 3)
             assert np.array_equal(out, ref.numpy())
+
+
+def test_plugin_dtypes_f16_f64():
+    """bias_act / upfirdn2d run natively on the element types the reference plugins dispatch (double, float, half:
+    bias_act.cpp:81, upfirdn2d.cpp:67) -- float arithmetic for half, double arithmetic for double."""
+    g = golden('ops.npz')
+    x, b = T(g['bias_act/x']), T(g['bias_act/b'])
+    for act in ('linear', 'lrelu', 'sigmoid', 'softplus', 'swish'):
+        y64 = rt.bias_act(x.double().to(DEV), b.double().to(DEV), act=act)
+        assert y64.dtype == torch.float64
+        close(y64, o_ops.bias_act(x.double(), b.double(), act=act), 1e-12, 'f64 ' + act)
+        xh, bh = x.half(), b.half()
+        y16 = rt.bias_act(xh.to(DEV), bh.to(DEV), act=act)
+        assert y16.dtype == torch.float16
+        want = o_ops.bias_act(xh.float(), bh.float(), act=act).half()        # float arithmetic, one rounding at the store
+        close(y16.float(), want.float(), 2e-3 * max(1.0, float(want.abs().max())), 'f16 ' + act)
+    xu, f = T(g['upfirdn2d/x']), T(g['upfirdn2d/f']).to(DEV)
+    y64 = rt.upfirdn2d(xu.double().to(DEV), f, up=(2, 2), padding=(2, 1, 2, 1), gain=4)
+    assert y64.dtype == torch.float64
+    close(y64, g['upfirdn2d/up2'], 1e-6)
+    y16 = rt.upfirdn2d(xu.half().to(DEV).contiguous(memory_format=torch.channels_last), f, up=(2, 2), padding=(2, 1, 2, 1), gain=4)
+    assert y16.dtype == torch.float16 and y16.is_contiguous(memory_format=torch.channels_last)
+    want = o_ops.upfirdn2d(xu.half().float(), T(g['upfirdn2d/f']), up=2, padding=[2, 1, 2, 1], gain=4)
+    close(y16.float(), want, 4e-3)
+
+
+def test_filtered_lrelu_export():
+    """ia_filtered_lrelu / ia_filtered_lrelu_act (filtered_lrelu.cpp:20,217) against the reference-minted vectors, the
+    library export and the bias_act/upfirdn2d composition (impl='ref'), fp32 and fp16, 1-D (separable) and 2-D filters."""
+    from invertavatar_b200 import ops
+    g = golden('ops.npz')
+    x, b, f = T(g['filtered_lrelu/x']).to(DEV), T(g['filtered_lrelu/b']).to(DEV), T(g['filtered_lrelu/f']).to(DEV)
+    for impl in ('cuda', 'ref'):
+        close(ops.filtered_lrelu(x, fu=f, fd=f, b=b, up=2, down=2, padding=3, clamp=0.9, impl=impl), g['filtered_lrelu/up2_down2'], 2e-6, impl)
+        close(ops.filtered_lrelu(x, b=b, impl=impl), g['filtered_lrelu/plain'], 1e-6, impl)
+    f2 = torch.outer(f, f)
+    close(ops.filtered_lrelu(x, fu=f2, fd=f2, b=b, up=2, down=2, padding=3, clamp=0.9), g['filtered_lrelu/up2_down2'], 2e-6, '2-D filters')
+    xc = x.expand(2, -1, -1, -1).contiguous(memory_format=torch.channels_last)
+    y = ops.filtered_lrelu(xc, fu=f, fd=f, b=b, up=2, down=2, padding=3, clamp=0.9)
+    assert y.is_contiguous(memory_format=torch.channels_last)
+    close(y[1:], g['filtered_lrelu/up2_down2'], 2e-6, 'channels-last')
+    yh = ops.filtered_lrelu(x.half(), fu=f, fd=f, b=b.half(), up=2, down=2, padding=3, clamp=0.9)
+    assert yh.dtype == torch.float16
+    close(yh.float(), o_ops.filtered_lrelu(x.half().float().cpu(), fu=f.cpu(), fd=f.cpu(), b=b.half().float().cpu(), up=2, down=2, padding=3, clamp=0.9), 2e-3)
+    xa = x.clone()
+    rt.filtered_lrelu_act_(xa, gain=1.5, slope=0.1, clamp=1.0)
+    close(xa, o_ops.bias_act(x.cpu(), None, act='lrelu', alpha=0.1, gain=1.5, clamp=1.0), 1e-6)
+
+
+def test_integration_stub_on_golden():
+    """The reference-side ctypes binding of INTEGRATION.md section 3, executed verbatim, on a reference-minted vector."""
+    from types import SimpleNamespace
+    from test_abi import integration_stub_namespace
+    g = golden('ops.npz')
+    fwd = integration_stub_namespace()['_bias_act_cuda_forward']
+    x, b = T(g['bias_act/x']).to(DEV), T(g['bias_act/b']).to(DEV)
+    for act in ('lrelu', 'sigmoid', 'linear'):
+        spec = SimpleNamespace(cuda_idx=rt.ACT_IDS[act])
+        y = fwd(x, b, 1, spec, rt.ACT_DEFAULTS[act][0], rt.ACT_DEFAULTS[act][1], None)
+        close(y, g[f'bias_act/{act}'], 2e-6, act)
+    y = fwd(x.half(), b.half(), 1, SimpleNamespace(cuda_idx=3), 0.2, 2 ** 0.5, 256.0)
+    close(y.float(), o_ops.bias_act(x.half().float().cpu(), b.half().float().cpu(), act='lrelu', clamp=256), 4e-3)
