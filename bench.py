@@ -470,6 +470,12 @@ def run_c2(args, rank, world, local, dev):
 
     parity = None
     with torch.no_grad():
+        # nvidia-smi sampler (every 200 ms) is started BEFORE the warm-up: its start-up (driver initialisation of a second
+        # process, ~0.5 s) stalls kernel launches for tens of milliseconds and must not land in a timed region
+        clocks = ClockSampler(local)
+        if rank == 0:
+            clocks.start()
+            time.sleep(1.0)
         for _ in range(max(args.warmup, 3)):
             step_resident()
         if peer is not None:   # the fused gather must reproduce the NCCL gather bit for bit
@@ -479,9 +485,7 @@ def run_c2(args, rank, world, local, dev):
             ok = torch.tensor([1 if torch.equal(gathered, peer.tensor) else 0], device=dev)
             dist.all_reduce(ok, op=dist.ReduceOp.MIN)
             assert int(ok.item()) == 1, 'fused peer-memory gather differs from the NCCL all-gather'
-        clocks = ClockSampler(local)
-        if rank == 0:
-            clocks.start()   # samples every 200 ms across both timed regions (resident + end-to-end)
+        clocks.rows.clear()     # keep only the samples taken from here on: both timed regions (resident + end-to-end)
         rt.reset_launch_count()
         ms = h.timed(step_resident, args.steps)
         launches = rt.launch_count()
@@ -619,11 +623,13 @@ def run_c3(args, rank, world, local, dev):
         return img
 
     with torch.no_grad():
-        for _ in range(max(args.warmup, 3)):
-            step_resident()
-        clocks = ClockSampler(local)
+        clocks = ClockSampler(local)      # started before the warm-up, see run_c2
         if rank == 0:
             clocks.start()
+            time.sleep(1.0)
+        for _ in range(max(args.warmup, 3)):
+            step_resident()
+        clocks.rows.clear()
         rt.reset_launch_count()
         ms = h.timed(step_resident, args.steps)
         launches = rt.launch_count()

@@ -197,6 +197,14 @@ typedef struct {
      * tiles the [B*(H+1)] x W concatenation of the images instead of every (H+1)-row phase grid on its own (a tile may span two
      * images; the zero row is the padding between them) -- fewer, fuller tiles.  mode 0, groups <= 1 only. */
     int32_t a_img_rows;
+    /* Split-K scratch (ia_conv_tc / ia_conv_tc_phases, persistent kernel; all NULL / 0: never split).  A launch with fewer
+     * output tiles than SMs splits the input channels over up to 16 CTAs per tile: partial accumulators go through
+     * splitk_ws (fp32, any contents), the last CTA to arrive on a tile's ticket in splitk_counters sums them in split order
+     * (deterministic) and runs the epilogue.  splitk_counters: splitk_n_counters int32, ZERO before the first launch that
+     * uses them -- every launch leaves them zero again.  Both buffers belong to ONE stream at a time (launches on the same
+     * stream may share them; concurrent streams need their own).  The split factor is clipped to what the buffers hold
+     * (per split: tiles x 256 x N-tile x 4 bytes; counters: 8 per tile). */
+    float* splitk_ws; int64_t splitk_ws_bytes; int32_t* splitk_counters; int32_t splitk_n_counters;
 } ia_conv_params;
 /* Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05.mma, TMEM accumulators, TMA-fed). */
 int ia_conv_tc(const ia_conv_params* p, void* stream);

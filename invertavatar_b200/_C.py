@@ -66,7 +66,8 @@ class ConvParams(C.Structure):
                 ('act', C.c_int32), ('alpha', C.c_float), ('gain', C.c_float), ('clamp', C.c_float),
                 ('emit', Emit),
                 ('groups', C.c_int32), ('imgs_per_group', C.c_int32), ('noise_gstride', C.c_int64),
-                ('img_prev', c_f32p), ('a_img_rows', C.c_int32)]
+                ('img_prev', c_f32p), ('a_img_rows', C.c_int32),
+                ('splitk_ws', c_f32p), ('splitk_ws_bytes', C.c_int64), ('splitk_counters', c_i32p), ('splitk_n_counters', C.c_int32)]
 
 
 class FirParams(C.Structure):

@@ -419,6 +419,10 @@ struct Tc2Params {
     int epi_vec4;                  // 1: Cout % 4 == 0 and every output pointer / pitch is 16-byte friendly -> epilogue_chunk_v4
     const float* img_prev;         // mode 2: previous-resolution image [B][OH/2][OW/2][Cout] (or null)
     int cat_rows, cat_B;           // > 0: the grid rows are the concatenation of cat_B images of cat_rows rows each (see launch_v2)
+    // split-K (plain variant): every tile is computed by `ksplit` CTAs, each over kc_per k-blocks of the input channels; the
+    // partial accumulators go through `ws`, the last CTA to arrive (ticket in `cnt`) sums them in split order and runs the epilogue
+    int ksplit, kc_per;
+    float4* ws; int* cnt;
 };
 
 
@@ -649,7 +653,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     const uint32_t crank = CL ? cluster_ctarank() : 0u;
     const int it_first = CL ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     const int it_step = CL ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-    const int it_end = CL ? p.total_pairs : p.total_tiles;
+    const int it_end = CL ? p.total_pairs : p.total_tiles * p.ksplit;
     // -> N tile, image, tile origin, sub-problem; `null_tile` (cluster padding) computes but stores nothing, `skip` (a tile
     // position outside this sub-problem's grid) is not executed at all -- every role takes the same decision.
     auto decode = [&](int it, int& n_idx, int& img, int& txi, int& tyi, int& pi, bool& null_tile, bool& skip) {
@@ -670,8 +674,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         // the same and every CTA draws (within one tile) the same number of tiles of each cost.  (An interleaved order gives a
         // CTA a random mix: max/mean load 1.2-1.5 on the (H+1)^2 phase grids of the 32^2..128^2 transposed convolutions.)
         null_tile = false; skip = false;
-        const int ch = it / p.chunk_tiles;
-        int r = it - ch * p.chunk_tiles;
+        const int tile_it = p.ksplit > 1 ? it / p.ksplit : it;       // schedule entry -> tile (the splits of a tile are adjacent entries)
+        const int ch = tile_it / p.chunk_tiles;
+        int r = tile_it - ch * p.chunk_tiles;
         const int per_ph = p.ic * p.n_tiles;
         pi = 0;
         while (pi + 1 < p.nph && r >= per_ph * p.ph_cum[pi + 1]) ++pi;
@@ -682,6 +687,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         const int il = r / T; r -= il * T;
         img = ch * p.ic + il;
         tyi = r / p.ph[pi].tiles_x; txi = r - tyi * p.ph[pi].tiles_x;
+    };
+    // k-blocks [kc0, kc1) of schedule entry `it` (split-K: a contiguous slice of the input channels; else all of them)
+    auto kc_range = [&](int it, int& kc0, int& kc1) {
+        if (CL || p.ksplit <= 1) { kc0 = 0; kc1 = p.Cin_blocks; return; }
+        const int sp = it % p.ksplit;
+        kc0 = sp * p.kc_per;
+        kc1 = min(kc0 + p.kc_per, p.Cin_blocks);
     };
 
     if (warp == 0) {
@@ -694,7 +706,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                 if (skip) continue;
                 const Tc2Phase& ph = p.ph[pi];
                 const int x0 = txi * p.tw, y0 = tyi * p.TH, col0 = n_idx * p.n_tile;
-                for (int kc = 0; kc < p.Cin_blocks; ++kc) {
+                int kc0, kc1;
+                kc_range(it, kc0, kc1);
+                for (int kc = kc0; kc < kc1; ++kc) {
                     for (int g = 0; g < ph.ngroups; ++g) {
                         const int as = (int)(a_it % (uint32_t)p.a_slots);
                         mbar_wait(a_empty(as), ((a_it / (uint32_t)p.a_slots) & 1u) ^ 1u);
@@ -744,7 +758,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                 const uint32_t d0 = tmem_base + (acc * 2u + 0u) * (uint32_t)p.acc_stride;
                 const uint32_t d1 = tmem_base + (acc * 2u + 1u) * (uint32_t)p.acc_stride;
                 bool first = true;
-                for (int kc = 0; kc < p.Cin_blocks; ++kc) {
+                int kc0, kc1;
+                kc_range(it, kc0, kc1);
+                for (int kc = kc0; kc < kc1; ++kc) {
                     for (int g = 0; g < ph.ngroups; ++g) {
                         const int as = (int)(a_it % (uint32_t)p.a_slots);
                         mbar_wait(a_full(as), (a_it / (uint32_t)p.a_slots) & 1u);
@@ -803,6 +819,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
             const int x0 = txi * p.tw, y0 = tyi * p.TH, col0 = n_idx * p.n_tile;
             mbar_wait(t_full(acc), (j >> 1) & 1u);
             tc_fence_after();
+            bool released_any = false;      // split-K releases the TMEM buffer as soon as the partials are parked
             {
                 const int row = lg * 32 + lane;
                 const int w_l = row & (p.tw - 1);
@@ -829,75 +846,136 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                 float racc[8][4];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) { racc[i][0] = 0.f; racc[i][1] = 0.f; racc[i][2] = 0.f; racc[i][3] = 0.f; }
+                bool vmask_done = false;     // split-K: another CTA of this tile runs the epilogue
+                // split-K: park this CTA's partial accumulators in the workspace ([tile][split][warp][chunk][8][32 lanes] float4: every
+                // store / load instruction moves one contiguous 512-byte run), release the TMEM buffer, take a ticket; the last of the
+                // tile's `ksplit` CTAs to arrive sums the partials in split order 0..ksplit-1 (the same order whoever arrives last:
+                // the result is deterministic) and runs the epilogue.  Rows are warp-private, so the ticket is per (tile, epilogue
+                // warp) and no CTA-wide synchronisation is needed.
+                const bool split = !CL && p.ksplit > 1;
+                const float4* ws_src = nullptr;
+                int64_t ws_sstride = 0;
+                if (split) {
+                    const int tile_it = it / p.ksplit, sp = it - tile_it * p.ksplit;
+                    const int nchunks = p.n_tile >> 5;
+                    const int wslot = warp - 2;
+                    float4* wsp = p.ws + (((int64_t)tile_it * p.ksplit + sp) * kEpiWarps2 + wslot) * (int64_t)(nchunks * 256);
 #pragma unroll 1
-                for (int c = 0; c < p.n_tile; c += 32) {
-                    uint32_t r[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + tcol + (uint32_t)c, r);
-                    if (vmask == 0u) continue;
-                    __syncwarp();
-                    if (p.epi_vec4) {
+                    for (int c = 0; c < p.n_tile; c += 32) {
+                        uint32_t r[32];
+                        tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + tcol + (uint32_t)c, r);
+                        if (vmask == 0u) continue;
+                        float4* dst = wsp + (c >> 5) * 256 + lane;
 #pragma unroll
                         for (int q = 0; q < 8; ++q)
-                            *reinterpret_cast<float4*>(tsm + lane * kTsmLd + 4 * q) =
-                                make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
-                        __syncwarp();
-                        const int co0 = col0 + c + 4 * (lane & 7);
-                        const bool cval = co0 < p.Cout;
-                        float4 dc4 = make_float4(1.f, 1.f, 1.f, 1.f), bs4 = make_float4(0.f, 0.f, 0.f, 0.f), s14 = dc4, s24 = dc4;
-                        if (cval) {
-                            if (p.mode == 1) {
-                                if (p.dcoef) dc4 = *reinterpret_cast<const float4*>(p.dcoef + (int64_t)img * p.Cout + co0);
-                                if (bias_g) bs4 = *reinterpret_cast<const float4*>(bias_g + co0);
-                            } else if (p.mode == 2) {
-                                if (bias_g) bs4 = *reinterpret_cast<const float4*>(bias_g + co0);
-                            }
-                            if (p.emit.hi1 && p.emit.s1) s14 = *reinterpret_cast<const float4*>(p.emit.s1 + (int64_t)img * p.Cout + co0);
-                            if (p.emit.hi2 && p.emit.s2) s24 = *reinterpret_cast<const float4*>(p.emit.s2 + (int64_t)img * p.Cout + co0);
-                        }
-                        // rows of lanes whose channel group is past Cout are masked out, the shuffles inside stay warp-wide
-                        const uint32_t vm = cval ? vmask : 0u;
-                        float* o32 = p.emit.out32 ? p.emit.out32 + img_pix0 * p.emit.out32_ld + co0 : nullptr;
-                        uint16_t* h1 = p.emit.hi1 ? p.emit.hi1 + img_pix1 * p.emit.c1_pad + co0 : nullptr;
-                        uint16_t* l1 = p.emit.hi1 ? p.emit.lo1 + img_pix1 * p.emit.c1_pad + co0 : nullptr;
-                        uint16_t* h2 = p.emit.hi2 ? p.emit.hi2 + img_pix0 * p.emit.c2_pad + co0 : nullptr;
-                        uint16_t* l2 = p.emit.hi2 ? p.emit.lo2 + img_pix0 * p.emit.c2_pad + co0 : nullptr;
-                        RgbLane rg;
-                        rg.s = make_float4(1.f, 1.f, 1.f, 1.f);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) rg.w[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (rgb && cval) {
-                            if (p.emit.rgb_s) rg.s = *reinterpret_cast<const float4*>(p.emit.rgb_s + (int64_t)img * p.Cout + co0);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                if (j < p.emit.rgb_n) rg.w[j] = *reinterpret_cast<const float4*>(p.emit.rgb_w + (int64_t)j * p.Cout + co0);
-                        }
-                        if (p.mode == 2) {
-                            const float* prev = p.img_prev ? p.img_prev + (int64_t)img * (p.OH >> 1) * (p.OW >> 1) * p.Cout + co0 : nullptr;
-                            epilogue_chunk_v4_torgb(p, tsm, lane, vm, my_pix, o32, bs4, prev);
-                        }
-                        else if (p.mode == 0) epilogue_chunk_v4_dispatch<0>(p, tsm, lane, vm, my_pix, my_nz, o32, h1, l1, h2, l2, dc4, bs4, s14, s24, rg, racc, false);
-                        else if (p.act == IA_ACT_LRELU) epilogue_chunk_v4_dispatch<IA_ACT_LRELU>(p, tsm, lane, vm, my_pix, my_nz, o32, h1, l1, h2, l2, dc4, bs4, s14, s24, rg, racc, rgb);
-                        else if (p.act == IA_ACT_LINEAR && !rgb) epilogue_chunk_v4_dispatch<IA_ACT_LINEAR>(p, tsm, lane, vm, my_pix, my_nz, o32, h1, l1, h2, l2, dc4, bs4, s14, s24, rg, racc, false);
-                        else epilogue_chunk_v4_dispatch<-1>(p, tsm, lane, vm, my_pix, my_nz, o32, h1, l1, h2, l2, dc4, bs4, s14, s24, rg, racc, rgb);
-                        continue;
+                            dst[q * 32] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
                     }
-#pragma unroll
-                    for (int q = 0; q < 32; ++q) tsm[lane * 33 + q] = __uint_as_float(r[q]);
+                    tc_fence_before();
                     __syncwarp();
-                    const int co = col0 + c + lane;
-                    const bool cvalid = co < p.Cout;
-                    float dc = 1.f, bs = 0.f, s1v = 1.f, s2v = 1.f;
-                    if (cvalid) {
-                        if (p.mode == 1) { if (p.dcoef) dc = p.dcoef[(int64_t)img * p.Cout + co]; if (bias_g) bs = bias_g[co]; }
-                        if (p.emit.hi1 && p.emit.s1) s1v = p.emit.s1[(int64_t)img * p.Cout + co];
-                        if (p.emit.hi2 && p.emit.s2) s2v = p.emit.s2[(int64_t)img * p.Cout + co];
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(t_empty(acc)) : "memory");
+                    released_any = true;
+                    vmask_done = true;
+                    if (vmask != 0u) {      // (vmask depends on the tile only: all splits of a tile take the same branch)
+                        __threadfence();
+                        __syncwarp();
+                        int ticket = 0;
+                        int* cnt = p.cnt + tile_it * kEpiWarps2 + wslot;
+                        if (lane == 0) ticket = atomicAdd(cnt, 1);
+                        ticket = __shfl_sync(0xffffffffu, ticket, 0);
+                        if (ticket == p.ksplit - 1) {
+                            if (lane == 0) *cnt = 0;       // every split has arrived: leave the counter ready for the next launch
+                            __threadfence();
+                            vmask_done = false;
+                            ws_src = p.ws + (((int64_t)tile_it * p.ksplit) * kEpiWarps2 + wslot) * (int64_t)(nchunks * 256);
+                            ws_sstride = (int64_t)kEpiWarps2 * nchunks * 256;
+                        }
                     }
-                    if (p.mode == 0) epilogue_chunk<0>(p, tsm, lane, vmask, my_pix, my_nz, img_pix0, img_pix1, co, cvalid, dc, bs, s1v, s2v);
-                    else if (p.act == IA_ACT_LRELU) epilogue_chunk<IA_ACT_LRELU>(p, tsm, lane, vmask, my_pix, my_nz, img_pix0, img_pix1, co, cvalid, dc, bs, s1v, s2v);
-                    else if (p.act == IA_ACT_LINEAR) epilogue_chunk<IA_ACT_LINEAR>(p, tsm, lane, vmask, my_pix, my_nz, img_pix0, img_pix1, co, cvalid, dc, bs, s1v, s2v);
-                    else epilogue_chunk<-1>(p, tsm, lane, vmask, my_pix, my_nz, img_pix0, img_pix1, co, cvalid, dc, bs, s1v, s2v);
                 }
-                if (rgb && vmask != 0u) {
+                if (!vmask_done) {
+#pragma unroll 1
+                    for (int c = 0; c < p.n_tile; c += 32) {
+                        uint32_t r[32];
+                        if (!split) {
+                            tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + tcol + (uint32_t)c, r);
+                        } else {
+                            const float4* src = ws_src + (c >> 5) * 256 + lane;
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                float4 a = __ldcg(src + q * 32);
+                                for (int s2 = 1; s2 < p.ksplit; ++s2) {
+                                    const float4 b = __ldcg(src + (int64_t)s2 * ws_sstride + q * 32);
+                                    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+                                }
+                                r[4 * q] = __float_as_uint(a.x); r[4 * q + 1] = __float_as_uint(a.y);
+                                r[4 * q + 2] = __float_as_uint(a.z); r[4 * q + 3] = __float_as_uint(a.w);
+                            }
+                        }
+                        if (vmask == 0u) continue;
+                        __syncwarp();
+                        if (p.epi_vec4) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q)
+                                *reinterpret_cast<float4*>(tsm + lane * kTsmLd + 4 * q) =
+                                    make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+                            __syncwarp();
+                            const int co0 = col0 + c + 4 * (lane & 7);
+                            const bool cval = co0 < p.Cout;
+                            float4 dc4 = make_float4(1.f, 1.f, 1.f, 1.f), bs4 = make_float4(0.f, 0.f, 0.f, 0.f), s14 = dc4, s24 = dc4;
+                            if (cval) {
+                                if (p.mode == 1) {
+                                    if (p.dcoef) dc4 = *reinterpret_cast<const float4*>(p.dcoef + (int64_t)img * p.Cout + co0);
+                                    if (bias_g) bs4 = *reinterpret_cast<const float4*>(bias_g + co0);
+                                } else if (p.mode == 2) {
+                                    if (bias_g) bs4 = *reinterpret_cast<const float4*>(bias_g + co0);
+                                }
+                                if (p.emit.hi1 && p.emit.s1) s14 = *reinterpret_cast<const float4*>(p.emit.s1 + (int64_t)img * p.Cout + co0);
+                                if (p.emit.hi2 && p.emit.s2) s24 = *reinterpret_cast<const float4*>(p.emit.s2 + (int64_t)img * p.Cout + co0);
+                            }
+                            // rows of lanes whose channel group is past Cout are masked out, the shuffles inside stay warp-wide
+                            const uint32_t vm = cval ? vmask : 0u;
+                            float* o32 = p.emit.out32 ? p.emit.out32 + img_pix0 * p.emit.out32_ld + co0 : nullptr;
+                            uint16_t* h1 = p.emit.hi1 ? p.emit.hi1 + img_pix1 * p.emit.c1_pad + co0 : nullptr;
+                            uint16_t* l1 = p.emit.hi1 ? p.emit.lo1 + img_pix1 * p.emit.c1_pad + co0 : nullptr;
+                            uint16_t* h2 = p.emit.hi2 ? p.emit.hi2 + img_pix0 * p.emit.c2_pad + co0 : nullptr;
+                            uint16_t* l2 = p.emit.hi2 ? p.emit.lo2 + img_pix0 * p.emit.c2_pad + co0 : nullptr;
+                            RgbLane rg;
+                            rg.s = make_float4(1.f, 1.f, 1.f, 1.f);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) rg.w[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (rgb && cval) {
+                                if (p.emit.rgb_s) rg.s = *reinterpret_cast<const float4*>(p.emit.rgb_s + (int64_t)img * p.Cout + co0);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    if (j < p.emit.rgb_n) rg.w[j] = *reinterpret_cast<const float4*>(p.emit.rgb_w + (int64_t)j * p.Cout + co0);
+                            }
+                            if (p.mode == 2) {
+                                const float* prev = p.img_prev ? p.img_prev + (int64_t)img * (p.OH >> 1) * (p.OW >> 1) * p.Cout + co0 : nullptr;
+                                epilogue_chunk_v4_torgb(p, tsm, lane, vm, my_pix, o32, bs4, prev);
+                            }
+                            else if (p.mode == 0) epilogue_chunk_v4_dispatch<0>(p, tsm, lane, vm, my_pix, my_nz, o32, h1, l1, h2, l2, dc4, bs4, s14, s24, rg, racc, false);
+                            else if (p.act == IA_ACT_LRELU) epilogue_chunk_v4_dispatch<IA_ACT_LRELU>(p, tsm, lane, vm, my_pix, my_nz, o32, h1, l1, h2, l2, dc4, bs4, s14, s24, rg, racc, rgb);
+                            else if (p.act == IA_ACT_LINEAR && !rgb) epilogue_chunk_v4_dispatch<IA_ACT_LINEAR>(p, tsm, lane, vm, my_pix, my_nz, o32, h1, l1, h2, l2, dc4, bs4, s14, s24, rg, racc, false);
+                            else epilogue_chunk_v4_dispatch<-1>(p, tsm, lane, vm, my_pix, my_nz, o32, h1, l1, h2, l2, dc4, bs4, s14, s24, rg, racc, rgb);
+                            continue;
+                        }
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) tsm[lane * 33 + q] = __uint_as_float(r[q]);
+                        __syncwarp();
+                        const int co = col0 + c + lane;
+                        const bool cvalid = co < p.Cout;
+                        float dc = 1.f, bs = 0.f, s1v = 1.f, s2v = 1.f;
+                        if (cvalid) {
+                            if (p.mode == 1) { if (p.dcoef) dc = p.dcoef[(int64_t)img * p.Cout + co]; if (bias_g) bs = bias_g[co]; }
+                            if (p.emit.hi1 && p.emit.s1) s1v = p.emit.s1[(int64_t)img * p.Cout + co];
+                            if (p.emit.hi2 && p.emit.s2) s2v = p.emit.s2[(int64_t)img * p.Cout + co];
+                        }
+                        if (p.mode == 0) epilogue_chunk<0>(p, tsm, lane, vmask, my_pix, my_nz, img_pix0, img_pix1, co, cvalid, dc, bs, s1v, s2v);
+                        else if (p.act == IA_ACT_LRELU) epilogue_chunk<IA_ACT_LRELU>(p, tsm, lane, vmask, my_pix, my_nz, img_pix0, img_pix1, co, cvalid, dc, bs, s1v, s2v);
+                        else if (p.act == IA_ACT_LINEAR) epilogue_chunk<IA_ACT_LINEAR>(p, tsm, lane, vmask, my_pix, my_nz, img_pix0, img_pix1, co, cvalid, dc, bs, s1v, s2v);
+                        else epilogue_chunk<-1>(p, tsm, lane, vmask, my_pix, my_nz, img_pix0, img_pix1, co, cvalid, dc, bs, s1v, s2v);
+                    }
+                }
+                if (rgb && vmask != 0u && !vmask_done) {
                     // sum the partial contractions of the 8 lanes that share a row (their 4-channel groups), then lane c4 == 0 adds
                     // this N tile's share into the zero-filled output (one add per N tile: two tiles commute, the result is exact)
                     const int rs = lane >> 3;
@@ -924,7 +1002,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(t_empty(acc)) : "memory");
+            if (!released_any && lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(t_empty(acc)) : "memory");
             ++j;
         }
     }
@@ -1006,7 +1084,21 @@ int launch_v2(const ia_conv_params* const* ps, int nph, void* stream) {
     for (int q = 0; q < nph; ++q) real_tiles += cdiv(cat ? rowsB : ps[q]->GH, t.TH) * cdiv(ps[q]->GW, t.tw) * t.B;
     t.Cin_blocks = p->Cin_pad / BK;
     t.Cout = p->Cout; t.Cout_pad = p->Cout_pad;
+    if (g_sm_count == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+        if (g_sm_count <= 0) g_sm_count = 148;
+    }
     int n_tile = 32;
+    // Split-K (needs the caller's workspace + ticket counters): a launch with fewer tiles than SMs keeps the WIDEST N tile --
+    // every activation tile is then amortised over 128 output channels instead of being re-read by 4 narrow-tile CTAs -- and is
+    // spread over the idle SMs by splitting the input channels instead.  Measured motivation (round 1): 1024->512 @16^2 x 4
+    // images ran as 64 CTAs of N=32 with a serial chain of 288 (tap, k-block) stages each: 203 us, 48 TF/s.
+    int ksplit = 1;
+    static int splitk_max = -1;    // IA_CONV_SPLITK: 0 = off, n = upper bound on the split factor (default 16)
+    if (splitk_max < 0) { const char* ev = getenv("IA_CONV_SPLITK"); splitk_max = ev ? atoi(ev) : 16; }
+    const bool can_split = splitk_max > 1 && p->splitk_ws && p->splitk_counters && !p->emit.rgb_out;
     for (int cand = 128; cand >= 32; cand -= 32) {
         if (p->Cout_pad % cand) continue;
         n_tile = cand;
@@ -1015,11 +1107,45 @@ int launch_v2(const ia_conv_params* const* ps, int nph, void* stream) {
         // 16x16 x 24 images: 96 CTAs of N=128 take 126 us, 384 CTAs of N=32 take 213 us); IA_CONV_MIN_TILES overrides
         static int min_tiles = -1;
         if (min_tiles < 0) { const char* ev = getenv("IA_CONV_MIN_TILES"); min_tiles = ev ? atoi(ev) : 48; }
+        if (can_split) break;
         if (real_tiles * (p->Cout_pad / cand) >= min_tiles) break;
         // fused ToRGB: every N tile adds its share into the same pixels; with at most two tiles the two adds commute and the
         // result does not depend on their order -> take the widest tile whatever the grid size
         if (p->emit.rgb_out) break;
     }
+    if (can_split) {
+        const int64_t tiles = real_tiles * (p->Cout_pad / n_tile);
+        const int cin_blocks = p->Cin_pad / BK;
+        static int min_kc = -1;        // IA_CONV_SPLITK_MIN_KC: fewest k-blocks a split may get (default 2 = 64 channels x all taps)
+        if (min_kc < 0) { const char* ev = getenv("IA_CONV_SPLITK_MIN_KC"); min_kc = ev ? atoi(ev) : 2; if (min_kc < 1) min_kc = 1; }
+        if (tiles * 4 < (int64_t)g_sm_count * 3 && cin_blocks >= 2 * min_kc) {
+            int want = (int)(g_sm_count / tiles);                         // splits that fill the machine once
+            if (want > splitk_max) want = splitk_max;
+            if (want > cin_blocks / min_kc) want = cin_blocks / min_kc;
+            // workspace / counter capacity
+            const int64_t per_split = tiles * 256 * (int64_t)n_tile * 4;
+            if (per_split > 0 && want > p->splitk_ws_bytes / per_split) want = (int)(p->splitk_ws_bytes / per_split);
+            if (tiles * kEpiWarps2 > p->splitk_n_counters) want = 1;
+            if (want > 1) {
+                const int kc_per = (cin_blocks + want - 1) / want;
+                ksplit = (cin_blocks + kc_per - 1) / kc_per;                 // every split non-empty
+                t.kc_per = kc_per;
+            }
+        }
+        if (ksplit <= 1) {
+            // not split after all: fall back to the narrow-tile rule
+            for (int cand = 128; cand >= 32; cand -= 32) {
+                if (p->Cout_pad % cand) continue;
+                n_tile = cand;
+                static int min_tiles2 = -1;
+                if (min_tiles2 < 0) { const char* ev = getenv("IA_CONV_MIN_TILES"); min_tiles2 = ev ? atoi(ev) : 48; }
+                if (real_tiles * (p->Cout_pad / cand) >= min_tiles2) break;
+            }
+        }
+    }
+    t.ksplit = ksplit;
+    if (ksplit <= 1) { t.ksplit = 1; t.kc_per = p->Cin_pad / BK; }
+    t.ws = reinterpret_cast<float4*>(p->splitk_ws); t.cnt = p->splitk_counters;
     t.n_tile = n_tile; t.acc_stride = 128;
     t.n_tiles = p->Cout_pad / n_tile;
     t.total_tiles = t.m_tiles * t.n_tiles;
@@ -1068,6 +1194,7 @@ int launch_v2(const ia_conv_params* const* ps, int nph, void* stream) {
         int next = n_tile - 32;
         while (next > 32 && p->Cout_pad % next) next -= 32;
         n_tile = next;
+        t.ksplit = 1; t.kc_per = p->Cin_pad / BK;      // (the split plan was sized for the wider tile)
         t.n_tile = n_tile; t.n_tiles = p->Cout_pad / n_tile; t.total_tiles = t.m_tiles * t.n_tiles;
         t.b_tx = (uint32_t)n_tile * BK * 2u;
         t.b_bytes = (t.b_tx + 1023u) & ~1023u;
@@ -1181,7 +1308,7 @@ int launch_v2(const ia_conv_params* const* ps, int nph, void* stream) {
     t.m_tiles_p = (t.m_tiles + 1) & ~1;
     t.total_pairs = (t.m_tiles_p * t.n_tiles) / 2;
     const int sm_even = g_sm_count & ~1;
-    if (use_cluster && nph == 1 && p->groups <= 1 && t.total_pairs >= sm_even / 2) {
+    if (use_cluster && nph == 1 && p->groups <= 1 && t.total_pairs >= sm_even / 2 && t.ksplit <= 1) {
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
         cfg.gridDim = dim3((unsigned)sm_even, 1, 1);
@@ -1198,7 +1325,7 @@ int launch_v2(const ia_conv_params* const* ps, int nph, void* stream) {
         IA_LAUNCH_CHECK("ia_conv_tc");
         return 0;
     }
-    const int64_t real_total = real_tiles * t.n_tiles;
+    const int64_t real_total = real_tiles * t.n_tiles * t.ksplit;
     const int grid = real_total < g_sm_count ? (int)real_total : g_sm_count;
     ia::prof_begin(ia::prof_detail_name("ia_conv_tc", taps_sum, GHm, GWm, p->Cin_pad, p->Cout), as_stream(stream));
     conv_tc2_kernel<BK, false><<<grid, kThreads2, smem, as_stream(stream)>>>(ma_hi, ma_lo, mw_hi, mw_lo, t);

@@ -574,6 +574,24 @@ def _emit(out32=None, e1=None, e2=None, rgb=None):
     return e
 
 
+_SPLITK = {}
+_SPLITK_WS_BYTES = 48 << 20          # fp32 partial accumulators: tiles x 256 pixels x N tile x splits (<= ~150 tile-splits of 128 KB)
+_SPLITK_COUNTERS = 4096              # 8 tickets per tile; split launches have fewer tiles than SMs
+
+
+def _splitk_scratch(p, device, st):
+    """Split-K workspace + ticket counters of (device, stream): owned by one stream at a time, as ia_conv_params asks (launches of
+    a stream are ordered; the counters are zero between launches).  Persistent, so CUDA-graph captures may hold them."""
+    if os.environ.get('IA_CONV_SPLITK', '') == '0':
+        return
+    key = (device.index, int(st or 0))
+    buf = _SPLITK.get(key)
+    if buf is None:
+        buf = (torch.empty(_SPLITK_WS_BYTES // 4, dtype=torch.float32, device=device), torch.zeros(_SPLITK_COUNTERS, dtype=torch.int32, device=device))
+        _SPLITK[key] = buf
+    p.splitk_ws, p.splitk_ws_bytes, p.splitk_counters, p.splitk_n_counters = _p(buf[0]), _SPLITK_WS_BYTES, _p(buf[1]), _SPLITK_COUNTERS
+
+
 def _conv_call(p, st, impl=None):
     impl = impl or _conv_impl
     fn = _C.lib().ia_conv_tc if impl == 'tc' else _C.lib().ia_conv_simt
@@ -617,6 +635,7 @@ def conv_same(hi, lo, pack, Cin_pad, out32, dcoef=None, noise=None, noise_streng
         p.img_prev = _p(img_prev)
     _set_group(p, group)
     _count_conv(B, H, W, pack, k * k, stride=alg_stride)
+    _splitk_scratch(p, hi.device, st)
     _conv_call(p, st, impl)
 
 
@@ -663,6 +682,7 @@ def conv_transpose_up2_raw(hi, lo, pack, Cin_pad, raw, impl=None, group=None, im
             p.emit = _emit(raw)
             p.a_img_rows = int(img_rows) if img_rows and img_rows != H else 0
             _set_group(p, group)
+            _splitk_scratch(p, hi.device, st)
     _count_conv(B, H, W, pack, 9)
     if (impl or _conv_impl) == 'tc':
         _C.check(_C.lib().ia_conv_tc_phases(phases, 4, st), 'ia_conv_tc_phases')     # one persistent launch for the four phases

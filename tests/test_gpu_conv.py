@@ -235,3 +235,38 @@ def test_row_padded_operand_layout_bit_identical(monkeypatch):
         outs[flag] = [t.clone() for t in a] + [b.clone()]
     for x, y in zip(outs['1'], outs['0']):
         assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize('B,H,cin,cout,k', [(4, 16, 1024, 512, 3), (4, 32, 256, 256, 3), (1, 16, 512, 512, 3), (2, 32, 384, 96, 1), (3, 24, 200, 72, 3)])
+def test_split_k_matches_unsplit_and_is_deterministic(monkeypatch, B, H, cin, cout, k):
+    """Low-resolution / small-batch convolutions (the encoder UNets, the <= 32^2 generator layers) split their input channels
+    over several CTAs per tile; the partial accumulators are summed in split order by the last CTA to arrive, so the result
+    (a) equals the unsplit kernel up to fp32 reassociation, (b) matches fp32 conv2d on the CPU and (c) is bit-identical from
+    run to run."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(B * 100 + H + cin)
+    x = torch.randn(B, cin, H, H, generator=g)
+    conv = torch.nn.Conv2d(cin, cout, k, padding=k // 2, bias=False).requires_grad_(False)
+    conv.weight.copy_(torch.randn(conv.weight.shape, generator=g) / np.sqrt(cin * k * k))
+    want = F.conv2d(x, conv.weight, padding=k // 2).permute(0, 2, 3, 1)
+    conv = conv.to(DEV)
+    xn = x.to(DEV).permute(0, 2, 3, 1)
+    pack = rt.ConvPack.current(conv, '_ia_pack', conv.weight, need_wsq=False)
+
+    def run():
+        a, _ = rt.enc_prep([xn], C_pad=pack.Cin_pad)
+        return rt.enc_conv(a, conv).clone()
+    monkeypatch.setenv('IA_CONV_SPLITK', '0')
+    plain = run()
+    monkeypatch.delenv('IA_CONV_SPLITK')
+    s1 = run()
+    s2 = run()
+    torch.cuda.synchronize()
+    scale = max(1.0, float(want.abs().max()))
+    assert maxerr(plain, want) <= TOL * scale
+    assert maxerr(s1, want) <= TOL * scale, maxerr(s1, want)
+    assert maxerr(s1, plain) <= TOL * scale       # (fp32 accumulation order differs: K = 9 * cin products per output)
+    assert torch.equal(s1, s2), 'split-K sum order must not depend on the arrival order of the CTAs'
+    # the ticket counters are left at zero for the next launch
+    for ws, cnt in rt._SPLITK.values():
+        assert int(cnt.abs().max()) == 0

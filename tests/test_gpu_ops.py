@@ -223,7 +223,9 @@ def test_plugin_dtypes_f16_f64():
     for act in ('linear', 'lrelu', 'sigmoid', 'softplus', 'swish'):
         y64 = rt.bias_act(x.double().to(DEV), b.double().to(DEV), act=act)
         assert y64.dtype == torch.float64
-        close(y64, o_ops.bias_act(x.double(), b.double(), act=act), 1e-12, 'f64 ' + act)
+        # (alpha / gain travel as C floats, as in the reference plugin's bias_act_kernel_params: 0.2 and sqrt(2) are rounded to fp32)
+        close(y64, o_ops.bias_act(x.double(), b.double(), act=act, alpha=float(np.float32(rt.ACT_DEFAULTS[act][0])),
+                                  gain=float(np.float32(rt.ACT_DEFAULTS[act][1]))), 1e-12, 'f64 ' + act)
         xh, bh = x.half(), b.half()
         y16 = rt.bias_act(xh.to(DEV), bh.to(DEV), act=act)
         assert y16.dtype == torch.float16
