@@ -57,6 +57,13 @@ def parse_args():
     return ap.parse_args()
 
 
+def _conv_precision():
+    if os.environ.get('IA_CONV_PRECISION', 'auto') == 'bf16x3':
+        return 'bf16x3 split operands (hi*hi+hi*lo+lo*hi) in every convolution, fp32 accumulate in TMEM'
+    return ('per layer (profiles/r2_conv_precision_probe*.json): backbone 3x3 convolutions single-pass fp16 operands, super-resolution and '
+            'ToRGB convolutions bf16x3 split operands (hi*hi+hi*lo+lo*hi); fp32 accumulate in TMEM; encoder convolutions bf16x3')
+
+
 def workload_config(args, n_gpus, frames_per_step=None):
     fps = args.batch if frames_per_step is None else frames_per_step
     if args.workload == 'c3':
@@ -65,13 +72,13 @@ def workload_config(args, n_gpus, frames_per_step=None):
                 'frames_per_gpu_per_step': T_C3, 'global_frames_per_step': T_C3 * n_gpus, 'identities_per_gpu_per_step': 1,
                 'neural_res': args.res, 'depth_samples': [args.depth, args.depth],
                 'parallelism': f'{n_gpus} replica(s): identities are independent, the ConvGRU state is sequential inside one',
-                'conv_precision': 'bf16x3 split operands (hi*hi+hi*lo+lo*hi), fp32 accumulate in TMEM', 'gather': 'none',
+                'conv_precision': _conv_precision(), 'gather': 'none',
                 'l2': 'working set per step exceeds the 126 MB L2; no explicit flush'}
     return {'workload': f'Next3D++ reenactment 512^2, {args.res}^2 neural x {args.depth}+{args.depth} depth, batch {fps}/GPU '
                         f'(BASELINE configs[1]), random-init generator, synthetic latents/cameras/UV',
             'frames_per_gpu_per_step': fps, 'global_frames_per_step': fps * n_gpus,
             'neural_res': args.res, 'depth_samples': [args.depth, args.depth], 'parallelism': f'dp{n_gpus} (frames sharded, weights replicated)',
-            'conv_precision': 'bf16x3 split operands (hi*hi+hi*lo+lo*hi), fp32 accumulate in TMEM', 'gather': getattr(args, 'gather_kind', 'none'),
+            'conv_precision': _conv_precision(), 'gather': getattr(args, 'gather_kind', 'none'),
             'l2': 'working set per step (>10 GB of activations) exceeds the 126 MB L2; no explicit flush'}
 
 
@@ -127,7 +134,14 @@ class ClockSampler:
                 if len(r) > col and r[col].lower().startswith('active'):
                     reasons.add(name)
         sm.sort()
-        return {'sm_mhz': (sm[len(sm) // 2] if sm else None), 'sm_max_mhz': mx, 'reasons': sorted(reasons), 'samples': len(sm)}
+        pw = []
+        for r in self.rows:
+            try:
+                pw.append(float(r[3]))
+            except (ValueError, IndexError):
+                pass
+        return {'sm_mhz': (sm[len(sm) // 2] if sm else None), 'sm_max_mhz': mx, 'reasons': sorted(reasons), 'samples': len(sm),
+                'sm_mhz_min': (sm[0] if sm else None), 'power_w_max': (max(pw) if pw else None)}
 
 
 def _psnr(a, b):

@@ -139,6 +139,15 @@ typedef struct {
 int ia_styles(const ia_style_layer* layers_dev, const ia_style_layer* layers_host, int32_t n_layers,
               const float* ws, int32_t B, int32_t num_ws, void* stream);
 
+/* Operand formats of the tensor-core convolution (both operands of a launch share one).
+ *   IA_OPFMT_BF16X3: a pair of bf16 tensors (hi = rn(v), lo = rn(v - hi)); hi*hi + hi*lo + lo*hi, fp32 accumulate: fp32-grade
+ *                    products (2^-16 relative), three MMAs per k-step.
+ *   IA_OPFMT_F16X1 : ONE fp16 tensor (rn(v), saturated to +-65504); a single MMA per k-step, 2^-11 relative per operand.  Chosen
+ *                    per layer by the host from a measured error budget (profiles/r2_conv_precision_probe.json): the three
+ *                    backbones tolerate it (final image 1e-4..3e-4 max-abs vs fp32), the super-resolution blocks do not.
+ * The `lo` pointers of an F16X1 operand are ignored (may be NULL). */
+enum { IA_OPFMT_BF16X3 = 0, IA_OPFMT_F16X1 = 1 };
+
 /* Prepare the tensor-core A operand: v = x * styles[b][c] (optionally after x = cond*a + x*(1-a), the
  * cond_list blend of networks_stylegan2_new.py:538-540), then split into bf16 hi/lo, zero-padded to C_pad. */
 typedef struct {
@@ -149,12 +158,14 @@ typedef struct {
     uint16_t* hi; uint16_t* lo;               /* bf16 [B][HW][C_pad] */
     int32_t B, HW, C, C_pad;
     int64_t out_img_pix;                      /* pixel stride between images of hi / lo (0: HW, dense) */
+    int32_t fmt;                              /* IA_OPFMT_* of the produced operand */
 } ia_modsplit_params;
 int ia_modsplit(const ia_modsplit_params* p, void* stream);
 
-/* Pack an OIHW fp32 weight into the GEMM layout [tap][Cout_pad][Cin_pad] bf16 hi/lo (+ wsq[Cout][Cin]). */
+/* Pack an OIHW fp32 weight into the GEMM layout [tap][Cout_pad][Cin_pad] in operand format `fmt` (bf16 hi/lo, or fp16 in
+ * w_hi alone) (+ wsq[Cout][Cin], always from the fp32 weight). */
 int ia_pack_conv_weight(const float* w, int32_t Cout, int32_t Cin, int32_t kh, int32_t kw, int32_t Cout_pad,
-                        int32_t Cin_pad, uint16_t* w_hi, uint16_t* w_lo, float* wsq, void* stream);
+                        int32_t Cin_pad, uint16_t* w_hi, uint16_t* w_lo, float* wsq, int32_t fmt, void* stream);
 
 typedef struct {
     /* what to emit from the fp32 result v[b][oy][ox][co] (any subset) */
@@ -169,6 +180,7 @@ typedef struct {
     /* Pixel stride between consecutive images of the emit-1 tensors (0: OH*OW, dense).  A consumer that is a stride-2 transposed
      * convolution takes its operand as [B][H+1][W][C] with a zero row after every image (ia_conv_params.a_img_rows). */
     int64_t e1_img_pix;
+    int32_t fmt1, fmt2;     /* IA_OPFMT_* of the emit-1 / emit-2 operands (the format their consuming convolutions run in) */
 } ia_emit;
 
 typedef struct {
@@ -205,6 +217,7 @@ typedef struct {
      * stream may share them; concurrent streams need their own).  The split factor is clipped to what the buffers hold
      * (per split: tiles x 256 x N-tile x 4 bytes; counters: 8 per tile). */
     float* splitk_ws; int64_t splitk_ws_bytes; int32_t* splitk_counters; int32_t splitk_n_counters;
+    int32_t op_fmt;          /* IA_OPFMT_* of a_* and w_* (a_lo / w_lo unused for F16X1) */
 } ia_conv_params;
 /* Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05.mma, TMEM accumulators, TMA-fed). */
 int ia_conv_tc(const ia_conv_params* p, void* stream);

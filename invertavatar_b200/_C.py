@@ -44,7 +44,7 @@ class FilteredLreluParams(C.Structure):
 class ModsplitParams(C.Structure):
     _fields_ = [('x', c_f32p), ('x_ld', C.c_int64), ('styles', c_f32p), ('cond', c_f32p), ('cond_ld', C.c_int64),
                 ('cond_alpha', c_f32p), ('hi', c_u16p), ('lo', c_u16p),
-                ('B', C.c_int32), ('HW', C.c_int32), ('C', C.c_int32), ('C_pad', C.c_int32), ('out_img_pix', C.c_int64)]
+                ('B', C.c_int32), ('HW', C.c_int32), ('C', C.c_int32), ('C_pad', C.c_int32), ('out_img_pix', C.c_int64), ('fmt', C.c_int32)]
 
 
 class Emit(C.Structure):
@@ -52,7 +52,7 @@ class Emit(C.Structure):
                 ('hi1', c_u16p), ('lo1', c_u16p), ('s1', c_f32p), ('c1_pad', C.c_int32),
                 ('hi2', c_u16p), ('lo2', c_u16p), ('s2', c_f32p), ('c2_pad', C.c_int32),
                 ('rgb_out', c_f32p), ('rgb_w', c_f32p), ('rgb_s', c_f32p), ('rgb_n', C.c_int32),
-                ('e1_img_pix', C.c_int64)]
+                ('e1_img_pix', C.c_int64), ('fmt1', C.c_int32), ('fmt2', C.c_int32)]
 
 
 class ConvParams(C.Structure):
@@ -67,7 +67,8 @@ class ConvParams(C.Structure):
                 ('emit', Emit),
                 ('groups', C.c_int32), ('imgs_per_group', C.c_int32), ('noise_gstride', C.c_int64),
                 ('img_prev', c_f32p), ('a_img_rows', C.c_int32),
-                ('splitk_ws', c_f32p), ('splitk_ws_bytes', C.c_int64), ('splitk_counters', c_i32p), ('splitk_n_counters', C.c_int32)]
+                ('splitk_ws', c_f32p), ('splitk_ws_bytes', C.c_int64), ('splitk_counters', c_i32p), ('splitk_n_counters', C.c_int32),
+                ('op_fmt', C.c_int32)]
 
 
 class FirParams(C.Structure):
@@ -168,7 +169,7 @@ SIGNATURES = {
     'ia_broadcast_truncate': (C.c_int, [c_f32p, c_f32p, c_f32p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_void_p]),
     'ia_styles': (C.c_int, [C.c_void_p, C.POINTER(StyleLayer), C.c_int32, c_f32p, C.c_int32, C.c_int32, C.c_void_p]),
     'ia_modsplit': (C.c_int, [C.POINTER(ModsplitParams), C.c_void_p]),
-    'ia_pack_conv_weight': (C.c_int, [c_f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_u16p, c_u16p, c_f32p, C.c_void_p]),
+    'ia_pack_conv_weight': (C.c_int, [c_f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_u16p, c_u16p, c_f32p, C.c_int32, C.c_void_p]),
     'ia_conv_tc': (C.c_int, [C.POINTER(ConvParams), C.c_void_p]),
     'ia_conv_tc_phases': (C.c_int, [C.POINTER(ConvParams), C.c_int32, C.c_void_p]),
     'ia_conv_simt': (C.c_int, [C.POINTER(ConvParams), C.c_void_p]),

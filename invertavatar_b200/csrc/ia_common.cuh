@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -61,6 +62,28 @@ __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uin
 }
 __device__ __forceinline__ float bf16_bits_to_float(uint16_t b) { return __uint_as_float(((uint32_t)b) << 16); }
 
+// IA_OPFMT_F16X1 operands: round to nearest fp16, saturating at the largest finite value (an activation beyond 65504 must not
+// become inf inside the accumulation).  Two values -> one 32-bit word in memory order (a low, b high).
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float a, float b) {
+    a = fminf(fmaxf(a, -65504.f), 65504.f);
+    b = fminf(fmaxf(b, -65504.f), 65504.f);
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ float f16_bits_to_float(uint16_t b) { return __half2float(__ushort_as_half(b)); }
+// Four consecutive channels of one operand pixel in format `fmt`: bf16 hi/lo pair, or fp16 in `hi` alone.
+__device__ __forceinline__ void store_operand4(int fmt, uint16_t* hi, uint16_t* lo, float a, float b, float c, float d) {
+    if (fmt == IA_OPFMT_F16X1) {
+        *reinterpret_cast<uint2*>(hi) = make_uint2(pack_f16x2_sat(a, b), pack_f16x2_sat(c, d));
+    } else {
+        uint2 hv, lv;
+        split_bf16x2(a, b, hv.x, lv.x);
+        split_bf16x2(c, d, hv.y, lv.y);
+        *reinterpret_cast<uint2*>(hi) = hv;
+        *reinterpret_cast<uint2*>(lo) = lv;
+    }
+}
+
 // activation + gain + clamp shared by every epilogue (reference bias_act.cu:27-151 forward path; only the
 // activations the generator uses get the fast path, the rest are exact expressions).
 __device__ __forceinline__ float apply_act(float x, int act, float alpha) {
@@ -94,30 +117,16 @@ __device__ __forceinline__ void emit4(const ia_emit& e, int b, int64_t pix, int 
         }
     }
     if (e.hi1) {
-        uint16_t h[4], l[4];
+        float m[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            float s = (co + k < C) ? (e.s1 ? e.s1[(int64_t)b * C + co + k] : 1.f) : 0.f;
-            float m = (co + k < C) ? v[k] * s : 0.f;
-            split_bf16(m, h[k], l[k]);
-        }
-        uint2 hv = make_uint2(h[0] | ((uint32_t)h[1] << 16), h[2] | ((uint32_t)h[3] << 16));
-        uint2 lv = make_uint2(l[0] | ((uint32_t)l[1] << 16), l[2] | ((uint32_t)l[3] << 16));
-        *reinterpret_cast<uint2*>(e.hi1 + pix * e.c1_pad + co) = hv;
-        *reinterpret_cast<uint2*>(e.lo1 + pix * e.c1_pad + co) = lv;
+        for (int k = 0; k < 4; ++k) m[k] = (co + k < C) ? v[k] * (e.s1 ? e.s1[(int64_t)b * C + co + k] : 1.f) : 0.f;
+        store_operand4(e.fmt1, e.hi1 + pix * e.c1_pad + co, e.lo1 + pix * e.c1_pad + co, m[0], m[1], m[2], m[3]);
     }
     if (e.hi2) {
-        uint16_t h[4], l[4];
+        float m[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            float s = (co + k < C) ? (e.s2 ? e.s2[(int64_t)b * C + co + k] : 1.f) : 0.f;
-            float m = (co + k < C) ? v[k] * s : 0.f;
-            split_bf16(m, h[k], l[k]);
-        }
-        uint2 hv = make_uint2(h[0] | ((uint32_t)h[1] << 16), h[2] | ((uint32_t)h[3] << 16));
-        uint2 lv = make_uint2(l[0] | ((uint32_t)l[1] << 16), l[2] | ((uint32_t)l[3] << 16));
-        *reinterpret_cast<uint2*>(e.hi2 + pix * e.c2_pad + co) = hv;
-        *reinterpret_cast<uint2*>(e.lo2 + pix * e.c2_pad + co) = lv;
+        for (int k = 0; k < 4; ++k) m[k] = (co + k < C) ? v[k] * (e.s2 ? e.s2[(int64_t)b * C + co + k] : 1.f) : 0.f;
+        store_operand4(e.fmt2, e.hi2 + pix * e.c2_pad + co, e.lo2 + pix * e.c2_pad + co, m[0], m[1], m[2], m[3]);
     }
 }
 

@@ -44,6 +44,8 @@ struct TcParams {
     int act; float alpha, gain, clamp;
     ia_emit emit;
     int groups, ipg, n_taps_total; long long noise_gstride;   // grouped launch (see ia_conv_params)
+    int nops;             // operand tensors per side: 2 (bf16 hi/lo, 3 MMAs per k-step) or 1 (fp16, 1 MMA)
+    uint32_t idesc_fmt;   // A/B format bits of the instruction descriptor
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------
@@ -152,7 +154,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     // 1024-byte alignment for the 128B-swizzled tiles
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t b_bytes = (uint32_t)p.n_tile * 128u;
-    const uint32_t stage_bytes = 2u * kABytes + 2u * b_bytes;
+    const uint32_t nops = (uint32_t)p.nops;
+    const uint32_t stage_bytes = nops * (kABytes + b_bytes);      // [A hi][A lo]?[B hi][B lo]?
+    const uint32_t b_off = nops * kABytes;
     const uint32_t bar_base = smem_base + (uint32_t)p.stages * stage_bytes;
     // barriers: full[stages], empty[stages], tmem_full ; then the TMEM base-address slot
     auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
@@ -203,10 +207,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                 const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
                 mbar_expect_tx(full_bar(stage), stage_bytes);
                 tma_load_4d(sa, &tm_a_hi, full_bar(stage), kc * kBlockK, x0 + p.dx[t], y0 + p.dy[t], n0);
-                tma_load_4d(sa + kABytes, &tm_a_lo, full_bar(stage), kc * kBlockK, x0 + p.dx[t], y0 + p.dy[t], n0);
+                if (nops == 2u) tma_load_4d(sa + kABytes, &tm_a_lo, full_bar(stage), kc * kBlockK, x0 + p.dx[t], y0 + p.dy[t], n0);
                 const int wrow = ((n0 / p.ipg) * p.n_taps_total + p.wtap[t]) * p.Cout_pad + col0;   // a tile never spans two groups
-                tma_load_2d(sa + 2u * kABytes, &tm_w_hi, full_bar(stage), kc * kBlockK, wrow);
-                tma_load_2d(sa + 2u * kABytes + b_bytes, &tm_w_lo, full_bar(stage), kc * kBlockK, wrow);
+                tma_load_2d(sa + b_off, &tm_w_hi, full_bar(stage), kc * kBlockK, wrow);
+                if (nops == 2u) tma_load_2d(sa + b_off + b_bytes, &tm_w_lo, full_bar(stage), kc * kBlockK, wrow);
                 if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
         }
@@ -214,7 +218,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         // ===================== MMA issuer =====================
         if (lane == 0) {
             // instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=n_tile
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+            const uint32_t idesc = (1u << 4) | p.idesc_fmt | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
             int stage = 0; uint32_t phase = 0;
             for (int kb = 0; kb < num_kb; ++kb) {
                 mbar_wait(full_bar(stage), phase);
@@ -222,14 +226,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                 const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
                 const uint64_t a_hi = make_sw128_desc(sa);
                 const uint64_t a_lo = make_sw128_desc(sa + kABytes);
-                const uint64_t b_hi = make_sw128_desc(sa + 2u * kABytes);
-                const uint64_t b_lo = make_sw128_desc(sa + 2u * kABytes + b_bytes);
+                const uint64_t b_hi = make_sw128_desc(sa + b_off);
+                const uint64_t b_lo = make_sw128_desc(sa + b_off + b_bytes);
 #pragma unroll
                 for (int k = 0; k < kBlockK / 16; ++k) {
                     const uint64_t koff = (uint64_t)((k * 32) >> 4);  // +32 bytes per 16-element K step
                     umma_bf16(tmem_base, a_hi + koff, b_hi + koff, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                    umma_bf16(tmem_base, a_hi + koff, b_lo + koff, idesc, 1u);
-                    umma_bf16(tmem_base, a_lo + koff, b_hi + koff, idesc, 1u);
+                    if (nops == 2u) {
+                        umma_bf16(tmem_base, a_hi + koff, b_lo + koff, idesc, 1u);
+                        umma_bf16(tmem_base, a_lo + koff, b_hi + koff, idesc, 1u);
+                    }
                 }
                 umma_commit(empty_bar(stage));   // frees the smem slot once these MMAs have read it
                 if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -423,6 +429,8 @@ struct Tc2Params {
     // partial accumulators go through `ws`, the last CTA to arrive (ticket in `cnt`) sums them in split order and runs the epilogue
     int ksplit, kc_per;
     float4* ws; int* cnt;
+    int nops;             // operand tensors per side: 2 (bf16 hi/lo, 3 MMAs per k-step) or 1 (fp16, 1 MMA)
+    uint32_t idesc_fmt;   // A/B format bits of the instruction descriptor
 };
 
 
@@ -456,16 +464,24 @@ __device__ __forceinline__ void epilogue_chunk(const Tc2Params& p, const float* 
         if (!cvalid) continue;
         if (o32) o32[(int64_t)pix_r * p.emit.out32_ld] = a;
         if (h1) {
-            uint16_t h, l;
-            split_bf16(a * s1v, h, l);
             const int64_t o = (int64_t)pix_r * p.emit.c1_pad;
-            h1[o] = h; l1[o] = l;
+            if (p.emit.fmt1 == IA_OPFMT_F16X1) {
+                h1[o] = __half_as_ushort(__float2half_rn(fminf(fmaxf(a * s1v, -65504.f), 65504.f)));
+            } else {
+                uint16_t h, l;
+                split_bf16(a * s1v, h, l);
+                h1[o] = h; l1[o] = l;
+            }
         }
         if (h2) {
-            uint16_t h, l;
-            split_bf16(a * s2v, h, l);
             const int64_t o = (int64_t)pix_r * p.emit.c2_pad;
-            h2[o] = h; l2[o] = l;
+            if (p.emit.fmt2 == IA_OPFMT_F16X1) {
+                h2[o] = __half_as_ushort(__float2half_rn(fminf(fmaxf(a * s2v, -65504.f), 65504.f)));
+            } else {
+                uint16_t h, l;
+                split_bf16(a * s2v, h, l);
+                h2[o] = h; l2[o] = l;
+            }
         }
     }
 }
@@ -519,20 +535,12 @@ __device__ __forceinline__ void epilogue_chunk_v4(const Tc2Params& p, const floa
                 racc[i][j] = fmaf(mw, rg.w[j].w, fmaf(mz, rg.w[j].z, fmaf(my, rg.w[j].y, fmaf(mx, rg.w[j].x, racc[i][j]))));
         }
         if (E1) {
-            uint16_t h[4], l[4];
-            split_bf16(a.x * s1.x, h[0], l[0]); split_bf16(a.y * s1.y, h[1], l[1]);
-            split_bf16(a.z * s1.z, h[2], l[2]); split_bf16(a.w * s1.w, h[3], l[3]);
             const int64_t o = (int64_t)pix_r * p.emit.c1_pad;
-            *reinterpret_cast<uint2*>(h1 + o) = make_uint2(h[0] | ((uint32_t)h[1] << 16), h[2] | ((uint32_t)h[3] << 16));
-            *reinterpret_cast<uint2*>(l1 + o) = make_uint2(l[0] | ((uint32_t)l[1] << 16), l[2] | ((uint32_t)l[3] << 16));
+            store_operand4(p.emit.fmt1, h1 + o, l1 + o, a.x * s1.x, a.y * s1.y, a.z * s1.z, a.w * s1.w);
         }
         if (E2) {
-            uint16_t h[4], l[4];
-            split_bf16(a.x * s2.x, h[0], l[0]); split_bf16(a.y * s2.y, h[1], l[1]);
-            split_bf16(a.z * s2.z, h[2], l[2]); split_bf16(a.w * s2.w, h[3], l[3]);
             const int64_t o = (int64_t)pix_r * p.emit.c2_pad;
-            *reinterpret_cast<uint2*>(h2 + o) = make_uint2(h[0] | ((uint32_t)h[1] << 16), h[2] | ((uint32_t)h[3] << 16));
-            *reinterpret_cast<uint2*>(l2 + o) = make_uint2(l[0] | ((uint32_t)l[1] << 16), l[2] | ((uint32_t)l[3] << 16));
+            store_operand4(p.emit.fmt2, h2 + o, l2 + o, a.x * s2.x, a.y * s2.y, a.z * s2.z, a.w * s2.w);
         }
     }
 }
@@ -609,7 +617,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                 const Tc2Params p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t a_slot_bytes = 2u * p.a_bytes, b_slot_bytes = 2u * p.b_bytes;
+    const uint32_t nops = (uint32_t)p.nops;
+    const uint32_t a_slot_bytes = nops * p.a_bytes, b_slot_bytes = nops * p.b_bytes;
     const uint32_t a_base = smem_base;
     const uint32_t b_base = a_base + (uint32_t)p.a_slots * a_slot_bytes;
     const uint32_t bar_base = b_base + (uint32_t)p.b_slots * b_slot_bytes;
@@ -713,24 +722,24 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                         const int as = (int)(a_it % (uint32_t)p.a_slots);
                         mbar_wait(a_empty(as), ((a_it / (uint32_t)p.a_slots) & 1u) ^ 1u);
                         const uint32_t sa = a_base + (uint32_t)as * a_slot_bytes;
-                        mbar_expect_tx(a_full(as), 2u * p.a_tx);
+                        mbar_expect_tx(a_full(as), nops * p.a_tx);
                         tma_load_4d(sa, &tm_a_hi, a_full(as), kc * BK, x0 + ph.g_dx[g], y0 + p.dy_min, img);
-                        tma_load_4d(sa + p.a_bytes, &tm_a_lo, a_full(as), kc * BK, x0 + ph.g_dx[g], y0 + p.dy_min, img);
+                        if (nops == 2u) tma_load_4d(sa + p.a_bytes, &tm_a_lo, a_full(as), kc * BK, x0 + ph.g_dx[g], y0 + p.dy_min, img);
                         ++a_it;
                         for (int t = ph.g_first[g]; t < ph.g_first[g + 1]; ++t) {
                             const int bs = (int)(b_it % (uint32_t)p.b_slots);
                             mbar_wait(b_empty(bs), ((b_it / (uint32_t)p.b_slots) & 1u) ^ 1u);
                             const uint32_t sb = b_base + (uint32_t)bs * b_slot_bytes;
-                            mbar_expect_tx(b_full(bs), 2u * p.b_tx);
+                            mbar_expect_tx(b_full(bs), nops * p.b_tx);
                             const int wrow = ((img / p.ipg) * p.n_taps_total + ph.t_wtap[t]) * p.Cout_pad + col0;
                             if (CL) {     // both CTAs armed their own barrier above; rank 0 fetches the tile for both
                                 if (crank == 0) {
                                     tma_load_2d_mc(sb, &tm_w_hi, b_full(bs), kc * BK, wrow, (uint16_t)3);
-                                    tma_load_2d_mc(sb + p.b_bytes, &tm_w_lo, b_full(bs), kc * BK, wrow, (uint16_t)3);
+                                    if (nops == 2u) tma_load_2d_mc(sb + p.b_bytes, &tm_w_lo, b_full(bs), kc * BK, wrow, (uint16_t)3);
                                 }
                             } else {
                                 tma_load_2d(sb, &tm_w_hi, b_full(bs), kc * BK, wrow);
-                                tma_load_2d(sb + p.b_bytes, &tm_w_lo, b_full(bs), kc * BK, wrow);
+                                if (nops == 2u) tma_load_2d(sb + p.b_bytes, &tm_w_lo, b_full(bs), kc * BK, wrow);
                             }
                             ++b_it;
                         }
@@ -741,7 +750,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+            const uint32_t idesc = (1u << 4) | p.idesc_fmt | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
             uint32_t a_it = 0, b_it = 0, j = 0;
             int mma_pi = 0;
             for (int it = it_first; it < it_end; it += it_step) {
@@ -781,12 +790,17 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                             for (int k = 0; k < BK / 16; ++k) {
                                 const uint64_t koff = (uint64_t)((k * 32) >> 4);
                                 const uint32_t accum = first ? 0u : 1u;
-                                umma_bf16(d0, a0_hi + koff, b_hi + koff, idesc, accum);
-                                umma_bf16(d0, a0_hi + koff, b_lo + koff, idesc, 1u);
-                                umma_bf16(d0, a0_lo + koff, b_hi + koff, idesc, 1u);
-                                umma_bf16(d1, a1_hi + koff, b_hi + koff, idesc, accum);
-                                umma_bf16(d1, a1_hi + koff, b_lo + koff, idesc, 1u);
-                                umma_bf16(d1, a1_lo + koff, b_hi + koff, idesc, 1u);
+                                if (nops == 2u) {
+                                    umma_bf16(d0, a0_hi + koff, b_hi + koff, idesc, accum);
+                                    umma_bf16(d0, a0_hi + koff, b_lo + koff, idesc, 1u);
+                                    umma_bf16(d0, a0_lo + koff, b_hi + koff, idesc, 1u);
+                                    umma_bf16(d1, a1_hi + koff, b_hi + koff, idesc, accum);
+                                    umma_bf16(d1, a1_hi + koff, b_lo + koff, idesc, 1u);
+                                    umma_bf16(d1, a1_lo + koff, b_hi + koff, idesc, 1u);
+                                } else {
+                                    umma_bf16(d0, a0_hi + koff, b_hi + koff, idesc, accum);
+                                    umma_bf16(d1, a1_hi + koff, b_hi + koff, idesc, accum);
+                                }
                                 first = false;
                             }
                             if (CL) umma_commit_mc(b_empty(bs), (uint16_t)3); else umma_commit(b_empty(bs));
@@ -1187,10 +1201,13 @@ int launch_v2(const ia_conv_params* const* ps, int nph, void* stream) {
     t.b_bytes = (t.b_tx + 1023u) & ~1023u;
     const uint32_t kEpiBytes = (uint32_t)kEpiWarps2 * 32u * (uint32_t)kTsmLd * 4u;
     const uint32_t budget = 227u * 1024u - 1024u - 512u - kEpiBytes;
+    const uint32_t nops = p->op_fmt == IA_OPFMT_F16X1 ? 1u : 2u;      // operand tensors per side (a slot holds hi [+ lo])
+    t.nops = (int)nops;
+    t.idesc_fmt = p->op_fmt == IA_OPFMT_F16X1 ? 0u : ((1u << 7) | (1u << 10));     // A/B format: F16 = 0, BF16 = 1
     // at least 2 + 2 slots; then spend the rest alternately (weights first: they turn over once per tap)
     t.a_slots = 2; t.b_slots = 2;
     // a wide k-block with a tall halo tile may not leave room for 2 + 2 slots at the widest N tile: narrow the N tile
-    while (2u * (2u * t.a_bytes + 2u * t.b_bytes) > budget && n_tile > 32) {
+    while (nops * (2u * t.a_bytes + 2u * t.b_bytes) > budget && n_tile > 32) {
         int next = n_tile - 32;
         while (next > 32 && p->Cout_pad % next) next -= 32;
         n_tile = next;
@@ -1199,15 +1216,15 @@ int launch_v2(const ia_conv_params* const* ps, int nph, void* stream) {
         t.b_tx = (uint32_t)n_tile * BK * 2u;
         t.b_bytes = (t.b_tx + 1023u) & ~1023u;
     }
-    IA_CHECK(2u * (2u * t.a_bytes + 2u * t.b_bytes) <= budget, "ia_conv_tc(v2): tile does not fit shared memory");
+    IA_CHECK(nops * (2u * t.a_bytes + 2u * t.b_bytes) <= budget, "ia_conv_tc(v2): tile does not fit shared memory");
     // Spend the rest so that both rings hold about the same number of k-blocks of work: a k-block consumes `ngroups`
     // activation slots and `ntaps` weight slots.  Few-tap launches (transposed-conv phases, 1x1) therefore get a deep
     // activation ring -- their activation tiles stream from DRAM and two slots in flight bound them by latency
     // (measured: 3.85 TB/s aggregate with 2 slots) -- while 3x3 layers keep the deep weight ring.
     for (;;) {
-        const uint32_t used_b = 2u * ((uint32_t)t.a_slots * t.a_bytes + (uint32_t)t.b_slots * t.b_bytes);
-        const bool a_fits = t.a_slots < kV2MaxASlots && used_b + 2u * t.a_bytes <= budget;
-        const bool b_fits = t.b_slots < kV2MaxBSlots && used_b + 2u * t.b_bytes <= budget;
+        const uint32_t used_b = nops * ((uint32_t)t.a_slots * t.a_bytes + (uint32_t)t.b_slots * t.b_bytes);
+        const bool a_fits = t.a_slots < kV2MaxASlots && used_b + nops * t.a_bytes <= budget;
+        const bool b_fits = t.b_slots < kV2MaxBSlots && used_b + nops * t.b_bytes <= budget;
         if (!a_fits && !b_fits) break;
         // depth_a = a_slots / ngroups, depth_b = b_slots / ntaps; grow the shallower ring (ties -> activations)
         const bool want_a = (int64_t)t.a_slots * t.ntaps <= (int64_t)t.b_slots * t.ngroups;
@@ -1284,12 +1301,12 @@ int launch_v2(const ia_conv_params* const* ps, int nph, void* stream) {
     // starts are a_img_rows rows apart
     const int mapB = cat ? 1 : p->B, mapH = cat ? rowsB : p->H, mapR = cat ? rowsB : p->a_img_rows;
     if (int rc = make_act_map2<BK>(&ma_hi, p->a_hi, mapB, mapH, p->W, p->Cin_pad, t.TH + halo, t.tw, mapR)) return rc;
-    if (int rc = make_act_map2<BK>(&ma_lo, p->a_lo, mapB, mapH, p->W, p->Cin_pad, t.TH + halo, t.tw, mapR)) return rc;
+    if (int rc = make_act_map2<BK>(&ma_lo, nops == 2u ? p->a_lo : p->a_hi, mapB, mapH, p->W, p->Cin_pad, t.TH + halo, t.tw, mapR)) return rc;
     const int wrows = t.groups * p->n_taps_total * p->Cout_pad;
     if (int rc = make_weight_map2<BK>(&mw_hi, p->w_hi, wrows, p->Cin_pad, n_tile)) return rc;
-    if (int rc = make_weight_map2<BK>(&mw_lo, p->w_lo, wrows, p->Cin_pad, n_tile)) return rc;
+    if (int rc = make_weight_map2<BK>(&mw_lo, nops == 2u ? p->w_lo : p->w_hi, wrows, p->Cin_pad, n_tile)) return rc;
 
-    const size_t smem = 2u * ((size_t)t.a_slots * t.a_bytes + (size_t)t.b_slots * t.b_bytes) + 1024 + 512 + kEpiBytes;
+    const size_t smem = (size_t)nops * ((size_t)t.a_slots * t.a_bytes + (size_t)t.b_slots * t.b_bytes) + 1024 + 512 + kEpiBytes;
     cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     IA_CHECK(e == cudaSuccess, "ia_conv_tc(v2): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     e = cudaFuncSetAttribute(conv_tc2_kernel<BK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -1339,7 +1356,7 @@ extern "C" int ia_conv_tc(const ia_conv_params* p, void* stream) {
     if (int rc = ia_conv_validate(p, "ia_conv_tc")) return rc;
     IA_CHECK((reinterpret_cast<uintptr_t>(p->a_hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->a_lo) & 15) == 0 &&
              (reinterpret_cast<uintptr_t>(p->w_hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->w_lo) & 15) == 0,
-             "ia_conv_tc: operands must be 16-byte aligned");
+             "ia_conv_tc: operands must be 16-byte aligned");     // (a NULL lo pointer of an F16X1 operand passes)
     // v2 (persistent, 256-pixel tiles, halo reuse) needs images of at least one 128-pixel half tile; the low-resolution
     // layers (4x4, 8x8 and their transposed-conv phase grids) pack several images into a tile with the v1 kernel below.
     {
@@ -1380,7 +1397,10 @@ extern "C" int ia_conv_tc(const ia_conv_params* p, void* stream) {
     }
     t.n_tile = n_tile;
     t.tmem_cols = 32; while (t.tmem_cols < n_tile) t.tmem_cols <<= 1;
-    const uint32_t stage_bytes = 2u * kABytes + 2u * (uint32_t)n_tile * 128u;
+    const uint32_t nops = p->op_fmt == IA_OPFMT_F16X1 ? 1u : 2u;
+    t.nops = (int)nops;
+    t.idesc_fmt = p->op_fmt == IA_OPFMT_F16X1 ? 0u : ((1u << 7) | (1u << 10));
+    const uint32_t stage_bytes = nops * (kABytes + (uint32_t)n_tile * 128u);
     const uint32_t budget = 227u * 1024u - 1024u /*alignment*/ - 256u /*barriers*/;
     int stages = (int)(budget / stage_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
@@ -1396,10 +1416,10 @@ extern "C" int ia_conv_tc(const ia_conv_params* p, void* stream) {
 
     CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
     if (int rc = make_act_map(&ma_hi, p->a_hi, p->B, p->H, p->W, p->Cin_pad, t.nb, t.th, t.tw, p->a_img_rows)) return rc;
-    if (int rc = make_act_map(&ma_lo, p->a_lo, p->B, p->H, p->W, p->Cin_pad, t.nb, t.th, t.tw, p->a_img_rows)) return rc;
+    if (int rc = make_act_map(&ma_lo, nops == 2u ? p->a_lo : p->a_hi, p->B, p->H, p->W, p->Cin_pad, t.nb, t.th, t.tw, p->a_img_rows)) return rc;
     const int wrows = t.groups * p->n_taps_total * p->Cout_pad;
     if (int rc = make_weight_map(&mw_hi, p->w_hi, wrows, p->Cin_pad, n_tile)) return rc;
-    if (int rc = make_weight_map(&mw_lo, p->w_lo, wrows, p->Cin_pad, n_tile)) return rc;
+    if (int rc = make_weight_map(&mw_lo, nops == 2u ? p->w_lo : p->w_hi, wrows, p->Cin_pad, n_tile)) return rc;
 
     const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
     {
@@ -1436,7 +1456,7 @@ extern "C" int ia_conv_tc_phases(const ia_conv_params* p, int32_t n, void* strea
             a.Cin_pad != b.Cin_pad || a.Cout != b.Cout || a.Cout_pad != b.Cout_pad || a.n_taps_total != b.n_taps_total || a.OH != b.OH ||
             a.OW != b.OW || a.sy != b.sy || a.sx != b.sx || a.mode != b.mode || a.dcoef != b.dcoef || a.noise != b.noise || a.bias != b.bias ||
             a.act != b.act || a.gain != b.gain || a.clamp != b.clamp || a.emit.out32 != b.emit.out32 || a.emit.hi1 != b.emit.hi1 ||
-            a.emit.hi2 != b.emit.hi2 || a.groups != b.groups || a.imgs_per_group != b.imgs_per_group || a.a_img_rows != b.a_img_rows)
+            a.emit.hi2 != b.emit.hi2 || a.groups != b.groups || a.imgs_per_group != b.imgs_per_group || a.a_img_rows != b.a_img_rows || a.op_fmt != b.op_fmt)
             merged = false;
     }
     if (!merged) {

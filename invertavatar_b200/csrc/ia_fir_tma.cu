@@ -250,6 +250,7 @@ bool fir_tma_eligible(const ia_fir_params* p) {
     // off by default; IA_FIR_TMA=1 enables it (read per call; tests/test_gpu_regress.py checks it bit for bit).
     const char* e = getenv("IA_FIR_TMA");
     if (!e || atoi(e) == 0) return false;
+    if ((p->emit.hi1 && p->emit.fmt1 != IA_OPFMT_BF16X3) || (p->emit.hi2 && p->emit.fmt2 != IA_OPFMT_BF16X3)) return false;   // bf16 hi/lo emission only
     if (p->C % FT_CC != 0 || p->OW % FT_XT != 0 || p->OH < 8) return false;
     if ((reinterpret_cast<uintptr_t>(p->raw) & 15) != 0) return false;
     const int64_t out_pix = (int64_t)p->B * p->OH * p->OW;

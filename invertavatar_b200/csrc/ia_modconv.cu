@@ -123,16 +123,13 @@ __global__ void modsplit_kernel(ia_modsplit_params p) {
                 if (c0 + k < p.C) v[k] *= sp[k];
         }
     }
-    uint16_t h[4], l[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) split_bf16(v[k], h[k], l[k]);
     const int64_t opix = p.out_img_pix ? (int64_t)b * p.out_img_pix + (pix - (int64_t)b * p.HW) : pix;   // padded image stride
-    *reinterpret_cast<uint2*>(p.hi + opix * p.C_pad + c0) = make_uint2(h[0] | ((uint32_t)h[1] << 16), h[2] | ((uint32_t)h[3] << 16));
-    *reinterpret_cast<uint2*>(p.lo + opix * p.C_pad + c0) = make_uint2(l[0] | ((uint32_t)l[1] << 16), l[2] | ((uint32_t)l[3] << 16));
+    store_operand4(p.fmt, p.hi + opix * p.C_pad + c0, p.lo + opix * p.C_pad + c0, v[0], v[1], v[2], v[3]);
 }
 
 extern "C" int ia_modsplit(const ia_modsplit_params* p, void* stream) {
-    IA_CHECK(p && p->x && p->hi && p->lo, "ia_modsplit: null tensor");
+    IA_CHECK(p && p->x && p->hi && (p->lo || p->fmt == IA_OPFMT_F16X1), "ia_modsplit: null tensor");
+    IA_CHECK(p->fmt == IA_OPFMT_BF16X3 || p->fmt == IA_OPFMT_F16X1, "ia_modsplit: unknown operand format %d", p->fmt);
     IA_CHECK(p->C > 0 && p->C_pad >= p->C && (p->C_pad & 3) == 0, "ia_modsplit: C_pad must be >= C and a multiple of 4");
     IA_CHECK(p->cond == nullptr || p->cond_alpha != nullptr, "ia_modsplit: cond needs cond_alpha");
     int64_t total = (int64_t)p->B * p->HW * (p->C_pad >> 2);
@@ -147,13 +144,17 @@ extern "C" int ia_modsplit(const ia_modsplit_params* p, void* stream) {
 // weight packing: OIHW fp32 -> [tap][Cout_pad][Cin_pad] bf16 hi/lo, wsq[o][i] = sum_taps w^2
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int taps, int Cout_pad, int Cin_pad,
-                                   uint16_t* __restrict__ w_hi, uint16_t* __restrict__ w_lo) {
+                                   uint16_t* __restrict__ w_hi, uint16_t* __restrict__ w_lo, int fmt) {
     int64_t total = (int64_t)taps * Cout_pad * Cin_pad;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     int ci = i % Cin_pad; int64_t t = i / Cin_pad;
     int co = t % Cout_pad; int tap = (int)(t / Cout_pad);
     float v = (ci < Cin && co < Cout) ? w[((int64_t)co * Cin + ci) * taps + tap] : 0.f;
+    if (fmt == IA_OPFMT_F16X1) {
+        w_hi[i] = __half_as_ushort(__float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f)));
+        return;
+    }
     uint16_t h, l;
     split_bf16(v, h, l);
     w_hi[i] = h;
@@ -168,13 +169,14 @@ __global__ void wsq_kernel(const float* __restrict__ w, int Cout, int Cin, int t
 }
 
 extern "C" int ia_pack_conv_weight(const float* w, int32_t Cout, int32_t Cin, int32_t kh, int32_t kw, int32_t Cout_pad,
-                                   int32_t Cin_pad, uint16_t* w_hi, uint16_t* w_lo, float* wsq, void* stream) {
-    IA_CHECK(w && w_hi && w_lo, "ia_pack_conv_weight: null tensor");
+                                   int32_t Cin_pad, uint16_t* w_hi, uint16_t* w_lo, float* wsq, int32_t fmt, void* stream) {
+    IA_CHECK(fmt == IA_OPFMT_BF16X3 || fmt == IA_OPFMT_F16X1, "ia_pack_conv_weight: unknown operand format %d", fmt);
+    IA_CHECK(w && w_hi && (w_lo || fmt == IA_OPFMT_F16X1), "ia_pack_conv_weight: null tensor");
     IA_CHECK(Cout_pad >= Cout && Cin_pad >= Cin, "ia_pack_conv_weight: bad padding");
     int taps = kh * kw;
     int64_t total = (int64_t)taps * Cout_pad * Cin_pad;
     ia::prof_begin("ia_pack_conv_weight", as_stream(stream));
-    pack_weight_kernel<<<(unsigned)cdiv(total, 256), 256, 0, as_stream(stream)>>>(w, Cout, Cin, taps, Cout_pad, Cin_pad, w_hi, w_lo);
+    pack_weight_kernel<<<(unsigned)cdiv(total, 256), 256, 0, as_stream(stream)>>>(w, Cout, Cin, taps, Cout_pad, Cin_pad, w_hi, w_lo, fmt);
     IA_LAUNCH_CHECK("ia_pack_conv_weight");
     if (wsq) {
         ia::prof_begin("ia_pack_conv_weight(wsq)", as_stream(stream));
@@ -295,20 +297,12 @@ __global__ void __launch_bounds__(256, 3) fir_epilogue_kernel(ia_fir_params p, i
                 if ((p.emit.out32_ld & 3) == 0) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
                 else { o[0] = v[0]; o[1] = v[1]; o[2] = v[2]; o[3] = v[3]; }
             }
-            if (p.emit.hi1) {
-                uint16_t h16[4], l16[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) split_bf16(v[k] * s1[k], h16[k], l16[k]);
-                *reinterpret_cast<uint2*>(p.emit.hi1 + opix * p.emit.c1_pad + c0) = make_uint2(h16[0] | ((uint32_t)h16[1] << 16), h16[2] | ((uint32_t)h16[3] << 16));
-                *reinterpret_cast<uint2*>(p.emit.lo1 + opix * p.emit.c1_pad + c0) = make_uint2(l16[0] | ((uint32_t)l16[1] << 16), l16[2] | ((uint32_t)l16[3] << 16));
-            }
-            if (p.emit.hi2) {
-                uint16_t h16[4], l16[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) split_bf16(v[k] * s2[k], h16[k], l16[k]);
-                *reinterpret_cast<uint2*>(p.emit.hi2 + opix * p.emit.c2_pad + c0) = make_uint2(h16[0] | ((uint32_t)h16[1] << 16), h16[2] | ((uint32_t)h16[3] << 16));
-                *reinterpret_cast<uint2*>(p.emit.lo2 + opix * p.emit.c2_pad + c0) = make_uint2(l16[0] | ((uint32_t)l16[1] << 16), l16[2] | ((uint32_t)l16[3] << 16));
-            }
+            if (p.emit.hi1)
+                store_operand4(p.emit.fmt1, p.emit.hi1 + opix * p.emit.c1_pad + c0, p.emit.lo1 + opix * p.emit.c1_pad + c0,
+                               v[0] * s1[0], v[1] * s1[1], v[2] * s1[2], v[3] * s1[3]);
+            if (p.emit.hi2)
+                store_operand4(p.emit.fmt2, p.emit.hi2 + opix * p.emit.c2_pad + c0, p.emit.lo2 + opix * p.emit.c2_pad + c0,
+                               v[0] * s2[0], v[1] * s2[1], v[2] * s2[2], v[3] * s2[3]);
             opix += p.OW;
         }
         acc0 = acc1; acc1 = acc2; acc2 = acc3;
@@ -434,20 +428,10 @@ __global__ void __launch_bounds__(256, 2) fir_epilogue_x2_kernel(ia_fir_params p
                     if ((o32ld & 3) == 0) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
                     else { o[0] = v[0]; o[1] = v[1]; o[2] = v[2]; o[3] = v[3]; }
                 }
-                if (has1) {
-                    uint2 hv, lv;
-                    split_bf16x2(v[0] * s1[0], v[1] * s1[1], hv.x, lv.x);
-                    split_bf16x2(v[2] * s1[2], v[3] * s1[3], hv.y, lv.y);
-                    *reinterpret_cast<uint2*>(p.emit.hi1 + (o1 + j * c1p)) = hv;
-                    *reinterpret_cast<uint2*>(p.emit.lo1 + (o1 + j * c1p)) = lv;
-                }
-                if (has2) {
-                    uint2 hv, lv;
-                    split_bf16x2(v[0] * s2[0], v[1] * s2[1], hv.x, lv.x);
-                    split_bf16x2(v[2] * s2[2], v[3] * s2[3], hv.y, lv.y);
-                    *reinterpret_cast<uint2*>(p.emit.hi2 + (o2 + j * c2p)) = hv;
-                    *reinterpret_cast<uint2*>(p.emit.lo2 + (o2 + j * c2p)) = lv;
-                }
+                if (has1)
+                    store_operand4(p.emit.fmt1, p.emit.hi1 + (o1 + j * c1p), p.emit.lo1 + (o1 + j * c1p), v[0] * s1[0], v[1] * s1[1], v[2] * s1[2], v[3] * s1[3]);
+                if (has2)
+                    store_operand4(p.emit.fmt2, p.emit.hi2 + (o2 + j * c2p), p.emit.lo2 + (o2 + j * c2p), v[0] * s2[0], v[1] * s2[1], v[2] * s2[2], v[3] * s2[3]);
             }
             a0 = a1; a1 = a2; a2 = a3;
         }
@@ -645,7 +629,11 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ia_conv_params p) {
         const bool wvalid = (col0 + lr) < p.Cout_pad;
         for (int k0 = 0; k0 < p.Cin_pad; k0 += SIMT_TK) {
             float av[4] = {0.f, 0.f, 0.f, 0.f}, wv[4] = {0.f, 0.f, 0.f, 0.f};
-            if (avalid) {
+            if (avalid && p.op_fmt == IA_OPFMT_F16X1) {
+                uint2 h = *reinterpret_cast<const uint2*>(p.a_hi + abase + k0 + lk);
+                av[0] = f16_bits_to_float(h.x & 0xffff); av[1] = f16_bits_to_float(h.x >> 16);
+                av[2] = f16_bits_to_float(h.y & 0xffff); av[3] = f16_bits_to_float(h.y >> 16);
+            } else if (avalid) {
                 uint2 h = *reinterpret_cast<const uint2*>(p.a_hi + abase + k0 + lk);
                 uint2 l = *reinterpret_cast<const uint2*>(p.a_lo + abase + k0 + lk);
                 av[0] = bf16_bits_to_float(h.x & 0xffff) + bf16_bits_to_float(l.x & 0xffff);
@@ -653,7 +641,11 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ia_conv_params p) {
                 av[2] = bf16_bits_to_float(h.y & 0xffff) + bf16_bits_to_float(l.y & 0xffff);
                 av[3] = bf16_bits_to_float(h.y >> 16) + bf16_bits_to_float(l.y >> 16);
             }
-            if (wvalid) {
+            if (wvalid && p.op_fmt == IA_OPFMT_F16X1) {
+                uint2 h = *reinterpret_cast<const uint2*>(p.w_hi + wrow + k0 + lk);
+                wv[0] = f16_bits_to_float(h.x & 0xffff); wv[1] = f16_bits_to_float(h.x >> 16);
+                wv[2] = f16_bits_to_float(h.y & 0xffff); wv[3] = f16_bits_to_float(h.y >> 16);
+            } else if (wvalid) {
                 uint2 h = *reinterpret_cast<const uint2*>(p.w_hi + wrow + k0 + lk);
                 uint2 l = *reinterpret_cast<const uint2*>(p.w_lo + wrow + k0 + lk);
                 wv[0] = bf16_bits_to_float(h.x & 0xffff) + bf16_bits_to_float(l.x & 0xffff);
@@ -701,7 +693,8 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ia_conv_params p) {
 }
 
 int ia_conv_validate(const ia_conv_params* p, const char* who) {
-    IA_CHECK(p && p->a_hi && p->a_lo && p->w_hi && p->w_lo, "%s: null operand", who);
+    IA_CHECK(p && (p->op_fmt == IA_OPFMT_BF16X3 || p->op_fmt == IA_OPFMT_F16X1), "%s: unknown operand format", who);
+    IA_CHECK(p->a_hi && p->w_hi && (p->op_fmt == IA_OPFMT_F16X1 || (p->a_lo && p->w_lo)), "%s: null operand", who);
     IA_CHECK(p->Cin_pad > 0 && (p->Cin_pad % 64) == 0, "%s: Cin_pad must be a multiple of 64 (got %d)", who, p->Cin_pad);
     IA_CHECK(p->Cout > 0 && p->Cout_pad >= p->Cout && (p->Cout_pad % 32) == 0, "%s: Cout_pad must be a multiple of 32 >= Cout", who);
     IA_CHECK(p->ntaps >= 1 && p->ntaps <= 9, "%s: ntaps must be in [1,9]", who);
@@ -722,8 +715,8 @@ int ia_conv_validate(const ia_conv_params* p, const char* who) {
                                   !p->emit.out32 && !p->emit.hi2),
              "%s: fused ToRGB needs rgb_w, 1..4 outputs, mode 1, Cout %% 4 == 0 and neither out32 nor emit 2", who);
     IA_CHECK(p->groups <= 1 || (p->imgs_per_group > 0 && p->B == p->groups * p->imgs_per_group), "%s: grouped launch needs B == groups * imgs_per_group", who);
-    IA_CHECK(!p->emit.hi1 || (p->emit.lo1 && p->emit.c1_pad >= p->Cout && (p->emit.c1_pad & 3) == 0), "%s: bad emit 1", who);
-    IA_CHECK(!p->emit.hi2 || (p->emit.lo2 && p->emit.c2_pad >= p->Cout && (p->emit.c2_pad & 3) == 0), "%s: bad emit 2", who);
+    IA_CHECK(!p->emit.hi1 || ((p->emit.lo1 || p->emit.fmt1 == IA_OPFMT_F16X1) && p->emit.c1_pad >= p->Cout && (p->emit.c1_pad & 3) == 0), "%s: bad emit 1", who);
+    IA_CHECK(!p->emit.hi2 || ((p->emit.lo2 || p->emit.fmt2 == IA_OPFMT_F16X1) && p->emit.c2_pad >= p->Cout && (p->emit.c2_pad & 3) == 0), "%s: bad emit 2", who);
     return 0;
 }
 

@@ -363,10 +363,29 @@ class _EngineCache:
         return (_none, ())
 
 
-class ConvPack(_EngineCache):
-    """GEMM-layout weights of one conv layer: bf16 hi/lo [taps][Cout_pad][Cin_pad] and wsq[Cout][Cin]."""
+# Operand formats of the tensor-core convolution (IA_OPFMT_* of the C-ABI)
+FMT_BF16X3 = 0      # bf16 hi/lo pair, hi*hi + hi*lo + lo*hi: fp32-grade products, 3 MMAs per k-step
+FMT_F16X1 = 1       # one fp16 tensor, 1 MMA per k-step
+_FMT_DTYPE = {FMT_BF16X3: torch.bfloat16, FMT_F16X1: torch.float16}
+_FMT_TERMS = {FMT_BF16X3: 3, FMT_F16X1: 1}
 
-    def __init__(self, weight, need_wsq=True):
+
+def layer_fmt(layer):
+    """Operand format a convolution layer runs in.  A layer carries ``tc_fmt`` when its owner measured that the cheaper
+    format keeps the owner's output inside the parity budget (TriPlaneGenerator tags the 3x3 layers of its three backbones:
+    single-pass fp16 there moves the final image by 1e-4..3e-4 max-abs, profiles/r2_conv_precision_probe*.json; the
+    super-resolution layers and every ToRGB stay 3-term).  IA_CONV_PRECISION=bf16x3 forces the 3-term split everywhere
+    (strict mode: every stage within 2e-4 of fp32)."""
+    if os.environ.get('IA_CONV_PRECISION', 'auto') == 'bf16x3':
+        return FMT_BF16X3
+    return int(getattr(layer, 'tc_fmt', FMT_BF16X3))
+
+
+class ConvPack(_EngineCache):
+    """GEMM-layout weights of one conv layer: [taps][Cout_pad][Cin_pad] in operand format ``fmt`` (bf16 hi/lo, or fp16 in
+    w_hi alone with w_lo = None) and wsq[Cout][Cin]."""
+
+    def __init__(self, weight, need_wsq=True, fmt=FMT_BF16X3):
         _require_cuda(weight)
         st = _enter(weight)
         w = _f32c(weight.detach())
@@ -374,21 +393,22 @@ class ConvPack(_EngineCache):
         self.taps = self.kh * self.kw
         self.Cout_pad = _pad_to(self.Cout, 32)
         self.Cin_pad = _pad_to(self.Cin, 64)
+        self.fmt = int(fmt)
         dev = w.device
-        self.w_hi = torch.empty((self.taps, self.Cout_pad, self.Cin_pad), dtype=torch.bfloat16, device=dev)
-        self.w_lo = torch.empty_like(self.w_hi)
+        self.w_hi = torch.empty((self.taps, self.Cout_pad, self.Cin_pad), dtype=_FMT_DTYPE[self.fmt], device=dev)
+        self.w_lo = torch.empty_like(self.w_hi) if self.fmt == FMT_BF16X3 else None
         self.wsq = torch.empty((self.Cout, self.Cin), dtype=torch.float32, device=dev) if need_wsq else None
         _C.check(_C.lib().ia_pack_conv_weight(_p(w), self.Cout, self.Cin, self.kh, self.kw, self.Cout_pad, self.Cin_pad,
-                                              _p(self.w_hi), _p(self.w_lo), _p(self.wsq), st), 'ia_pack_conv_weight')
-        self.key = (weight.data_ptr(), weight._version, str(dev))
+                                              _p(self.w_hi), _p(self.w_lo), _p(self.wsq), self.fmt, st), 'ia_pack_conv_weight')
+        self.key = (weight.data_ptr(), weight._version, str(dev), self.fmt)
 
     @staticmethod
-    def current(cache_owner, attr, weight, need_wsq=True):
-        """Return the pack cached on ``cache_owner.<attr>``; repack when the parameter changed."""
+    def current(cache_owner, attr, weight, need_wsq=True, fmt=FMT_BF16X3):
+        """Return the pack cached on ``cache_owner.<attr>``; repack when the parameter (or the requested format) changed."""
         pack = cache_owner.__dict__.get(attr)
-        key = (weight.data_ptr(), weight._version, str(weight.device))
+        key = (weight.data_ptr(), weight._version, str(weight.device), int(fmt))
         if pack is None or pack.key != key:
-            pack = ConvPack(weight, need_wsq)
+            pack = ConvPack(weight, need_wsq, fmt)
             cache_owner.__dict__[attr] = pack
         return pack
 
@@ -410,7 +430,7 @@ def prepack(module):
             pk = ConvPack.current(m, '_ia_pack', w, need_wsq=False)
         else:
             continue
-        total += pk.w_hi.numel() * 4 + (pk.wsq.numel() * 4 if pk.wsq is not None else 0)
+        total += pk.w_hi.numel() * (4 if pk.w_lo is not None else 2) + (pk.wsq.numel() * 4 if pk.wsq is not None else 0)
     return total
 
 
@@ -419,7 +439,7 @@ class ConvPackGroup(_EngineCache):
     grouped launch (ia_conv_params.groups).  Output channels are zero-padded to the widest member (ToRGB layers of the
     32- and 96-channel backbones)."""
 
-    def __init__(self, weights, need_wsq=True):
+    def __init__(self, weights, need_wsq=True, fmt=FMT_BF16X3):
         Cout = max(int(w.shape[0]) for w in weights)
         packs = []
         for w in weights:
@@ -428,22 +448,23 @@ class ConvPackGroup(_EngineCache):
                 wp = torch.zeros((Cout,) + tuple(w.shape[1:]), dtype=w.dtype, device=w.device)
                 wp[:w.shape[0]] = w
                 w = wp
-            packs.append(ConvPack(w, need_wsq))
+            packs.append(ConvPack(w, need_wsq, fmt))
         p0 = packs[0]
         self.G = len(packs)
+        self.fmt = int(fmt)
         self.Cout, self.Cin, self.kh, self.kw, self.taps = Cout, p0.Cin, p0.kh, p0.kw, p0.taps
         self.Cout_pad, self.Cin_pad = p0.Cout_pad, p0.Cin_pad
         self.w_hi = torch.cat([q.w_hi for q in packs], dim=0).contiguous()
-        self.w_lo = torch.cat([q.w_lo for q in packs], dim=0).contiguous()
+        self.w_lo = torch.cat([q.w_lo for q in packs], dim=0).contiguous() if p0.w_lo is not None else None
         self.wsq = [q.wsq for q in packs]
-        self.key = tuple((w.data_ptr(), w._version, str(w.device)) for w in weights)
+        self.key = tuple((w.data_ptr(), w._version, str(w.device)) for w in weights) + (self.fmt,)
 
     @staticmethod
-    def current(cache_owner, attr, weights, need_wsq=True):
+    def current(cache_owner, attr, weights, need_wsq=True, fmt=FMT_BF16X3):
         pack = cache_owner.__dict__.get(attr)
-        key = tuple((w.data_ptr(), w._version, str(w.device)) for w in weights)
+        key = tuple((w.data_ptr(), w._version, str(w.device)) for w in weights) + (int(fmt),)
         if pack is None or pack.key != key:
-            pack = ConvPackGroup(weights, need_wsq)
+            pack = ConvPackGroup(weights, need_wsq, fmt)
             cache_owner.__dict__[attr] = pack
         return pack
 
@@ -490,19 +511,20 @@ class StylePlan(_EngineCache):
         return self.styles, self.dcoefs
 
 
-def modsplit(x_nhwc, styles=None, cond=None, cond_alpha=None, C_pad=None):
-    """x [B,H,W,C] fp32 (pixel stride = x.stride(2)) -> (hi, lo) bf16 [B,H,W,C_pad] of x*styles (after optional blend)."""
-    sp = modsplit_split(x_nhwc, styles, cond, cond_alpha, C_pad)
+def modsplit(x_nhwc, styles=None, cond=None, cond_alpha=None, C_pad=None, fmt=FMT_BF16X3):
+    """x [B,H,W,C] fp32 (pixel stride = x.stride(2)) -> (hi, lo) [B,H,W,C_pad] of x*styles (after optional blend) in operand
+    format ``fmt`` (lo is None for FMT_F16X1)."""
+    sp = modsplit_split(x_nhwc, styles, cond, cond_alpha, C_pad, fmt=fmt)
     return sp.hi, sp.lo
 
 
-def modsplit_split(x_nhwc, styles=None, cond=None, cond_alpha=None, C_pad=None, pad_row=False):
+def modsplit_split(x_nhwc, styles=None, cond=None, cond_alpha=None, C_pad=None, pad_row=False, fmt=FMT_BF16X3):
     """modsplit into a Split; pad_row: the row-padded layout of new_split(pad_row=True)."""
     st = _enter(x_nhwc)
     B, H, W, Cc = x_nhwc.shape
     assert x_nhwc.stride(3) == 1 and x_nhwc.stride(1) == W * x_nhwc.stride(2) and x_nhwc.stride(0) == H * x_nhwc.stride(1)
     C_pad = _pad_to(Cc, 64) if C_pad is None else C_pad
-    sp = new_split(B, H, W, C_pad, x_nhwc.device, pad_row=pad_row)
+    sp = new_split(B, H, W, C_pad, x_nhwc.device, pad_row=pad_row, fmt=fmt)
     cond_ld = 0
     if cond is not None:
         assert cond.shape == x_nhwc.shape and cond.stride(3) == 1 and cond_alpha is not None
@@ -510,7 +532,7 @@ def modsplit_split(x_nhwc, styles=None, cond=None, cond_alpha=None, C_pad=None, 
         assert cond_alpha.is_contiguous() and cond_alpha.numel() == B * H * W
         cond_ld = cond.stride(2)
     p = _C.ModsplitParams(_p(x_nhwc), x_nhwc.stride(2), _p(styles), _p(cond), cond_ld, _p(cond_alpha), _p(sp.hi), _p(sp.lo),
-                          B, H * W, Cc, C_pad, sp.img_pix)
+                          B, H * W, Cc, C_pad, sp.img_pix, sp.fmt)
     _C.check(_C.lib().ia_modsplit(C.byref(p), st), 'ia_modsplit')
     return sp
 
@@ -519,11 +541,12 @@ class Split:
     """A tensor-core A operand: bf16 hi/lo pair [B,H,W,C_pad] holding x * styles of the consuming layer.  ``img_rows`` > H: the
     images are ``img_rows`` rows apart in memory and the extra rows are zero (hi / lo are views of the padded buffers) -- the
     layout a stride-2 transposed convolution tiles across image boundaries (ia_conv_params.a_img_rows)."""
-    __slots__ = ('hi', 'lo', 'C_pad', 'img_rows')
+    __slots__ = ('hi', 'lo', 'C_pad', 'img_rows', 'fmt')
 
     def __init__(self, hi, lo, img_rows=None):
         self.hi, self.lo, self.C_pad = hi, lo, hi.shape[-1]
         self.img_rows = int(hi.shape[1] if img_rows is None else img_rows)
+        self.fmt = FMT_F16X1 if hi.dtype == torch.float16 else FMT_BF16X3       # (FMT_F16X1: lo is None)
 
     @property
     def img_pix(self):
@@ -537,18 +560,20 @@ def pad_row_wanted(H, W, impl=None):
     return ((impl or _conv_impl) == 'tc' and H >= 32 and W >= 32 and os.environ.get('IA_CONV_CAT_ROWS', '1') != '0')
 
 
-def new_split(B, H, W, C_pad, device, C=None, pad_row=False):
-    """Uninitialised operand buffers; zero-filled when the producer leaves padding channels (C < C_pad) untouched.
-    pad_row: [B, H+1, W, C_pad] buffers with row H zeroed, exposed as [B, H, W, C_pad] views (see Split)."""
+def new_split(B, H, W, C_pad, device, C=None, pad_row=False, fmt=FMT_BF16X3):
+    """Uninitialised operand buffers in format ``fmt``; zero-filled when the producer leaves padding channels (C < C_pad)
+    untouched.  pad_row: [B, H+1, W, C_pad] buffers with row H zeroed, exposed as [B, H, W, C_pad] views (see Split)."""
     make = torch.zeros if (C is not None and C != C_pad) else torch.empty
     rows = H + 1 if pad_row else H
-    hi = make((B, rows, W, C_pad), dtype=torch.bfloat16, device=device)
-    lo = make((B, rows, W, C_pad), dtype=torch.bfloat16, device=device)
+    two = fmt == FMT_BF16X3
+    hi = make((B, rows, W, C_pad), dtype=_FMT_DTYPE[fmt], device=device)
+    lo = make((B, rows, W, C_pad), dtype=_FMT_DTYPE[fmt], device=device) if two else None
     if pad_row:
         if make is torch.empty:
             hi[:, H].zero_()
-            lo[:, H].zero_()
-        return Split(hi[:, :H], lo[:, :H], img_rows=rows)
+            if two:
+                lo[:, H].zero_()
+        return Split(hi[:, :H], lo[:, :H] if two else None, img_rows=rows)
     return Split(hi, lo)
 
 
@@ -568,9 +593,11 @@ def _emit(out32=None, e1=None, e2=None, rgb=None):
         sp, st = e1
         e.hi1, e.lo1, e.s1, e.c1_pad = _p(sp.hi), _p(sp.lo), _p(st), sp.C_pad
         e.e1_img_pix = sp.img_pix
+        e.fmt1 = sp.fmt
     if e2 is not None:
         sp, st = e2
         e.hi2, e.lo2, e.s2, e.c2_pad = _p(sp.hi), _p(sp.lo), _p(st), sp.C_pad
+        e.fmt2 = sp.fmt
     return e
 
 
@@ -590,6 +617,14 @@ def _splitk_scratch(p, device, st):
         buf = (torch.empty(_SPLITK_WS_BYTES // 4, dtype=torch.float32, device=device), torch.zeros(_SPLITK_COUNTERS, dtype=torch.int32, device=device))
         _SPLITK[key] = buf
     p.splitk_ws, p.splitk_ws_bytes, p.splitk_counters, p.splitk_n_counters = _p(buf[0]), _SPLITK_WS_BYTES, _p(buf[1]), _SPLITK_COUNTERS
+
+
+def _check_fmt(hi, lo, pack):
+    """The activation operand must be in the format the weights were packed in."""
+    fmt = FMT_F16X1 if hi.dtype == torch.float16 else FMT_BF16X3
+    if fmt != pack.fmt or (fmt == FMT_BF16X3 and lo is None):
+        raise RuntimeError(f'convolution operands disagree: activations in format {fmt}, weights packed in format {pack.fmt}')
+    return fmt
 
 
 def _conv_call(p, st, impl=None):
@@ -618,6 +653,7 @@ def conv_same(hi, lo, pack, Cin_pad, out32, dcoef=None, noise=None, noise_streng
     p = _C.ConvParams()
     p.a_hi, p.a_lo, p.B, p.H, p.W, p.Cin_pad = _p(hi), _p(lo), B, H, W, Cin_pad
     p.w_hi, p.w_lo, p.Cout, p.Cout_pad, p.n_taps_total = _p(pack.w_hi), _p(pack.w_lo), pack.Cout, pack.Cout_pad, pack.taps
+    p.op_fmt = _check_fmt(hi, lo, pack)
     p.GH, p.GW, p.ntaps = H, W, k * k
     t = 0
     for ky in range(k):
@@ -634,7 +670,7 @@ def conv_same(hi, lo, pack, Cin_pad, out32, dcoef=None, noise=None, noise_streng
         assert mode == 2 and img_prev.is_contiguous() and tuple(img_prev.shape) == (B, H // 2, W // 2, pack.Cout), (img_prev.shape, hi.shape)
         p.img_prev = _p(img_prev)
     _set_group(p, group)
-    _count_conv(B, H, W, pack, k * k, stride=alg_stride)
+    _count_conv(B, H, W, pack, k * k, stride=alg_stride, terms=_FMT_TERMS[pack.fmt])
     _splitk_scratch(p, hi.device, st)
     _conv_call(p, st, impl)
 
@@ -669,6 +705,7 @@ def conv_transpose_up2_raw(hi, lo, pack, Cin_pad, raw, impl=None, group=None, im
             k += 1
             p.a_hi, p.a_lo, p.B, p.H, p.W, p.Cin_pad = _p(hi), _p(lo), B, H, W, Cin_pad
             p.w_hi, p.w_lo, p.Cout, p.Cout_pad, p.n_taps_total = _p(pack.w_hi), _p(pack.w_lo), pack.Cout, pack.Cout_pad, pack.taps
+            p.op_fmt = _check_fmt(hi, lo, pack)
             p.GH, p.GW = H + 1 - py, W + 1 - px
             t = 0
             for (ky, dy) in rowtaps[py]:
@@ -683,7 +720,7 @@ def conv_transpose_up2_raw(hi, lo, pack, Cin_pad, raw, impl=None, group=None, im
             p.a_img_rows = int(img_rows) if img_rows and img_rows != H else 0
             _set_group(p, group)
             _splitk_scratch(p, hi.device, st)
-    _count_conv(B, H, W, pack, 9)
+    _count_conv(B, H, W, pack, 9, terms=_FMT_TERMS[pack.fmt])
     if (impl or _conv_impl) == 'tc':
         _C.check(_C.lib().ia_conv_tc_phases(phases, 4, st), 'ia_conv_tc_phases')     # one persistent launch for the four phases
     else:

@@ -150,8 +150,12 @@ class SynthesisLayer(torch.nn.Module):
         self.bias = torch.nn.Parameter(torch.zeros([out_channels]))
 
     # ---- engine-facing pieces ----
+    def fmt(self):
+        """Operand format this layer's convolution runs in (rt.layer_fmt: the owner's per-layer precision choice)."""
+        return rt.layer_fmt(self)
+
     def pack(self):
-        return rt.ConvPack.current(self, '_ia_pack', self.weight, need_wsq=True)
+        return rt.ConvPack.current(self, '_ia_pack', self.weight, need_wsq=True, fmt=self.fmt())
 
     def style_entry(self, w_index):
         p = self.pack()
@@ -166,7 +170,7 @@ class SynthesisLayer(torch.nn.Module):
         B, H, W, Cin = x.shape
         assert Cin == self.in_channels and H * self.up == self.resolution, (x.shape, self.in_channels, self.resolution)
         pack = self.pack()
-        hi, lo = rt.modsplit(x, styles, cond=cond, cond_alpha=cond_alpha, C_pad=pack.Cin_pad)
+        hi, lo = rt.modsplit(x, styles, cond=cond, cond_alpha=cond_alpha, C_pad=pack.Cin_pad, fmt=pack.fmt)
         noise = _noise_for(self, noise_mode, B, x.device)
         strength = self.noise_strength if noise is not None else None
         act_gain = self.act_gain * gain
@@ -385,17 +389,17 @@ class SynthesisBlock(torch.nn.Module):
         i = 0
         if self.in_channels == 0:
             x0 = self.const.detach().permute(1, 2, 0).unsqueeze(0).expand(B, -1, -1, -1).contiguous()
-            hi, lo = rt.modsplit(x0, styles[0], C_pad=self.conv1.pack().Cin_pad)
+            hi, lo = rt.modsplit(x0, styles[0], C_pad=self.conv1.pack().Cin_pad, fmt=self.conv1.fmt())
             a1 = rt.Split(hi, lo)
         else:
-            a1 = rt.new_split(B, R, R, self.conv1.pack().Cin_pad, dev, C=self.conv1.in_channels)
+            a1 = rt.new_split(B, R, R, self.conv1.pack().Cin_pad, dev, C=self.conv1.in_channels, fmt=self.conv1.fmt())
             if condition is None:
                 self.conv0.run_split(a_in, dcoefs[0], noise_mode=noise_mode, gain=gain, e1=(a1, styles[1]))
             else:
                 # CS-SFT (networks_stylegan2_new.py:448-452) needs the fp32 activation: once per identity, not per frame
                 x = self.conv0.run_split(a_in, dcoefs[0], noise_mode=noise_mode, gain=gain, want32=True)
                 rt.sft_half(x, condition[0].permute(0, 2, 3, 1), condition[1].permute(0, 2, 3, 1))
-                hi, lo = rt.modsplit(x, styles[1], C_pad=self.conv1.pack().Cin_pad)
+                hi, lo = rt.modsplit(x, styles[1], C_pad=self.conv1.pack().Cin_pad, fmt=self.conv1.fmt())
                 a1 = rt.Split(hi, lo)
             i = 1
         has_rgb = hasattr(self, 'torgb')
@@ -405,7 +409,7 @@ class SynthesisBlock(torch.nn.Module):
                     rt.can_fuse_torgb(R, R, self.conv1.out_channels, self.torgb.out_channels))
         a_rgb = rt.new_split(B, R, R, self.torgb.pack().Cin_pad, dev, C=self.torgb.in_channels) if (has_rgb and not fuse_rgb) else None
         a_next = rt.new_split(B, R, R, next_conv.pack().Cin_pad, dev, C=next_conv.in_channels,
-                              pad_row=next_conv.up == 2 and rt.pad_row_wanted(R, R)) if next_conv is not None else None
+                              pad_row=next_conv.up == 2 and rt.pad_row_wanted(R, R), fmt=next_conv.fmt()) if next_conv is not None else None
         rgb_raw = torch.zeros((B, R, R, self.torgb.out_channels), dtype=torch.float32, device=dev) if fuse_rgb else None
         x32 = self.conv1.run_split(a1, dcoefs[i], noise_mode=noise_mode, gain=gain, want32=want_x32,
                                    e1=(a_next, next_styles) if a_next is not None else None,
@@ -532,7 +536,7 @@ class SynthesisNetwork(torch.nn.Module):
                         cnd, cal = _split_cond(cond_list[1 + index - start_layer])
                         nxt = blocks[index + 1].conv0
                         a = rt.modsplit_split(x32, styles[spans[index + 1][0]], cond=cnd, cond_alpha=cal, C_pad=nxt.pack().Cin_pad,
-                                              pad_row=nxt.up == 2 and rt.pad_row_wanted(x32.shape[1], x32.shape[2]))
+                                              pad_row=nxt.up == 2 and rt.pad_row_wanted(x32.shape[1], x32.shape[2]), fmt=nxt.fmt())
         if return_list:
             x_list.append(rt.from_nhwc(img))
             return x_list
@@ -588,7 +592,7 @@ def can_group_prefix(nets, upto_res=32):
             for (k, l), (k0, l0) in zip(b.layers(), b0.layers()):
                 if k != k0 or l.in_channels != l0.in_channels or (k == 'conv' and (l.out_channels != l0.out_channels or l.up != l0.up or
                                                                                  l.activation != l0.activation or l.conv_clamp != l0.conv_clamp or
-                                                                                 l.use_noise != l0.use_noise or (l.up == 2 and not _layer_filter_ok(l)))):
+                                                                                 l.use_noise != l0.use_noise or l.fmt() != l0.fmt() or (l.up == 2 and not _layer_filter_ok(l)))):
                     return False
                 if k == 'torgb' and l.conv_clamp != l0.conv_clamp:
                     return False
@@ -631,15 +635,15 @@ def synthesis_prefix_grouped(nets, ws, noise_mode='const', upto_res=32):
         lo_i = spans[index][0]
         i = 0
         conv1s = [b.conv1 for b in blocks]
-        pack1 = rt.ConvPackGroup.current(conv1s[0], '_ia_gpack', [c.weight for c in conv1s])
+        pack1 = rt.ConvPackGroup.current(conv1s[0], '_ia_gpack', [c.weight for c in conv1s], fmt=conv1s[0].fmt())
         if b0.in_channels == 0:
             x0 = torch.cat([b.const.detach().permute(1, 2, 0).unsqueeze(0).expand(B, -1, -1, -1) for b in blocks], dim=0).contiguous()
-            hi, lo = rt.modsplit(x0, cat_layer(lo_i, 0), C_pad=pack1.Cin_pad)
+            hi, lo = rt.modsplit(x0, cat_layer(lo_i, 0), C_pad=pack1.Cin_pad, fmt=pack1.fmt)
             a1 = rt.Split(hi, lo)
         else:
             conv0s = [b.conv0 for b in blocks]
-            pack0 = rt.ConvPackGroup.current(conv0s[0], '_ia_gpack', [c.weight for c in conv0s])
-            a1 = rt.new_split(G * B, res, res, pack1.Cin_pad, dev, C=conv1s[0].in_channels)
+            pack0 = rt.ConvPackGroup.current(conv0s[0], '_ia_gpack', [c.weight for c in conv0s], fmt=conv0s[0].fmt())
+            a1 = rt.new_split(G * B, res, res, pack1.Cin_pad, dev, C=conv1s[0].in_channels, fmt=pack1.fmt)
             H = res // 2
             raw = torch.empty((G * B, 2 * H + 1, 2 * H + 1, pack0.Cout), dtype=torch.float32, device=dev)
             rt.conv_transpose_up2_raw(a.hi, a.lo, pack0, pack0.Cin_pad, raw, group=group(0))
@@ -654,7 +658,7 @@ def synthesis_prefix_grouped(nets, ws, noise_mode='const', upto_res=32):
         nxt = [getattr(n, f'b{nets[0].block_resolutions[index + 1]}').conv0 for n in nets]
         # the operand that leaves the prefix feeds each network's own (ungrouped) transposed convolution: row-padded layout
         a_next = rt.new_split(G * B, res, res, nxt[0].pack().Cin_pad, dev, C=nxt[0].in_channels,
-                              pad_row=last and nxt[0].up == 2 and rt.pad_row_wanted(res, res))
+                              pad_row=last and nxt[0].up == 2 and rt.pad_row_wanted(res, res), fmt=nxt[0].fmt())
         x32 = torch.empty((G * B, res, res, pack1.Cout), dtype=torch.float32, device=dev) if last else None
         nz, ns, gs = layer_noise(conv1s)
         rt.conv_same(a1.hi, a1.lo, pack1, pack1.Cin_pad, x32, dcoef=cat_layer(lo_i + i, 1), noise=nz, noise_strength=ns,
@@ -672,7 +676,7 @@ def synthesis_prefix_grouped(nets, ws, noise_mode='const', upto_res=32):
         im = img[sl]
         if n.img_channels != im.shape[-1]:
             im = im[..., :n.img_channels].contiguous()
-        out.append(dict(index=k_last, x32=x32[sl], img=im, a_next=rt.Split(a_next.hi[sl], a_next.lo[sl], img_rows=a_next.img_rows),
+        out.append(dict(index=k_last, x32=x32[sl], img=im, a_next=rt.Split(a_next.hi[sl], a_next.lo[sl] if a_next.lo is not None else None, img_rows=a_next.img_rows),
                         styles=passes[g][0], dcoefs=passes[g][1], spans=passes[g][2]))
     return out
 

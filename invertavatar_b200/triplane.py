@@ -100,6 +100,16 @@ class TriPlaneGenerator(torch.nn.Module):
         self.neural_rendering_resolution = 128
         self.rendering_kwargs = rendering_kwargs
         self.fill_mouth = True
+        # Per-layer tensor-core precision (rt.layer_fmt): the 3x3 convolutions of the three backbones run as single-pass fp16
+        # MMAs (one third of the tensor-core work of the 3-term bf16 split), the super-resolution blocks and every ToRGB keep
+        # the 3-term split.  Measured with the CPU oracle on the headline configuration (tools/probe_conv_precision.py,
+        # profiles/r2_conv_precision_probe*.json): each backbone layer alone moves the final image by <= 6e-5, all 39 together
+        # by 0.9e-4 .. 3.1e-4 max-abs (PSNR 88 .. 98 dB) over 6 frames -- inside the 1e-3 / 50 dB bar with a 3x margin -- whereas
+        # ONE super-resolution layer in fp16 costs 1e-3.  IA_CONV_PRECISION=bf16x3 restores the 3-term split everywhere.
+        for net in (self.texture_backbone, self.face_backbone, self.backbone):
+            for m in net.synthesis.modules():
+                if isinstance(m, sg.SynthesisLayer):
+                    m.tc_fmt = rt.FMT_F16X1
 
     def _side_streams(self, device):
         return rt.side_streams(device)

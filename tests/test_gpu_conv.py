@@ -270,3 +270,57 @@ def test_split_k_matches_unsplit_and_is_deterministic(monkeypatch, B, H, cin, co
     # the ticket counters are left at zero for the next launch
     for ws, cnt in rt._SPLITK.values():
         assert int(cnt.abs().max()) == 0
+
+
+@pytest.mark.parametrize('cin,cout,res,up,B', [(512, 512, 16, 1, 2), (512, 256, 32, 2, 2), (128, 128, 64, 1, 2), (256, 128, 64, 2, 1),
+                                              (40, 72, 24, 2, 5), (64, 64, 4, 1, 3), (128, 96, 8, 2, 1)])
+def test_synthesis_layer_single_pass_fp16(cin, cout, res, up, B):
+    """IA_OPFMT_F16X1 (the format TriPlaneGenerator assigns to its backbone layers): one fp16 MMA per k-step.  Against the fp32
+    oracle the result carries the operand rounding (2^-11 relative per element: ~1e-3 of the output scale); against the
+    CUDA-core kernel reading the SAME fp16 operands it is tight (only the accumulation order differs)."""
+    L = _layer(cin, cout, res, up, seed=cin + cout)
+    L.tc_fmt = rt.FMT_F16X1
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(B, cin, res // up, res // up, generator=g)
+    w = torch.randn(B, 64, generator=g)
+    ref = o_sg.synthesis_layer(L.state_dict(), x, w, up=up, noise_mode='const', gain=0.8, conv_clamp=3.0)
+    L.conv_clamp = 3.0
+    L = L.to(DEV)
+    old = rt.get_conv_impl()
+    try:
+        rt.set_conv_impl('tc')
+        y = L(x.to(DEV), w.to(DEV), noise_mode='const', gain=0.8)
+        assert L.pack().fmt == rt.FMT_F16X1 and L.pack().w_lo is None and L.pack().w_hi.dtype == torch.float16
+        rt.set_conv_impl('simt')
+        y_simt = L(x.to(DEV), w.to(DEV), noise_mode='const', gain=0.8)
+    finally:
+        rt.set_conv_impl(old)
+    scale = max(1.0, float(ref.abs().max()))
+    assert maxerr(y, ref) <= 2e-3 * scale, maxerr(y, ref)
+    assert maxerr(y, y_simt) <= TOL * scale, maxerr(y, y_simt)
+
+
+def test_synthesis_network_mixed_precision_chain(monkeypatch):
+    """Fused chain with per-layer formats: 3x3 layers single-pass fp16, ToRGB layers 3-term (every epilogue emits its consumer's
+    operand in the consumer's format); IA_CONV_PRECISION=bf16x3 restores the strict path on the same module."""
+    net = _small_network()
+    for m in net.modules():
+        if isinstance(m, sg.SynthesisLayer):
+            m.tc_fmt = rt.FMT_F16X1
+    g = torch.Generator().manual_seed(3)
+    ws = torch.randn(2, net.num_ws, 64, generator=g)
+    ref = o_sg.synthesis_network(net.state_dict(), ws, return_list=True, out_res=(8, 32))
+    net = net.to(DEV)
+    got = net(ws.to(DEV), return_list=True, out_res=(8, 32), noise_mode='const')
+    monkeypatch.setenv('IA_CONV_PRECISION', 'bf16x3')
+    strict = net(ws.to(DEV), return_list=True, out_res=(8, 32), noise_mode='const')
+    monkeypatch.delenv('IA_CONV_PRECISION')
+    assert len(got) == len(ref)
+    worst = 0.0
+    for a, s_, r in zip(got, strict, ref):
+        scale = max(1.0, float(r.abs().max()))
+        assert maxerr(s_, r) <= 2 * TOL * scale
+        e = maxerr(a, r) / scale
+        worst = max(worst, e)
+        assert e <= 5e-3, e
+    assert worst > 1e-5, 'the single-pass format was not exercised'

@@ -23,10 +23,14 @@ def test_expanded_ws_batch():
         assert torch.equal(x[0], x[2])
 
 
-def test_grouped_prefix_matches_sequential(monkeypatch):
+@pytest.mark.parametrize('precision,tol', [('bf16x3', 1e-4), ('auto', 2e-3)])
+def test_grouped_prefix_matches_sequential(monkeypatch, precision, tol):
     """The grouped evaluation of the three backbones' low-resolution blocks (ia_conv_params.groups) must reproduce the
-    one-network-at-a-time path: same kernels, same operands, different tiling only."""
+    one-network-at-a-time path: same kernels, same operands, different tiling only -- i.e. a different fp32 accumulation
+    order, whose last-bit differences the next layer's operand rounding turns into (rare) one-ulp operand differences:
+    2^-16 relative in the strict 3-term format, 2^-11 in the single-pass fp16 format of the shipped policy."""
     import copy
+    monkeypatch.setenv('IA_CONV_PRECISION', precision)
     G = copy.deepcopy(build_generator(16, 16)).to('cuda')
     B = 3
     z, cond, c, uv = synth.latents(B).cuda(), synth.frontal_camera(B).cuda(), synth.cameras(B).cuda(), synth.uvcoords_image(B).cuda()
@@ -40,9 +44,9 @@ def test_grouped_prefix_matches_sequential(monkeypatch):
                                      depth_jitter=jit.clone(), return_featmap=True)
     for k in ('image', 'image_raw', 'feature_image', 'triplane'):
         d = float((outs['1'][k].float() - outs['0'][k].float()).abs().max())
-        assert d <= 2e-5 * max(1.0, float(outs['0'][k].abs().max())), (k, d)
+        assert d <= tol * max(1.0, float(outs['0'][k].abs().max())), (k, d)
     for a, b in zip(outs['1']['texture'], outs['0']['texture']):
-        assert float((a - b).abs().max()) <= 2e-5 * max(1.0, float(b.abs().max()))
+        assert float((a - b).abs().max()) <= tol * max(1.0, float(b.abs().max()))
 
 
 def test_graphed_synthesis_matches_eager():
@@ -104,7 +108,7 @@ def test_prepack_builds_every_pack_once():
     from invertavatar_b200 import runtime as rt
     G = copy.deepcopy(build_generator(16, 16)).to('cuda')
     nbytes = invertavatar_b200.prepack(G)
-    assert nbytes > 300e6                       # 88 M parameters -> ~353 MB of bf16 hi/lo pairs
+    assert nbytes > 150e6                       # 88 M parameters: fp16 for the backbone 3x3 layers (2 B), bf16 hi/lo pairs (4 B) elsewhere
     packs = {id(m): m.__dict__['_ia_pack'] for m in G.modules() if '_ia_pack' in m.__dict__}
     assert len(packs) == 3 * 20 + 6             # per backbone: b4 conv1+torgb, b8..b256 conv0+conv1+torgb; SR: 2 blocks x 3
     z, cond, c, uv = synth.latents(1).cuda(), synth.frontal_camera(1).cuda(), synth.cameras(1).cuda(), synth.uvcoords_image(1).cuda()

@@ -12,8 +12,16 @@ from oracle import triplane as o_tp
 
 pytestmark = pytest.mark.gpu
 DEV = 'cuda'
-IMAGE_ATOL = 1e-3       # north_star
-STAGE_ATOL = 2e-4       # intermediate feature maps (fp32 3-term split convolutions)
+IMAGE_ATOL = 1e-3       # north_star: the generator's outputs (image, image_raw, image_depth, feature_image)
+# intermediate feature maps, relative to their scale.  strict = IA_CONV_PRECISION=bf16x3 (3-term split in every convolution);
+# auto = the shipped per-layer policy (backbone 3x3 layers single-pass fp16: 2^-11 relative operand rounding per layer)
+STAGE_ATOL = {'bf16x3': 2e-4, 'auto': 2e-3}
+
+
+@pytest.fixture(params=['auto', 'bf16x3'])
+def precision(request, monkeypatch):
+    monkeypatch.setenv('IA_CONV_PRECISION', request.param)
+    return request.param
 
 
 def _run(tag, npz, stages=True):
@@ -44,12 +52,13 @@ def _run(tag, npz, stages=True):
     return g, G, ws, out
 
 
-def _check(g, tag, out):
+def _check(g, tag, out, precision='bf16x3'):
+    STAGE = STAGE_ATOL[precision]
     errs = {}
     for i, t in enumerate(out['texture']):
-        errs[f'texture{i}'] = compare(t, unpack(f'{tag}/texture{i}', g), STAGE_ATOL * max(1.0, float(np.abs(g[f'{tag}/texture{i}/sub']).max())), f'texture{i}')[0]
+        errs[f'texture{i}'] = compare(t, unpack(f'{tag}/texture{i}', g), STAGE * max(1.0, float(np.abs(g[f'{tag}/texture{i}/sub']).max())), f'texture{i}')[0]
     def scaled(name):
-        return STAGE_ATOL * max(1.0, float(np.abs(g[f'{tag}/{name}/sub']).max()))
+        return STAGE * max(1.0, float(np.abs(g[f'{tag}/{name}/sub']).max()))
     for i, t in enumerate(out.get('static', [])):
         errs[f'static{i}'] = compare(t, unpack(f'{tag}/static{i}', g), scaled(f'static{i}'), f'static{i}')[0]
     for i, t in enumerate(out.get('rendering_images', [])):
@@ -57,7 +66,7 @@ def _check(g, tag, out):
     if 'full_alpha' in out:
         errs['full_alpha'] = compare(out['full_alpha'], unpack(f'{tag}/full_alpha', g), 1e-6, 'full_alpha')[0]
         errs['stitch'] = compare(out['stitch'], unpack(f'{tag}/stitch', g), scaled('stitch'), 'stitch')[0]
-    errs['triplane'] = compare(out['triplane'], unpack(f'{tag}/triplane', g), STAGE_ATOL * max(1.0, float(np.abs(g[f'{tag}/triplane/sub']).max())), 'triplane')[0]
+    errs['triplane'] = compare(out['triplane'], unpack(f'{tag}/triplane', g), STAGE * max(1.0, float(np.abs(g[f'{tag}/triplane/sub']).max())), 'triplane')[0]
     errs['feature_image'] = compare(out['feature_image'], unpack(f'{tag}/feature_image', g), IMAGE_ATOL, 'feature_image')[0]
     errs['image_raw'] = compare(out['image_raw'], unpack(f'{tag}/image_raw', g), IMAGE_ATOL, 'image_raw')[0]
     errs['image_depth'] = compare(out['image_depth'], unpack(f'{tag}/image_depth', g), IMAGE_ATOL, 'image_depth')[0]
@@ -66,9 +75,9 @@ def _check(g, tag, out):
     return errs
 
 
-def test_synthesis_c1_golden():
+def test_synthesis_c1_golden(precision):
     g, G, ws, out = _run('c1', 'synthesis_c1.npz')
-    _check(g, 'c1', out)
+    _check(g, 'c1', out, precision)
     assert tuple(out['image'].shape) == (1, 3, 512, 512) and tuple(out['image_raw'].shape) == (1, 3, 64, 64)
     # per-frame driver of eval_seq.py: synthesis_withTexture, evaluation=False with pinned importance u
     ws1 = ws[:1]
@@ -94,11 +103,11 @@ def test_synthesis_c1_psnr_vs_oracle():
     assert err <= IMAGE_ATOL and p > 50.0
 
 
-def test_synthesis_c2_golden():
+def test_synthesis_c2_golden(precision):
     """Headline shape 128^2 x (48+48), two different frames in one batch; then the per-frame driver of eval_seq.py
     (synthesis_withTexture, evaluation=False with pinned u) at the same size."""
     g, G, ws, out = _run('c2', 'synthesis_c2.npz')
-    _check(g, 'c2', out)
+    _check(g, 'c2', out, precision)
     ws1 = ws[:1]
     tex = G.texture_backbone.synthesis(ws1, cond_list=None, return_list=True, noise_mode='const')
     sta = G.backbone.synthesis(ws1, cond_list=None, return_list=True, noise_mode='const')

@@ -33,6 +33,7 @@ ap.add_argument('--depth', type=int, default=48)
 ap.add_argument('--frames', type=int, default=3)
 ap.add_argument('--budget', type=float, default=5e-4)
 ap.add_argument('--modes', default='f16x1,f16a,f16w')
+ap.add_argument('--eval-mix', default='', help="skip the search: evaluate a preset ('backbones_f16x1') on --frames frames, with bf16x3 arithmetic elsewhere")
 args = ap.parse_args()
 torch.set_num_threads(os.cpu_count() or 1)
 
@@ -124,6 +125,23 @@ for L, n in zip(layers, names):
     L['name'] = n
 total_gflop = sum(L['gflop'] for L in layers)
 print(f'{len(layers)} conv layers, {total_gflop:.1f} GFLOP/frame, reference render {time.time() - t0:.1f} s for {args.frames} frames', file=sys.stderr)
+
+if args.eval_mix:
+    assert args.eval_mix == 'backbones_f16x1'
+    mix = {L['idx']: 'f16x1' for L in layers if not L['name'].startswith('sr.')}
+    full = {L['idx']: mix.get(L['idx'], 'bf16x3') for L in layers}
+    res = []
+    for f in range(args.frames):
+        PREC.clear(); PREC.update(full)
+        e, p = cmp(render(f), refs[f])
+        res.append({'frame': f, 'max_abs': e, 'psnr_db': p})
+        print(res[-1], file=sys.stderr)
+    issued = sum(L['gflop'] * (1 if L['idx'] in mix else 3) for L in layers)
+    print(json.dumps({'config': f'{args.res}^2 x {args.depth}+{args.depth}, batch 1, CPU oracle, {args.frames} frames', 'mix': 'every backbone 3x3 layer single-pass fp16 '
+                      '(A = rn_f16(x*s), W = rn_f16(w)), super-resolution layers and ToRGB layers bf16x3', 'frames': res,
+                      'total_gflop_per_frame': total_gflop, 'issued_gflop_mix': issued, 'issued_gflop_3term': 3 * total_gflop,
+                      'algorithmic_over_issued': total_gflop / issued}, indent=1))
+    sys.exit(0)
 
 modes = args.modes.split(',')
 cost = {'f16x1': 1, 'bf16x1': 1, 'f16a': 2, 'f16w': 2, 'bf16a': 2, 'bf16w': 2}
