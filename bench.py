@@ -326,8 +326,19 @@ class _Harness:
         self.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        # Host flow control: at most `depth` steps are in flight.  Without it the host (8 ms of launch work per 17 ms step) runs
+        # up to a launch queue (~8 steps) ahead of the device, every step in flight pins its own set of cross-stream activation
+        # blocks in torch's caching allocator (blocks handed between the backbone streams are reusable only after their
+        # record_stream events complete), and the pool grows by cudaMalloc in the middle of a timed region -- measured as a
+        # one-off 100-200 ms stall in one region out of five.  The device still runs back to back (two steps are queued).
+        depth, marks = 2, []
         for _ in range(steps):
+            if len(marks) >= depth:
+                marks.pop(0).synchronize()
             fn()
+            ev = torch.cuda.Event()
+            ev.record()
+            marks.append(ev)
         torch.cuda.current_stream().wait_stream(self.copy_stream)   # the last read-back belongs to the timed region
         e1.record()
         self.barrier()

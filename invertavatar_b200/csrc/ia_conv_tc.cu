@@ -1366,8 +1366,13 @@ extern "C" int ia_conv_tc(const ia_conv_params* p, void* stream) {
                                     // row) bounds them and 128-byte rows (k-block 64) halve the request count
         if (mode < 0) { const char* e = getenv("IA_CONV_TC"); mode = e ? atoi(e) : 32; }
         if (mode_few < 0) { const char* e = getenv("IA_CONV_TC_FEW"); mode_few = e ? atoi(e) : 32; }
+        static int mode_f16 = -1;   // IA_CONV_TC_F16: k-block of single-pass fp16 launches.  One operand tensor per side: a 64-channel
+                                    // k-block costs the shared memory of a 32-channel bf16 hi/lo one, and its 128-byte rows halve the
+                                    // number of TMA row requests per byte
+        if (mode_f16 < 0) { const char* e = getenv("IA_CONV_TC_F16"); mode_f16 = e ? atoi(e) : 64; }
         if (mode != 0 && p->GH * p->GW >= 128 && p->GW >= 8) {
-            const int bk = (p->ntaps <= 4) ? mode_few : mode;
+            int bk = (p->ntaps <= 4) ? mode_few : mode;
+            if (p->op_fmt == IA_OPFMT_F16X1) bk = mode_f16;
             return bk == 64 ? launch_v2<64>(&p, 1, stream) : launch_v2<32>(&p, 1, stream);
         }
     }
@@ -1469,5 +1474,8 @@ extern "C" int ia_conv_tc_phases(const ia_conv_params* p, int32_t n, void* strea
              "ia_conv_tc_phases: operands must be 16-byte aligned");
     const ia_conv_params* ps[4];
     for (int i = 0; i < n; ++i) ps[i] = &p[i];
+    static int ph_f16 = -1;     // IA_CONV_TC_F16_PHASES: k-block of single-pass fp16 merged-phase launches
+    if (ph_f16 < 0) { const char* e = getenv("IA_CONV_TC_F16_PHASES"); ph_f16 = e ? atoi(e) : 64; }
+    if (p->op_fmt == IA_OPFMT_F16X1 && ph_f16 == 64) return launch_v2<64>(ps, n, stream);
     return launch_v2<32>(ps, n, stream);
 }
