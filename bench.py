@@ -537,14 +537,16 @@ def run_c2(args, rank, world, local, dev):
             if rank == 0:
                 conv = rep.get('ia_conv_tc', {'ms': 0.0, 'launches': 0})
                 per_frame = conv_flops_per_frame(G)
-                flops = per_frame * B * args.steps
+                # numerator: the convolutions actually launched (runtime counter) -- the texture backbone's dead 256^2 block and dead
+                # skip images are not launched, so they are not counted either (the module-based figure below includes them)
+                flops = counted['algorithmic']
                 roofline = _roofline(conv['ms'], conv['launches'], flops, args.steps, {
                     # DRAM bytes of one launch from the committed `ncu --set full` capture (profiles/r1_conv_same_full_v7.txt): the
                     # 128->128 @512^2 layer at batch 8 reads 1.085 GB and writes 1.030 GB; its algorithmic bytes are the bf16 hi/lo
                     # operand in (1.074 GB) and the next layer's operand out (1.074 GB) -- no re-reads
                     'traffic': 2.115e9, 'traffic_launch': 'conv_tc2 128->128 @512x512, batch 8 (algorithmic 2.147e9 B)',
-                    'algorithmic_flops_per_frame': per_frame,
-                    'counted_flops_per_frame': counted['algorithmic'] / (B * args.steps),
+                    'algorithmic_flops_per_frame': counted['algorithmic'] / (B * args.steps),
+                    'reference_flops_per_frame_incl_dead_layers': per_frame,
                     'issued_mma_flops_per_frame': counted['issued_mma'] / (B * args.steps),
                     'issued_tflops': counted['issued_mma'] / (conv['ms'] * 1e-3) / 1e12 if conv['ms'] > 0 else 0.0,
                     'note': 'achieved/frac count algorithmic FLOPs (fp32 semantics); issued_* count the tensor-core MMAs really issued '

@@ -338,6 +338,10 @@ typedef struct {
      * render kernel.  Per call, so that the library keeps no mutable device state: concurrent renders on different streams
      * (two generators, a graph replay next to an eager call) cannot race. */
     void* scratch;
+    /* Decoder MLP arithmetic: IA_OPFMT_BF16X3-style 3-term split of fp16 hi/lo operands (0: reproduces the fp32 MLP to ~1e-6) or
+     * single-pass fp16 products (IA_OPFMT_F16X1 = 1: a third of the mma.sync work; moves the final image by ~1.2e-4,
+     * profiles/r1_render_precision_probe.json, r2_conv_precision_probe_mix_mlp.json).  fp32 accumulation in both. */
+    int32_t mlp_fmt;
 } ia_render_params;
 int64_t ia_render_scratch_bytes(void);
 /* near/far = mean_b ||c2w_b[:3,3]|| - 0.45 / + 0.6 (renderer.py:311-313), computed on device (no host sync). */

@@ -111,7 +111,7 @@ class RenderParams(C.Structure):
                 ('cam', c_f32p), ('cam_ld', C.c_int64), ('rays_o', c_f32p), ('rays_d', c_f32p), ('res', C.c_int32), ('Dc', C.c_int32), ('Df', C.c_int32),
                 ('jitter', c_f32p), ('u', c_f32p), ('box_warp', C.c_float), ('white_back', C.c_int32),
                 ('near_far', c_f32p), ('w1', c_f32p), ('b1', c_f32p), ('w2', c_f32p), ('b2', c_f32p),
-                ('feat', c_f32p), ('depth', c_f32p), ('wsum', c_f32p), ('depth_minmax', c_f32p), ('scratch', C.c_void_p)]
+                ('feat', c_f32p), ('depth', c_f32p), ('wsum', c_f32p), ('depth_minmax', c_f32p), ('scratch', C.c_void_p), ('mlp_fmt', C.c_int32)]
 
 
 class RasterLevelParams(C.Structure):

@@ -314,9 +314,9 @@ __global__ void __launch_bounds__(256, 3) fir_epilogue_kernel(ia_fir_params p, i
 // reads in flight per SM, about a third of what the HBM latency-bandwidth product asks for -- it ran at 3.3 TB/s, issue- and
 // latency-bound rather than bandwidth-bound (profiles/r1_fir_full_v3.txt).  Here a thread reads 5 neighbouring float4 per
 // raw row for 2 outputs (2.5 loads per output instead of 4) and prefetches two rows ahead (64 B unique per thread in flight).
-// NPF (opt-in, IA_FIR_NOISE_PREFETCH=1): the noise value of an output row is loaded one emission ahead instead of in the iteration
-// that consumes it (ncu: 34 % of this kernel's stall samples sit on that consumer, profiles/r1_fir_x2_full_v6.txt); same values,
-// same arithmetic.  Off by default until it has been run against the test-suite on hardware.
+// NPF (default; IA_FIR_NOISE_PREFETCH=0 disables): the noise value of an output row is loaded one emission ahead instead of in the
+// iteration that consumes it (ncu: 34 % of this kernel's stall samples sat on that consumer, profiles/r1_fir_x2_full_v6.txt); same
+// values, same arithmetic -- bit-identical on hardware (tests/test_gpu_regress.py), 1.62 -> 1.54 ms per step.
 template <int ACT, bool NPF>
 __global__ void __launch_bounds__(256, 2) fir_epilogue_x2_kernel(ia_fir_params p, int cg, int xt, int cchunks) {
     const int c4 = threadIdx.x % cg;
@@ -464,8 +464,8 @@ extern "C" int ia_fir_epilogue(const ia_fir_params* p, void* stream) {
                        out_pix * (p->emit.hi2 ? p->emit.c2_pad : 0) < (1ll << 31);
     if (x2 && (p->OW & 1) == 0 && small) {
         dim3 grid((unsigned)cdiv(p->OW / 2, xt), (unsigned)cdiv(p->OH, FIR_YT), (unsigned)(p->B * cchunks));
-        bool npf = false;
-        { const char* e = getenv("IA_FIR_NOISE_PREFETCH"); if (e && atoi(e) != 0) npf = true; }
+        bool npf = true;       // noise of the next output row loaded one emission ahead (bit-identical; IA_FIR_NOISE_PREFETCH=0: in the consuming iteration)
+        { const char* e = getenv("IA_FIR_NOISE_PREFETCH"); if (e && atoi(e) == 0) npf = false; }
         if (npf) {
             if (p->act == IA_ACT_LRELU) fir_epilogue_x2_kernel<IA_ACT_LRELU, true><<<grid, 256, 0, as_stream(stream)>>>(*p, cg, xt, cchunks);
             else if (p->act == IA_ACT_LINEAR) fir_epilogue_x2_kernel<IA_ACT_LINEAR, true><<<grid, 256, 0, as_stream(stream)>>>(*p, cg, xt, cchunks);

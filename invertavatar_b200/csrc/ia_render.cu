@@ -168,10 +168,10 @@ __device__ __forceinline__ void plane_gather8(const float* __restrict__ plane_ba
 // (mma.sync m16n8k16, fp16 hi/lo split operands, fp32 accumulate).  Lane (g = lane/4, t = lane%4) gathers 8 channels of
 // samples 16m+g and 16m+g+8 straight into its A fragment; layer 1's C fragments become layer 2's A fragments in
 // registers.  Colours go to col[sample][channel], sigma to sig[sample].
-// MLP1 (opt-in, IA_RENDER_MLP=fp16): both decoder layers as single-pass fp16 products (fp32 accumulate) instead of the 3-term
-// hi/lo split -- a third of the mma.sync and none of the lo-fragment arithmetic.  CPU probe with the oracle
+// MLP1 (ia_render_params.mlp_fmt = IA_OPFMT_F16X1): both decoder layers as single-pass fp16 products (fp32 accumulate) instead of
+// the 3-term hi/lo split -- a third of the mma.sync and none of the lo-fragment arithmetic.  CPU probe with the oracle
 // (tools/probe_render_precision.py): 1.2e-4 max-abs / 94 dB on the final image, inside the 1e-3 bar but outside the 2e-5 the
-// op-level renderer tests hold the feature image to; off by default, not yet run on hardware.
+// op-level renderer tests hold the feature image to: the generator asks for it (its measured budget), a bare renderer does not.
 template <bool MLP1>
 __device__ __forceinline__ void gather_mlp_pass(const ia_render_params& p, const float* __restrict__ planes_b, const Ray& r,
                                                 const float* dep, float* col, float* sig, int s0, int n, int lane,
@@ -605,8 +605,8 @@ extern "C" int ia_render(const ia_render_params* p, void* stream) {
     if (kWarpsPerCta > kMaxWarpsPerCta) kWarpsPerCta = kMaxWarpsPerCta;
     IA_CHECK(kWarpsPerCta >= 1, "ia_render: shared memory request too large");
     const size_t smem = sizeof(DecoderFrags) + per_warp * kWarpsPerCta * sizeof(float);
-    bool mlp1 = false;      // IA_RENDER_MLP=fp16: single-pass fp16 decoder (opt-in, see gather_mlp_pass)
-    { const char* ev = getenv("IA_RENDER_MLP"); if (ev && strcmp(ev, "fp16") == 0) mlp1 = true; }
+    IA_CHECK(p->mlp_fmt == IA_OPFMT_BF16X3 || p->mlp_fmt == IA_OPFMT_F16X1, "ia_render: unknown mlp_fmt %d", p->mlp_fmt);
+    const bool mlp1 = p->mlp_fmt == IA_OPFMT_F16X1;      // single-pass fp16 decoder (see gather_mlp_pass)
     e = mlp1 ? cudaFuncSetAttribute(render_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
              : cudaFuncSetAttribute(render_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     IA_CHECK(e == cudaSuccess, "ia_render: cudaFuncSetAttribute: %s", cudaGetErrorString(e));

@@ -95,6 +95,15 @@ class ImportanceRenderer_bsMotion(torch.nn.Module):
         self.depth_jitter = None     # [B, rays, Dc(,1)] U[0,1); consumed by the next forward
         self.importance_u = None     # [B*rays, Df] U[0,1); consumed by the next forward when evaluation=False
         self.fixed_jitter = None     # [B, rays, Dc] used by every forward while set (depth_jitter takes precedence)
+        # decoder MLP arithmetic (ia_render_params.mlp_fmt): 3-term split by default (the op-level API reproduces the fp32 MLP);
+        # TriPlaneGenerator sets rt.FMT_F16X1 from its measured error budget, IA_CONV_PRECISION=bf16x3 overrides it (strict mode)
+        self.mlp_fmt = rt.FMT_BF16X3
+
+    def _mlp_fmt(self):
+        import os
+        if os.environ.get('IA_CONV_PRECISION', 'auto') == 'bf16x3':
+            return rt.FMT_BF16X3
+        return int(getattr(self, 'mlp_fmt', rt.FMT_BF16X3))
 
     def _draws(self, B, rays, Dc, Df, evaluation, device):
         jit, u = self.depth_jitter, self.importance_u
@@ -121,7 +130,7 @@ class ImportanceRenderer_bsMotion(torch.nn.Module):
         jit, u = self._draws(B, res * res, Dc, Df, evaluation, planes_nhwc.device)
         w1, b1, w2, b2 = _decoder_weights(decoder)
         return rt.render(planes_nhwc, cam, res, Dc, Df, jit, u, float(options['box_warp']), bool(options.get('white_back', False)),
-                         w1, b1, w2, b2)
+                         w1, b1, w2, b2, mlp_fmt=self._mlp_fmt())
 
     def forward(self, planes, decoder, ray_origins, ray_directions, rendering_options, evaluation=False):
         """Reference signature: planes [B,3,32,H,W], rays [B,M,3] -> (rgb [B,M,32], depth [B,M,1], weights.sum [B,M,1])."""
@@ -136,7 +145,7 @@ class ImportanceRenderer_bsMotion(torch.nn.Module):
         w1, b1, w2, b2 = _decoder_weights(decoder)
         feat, depth, wsum = rt.render(planes_nhwc, None, res, Dc, Df, jit, u, float(rendering_options['box_warp']),
                                       bool(rendering_options.get('white_back', False)), w1, b1, w2, b2,
-                                      rays=(ray_origins, ray_directions))
+                                      rays=(ray_origins, ray_directions), mlp_fmt=self._mlp_fmt())
         return feat.reshape(B, M, 32), depth.reshape(B, M, 1), wsum.reshape(B, M, 1)
 
 

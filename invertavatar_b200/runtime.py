@@ -967,7 +967,7 @@ def ray_sampler(cam, res):
     return o, d
 
 
-def render(planes_nhwc, cam, res, Dc, Df, jitter, u, box_warp, white_back, w1, b1, w2, b2, rays=None):
+def render(planes_nhwc, cam, res, Dc, Df, jitter, u, box_warp, white_back, w1, b1, w2, b2, rays=None, mlp_fmt=0):
     """planes [B,PH,PW,>=96] NHWC fp32 (plane p = channels 32p..32p+31); cam [B,>=25] (or rays=(origins, dirs)
     [B,res*res,3] with cam=None); returns feat [B,res,res,32], depth [B,res,res] (clamped), wsum [B,res,res]."""
     st = _enter(planes_nhwc)
@@ -1000,7 +1000,7 @@ def render(planes_nhwc, cam, res, Dc, Df, jitter, u, box_warp, white_back, w1, b
     w1, b1, w2, b2 = _f32c(w1), _f32c(b1), _f32c(w2), _f32c(b2)
     p = _C.RenderParams(_p(planes_nhwc), PC, B, PH, PW, _p(cam), (cam.stride(0) if cam is not None else 0), _p(rays_o), _p(rays_d), res, Dc, Df, _p(jitter), _p(u),
                         float(box_warp), 1 if white_back else 0, _p(near_far), _p(w1), _p(b1), _p(w2), _p(b2),
-                        _p(feat), _p(depth), _p(wsum), _p(mm), _p(scratch))
+                        _p(feat), _p(depth), _p(wsum), _p(mm), _p(scratch), int(mlp_fmt))
     _C.check(_C.lib().ia_render(C.byref(p), st), 'ia_render')
     _C.check(_C.lib().ia_depth_clamp(_p(depth), depth.numel(), _p(mm), st), 'ia_depth_clamp')
     return feat, depth, wsum

@@ -379,10 +379,11 @@ class SynthesisBlock(torch.nn.Module):
         return out
 
     def run_chain(self, a_in, img, styles, dcoefs, B, noise_mode='const', condition=None, want_x32=False, next_conv=None,
-                  next_styles=None, img_nchw=False, gain=1):
+                  next_styles=None, img_nchw=False, gain=1, skip_rgb=False):
         """Fused block: every convolution epilogue writes the operand(s) of its consumer(s) directly.
         a_in: rt.Split for conv0 (None for the const block); styles/dcoefs: this block's entries in layers() order;
         next_conv/next_styles: the following block's conv0 and its styles (None -> no operand emitted for it).
+        skip_rgb: this block's image (ToRGB + skip-connection up-sampling) has no consumer -- not computed, img comes back None.
         Returns (x32 or None, img, a_next or None)."""
         dev = styles[0].device
         R = self.resolution
@@ -402,7 +403,9 @@ class SynthesisBlock(torch.nn.Module):
                 hi, lo = rt.modsplit(x, styles[1], C_pad=self.conv1.pack().Cin_pad, fmt=self.conv1.fmt())
                 a1 = rt.Split(hi, lo)
             i = 1
-        has_rgb = hasattr(self, 'torgb')
+        has_rgb = hasattr(self, 'torgb') and not skip_rgb
+        if skip_rgb:
+            img = None
         # ToRGB with few image channels (the super-resolution blocks: 3) is contracted inside conv1's epilogue: no ToRGB operand is
         # written and re-read, no 1x1 convolution launch
         fuse_rgb = (has_rgb and not want_x32 and self.torgb.weight.shape[2] == 1 and
@@ -484,8 +487,14 @@ class SynthesisNetwork(torch.nn.Module):
     def forward(self, ws, cond_list=None, return_list=False, feat_conditions=None, return_imgs=False, out_res=(32, 256),
                 **block_kwargs):
         """cond_list / return_list / feat_conditions semantics of networks_stylegan2_new.py:509-548.  (The stock
-        training/networks_stylegan2.SynthesisNetwork.forward(ws, **kw) is the cond_list=None, return_list=False case.)"""
+        training/networks_stylegan2.SynthesisNetwork.forward(ws, **kw) is the cond_list=None, return_list=False case.)
+        Engine-internal kwarg ``prune_after=res`` (return_list only): the caller reads nothing above the features of block
+        ``res`` -- the list then ends with that block's x ([img_start, x_start, ..., x_res]); the blocks above it and the
+        skip-connection images after the first one are dead code and are not evaluated (the surviving entries are bit-identical
+        to the unpruned call's)."""
         assert not (return_list and return_imgs)
+        prune_after = block_kwargs.pop('prune_after', None)
+        assert prune_after is None or (return_list and cond_list is None), "prune_after applies to plain return_list calls"
         assert ws.shape[1] == self.num_ws and ws.shape[2] == self.w_dim, (ws.shape, self.num_ws)
         noise_mode = block_kwargs.get('noise_mode', 'random')
         ws = ws.to(torch.float32)
@@ -511,6 +520,11 @@ class SynthesisNetwork(torch.nn.Module):
             has_next = index + 1 < len(blocks)
             next_conv = blocks[index + 1].conv0 if (has_next and not blend_next) else None
             next_styles = styles[spans[index + 1][0]] if next_conv is not None else None
+            if prune_after is not None and res > prune_after:
+                break                                     # nothing above this block is read by the caller
+            dead_img = prune_after is not None and index > start_layer     # images after the first exported one feed only later images
+            if prune_after is not None and res == prune_after:
+                next_conv = next_styles = None
             if prefix is not None and index < prefix['index']:
                 continue                                  # evaluated by the grouped prefix
             if prefix is not None and index == prefix['index']:
@@ -518,7 +532,7 @@ class SynthesisNetwork(torch.nn.Module):
                 x32, img, a = prefix['x32'], prefix['img'], prefix['a_next']
             else:
                 x32, img, a = block.run_chain(a, img, styles[lo_i:hi_i], dcoefs[lo_i:hi_i], B, noise_mode=noise_mode, condition=cond_feat,
-                                              want_x32=want_x32, next_conv=next_conv, next_styles=next_styles)
+                                              want_x32=want_x32, next_conv=next_conv, next_styles=next_styles, skip_rgb=dead_img)
             if emitting:
                 if return_list:
                     if index == start_layer:
@@ -538,7 +552,8 @@ class SynthesisNetwork(torch.nn.Module):
                         a = rt.modsplit_split(x32, styles[spans[index + 1][0]], cond=cnd, cond_alpha=cal, C_pad=nxt.pack().Cin_pad,
                                               pad_row=nxt.up == 2 and rt.pad_row_wanted(x32.shape[1], x32.shape[2]), fmt=nxt.fmt())
         if return_list:
-            x_list.append(rt.from_nhwc(img))
+            if prune_after is None:
+                x_list.append(rt.from_nhwc(img))
             return x_list
         if return_imgs:
             return out_imgs

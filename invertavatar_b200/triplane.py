@@ -29,6 +29,11 @@ def _grouped_prefix_enabled():
     return os.environ.get('IA_GROUPED_PREFIX', '1') != '0'
 
 
+def _prune_dead_enabled():
+    import os
+    return os.environ.get('IA_PRUNE_DEAD', '1') != '0'
+
+
 _backbone_streams = None
 
 
@@ -110,6 +115,9 @@ class TriPlaneGenerator(torch.nn.Module):
             for m in net.synthesis.modules():
                 if isinstance(m, sg.SynthesisLayer):
                     m.tc_fmt = rt.FMT_F16X1
+        # the renderer's decoder MLP as single-pass fp16 mma.sync as well: +1.2e-4 on the final image on its own, 1.2e-4 .. 3.6e-4
+        # (PSNR 86 .. 95 dB) together with the backbone layers (profiles/r2_conv_precision_probe_mix_mlp.json)
+        self.renderer.mlp_fmt = rt.FMT_F16X1
 
     def _side_streams(self, device):
         return rt.side_streams(device)
@@ -205,7 +213,7 @@ class TriPlaneGenerator(torch.nn.Module):
         N = ws.shape[0]
         tex = [rt.to_nhwc(t) for t in texture_feats]
         static_views, plane_img = self._static_views(static_feats)
-        assert len(static_views) == len(tex)
+        assert len(tex) >= 4 and len(static_views) >= 4     # (a pruned texture list ends with the last level the rasterizer reads)
         assert plane_img.shape[-1] == 96, 'static backbone must emit 3 x 32 plane channels'
 
         # UV rasterize: only the four levels the face backbone consumes (cond_list[0..3], networks_stylegan2_new.py:536-540)
@@ -250,6 +258,13 @@ class TriPlaneGenerator(torch.nn.Module):
         # The blocks up to 32^2 of the three backbones do not depend on each other (the face backbone receives its
         # conditions after its own 32^2 block) and are latency-bound: evaluate them as one grouped batch.
         nets = [self.texture_backbone.synthesis, self.backbone.synthesis, self.face_backbone.synthesis]
+        # Dead-code elimination in the texture backbone: of its return_list [img32, x32, x64, x128, x256, img256] the rasterizer
+        # reads the first four (cond_list of the face backbone, networks_stylegan2_new.py:536-540); the 256^2 block and the
+        # skip-connection images after img32 feed nothing unless the caller asked for the feature maps (return_featmap).  The
+        # reference evaluates them and drops them; here they are not launched (IA_PRUNE_DEAD=0 evaluates them anyway).
+        tex_kwargs = dict(noise_kwargs)
+        if not return_featmap and _prune_dead_enabled():
+            tex_kwargs['prune_after'] = 128
         pre = [None, None, None]
         if _grouped_prefix_enabled() and sg.can_group_prefix(nets):
             pre = sg.synthesis_prefix_grouped(nets, ws, noise_mode=noise_kwargs.get('noise_mode', 'random'))
@@ -267,7 +282,7 @@ class TriPlaneGenerator(torch.nn.Module):
             with torch.cuda.stream(s_c):
                 uv_prep = self._uv_prep(mesh_condition['uvcoords_image'], (32, 64, 128), want_alpha128=True)   # levels 0..3 of the texture list
             with torch.cuda.stream(s_a):
-                texture_feats = self.texture_backbone.synthesis(ws, cond_list=None, return_list=True, prefix=pre[0], **noise_kwargs)
+                texture_feats = self.texture_backbone.synthesis(ws, cond_list=None, return_list=True, prefix=pre[0], **tex_kwargs)
             with torch.cuda.stream(s_b):
                 static_feats = self.backbone.synthesis(ws, cond_list=None, return_list=True, prefix=pre[1], **noise_kwargs)
             cur.wait_stream(s_a)
@@ -277,7 +292,7 @@ class TriPlaneGenerator(torch.nn.Module):
                 t.record_stream(cur)
         else:
             uv_prep = None
-            texture_feats = self.texture_backbone.synthesis(ws, cond_list=None, return_list=True, prefix=pre[0], **noise_kwargs)
+            texture_feats = self.texture_backbone.synthesis(ws, cond_list=None, return_list=True, prefix=pre[0], **tex_kwargs)
             static_feats = self.backbone.synthesis(ws, cond_list=None, return_list=True, prefix=pre[1], **noise_kwargs)
         out = self._stitch_render_sr(ws, c, mesh_condition, texture_feats, static_feats, neural_rendering_resolution,
                                      evaluation, synthesis_kwargs, face_prefix=pre[2], uv_prep=uv_prep)

@@ -120,20 +120,48 @@ def test_prepack_builds_every_pack_once():
             assert m.__dict__['_ia_pack'] is packs[id(m)]
 
 
-@pytest.mark.skipif(not os.environ.get('IA_TEST_OPTIN'), reason='opt-in code path (IA_RENDER_MLP=fp16), not yet validated on hardware')
 def test_single_pass_decoder_within_north_star(monkeypatch):
-    """IA_RENDER_MLP=fp16 (decoder MLP as single-pass fp16 MMAs): the final image stays within the north-star tolerance of the default
-    3-term path (CPU probe: 1.2e-4 max-abs, tools/probe_render_precision.py)."""
+    """Decoder MLP as single-pass fp16 MMAs (the generator's default) against the 3-term path (strict mode): the final image stays
+    well inside the north-star tolerance (CPU probe: 1.2e-4 max-abs, tools/probe_render_precision.py)."""
     import copy
+    from invertavatar_b200 import runtime as rt
     G = copy.deepcopy(build_generator(16, 16)).to('cuda')
     z, cond, c, uv = synth.latents(2).cuda(), synth.frontal_camera(2).cuda(), synth.cameras(2).cuda(), synth.uvcoords_image(2).cuda()
     jit = synth.depth_jitter(2, 64 * 64, 16).cuda()
     outs = {}
+    for m in G.modules():                                     # isolate the decoder: convolutions 3-term in both runs
+        if hasattr(m, 'tc_fmt'):
+            m.tc_fmt = rt.FMT_BF16X3
     with torch.no_grad():
         ws = G.mapping(z, cond, truncation_psi=0.7, truncation_cutoff=14)
         for mode in ('fp32x3', 'fp16'):
-            monkeypatch.setenv('IA_RENDER_MLP', mode)
+            G.renderer.mlp_fmt = rt.FMT_F16X1 if mode == 'fp16' else rt.FMT_BF16X3
             outs[mode] = G.synthesis(ws, c, {'uvcoords_image': uv}, neural_rendering_resolution=64, noise_mode='const', evaluation=True,
                                      depth_jitter=jit)['image'].clone()
     err = float((outs['fp16'] - outs['fp32x3']).abs().max())
     assert 0 < err <= 5e-4, err
+
+
+def test_dead_code_elimination_is_bit_identical(monkeypatch):
+    """TriPlaneGenerator.synthesis does not launch the texture backbone's 256^2 block nor its skip images after img32 (nothing
+    reads them unless return_featmap): the outputs are bit-identical to the full evaluation, with fewer launches."""
+    import copy
+    from invertavatar_b200 import runtime as rt
+    G = copy.deepcopy(build_generator(16, 16)).to('cuda')
+    z, cond, c, uv = synth.latents(2).cuda(), synth.frontal_camera(2).cuda(), synth.cameras(2).cuda(), synth.uvcoords_image(2).cuda()
+    jit = synth.depth_jitter(2, 64 * 64, 16).cuda()
+    outs, launches = {}, {}
+    with torch.no_grad():
+        ws = G.mapping(z, cond, truncation_psi=0.7, truncation_cutoff=14)
+        for flag in ('0', '1'):
+            monkeypatch.setenv('IA_PRUNE_DEAD', flag)
+            rt.reset_launch_count()
+            outs[flag] = G.synthesis(ws, c, {'uvcoords_image': uv}, neural_rendering_resolution=64, noise_mode='const', evaluation=True,
+                                     depth_jitter=jit.clone())
+            launches[flag] = rt.launch_count()
+        full = G.synthesis(ws, c, {'uvcoords_image': uv}, neural_rendering_resolution=64, noise_mode='const', evaluation=True,
+                           depth_jitter=jit.clone(), return_featmap=True)
+    for k in ('image', 'image_raw', 'image_depth'):
+        assert torch.equal(outs['0'][k], outs['1'][k]), k
+        assert torch.equal(full[k], outs['1'][k]), k
+    assert len(full['texture']) == 6 and launches['1'] < launches['0']

@@ -33,6 +33,7 @@ ap.add_argument('--depth', type=int, default=48)
 ap.add_argument('--frames', type=int, default=3)
 ap.add_argument('--budget', type=float, default=5e-4)
 ap.add_argument('--modes', default='f16x1,f16a,f16w')
+ap.add_argument('--mlp-fp16', action='store_true', help='also evaluate the renderer decoder MLP as single-pass fp16 products (IA_RENDER_MLP=fp16)')
 ap.add_argument('--eval-mix', default='', help="skip the search: evaluate a preset ('backbones_f16x1') on --frames frames, with bf16x3 arithmetic elsewhere")
 args = ap.parse_args()
 torch.set_num_threads(os.cpu_count() or 1)
@@ -128,6 +129,23 @@ print(f'{len(layers)} conv layers, {total_gflop:.1f} GFLOP/frame, reference rend
 
 if args.eval_mix:
     assert args.eval_mix == 'backbones_f16x1'
+    if args.mlp_fp16:
+        import math
+        import torch.nn.functional as F
+        from oracle import renderer as o_r
+
+        def fc16(x, weight, bias):
+            w = (weight * (1.0 / math.sqrt(weight.shape[1]))).half().float()
+            return torch.addmm(bias.unsqueeze(0), x.half().float(), w.t())
+
+        def dec_single(sdd, feats):
+            x = feats.mean(1)
+            N, M, C = x.shape
+            x = fc16(x.reshape(N * M, C), sdd['net.0.weight'], sdd['net.0.bias'])
+            x = fc16(F.softplus(x), sdd['net.2.weight'], sdd['net.2.bias']).reshape(N, M, -1)
+            return torch.sigmoid(x[..., 1:]) * (1 + 2 * 0.001) - 0.001, x[..., 0:1]
+        refs = [render(f) for f in range(args.frames)]      # (references were rendered above with the exact decoder)
+        o_r.osg_decoder = dec_single
     mix = {L['idx']: 'f16x1' for L in layers if not L['name'].startswith('sr.')}
     full = {L['idx']: mix.get(L['idx'], 'bf16x3') for L in layers}
     res = []
