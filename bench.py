@@ -334,15 +334,20 @@ class _Harness:
         depth, marks = 2, []
         for _ in range(steps):
             if len(marks) >= depth:
-                marks.pop(0).synchronize()
+                marks[len(marks) - depth].synchronize()
             fn()
-            ev = torch.cuda.Event()
+            ev = torch.cuda.Event(enable_timing=True)
             ev.record()
             marks.append(ev)
         torch.cuda.current_stream().wait_stream(self.copy_stream)   # the last read-back belongs to the timed region
         e1.record()
         self.barrier()
         ms = e0.elapsed_time(e1)
+        prev, per_step = e0, []
+        for ev in marks:                       # per-step device time (diagnostic: a stall shows up as one long step)
+            per_step.append(prev.elapsed_time(ev))
+            prev = ev
+        self.last_step_ms = per_step
         if self.world > 1:
             t = torch.tensor([ms], device=self.dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -513,10 +518,12 @@ def run_c2(args, rank, world, local, dev):
         clocks.rows.clear()     # keep only the samples taken from here on: both timed regions (resident + end-to-end)
         rt.reset_launch_count()
         ms = h.timed(step_resident, args.steps)
+        step_ms = sorted(h.last_step_ms)
         launches = rt.launch_count()
         for _ in range(2):
             step_e2e()
         ms_e2e = h.timed(step_e2e, args.steps)
+        step_ms_e2e = sorted(h.last_step_ms)
         clk = clocks.stop() if rank == 0 else None
 
         roofline = breakdown = None
@@ -580,7 +587,9 @@ def run_c2(args, rank, world, local, dev):
             'data': 'synthetic', 'config': workload_config(args, world), 'clocks': clk,
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'ms_per_step': ms_e2e / args.steps,
                     'readback': 'fp32 NCHW images' if args.e2e_f32 else 'uint8 HWC frames (layout_grid, reenact_avatar_next3d.py:117-131)'},
-            'gpu_launches': launches}
+            'gpu_launches': launches,
+            'step_ms': {'median': step_ms[len(step_ms) // 2], 'min': step_ms[0], 'max': step_ms[-1],
+                        'e2e_median': step_ms_e2e[len(step_ms_e2e) // 2], 'e2e_max': step_ms_e2e[-1]}}
     if roofline is not None:
         line['roofline'] = roofline
         line['kernel_breakdown'] = breakdown

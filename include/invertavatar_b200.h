@@ -316,6 +316,16 @@ typedef struct {
 } ia_raster_level_params;
 int ia_raster_level(const ia_raster_level_params* p, void* stream);
 
+/* Plane stitch (triplane_v20.py:119-128) in one pass: out = planes, except channels [0,32) (plane 0) inside the window
+ * rows [y0,y0+wh) x cols [x0,x0+ww), which become stitch*alpha + planes*(1-alpha); out is fp32 or fp16 (out_fmt as
+ * ia_render_params.planes_fmt).  planes [B][H][W][C] fp32 NHWC (pixel stride planes_ld), stitch [B][wh][ww][32], alpha [B][wh][ww]. */
+typedef struct {
+    const float* planes; int64_t planes_ld; int32_t B, H, W, C;
+    const float* stitch; const float* alpha; int32_t y0, x0, wh, ww;
+    void* out; int32_t out_fmt;
+} ia_stitch_params;
+int ia_stitch_planes(const ia_stitch_params* p, void* stream);
+
 /* ---- volume renderer (renderer.py:309-469, ray_sampler.py:70-107, ray_marcher.py:25-57, triplane_v20.py:415-438) */
 typedef struct {
     const float* planes; int64_t plane_px_ld;    /* [B][PH][PW][>=96]: plane p = channels [32p, 32p+32) */
@@ -342,6 +352,10 @@ typedef struct {
      * single-pass fp16 products (IA_OPFMT_F16X1 = 1: a third of the mma.sync work; moves the final image by ~1.2e-4,
      * profiles/r1_render_precision_probe.json, r2_conv_precision_probe_mix_mlp.json).  fp32 accumulation in both. */
     int32_t mlp_fmt;
+    /* Storage type of `planes`: 0 = fp32 (as declared), IA_OPFMT_F16X1 = fp16 (the pointer is then a __half*; plane_px_ld stays
+     * in elements, a multiple of 8).  Halves the gather traffic -- the kernel's bound: 1536 B of L2 reads per sample in fp32 --
+     * at 9.4e-6 on the final image; interpolation arithmetic is fp32 either way.  ia_stitch_planes produces such planes. */
+    int32_t planes_fmt;
 } ia_render_params;
 int64_t ia_render_scratch_bytes(void);
 /* near/far = mean_b ||c2w_b[:3,3]|| - 0.45 / + 0.6 (renderer.py:311-313), computed on device (no host sync). */

@@ -111,7 +111,13 @@ class RenderParams(C.Structure):
                 ('cam', c_f32p), ('cam_ld', C.c_int64), ('rays_o', c_f32p), ('rays_d', c_f32p), ('res', C.c_int32), ('Dc', C.c_int32), ('Df', C.c_int32),
                 ('jitter', c_f32p), ('u', c_f32p), ('box_warp', C.c_float), ('white_back', C.c_int32),
                 ('near_far', c_f32p), ('w1', c_f32p), ('b1', c_f32p), ('w2', c_f32p), ('b2', c_f32p),
-                ('feat', c_f32p), ('depth', c_f32p), ('wsum', c_f32p), ('depth_minmax', c_f32p), ('scratch', C.c_void_p), ('mlp_fmt', C.c_int32)]
+                ('feat', c_f32p), ('depth', c_f32p), ('wsum', c_f32p), ('depth_minmax', c_f32p), ('scratch', C.c_void_p), ('mlp_fmt', C.c_int32), ('planes_fmt', C.c_int32)]
+
+
+class StitchParams(C.Structure):
+    _fields_ = [('planes', c_f32p), ('planes_ld', C.c_int64), ('B', C.c_int32), ('H', C.c_int32), ('W', C.c_int32), ('C', C.c_int32),
+                ('stitch', c_f32p), ('alpha', c_f32p), ('y0', C.c_int32), ('x0', C.c_int32), ('wh', C.c_int32), ('ww', C.c_int32),
+                ('out', C.c_void_p), ('out_fmt', C.c_int32)]
 
 
 class RasterLevelParams(C.Structure):
@@ -184,6 +190,7 @@ SIGNATURES = {
     'ia_ray_bounds_from_origins': (C.c_int, [c_f32p, C.c_int64, c_f32p, C.c_void_p]),
     'ia_render': (C.c_int, [C.POINTER(RenderParams), C.c_void_p]),
     'ia_render_scratch_bytes': (C.c_int64, []),
+    'ia_stitch_planes': (C.c_int, [C.POINTER(StitchParams), C.c_void_p]),
     'ia_depth_clamp': (C.c_int, [c_f32p, C.c_int64, c_f32p, C.c_void_p]),
     'ia_ray_sampler': (C.c_int, [c_f32p, C.c_int64, C.c_int32, C.c_int32, c_f32p, c_f32p, C.c_void_p]),
     'ia_enc_chan_stats': (C.c_int, [C.POINTER(View), C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),

@@ -406,3 +406,53 @@ extern "C" int ia_raster_level(const ia_raster_level_params* p, void* stream) {
     IA_LAUNCH_CHECK("ia_raster_level(vpass)");
     return 0;
 }
+
+
+// ------------------------------------------------------------------------------------------------
+// plane stitch (triplane_v20.py:119-128): copy of the static planes with the face-backbone output blended into plane 0
+// inside the face window, written once in the renderer's storage format
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) stitch_planes_kernel(ia_stitch_params p) {
+    const int groups = p.C >> 2;
+    const int64_t total = (int64_t)p.B * p.H * p.W * groups;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)(i % groups) * 4;
+    int64_t t = i / groups;
+    const int x = (int)(t % p.W); t /= p.W;
+    const int y = (int)(t % p.H); const int b = (int)(t / p.H);
+    const int64_t pix = ((int64_t)b * p.H + y) * p.W + x;
+    float4 v = __ldg(reinterpret_cast<const float4*>(p.planes + pix * p.planes_ld + c));
+    const int wy = y - p.y0, wx = x - p.x0;
+    if (c < 32 && wy >= 0 && wy < p.wh && wx >= 0 && wx < p.ww) {
+        const int64_t wp = ((int64_t)b * p.wh + wy) * p.ww + wx;
+        const float a = p.alpha[wp];
+        const float4 s = __ldg(reinterpret_cast<const float4*>(p.stitch + wp * 32 + c));
+        // a*alpha + b*(1-alpha), the arithmetic of ia_lerp_alpha
+        v.x = s.x * a + v.x * (1.f - a); v.y = s.y * a + v.y * (1.f - a);
+        v.z = s.z * a + v.z * (1.f - a); v.w = s.w * a + v.w * (1.f - a);
+    }
+    if (p.out_fmt == IA_OPFMT_F16X1) {
+        const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+        uint2 o;
+        o.x = *reinterpret_cast<const uint32_t*>(&h0); o.y = *reinterpret_cast<const uint32_t*>(&h1);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out) + pix * p.C + c) = o;
+    } else {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.C + c) = v;
+    }
+}
+
+extern "C" int ia_stitch_planes(const ia_stitch_params* p, void* stream) {
+    IA_CHECK(p && p->planes && p->stitch && p->alpha && p->out, "ia_stitch_planes: null tensor");
+    IA_CHECK(p->C >= 32 && (p->C & 7) == 0 && (p->planes_ld & 3) == 0, "ia_stitch_planes: C must be a multiple of 8 (>= 32), fp32 pixel stride a multiple of 4");
+    IA_CHECK(p->y0 >= 0 && p->x0 >= 0 && p->y0 + p->wh <= p->H && p->x0 + p->ww <= p->W, "ia_stitch_planes: window outside the planes");
+    IA_CHECK(p->out_fmt == IA_OPFMT_BF16X3 || p->out_fmt == IA_OPFMT_F16X1, "ia_stitch_planes: out_fmt must be 0 (fp32) or IA_OPFMT_F16X1");
+    IA_CHECK((reinterpret_cast<uintptr_t>(p->planes) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->stitch) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->out) & 15) == 0,
+             "ia_stitch_planes: tensors must be 16-byte aligned");
+    const int64_t total = (int64_t)p->B * p->H * p->W * (p->C >> 2);
+    if (total == 0) return 0;
+    ia::prof_begin("ia_stitch_planes", as_stream(stream));
+    stitch_planes_kernel<<<(unsigned)cdiv(total, 256), 256, 0, as_stream(stream)>>>(*p);
+    IA_LAUNCH_CHECK("ia_stitch_planes");
+    return 0;
+}

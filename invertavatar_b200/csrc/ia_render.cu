@@ -46,13 +46,18 @@ __device__ __forceinline__ void split_half(float v, __half& hi, __half& lo) {
     hi = __float2half_rn(v);
     lo = __float2half_rn(v - __half2float(hi));
 }
-__device__ __forceinline__ int phys_channel(int k) {   // logical layer-1 k index -> physical feature channel
+// logical layer-1 k index -> physical feature channel.  fp32 planes: lane quad member t gathers channels 4t..4t+3 (k-step 0) and
+// 16+4t..16+4t+3 (k-step 1) -- two 16-byte loads per texel; fp16 planes (H16): channels 8t..8t+7 -- ONE 16-byte load per texel,
+// of which 8t..8t+3 feed k-step 0 and 8t+4..8t+7 feed k-step 1.
+__device__ __forceinline__ int phys_channel(int k, bool h16) {
     const int ks = k >> 4, r = k & 15;
-    return (r < 8) ? 16 * ks + 4 * (r >> 1) + (r & 1) : 16 * ks + 4 * ((r - 8) >> 1) + 2 + ((r - 8) & 1);
+    const int t = (r < 8) ? (r >> 1) : ((r - 8) >> 1);
+    const int q = (r < 8) ? (r & 1) : 2 + ((r - 8) & 1);
+    return h16 ? 8 * t + 4 * ks + q : 16 * ks + 4 * t + q;
 }
 
 __global__ void decoder_stage_kernel(const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
-                                     const float* __restrict__ b2, DecoderFrags* __restrict__ out) {
+                                     const float* __restrict__ b2, DecoderFrags* __restrict__ out, int h16) {
     DecoderFrags& g_dec = *out;
     const float g1 = 1.0f / sqrtf((float)kFeat), g2 = 1.0f / sqrtf((float)kHidden);
     // layer 1: B[k][n] = W1[n][phys(k)] * g1
@@ -62,7 +67,7 @@ __global__ void decoder_stage_kernel(const float* __restrict__ w1, const float* 
         float v[4];
         const int kk[4] = {16 * ks + 2 * t, 16 * ks + 2 * t + 1, 16 * ks + 2 * t + 8, 16 * ks + 2 * t + 9};
         __half h[4], l[4];
-        for (int q = 0; q < 4; ++q) { v[q] = w1[n * kFeat + phys_channel(kk[q])] * g1; split_half(v[q], h[q], l[q]); }
+        for (int q = 0; q < 4; ++q) { v[q] = w1[n * kFeat + phys_channel(kk[q], h16 != 0)] * g1; split_half(v[q], h[q], l[q]); }
         g_dec.w1f[((nt * 2 + ks) * 2 + 0) * 32 + lane] = make_uint2(pack_half2(h[0], h[1]), pack_half2(h[2], h[3]));
         g_dec.w1f[((nt * 2 + ks) * 2 + 1) * 32 + lane] = make_uint2(pack_half2(l[0], l[1]), pack_half2(l[2], l[3]));
     }
@@ -164,6 +169,48 @@ __device__ __forceinline__ void plane_gather8(const float* __restrict__ plane_ba
     for (int k = 0; k < 8; ++k) acc[k] += s[k];
 }
 
+// fp16 planes: this lane's 8 channels 8t..8t+7 of a texel are one 16-byte load; arithmetic stays fp32 (only the storage is
+// rounded: 9.4e-6 on the final image, profiles/r1_render_precision_probe.json).  Same zero-padding scheme as above.
+__device__ __forceinline__ void plane_gather8_h(const __half* __restrict__ plane_base, int64_t px_ld, int PH, int PW, float gx, float gy,
+                                                float acc[8]) {
+    const float ix = ((gx + 1.f) * PW - 1.f) / 2.f;
+    const float iy = ((gy + 1.f) * PH - 1.f) / 2.f;
+    const float fx = floorf(ix), fy = floorf(iy);
+    const int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;
+    const float wnw = ((float)x1 - ix) * ((float)y1 - iy);
+    const float wne = (ix - (float)x0) * ((float)y1 - iy);
+    const float wsw = ((float)x1 - ix) * (iy - (float)y0);
+    const float wse = (ix - (float)x0) * (iy - (float)y0);
+    const bool vx0 = x0 >= 0 && x0 < PW, vx1 = x1 >= 0 && x1 < PW, vy0 = y0 >= 0 && y0 < PH, vy1 = y1 >= 0 && y1 < PH;
+    const int x0c = min(max(x0, 0), PW - 1), x1c = min(max(x1, 0), PW - 1);
+    const int y0c = min(max(y0, 0), PH - 1), y1c = min(max(y1, 0), PH - 1);
+    const float w00 = (vy0 && vx0) ? wnw : 0.f, w01 = (vy0 && vx1) ? wne : 0.f;
+    const float w10 = (vy1 && vx0) ? wsw : 0.f, w11 = (vy1 && vx1) ? wse : 0.f;
+    const __half* r0 = plane_base + (int64_t)(y0c * PW) * px_ld;
+    const __half* r1 = plane_base + (int64_t)(y1c * PW) * px_ld;
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(r0 + (int64_t)x0c * px_ld));
+    const uint4 b = __ldg(reinterpret_cast<const uint4*>(r0 + (int64_t)x1c * px_ld));
+    const uint4 c = __ldg(reinterpret_cast<const uint4*>(r1 + (int64_t)x0c * px_ld));
+    const uint4 d = __ldg(reinterpret_cast<const uint4*>(r1 + (int64_t)x1c * px_ld));
+    float s[8];
+    auto tap = [&](const uint4& v, float w, bool first) {
+        const float2 p0 = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
+        const float2 p1 = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+        const float2 p2 = __half22float2(*reinterpret_cast<const __half2*>(&v.z));
+        const float2 p3 = __half22float2(*reinterpret_cast<const __half2*>(&v.w));
+        if (first) {
+            s[0] = p0.x * w; s[1] = p0.y * w; s[2] = p1.x * w; s[3] = p1.y * w;
+            s[4] = p2.x * w; s[5] = p2.y * w; s[6] = p3.x * w; s[7] = p3.y * w;
+        } else {
+            s[0] += p0.x * w; s[1] += p0.y * w; s[2] += p1.x * w; s[3] += p1.y * w;
+            s[4] += p2.x * w; s[5] += p2.y * w; s[6] += p3.x * w; s[7] += p3.y * w;
+        }
+    };
+    tap(a, w00, true); tap(b, w01, false); tap(c, w10, false); tap(d, w11, false);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] += s[k];
+}
+
 // Tri-plane gather + OSG decoder for samples [s0, s0+n) of this warp's ray, 16 samples per step on the tensor cores
 // (mma.sync m16n8k16, fp16 hi/lo split operands, fp32 accumulate).  Lane (g = lane/4, t = lane%4) gathers 8 channels of
 // samples 16m+g and 16m+g+8 straight into its A fragment; layer 1's C fragments become layer 2's A fragments in
@@ -172,13 +219,14 @@ __device__ __forceinline__ void plane_gather8(const float* __restrict__ plane_ba
 // the 3-term hi/lo split -- a third of the mma.sync and none of the lo-fragment arithmetic.  CPU probe with the oracle
 // (tools/probe_render_precision.py): 1.2e-4 max-abs / 94 dB on the final image, inside the 1e-3 bar but outside the 2e-5 the
 // op-level renderer tests hold the feature image to: the generator asks for it (its measured budget), a bare renderer does not.
-template <bool MLP1>
+template <bool MLP1, bool H16>
 __device__ __forceinline__ void gather_mlp_pass(const ia_render_params& p, const float* __restrict__ planes_b, const Ray& r,
                                                 const float* dep, float* col, float* sig, int s0, int n, int lane,
                                                 const DecoderFrags* __restrict__ dec) {
     const int g = lane >> 2, t = lane & 3;
     const float scale = 2.0f / p.box_warp;
     const float* pb = planes_b + 4 * t;
+    const __half* pbh = reinterpret_cast<const __half*>(planes_b) + 8 * t;
     for (int m0 = 0; m0 < n; m0 += 16) {
         float feat[2][8];
 #pragma unroll
@@ -189,9 +237,15 @@ __device__ __forceinline__ void gather_mlp_pass(const ia_render_params& p, const
             const float qy = (r.oy + tt * r.dy) * scale;
             const float qz = (r.oz + tt * r.dz) * scale;
             float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            plane_gather8(pb + 0, p.plane_px_ld, p.PH, p.PW, qx, qy, acc);    // plane 0: (x, y)
-            plane_gather8(pb + 32, p.plane_px_ld, p.PH, p.PW, qx, qz, acc);   // plane 1: (x, z)
-            plane_gather8(pb + 64, p.plane_px_ld, p.PH, p.PW, qz, qx, acc);   // plane 2: (z, x)
+            if (H16) {
+                plane_gather8_h(pbh + 0, p.plane_px_ld, p.PH, p.PW, qx, qy, acc);    // plane 0: (x, y)
+                plane_gather8_h(pbh + 32, p.plane_px_ld, p.PH, p.PW, qx, qz, acc);   // plane 1: (x, z)
+                plane_gather8_h(pbh + 64, p.plane_px_ld, p.PH, p.PW, qz, qx, acc);   // plane 2: (z, x)
+            } else {
+                plane_gather8(pb + 0, p.plane_px_ld, p.PH, p.PW, qx, qy, acc);    // plane 0: (x, y)
+                plane_gather8(pb + 32, p.plane_px_ld, p.PH, p.PW, qx, qz, acc);   // plane 1: (x, z)
+                plane_gather8(pb + 64, p.plane_px_ld, p.PH, p.PW, qz, qx, acc);   // plane 2: (z, x)
+            }
 #pragma unroll
             for (int k = 0; k < 8; ++k) feat[rr][k] = acc[k] * (1.0f / 3.0f);  // mean over the three planes (<= 1 ulp from the division)
         }
@@ -311,7 +365,7 @@ __device__ __forceinline__ void march_weights(const float* d, const float* sg, f
     wsum = ws; dnum = dn;
 }
 
-template <bool MLP1>
+template <bool MLP1, bool H16>
 __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1) render_kernel(const ia_render_params p) {
     const int kWarpsPerCta = blockDim.x >> 5;
     extern __shared__ __align__(16) float smem[];
@@ -354,7 +408,9 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1) render_kernel(const i
         } else {
             r = make_ray(p.cam + (int64_t)b * p.cam_ld, p.res, px, py);
         }
-        const float* planes_b = p.planes + (int64_t)b * p.PH * p.PW * p.plane_px_ld;
+        // (fp16 planes: the same element offset, two bytes per element)
+        const float* planes_b = H16 ? reinterpret_cast<const float*>(reinterpret_cast<const __half*>(p.planes) + (int64_t)b * p.PH * p.PW * p.plane_px_ld)
+                                    : p.planes + (int64_t)b * p.PH * p.PW * p.plane_px_ld;
 
         // ---- coarse depths (renderer.py:404-406) ----
         for (int s = lane; s < p.Dc; s += 32) {
@@ -363,7 +419,7 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1) render_kernel(const i
             dmin = fminf(dmin, t); dmax = fmaxf(dmax, t);
         }
         __syncwarp();
-        gather_mlp_pass<MLP1>(p, planes_b, r, dep, col, sig, 0, p.Dc, lane, dec);
+        gather_mlp_pass<MLP1, H16>(p, planes_b, r, dep, col, sig, 0, p.Dc, lane, dec);
         __syncwarp();
 
         int n_all = p.Dc;
@@ -424,7 +480,7 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1) render_kernel(const i
                 dmin = fminf(dmin, t); dmax = fmaxf(dmax, t);
             }
             __syncwarp();
-            gather_mlp_pass<MLP1>(p, planes_b, r, dep, col, sig, p.Dc, p.Df, lane, dec);
+            gather_mlp_pass<MLP1, H16>(p, planes_b, r, dep, col, sig, p.Dc, p.Df, lane, dec);
             __syncwarp();
             // ---- merge: stable rank of every sample among all S (unify_samples, renderer.py:372-382) ----
             // Both lists are normally already sorted (coarse: jitter < bin width; fine: deterministic u), in which case the
@@ -587,11 +643,14 @@ extern "C" int ia_render(const ia_render_params* p, void* stream) {
     IA_CHECK(p->w1 && p->b1 && p->w2 && p->b2, "ia_render: null decoder weights");
     IA_CHECK(p->scratch && (reinterpret_cast<uintptr_t>(p->scratch) & 15) == 0, "ia_render: scratch of ia_render_scratch_bytes() bytes (16-byte aligned) required");
     IA_CHECK(p->Dc >= 4 && p->Dc <= 96 && p->Df >= 0 && p->Df <= 96, "ia_render: depth resolutions must be in [4,96] / [0,96]");
-    IA_CHECK((p->plane_px_ld & 3) == 0 && p->plane_px_ld >= 96, "ia_render: planes need >= 96 channels, pixel stride multiple of 4");
+    IA_CHECK(p->planes_fmt == IA_OPFMT_BF16X3 || p->planes_fmt == IA_OPFMT_F16X1, "ia_render: planes_fmt must be 0 (fp32) or IA_OPFMT_F16X1 (fp16)");
+    const bool h16 = p->planes_fmt == IA_OPFMT_F16X1;
+    IA_CHECK((p->plane_px_ld & (h16 ? 7 : 3)) == 0 && p->plane_px_ld >= 96 && (reinterpret_cast<uintptr_t>(p->planes) & 15) == 0,
+             "ia_render: planes need >= 96 channels, 16-byte aligned pixels");
     IA_CHECK(p->res > 0 && p->B > 0, "ia_render: empty batch");
     cudaStream_t st = as_stream(stream);
     ia::prof_begin("ia_render(decoder_stage)", st);
-    decoder_stage_kernel<<<1, 256, 0, st>>>(p->w1, p->b1, p->w2, p->b2, reinterpret_cast<DecoderFrags*>(p->scratch));
+    decoder_stage_kernel<<<1, 256, 0, st>>>(p->w1, p->b1, p->w2, p->b2, reinterpret_cast<DecoderFrags*>(p->scratch), h16 ? 1 : 0);
     IA_LAUNCH_CHECK("ia_render(decoder_stage)");
     cudaError_t e = cudaSuccess;
     ia::prof_begin("ia_render(minmax_init)", st);
@@ -607,22 +666,21 @@ extern "C" int ia_render(const ia_render_params* p, void* stream) {
     const size_t smem = sizeof(DecoderFrags) + per_warp * kWarpsPerCta * sizeof(float);
     IA_CHECK(p->mlp_fmt == IA_OPFMT_BF16X3 || p->mlp_fmt == IA_OPFMT_F16X1, "ia_render: unknown mlp_fmt %d", p->mlp_fmt);
     const bool mlp1 = p->mlp_fmt == IA_OPFMT_F16X1;      // single-pass fp16 decoder (see gather_mlp_pass)
-    e = mlp1 ? cudaFuncSetAttribute(render_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-             : cudaFuncSetAttribute(render_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    void (*kern)(const ia_render_params) = mlp1 ? (h16 ? render_kernel<true, true> : render_kernel<true, false>)
+                                                : (h16 ? render_kernel<false, true> : render_kernel<false, false>);
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     IA_CHECK(e == cudaSuccess, "ia_render: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     int dev = 0, sms = 148, per_sm = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (mlp1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_kernel<true>, kWarpsPerCta * 32, smem);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_kernel<false>, kWarpsPerCta * 32, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWarpsPerCta * 32, smem);
     if (per_sm < 1) per_sm = 1;
     int64_t total_rays = (int64_t)p->B * p->res * p->res;
     int64_t want = cdiv(total_rays, kWarpsPerCta);
     int64_t grid = (int64_t)sms * per_sm;
     if (grid > want) grid = want;
     ia::prof_begin("ia_render", st);
-    if (mlp1) render_kernel<true><<<(unsigned)grid, kWarpsPerCta * 32, smem, st>>>(*p);
-    else render_kernel<false><<<(unsigned)grid, kWarpsPerCta * 32, smem, st>>>(*p);
+    kern<<<(unsigned)grid, kWarpsPerCta * 32, smem, st>>>(*p);
     IA_LAUNCH_CHECK("ia_render");
     return 0;
 }

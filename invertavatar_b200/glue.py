@@ -93,6 +93,10 @@ def copy_params_and_buffers(src_module, dst_module, require_all=False, print_=Tr
                 if require_all:
                     print(name, src[name].shape, tensor.shape)
                     raise AssertionError(f'copy_params_and_buffers: shape mismatch for {name}')
+    # the "reload" idiom of the scripts (Cls(*G.init_args, **G.init_kwargs) + copy_params_and_buffers(G, G_new, require_all=True),
+    # reenact_avatar_next3d.py:158-160) keeps the checkpoint identity: the pack cache of runtime.prepack stays keyed by it
+    if require_all and '_ia_source_hash' in src_module.__dict__:
+        dst_module.__dict__['_ia_source_hash'] = src_module.__dict__['_ia_source_hash']
 
 
 @contextlib.contextmanager
@@ -168,7 +172,12 @@ class _Unpickler(pickle.Unpickler):
 
 def load_network_pkl(f, force_fp16=False):
     """legacy.load_network_pkl (legacy.py:24-60) for PyTorch pickles written by the reference's persistence layer."""
-    data = _Unpickler(f).load()
+    # content hash of the checkpoint: key of the on-disk cache of packed tensor-core weights (runtime.prepack, SURVEY 8f-3)
+    import hashlib
+    import io
+    raw = f.read()
+    digest = hashlib.sha256(raw).hexdigest()
+    data = _Unpickler(io.BytesIO(raw)).load()
     if not isinstance(data, dict):
         raise IOError('load_network_pkl: TensorFlow-era pickles are not supported by this build')
     data.setdefault('training_set_kwargs', None)
@@ -176,6 +185,9 @@ def load_network_pkl(f, force_fp16=False):
     assert isinstance(data['G'], torch.nn.Module)
     if force_fp16:
         raise NotImplementedError('force_fp16: the generator runs fp32 semantics with split-bf16 tensor-core operands on this engine')
+    for k in ('G', 'G_ema', 'D'):
+        if isinstance(data.get(k), torch.nn.Module):
+            data[k].__dict__['_ia_source_hash'] = f'{digest}:{k}'
     return data
 
 

@@ -105,6 +105,13 @@ class ImportanceRenderer_bsMotion(torch.nn.Module):
             return rt.FMT_BF16X3
         return int(getattr(self, 'mlp_fmt', rt.FMT_BF16X3))
 
+    def _planes_fp16(self):
+        """Whether the caller should hand render_nhwc fp16 planes (TriPlaneGenerator's storage policy; never in strict mode)."""
+        import os
+        if os.environ.get('IA_CONV_PRECISION', 'auto') == 'bf16x3':
+            return False
+        return int(getattr(self, 'planes_fmt', rt.FMT_BF16X3)) == rt.FMT_F16X1
+
     def _draws(self, B, rays, Dc, Df, evaluation, device):
         jit, u = self.depth_jitter, self.importance_u
         self.depth_jitter = self.importance_u = None

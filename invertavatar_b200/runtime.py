@@ -402,6 +402,18 @@ class ConvPack(_EngineCache):
                                               _p(self.w_hi), _p(self.w_lo), _p(self.wsq), self.fmt, st), 'ia_pack_conv_weight')
         self.key = (weight.data_ptr(), weight._version, str(dev), self.fmt)
 
+    @classmethod
+    def from_tensors(cls, weight, fmt, w_hi, w_lo, wsq):
+        """A pack rebuilt from tensors produced earlier by this class for the same weight values (the on-disk pack cache)."""
+        self = cls.__new__(cls)
+        self.Cout, self.Cin, self.kh, self.kw = [int(v) for v in weight.shape]
+        self.taps = self.kh * self.kw
+        self.Cout_pad, self.Cin_pad, self.fmt = _pad_to(self.Cout, 32), _pad_to(self.Cin, 64), int(fmt)
+        assert tuple(w_hi.shape) == (self.taps, self.Cout_pad, self.Cin_pad) and w_hi.dtype == _FMT_DTYPE[self.fmt]
+        self.w_hi, self.w_lo, self.wsq = w_hi, w_lo, wsq
+        self.key = (weight.data_ptr(), weight._version, str(weight.device), self.fmt)
+        return self
+
     @staticmethod
     def current(cache_owner, attr, weight, need_wsq=True, fmt=FMT_BF16X3):
         """Return the pack cached on ``cache_owner.<attr>``; repack when the parameter (or the requested format) changed."""
@@ -413,24 +425,82 @@ class ConvPack(_EngineCache):
         return pack
 
 
-def prepack(module):
-    """One-time weight packing at load: build the GEMM-layout bf16 hi/lo weights (+ the demodulation table
-    sum w^2) of every convolution / ToRGB layer of ``module`` now instead of at first use.  Call after ``module.to('cuda')``
-    (e.g. right after ``legacy.load_network_pkl``); returns the packed bytes.  Packs are keyed on the parameter's storage and
-    version, so a later in-place update (PTI fine-tuning, ``copy_params_and_buffers``) repacks that layer transparently."""
-    total = 0
-    for m in module.modules():
+def _packable(module):
+    """(qualified name, module, weight, packer) of every convolution layer of ``module`` that owns a tensor-core pack."""
+    for name, m in module.named_modules():
         w = getattr(m, 'weight', None)
         if not (isinstance(w, torch.Tensor) and w.is_cuda and w.ndim == 4):
             continue
         fn = getattr(m, 'pack', None)
         if callable(fn):
-            pk = fn()
+            yield name, m, w, fn
         elif isinstance(m, torch.nn.Conv2d) and m.groups == 1:      # encoder convolutions (plain nn.Conv2d parameters)
-            pk = ConvPack.current(m, '_ia_pack', w, need_wsq=False)
-        else:
-            continue
+            yield name, m, w, (lambda m=m, w=w: ConvPack.current(m, '_ia_pack', w, need_wsq=False))
+
+
+def pack_cache_path(source_hash, cache_dir=None):
+    """File of the on-disk pack cache for a checkpoint: keyed by the checkpoint's content hash (legacy.load_network_pkl records
+    the sha256 of the pickle bytes), the library's source hash (a new kernel layout must not read old packs) and the precision
+    policy in force."""
+    import hashlib
+    from . import build as _build
+    cache_dir = cache_dir or os.environ.get('IA_PACK_CACHE') or os.path.join(os.path.expanduser('~'), '.cache', 'invertavatar_b200', 'packs')
+    tag = hashlib.sha256(('|'.join([str(source_hash), _build.source_hash(), os.environ.get('IA_CONV_PRECISION', 'auto'),
+                                    str(_C.ABI_VERSION)])).encode()).hexdigest()[:32]
+    return os.path.join(cache_dir, tag + '.pt')
+
+
+def prepack(module, source_hash=None, cache_dir=None):
+    """One-time weight packing at load: build the GEMM-layout weights (bf16 hi/lo or fp16, per the layer's
+    precision) + the demodulation table sum w^2 of every convolution / ToRGB layer of ``module`` now instead of at first use.
+    Call after ``module.to('cuda')`` (e.g. right after ``legacy.load_network_pkl``); returns the packed bytes.  Packs are keyed
+    on the parameter's storage and version, so a later in-place update (PTI fine-tuning, ``copy_params_and_buffers``) repacks
+    that layer transparently.
+
+    ``source_hash`` (default: the hash ``legacy.load_network_pkl`` recorded on the module, if any) turns on the on-disk cache:
+    the packs are written to ``pack_cache_path(source_hash)`` the first time and read back -- no packing kernels, no fp32 ->
+    operand conversion -- on every later load of the same checkpoint with the same library."""
+    source_hash = source_hash or module.__dict__.get('_ia_source_hash')
+    path = pack_cache_path(source_hash, cache_dir) if source_hash else None
+    layers = list(_packable(module))
+    total = 0
+    if path and os.path.exists(path):
+        try:
+            blob = torch.load(path, map_location=layers[0][2].device if layers else 'cpu', weights_only=True)
+        except Exception:
+            blob = None
+        if blob is not None and set(blob.keys()) == {n for n, *_ in layers}:
+            ok = True
+            for name, m, w, fn in layers:
+                e = blob[name]
+                fmt = layer_fmt(m) if hasattr(m, 'fmt') else FMT_BF16X3
+                if int(e['fmt']) != fmt or tuple(e['shape']) != tuple(w.shape):
+                    ok = False
+                    break
+            if ok:
+                for name, m, w, fn in layers:
+                    e = blob[name]
+                    m.__dict__['_ia_pack'] = ConvPack.from_tensors(w, int(e['fmt']), e['w_hi'], e.get('w_lo'), e.get('wsq'))
+                    pk = m.__dict__['_ia_pack']
+                    total += pk.w_hi.numel() * (4 if pk.w_lo is not None else 2) + (pk.wsq.numel() * 4 if pk.wsq is not None else 0)
+                return total
+    for name, m, w, fn in layers:
+        pk = fn()
         total += pk.w_hi.numel() * (4 if pk.w_lo is not None else 2) + (pk.wsq.numel() * 4 if pk.wsq is not None else 0)
+    if path:
+        blob = {}
+        for name, m, w, fn in layers:
+            pk = m.__dict__['_ia_pack']
+            e = {'fmt': torch.tensor(pk.fmt), 'shape': torch.tensor(list(w.shape)), 'w_hi': pk.w_hi}
+            if pk.w_lo is not None:
+                e['w_lo'] = pk.w_lo
+            if pk.wsq is not None:
+                e['wsq'] = pk.wsq
+            blob[name] = e
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        tmp = path + f'.tmp{os.getpid()}'
+        torch.save(blob, tmp)
+        os.replace(tmp, path)
     return total
 
 
@@ -957,6 +1027,23 @@ def raster_level(tex_nhwc, uv, stat_nhwc, crop, alpha_r, res):
 # ---------------------------------------------------------------------------------------------------
 # renderer
 # ---------------------------------------------------------------------------------------------------
+def stitch_planes(plane_img, stitch, alpha, origin, fp16=False):
+    """Plane stitch (triplane_v20.py:119-128) in one pass: a copy of plane_img [B,H,W,C] fp32 NHWC (view with pixel stride >= C)
+    whose plane-0 channels [0,32) inside the window at ``origin`` = (y0, x0) are stitch*alpha + plane*(1-alpha); stitch
+    [B,h,w,32], alpha [B,h,w].  fp16=True writes the renderer's half-precision storage format."""
+    st = _enter(plane_img)
+    B, H, W, Cc = plane_img.shape
+    assert plane_img.stride(3) == 1 and plane_img.stride(1) == W * plane_img.stride(2) and plane_img.stride(0) == H * plane_img.stride(1)
+    stitch, alpha = _f32c(stitch), _f32c(alpha)
+    _, wh, ww, sc = stitch.shape
+    assert sc == 32 and tuple(alpha.shape) == (B, wh, ww)
+    out = torch.empty((B, H, W, Cc), dtype=torch.float16 if fp16 else torch.float32, device=plane_img.device)
+    p = _C.StitchParams(_p(plane_img), plane_img.stride(2), B, H, W, Cc, _p(stitch), _p(alpha), int(origin[0]), int(origin[1]), wh, ww,
+                        _p(out), FMT_F16X1 if fp16 else 0)
+    _C.check(_C.lib().ia_stitch_planes(C.byref(p), st), 'ia_stitch_planes')
+    return out
+
+
 def ray_sampler(cam, res):
     st = _enter(cam)
     cam = _f32c(cam)
@@ -972,7 +1059,8 @@ def render(planes_nhwc, cam, res, Dc, Df, jitter, u, box_warp, white_back, w1, b
     [B,res*res,3] with cam=None); returns feat [B,res,res,32], depth [B,res,res] (clamped), wsum [B,res,res]."""
     st = _enter(planes_nhwc)
     B, PH, PW, PC = planes_nhwc.shape
-    assert planes_nhwc.is_contiguous() and PC >= 96
+    assert planes_nhwc.is_contiguous() and PC >= 96 and planes_nhwc.dtype in (torch.float32, torch.float16)
+    planes_fmt = FMT_F16X1 if planes_nhwc.dtype == torch.float16 else 0
     rays_o = rays_d = None
     if rays is not None:
         rays_o, rays_d = _f32c(rays[0]), _f32c(rays[1])
@@ -1000,7 +1088,7 @@ def render(planes_nhwc, cam, res, Dc, Df, jitter, u, box_warp, white_back, w1, b
     w1, b1, w2, b2 = _f32c(w1), _f32c(b1), _f32c(w2), _f32c(b2)
     p = _C.RenderParams(_p(planes_nhwc), PC, B, PH, PW, _p(cam), (cam.stride(0) if cam is not None else 0), _p(rays_o), _p(rays_d), res, Dc, Df, _p(jitter), _p(u),
                         float(box_warp), 1 if white_back else 0, _p(near_far), _p(w1), _p(b1), _p(w2), _p(b2),
-                        _p(feat), _p(depth), _p(wsum), _p(mm), _p(scratch), int(mlp_fmt))
+                        _p(feat), _p(depth), _p(wsum), _p(mm), _p(scratch), int(mlp_fmt), planes_fmt)
     _C.check(_C.lib().ia_render(C.byref(p), st), 'ia_render')
     _C.check(_C.lib().ia_depth_clamp(_p(depth), depth.numel(), _p(mm), st), 'ia_depth_clamp')
     return feat, depth, wsum

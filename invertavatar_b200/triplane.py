@@ -60,6 +60,23 @@ def _construct(class_name, **kwargs):
     return cls(**kwargs)
 
 
+class _StageOutputs(dict):
+    """Result dictionary of synthesis_withTexture / synthesis_withCondition.  The reference returns the blended tri-planes
+    under 'triplane' from these calls (triplane_v20.py:243-244,311); the renderer here consumes them in fp16 and the
+    inference scripts never read the entry (eval_seq.py:212 takes ['image']), so the fp32 [B,3,32,256,256] tensor is
+    materialised on first access instead of on every frame."""
+
+    def __init__(self, items, make_triplane):
+        super().__init__(items)
+        self._make_triplane = make_triplane
+
+    def __missing__(self, key):
+        if key == 'triplane' and self._make_triplane is not None:
+            self['triplane'] = self._make_triplane()
+            return dict.__getitem__(self, 'triplane')
+        raise KeyError(key)
+
+
 class OSGDecoder(torch.nn.Module):
     """triplane_v20.py:415-438.  The forward used by the generator is fused into the render kernel; the module holds the
     parameters (decoder.net.{0,2}.{weight,bias}) and offers the standalone forward for API parity."""
@@ -118,6 +135,8 @@ class TriPlaneGenerator(torch.nn.Module):
         # the renderer's decoder MLP as single-pass fp16 mma.sync as well: +1.2e-4 on the final image on its own, 1.2e-4 .. 3.6e-4
         # (PSNR 86 .. 95 dB) together with the backbone layers (profiles/r2_conv_precision_probe_mix_mlp.json)
         self.renderer.mlp_fmt = rt.FMT_F16X1
+        # ... and the tri-planes it gathers from are stored as fp16 (9.4e-6 on the final image, profiles/r1_render_precision_probe.json)
+        self.renderer.planes_fmt = rt.FMT_F16X1
 
     def _side_streams(self, device):
         return rt.side_streams(device)
@@ -228,9 +247,12 @@ class TriPlaneGenerator(torch.nn.Module):
         stitch128 = rt.resize_aa(stitch, 128, 128)
         alpha128 = uv_prep['alpha128'] if (uv_prep is not None and 'alpha128' in uv_prep) else \
             rt.resize_aa(full_alpha.unsqueeze(-1), 128, 128).squeeze(-1)
-        planes = plane_img.clone()
-        win_out = planes[:, b0:b1, b2:b3, :32]
-        rt.lerp_alpha(stitch128, plane_img[:, b0:b1, b2:b3, :32], alpha128, out=win_out)
+        # one pass: copy of the static planes with the face window of plane 0 blended in, written in the renderer's storage
+        # format (fp16 by the generator's policy: halves the gather traffic, 9.4e-6 on the image; fp32 in strict mode or when
+        # the caller wants the tri-plane back)
+        want_planes32 = bool(synthesis_kwargs.get('_want_triplane', False))
+        planes_fp16 = self.renderer._planes_fp16() and not want_planes32
+        planes = rt.stitch_planes(plane_img, stitch128, alpha128, (b0, b2), fp16=planes_fp16)
 
         if evaluation:
             assert synthesis_kwargs.get('noise_mode') == 'const', ('noise_mode' in synthesis_kwargs, synthesis_kwargs.get('noise_mode'))
@@ -239,12 +261,18 @@ class TriPlaneGenerator(torch.nn.Module):
         feature_image = rt.from_nhwc(feat)                       # [B,32,res,res] view
         depth_image = depth.reshape(N, 1, res, res)
         rgb_image = feature_image[:, :3]
-        sr_kwargs = {k: v for k, v in synthesis_kwargs.items() if k != 'noise_mode' and k not in ('update_emas',)}
+        sr_kwargs = {k: v for k, v in synthesis_kwargs.items() if k != 'noise_mode' and k not in ('update_emas', '_want_triplane')}
         sr_image = self.superresolution(rgb_image, feature_image, ws, noise_mode=self.rendering_kwargs['superresolution_noise_mode'],
                                         **sr_kwargs)
-        triplane = rt.from_nhwc(planes).reshape(N, 3, 32, planes.shape[1], planes.shape[2])
-        return {'image': sr_image, 'image_raw': rgb_image, 'image_depth': depth_image, 'feature_image': feature_image,
-                'triplane': triplane}
+        out = {'image': sr_image, 'image_raw': rgb_image, 'image_depth': depth_image, 'feature_image': feature_image}
+        if planes.dtype == torch.float32:
+            out['triplane'] = rt.from_nhwc(planes).reshape(N, 3, 32, planes.shape[1], planes.shape[2])
+            return out
+
+        def make_triplane():
+            p32 = rt.stitch_planes(plane_img, stitch128, alpha128, (b0, b2), fp16=False)
+            return rt.from_nhwc(p32).reshape(N, 3, 32, p32.shape[1], p32.shape[2])
+        return _StageOutputs(out, make_triplane)
 
     def synthesis(self, ws, c, mesh_condition, neural_rendering_resolution=None, update_emas=False, cache_backbone=False,
                   use_cached_backbone=False, return_featmap=False, evaluation=False, depth_jitter=None, importance_u=None,
@@ -294,6 +322,8 @@ class TriPlaneGenerator(torch.nn.Module):
             uv_prep = None
             texture_feats = self.texture_backbone.synthesis(ws, cond_list=None, return_list=True, prefix=pre[0], **tex_kwargs)
             static_feats = self.backbone.synthesis(ws, cond_list=None, return_list=True, prefix=pre[1], **noise_kwargs)
+        if return_featmap:
+            synthesis_kwargs = dict(synthesis_kwargs, _want_triplane=True)      # the caller reads out['triplane']: fp32 planes
         out = self._stitch_render_sr(ws, c, mesh_condition, texture_feats, static_feats, neural_rendering_resolution,
                                      evaluation, synthesis_kwargs, face_prefix=pre[2], uv_prep=uv_prep)
         if return_featmap:

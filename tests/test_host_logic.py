@@ -108,3 +108,30 @@ print('ok')
 ''' % (ROOT, str(path), str(path2))
     r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and r.stdout.strip().endswith('ok'), r.stdout + r.stderr
+
+
+def test_checkpoint_hash_travels_to_the_pack_cache_key(tmp_path, monkeypatch):
+    """legacy.load_network_pkl records the sha256 of the pickle bytes on the loaded networks, copy_params_and_buffers(require_all)
+    carries it to the rebuilt module, and the pack-cache file name depends on it, on the library's source hash and on the
+    precision policy (one-time weight packing cached by checkpoint hash)."""
+    import hashlib
+    import pickle
+    from invertavatar_b200 import glue
+    from invertavatar_b200.stylegan2 import FullyConnectedLayer
+    torch.manual_seed(0)
+    G = FullyConnectedLayer(4, 3)
+    path = tmp_path / 'net.pkl'
+    with open(path, 'wb') as f:
+        pickle.dump({'G': G, 'G_ema': G}, f)
+    with open(path, 'rb') as f:
+        data = glue.load_network_pkl(f)
+    digest = hashlib.sha256(open(path, 'rb').read()).hexdigest()
+    assert data['G_ema'].__dict__['_ia_source_hash'] == digest + ':G_ema'
+    G2 = FullyConnectedLayer(4, 3)
+    glue.copy_params_and_buffers(data['G_ema'], G2, require_all=True)
+    assert G2.__dict__['_ia_source_hash'] == digest + ':G_ema' and torch.equal(G2.weight, G.weight)
+    a = rt.pack_cache_path(digest + ':G_ema', cache_dir=str(tmp_path))
+    b = rt.pack_cache_path(digest + ':G', cache_dir=str(tmp_path))
+    monkeypatch.setenv('IA_CONV_PRECISION', 'bf16x3')
+    c = rt.pack_cache_path(digest + ':G_ema', cache_dir=str(tmp_path))
+    assert a != b and a != c and a.startswith(str(tmp_path)) and a.endswith('.pt')

@@ -34,6 +34,7 @@ ap.add_argument('--frames', type=int, default=3)
 ap.add_argument('--budget', type=float, default=5e-4)
 ap.add_argument('--modes', default='f16x1,f16a,f16w')
 ap.add_argument('--mlp-fp16', action='store_true', help='also evaluate the renderer decoder MLP as single-pass fp16 products (IA_RENDER_MLP=fp16)')
+ap.add_argument('--torgb-f16', action='store_true', help='eval-mix: the backbone ToRGB layers (1x1, no demodulation) single-pass fp16 as well')
 ap.add_argument('--eval-mix', default='', help="skip the search: evaluate a preset ('backbones_f16x1') on --frames frames, with bf16x3 arithmetic elsewhere")
 args = ap.parse_args()
 torch.set_num_threads(os.cpu_count() or 1)
@@ -60,7 +61,12 @@ def split2(t, mode):
 
 def modconv(x, weight, styles, noise=None, up=1, padding=0, resample_filter=None, demodulate=True, flip_weight=True, fused_modconv=True):
     """The engine's formulation (fused_modconv=False, networks_stylegan2_new.py:70-79) with rounded tensor-core operands."""
-    if not demodulate:       # ToRGB: stays 3-term (tiny)
+    if not demodulate:       # ToRGB: 3-term (exact here) unless --torgb-f16; the super-resolution ToRGBs (3 output channels) are fp32 FMAs
+        if STATE.get('torgb_f16') and weight.shape[0] > 3:
+            B_, I_ = x.shape[0], weight.shape[1]
+            a = x * styles.reshape(B_, I_, 1, 1)
+            y = _conv0(rn(a, 'f16x1'), rn(weight, 'f16x1'), f=resample_filter, up=up, padding=padding, flip_weight=flip_weight)
+            return y + noise if noise is not None else y
         return _mod0(x, weight, styles, noise=noise, up=up, padding=padding, resample_filter=resample_filter, demodulate=demodulate,
                      flip_weight=flip_weight, fused_modconv=fused_modconv)
     idx = STATE['i']
@@ -147,6 +153,7 @@ if args.eval_mix:
         refs = [render(f) for f in range(args.frames)]      # (references were rendered above with the exact decoder)
         o_r.osg_decoder = dec_single
     mix = {L['idx']: 'f16x1' for L in layers if not L['name'].startswith('sr.')}
+    STATE['torgb_f16'] = bool(args.torgb_f16)
     full = {L['idx']: mix.get(L['idx'], 'bf16x3') for L in layers}
     res = []
     for f in range(args.frames):
