@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument('--depth', type=int, default=48, help='coarse = importance depth samples per ray')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-roofline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='workload c3: issue the identity step eagerly instead of replaying its CUDA graph')
     ap.add_argument('--e2e-f32', action='store_true', help='end-to-end leg reads back the fp32 images instead of uint8 HWC frames')
     return ap.parse_args()
 
@@ -627,8 +628,22 @@ def run_c3(args, rank, world, local, dev):
                                                   static_feats=upd['static'], evaluation=True)['image'])
         return torch.cat(frames)
 
+    # The identity step is ~2 400 launches whose host cost exceeds their device time: the public helper for such sequences,
+    # invertavatar_b200.graphs.GraphedCall, captures it once into a CUDA graph and replays it per identity (same kernels, same
+    # numbers; --no-graph issues them eagerly).
+    graphed = None
+    launches_per_step = None
+    if not args.no_graph:
+        from invertavatar_b200.graphs import GraphedCall
+        with torch.no_grad():
+            identity(res_in)                     # (first call builds the weight packs)
+            rt.reset_launch_count()
+            identity(res_in)
+            launches_per_step = rt.launch_count()
+        graphed = GraphedCall(lambda **kw: identity(kw), res_in)
+
     def step_resident():
-        return identity(res_in)
+        return graphed() if graphed is not None else identity(res_in)
 
     copy_stream = torch.cuda.Stream(device=dev)
     h = _Harness(dev, world, copy_stream)
@@ -644,14 +659,17 @@ def run_c3(args, rank, world, local, dev):
 
     def step_e2e():
         cur = torch.cuda.current_stream()
-        if stage['next'] is None:
+        if graphed is not None:
+            img = graphed(**host_in)             # pinned host -> the graph's static input buffers (H2D on the compute stream), replay
+        else:
+            if stage['next'] is None:
+                stage['next'] = upload()
+            ts, ev = stage['next']
+            cur.wait_event(ev)
+            for t in ts.values():
+                t.record_stream(cur)
             stage['next'] = upload()
-        ts, ev = stage['next']
-        cur.wait_event(ev)
-        for t in ts.values():
-            t.record_stream(cur)
-        stage['next'] = upload()
-        img = identity(ts)
+            img = identity(ts)
         out = img if args.e2e_f32 else rt.layout_grid_u8(img, grid_w=T_C3, grid_h=1)
         if rb['o'] is None:
             rb['o'] = _Readback(out, copy_stream)
@@ -668,7 +686,7 @@ def run_c3(args, rank, world, local, dev):
         clocks.rows.clear()
         rt.reset_launch_count()
         ms = h.timed(step_resident, args.steps)
-        launches = rt.launch_count()
+        launches = rt.launch_count() if graphed is None else launches_per_step * args.steps     # (a replay re-launches the captured kernels)
         for _ in range(2):
             step_e2e()
         ms_e2e = h.timed(step_e2e, args.steps)
@@ -685,7 +703,7 @@ def run_c3(args, rank, world, local, dev):
                 rt.flop_count_begin()
                 rt.profile_begin()
                 for _ in range(args.steps):
-                    step_resident()
+                    identity(res_in)             # eager: per-launch events cannot be recorded inside a graph replay
                 rep = rt.profile_report()
                 counted = rt.flop_count_end()
             finally:
@@ -746,7 +764,8 @@ def run_c3(args, rank, world, local, dev):
             'e2e': {'value': frames / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': sum(t.numel() * t.element_size() for t in host_in.values()),
                     'd2h_bytes_per_step': rb['o'].bytes, 'ms_per_step': ms_e2e / args.steps,
                     'readback': 'fp32 NCHW images' if args.e2e_f32 else 'uint8 HWC frames (layout_grid, eval_seq.py:214)'},
-            'gpu_launches': launches, 'identities_per_s': world * args.steps / (ms * 1e-3)}
+            'gpu_launches': launches, 'identities_per_s': world * args.steps / (ms * 1e-3),
+            'issue': 'eager (Python + ctypes launches)' if graphed is None else 'one CUDA graph per identity step (invertavatar_b200.graphs.GraphedCall), replayed'}
     if stages is not None:
         line['stages'] = stages
     if roofline is not None:

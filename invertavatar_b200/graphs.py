@@ -53,3 +53,39 @@ class GraphedSynthesis:
             self.uv.copy_(uvcoords_image, non_blocking=True)
         self.graph.replay()
         return self.out
+
+
+class GraphedCall:
+    """A whole call sequence captured into ONE CUDA graph:
+
+        gc = GraphedCall(fn, inputs)        # inputs: dict name -> CUDA tensor (shapes are frozen); fn(**inputs) -> tensor / tuple / dict of tensors
+        out = gc(image=new_image, ...)      # copy the given inputs into the static buffers, replay, return the (static) outputs
+
+    Meant for launch-bound sequences of this library -- e.g. one identity of eval_seq.py:164-212 (e4e encode + the two backbones +
+    inversionNet.AR_eval_forward + the per-frame synthesis_withTexture calls) is ~2 400 launches whose host cost (~25 us each
+    through Python + ctypes) exceeds their device time.  Everything the library does is capture-safe: kernels go to the
+    capturing stream(s), side streams fork and join with events, tensor maps are encoded on the host at capture time, scratch
+    comes from torch's (graph-private) caching allocator.  Random draws made with torch inside ``fn`` use the graph-safe
+    Philox state of torch.cuda.graph (a new draw on every replay).  The numbers are those of the eager call."""
+
+    def __init__(self, fn, inputs, warmup=2):
+        dev = next(iter(inputs.values())).device
+        assert dev.type == 'cuda', 'GraphedCall needs CUDA tensors'
+        self.fn = fn
+        self.inputs = {k: v.detach().clone() for k, v in inputs.items()}
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(warmup):          # builds every cache (packed weights, style plans, tap tables, split-K scratch) outside the capture
+                fn(**self.inputs)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            self.out = fn(**self.inputs)
+
+    def __call__(self, **new_inputs):
+        for k, v in new_inputs.items():
+            self.inputs[k].copy_(v, non_blocking=True)
+        self.graph.replay()
+        return self.out

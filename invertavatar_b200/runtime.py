@@ -546,26 +546,25 @@ class StylePlan(_EngineCache):
         # entries: list of dict(affine_w, affine_b, wsq|None, Cin, Cout, w_index, style_gain)
         self.entries = entries
         self.device = device
-        self.cap = 0
-        self.styles = []
-        self.dcoefs = []
-        self.host = None
-        self.dev = None
+        self._by_batch = {}       # B -> (styles, dcoefs, host table, device table): callers alternate between batch sizes (an identity of
+                                  # eval_seq.py runs the backbones at B = 1 and the T-frame render at B = T), and a rebuild is an
+                                  # unpinned H2D copy -- not allowed inside a CUDA-graph capture and a stall outside of one
 
     def _build(self, B):
         n = len(self.entries)
-        self.cap = B
-        self.styles = [torch.empty((B, e['Cin']), dtype=torch.float32, device=self.device) for e in self.entries]
-        self.dcoefs = [torch.empty((B, e['Cout']), dtype=torch.float32, device=self.device) if e['wsq'] is not None else None
-                       for e in self.entries]
+        styles = [torch.empty((B, e['Cin']), dtype=torch.float32, device=self.device) for e in self.entries]
+        dcoefs = [torch.empty((B, e['Cout']), dtype=torch.float32, device=self.device) if e['wsq'] is not None else None
+                  for e in self.entries]
         arr = (_C.StyleLayer * n)()
         for i, e in enumerate(self.entries):
             w_dim = e['affine_w'].shape[1]
-            arr[i] = _C.StyleLayer(_p(e['affine_w']), _p(e['affine_b']), _p(e['wsq']), _p(self.styles[i]), _p(self.dcoefs[i]),
+            arr[i] = _C.StyleLayer(_p(e['affine_w']), _p(e['affine_b']), _p(e['wsq']), _p(styles[i]), _p(dcoefs[i]),
                                    e['Cin'], e['Cout'], e['w_index'], w_dim, 1.0 / math.sqrt(w_dim), float(e['style_gain']))
-        self.host = arr
         raw = np.frombuffer(bytes(arr), dtype=np.uint8).copy()
-        self.dev = torch.from_numpy(raw).to(self.device)
+        dev = torch.from_numpy(raw).to(self.device)
+        built = (styles, dcoefs, arr, dev)
+        self._by_batch[B] = built
+        return built
 
     def run(self, ws):
         """ws: [B, n, w_dim] fp32 with unit inner stride (may be a narrow() view of a wider tensor)."""
@@ -574,11 +573,11 @@ class StylePlan(_EngineCache):
                 ws.stride(0) < ws.shape[1] * ws.shape[2]:   # (an expand()ed batch has stride 0: materialise it)
             ws = ws.float().contiguous()
         B = ws.shape[0]
-        if self.host is None or B != self.cap:
-            self._build(B)
+        built = self._by_batch.get(B) or self._build(B)
+        styles, dcoefs, host, dev = built
         num_ws = max(ws.stride(0) // ws.shape[2], ws.shape[1])  # batch stride of a narrow() view, in rows
-        _C.check(_C.lib().ia_styles(_p(self.dev), self.host, len(self.entries), _p(ws), B, num_ws, st), 'ia_styles')
-        return self.styles, self.dcoefs
+        _C.check(_C.lib().ia_styles(_p(dev), host, len(self.entries), _p(ws), B, num_ws, st), 'ia_styles')
+        return styles, dcoefs
 
 
 def modsplit(x_nhwc, styles=None, cond=None, cond_alpha=None, C_pad=None, fmt=FMT_BF16X3):

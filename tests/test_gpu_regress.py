@@ -202,3 +202,21 @@ def test_pack_cache_round_trip(tmp_path):
     for m in G2.modules():          # the cached packs are the ones the forward used (keys match the parameters)
         if '_ia_pack' in m.__dict__ and hasattr(m, 'pack'):
             assert m.pack() is m.__dict__['_ia_pack']
+
+
+def test_graphed_call_matches_eager():
+    """graphs.GraphedCall (whole call sequence in one CUDA graph) on the e4e encoder: replay == eager for new inputs (up to the
+    order of the float atomics in the SE-module pooling, which differs from run to run in eager mode too)."""
+    import copy
+    from common import build_inversion_net
+    from invertavatar_b200.graphs import GraphedCall
+    net = copy.deepcopy(build_inversion_net(16, 16, 64)).to('cuda')
+    net.encoder.eval()                       # (eval-mode BatchNorm: no running-statistics side effects between the two runs)
+    x, _, _ = synth.encoder_inputs(2)
+    imgs = x['image'].cuda()
+    with torch.no_grad():
+        gc = GraphedCall(lambda image: net.encode(image), {'image': imgs[:1]})
+        for i in (1, 0):
+            got = gc(image=imgs[i:i + 1]).clone()
+            want = net.encode(imgs[i:i + 1])
+            assert float((got - want).abs().max()) <= 1e-4 * max(1.0, float(want.abs().max())), i
