@@ -437,6 +437,44 @@ int ia_enc_gru_gate(int32_t stage, const float* raw, const float* bias, const fl
 int ia_sft_half(float* x, int64_t x_ld, const ia_view* scale, const ia_view* shift, int32_t B, int32_t H, int32_t W,
                 int32_t C, void* stream);
 
+/* ---- mesh-condition producer (the step in front of the path) -------------------------------------------------
+ * Faceverse_manager.make_driven_rendering (data_preprocess/FaceVerse/renderer.py:45-84): driving coefficients -> 3DMM vertices
+ * -> orthographic rasterisation of per-vertex (u, v, mask) -> the [256][256][3] uvcoords_image of TriPlaneGenerator.synthesis.
+ * Replaces FaceVerseModel_v3.get_vs / compute_eye_rotation_matrix (FaceVerseModel_v3.py:237-244,303-325) and the pytorch3d
+ * MeshRasterizer + render_after_rasterize (ortho_renderer.py:52-100, volumetric_rendering/renderer.py:556-571). */
+
+/* Per driving frame b: exp_out[b] = expression coefficients coeff[b][exp_off .. +exp_dims) with entries -4 / -2 clamped to
+ * [-0.75, 0.6] / [-0.75, 0.75] (renderer.py:48-49) and, when the bases are given, retargeted (e - base_drive_exp) +
+ * base_avatar_exp (:50-53); eye_rot[b][2][9] = Ry(eye[1]) Rx(eye[0]) of the left / right eye-ball from coeff[b][eye_off .. +4). */
+int ia_mesh_coeffs(const float* coeff, int64_t coeff_ld, int32_t B, int32_t exp_off, int32_t exp_dims, int32_t eye_off,
+                   const float* base_drive_exp, const float* base_avatar_exp, float* exp_out, float* eye_rot, void* stream);
+/* centres[2][3]: mean of the identity's neutral eye-ball vertices [eye0,eye1) / [eye1,eye2) with z + 0.005 (FaceVerseModel_v3.py:252-264). */
+int ia_mesh_eye_centres(const float* neutral, int32_t eye0, int32_t eye1, int32_t eye2, float* centres, void* stream);
+typedef struct {
+    const float* neutral;        /* [NV][3] identity shape: meanshape + idBase * id (loader conventions applied) */
+    const float* exp_basis_t;    /* [exp_dims][NV*3] expression basis, transposed (coalesced over vertices) */
+    const float* exp;            /* [B][exp_dims] from ia_mesh_coeffs */
+    int32_t B, NV, exp_dims;
+    int32_t eye0, eye1, eye2;    /* eye-ball vertex ranges */
+    const float* eye_rot;        /* [B][2][9] */
+    const float* eye_centre;     /* [2][3] */
+    float M[12];                 /* last step: out = M[:, :3] v + M[:, 3]  (fv2fl transform, orthographic shift / scale, z flip) */
+    float* verts;                /* out [B][NV][3] */
+} ia_blendshape_params;
+int ia_blendshape(const ia_blendshape_params* p, void* stream);
+typedef struct {
+    const float* verts; int32_t B, NV;        /* [B][NV][3]; camera: x_ndc = -x, y_ndc = -y, view z = z + cam_z */
+    const int32_t* tri; int32_t F;             /* [F][3] */
+    const float* attr;                         /* [NV][3] per-vertex (u, v, face mask) */
+    int32_t size; float cam_z; float blur_radius;
+    int32_t crop_x, crop_y, crop_w, crop_h;    /* window of the size x size raster that is written out */
+    unsigned long long* zbuf;                  /* scratch, ia_ortho_raster_scratch_bytes(B, size) */
+    float* out;                                /* [B][crop_h][crop_w][3]: (u, v, mask) * vis * mask, mask binarised at 0.5 */
+    int32_t* pix_to_face;                      /* optional [B][crop_h][crop_w] face index or -1 (diagnostics), or NULL */
+} ia_ortho_raster_params;
+int64_t ia_ortho_raster_scratch_bytes(int32_t B, int32_t size);
+int ia_ortho_raster(const ia_ortho_raster_params* p, void* stream);
+
 /* ---- output stage (the step after the path) ------------------------------------------------------------
  * layout_grid (reenact_avatar_next3d.py:117-131) with float_to_uint8 and chw_to_hwc: frame g = gy*grid_w + gx of the
  * [B][C][H][W]-indexed image (element strides s_b, s_c, s_h, s_w -- the generator's channels-last output or a planar

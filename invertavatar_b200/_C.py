@@ -120,6 +120,19 @@ class StitchParams(C.Structure):
                 ('out', C.c_void_p), ('out_fmt', C.c_int32)]
 
 
+class BlendshapeParams(C.Structure):
+    _fields_ = [('neutral', c_f32p), ('exp_basis_t', c_f32p), ('exp', c_f32p), ('B', C.c_int32), ('NV', C.c_int32), ('exp_dims', C.c_int32),
+                ('eye0', C.c_int32), ('eye1', C.c_int32), ('eye2', C.c_int32), ('eye_rot', c_f32p), ('eye_centre', c_f32p),
+                ('M', C.c_float * 12), ('verts', c_f32p)]
+
+
+class OrthoRasterParams(C.Structure):
+    _fields_ = [('verts', c_f32p), ('B', C.c_int32), ('NV', C.c_int32), ('tri', c_i32p), ('F', C.c_int32), ('attr', c_f32p),
+                ('size', C.c_int32), ('cam_z', C.c_float), ('blur_radius', C.c_float),
+                ('crop_x', C.c_int32), ('crop_y', C.c_int32), ('crop_w', C.c_int32), ('crop_h', C.c_int32),
+                ('zbuf', C.c_void_p), ('out', c_f32p), ('pix_to_face', c_i32p)]
+
+
 class RasterLevelParams(C.Structure):
     _fields_ = [('tex', c_f32p), ('Ht', C.c_int32), ('Wt', C.c_int32), ('C', C.c_int32),
                 ('uv', c_f32p), ('uv_ld', C.c_int64), ('UH', C.c_int32), ('UW', C.c_int32),
@@ -202,6 +215,11 @@ SIGNATURES = {
     'ia_enc_avgpool': (C.c_int, [C.POINTER(View), C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_f32p, C.c_void_p]),
     'ia_enc_upsample_add': (C.c_int, [c_f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_f32p, C.c_int32, C.c_int32, c_f32p, C.c_void_p]),
     'ia_enc_gru_gate': (C.c_int, [C.c_int32, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int64, C.c_int32, C.c_void_p]),
+    'ia_mesh_coeffs': (C.c_int, [c_f32p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p]),
+    'ia_mesh_eye_centres': (C.c_int, [c_f32p, C.c_int32, C.c_int32, C.c_int32, c_f32p, C.c_void_p]),
+    'ia_blendshape': (C.c_int, [C.POINTER(BlendshapeParams), C.c_void_p]),
+    'ia_ortho_raster_scratch_bytes': (C.c_int64, [C.c_int32, C.c_int32]),
+    'ia_ortho_raster': (C.c_int, [C.POINTER(OrthoRasterParams), C.c_void_p]),
     'ia_layout_grid_u8': (C.c_int, [c_f32p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                    C.c_void_p, C.c_void_p]),
     'ia_sft_half': (C.c_int, [c_f32p, C.c_int64, C.POINTER(View), C.POINTER(View), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),

@@ -202,3 +202,66 @@ def encoder_inputs(T, seed=31):
     uvimg = uvcoords_image(T)
     uv = torch.cat([tex, uvimg.permute(0, 3, 1, 2)], dim=1)
     return {'image': image, 'uv': uv}, cameras(T), {'uvcoords_image': uvimg}
+
+
+# ---- synthetic FaceVerse-style 3DMM (mesh-condition producer) -------------------------------------------
+# The real asset (data_preprocess/FaceVerse/v3/faceverse_v3_1.npy) is not part of the reference repository; this generator
+# builds a model dict with the same keys, conventions and dimensions (150 identity + 171 expression blend shapes, eye-ball
+# vertex ranges in ``ver_inds``, per-vertex UVs) over a small dome-shaped mesh, so that the producer can be exercised end to end.
+FV_ID_DIMS, FV_EXP_DIMS, FV_TEX_DIMS = 150, 171, 251
+
+
+def faceverse_model(n=64, n_eye=12, seed=5):
+    """-> (model dict as np.load('faceverse_v3_1.npy').item() would give, face_mask [NV], trans_init [4,4])."""
+    rs = np.random.RandomState(seed)
+
+    def grid(m, cx, cy, sx, sy, z0, depth):
+        a, b = np.meshgrid(np.linspace(-1, 1, m), np.linspace(-1, 1, m))
+        x, y = cx + sx * a, cy + sy * b
+        z = z0 - depth * (1 - 0.5 * (a * a + b * b))
+        idx = np.arange(m * m).reshape(m, m)
+        t0 = np.stack([idx[:-1, :-1], idx[1:, :-1], idx[:-1, 1:]], -1).reshape(-1, 3)
+        t1 = np.stack([idx[1:, :-1], idx[1:, 1:], idx[:-1, 1:]], -1).reshape(-1, 3)
+        return np.stack([x, y, z], -1).reshape(-1, 3), np.concatenate([t0, t1]), np.stack([a, b], -1).reshape(-1, 2)
+    face_v, face_t, face_ab = grid(n, 0.0, 0.0, 0.9, 1.0, 0.0, 0.6)
+    le_v, le_t, le_ab = grid(n_eye, -0.35, -0.3, 0.12, 0.08, -0.50, 0.06)
+    re_v, re_t, re_ab = grid(n_eye, 0.35, -0.3, 0.12, 0.08, -0.50, 0.06)
+    nf, ne = face_v.shape[0], le_v.shape[0]
+    verts = np.concatenate([face_v, le_v, re_v]).astype(np.float32)
+    tri = np.concatenate([face_t, le_t + nf, re_t + nf + ne]).astype(np.int64)
+    ab = np.concatenate([face_ab, 0.12 * le_ab + [-0.35, -0.3], 0.12 * re_ab + [0.35, -0.3]]).astype(np.float32)
+    nv = verts.shape[0]
+
+    def basis(dims, amp):
+        out = np.zeros((nv, 3, dims), dtype=np.float32)
+        for j in range(dims):
+            f = rs.uniform(0.5, 3.5, size=2)
+            ph = rs.uniform(0, 2 * math.pi)
+            d = rs.randn(3).astype(np.float32)
+            d /= np.linalg.norm(d)
+            out[:, :, j] = (amp * np.sin(f[0] * ab[:, 0] + f[1] * ab[:, 1] + ph))[:, None] * d[None, :]
+        return out.reshape(nv * 3, dims)
+    model = {
+        # raw model space: the loader flips y/z, scales by 0.1 and lifts y by 1 (FaceVerseModel_v3.py:41-57); stored pre-inverted
+        'meanshape': (verts * np.array([1, -1, -1], dtype=np.float32)).reshape(-1),
+        'idBase': basis(FV_ID_DIMS, 0.02), 'exBase': basis(FV_EXP_DIMS, 0.03),
+        'tri': tri, 'ver_inds': np.array([nf, nf + ne, nf + 2 * ne], dtype=np.int64),
+        'uv_per_ver': ((ab + 1) / 2).astype(np.float32),
+    }
+    face_mask = np.concatenate([(face_ab[:, 0] ** 2 + face_ab[:, 1] ** 2 < 0.9).astype(np.float32), np.zeros(2 * ne, dtype=np.float32)])
+    trans_init = np.eye(4, dtype=np.float32)
+    trans_init[1, 3] = -1.0                      # undo the loader's y lift: the head ends up centred in the orthographic window
+    return model, face_mask, trans_init
+
+
+def faceverse_coeffs(batch, first=0, with_scale=True):
+    """Driving coefficient vectors [B, 150 + 171 + 251 + 3 + 27 + 3 + 4 (+1)] in FaceVerseModel.split_coeffs order
+    (FaceVerseModel_v3.py:139-153): small random identity / expression, eye rotations within +-0.3 rad."""
+    out = []
+    for i in range(first, first + batch):
+        rs = np.random.RandomState(3000 + i)
+        c = np.concatenate([0.5 * rs.randn(FV_ID_DIMS), 0.5 * rs.randn(FV_EXP_DIMS), np.zeros(FV_TEX_DIMS), np.zeros(3), np.zeros(27), np.zeros(3),
+                            rs.uniform(-0.3, 0.3, size=4), np.ones(1 if with_scale else 0)])
+        c[FV_ID_DIMS + FV_EXP_DIMS - 4] = 2.0          # outside the clamp range of renderer.py:48
+        out.append(c)
+    return torch.from_numpy(np.stack(out)).float()

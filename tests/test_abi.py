@@ -64,7 +64,9 @@ def _struct_fields(name):
                                           ('ia_fir_params', 'FirParams'), ('ia_torgb_params', 'TorgbParams'),
                                           ('ia_resize_params', 'ResizeParams'), ('ia_lerp_params', 'LerpParams'),
                                           ('ia_render_params', 'RenderParams'), ('ia_view', 'View'), ('ia_raster_level_params', 'RasterLevelParams'),
-                                          ('ia_enc_prep_params', 'EncPrepParams'), ('ia_enc_affine_params', 'EncAffineParams')])
+                                          ('ia_enc_prep_params', 'EncPrepParams'), ('ia_enc_affine_params', 'EncAffineParams'),
+                                          ('ia_stitch_params', 'StitchParams'), ('ia_blendshape_params', 'BlendshapeParams'),
+                                          ('ia_ortho_raster_params', 'OrthoRasterParams')])
 def test_ctypes_structs_follow_header(cname, pyname):
     from invertavatar_b200 import _C
     want = _struct_fields(cname)
