@@ -362,6 +362,11 @@ int64_t ia_render_scratch_bytes(void);
 int ia_ray_bounds(const float* cam, int64_t cam_ld, int32_t B, float* near_far, void* stream);
 int ia_ray_bounds_from_origins(const float* origins, int64_t n, float* near_far, void* stream);
 int ia_render(const ia_render_params* p, void* stream);
+/* MipRayMarcher2.run_forward (ray_marcher.py:25-57) on caller-provided samples: colors [rays][S][C], densities / depths [rays][S]
+ * (sorted along S) -> rgb [rays][C] (scaled to (-1,1), + 1 - sum w with white_back), depth [rays] = sum w d_mid / sum w (unclamped;
+ * follow with ia_depth_clamp on depth_minmax, which receives the global min / max of `depths`), weights [rays][S-1]. */
+int ia_ray_march(const float* colors, const float* densities, const float* depths, int64_t rays, int32_t S, int32_t C, int32_t white_back,
+                 float* rgb, float* depth, float* weights, float* depth_minmax, void* stream);
 /* depth = clamp(nan_to_num(depth, inf), min, max) (ray_marcher.py:49-50) */
 int ia_depth_clamp(float* depth, int64_t n, const float* depth_minmax, void* stream);
 /* Ray generation only (RaySampler_zxc API): origins/dirs [B][rays][3]. */

@@ -204,6 +204,7 @@ SIGNATURES = {
     'ia_render': (C.c_int, [C.POINTER(RenderParams), C.c_void_p]),
     'ia_render_scratch_bytes': (C.c_int64, []),
     'ia_stitch_planes': (C.c_int, [C.POINTER(StitchParams), C.c_void_p]),
+    'ia_ray_march': (C.c_int, [c_f32p, c_f32p, c_f32p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p]),
     'ia_depth_clamp': (C.c_int, [c_f32p, C.c_int64, c_f32p, C.c_void_p]),
     'ia_ray_sampler': (C.c_int, [c_f32p, C.c_int64, C.c_int32, C.c_int32, c_f32p, c_f32p, C.c_void_p]),
     'ia_enc_chan_stats': (C.c_int, [C.POINTER(View), C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),

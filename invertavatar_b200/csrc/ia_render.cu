@@ -557,6 +557,47 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1) render_kernel(const i
     }
 }
 
+// ---- standalone MipRayMarcher2 (ray_marcher.py:25-57): the generator never calls it on its own (fused into render_kernel); this is
+// the reference's module-level API for callers that march their own samples.  One thread per ray walks the S samples.
+__global__ void __launch_bounds__(128) ray_march_kernel(const float* __restrict__ colors, const float* __restrict__ sigmas, const float* __restrict__ depths,
+                                                        int64_t rays, int S, int C, int white_back, float* __restrict__ rgb, float* __restrict__ depth,
+                                                        float* __restrict__ weights, float* __restrict__ minmax) {
+    const int64_t ray = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float dmin = CUDART_INF_F, dmax = -CUDART_INF_F;
+    if (ray < rays) {
+        const float* d = depths + ray * S;
+        const float* sg = sigmas + ray * S;
+        float T = 1.0f, wsum = 0.f, dnum = 0.f;
+        for (int i = 0; i < S; ++i) { dmin = fminf(dmin, d[i]); dmax = fmaxf(dmax, d[i]); }
+        for (int i = 0; i < S - 1; ++i) {
+            const float delta = d[i + 1] - d[i];
+            const float dens = softplus_acc((sg[i] + sg[i + 1]) / 2.0f - 1.0f);
+            const float alpha = 1.0f - expf(-(dens * delta));
+            const float w = alpha * T;
+            weights[ray * (S - 1) + i] = w;
+            wsum += w; dnum += w * ((d[i] + d[i + 1]) / 2.0f);
+            T *= 1.0f - alpha + 1e-10f;
+        }
+        for (int c = 0; c < C; ++c) {
+            const float* col = colors + ray * S * C + c;
+            float acc = 0.f;
+            for (int i = 0; i < S - 1; ++i) acc = fmaf(weights[ray * (S - 1) + i], (col[(int64_t)i * C] + col[(int64_t)(i + 1) * C]) / 2.0f, acc);
+            if (white_back) acc = acc + 1.0f - wsum;
+            rgb[ray * C + c] = acc * 2.0f - 1.0f;
+        }
+        depth[ray] = dnum / wsum;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        dmin = fminf(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
+        dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+    }
+    if ((threadIdx.x & 31) == 0 && dmin <= dmax) {      // depths are positive: the int ordering of the bit patterns is the float ordering
+        atomicMin(reinterpret_cast<int*>(minmax), __float_as_int(dmin));
+        atomicMax(reinterpret_cast<int*>(minmax) + 1, __float_as_int(dmax));
+    }
+}
+
 __global__ void ray_bounds_kernel(const float* __restrict__ cam, int64_t cam_ld, int B, float* __restrict__ near_far) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     float s = 0.f;
@@ -682,6 +723,21 @@ extern "C" int ia_render(const ia_render_params* p, void* stream) {
     ia::prof_begin("ia_render", st);
     kern<<<(unsigned)grid, kWarpsPerCta * 32, smem, st>>>(*p);
     IA_LAUNCH_CHECK("ia_render");
+    return 0;
+}
+
+extern "C" int ia_ray_march(const float* colors, const float* densities, const float* depths, int64_t rays, int32_t S, int32_t C, int32_t white_back,
+                            float* rgb, float* depth, float* weights, float* depth_minmax, void* stream) {
+    IA_CHECK(colors && densities && depths && rgb && depth && weights && depth_minmax, "ia_ray_march: null argument");
+    IA_CHECK(rays >= 0 && S >= 2 && C >= 1, "ia_ray_march: need at least two samples per ray and one channel");
+    if (rays == 0) return 0;
+    cudaStream_t st = as_stream(stream);
+    ia::prof_begin("ia_ray_march(minmax_init)", st);
+    minmax_init_kernel<<<1, 32, 0, st>>>(depth_minmax);
+    IA_LAUNCH_CHECK("ia_ray_march(minmax_init)");
+    ia::prof_begin("ia_ray_march", st);
+    ray_march_kernel<<<(unsigned)cdiv(rays, 128), 128, 0, st>>>(colors, densities, depths, rays, S, C, white_back, rgb, depth, weights, depth_minmax);
+    IA_LAUNCH_CHECK("ia_ray_march");
     return 0;
 }
 

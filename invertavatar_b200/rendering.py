@@ -64,14 +64,18 @@ RaySampler = RaySampler_zxc
 
 
 class MipRayMarcher2(torch.nn.Module):
-    """API placeholder: the ray marcher (ray_marcher.py:25-57) is fused into the render kernel and never called on its own
-    by the generator forward."""
+    """ray_marcher.py:19-62.  Inside the generator the marcher is fused into the render kernel; this module is the reference's
+    standalone API (one kernel, ia_ray_march) for callers that march their own sorted samples."""
 
     def __init__(self):
         super().__init__()
 
+    def run_forward(self, colors, densities, depths, rendering_options):
+        assert rendering_options.get('clamp_mode', 'softplus') == 'softplus', 'MipRayMarcher only supports `clamp_mode`=`softplus`!'
+        return rt.ray_march(colors, densities, depths, white_back=bool(rendering_options.get('white_back', False)))
+
     def forward(self, colors, densities, depths, rendering_options):
-        raise NotImplementedError('MipRayMarcher2 is fused into ImportanceRenderer_bsMotion on this engine')
+        return self.run_forward(colors, densities, depths, rendering_options)
 
 
 def _decoder_weights(decoder):
@@ -104,6 +108,13 @@ class ImportanceRenderer_bsMotion(torch.nn.Module):
         if os.environ.get('IA_CONV_PRECISION', 'auto') == 'bf16x3':
             return rt.FMT_BF16X3
         return int(getattr(self, 'mlp_fmt', rt.FMT_BF16X3))
+
+    def run_model(self, planes, decoder, sample_coordinates, sample_directions, options):
+        """renderer.py:353-363: features of arbitrary 3-D points -> decoder outputs {'rgb', 'sigma'} (shape extraction)."""
+        if options.get('density_noise', 0) > 0:
+            raise NotImplementedError('density_noise > 0 is a training-time regulariser, not part of the inference path')
+        feats = sample_from_planes(self.plane_axes, planes, sample_coordinates, padding_mode='zeros', box_warp=options['box_warp'])
+        return decoder(feats, sample_directions)
 
     def _planes_fp16(self):
         """Whether the caller should hand render_nhwc fp16 planes (TriPlaneGenerator's storage policy; never in strict mode)."""

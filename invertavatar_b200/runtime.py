@@ -1026,6 +1026,24 @@ def raster_level(tex_nhwc, uv, stat_nhwc, crop, alpha_r, res):
 # ---------------------------------------------------------------------------------------------------
 # renderer
 # ---------------------------------------------------------------------------------------------------
+def ray_march(colors, densities, depths, white_back=False):
+    """MipRayMarcher2.run_forward (ray_marcher.py:25-57): colors [B,R,S,C], densities / depths [B,R,S,1] sorted along S ->
+    (rgb [B,R,C], depth [B,R,1] clamped to the global depth range, weights [B,R,S-1,1])."""
+    st = _enter(colors)
+    colors, densities, depths = _f32c(colors), _f32c(densities), _f32c(depths)
+    B, R, S, Cc = colors.shape
+    assert densities.numel() == B * R * S and depths.numel() == B * R * S
+    dev = colors.device
+    rgb = torch.empty((B, R, Cc), dtype=torch.float32, device=dev)
+    depth = torch.empty((B, R, 1), dtype=torch.float32, device=dev)
+    weights = torch.empty((B, R, S - 1, 1), dtype=torch.float32, device=dev)
+    mm = torch.empty(2, dtype=torch.float32, device=dev)
+    _C.check(_C.lib().ia_ray_march(_p(colors), _p(densities), _p(depths), B * R, S, Cc, 1 if white_back else 0, _p(rgb), _p(depth), _p(weights),
+                                   _p(mm), st), 'ia_ray_march')
+    _C.check(_C.lib().ia_depth_clamp(_p(depth), depth.numel(), _p(mm), st), 'ia_depth_clamp')
+    return rgb, depth, weights
+
+
 def stitch_planes(plane_img, stitch, alpha, origin, fp16=False):
     """Plane stitch (triplane_v20.py:119-128) in one pass: a copy of plane_img [B,H,W,C] fp32 NHWC (view with pixel stride >= C)
     whose plane-0 channels [0,32) inside the window at ``origin`` = (y0, x0) are stitch*alpha + plane*(1-alpha); stitch

@@ -12,6 +12,7 @@ from . import runtime as rt
 from . import stylegan2 as sg
 from . import superresolution as sr_mod
 from .rendering import ImportanceRenderer_bsMotion, RaySampler_zxc
+from .rendering import fill_mouth as rendering_fill_mouth
 from .stylegan2 import FullyConnectedLayer
 from .stylegan2 import Generator as StyleGAN2Backbone_cond
 
@@ -364,6 +365,45 @@ class TriPlaneGenerator(torch.nn.Module):
             out['static'] = static_feats
             out['texture'] = texture_feats
         return out
+
+    def _blended_planes(self, ws, mesh_condition, synthesis_kwargs):
+        """The tri-planes a frame is rendered from (backbones -> rasterize -> face backbone -> stitch), fp32 [B,3,32,256,256]."""
+        noise_kwargs = {k: v for k, v in synthesis_kwargs.items() if k in ('noise_mode',)}
+        texture_feats = self.texture_backbone.synthesis(ws, cond_list=None, return_list=True, **noise_kwargs)
+        static_feats = self.backbone.synthesis(ws, cond_list=None, return_list=True, **noise_kwargs)
+        tex = [rt.to_nhwc(t) for t in texture_feats]
+        static_views, plane_img = self._static_views(static_feats)
+        conds, full_alpha, _ = self._rasterize_nhwc(tex, mesh_condition['uvcoords_image'], static_views, BBOX_256, levels=(0, 1, 2, 3))
+        stitch = rt.to_nhwc(self.face_backbone.synthesis(ws, cond_list=conds[:4], return_list=False, **noise_kwargs))
+        b0, b1, b2, b3 = BBOX_256
+        planes = rt.stitch_planes(plane_img, rt.resize_aa(stitch, 128, 128), rt.resize_aa(full_alpha.unsqueeze(-1), 128, 128).squeeze(-1),
+                                  (b0, b2), fp16=False)
+        N = ws.shape[0]
+        return rt.from_nhwc(planes).reshape(N, 3, 32, planes.shape[1], planes.shape[2])
+
+    def sample(self, coordinates, directions, z, c, mesh_condition, truncation_psi=1, truncation_cutoff=None, update_emas=False,
+               **synthesis_kwargs):
+        """triplane_v20.py:341-371: decoder outputs {'rgb', 'sigma'} at arbitrary 3-D coordinates [B,M,3] (shape extraction)."""
+        ws = self.mapping(z, c, truncation_psi=truncation_psi, truncation_cutoff=truncation_cutoff, update_emas=update_emas)
+        return self.sample_mixed(coordinates, directions, ws, mesh_condition, update_emas=update_emas, **synthesis_kwargs)
+
+    def sample_mixed(self, coordinates, directions, ws, mesh_condition, truncation_psi=1, truncation_cutoff=None, update_emas=False,
+                     **synthesis_kwargs):
+        """triplane_v20.py:373-402: as ``sample`` but from W+ latents."""
+        planes = self._blended_planes(ws, mesh_condition, synthesis_kwargs)
+        return self.renderer.run_model(planes, self.decoder, coordinates, directions, self.rendering_kwargs)
+
+    def visualize_mesh_condition(self, mesh_condition, to_imgs=False):
+        """triplane_v20.py:71-87: the UV-coordinate image [B,3,H,W] with everything outside the mouth-filled mask set to -1
+        (uint8 PIL images with to_imgs=True)."""
+        uv = mesh_condition['uvcoords_image'].clone().permute(0, 3, 1, 2)
+        full_alpha, _ = rendering_fill_mouth(uv[:, 2:].clone(), blur_mouth_edge=False)
+        if not to_imgs:
+            return uv
+        uv[full_alpha.expand(-1, 3, -1, -1) == 0] = -1
+        u8 = ((uv + 1) * 127.5).to(dtype=torch.uint8).cpu()
+        from PIL import Image
+        return [Image.fromarray(img.permute(1, 2, 0).numpy()) for img in u8]
 
     def forward(self, z, c, v, truncation_psi=1, truncation_cutoff=None, neural_rendering_resolution=None, update_emas=False,
                 cache_backbone=False, use_cached_backbone=False, **synthesis_kwargs):

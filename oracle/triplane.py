@@ -146,3 +146,30 @@ def synthesis_with_texture(sd, ws, texture_feats, c, uvcoords_image, rendering_k
         static_feats = sg.synthesis_network(sg.sub(sd, 'backbone.synthesis'), ws, return_list=True)
     return _stitch_render_sr(sd, ws, c, uvcoords_image, texture_feats, static_feats, rendering_kwargs, jitter,
                              evaluation, u, neural_rendering_resolution, stages)
+
+
+def sample_mixed(sd, coordinates, ws, uvcoords_image, rendering_kwargs):
+    """triplane_v20.py:373-402 (= ``sample`` after the mapping, :341-371): decoder outputs at arbitrary 3-D points, from the
+    blended tri-planes of the frame; ``run_model`` (renderer.py:353-363) without density noise.  Returns (rgb, sigma)."""
+    texture_feats = sg.synthesis_network(sg.sub(sd, 'texture_backbone.synthesis'), ws, return_list=True)
+    static_raw = sg.synthesis_network(sg.sub(sd, 'backbone.synthesis'), ws, return_list=True)
+    static_feats, static_plane = _split_static(static_raw)
+    rendering_images, full_alpha, _ = rasterize(texture_feats, uvcoords_image, static_feats)
+    stitch = sg.synthesis_network(sg.sub(sd, 'face_backbone.synthesis'), ws, cond_list=rendering_images, return_list=False)
+    b0, b1, b2, b3 = BBOX_256
+    stitch_, alpha_ = torch.zeros_like(stitch), torch.zeros_like(full_alpha)
+    stitch_[:, :, b0:b1, b2:b3] = F.interpolate(stitch, size=(128, 128), mode='bilinear', antialias=True)
+    alpha_[:, :, b0:b1, b2:b3] = F.interpolate(full_alpha, size=(128, 128), mode='bilinear', antialias=True)
+    alpha3 = torch.cat((alpha_, torch.zeros_like(alpha_), torch.zeros_like(alpha_)), 1).unsqueeze(2)
+    stitch3 = torch.cat((stitch_, torch.zeros_like(stitch_), torch.zeros_like(stitch_)), 1).view(*static_plane.shape)
+    planes = stitch3 * alpha3 + static_plane * (1 - alpha3)
+    feats = rd.sample_from_planes(planes, coordinates, rendering_kwargs['box_warp'])
+    return rd.osg_decoder(sg.sub(sd, 'decoder'), feats)
+
+
+def visualize_mesh_condition(uvcoords_image):
+    """triplane_v20.py:71-87 with to_imgs=True, up to the PIL conversion: uint8 [B,3,H,W]."""
+    uv = uvcoords_image.clone().permute(0, 3, 1, 2)
+    full_alpha, _ = fill_mouth(uv[:, 2:].clone())
+    uv[full_alpha.expand(-1, 3, -1, -1) == 0] = -1
+    return ((uv + 1) * 127.5).to(dtype=torch.uint8)

@@ -113,3 +113,20 @@ def test_renderer_properties_full_size():
     assert float((feat - expect).abs().max()) <= 1e-5
     near = 2.7 - 0.45
     assert float(depth.min()) >= near - 1e-4 and float(depth.max()) <= 2.7 + 0.6 + 1e-4
+
+
+@pytest.mark.parametrize('white', [False, True])
+def test_ray_marcher_standalone_vs_oracle(white):
+    """MipRayMarcher2 on caller-provided sorted samples (ray_marcher.py:25-57) -- the module-level API; inside the generator the
+    marcher is fused into the render kernel."""
+    from invertavatar_b200.rendering import MipRayMarcher2
+    g = torch.Generator().manual_seed(11)
+    B, R, S, C = 2, 333, 24, 32
+    depths = (2.2 + torch.rand(B, R, S, 1, generator=g)).sort(dim=2).values
+    colors = torch.rand(B, R, S, C, generator=g)
+    dens = torch.randn(B, R, S, 1, generator=g) * 3
+    dens[0, :7] = -30.0            # empty rays: sum of weights ~ 0 -> depth NaN/inf -> clamped to the global range
+    rgb, depth, w = MipRayMarcher2()(colors.to(DEV), dens.to(DEV), depths.to(DEV), {'clamp_mode': 'softplus', 'white_back': white})
+    r_rgb, r_depth, r_w = o_rd.ray_march(colors, dens, depths, white_back=white)
+    assert tuple(rgb.shape) == (B, R, C) and tuple(depth.shape) == (B, R, 1) and tuple(w.shape) == (B, R, S - 1, 1)
+    assert maxerr(w, r_w) <= 2e-6 and maxerr(rgb, r_rgb) <= 1e-5 and maxerr(depth, r_depth) <= 1e-5

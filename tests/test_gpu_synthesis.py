@@ -180,3 +180,33 @@ def test_synthesis_sweep_vs_oracle(res, D):
     assert tuple(out['image_raw'].shape) == (1, 3, res, res)
     assert err <= IMAGE_ATOL and p > 50.0
     assert float((out['image_depth'].cpu() - ref['image_depth']).abs().max()) <= 1e-3
+
+
+def test_sample_mixed_and_visualize_vs_oracle():
+    """Shape-extraction API (triplane_v20.py:341-402: decoder outputs at arbitrary 3-D points of the frame's blended tri-planes) and
+    visualize_mesh_condition (:71-87) against the oracle; strict 3-term convolutions, so the density field is held to 2e-4."""
+    import copy
+    import os
+    os.environ['IA_CONV_PRECISION'] = 'bf16x3'
+    try:
+        G = copy.deepcopy(build_generator(16, 16)).to(DEV)
+        z, cond, uv = synth.latents(1), synth.frontal_camera(1), synth.uvcoords_image(1)
+        pts = (torch.rand(1, 5000, 3, generator=torch.Generator().manual_seed(3)) - 0.5) * 1.1      # a few points outside the box
+        with torch.no_grad():
+            ws = G.mapping(z.to(DEV), cond.to(DEV), truncation_psi=0.7, truncation_cutoff=14)
+            out = G.sample_mixed(pts.to(DEV), torch.zeros_like(pts).to(DEV), ws, {'uvcoords_image': uv.to(DEV)}, noise_mode='const')
+            out2 = G.sample(pts.to(DEV), torch.zeros_like(pts).to(DEV), z.to(DEV), cond.to(DEV), {'uvcoords_image': uv.to(DEV)},
+                            truncation_psi=0.7, truncation_cutoff=14, noise_mode='const')
+            sd = {k: v.cpu() for k, v in G.state_dict().items()}
+            rgb, sigma = o_tp.sample_mixed(sd, pts, ws.cpu(), uv, G.rendering_kwargs)
+    finally:
+        os.environ.pop('IA_CONV_PRECISION', None)
+    assert tuple(out['rgb'].shape) == (1, 5000, 32) and tuple(out['sigma'].shape) == (1, 5000, 1)
+    e_rgb, e_sig = float((out['rgb'].cpu() - rgb).abs().max()), float((out['sigma'].cpu() - sigma).abs().max())
+    print(f'sample_mixed: rgb {e_rgb:.2e} sigma {e_sig:.2e} (sigma range {float(sigma.abs().max()):.2f})')
+    assert e_rgb <= 2e-4 and e_sig <= 2e-4 * max(1.0, float(sigma.abs().max()))
+    assert torch.equal(out2['sigma'], out['sigma'])
+    vis = G.visualize_mesh_condition({'uvcoords_image': uv.to(DEV)}, to_imgs=True)
+    ref = o_tp.visualize_mesh_condition(uv)
+    assert len(vis) == 1 and np.array_equal(np.asarray(vis[0]), ref[0].permute(1, 2, 0).numpy())
+    assert tuple(G.visualize_mesh_condition({'uvcoords_image': uv.to(DEV)}).shape) == (1, 3, 256, 256)
