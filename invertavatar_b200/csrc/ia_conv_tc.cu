@@ -110,15 +110,68 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-// Cluster-of-2 variant: one CTA loads a weight tile for both (TMA multicast), and every CTA's MMA warp releases a weight
-// slot in both CTAs (commit with a multicast arrive), so a slot is refilled only after both consumers are done with it.
-__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
-        ::"r"(dst), "l"(map), "r"(bar), "h"(mask), "r"(c0), "r"(c1) : "memory");
+// CTA-pair variant (tcgen05 cta_group::2): the two CTAs of a cluster (one TPC) execute ONE M=256 MMA per instruction -- 128 pixel
+// rows from each CTA's shared memory, the weight tile split between them (each CTA stages and reads half of its rows), 128 TMEM
+// lanes of accumulator in each.  Only the leader (cluster rank 0) issues MMAs; both CTAs' TMA loads signal the leader's "full"
+// barriers (.cta_group::2 form with the barrier address mapped into the leader), the leader's commits release the slots /
+// publish the accumulators in both CTAs (multicast arrive), and both CTAs' epilogue warps release an accumulator buffer on the
+// leader's barrier.
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
 }
-__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {      // arrives on `bar` (same offset) in both CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
+// One lane of a converged warp (the issuer of the asynchronous tensor-core / TMA instructions).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+// MMA from the low words of the two shared-memory descriptors (address >> 4 | LBO) and their common high word.
+template <bool PAIR>
+__device__ __forceinline__ void umma_issue(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t accumulate) {
+    if (PAIR) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+            "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+            "setp.ne.b32 p, %5, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}"
+            ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate) : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+            "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+            "setp.ne.b32 p, %5, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+            ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate) : "memory");
+    }
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -417,7 +470,11 @@ struct Tc2Params {
     int act; float alpha, gain, clamp;
     ia_emit emit;
     int groups, ipg, n_taps_total; long long noise_gstride;   // grouped launch (see ia_conv_params)
-    int m_tiles_p, total_pairs;    // cluster variant: m_tiles rounded up to even; (m_tiles_p * n_tiles) / 2 tile pairs
+    // CTA-pair variant: the schedule of the plain variant with every (chunk, sub-problem, N tile) list of ic * T tiles padded to an
+    // even length, so that the two CTAs of a pair always hold two tiles of the same sub-problem and N tile
+    int pp_cum[5];                 // pp_cum[q] = sum_{k<q} ceil(ic * T_k / 2)
+    int chunk_pairs, total_pairs;  // n_tiles * pp_cum[nph]; (B / ic) * chunk_pairs
+    uint32_t b_half_tx;            // bytes of the half weight tile one CTA of a pair stages
     // balanced schedule (plain variant): tiles ordered (image chunk, sub-problem, N tile, image, tile) with the sub-problems by
     // descending tap count, only real tiles enumerated -- see decode()
     int ic, chunk_tiles;           // images per chunk; schedule entries of one chunk = ic * n_tiles * ph_cum[nph]
@@ -636,8 +693,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.a_slots; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
-        for (int s = 0; s < p.b_slots; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), CL ? 2 : 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(t_full(s), 1); mbar_init(t_empty(s), kEpiWarps2); }
+        for (int s = 0; s < p.b_slots; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+        // pair: the leader's t_empty collects the epilogue warps of both CTAs
+        for (int s = 0; s < 2; ++s) { mbar_init(t_full(s), 1); mbar_init(t_empty(s), CL ? 2 * kEpiWarps2 : kEpiWarps2); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -645,8 +703,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         prefetch_tmap(&tm_a_hi); prefetch_tmap(&tm_a_lo); prefetch_tmap(&tm_w_hi); prefetch_tmap(&tm_w_lo);
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (CL) {       // the same warp of both CTAs allocates (and frees) the pair's tensor memory
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -656,9 +719,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
     const int th_half = p.TH >> 1;
-    // tile schedule.  Plain: CTA b takes tiles b, b+grid, ...  Cluster: the pair (2q, 2q+1) takes tile pairs q, q+grid/2, ...;
-    // both tiles of a pair share the N tile (m_tiles is padded to even: a padding tile recomputes the last M tile and
-    // stores nothing), so the weight tiles of the pair are identical and are loaded once.
+    // tile schedule.  Plain: CTA b takes tiles b, b+grid, ...  Pair: the CTAs (2q, 2q+1) take tile pairs q, q+grid/2, ...; both
+    // tiles of a pair belong to the same sub-problem and N tile (every such list is padded to an even length: a padding tile
+    // recomputes the list's last tile and stores nothing), so one M=256 MMA serves both.
     const uint32_t crank = CL ? cluster_ctarank() : 0u;
     const int it_first = CL ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     const int it_step = CL ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -667,15 +730,21 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     // position outside this sub-problem's grid) is not executed at all -- every role takes the same decision.
     auto decode = [&](int it, int& n_idx, int& img, int& txi, int& tyi, int& pi, bool& null_tile, bool& skip) {
         if (CL) {
-            const int lin = 2 * it + (int)crank;
-            n_idx = lin / p.m_tiles_p;
-            int m = lin - n_idx * p.m_tiles_p;
-            null_tile = m >= p.m_tiles;
-            if (null_tile) m = p.m_tiles - 1;
-            pi = 0;                                   // (the cluster variant is launched for single sub-problems only)
-            txi = m % p.S_tx; m /= p.S_tx;
-            tyi = m % p.S_ty; img = m / p.S_ty;
             skip = false;
+            const int ch = it / p.chunk_pairs;
+            int r = it - ch * p.chunk_pairs;
+            pi = 0;
+            while (pi + 1 < p.nph && r >= p.n_tiles * p.pp_cum[pi + 1]) ++pi;
+            r -= p.n_tiles * p.pp_cum[pi];
+            const int Lp = p.pp_cum[pi + 1] - p.pp_cum[pi];
+            n_idx = r / Lp; r -= n_idx * Lp;
+            const int T = p.ph_cum[pi + 1] - p.ph_cum[pi];
+            int lin = 2 * r + (int)crank;
+            null_tile = lin >= p.ic * T;
+            if (null_tile) lin = p.ic * T - 1;
+            const int il = lin / T; lin -= il * T;
+            img = ch * p.ic + il;
+            tyi = lin / p.ph[pi].tiles_x; txi = lin - tyi * p.ph[pi].tiles_x;
             return;
         }
         // Static round-robin over a cost-sorted tile list: inside a chunk of p.ic images all tiles of the 4-tap sub-problem come
@@ -705,60 +774,83 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         kc1 = min(kc0 + p.kc_per, p.Cin_blocks);
     };
 
+    // The producer and the MMA issuer run their loops with the WHOLE warp (every value is warp-uniform and lives in uniform
+    // registers) and let one elected lane issue the asynchronous instructions.  Running the loop inside `if (lane == 0)` makes
+    // the control flow divergent: every UTCHMMA / UTMALDG operand then sits in a vector register and is moved to the uniform
+    // datapath through an R2UR + ELECT + BRA.U.ANY waterfall -- ~430 SASS instructions per weight slot, which bound the MMA
+    // warp's issue rate well below the tensor pipe (ncu source view, profiles/r2_conv_mma_issue.txt).
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
-            uint32_t a_it = 0, b_it = 0;
-            for (int it = it_first; it < it_end; it += it_step) {
-                int n_idx, img, txi, tyi, pi; bool null_tile, skip;
-                decode(it, n_idx, img, txi, tyi, pi, null_tile, skip);
-                if (skip) continue;
-                const Tc2Phase& ph = p.ph[pi];
-                const int x0 = txi * p.tw, y0 = tyi * p.TH, col0 = n_idx * p.n_tile;
-                int kc0, kc1;
-                kc_range(it, kc0, kc1);
-                for (int kc = kc0; kc < kc1; ++kc) {
-                    for (int g = 0; g < ph.ngroups; ++g) {
-                        const int as = (int)(a_it % (uint32_t)p.a_slots);
-                        mbar_wait(a_empty(as), ((a_it / (uint32_t)p.a_slots) & 1u) ^ 1u);
-                        const uint32_t sa = a_base + (uint32_t)as * a_slot_bytes;
-                        mbar_expect_tx(a_full(as), nops * p.a_tx);
-                        tma_load_4d(sa, &tm_a_hi, a_full(as), kc * BK, x0 + ph.g_dx[g], y0 + p.dy_min, img);
-                        if (nops == 2u) tma_load_4d(sa + p.a_bytes, &tm_a_lo, a_full(as), kc * BK, x0 + ph.g_dx[g], y0 + p.dy_min, img);
-                        ++a_it;
-                        for (int t = ph.g_first[g]; t < ph.g_first[g + 1]; ++t) {
-                            const int bs = (int)(b_it % (uint32_t)p.b_slots);
-                            mbar_wait(b_empty(bs), ((b_it / (uint32_t)p.b_slots) & 1u) ^ 1u);
-                            const uint32_t sb = b_base + (uint32_t)bs * b_slot_bytes;
-                            mbar_expect_tx(b_full(bs), nops * p.b_tx);
-                            const int wrow = ((img / p.ipg) * p.n_taps_total + ph.t_wtap[t]) * p.Cout_pad + col0;
-                            if (CL) {     // both CTAs armed their own barrier above; rank 0 fetches the tile for both
-                                if (crank == 0) {
-                                    tma_load_2d_mc(sb, &tm_w_hi, b_full(bs), kc * BK, wrow, (uint16_t)3);
-                                    if (nops == 2u) tma_load_2d_mc(sb + p.b_bytes, &tm_w_lo, b_full(bs), kc * BK, wrow, (uint16_t)3);
-                                }
+        const bool el = elect_one();
+        uint32_t as = 0, a_par = 1, bs = 0, b_par = 1;      // ring slot + the parity to wait for on its "empty" barrier
+        const uint32_t a_tx = (CL ? 2u : 1u) * nops * p.a_tx, b_tx = CL ? 2u * nops * p.b_half_tx : nops * p.b_tx;
+        for (int it = it_first; it < it_end; it += it_step) {
+            int n_idx, img, txi, tyi, pi; bool null_tile, skip;
+            decode(it, n_idx, img, txi, tyi, pi, null_tile, skip);
+            if (skip) continue;
+            const Tc2Phase& ph = p.ph[pi];
+            const int x0 = txi * p.tw, y0 = tyi * p.TH, col0 = n_idx * p.n_tile;
+            const int wrow_base = (img / p.ipg) * p.n_taps_total;
+            int kc0, kc1;
+            kc_range(it, kc0, kc1);
+            for (int kc = kc0; kc < kc1; ++kc) {
+                for (int g = 0; g < ph.ngroups; ++g) {
+                    mbar_wait(a_empty(as), a_par);
+                    const uint32_t sa = a_base + as * a_slot_bytes;
+                    if (el) {
+                        if (CL) {     // the leader arms its barrier for the bytes of both CTAs; both load their own pixel tile
+                            if (crank == 0) mbar_expect_tx(a_full(as), a_tx);
+                            const uint32_t lbar = mapa_rank(a_full(as), 0u);
+                            tma_load_4d_pair(sa, &tm_a_hi, lbar, kc * BK, x0 + ph.g_dx[g], y0 + p.dy_min, img);
+                            if (nops == 2u) tma_load_4d_pair(sa + p.a_bytes, &tm_a_lo, lbar, kc * BK, x0 + ph.g_dx[g], y0 + p.dy_min, img);
+                        } else {
+                            mbar_expect_tx(a_full(as), a_tx);
+                            tma_load_4d(sa, &tm_a_hi, a_full(as), kc * BK, x0 + ph.g_dx[g], y0 + p.dy_min, img);
+                            if (nops == 2u) tma_load_4d(sa + p.a_bytes, &tm_a_lo, a_full(as), kc * BK, x0 + ph.g_dx[g], y0 + p.dy_min, img);
+                        }
+                    }
+                    if (++as == (uint32_t)p.a_slots) { as = 0; a_par ^= 1u; }
+                    for (int t = ph.g_first[g]; t < ph.g_first[g + 1]; ++t) {
+                        mbar_wait(b_empty(bs), b_par);
+                        const uint32_t sb = b_base + bs * b_slot_bytes;
+                        const int wrow = (wrow_base + ph.t_wtap[t]) * p.Cout_pad + col0;
+                        if (el) {
+                            if (CL) {     // every CTA stages its half of the weight rows (rank r: rows [r, r + 1) * n_tile / 2)
+                                if (crank == 0) mbar_expect_tx(b_full(bs), b_tx);
+                                const uint32_t lbar = mapa_rank(b_full(bs), 0u);
+                                const int hrow = wrow + (int)crank * (p.n_tile >> 1);
+                                tma_load_2d_pair(sb, &tm_w_hi, lbar, kc * BK, hrow);
+                                if (nops == 2u) tma_load_2d_pair(sb + p.b_bytes, &tm_w_lo, lbar, kc * BK, hrow);
                             } else {
+                                mbar_expect_tx(b_full(bs), b_tx);
                                 tma_load_2d(sb, &tm_w_hi, b_full(bs), kc * BK, wrow);
                                 if (nops == 2u) tma_load_2d(sb + p.b_bytes, &tm_w_lo, b_full(bs), kc * BK, wrow);
                             }
-                            ++b_it;
                         }
+                        if (++bs == (uint32_t)p.b_slots) { bs = 0; b_par ^= 1u; }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            const uint32_t idesc = (1u << 4) | p.idesc_fmt | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-            uint32_t a_it = 0, b_it = 0, j = 0;
-            int mma_pi = 0;
+        // ===================== MMA issuer (pair: the leader CTA only) =====================
+        if (crank == 0u) {
+            const bool el = elect_one();
+            // instruction descriptor: D = f32, A/B format, both K-major, N = n_tile, M = 128 (256 across the pair)
+            const uint32_t idesc = (1u << 4) | p.idesc_fmt | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)((CL ? 2 * kTileM : kTileM) >> 4) << 24);
+            // shared-memory descriptors: the high word is constant, the low word is (address >> 4) | LBO
+            const uint32_t desc_hi = (uint32_t)(make_kmajor_desc<BK>(0u) >> 32);
+            auto dlo = [](uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); };
+            uint32_t as = 0, a_par = 0, bs = 0, b_par = 0, j = 0;
+            const uint32_t row_bytes = (uint32_t)BK * 2u;
+            const uint32_t a_lo_off = p.a_bytes >> 4, b_lo_off = p.b_bytes >> 4;       // hi -> lo tile, in descriptor units
+            const uint32_t half_off = ((uint32_t)(th_half * p.tw) * row_bytes) >> 4;  // first -> second 128-pixel half
             for (int it = it_first; it < it_end; it += it_step) {
+                int mma_pi;
                 {
-                    int n_idx, img, txi, tyi, pi_; bool null_tile, skip;
-                    decode(it, n_idx, img, txi, tyi, pi_, null_tile, skip);
+                    int n_idx, img, txi, tyi; bool null_tile, skip;
+                    decode(it, n_idx, img, txi, tyi, mma_pi, null_tile, skip);
                     if (skip) continue;
-                    mma_pi = pi_;
                 }
                 const Tc2Phase& ph = p.ph[mma_pi];
                 const uint32_t acc = j & 1u;
@@ -766,51 +858,46 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                 tc_fence_after();
                 const uint32_t d0 = tmem_base + (acc * 2u + 0u) * (uint32_t)p.acc_stride;
                 const uint32_t d1 = tmem_base + (acc * 2u + 1u) * (uint32_t)p.acc_stride;
-                bool first = true;
+                uint32_t accum = 0u;
                 int kc0, kc1;
                 kc_range(it, kc0, kc1);
                 for (int kc = kc0; kc < kc1; ++kc) {
                     for (int g = 0; g < ph.ngroups; ++g) {
-                        const int as = (int)(a_it % (uint32_t)p.a_slots);
-                        mbar_wait(a_full(as), (a_it / (uint32_t)p.a_slots) & 1u);
-                        const uint32_t sa = a_base + (uint32_t)as * a_slot_bytes;
+                        mbar_wait(a_full(as), a_par);
+                        const uint32_t a_lo0 = dlo(a_base + as * a_slot_bytes);
                         for (int t = ph.g_first[g]; t < ph.g_first[g + 1]; ++t) {
-                            const int bs = (int)(b_it % (uint32_t)p.b_slots);
-                            mbar_wait(b_full(bs), (b_it / (uint32_t)p.b_slots) & 1u);
+                            mbar_wait(b_full(bs), b_par);
                             tc_fence_after();
-                            const uint32_t sb = b_base + (uint32_t)bs * b_slot_bytes;
-                            const uint64_t b_hi = make_kmajor_desc<BK>(sb);
-                            const uint64_t b_lo = make_kmajor_desc<BK>(sb + p.b_bytes);
-                            const uint32_t row_bytes = (uint32_t)BK * 2u;
-                            const uint32_t off0 = (uint32_t)(ph.t_dyoff[t] * p.tw) * row_bytes;
-                            const uint32_t off1 = (uint32_t)((th_half + ph.t_dyoff[t]) * p.tw) * row_bytes;
-                            const uint64_t a0_hi = make_kmajor_desc<BK>(sa + off0), a0_lo = make_kmajor_desc<BK>(sa + p.a_bytes + off0);
-                            const uint64_t a1_hi = make_kmajor_desc<BK>(sa + off1), a1_lo = make_kmajor_desc<BK>(sa + p.a_bytes + off1);
+                            const uint32_t b_hi = dlo(b_base + bs * b_slot_bytes);
+                            const uint32_t a0_hi = a_lo0 + (((uint32_t)(ph.t_dyoff[t] * p.tw) * row_bytes) >> 4);
+                            const uint32_t a1_hi = a0_hi + half_off;
+                            if (el) {
 #pragma unroll
-                            for (int k = 0; k < BK / 16; ++k) {
-                                const uint64_t koff = (uint64_t)((k * 32) >> 4);
-                                const uint32_t accum = first ? 0u : 1u;
-                                if (nops == 2u) {
-                                    umma_bf16(d0, a0_hi + koff, b_hi + koff, idesc, accum);
-                                    umma_bf16(d0, a0_hi + koff, b_lo + koff, idesc, 1u);
-                                    umma_bf16(d0, a0_lo + koff, b_hi + koff, idesc, 1u);
-                                    umma_bf16(d1, a1_hi + koff, b_hi + koff, idesc, accum);
-                                    umma_bf16(d1, a1_hi + koff, b_lo + koff, idesc, 1u);
-                                    umma_bf16(d1, a1_lo + koff, b_hi + koff, idesc, 1u);
-                                } else {
-                                    umma_bf16(d0, a0_hi + koff, b_hi + koff, idesc, accum);
-                                    umma_bf16(d1, a1_hi + koff, b_hi + koff, idesc, accum);
+                                for (int k = 0; k < BK / 16; ++k) {
+                                    const uint32_t ko = (uint32_t)(k * 2);          // +32 bytes per 16-element K step
+                                    if (nops == 2u) {
+                                        umma_issue<CL>(d0, a0_hi + ko, b_hi + ko, desc_hi, idesc, accum);
+                                        umma_issue<CL>(d0, a0_hi + ko, b_hi + b_lo_off + ko, desc_hi, idesc, 1u);
+                                        umma_issue<CL>(d0, a0_hi + a_lo_off + ko, b_hi + ko, desc_hi, idesc, 1u);
+                                        umma_issue<CL>(d1, a1_hi + ko, b_hi + ko, desc_hi, idesc, accum);
+                                        umma_issue<CL>(d1, a1_hi + ko, b_hi + b_lo_off + ko, desc_hi, idesc, 1u);
+                                        umma_issue<CL>(d1, a1_hi + a_lo_off + ko, b_hi + ko, desc_hi, idesc, 1u);
+                                    } else {
+                                        umma_issue<CL>(d0, a0_hi + ko, b_hi + ko, desc_hi, idesc, accum);
+                                        umma_issue<CL>(d1, a1_hi + ko, b_hi + ko, desc_hi, idesc, accum);
+                                    }
+                                    accum = 1u;
                                 }
-                                first = false;
+                                if (CL) umma_commit_pair(b_empty(bs)); else umma_commit(b_empty(bs));
                             }
-                            if (CL) umma_commit_mc(b_empty(bs), (uint16_t)3); else umma_commit(b_empty(bs));
-                            ++b_it;
+                            accum = 1u;
+                            if (++bs == (uint32_t)p.b_slots) { bs = 0; b_par ^= 1u; }
                         }
-                        umma_commit(a_empty(as));
-                        ++a_it;
+                        if (el) { if (CL) umma_commit_pair(a_empty(as)); else umma_commit(a_empty(as)); }
+                        if (++as == (uint32_t)p.a_slots) { as = 0; a_par ^= 1u; }
                     }
                 }
-                umma_commit(t_full(acc));
+                if (el) { if (CL) umma_commit_pair(t_full(acc)); else umma_commit(t_full(acc)); }
                 ++j;
             }
         }
@@ -886,7 +973,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                     }
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(t_empty(acc)) : "memory");
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(t_empty(acc)) : "memory");     // (split-K: never a pair launch)
                     released_any = true;
                     vmask_done = true;
                     if (vmask != 0u) {      // (vmask depends on the tile only: all splits of a tile take the same branch)
@@ -1016,16 +1103,20 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
             }
             tc_fence_before();
             __syncwarp();
-            if (!released_any && lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(t_empty(acc)) : "memory");
+            if (!released_any && lane == 0) {
+                if (CL) mbar_arrive_cluster(mapa_rank(t_empty(acc), 0u));      // the leader's MMA warp waits for both CTAs' epilogues
+                else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(t_empty(acc)) : "memory");
+            }
             ++j;
         }
     }
 
     __syncthreads();
-    if (CL) cluster_sync_all();      // no CTA leaves while its peer may still multicast into it or arrive on its barriers
+    if (CL) cluster_sync_all();      // no CTA leaves while its peer may still read its tiles or arrive on its barriers
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        if (CL) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
@@ -1159,6 +1250,14 @@ int launch_v2(const ia_conv_params* const* ps, int nph, void* stream) {
     }
     t.ksplit = ksplit;
     if (ksplit <= 1) { t.ksplit = 1; t.kc_per = p->Cin_pad / BK; }
+    // CTA-pair launch (tcgen05 cta_group::2; IA_CONV_PAIR=0 disables): M = 256 MMAs over two CTAs' pixel tiles with the weight tile
+    // split between them -- half the weight bytes staged and read per CTA.  Needs at least one tile pair per SM pair, one weight
+    // group, no split-K.
+    static int pair_env = -1;
+    if (pair_env < 0) { const char* ev = getenv("IA_CONV_PAIR"); pair_env = ev ? atoi(ev) : 1; }
+    static int pair_min_tiles = -1;      // IA_CONV_PAIR_MIN_TILES: fewest (M tile, N tile) entries of a pair launch, in units of SMs x 1/4
+    if (pair_min_tiles < 0) { const char* ev = getenv("IA_CONV_PAIR_MIN_TILES"); pair_min_tiles = ev ? atoi(ev) : 4; }
+    bool use_pair = pair_env != 0 && p->groups <= 1 && t.ksplit <= 1 && real_tiles * (p->Cout_pad / n_tile) * 4 >= (int64_t)g_sm_count * pair_min_tiles;
     t.ws = reinterpret_cast<float4*>(p->splitk_ws); t.cnt = p->splitk_counters;
     t.n_tile = n_tile; t.acc_stride = 128;
     t.n_tiles = p->Cout_pad / n_tile;
@@ -1198,6 +1297,8 @@ int launch_v2(const ia_conv_params* const* ps, int nph, void* stream) {
     t.a_tx = (uint32_t)a_rows * BK * 2u;
     t.a_bytes = (t.a_tx + 1023u) & ~1023u;
     t.b_tx = (uint32_t)n_tile * BK * 2u;
+    t.b_half_tx = t.b_tx >> 1;
+    if (use_pair) t.b_tx = t.b_half_tx;      // a pair CTA's weight slot holds its half of the tile
     t.b_bytes = (t.b_tx + 1023u) & ~1023u;
     const uint32_t kEpiBytes = (uint32_t)kEpiWarps2 * 32u * (uint32_t)kTsmLd * 4u;
     const uint32_t budget = 227u * 1024u - 1024u - 512u - kEpiBytes;
@@ -1214,6 +1315,8 @@ int launch_v2(const ia_conv_params* const* ps, int nph, void* stream) {
         t.ksplit = 1; t.kc_per = p->Cin_pad / BK;      // (the split plan was sized for the wider tile)
         t.n_tile = n_tile; t.n_tiles = p->Cout_pad / n_tile; t.total_tiles = t.m_tiles * t.n_tiles;
         t.b_tx = (uint32_t)n_tile * BK * 2u;
+        t.b_half_tx = t.b_tx >> 1;
+        if (use_pair) t.b_tx = t.b_half_tx;
         t.b_bytes = (t.b_tx + 1023u) & ~1023u;
     }
     IA_CHECK(nops * (2u * t.a_bytes + 2u * t.b_bytes) <= budget, "ia_conv_tc(v2): tile does not fit shared memory");
@@ -1267,10 +1370,14 @@ int launch_v2(const ia_conv_params* const* ps, int nph, void* stream) {
             for (int i = 0; i < gg; ++i) mx = load[i] > mx ? load[i] : mx;
             if (best_max < 0 || mx < best_max) { best_max = mx; best_ic = ic; }
         }
-        if (nph == 1) best_ic = 1;
+        if (nph == 1) best_ic = use_pair ? t.B : 1;      // (pair: one list per N tile, so at most one padding tile each)
         t.ic = best_ic;
         t.chunk_tiles = t.ic * t.n_tiles * t.ph_cum[nph];
         t.total_tiles = (int)total;
+        t.pp_cum[0] = 0;
+        for (int q = 0; q < nph; ++q) t.pp_cum[q + 1] = t.pp_cum[q] + (t.ic * (t.ph_cum[q + 1] - t.ph_cum[q]) + 1) / 2;
+        t.chunk_pairs = t.n_tiles * t.pp_cum[nph];
+        t.total_pairs = (t.B / t.ic) * t.chunk_pairs;
     }
     t.OH = p->OH; t.OW = p->OW; t.sy = p->sy; t.sx = p->sx; t.py = p->py; t.px = p->px;
     t.mode = p->mode; t.dcoef = p->dcoef; t.noise = p->noise; t.noise_strength = p->noise_strength; t.bias = p->bias;
@@ -1303,8 +1410,9 @@ int launch_v2(const ia_conv_params* const* ps, int nph, void* stream) {
     if (int rc = make_act_map2<BK>(&ma_hi, p->a_hi, mapB, mapH, p->W, p->Cin_pad, t.TH + halo, t.tw, mapR)) return rc;
     if (int rc = make_act_map2<BK>(&ma_lo, nops == 2u ? p->a_lo : p->a_hi, mapB, mapH, p->W, p->Cin_pad, t.TH + halo, t.tw, mapR)) return rc;
     const int wrows = t.groups * p->n_taps_total * p->Cout_pad;
-    if (int rc = make_weight_map2<BK>(&mw_hi, p->w_hi, wrows, p->Cin_pad, n_tile)) return rc;
-    if (int rc = make_weight_map2<BK>(&mw_lo, nops == 2u ? p->w_lo : p->w_hi, wrows, p->Cin_pad, n_tile)) return rc;
+    const int w_box = use_pair ? n_tile / 2 : n_tile;
+    if (int rc = make_weight_map2<BK>(&mw_hi, p->w_hi, wrows, p->Cin_pad, w_box)) return rc;
+    if (int rc = make_weight_map2<BK>(&mw_lo, nops == 2u ? p->w_lo : p->w_hi, wrows, p->Cin_pad, w_box)) return rc;
 
     const size_t smem = (size_t)nops * ((size_t)t.a_slots * t.a_bytes + (size_t)t.b_slots * t.b_bytes) + 1024 + 512 + kEpiBytes;
     cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -1317,18 +1425,12 @@ int launch_v2(const ia_conv_params* const* ps, int nph, void* stream) {
         cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
         if (g_sm_count <= 0) g_sm_count = 148;
     }
-    // Cluster-of-2 weight multicast (IA_CONV_CLUSTER=1 enables).
-    static int use_cluster = -1;
-    // Measured on B200: 367 (cluster) vs 396 (plain) TF/s algorithmic on the 128->128 @512^2 layer -- the lock-step
-    // coupling of the pair costs more than the halved weight traffic saves, so the variant is off by default.
-    if (use_cluster < 0) { const char* ev = getenv("IA_CONV_CLUSTER"); use_cluster = ev ? atoi(ev) : 0; }
-    t.m_tiles_p = (t.m_tiles + 1) & ~1;
-    t.total_pairs = (t.m_tiles_p * t.n_tiles) / 2;
-    const int sm_even = g_sm_count & ~1;
-    if (use_cluster && nph == 1 && p->groups <= 1 && t.total_pairs >= sm_even / 2 && t.ksplit <= 1) {
+    if (use_pair) {
+        const int sm_even = g_sm_count & ~1;
+        const int grid = 2 * t.total_pairs < sm_even ? 2 * t.total_pairs : sm_even;
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
-        cfg.gridDim = dim3((unsigned)sm_even, 1, 1);
+        cfg.gridDim = dim3((unsigned)grid, 1, 1);
         cfg.blockDim = dim3(kThreads2, 1, 1);
         cfg.dynamicSmemBytes = smem;
         cfg.stream = as_stream(stream);
@@ -1338,7 +1440,7 @@ int launch_v2(const ia_conv_params* const* ps, int nph, void* stream) {
         cfg.attrs = attr; cfg.numAttrs = 1;
         ia::prof_begin(ia::prof_detail_name("ia_conv_tc", taps_sum, GHm, GWm, p->Cin_pad, p->Cout), as_stream(stream));
         cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tc2_kernel<BK, true>, ma_hi, ma_lo, mw_hi, mw_lo, t);
-        IA_CHECK(le == cudaSuccess, "ia_conv_tc(v2): cluster launch failed: %s", cudaGetErrorString(le));
+        IA_CHECK(le == cudaSuccess, "ia_conv_tc(v2): pair launch failed: %s", cudaGetErrorString(le));
         IA_LAUNCH_CHECK("ia_conv_tc");
         return 0;
     }

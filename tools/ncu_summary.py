@@ -45,8 +45,11 @@ def launches(path):
 
 
 def full(path):
-    out = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
-    rows = list(csv.reader(out.splitlines()))
+    if path.endswith('.csv'):        # a `ncu -i x.ncu-rep --page raw --csv` dump made on the GPU box
+        out = open(path).read()
+    else:
+        out = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    rows = list(csv.reader([l for l in out.splitlines() if l.startswith('"')]))
     hdr, units = rows[0], rows[1]
     kn = hdr.index('Kernel Name')
     for vals in rows[2:]:
