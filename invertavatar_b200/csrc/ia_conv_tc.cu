@@ -250,50 +250,55 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     const int num_kb = p.ntaps * p.Cin_blocks;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
+        // ===================== TMA producer (whole warp runs the loop, one elected lane issues: see conv_tc2_kernel) =====================
+        {
+            const bool el = elect_one();
             int stage = 0; uint32_t phase = 0;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int t = kb / p.Cin_blocks;
-                const int kc = kb - t * p.Cin_blocks;
-                mbar_wait(empty_bar(stage), phase ^ 1u);
-                const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
-                mbar_expect_tx(full_bar(stage), stage_bytes);
-                tma_load_4d(sa, &tm_a_hi, full_bar(stage), kc * kBlockK, x0 + p.dx[t], y0 + p.dy[t], n0);
-                if (nops == 2u) tma_load_4d(sa + kABytes, &tm_a_lo, full_bar(stage), kc * kBlockK, x0 + p.dx[t], y0 + p.dy[t], n0);
+            for (int t = 0; t < p.ntaps; ++t) {
                 const int wrow = ((n0 / p.ipg) * p.n_taps_total + p.wtap[t]) * p.Cout_pad + col0;   // a tile never spans two groups
-                tma_load_2d(sa + b_off, &tm_w_hi, full_bar(stage), kc * kBlockK, wrow);
-                if (nops == 2u) tma_load_2d(sa + b_off + b_bytes, &tm_w_lo, full_bar(stage), kc * kBlockK, wrow);
-                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                for (int kc = 0; kc < p.Cin_blocks; ++kc) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
+                    if (el) {
+                        mbar_expect_tx(full_bar(stage), stage_bytes);
+                        tma_load_4d(sa, &tm_a_hi, full_bar(stage), kc * kBlockK, x0 + p.dx[t], y0 + p.dy[t], n0);
+                        if (nops == 2u) tma_load_4d(sa + kABytes, &tm_a_lo, full_bar(stage), kc * kBlockK, x0 + p.dx[t], y0 + p.dy[t], n0);
+                        tma_load_2d(sa + b_off, &tm_w_hi, full_bar(stage), kc * kBlockK, wrow);
+                        if (nops == 2u) tma_load_2d(sa + b_off + b_bytes, &tm_w_lo, full_bar(stage), kc * kBlockK, wrow);
+                    }
+                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        {
+            const bool el = elect_one();
             // instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=n_tile
             const uint32_t idesc = (1u << 4) | p.idesc_fmt | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+            const uint32_t desc_hi = (uint32_t)(make_sw128_desc(0u) >> 32);
             int stage = 0; uint32_t phase = 0;
             for (int kb = 0; kb < num_kb; ++kb) {
                 mbar_wait(full_bar(stage), phase);
                 tc_fence_after();
                 const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
-                const uint64_t a_hi = make_sw128_desc(sa);
-                const uint64_t a_lo = make_sw128_desc(sa + kABytes);
-                const uint64_t b_hi = make_sw128_desc(sa + b_off);
-                const uint64_t b_lo = make_sw128_desc(sa + b_off + b_bytes);
+                const uint32_t a_hi = ((sa & 0x3FFFFu) >> 4) | (1u << 16);
+                const uint32_t a_lo = a_hi + (kABytes >> 4), b_hi = a_hi + (b_off >> 4), b_lo = b_hi + (b_bytes >> 4);
+                if (el) {
 #pragma unroll
-                for (int k = 0; k < kBlockK / 16; ++k) {
-                    const uint64_t koff = (uint64_t)((k * 32) >> 4);  // +32 bytes per 16-element K step
-                    umma_bf16(tmem_base, a_hi + koff, b_hi + koff, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                    if (nops == 2u) {
-                        umma_bf16(tmem_base, a_hi + koff, b_lo + koff, idesc, 1u);
-                        umma_bf16(tmem_base, a_lo + koff, b_hi + koff, idesc, 1u);
+                    for (int k = 0; k < kBlockK / 16; ++k) {
+                        const uint32_t ko = (uint32_t)(k * 2);  // +32 bytes per 16-element K step
+                        umma_issue<false>(tmem_base, a_hi + ko, b_hi + ko, desc_hi, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        if (nops == 2u) {
+                            umma_issue<false>(tmem_base, a_hi + ko, b_lo + ko, desc_hi, idesc, 1u);
+                            umma_issue<false>(tmem_base, a_lo + ko, b_hi + ko, desc_hi, idesc, 1u);
+                        }
                     }
+                    umma_commit(empty_bar(stage));   // frees the smem slot once these MMAs have read it
                 }
-                umma_commit(empty_bar(stage));   // frees the smem slot once these MMAs have read it
                 if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
-            umma_commit(tmem_full_bar);          // accumulator complete
+            if (el) umma_commit(tmem_full_bar);          // accumulator complete
         }
     } else {
         // ===================== epilogue (warps 2..5) =====================
