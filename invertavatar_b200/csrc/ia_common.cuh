@@ -130,4 +130,40 @@ __device__ __forceinline__ void emit4(const ia_emit& e, int b, int64_t pix, int 
     }
 }
 
+
+// Warp-cooperative dot products of one weight row with up to NB activation rows: acc[i] += sum_k f(x[i * xs + k]) * w[k], f = square or
+// identity, partial sums per lane (the caller reduces across the warp).  The tiny GEMVs of the mapping network / style affines /
+// demodulation coefficients are latency-bound: with K a multiple of 128 and 16-byte aligned rows every lane issues its float4 loads of
+// four 128-element chunks back to back (one exposed memory latency per 512 elements instead of one per 32).
+template <int NB, bool SQUARE>
+__device__ __forceinline__ void warp_dot_rows(const float* __restrict__ w, const float* __restrict__ x, int64_t xs, int K, int nb, int lane,
+                                              float (&acc)[NB]) {
+    const bool vec = (K & 127) == 0 && ((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(x)) & 15) == 0 && (xs & 3) == 0;
+    if (vec) {
+#pragma unroll 4
+        for (int k0 = 0; k0 < K; k0 += 128) {
+            const int k = k0 + 4 * lane;
+            const float4 wv = __ldg(reinterpret_cast<const float4*>(w + k));
+#pragma unroll
+            for (int i = 0; i < NB; ++i)
+                if (i < nb) {
+                    float4 xv = *reinterpret_cast<const float4*>(x + (int64_t)i * xs + k);
+                    if (SQUARE) { xv.x *= xv.x; xv.y *= xv.y; xv.z *= xv.z; xv.w *= xv.w; }
+                    acc[i] = fmaf(xv.w, wv.w, fmaf(xv.z, wv.z, fmaf(xv.y, wv.y, fmaf(xv.x, wv.x, acc[i]))));
+                }
+        }
+        return;
+    }
+    for (int k = lane; k < K; k += 32) {
+        const float wv = w[k];
+#pragma unroll
+        for (int i = 0; i < NB; ++i)
+            if (i < nb) {
+                float xv = x[(int64_t)i * xs + k];
+                if (SQUARE) xv *= xv;
+                acc[i] = fmaf(xv, wv, acc[i]);
+            }
+    }
+}
+
 }  // namespace ia

@@ -1004,16 +1004,24 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                         if (!split) {
                             tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + tcol + (uint32_t)c, r);
                         } else {
+                            // split-major: the eight 16-byte loads of one split are in flight together (one exposed L2 latency per
+                            // split instead of one per load); every element is still summed in split order 0, 1, ...
                             const float4* src = ws_src + (c >> 5) * 256 + lane;
+                            float4 a[8];
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) a[q] = __ldcg(src + q * 32);
+#pragma unroll 2
+                            for (int s2 = 1; s2 < p.ksplit; ++s2) {
+                                float4 b[8];
+#pragma unroll
+                                for (int q = 0; q < 8; ++q) b[q] = __ldcg(src + (int64_t)s2 * ws_sstride + q * 32);
+#pragma unroll
+                                for (int q = 0; q < 8; ++q) { a[q].x += b[q].x; a[q].y += b[q].y; a[q].z += b[q].z; a[q].w += b[q].w; }
+                            }
 #pragma unroll
                             for (int q = 0; q < 8; ++q) {
-                                float4 a = __ldcg(src + q * 32);
-                                for (int s2 = 1; s2 < p.ksplit; ++s2) {
-                                    const float4 b = __ldcg(src + (int64_t)s2 * ws_sstride + q * 32);
-                                    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-                                }
-                                r[4 * q] = __float_as_uint(a.x); r[4 * q + 1] = __float_as_uint(a.y);
-                                r[4 * q + 2] = __float_as_uint(a.z); r[4 * q + 3] = __float_as_uint(a.w);
+                                r[4 * q] = __float_as_uint(a[q].x); r[4 * q + 1] = __float_as_uint(a[q].y);
+                                r[4 * q + 2] = __float_as_uint(a[q].z); r[4 * q + 3] = __float_as_uint(a[q].w);
                             }
                         }
                         if (vmask == 0u) continue;

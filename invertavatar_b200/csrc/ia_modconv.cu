@@ -21,12 +21,7 @@ __global__ void styles_kernel(const ia_style_layer* __restrict__ layers, const f
         float acc[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-        for (int k = lane; k < L.w_dim; k += 32) {
-            float wv = wr[k];
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-                if (i < nb) acc[i] = fmaf(ws[((int64_t)(b0 + i) * num_ws + L.w_index) * L.w_dim + k], wv, acc[i]);
-        }
+        warp_dot_rows<8, false>(wr, ws + ((int64_t)b0 * num_ws + L.w_index) * L.w_dim, (int64_t)num_ws * L.w_dim, L.w_dim, nb, lane, acc);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             float v = acc[i];
@@ -49,15 +44,7 @@ __global__ void demod_kernel(const ia_style_layer* __restrict__ layers, int B) {
         float acc[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-        for (int k = lane; k < L.Cin; k += 32) {
-            float wv = wr[k];
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-                if (i < nb) {
-                    float s = L.styles[(int64_t)(b0 + i) * L.Cin + k];
-                    acc[i] = fmaf(s * s, wv, acc[i]);
-                }
-        }
+        warp_dot_rows<8, true>(wr, L.styles + (int64_t)b0 * L.Cin, (int64_t)L.Cin, L.Cin, nb, lane, acc);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             float v = acc[i];

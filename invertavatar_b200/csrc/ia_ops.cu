@@ -421,12 +421,7 @@ __global__ void fc_kernel(const float* __restrict__ x, const float* __restrict__
 #pragma unroll
     for (int i = 0; i < MAXB; ++i) acc[i] = 0.f;
     const float* wr = w + (int64_t)warp * In;
-    for (int k = lane; k < In; k += 32) {
-        float wv = wr[k];
-#pragma unroll
-        for (int i = 0; i < MAXB; ++i)
-            if (i < nb) acc[i] = fmaf(x[(int64_t)(b0 + i) * xs + k], wv, acc[i]);
-    }
+    ia::warp_dot_rows<MAXB, false>(wr, x + (int64_t)b0 * xs, xs, In, nb, lane, acc);
 #pragma unroll
     for (int i = 0; i < MAXB; ++i) {
         float v = acc[i];
