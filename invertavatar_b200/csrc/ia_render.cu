@@ -59,7 +59,11 @@ __device__ __forceinline__ int phys_channel(int k, bool h16) {
 __global__ void decoder_stage_kernel(const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
                                      const float* __restrict__ b2, DecoderFrags* __restrict__ out, int h16) {
     DecoderFrags& g_dec = *out;
-    const float g1 = 1.0f / sqrtf((float)kFeat), g2 = 1.0f / sqrtf((float)kHidden);
+    // The transcendental constants of the two activations are folded into the staged weights: layer 1 produces pre * log2(e), so
+    // softplus(pre) / ln 2 = lg2(1 + ex2(pre')) is two bare MUFU ops; layer 2's density row carries the ln 2, its colour rows
+    // carry -log2(e) * ln 2 = -1 (and their bias -log2(e)), so sigmoid(o) = rcp(1 + ex2(o')).
+    const float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+    const float g1 = kLog2e / sqrtf((float)kFeat), g2 = 1.0f / sqrtf((float)kHidden);
     // layer 1: B[k][n] = W1[n][phys(k)] * g1
     for (int i = threadIdx.x; i < 8 * 2 * 32; i += blockDim.x) {
         const int lane = i & 31, ks = (i >> 5) & 1, nt = i >> 6;
@@ -78,15 +82,20 @@ __global__ void decoder_stage_kernel(const float* __restrict__ w1, const float* 
         const int row = col < 32 ? col + 1 : (col == 32 ? 0 : -1);
         const int kk[4] = {16 * ks + 2 * t, 16 * ks + 2 * t + 1, 16 * ks + 2 * t + 8, 16 * ks + 2 * t + 9};
         __half h[4], l[4];
-        for (int q = 0; q < 4; ++q) { const float v = row >= 0 ? w2[row * kHidden + kk[q]] * g2 : 0.f; split_half(v, h[q], l[q]); }
+        const float gq = col < 32 ? -g2 : g2 * kLn2;
+        for (int q = 0; q < 4; ++q) { const float v = row >= 0 ? w2[row * kHidden + kk[q]] * gq : 0.f; split_half(v, h[q], l[q]); }
         g_dec.w2f[((nt * 4 + ks) * 2 + 0) * 32 + lane] = make_uint2(pack_half2(h[0], h[1]), pack_half2(h[2], h[3]));
         g_dec.w2f[((nt * 4 + ks) * 2 + 1) * 32 + lane] = make_uint2(pack_half2(l[0], l[1]), pack_half2(l[2], l[3]));
     }
-    for (int i = threadIdx.x; i < kHidden; i += blockDim.x) g_dec.b1[i] = b1[i];
-    for (int i = threadIdx.x; i < kOutPad; i += blockDim.x) g_dec.b2[i] = i < 32 ? b2[i + 1] : (i == 32 ? b2[0] : 0.f);
+    for (int i = threadIdx.x; i < kHidden; i += blockDim.x) g_dec.b1[i] = b1[i] * kLog2e;
+    for (int i = threadIdx.x; i < kOutPad; i += blockDim.x) g_dec.b2[i] = i < 32 ? -b2[i + 1] * kLog2e : (i == 32 ? b2[0] : 0.f);
 }
 
-__device__ __forceinline__ float softplus_fast(float x) { return x > 20.f ? x : __logf(1.f + __expf(x)); }
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// softplus(pre) / ln 2 from pre' = pre * log2(e) (threshold 20 of F.softplus in the scaled variable)
+__device__ __forceinline__ float softplus_log2(float xs) { return xs > 28.853900817779268f ? xs : lg2_approx(1.f + ex2_approx(xs)); }
 __device__ __forceinline__ float softplus_acc(float x) { return x > 20.f ? x : log1pf(expf(x)); }
 
 __device__ __forceinline__ void mma_f16(float (&c)[4], const uint32_t (&a)[4], const uint2 b) {
@@ -171,8 +180,12 @@ __device__ __forceinline__ void plane_gather8(const float* __restrict__ plane_ba
 
 // fp16 planes: this lane's 8 channels 8t..8t+7 of a texel are one 16-byte load; arithmetic stays fp32 (only the storage is
 // rounded: 9.4e-6 on the final image, profiles/r1_render_precision_probe.json).  Same zero-padding scheme as above.
-__device__ __forceinline__ void plane_gather8_h(const __half* __restrict__ plane_base, int64_t px_ld, int PH, int PW, float gx, float gy,
-                                                float acc[8]) {
+// Bilinear set-up of ONE plane of one sample (the arithmetic of plane_gather8_h, split from its loads): clamped texel offsets
+// (elements, relative to the plane's channel 0) and the four zero-padding-masked weights.  In gather_mlp_pass the four lanes of a
+// quad need the same 3 planes x 2 samples: lane t computes plane min(t, 2) of both samples and the quad exchanges the results by
+// shuffle (8 values per plane and sample) instead of every lane computing all six -- same values, bit-identical features.
+struct TapSetup { int o00, o01, o10, o11; float w00, w01, w10, w11; };
+__device__ __forceinline__ TapSetup tap_setup(int64_t px_ld, int PH, int PW, float gx, float gy) {
     const float ix = ((gx + 1.f) * PW - 1.f) / 2.f;
     const float iy = ((gy + 1.f) * PH - 1.f) / 2.f;
     const float fx = floorf(ix), fy = floorf(iy);
@@ -184,31 +197,30 @@ __device__ __forceinline__ void plane_gather8_h(const __half* __restrict__ plane
     const bool vx0 = x0 >= 0 && x0 < PW, vx1 = x1 >= 0 && x1 < PW, vy0 = y0 >= 0 && y0 < PH, vy1 = y1 >= 0 && y1 < PH;
     const int x0c = min(max(x0, 0), PW - 1), x1c = min(max(x1, 0), PW - 1);
     const int y0c = min(max(y0, 0), PH - 1), y1c = min(max(y1, 0), PH - 1);
-    const float w00 = (vy0 && vx0) ? wnw : 0.f, w01 = (vy0 && vx1) ? wne : 0.f;
-    const float w10 = (vy1 && vx0) ? wsw : 0.f, w11 = (vy1 && vx1) ? wse : 0.f;
-    const __half* r0 = plane_base + (int64_t)(y0c * PW) * px_ld;
-    const __half* r1 = plane_base + (int64_t)(y1c * PW) * px_ld;
-    const uint4 a = __ldg(reinterpret_cast<const uint4*>(r0 + (int64_t)x0c * px_ld));
-    const uint4 b = __ldg(reinterpret_cast<const uint4*>(r0 + (int64_t)x1c * px_ld));
-    const uint4 c = __ldg(reinterpret_cast<const uint4*>(r1 + (int64_t)x0c * px_ld));
-    const uint4 d = __ldg(reinterpret_cast<const uint4*>(r1 + (int64_t)x1c * px_ld));
-    float s[8];
-    auto tap = [&](const uint4& v, float w, bool first) {
-        const float2 p0 = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
-        const float2 p1 = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
-        const float2 p2 = __half22float2(*reinterpret_cast<const __half2*>(&v.z));
-        const float2 p3 = __half22float2(*reinterpret_cast<const __half2*>(&v.w));
-        if (first) {
-            s[0] = p0.x * w; s[1] = p0.y * w; s[2] = p1.x * w; s[3] = p1.y * w;
-            s[4] = p2.x * w; s[5] = p2.y * w; s[6] = p3.x * w; s[7] = p3.y * w;
-        } else {
-            s[0] += p0.x * w; s[1] += p0.y * w; s[2] += p1.x * w; s[3] += p1.y * w;
-            s[4] += p2.x * w; s[5] += p2.y * w; s[6] += p3.x * w; s[7] += p3.y * w;
-        }
-    };
-    tap(a, w00, true); tap(b, w01, false); tap(c, w10, false); tap(d, w11, false);
+    TapSetup t;
+    t.w00 = (vy0 && vx0) ? wnw : 0.f; t.w01 = (vy0 && vx1) ? wne : 0.f;
+    t.w10 = (vy1 && vx0) ? wsw : 0.f; t.w11 = (vy1 && vx1) ? wse : 0.f;
+    const int ld = (int)px_ld;
+    t.o00 = (y0c * PW + x0c) * ld; t.o01 = (y0c * PW + x1c) * ld;
+    t.o10 = (y1c * PW + x0c) * ld; t.o11 = (y1c * PW + x1c) * ld;
+    return t;
+}
+// The four taps of one plane for this lane's 8 fp16 channels, fp32 arithmetic on packed pairs (fma.rn.f32x2: the same roundings as
+// eight scalar FMAs in half the instructions).
+__device__ __forceinline__ void plane_taps8_h(const __half* __restrict__ base, const TapSetup& t, float2 (&acc)[4]) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(base + t.o00));
+    const uint4 b = __ldg(reinterpret_cast<const uint4*>(base + t.o01));
+    const uint4 c = __ldg(reinterpret_cast<const uint4*>(base + t.o10));
+    const uint4 d = __ldg(reinterpret_cast<const uint4*>(base + t.o11));
+    float2 s[4];
+    auto h2 = [](uint32_t v) { return __half22float2(*reinterpret_cast<const __half2*>(&v)); };
+    const float2 wa = make_float2(t.w00, t.w00), wb = make_float2(t.w01, t.w01), wc = make_float2(t.w10, t.w10), wd = make_float2(t.w11, t.w11);
+    s[0] = __fmul2_rn(h2(a.x), wa); s[1] = __fmul2_rn(h2(a.y), wa); s[2] = __fmul2_rn(h2(a.z), wa); s[3] = __fmul2_rn(h2(a.w), wa);
+    s[0] = __ffma2_rn(h2(b.x), wb, s[0]); s[1] = __ffma2_rn(h2(b.y), wb, s[1]); s[2] = __ffma2_rn(h2(b.z), wb, s[2]); s[3] = __ffma2_rn(h2(b.w), wb, s[3]);
+    s[0] = __ffma2_rn(h2(c.x), wc, s[0]); s[1] = __ffma2_rn(h2(c.y), wc, s[1]); s[2] = __ffma2_rn(h2(c.z), wc, s[2]); s[3] = __ffma2_rn(h2(c.w), wc, s[3]);
+    s[0] = __ffma2_rn(h2(d.x), wd, s[0]); s[1] = __ffma2_rn(h2(d.y), wd, s[1]); s[2] = __ffma2_rn(h2(d.z), wd, s[2]); s[3] = __ffma2_rn(h2(d.w), wd, s[3]);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc[k] += s[k];
+    for (int k = 0; k < 4; ++k) acc[k] = __fadd2_rn(acc[k], s[k]);
 }
 
 // Tri-plane gather + OSG decoder for samples [s0, s0+n) of this warp's ray, 16 samples per step on the tensor cores
@@ -229,25 +241,52 @@ __device__ __forceinline__ void gather_mlp_pass(const ia_render_params& p, const
     const __half* pbh = reinterpret_cast<const __half*>(planes_b) + 8 * t;
     for (int m0 = 0; m0 < n; m0 += 16) {
         float feat[2][8];
+        if (H16) {
+            // quad-cooperative set-up: lane t owns plane min(t, 2) -- (x, y), (x, z), (z, x) -- of the quad's two samples
+            TapSetup mine[2];
 #pragma unroll
-        for (int rr = 0; rr < 2; ++rr) {
-            const int sidx = min(m0 + g + 8 * rr, n - 1);      // rows past the end repeat the last sample; results are dropped
-            const float tt = dep[s0 + sidx];
-            const float qx = (r.ox + tt * r.dx) * scale;
-            const float qy = (r.oy + tt * r.dy) * scale;
-            const float qz = (r.oz + tt * r.dz) * scale;
-            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            if (H16) {
-                plane_gather8_h(pbh + 0, p.plane_px_ld, p.PH, p.PW, qx, qy, acc);    // plane 0: (x, y)
-                plane_gather8_h(pbh + 32, p.plane_px_ld, p.PH, p.PW, qx, qz, acc);   // plane 1: (x, z)
-                plane_gather8_h(pbh + 64, p.plane_px_ld, p.PH, p.PW, qz, qx, acc);   // plane 2: (z, x)
-            } else {
+            for (int rr = 0; rr < 2; ++rr) {
+                const int sidx = min(m0 + g + 8 * rr, n - 1);      // rows past the end repeat the last sample; results are dropped
+                const float tt = dep[s0 + sidx];
+                const float qx = (r.ox + tt * r.dx) * scale;
+                const float qy = (r.oy + tt * r.dy) * scale;
+                const float qz = (r.oz + tt * r.dz) * scale;
+                const float gx = t < 2 ? qx : qz;
+                const float gy = t == 0 ? qy : (t == 1 ? qz : qx);
+                mine[rr] = tap_setup(p.plane_px_ld, p.PH, p.PW, gx, gy);
+            }
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                float2 acc[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+                for (int pl = 0; pl < 3; ++pl) {
+                    const int src = (lane & ~3) | pl;
+                    TapSetup ts;
+                    ts.o00 = __shfl_sync(0xffffffffu, mine[rr].o00, src); ts.o01 = __shfl_sync(0xffffffffu, mine[rr].o01, src);
+                    ts.o10 = __shfl_sync(0xffffffffu, mine[rr].o10, src); ts.o11 = __shfl_sync(0xffffffffu, mine[rr].o11, src);
+                    ts.w00 = __shfl_sync(0xffffffffu, mine[rr].w00, src); ts.w01 = __shfl_sync(0xffffffffu, mine[rr].w01, src);
+                    ts.w10 = __shfl_sync(0xffffffffu, mine[rr].w10, src); ts.w11 = __shfl_sync(0xffffffffu, mine[rr].w11, src);
+                    plane_taps8_h(pbh + 32 * pl, ts, acc);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { feat[rr][2 * k] = acc[k].x * (1.0f / 3.0f); feat[rr][2 * k + 1] = acc[k].y * (1.0f / 3.0f); }
+            }
+        }
+        if (!H16) {
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                const int sidx = min(m0 + g + 8 * rr, n - 1);      // rows past the end repeat the last sample; results are dropped
+                const float tt = dep[s0 + sidx];
+                const float qx = (r.ox + tt * r.dx) * scale;
+                const float qy = (r.oy + tt * r.dy) * scale;
+                const float qz = (r.oz + tt * r.dz) * scale;
+                float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                 plane_gather8(pb + 0, p.plane_px_ld, p.PH, p.PW, qx, qy, acc);    // plane 0: (x, y)
                 plane_gather8(pb + 32, p.plane_px_ld, p.PH, p.PW, qx, qz, acc);   // plane 1: (x, z)
                 plane_gather8(pb + 64, p.plane_px_ld, p.PH, p.PW, qz, qx, acc);   // plane 2: (z, x)
-            }
 #pragma unroll
-            for (int k = 0; k < 8; ++k) feat[rr][k] = acc[k] * (1.0f / 3.0f);  // mean over the three planes (<= 1 ulp from the division)
+                for (int k = 0; k < 8; ++k) feat[rr][k] = acc[k] * (1.0f / 3.0f);  // mean over the three planes (<= 1 ulp from the division)
+            }
         }
         // ---- layer 1: [16 x 32] x [32 x 64] ----
         uint32_t ah[2][4], al[2][4];
@@ -283,7 +322,7 @@ __device__ __forceinline__ void gather_mlp_pass(const ia_render_params& p, const
                 }
             }
 #pragma unroll
-            for (int q = 0; q < 4; ++q) hid[nt][q] = softplus_fast(c[q]);
+            for (int q = 0; q < 4; ++q) hid[nt][q] = softplus_log2(c[q]);
         }
         // ---- layer 2: [16 x 64] x [64 x 40] ----
         float out[5][4];
@@ -320,8 +359,8 @@ __device__ __forceinline__ void gather_mlp_pass(const ia_render_params& p, const
                 float* row = col + (s0 + sidx) * kRowLd;
 #pragma unroll
                 for (int nt = 0; nt < 4; ++nt) {
-                    const float v0 = __fdividef(1.0f, 1.0f + __expf(-out[nt][2 * rr + 0]));
-                    const float v1 = __fdividef(1.0f, 1.0f + __expf(-out[nt][2 * rr + 1]));
+                    const float v0 = rcp_approx(1.0f + ex2_approx(out[nt][2 * rr + 0]));      // sigmoid: out' = -out * log2(e)
+                    const float v1 = rcp_approx(1.0f + ex2_approx(out[nt][2 * rr + 1]));
                     *reinterpret_cast<float2*>(row + nt * 8 + 2 * t) =
                         make_float2(v0 * (1.0f + 2.0f * 0.001f) - 0.001f, v1 * (1.0f + 2.0f * 0.001f) - 0.001f);
                 }
