@@ -247,7 +247,18 @@ namespace {
 // 256^2 sample a tap of two neighbouring outputs: a thread that owns NX neighbours gathers each sample of their union once
 // (NX = 4: 40 instead of 64 gathers at scale 8) and adds it to each output whose window holds it, in the same ascending-tap
 // order as before -- results are bit-identical to NX = 1.
-template <int KC, int NX>
+// COOP (lpp == 32: the 32 lanes of a warp share one pixel group): the bilinear set-up of a sample -- uv load, coordinates, the four
+// zero-padding-masked weights and clamped texel offsets -- is computed ONCE, by lane (x - x_lo) % 32, and broadcast by shuffle,
+// instead of by all 32 lanes; out-of-range corners read a clamped texel with weight 0 (branch-free, v * 0 adds nothing).  The
+// accumulations use packed fp32 FMAs (fma.rn.f32x2: the roundings of the scalar FMAs).  Results are bit-identical to the plain path.
+__device__ __forceinline__ void fma4(float4& a, const float4& v, float w) {
+    const float2 ww = make_float2(w, w);
+    const float2 lo = __ffma2_rn(make_float2(v.x, v.y), ww, make_float2(a.x, a.y));
+    const float2 hi = __ffma2_rn(make_float2(v.z, v.w), ww, make_float2(a.z, a.w));
+    a = make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+
+template <int KC, int NX, bool COOP>
 __global__ void __launch_bounds__(256) raster_hpass_kernel(ia_raster_level_params p, int lpp) {
     const int rg = (p.r + NX - 1) / NX;
     const int64_t total = (int64_t)p.B * p.UH * rg * lpp;
@@ -275,41 +286,89 @@ __global__ void __launch_bounds__(256) raster_hpass_kernel(ia_raster_level_param
         for (int k = 0; k < KC; ++k) acc[j][k] = make_float4(0.f, 0.f, 0.f, 0.f);
     const int Wi = p.Wt, Hi = p.Ht;
     const int kstride = lpp * 4;
-    for (int x = x_lo; x < x_hi; ++x) {
+    // grid_sample(bilinear, zeros, align_corners=False), same arithmetic as grid_sample_kernel
+    auto setup = [&](int x, float& wnw, float& wne, float& wsw, float& wse, int& x0, int& y0, bool& vx0, bool& vx1, bool& vy0, bool& vy1) {
         const float gx = uvrow[(int64_t)x * p.uv_ld + 0], gy = uvrow[(int64_t)x * p.uv_ld + 1];
-        // grid_sample(bilinear, zeros, align_corners=False), same arithmetic as grid_sample_kernel
         const float ix = ((gx + 1.f) * Wi - 1.f) / 2.f;
         const float iy = ((gy + 1.f) * Hi - 1.f) / 2.f;
         const float fx = floorf(ix), fy = floorf(iy);
-        const int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;
-        const float wnw = ((float)x1 - ix) * ((float)y1 - iy);
-        const float wne = (ix - (float)x0) * ((float)y1 - iy);
-        const float wsw = ((float)x1 - ix) * (iy - (float)y0);
-        const float wse = (ix - (float)x0) * (iy - (float)y0);
-        const bool vx0 = x0 >= 0 && x0 < Wi, vx1 = x1 >= 0 && x1 < Wi, vy0 = y0 >= 0 && y0 < Hi, vy1 = y1 >= 0 && y1 < Hi;
-        float4 s[KC];
-#pragma unroll
-        for (int k = 0; k < KC; ++k) s[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        auto corner = [&](int yy, int xx, float cw) {
-            const float* q = tbase + ((int64_t)yy * Wi + xx) * p.C;
-#pragma unroll
-            for (int k = 0; k < KC; ++k) {
-                const float4 v = __ldg(reinterpret_cast<const float4*>(q + k * kstride));
-                s[k].x += v.x * cw; s[k].y += v.y * cw; s[k].z += v.z * cw; s[k].w += v.w * cw;
-            }
-        };
-        if (vy0 && vx0) corner(y0, x0, wnw);
-        if (vy0 && vx1) corner(y0, x1, wne);
-        if (vy1 && vx0) corner(y1, x0, wsw);
-        if (vy1 && vx1) corner(y1, x1, wse);
+        x0 = (int)fx; y0 = (int)fy;
+        const int x1 = x0 + 1, y1 = y0 + 1;
+        wnw = ((float)x1 - ix) * ((float)y1 - iy);
+        wne = (ix - (float)x0) * ((float)y1 - iy);
+        wsw = ((float)x1 - ix) * (iy - (float)y0);
+        wse = (ix - (float)x0) * (iy - (float)y0);
+        vx0 = x0 >= 0 && x0 < Wi; vx1 = x1 >= 0 && x1 < Wi; vy0 = y0 >= 0 && y0 < Hi; vy1 = y1 >= 0 && y1 < Hi;
+    };
+    auto accumulate = [&](int x, const float4 (&s)[KC]) {
 #pragma unroll
         for (int j = 0; j < NX; ++j) {
             const int tx = x - xs[j];
             if (tx >= 0 && tx < xn[j]) {
                 const float w = p.ux_w[(int64_t)(ox0 + j) * p.ux_max_taps + tx];
 #pragma unroll
-                for (int k = 0; k < KC; ++k) { acc[j][k].x += s[k].x * w; acc[j][k].y += s[k].y * w; acc[j][k].z += s[k].z * w; acc[j][k].w += s[k].w * w; }
+                for (int k = 0; k < KC; ++k) fma4(acc[j][k], s[k], w);
             }
+        }
+    };
+    if (COOP) {
+        for (int xb = x_lo; xb < x_hi; xb += 32) {
+            float mw00 = 0.f, mw01 = 0.f, mw10 = 0.f, mw11 = 0.f;
+            int mo00 = 0, mo01 = 0, mo10 = 0, mo11 = 0;
+            if (xb + lane < x_hi) {
+                float wnw, wne, wsw, wse; int x0, y0; bool vx0, vx1, vy0, vy1;
+                setup(xb + lane, wnw, wne, wsw, wse, x0, y0, vx0, vx1, vy0, vy1);
+                const int x0c = min(max(x0, 0), Wi - 1), x1c = min(max(x0 + 1, 0), Wi - 1);
+                const int y0c = min(max(y0, 0), Hi - 1), y1c = min(max(y0 + 1, 0), Hi - 1);
+                mw00 = (vy0 && vx0) ? wnw : 0.f; mw01 = (vy0 && vx1) ? wne : 0.f;
+                mw10 = (vy1 && vx0) ? wsw : 0.f; mw11 = (vy1 && vx1) ? wse : 0.f;
+                mo00 = (y0c * Wi + x0c) * p.C; mo01 = (y0c * Wi + x1c) * p.C;
+                mo10 = (y1c * Wi + x0c) * p.C; mo11 = (y1c * Wi + x1c) * p.C;
+            }
+            const int cnt = min(32, x_hi - xb);
+            for (int q = 0; q < cnt; ++q) {
+                const float w00 = __shfl_sync(0xffffffffu, mw00, q), w01 = __shfl_sync(0xffffffffu, mw01, q);
+                const float w10 = __shfl_sync(0xffffffffu, mw10, q), w11 = __shfl_sync(0xffffffffu, mw11, q);
+                const int o00 = __shfl_sync(0xffffffffu, mo00, q), o01 = __shfl_sync(0xffffffffu, mo01, q);
+                const int o10 = __shfl_sync(0xffffffffu, mo10, q), o11 = __shfl_sync(0xffffffffu, mo11, q);
+                float4 s[KC];
+                float4 va[KC], vb[KC], vc[KC], vd[KC];
+#pragma unroll
+                for (int k = 0; k < KC; ++k) {
+                    va[k] = __ldg(reinterpret_cast<const float4*>(tbase + o00 + k * kstride));
+                    vb[k] = __ldg(reinterpret_cast<const float4*>(tbase + o01 + k * kstride));
+                    vc[k] = __ldg(reinterpret_cast<const float4*>(tbase + o10 + k * kstride));
+                    vd[k] = __ldg(reinterpret_cast<const float4*>(tbase + o11 + k * kstride));
+                }
+#pragma unroll
+                for (int k = 0; k < KC; ++k) {
+                    s[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    fma4(s[k], va[k], w00); fma4(s[k], vb[k], w01); fma4(s[k], vc[k], w10); fma4(s[k], vd[k], w11);
+                }
+                accumulate(xb + q, s);
+            }
+        }
+    } else {
+        for (int x = x_lo; x < x_hi; ++x) {
+            float wnw, wne, wsw, wse; int x0, y0; bool vx0, vx1, vy0, vy1;
+            setup(x, wnw, wne, wsw, wse, x0, y0, vx0, vx1, vy0, vy1);
+            const int x1 = x0 + 1, y1 = y0 + 1;
+            float4 s[KC];
+#pragma unroll
+            for (int k = 0; k < KC; ++k) s[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            auto corner = [&](int yy, int xx, float cw) {
+                const float* q = tbase + ((int64_t)yy * Wi + xx) * p.C;
+#pragma unroll
+                for (int k = 0; k < KC; ++k) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(q + k * kstride));
+                    fma4(s[k], v, cw);
+                }
+            };
+            if (vy0 && vx0) corner(y0, x0, wnw);
+            if (vy0 && vx1) corner(y0, x1, wne);
+            if (vy1 && vx0) corner(y1, x0, wsw);
+            if (vy1 && vx1) corner(y1, x1, wse);
+            accumulate(x, s);
         }
     }
 #pragma unroll
@@ -394,7 +453,10 @@ extern "C" int ia_raster_level(const ia_raster_level_params* p, void* stream) {
     const int64_t total1 = (int64_t)p->B * p->UH * cdiv(p->r, nx) * lpp;
     const unsigned grid1 = (unsigned)cdiv(total1, 256);
     ia::prof_begin("ia_raster_level(hpass)", as_stream(stream));
-#define IA_HPASS(K, N) raster_hpass_kernel<K, N><<<grid1, 256, 0, as_stream(stream)>>>(*p, lpp)
+    static int coop_env = -1;      // IA_RASTER_COOP=0: every lane computes every sample's set-up (the round-1 kernel)
+    if (coop_env < 0) { const char* e = getenv("IA_RASTER_COOP"); coop_env = e ? atoi(e) : 1; }
+    const bool coop = coop_env != 0 && lpp == 32;
+#define IA_HPASS(K, N) do { if (coop) raster_hpass_kernel<K, N, true><<<grid1, 256, 0, as_stream(stream)>>>(*p, lpp); else raster_hpass_kernel<K, N, false><<<grid1, 256, 0, as_stream(stream)>>>(*p, lpp); } while (0)
     if (kc == 4) { if (nx == 2) IA_HPASS(4, 2); else IA_HPASS(4, 1); }
     else if (kc == 2) { if (nx == 4) IA_HPASS(2, 4); else if (nx == 2) IA_HPASS(2, 2); else IA_HPASS(2, 1); }
     else { if (nx == 4) IA_HPASS(1, 4); else if (nx == 2) IA_HPASS(1, 2); else IA_HPASS(1, 1); }
