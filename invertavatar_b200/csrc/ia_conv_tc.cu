@@ -1266,10 +1266,10 @@ int launch_v2(const ia_conv_params* const* ps, int nph, void* stream) {
     // CTA-pair launch (tcgen05 cta_group::2; IA_CONV_PAIR=0 disables): M = 256 MMAs over two CTAs' pixel tiles with the weight tile
     // split between them -- half the weight bytes staged and read per CTA.  Needs at least one tile pair per SM pair, one weight
     // group, no split-K.
-    static int pair_env = -1;
-    if (pair_env < 0) { const char* ev = getenv("IA_CONV_PAIR"); pair_env = ev ? atoi(ev) : 1; }
-    static int pair_min_tiles = -1;      // IA_CONV_PAIR_MIN_TILES: fewest (M tile, N tile) entries of a pair launch, in units of SMs x 1/4
-    if (pair_min_tiles < 0) { const char* ev = getenv("IA_CONV_PAIR_MIN_TILES"); pair_min_tiles = ev ? atoi(ev) : 4; }
+    // (read per launch, not cached: the bit-identity test toggles them inside one process)
+    int pair_env = 1, pair_min_tiles = 4;      // IA_CONV_PAIR_MIN_TILES: fewest (M tile, N tile) entries of a pair launch, in units of SMs x 1/4
+    { const char* ev = getenv("IA_CONV_PAIR"); if (ev) pair_env = atoi(ev); }
+    { const char* ev = getenv("IA_CONV_PAIR_MIN_TILES"); if (ev) pair_min_tiles = atoi(ev); }
     bool use_pair = pair_env != 0 && p->groups <= 1 && t.ksplit <= 1 && real_tiles * (p->Cout_pad / n_tile) * 4 >= (int64_t)g_sm_count * pair_min_tiles;
     t.ws = reinterpret_cast<float4*>(p->splitk_ws); t.cnt = p->splitk_counters;
     t.n_tile = n_tile; t.acc_stride = 128;

@@ -324,3 +324,34 @@ def test_synthesis_network_mixed_precision_chain(monkeypatch):
         worst = max(worst, e)
         assert e <= 5e-3, e
     assert worst > 1e-5, 'the single-pass format was not exercised'
+
+
+@pytest.mark.parametrize('fmt', ['bf16x3', 'f16x1'])
+@pytest.mark.parametrize('cin,cout,res,up,B', [
+    (128, 128, 64, 1, 3),      # 48 M tiles x 1 N tile
+    (256, 256, 32, 1, 5),      # 20 M tiles x 2 N tiles
+    (128, 96, 48, 1, 3),       # ragged tiles, odd tile count per N tile -> a padding tile in the last pair, Cout not a multiple of 32
+    (256, 128, 64, 2, 3),      # merged transposed-conv phases: (H+1)^2 grids, per-phase pair lists padded to even
+    (64, 64, 40, 2, 1),        # phases with an odd number of tiles in every list
+])
+def test_cta_pair_matches_single_cta(monkeypatch, fmt, cin, cout, res, up, B):
+    """tcgen05 cta_group::2 launches (M = 256 MMAs over two CTAs' pixel tiles, weight tile split across the pair) accumulate every
+    output element over k in the same order as the 1-CTA kernel: bit-identical layer outputs, in both operand formats."""
+    old = rt.get_conv_impl()
+    rt.set_conv_impl('tc')
+    try:
+        L = _layer(cin, cout, res, up, seed=cin + cout + res).to(DEV)
+        L.tc_fmt = rt.FMT_F16X1 if fmt == 'f16x1' else rt.FMT_BF16X3
+        g = torch.Generator().manual_seed(11)
+        x = torch.randn(B, cin, res // up, res // up, generator=g).to(DEV)
+        w = torch.randn(B, 64, generator=g).to(DEV)
+        monkeypatch.setenv('IA_CONV_SPLITK', '0')            # (a split launch is never a pair launch)
+        monkeypatch.setenv('IA_CONV_PAIR', '0')
+        y0 = L(x, w, noise_mode='const', gain=1.0).clone()
+        monkeypatch.setenv('IA_CONV_PAIR', '1')
+        monkeypatch.setenv('IA_CONV_PAIR_MIN_TILES', '0')    # pair launches whatever the grid size
+        y1 = L(x, w, noise_mode='const', gain=1.0).clone()
+        assert torch.isfinite(y1).all()
+        assert torch.equal(y0, y1), float((y0 - y1).abs().max())
+    finally:
+        rt.set_conv_impl(old)
