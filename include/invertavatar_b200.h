@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define IA_ABI_VERSION 2
+#define IA_ABI_VERSION 3
 
 /* ---- library management ------------------------------------------------------------------------ */
 int ia_abi_version(void);
@@ -441,6 +441,45 @@ int ia_enc_gru_gate(int32_t stage, const float* raw, const float* bias, const fl
  * place on the fp32 NHWC activation x [B][HW][C]; scale/shift are views of [1|B][HW][C/2]. */
 int ia_sft_half(float* x, int64_t x_ld, const ia_view* scale, const ia_view* shift, int32_t B, int32_t H, int32_t W,
                 int32_t C, void* stream);
+
+/* ---- "improved one-shot" encoder: Mix-Transformer pieces ------------------------------------------------------
+ * encoder_inversion/models/mmseg/mix_transformer.py (MixVisionTransformer :201, Block :118, Attention :56, Mlp :18, DWConv :379,
+ * OverlapPatchEmbed :159, transformer_block :453) and the UpLayer decoders of unet_transformer.py:255,340,523.  Tokens are
+ * stored as [B][H][W][C] fp32 -- an NHWC image whose pixels are the tokens -- so every nn.Linear is a 1x1 ia_conv_tc and the
+ * reference's flatten / transpose / reshape / permute calls do not exist here. */
+
+/* Patch gather for a k x k, stride s, zero-pad convolution evaluated as ONE GEMM (OverlapPatchEmbed.proj: 7x7 s2 / s4, 3x3 s2;
+ * Attention.sr: k = stride = sr_ratio): out[b][oy][ox][(ky*k + kx)*C + c] = cat(src)[b][oy*s - pad + ky][ox*s - pad + kx][c] as
+ * the bf16 hi/lo operand [B][OH][OW][K_pad] (zero beyond k*k*C).  The matching weight is the OIHW filter permuted to
+ * [O][kh][kw][I] and packed as a 1x1 convolution with k*k*C input channels. */
+typedef struct {
+    ia_view src[4]; int32_t nsrc;
+    int32_t B, H, W, k, stride, pad, OH, OW;
+    uint16_t* hi; uint16_t* lo; int32_t K_pad;
+} ia_enc_im2col_params;
+int ia_enc_im2col(const ia_enc_im2col_params* p, void* stream);
+/* torch.nn.LayerNorm over the last dimension of x [rows][C] (row pitch x_ld) after adding pre_bias[c] (may be NULL: the bias of
+ * the convolution whose raw accumulators x holds): y = (x - mean) * rsqrt(var + eps) * gamma + beta, biased variance.  Writes
+ * fp32 out32 [rows][out32_ld] and / or the bf16 hi/lo operand [rows][C_pad] of the linear layer that follows. */
+int ia_layer_norm(const float* x, int64_t x_ld, const float* pre_bias, const float* gamma, const float* beta, float eps,
+                  int64_t rows, int32_t C, float* out32, int64_t out32_ld, uint16_t* hi, uint16_t* lo, int32_t C_pad,
+                  void* stream);
+/* Multi-head attention (mix_transformer.py:97-112): out[b][n][h*hd + d] = sum_m softmax_m((q[b][n][h] + q_bias) . (k[b][m][h] +
+ * k_bias) * scale) (v[b][m][h][d] + v_bias).  q [B][Nq][q_ld], k / v [B][Nk][k_ld / v_ld] fp32 (raw accumulators of the q / kv
+ * projections; k and v may point into one kv tensor), head h at channel offset h*head_dim; biases [heads*head_dim] or NULL
+ * (qkv_bias=False).  head_dim 64 or 256.  The N x N score matrix is never stored (online softmax over 64-key tiles). */
+typedef struct {
+    const float* q; const float* k; const float* v; int64_t q_ld, k_ld, v_ld;
+    const float* q_bias; const float* k_bias; const float* v_bias;
+    int32_t B, heads, head_dim, Nq, Nk; float scale;
+    float* out32; int64_t out32_ld;
+    uint16_t* hi; uint16_t* lo; int32_t C_pad;      /* operand of the proj layer [B*Nq][C_pad], C_pad == heads*head_dim */
+} ia_attention_params;
+int ia_attention(const ia_attention_params* p, void* stream);
+/* Mix-FFN middle (mix_transformer.py:46-49): gelu(depthwise3x3(x + in_bias) + bias), exact (erf) GELU, zero padding.
+ * x [B][H][W][C] fp32 contiguous (raw fc1 accumulators), w [C][3][3]; writes fp32 out32 [B][H][W][C] and / or the fc2 operand. */
+int ia_dwconv_gelu(const float* x, const float* in_bias, const float* w, const float* bias, int32_t B, int32_t H, int32_t W,
+                   int32_t C, float* out32, uint16_t* hi, uint16_t* lo, int32_t C_pad, void* stream);
 
 /* ---- mesh-condition producer (the step in front of the path) -------------------------------------------------
  * Faceverse_manager.make_driven_rendering (data_preprocess/FaceVerse/renderer.py:45-84): driving coefficients -> 3DMM vertices

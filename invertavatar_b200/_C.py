@@ -168,6 +168,21 @@ class EncAffineParams(C.Structure):
                 ('B', C.c_int32), ('H', C.c_int32), ('W', C.c_int32), ('C', C.c_int32)]
 
 
+class EncIm2colParams(C.Structure):
+    _fields_ = [('src', View * 4), ('nsrc', C.c_int32),
+                ('B', C.c_int32), ('H', C.c_int32), ('W', C.c_int32), ('k', C.c_int32), ('stride', C.c_int32), ('pad', C.c_int32),
+                ('OH', C.c_int32), ('OW', C.c_int32),
+                ('hi', c_u16p), ('lo', c_u16p), ('K_pad', C.c_int32)]
+
+
+class AttentionParams(C.Structure):
+    _fields_ = [('q', c_f32p), ('k', c_f32p), ('v', c_f32p), ('q_ld', C.c_int64), ('k_ld', C.c_int64), ('v_ld', C.c_int64),
+                ('q_bias', c_f32p), ('k_bias', c_f32p), ('v_bias', c_f32p),
+                ('B', C.c_int32), ('heads', C.c_int32), ('head_dim', C.c_int32), ('Nq', C.c_int32), ('Nk', C.c_int32), ('scale', C.c_float),
+                ('out32', c_f32p), ('out32_ld', C.c_int64),
+                ('hi', c_u16p), ('lo', c_u16p), ('C_pad', C.c_int32)]
+
+
 # name -> (restype, argtypes); every symbol include/invertavatar_b200.h declares
 SIGNATURES = {
     'ia_abi_version': (C.c_int, []),
@@ -224,9 +239,15 @@ SIGNATURES = {
     'ia_layout_grid_u8': (C.c_int, [c_f32p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                    C.c_void_p, C.c_void_p]),
     'ia_sft_half': (C.c_int, [c_f32p, C.c_int64, C.POINTER(View), C.POINTER(View), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    'ia_enc_im2col': (C.c_int, [C.POINTER(EncIm2colParams), C.c_void_p]),
+    'ia_layer_norm': (C.c_int, [c_f32p, C.c_int64, c_f32p, c_f32p, c_f32p, C.c_float, C.c_int64, C.c_int32, c_f32p, C.c_int64, c_u16p, c_u16p,
+                               C.c_int32, C.c_void_p]),
+    'ia_attention': (C.c_int, [C.POINTER(AttentionParams), C.c_void_p]),
+    'ia_dwconv_gelu': (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_f32p, c_u16p, c_u16p, C.c_int32,
+                                C.c_void_p]),
 }
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 _lib = None
 
 

@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, 'csrc')
 OBJ = os.path.join(HERE, '_build')
 LIB = os.path.join(HERE, 'libinvertavatar_b200.so')
 STAMP = LIB + '.srchash'
-SOURCES = ['ia_ops.cu', 'ia_modconv.cu', 'ia_fir_tma.cu', 'ia_conv_tc.cu', 'ia_raster.cu', 'ia_render.cu', 'ia_encoder.cu', 'ia_mesh.cu']
+SOURCES = ['ia_ops.cu', 'ia_modconv.cu', 'ia_fir_tma.cu', 'ia_conv_tc.cu', 'ia_raster.cu', 'ia_render.cu', 'ia_encoder.cu', 'ia_mesh.cu', 'ia_vit.cu']
 HEADERS = [os.path.join(CSRC, 'ia_common.cuh'), os.path.normpath(os.path.join(HERE, '..', 'include', 'invertavatar_b200.h'))]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=default']

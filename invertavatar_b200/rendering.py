@@ -96,8 +96,8 @@ class ImportanceRenderer_bsMotion(torch.nn.Module):
         super().__init__()
         self.ray_marcher = MipRayMarcher2()
         self.plane_axes = generate_planes()
-        self.depth_jitter = None     # [B, rays, Dc(,1)] U[0,1); consumed by the next forward
-        self.importance_u = None     # [B*rays, Df] U[0,1); consumed by the next forward when evaluation=False
+        self.depth_jitter = None     # [B, rays, Dc(,1)] U[0,1) (or a list: one per forward); consumed by the next forward
+        self.importance_u = None     # [B*rays, Df] U[0,1) (or a list); consumed by the next forward when evaluation=False
         self.fixed_jitter = None     # [B, rays, Dc] used by every forward while set (depth_jitter takes precedence)
         # decoder MLP arithmetic (ia_render_params.mlp_fmt): 3-term split by default (the op-level API reproduces the fp32 MLP);
         # TriPlaneGenerator sets rt.FMT_F16X1 from its measured error budget, IA_CONV_PRECISION=bf16x3 overrides it (strict mode)
@@ -125,7 +125,15 @@ class ImportanceRenderer_bsMotion(torch.nn.Module):
 
     def _draws(self, B, rays, Dc, Df, evaluation, device):
         jit, u = self.depth_jitter, self.importance_u
-        self.depth_jitter = self.importance_u = None
+        # a list pins several consecutive forwards (inversionNet.forward renders twice): one entry is consumed per call
+        if isinstance(jit, (list, tuple)):
+            jit, self.depth_jitter = (jit[0] if len(jit) else None), (list(jit[1:]) or None)
+        else:
+            self.depth_jitter = None
+        if isinstance(u, (list, tuple)):
+            u, self.importance_u = (u[0] if len(u) else None), (list(u[1:]) or None)
+        else:
+            self.importance_u = None
         if jit is None:
             jit = getattr(self, 'fixed_jitter', None)     # persistent (not consumed) jitter tensor: reproducible video / tests
         if jit is None:

@@ -1312,6 +1312,129 @@ def sft_half(x_nhwc, scale, shift):
 
 
 # ---------------------------------------------------------------------------------------------------
+# Mix-Transformer pieces of the improved one-shot encoder (csrc/ia_vit.cu).  Tokens are [B,H,W,C] fp32 maps.
+# ---------------------------------------------------------------------------------------------------
+def linear_pack(owner, weight, attr='_ia_pack'):
+    """ConvPack of an nn.Linear weight [Out,In] seen as a 1x1 convolution (cached on ``owner``, repacked when the parameter changes)."""
+    return ConvPack.current(owner, attr, weight.detach().view(weight.shape[0], weight.shape[1], 1, 1), need_wsq=False)
+
+
+class _Im2colPack(_EngineCache):
+    """ConvPack of a k x k nn.Conv2d weight laid out for the im2col GEMM: [O][kh][kw][I] flattened to a 1x1 convolution with
+    kh*kw*I input channels (the K order ia_enc_im2col writes)."""
+
+    def __init__(self, weight):
+        O, I, kh, kw = weight.shape
+        w2 = weight.detach().permute(0, 2, 3, 1).reshape(O, kh * kw * I, 1, 1).contiguous()
+        self.pack = ConvPack(w2, need_wsq=False)
+        self.k = kh
+        self.key = (weight.data_ptr(), weight._version, str(weight.device))
+
+    @staticmethod
+    def current(conv):
+        w = conv.weight
+        assert w.shape[2] == w.shape[3] and conv.groups == 1
+        c = conv.__dict__.get('_ia_pack_i2c')
+        if c is None or c.key != (w.data_ptr(), w._version, str(w.device)):
+            c = _Im2colPack(w)
+            conv.__dict__['_ia_pack_i2c'] = c
+        return c.pack
+
+
+def im2col_pack(conv):
+    return _Im2colPack.current(conv)
+
+
+def enc_im2col(srcs, k, stride, pad, K_pad=None):
+    """cat(srcs) [B,H,W,C] (tensors or (tensor, pixel_shuffle)) -> Split [B,OH,OW,K_pad] of k x k patches, K order (ky, kx, c)."""
+    views = [_as_view(s) for s in srcs]
+    B, H, W, _ = views[0][1]
+    for _, shp in views:
+        assert shp[:3] == (B, H, W), ('enc_im2col: sources disagree', [s for _, s in views])
+    Ctot = sum(shp[3] for _, shp in views)
+    dev = views[0][0]._keep.device
+    st = _enter(views[0][0]._keep)
+    OH, OW = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    K_pad = _pad_to(k * k * Ctot, 64) if K_pad is None else K_pad
+    sp = Split(torch.empty((B, OH, OW, K_pad), dtype=torch.bfloat16, device=dev), torch.empty((B, OH, OW, K_pad), dtype=torch.bfloat16, device=dev))
+    p = _C.EncIm2colParams()
+    for i, (v, _) in enumerate(views):
+        p.src[i] = v
+    p.nsrc = len(views)
+    p.B, p.H, p.W, p.k, p.stride, p.pad, p.OH, p.OW = B, H, W, int(k), int(stride), int(pad), OH, OW
+    p.hi, p.lo, p.K_pad = _p(sp.hi), _p(sp.lo), K_pad
+    _C.check(_C.lib().ia_enc_im2col(C.byref(p), st), 'ia_enc_im2col')
+    return sp
+
+
+def enc_gemm(a, pack):
+    """a: Split [B,H,W,K_pad]; pack: ConvPack of a 1x1 convolution -> raw fp32 accumulators [B,H,W,Cout] (bias not added)."""
+    assert pack.taps == 1 and a.C_pad == pack.Cin_pad, (pack.taps, a.C_pad, pack.Cin_pad)
+    B, H, W, _ = a.hi.shape
+    raw = torch.empty((B, H, W, pack.Cout), dtype=torch.float32, device=a.hi.device)
+    conv_same(a.hi, a.lo, pack, pack.Cin_pad, raw, mode=0)
+    return raw
+
+
+def layer_norm(x, ln, pre_bias=None, want_split=True, want32=False):
+    """torch.nn.LayerNorm ``ln`` over the channels of x [B,H,W,C] fp32 (dense rows; + pre_bias[c] first) ->
+    (Split [B,H,W,C_pad] or None, fp32 [B,H,W,C] or None)."""
+    _require_cuda(x)
+    st = _enter(x)
+    B, H, W, Cc = x.shape
+    assert x.dtype == torch.float32 and x.stride(3) == 1 and x.is_contiguous(), (x.dtype, x.stride())
+    assert tuple(ln.normalized_shape) == (Cc,) and ln.elementwise_affine
+    sp = out32 = None
+    if want_split:
+        C_pad = _pad_to(Cc, 64)
+        sp = Split(torch.empty((B, H, W, C_pad), dtype=torch.bfloat16, device=x.device), torch.empty((B, H, W, C_pad), dtype=torch.bfloat16, device=x.device))
+    if want32:
+        out32 = torch.empty((B, H, W, Cc), dtype=torch.float32, device=x.device)
+    _C.check(_C.lib().ia_layer_norm(_p(x), Cc, _p(pre_bias), _p(ln.weight), _p(ln.bias), float(ln.eps), B * H * W, Cc, _p(out32), Cc,
+                                    _p(sp.hi) if sp else None, _p(sp.lo) if sp else None, sp.C_pad if sp else 0, st), 'ia_layer_norm')
+    return sp, out32
+
+
+def attention(q, kv, heads, scale, q_bias=None, kv_bias=None, want32=False):
+    """q [B,H,W,C] and kv [B,h,w,2C] fp32 raw projections (kv channels = (k | v), heads-major inside each half, the layout of
+    mix_transformer.py:105) -> Split [B,H,W,C] of softmax(q k^T scale) v (the proj layer's operand) (+ fp32 copy)."""
+    _require_cuda(q, kv)
+    st = _enter(q)
+    B, H, W, Cc = q.shape
+    Bk, h, w, C2 = kv.shape
+    assert Bk == B and C2 == 2 * Cc and Cc % heads == 0 and q.is_contiguous() and kv.is_contiguous()
+    assert Cc % 64 == 0, 'attention: channel count must be a multiple of 64 (operand padding)'
+    sp = Split(torch.empty((B, H, W, Cc), dtype=torch.bfloat16, device=q.device), torch.empty((B, H, W, Cc), dtype=torch.bfloat16, device=q.device))
+    out32 = torch.empty((B, H, W, Cc), dtype=torch.float32, device=q.device) if want32 else None
+    p = _C.AttentionParams()
+    kvf = kv.view(-1)
+    p.q, p.k, p.v, p.q_ld, p.k_ld, p.v_ld = _p(q), _p(kvf), _p(kvf[Cc:]), Cc, C2, C2
+    if q_bias is not None:
+        p.q_bias = _p(q_bias)
+    if kv_bias is not None:
+        kb = kv_bias.detach()
+        p.k_bias, p.v_bias = _p(kb), _p(kb[Cc:])
+    p.B, p.heads, p.head_dim, p.Nq, p.Nk, p.scale = B, int(heads), Cc // heads, H * W, h * w, float(scale)
+    p.out32, p.out32_ld = _p(out32), Cc
+    p.hi, p.lo, p.C_pad = _p(sp.hi), _p(sp.lo), Cc
+    _C.check(_C.lib().ia_attention(C.byref(p), st), 'ia_attention')
+    return (sp, out32) if want32 else sp
+
+
+def dwconv_gelu(x, in_bias, dw):
+    """gelu(depthwise3x3(x + in_bias) + bias): x [B,H,W,C] raw fc1 accumulators, dw: nn.Conv2d(C, C, 3, 1, 1, groups=C) -> Split."""
+    _require_cuda(x)
+    st = _enter(x)
+    B, H, W, Cc = x.shape
+    assert x.is_contiguous() and tuple(dw.weight.shape) == (Cc, 1, 3, 3)
+    C_pad = _pad_to(Cc, 64)
+    sp = Split(torch.empty((B, H, W, C_pad), dtype=torch.bfloat16, device=x.device), torch.empty((B, H, W, C_pad), dtype=torch.bfloat16, device=x.device))
+    _C.check(_C.lib().ia_dwconv_gelu(_p(x), _p(in_bias), _p(dw.weight), _p(dw.bias), B, H, W, Cc, None, _p(sp.hi), _p(sp.lo), C_pad, st),
+             'ia_dwconv_gelu')
+    return sp
+
+
+# ---------------------------------------------------------------------------------------------------
 # output stage
 # ---------------------------------------------------------------------------------------------------
 def layout_grid_u8(img, grid_w=None, grid_h=1):

@@ -193,6 +193,40 @@ def randomize_encoder(net, seed=321):
     return net
 
 
+def randomize_by_name(net, seed=77):
+    """Overwrite EVERY parameter and floating-point buffer of ``net`` with values drawn from a generator seeded by the tensor's
+    own state-dict name (crc32(name) ^ seed), so that two implementations with the same state-dict names and shapes end up
+    with identical weights whatever order their constructors draw random numbers in (used for the SegFormer-style one-shot
+    encoder, SURVEY 8f-4, whose reference constructors re-initialise nested modules several times).  Magnitudes keep
+    activations O(1): matrices / filters N(0, 1/fan_in), biases 0.1 N(0,1), norm weights in [0.8, 1.2], PReLU slopes in
+    [0.1, 0.4], running variances in [0.5, 1.5]."""
+    import zlib
+    kinds = {}
+    for mname, m in net.named_modules():
+        for pname, _ in list(m.named_parameters(recurse=False)) + list(m.named_buffers(recurse=False)):
+            kinds[(mname + '.' if mname else '') + pname] = type(m).__name__
+    with torch.no_grad():
+        for name, v in net.state_dict().items():
+            if not v.dtype.is_floating_point:
+                continue
+            g = torch.Generator(device='cpu').manual_seed((zlib.crc32(name.encode()) ^ seed) & 0x7FFFFFFF)
+            leaf = name.rsplit('.', 1)[-1]
+            kind = kinds.get(name, '')
+            if v.ndim >= 2:
+                fan_in = v[0].numel()
+                val = torch.randn(v.shape, generator=g) * (1.0 / fan_in) ** 0.5
+            elif leaf == 'running_var':
+                val = 0.5 + torch.rand(v.shape, generator=g)
+            elif leaf == 'weight' and kind == 'PReLU':
+                val = 0.1 + 0.3 * torch.rand(v.shape, generator=g)
+            elif leaf == 'weight':
+                val = 0.8 + 0.4 * torch.rand(v.shape, generator=g)
+            else:
+                val = 0.1 * torch.randn(v.shape, generator=g)
+            v.copy_(val.to(v.device))
+    return net
+
+
 def encoder_inputs(T, seed=31):
     """SURVEY 8(d) encoder config: images clamp(N(0,0.5),-1,1) [T,3,512,512]; uv [T,6,256,256] = (random texture 3 ch,
     the UV mesh condition image 3 ch); cameras and mesh conditions of frames 0..T-1."""

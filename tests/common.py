@@ -69,3 +69,66 @@ def build_inversion_net(Dc=16, Df=16, res=64):
         net.generator.neural_rendering_resolution = res
         _ENC_CACHE[key] = net
     return _ENC_CACHE[key]
+
+
+# ---- improved one-shot encoder (tests/golden/make_golden_segformer.py) ----------------------------------
+MIT_KW = dict(patch_size=4, embed_dims=[64, 128, 320, 512], num_heads=[1, 2, 5, 8], mlp_ratios=[4, 4, 4, 4], qkv_bias=True,
+              depths=[2, 1, 1, 1], sr_ratios=[8, 4, 2, 1], drop_rate=0.0, drop_path_rate=0.1, in_chans=6)
+SEG_RES, SEG_DC, SEG_DF = 64, 16, 16
+_SEG_CACHE = {}
+
+
+def segformer_inputs(kind, seed=41):
+    """The inputs make_golden_segformer.py fed the reference."""
+    g = torch.Generator(device='cpu').manual_seed(seed)
+    if kind == 'tb':
+        return torch.randn(2, 96, 24, 24, generator=g)
+    if kind == 'mit':
+        return torch.randn(2, 6, 64, 64, generator=g)
+    if kind == 'texdec':
+        return (0.5 * torch.randn(2, 7, 256, 256, generator=g)).clamp(-1, 1)
+    if kind == 'tridec':
+        return (0.5 * torch.randn(2, 6, 256, 256, generator=g)).clamp(-1, 1)
+    raise KeyError(kind)
+
+
+def segformer_forward_draws(B=1):
+    return [(synth.depth_jitter(B, SEG_RES * SEG_RES, SEG_DC, seed=50 + i), synth.importance_u(B, SEG_RES * SEG_RES, SEG_DF, seed=60 + i))
+            for i in range(2)]
+
+
+def build_segformer_part(kind):
+    """Product modules with the weights of make_golden_segformer.py (name-keyed, so constructor draw order is irrelevant); CPU, eval."""
+    from functools import partial
+    from invertavatar_b200 import segformer as sf
+    if kind not in _SEG_CACHE:
+        if kind == 'tb':
+            m = sf.transformer_block(in_chans=96, num_vit=2)
+        elif kind == 'mit':
+            m = sf.MixVisionTransformer(norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), **MIT_KW)
+        elif kind == 'texdec':
+            m = sf.TriPlanefeat_SegformerDecoder(inp_ch=7, res=256)
+        elif kind == 'tridec':
+            m = sf.TriPlaneSFTfeat_SegformerDecoder(inp_ch=6, res=256)
+        else:
+            raise KeyError(kind)
+        _SEG_CACHE[kind] = synth.randomize_by_name(m.eval().requires_grad_(False))
+    return _SEG_CACHE[kind]
+
+
+def build_os_inversion_net():
+    """The product uvnet_new.inversionNet as make_golden_segformer.py built the reference's: generator under seed 0, e4e under seed 1
+    (+ randomize_encoder), the two decoders by name; eval mode (eval_updated_os.py:93).  On CPU."""
+    from invertavatar_b200.segformer import inversionNet
+    from invertavatar_b200.triplane import TriPlaneGenerator
+    if 'net' not in _SEG_CACHE:
+        torch.manual_seed(0)
+        G = TriPlaneGenerator(**synth.generator_kwargs(SEG_DC, SEG_DF)).eval().requires_grad_(False)
+        synth.randomize_noise_and_wavg(G)
+        G.neural_rendering_resolution = SEG_RES
+        torch.manual_seed(1)
+        net = inversionNet(generator=G, encoding_triplane=True, encoding_texture=True).eval().requires_grad_(False)
+        synth.randomize_encoder(net)
+        synth.randomize_by_name(net.unet_encoder)
+        _SEG_CACHE['net'] = net
+    return _SEG_CACHE['net']

@@ -66,7 +66,8 @@ def _struct_fields(name):
                                           ('ia_render_params', 'RenderParams'), ('ia_view', 'View'), ('ia_raster_level_params', 'RasterLevelParams'),
                                           ('ia_enc_prep_params', 'EncPrepParams'), ('ia_enc_affine_params', 'EncAffineParams'),
                                           ('ia_stitch_params', 'StitchParams'), ('ia_blendshape_params', 'BlendshapeParams'),
-                                          ('ia_ortho_raster_params', 'OrthoRasterParams')])
+                                          ('ia_ortho_raster_params', 'OrthoRasterParams'),
+                                          ('ia_enc_im2col_params', 'EncIm2colParams'), ('ia_attention_params', 'AttentionParams')])
 def test_ctypes_structs_follow_header(cname, pyname):
     from invertavatar_b200 import _C
     want = _struct_fields(cname)
