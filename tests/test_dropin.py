@@ -33,6 +33,9 @@ PATHS = {
     'encoder_inversion.models.uvnet': ['inversionNet'],
     'encoder_inversion.models.unet_encoders': ['ConvGRU', 'TriPlanefeat_Encoder', 'TriPlaneSFTfeat_Encoder'],
     'encoder_inversion.models.e4e': ['Encoder4Editing'],
+    'encoder_inversion.models.uvnet_new': ['inversionNet', 'improved_os_unet_encoder'],
+    'encoder_inversion.models.unet_transformer': ['UpLayer', 'TriPlanefeat_SegformerDecoder', 'TriPlaneSFTfeat_SegformerDecoder'],
+    'encoder_inversion.models.mmseg.mix_transformer': ['MixVisionTransformer', 'Block', 'Attention', 'Mlp', 'OverlapPatchEmbed', 'transformer_block', 'MLP'],
     'dnnlib.util': ['EasyDict', 'construct_class_by_name', 'open_url'],
     'legacy': ['load_network_pkl'],
 }
