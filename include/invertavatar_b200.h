@@ -476,6 +476,19 @@ typedef struct {
     uint16_t* hi; uint16_t* lo; int32_t C_pad;      /* operand of the proj layer [B*Nq][C_pad], C_pad == heads*head_dim */
 } ia_attention_params;
 int ia_attention(const ia_attention_params* p, void* stream);
+/* The same attention on the tensor cores for head_dim 256 without q/kv bias (transformer_block: 4 heads x 256, qkv_bias=False).
+ * Operands are the bf16 hi/lo splits that the q and kv projections emit from their epilogues (ia_emit.hi1/lo1): q [B][Nq][q_ld],
+ * kv [B][Nk][kv_ld] with k in channels [0, heads*256) and v in [heads*256, 2*heads*256) of a row; both q k^T and p v are 3-term
+ * split products (hi*hi + hi*lo + lo*hi, fp32 accumulate) on mma.sync.m16n8k16, softmax in fp32.  Writes the proj operand
+ * [B*Nq][C_pad] (+ optional fp32 copy). */
+typedef struct {
+    const uint16_t* q_hi; const uint16_t* q_lo; int64_t q_ld;
+    const uint16_t* kv_hi; const uint16_t* kv_lo; int64_t kv_ld;
+    int32_t B, heads, head_dim, Nq, Nk; float scale;
+    float* out32; int64_t out32_ld;
+    uint16_t* hi; uint16_t* lo; int32_t C_pad;
+} ia_attention_tc_params;
+int ia_attention_tc(const ia_attention_tc_params* p, void* stream);
 /* Mix-FFN middle (mix_transformer.py:46-49): gelu(depthwise3x3(x + in_bias) + bias), exact (erf) GELU, zero padding.
  * x [B][H][W][C] fp32 contiguous (raw fc1 accumulators), w [C][3][3]; writes fp32 out32 [B][H][W][C] and / or the fc2 operand. */
 int ia_dwconv_gelu(const float* x, const float* in_bias, const float* w, const float* bias, int32_t B, int32_t H, int32_t W,

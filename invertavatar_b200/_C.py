@@ -183,6 +183,14 @@ class AttentionParams(C.Structure):
                 ('hi', c_u16p), ('lo', c_u16p), ('C_pad', C.c_int32)]
 
 
+class AttentionTcParams(C.Structure):
+    _fields_ = [('q_hi', c_u16p), ('q_lo', c_u16p), ('q_ld', C.c_int64),
+                ('kv_hi', c_u16p), ('kv_lo', c_u16p), ('kv_ld', C.c_int64),
+                ('B', C.c_int32), ('heads', C.c_int32), ('head_dim', C.c_int32), ('Nq', C.c_int32), ('Nk', C.c_int32), ('scale', C.c_float),
+                ('out32', c_f32p), ('out32_ld', C.c_int64),
+                ('hi', c_u16p), ('lo', c_u16p), ('C_pad', C.c_int32)]
+
+
 # name -> (restype, argtypes); every symbol include/invertavatar_b200.h declares
 SIGNATURES = {
     'ia_abi_version': (C.c_int, []),
@@ -243,6 +251,7 @@ SIGNATURES = {
     'ia_layer_norm': (C.c_int, [c_f32p, C.c_int64, c_f32p, c_f32p, c_f32p, C.c_float, C.c_int64, C.c_int32, c_f32p, C.c_int64, c_u16p, c_u16p,
                                C.c_int32, C.c_void_p]),
     'ia_attention': (C.c_int, [C.POINTER(AttentionParams), C.c_void_p]),
+    'ia_attention_tc': (C.c_int, [C.POINTER(AttentionTcParams), C.c_void_p]),
     'ia_dwconv_gelu': (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_f32p, c_u16p, c_u16p, C.c_int32,
                                 C.c_void_p]),
 }

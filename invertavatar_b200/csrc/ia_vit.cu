@@ -236,6 +236,203 @@ __global__ void __launch_bounds__(256, 1) attention_kernel(ia_attention_params p
     }
 }
 
+// ---- attention on the tensor cores (head_dim 256: transformer_block) -----------------------------------------------------
+// Operands arrive as the bf16 hi/lo splits the q / kv projections emit from their epilogues ([B][N][C_pad], head h at channel
+// h*256); products are the 3-term split hi*hi + hi*lo + lo*hi (fp32-grade) on mma.sync.m16n8k16 with fp32 accumulators, for
+// both q k^T and p v (p in [0,1] is split in registers).  One CTA = 128 queries of one (image, head), 8 warps x 16 query rows;
+// keys / values stream through two 32-key shared-memory tiles (K and V separately, so the load of the next K tile overlaps
+// softmax + p v and the load of the next V tile overlaps q k^T).  Rows are 512 bytes; 16-byte chunks are XOR-swizzled with the
+// row index so every ldmatrix phase touches 8 distinct bank groups.
+struct AttnTcSmem {
+    uint16_t q[2][128 * 256];      // hi, lo
+    uint16_t k[2][32 * 256];
+    uint16_t v[2][32 * 256];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+    const int n = valid ? 16 : 0;      // src-size 0: the 16 destination bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// byte offset of 16-byte chunk `chunk` (0..31) of row `row` inside a [rows][256] bf16 tile
+__device__ __forceinline__ uint32_t swz(int row, int chunk) { return (uint32_t)(row * 512 + ((chunk ^ (row & 7)) << 4)); }
+
+__global__ void __launch_bounds__(256, 1) attention_tc_kernel(ia_attention_tc_params p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    AttnTcSmem& sm = *reinterpret_cast<AttnTcSmem*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+    const float sscale = p.scale * 1.4426950408889634f;
+    const uint16_t* qsrc[2] = {p.q_hi + ((int64_t)b * p.Nq) * p.q_ld + h * 256, p.q_lo + ((int64_t)b * p.Nq) * p.q_ld + h * 256};
+    const uint16_t* ksrc[2] = {p.kv_hi + ((int64_t)b * p.Nk) * p.kv_ld + h * 256, p.kv_lo + ((int64_t)b * p.Nk) * p.kv_ld + h * 256};
+    const int v_off = p.heads * 256;       // v follows k inside a kv row
+    const uint32_t q_s[2] = {smem_u32(sm.q[0]), smem_u32(sm.q[1])};
+    const uint32_t k_s[2] = {smem_u32(sm.k[0]), smem_u32(sm.k[1])};
+    const uint32_t v_s[2] = {smem_u32(sm.v[0]), smem_u32(sm.v[1])};
+
+    auto load_kv_tile = [&](const uint32_t (&dst)[2], int k0, int coff) {
+        // 32 rows x 32 chunks x {hi, lo} = 2048 chunks of 16 bytes, 8 per thread
+#pragma unroll
+        for (int part = 0; part < 2; ++part)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int idx = tid + i * 256;
+                const int row = idx >> 5, chunk = idx & 31;
+                const bool ok = k0 + row < p.Nk;
+                const uint16_t* src = ksrc[part] + (int64_t)(ok ? k0 + row : 0) * p.kv_ld + coff + chunk * 8;
+                cp_async16(dst[part] + swz(row, chunk), src, ok);
+            }
+    };
+    // group 0: Q tile + first K tile; group 1: first V tile
+#pragma unroll
+    for (int part = 0; part < 2; ++part)
+#pragma unroll 4
+        for (int i = 0; i < 16; ++i) {
+            const int idx = tid + i * 256;
+            const int row = idx >> 5, chunk = idx & 31;
+            const bool ok = q0 + row < p.Nq;
+            cp_async16(q_s[part] + swz(row, chunk), qsrc[part] + (int64_t)(ok ? q0 + row : 0) * p.q_ld + chunk * 8, ok);
+        }
+    load_kv_tile(k_s, 0, 0);
+    cp_async_commit();
+    load_kv_tile(v_s, 0, v_off);
+    cp_async_commit();
+
+    float o[32][4];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;       // rows g and g+8 of this warp's 16
+    const int arow = warp * 16 + (lane & 15);       // ldmatrix row of the A (query) fragments
+    const int achk = lane >> 4;                     // + 0 / 1 chunk (k 0-7 / 8-15)
+    // B fragments of q k^T (K rows = keys): lanes 0-7 keys n0..7 @k0, 8-15 same keys @k0+8, 16-23 keys n0+8.. @k0, 24-31 @k0+8
+    const int brow = (lane & 7) + ((lane >> 4) << 3);
+    const int bchk = (lane >> 3) & 1;
+    // B fragments of p v (V rows = keys, transposed load): lanes 0-7 keys 0-7 @dim n0, 8-15 keys 8-15 @n0, 16-23 keys 0-7 @n0+8, 24-31 keys 8-15 @n0+8
+    const int vrow = (lane & 7) + (((lane >> 3) & 1) << 3);
+    const int vchk = lane >> 4;
+
+    for (int k0 = 0; k0 < p.Nk; k0 += 32) {
+        cp_async_wait<1>();          // K tile of this iteration (and Q) landed; the V tile may still be in flight
+        __syncthreads();
+        float s[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+#pragma unroll 4
+        for (int ks = 0; ks < 16; ++ks) {
+            uint32_t ah[4], al[4], bh[2][4], bl[2][4];
+            ldsm_x4(q_s[0] + swz(arow, ks * 2 + achk), ah);
+            ldsm_x4(q_s[1] + swz(arow, ks * 2 + achk), al);
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+                ldsm_x4(k_s[0] + swz(jj * 16 + brow, ks * 2 + bchk), bh[jj]);
+                ldsm_x4(k_s[1] + swz(jj * 16 + brow, ks * 2 + bchk), bl[jj]);
+            }
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+                mma_bf16(s[jj * 2], ah, bh[jj][0], bh[jj][1]);
+                mma_bf16(s[jj * 2 + 1], ah, bh[jj][2], bh[jj][3]);
+                mma_bf16(s[jj * 2], ah, bl[jj][0], bl[jj][1]);
+                mma_bf16(s[jj * 2 + 1], ah, bl[jj][2], bl[jj][3]);
+                mma_bf16(s[jj * 2], al, bh[jj][0], bh[jj][1]);
+                mma_bf16(s[jj * 2 + 1], al, bh[jj][2], bh[jj][3]);
+            }
+        }
+        __syncthreads();             // every warp is done with the K tile: refill it with the next one while softmax / p v run
+        if (k0 + 32 < p.Nk) load_kv_tile(k_s, k0 + 32, 0);
+        cp_async_commit();
+        // online softmax (exp2 domain); key columns of n-tile j held by this thread: k0 + 8j + 2t, +1
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = k0 + j * 8 + 2 * t;
+            s[j][0] = c < p.Nk ? s[j][0] * sscale : -INFINITY;
+            s[j][1] = c + 1 < p.Nk ? s[j][1] * sscale : -INFINITY;
+            s[j][2] = c < p.Nk ? s[j][2] * sscale : -INFINITY;
+            s[j][3] = c + 1 < p.Nk ? s[j][3] * sscale : -INFINITY;
+            mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+            mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);       // finite: key k0 is valid
+        const float c0 = exp2f(m0 - mn0), c1 = exp2f(m1 - mn1);
+        m0 = mn0; m1 = mn1;
+        float rs0 = 0.f, rs1 = 0.f;
+        uint32_t ph[2][4], pl[2][4];      // A fragments of p (hi / lo) for the two 16-key k-steps
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float e0 = exp2f(s[j][0] - mn0), e1 = exp2f(s[j][1] - mn0), e2 = exp2f(s[j][2] - mn1), e3 = exp2f(s[j][3] - mn1);
+            rs0 += e0 + e1; rs1 += e2 + e3;
+            // n-tile j covers keys 8j..8j+7: k-step j/2, low (a0,a1) or high (a2,a3) half
+            split_bf16x2(e0, e1, ph[j >> 1][(j & 1) * 2], pl[j >> 1][(j & 1) * 2]);
+            split_bf16x2(e2, e3, ph[j >> 1][(j & 1) * 2 + 1], pl[j >> 1][(j & 1) * 2 + 1]);
+        }
+        rs0 += __shfl_xor_sync(0xffffffffu, rs0, 1); rs0 += __shfl_xor_sync(0xffffffffu, rs0, 2);
+        rs1 += __shfl_xor_sync(0xffffffffu, rs1, 1); rs1 += __shfl_xor_sync(0xffffffffu, rs1, 2);
+        l0 = l0 * c0 + rs0; l1 = l1 * c1 + rs1;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { o[j][0] *= c0; o[j][1] *= c0; o[j][2] *= c1; o[j][3] *= c1; }
+        cp_async_wait<1>();          // V tile of this iteration landed (the K refill just committed may still be in flight)
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+#pragma unroll
+            for (int jn = 0; jn < 16; ++jn) {        // 2 n-tiles (16 dims) per step
+                uint32_t vh[4], vl[4];
+                ldsm_x4_trans(v_s[0] + swz(kk * 16 + vrow, jn * 2 + vchk), vh);
+                ldsm_x4_trans(v_s[1] + swz(kk * 16 + vrow, jn * 2 + vchk), vl);
+                mma_bf16(o[jn * 2], ph[kk], vh[0], vh[1]);
+                mma_bf16(o[jn * 2 + 1], ph[kk], vh[2], vh[3]);
+                mma_bf16(o[jn * 2], ph[kk], vl[0], vl[1]);
+                mma_bf16(o[jn * 2 + 1], ph[kk], vl[2], vl[3]);
+                mma_bf16(o[jn * 2], pl[kk], vh[0], vh[1]);
+                mma_bf16(o[jn * 2 + 1], pl[kk], vh[2], vh[3]);
+            }
+        }
+        __syncthreads();             // V tile consumed
+        if (k0 + 32 < p.Nk) load_kv_tile(v_s, k0 + 32, v_off);
+        cp_async_commit();
+    }
+    cp_async_wait<0>();
+    const float i0 = 1.f / l0, i1 = 1.f / l1;
+    const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const int c = h * 256 + j * 8 + 2 * t;
+        if (r0 < p.Nq) {
+            const int64_t row = (int64_t)b * p.Nq + r0;
+            uint32_t hv, lv;
+            split_bf16x2(o[j][0] * i0, o[j][1] * i0, hv, lv);
+            *reinterpret_cast<uint32_t*>(p.hi + row * p.C_pad + c) = hv;
+            *reinterpret_cast<uint32_t*>(p.lo + row * p.C_pad + c) = lv;
+            if (p.out32) *reinterpret_cast<float2*>(p.out32 + row * p.out32_ld + c) = make_float2(o[j][0] * i0, o[j][1] * i0);
+        }
+        if (r1 < p.Nq) {
+            const int64_t row = (int64_t)b * p.Nq + r1;
+            uint32_t hv, lv;
+            split_bf16x2(o[j][2] * i1, o[j][3] * i1, hv, lv);
+            *reinterpret_cast<uint32_t*>(p.hi + row * p.C_pad + c) = hv;
+            *reinterpret_cast<uint32_t*>(p.lo + row * p.C_pad + c) = lv;
+            if (p.out32) *reinterpret_cast<float2*>(p.out32 + row * p.out32_ld + c) = make_float2(o[j][2] * i1, o[j][3] * i1);
+        }
+    }
+}
+
 // ---- depthwise 3x3 (+ input bias, + bias) + GELU -> operand -----------------------------------------------------------
 __global__ void __launch_bounds__(256) dwconv_gelu_kernel(const float* __restrict__ x, const float* __restrict__ in_bias,
                                                           const float* __restrict__ w, const float* __restrict__ bias, int B, int H, int W,
@@ -355,6 +552,31 @@ extern "C" int ia_attention(const ia_attention_params* p, void* stream) {
         IA_CHECK(false, "ia_attention: C_pad (%d) must equal heads*head_dim (%lld)", p->C_pad, (long long)Cc);
     }
     return p->head_dim == 64 ? launch_attention<64>(p, as_stream(stream)) : launch_attention<256>(p, as_stream(stream));
+}
+
+extern "C" int ia_attention_tc(const ia_attention_tc_params* p, void* stream) {
+    IA_CHECK(p && p->q_hi && p->q_lo && p->kv_hi && p->kv_lo && p->hi && p->lo, "ia_attention_tc: null operand");
+    IA_CHECK(p->B > 0 && p->heads > 0 && p->Nq > 0 && p->Nk > 0, "ia_attention_tc: bad sizes");
+    IA_CHECK(p->head_dim == 256, "ia_attention_tc: head_dim %d not instantiated (256: transformer_block); use ia_attention", p->head_dim);
+    const int64_t Cc = (int64_t)p->heads * 256;
+    IA_CHECK(p->q_ld >= Cc && p->kv_ld >= 2 * Cc && ((p->q_ld | p->kv_ld | p->C_pad) & 7) == 0 && p->C_pad >= Cc,
+             "ia_attention_tc: row pitches must cover heads*256 (q, out) / 2*heads*256 (kv) channels and be multiples of 8");
+    IA_CHECK((((uintptr_t)p->q_hi | (uintptr_t)p->q_lo | (uintptr_t)p->kv_hi | (uintptr_t)p->kv_lo) & 15) == 0, "ia_attention_tc: operands must be 16-byte aligned");
+    IA_CHECK(!p->out32 || (p->out32_ld >= Cc && (p->out32_ld & 1) == 0), "ia_attention_tc: out32_ld");
+    const size_t smem = sizeof(AttnTcSmem);
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        IA_CHECK(e == cudaSuccess, "ia_attention_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        attr_set[dev] = true;
+    }
+    dim3 grid((unsigned)cdiv(p->Nq, 128), (unsigned)p->heads, (unsigned)p->B);
+    ia::prof_begin("ia_attention_tc", as_stream(stream));
+    attention_tc_kernel<<<grid, 256, smem, as_stream(stream)>>>(*p);
+    IA_LAUNCH_CHECK("ia_attention_tc");
+    return 0;
 }
 
 extern "C" int ia_dwconv_gelu(const float* x, const float* in_bias, const float* w, const float* bias, int32_t B, int32_t H, int32_t W,

@@ -1367,13 +1367,42 @@ def enc_im2col(srcs, k, stride, pad, K_pad=None):
     return sp
 
 
-def enc_gemm(a, pack):
-    """a: Split [B,H,W,K_pad]; pack: ConvPack of a 1x1 convolution -> raw fp32 accumulators [B,H,W,Cout] (bias not added)."""
+def enc_gemm(a, pack, emit_split=False):
+    """a: Split [B,H,W,K_pad]; pack: ConvPack of a 1x1 convolution -> raw fp32 accumulators [B,H,W,Cout] (bias not added), or,
+    with emit_split, the same values as the bf16 hi/lo operand [B,H,W,Cout] written by the GEMM's epilogue (no fp32 round trip)."""
     assert pack.taps == 1 and a.C_pad == pack.Cin_pad, (pack.taps, a.C_pad, pack.Cin_pad)
     B, H, W, _ = a.hi.shape
+    if emit_split:
+        assert pack.Cout % 64 == 0
+        sp = new_split(B, H, W, pack.Cout, a.hi.device)
+        conv_same(a.hi, a.lo, pack, pack.Cin_pad, None, mode=0, e1=(sp, None))
+        return sp
     raw = torch.empty((B, H, W, pack.Cout), dtype=torch.float32, device=a.hi.device)
     conv_same(a.hi, a.lo, pack, pack.Cin_pad, raw, mode=0)
     return raw
+
+
+def attention_tc_available(head_dim, q_bias, kv_bias):
+    """Tensor-core attention (ia_attention_tc) covers head_dim 256 without q/kv bias -- transformer_block's configuration."""
+    return head_dim == 256 and q_bias is None and kv_bias is None and os.environ.get('IA_ATTENTION', 'tc') != 'simt'
+
+
+def attention_tc(q, kv, heads, scale, want32=False):
+    """q: Split [B,H,W,C], kv: Split [B,h,w,2C] (the q / kv projections' emitted operands) -> Split [B,H,W,C] (+ fp32 copy)."""
+    st = _enter(q.hi)
+    B, H, W, Cc = q.hi.shape
+    Bk, h, w, C2 = kv.hi.shape
+    assert Bk == B and C2 == 2 * Cc and Cc == heads * 256 and q.fmt == FMT_BF16X3 and kv.fmt == FMT_BF16X3
+    assert q.hi.is_contiguous() and kv.hi.is_contiguous()
+    sp = new_split(B, H, W, Cc, q.hi.device)
+    out32 = torch.empty((B, H, W, Cc), dtype=torch.float32, device=q.hi.device) if want32 else None
+    p = _C.AttentionTcParams()
+    p.q_hi, p.q_lo, p.q_ld, p.kv_hi, p.kv_lo, p.kv_ld = _p(q.hi), _p(q.lo), Cc, _p(kv.hi), _p(kv.lo), C2
+    p.B, p.heads, p.head_dim, p.Nq, p.Nk, p.scale = B, int(heads), 256, H * W, h * w, float(scale)
+    p.out32, p.out32_ld = _p(out32), Cc
+    p.hi, p.lo, p.C_pad = _p(sp.hi), _p(sp.lo), Cc
+    _C.check(_C.lib().ia_attention_tc(C.byref(p), st), 'ia_attention_tc')
+    return (sp, out32) if want32 else sp
 
 
 def layer_norm(x, ln, pre_bias=None, want_split=True, want32=False):

@@ -111,6 +111,12 @@ class Attention(nn.Module):
     def run_raw(self, a, x32):
         """a: Split of the normalised tokens [B,H,W,C]; x32: the same tokens in fp32 (needed when sr_ratio > 1, else None)
         -> raw proj accumulators [B,H,W,C] (proj.bias not added)."""
+        if self.sr_ratio == 1 and rt.attention_tc_available(self.dim // self.num_heads, self.q.bias, self.kv.bias):
+            # tensor-core attention: the q / kv projections emit their bf16 hi/lo operands straight from the GEMM epilogue
+            q = rt.enc_gemm(a, rt.linear_pack(self.q, self.q.weight), emit_split=True)
+            kv = rt.enc_gemm(a, rt.linear_pack(self.kv, self.kv.weight), emit_split=True)
+            att = rt.attention_tc(q, kv, self.num_heads, self.scale)
+            return rt.enc_gemm(att, rt.linear_pack(self.proj, self.proj.weight))
         q = rt.enc_gemm(a, rt.linear_pack(self.q, self.q.weight))
         if self.sr_ratio > 1:
             pk = rt.im2col_pack(self.sr)

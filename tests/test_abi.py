@@ -67,7 +67,8 @@ def _struct_fields(name):
                                           ('ia_enc_prep_params', 'EncPrepParams'), ('ia_enc_affine_params', 'EncAffineParams'),
                                           ('ia_stitch_params', 'StitchParams'), ('ia_blendshape_params', 'BlendshapeParams'),
                                           ('ia_ortho_raster_params', 'OrthoRasterParams'),
-                                          ('ia_enc_im2col_params', 'EncIm2colParams'), ('ia_attention_params', 'AttentionParams')])
+                                          ('ia_enc_im2col_params', 'EncIm2colParams'), ('ia_attention_params', 'AttentionParams'),
+                                          ('ia_attention_tc_params', 'AttentionTcParams')])
 def test_ctypes_structs_follow_header(cname, pyname):
     from invertavatar_b200 import _C
     want = _struct_fields(cname)

@@ -100,6 +100,44 @@ def test_attention_vs_torch(heads, hd, Nq_hw, Nk_hw, bias):
     assert float((_join(sp).cpu() - want).abs().max()) < 4e-5 * max(1.0, float(want.abs().max()))
 
 
+def _split_of(x):
+    """fp32 -> Split (bf16 hi/lo) on the device, as a GEMM epilogue would emit it."""
+    hi = x.bfloat16()
+    lo = (x - hi.float()).bfloat16()
+    return rt.Split(hi.contiguous(), lo.contiguous())
+
+
+@pytest.mark.parametrize('heads,Nq_hw,Nk_hw,gain', [(4, (8, 8), (8, 8), 1.0), (4, (12, 12), (12, 12), 3.0), (2, (17, 9), (5, 7), 2.0), (4, (32, 32), (32, 32), 1.0)])
+def test_attention_tc_vs_torch(heads, Nq_hw, Nk_hw, gain):
+    """Tensor-core attention (mma.sync, 3-term bf16 split for q k^T and p v) vs float64: ragged query / key tiles (N not a multiple of
+    128 / 32), Nk != Nq, logits of several units (gain), against the values the split operands actually hold."""
+    g = torch.Generator().manual_seed(heads + Nq_hw[0])
+    Cc = heads * 256
+    B = 2
+    q = torch.randn(B, *Nq_hw, Cc, generator=g).to(DEV)
+    kv = torch.randn(B, *Nk_hw, 2 * Cc, generator=g).to(DEV)
+    qs, kvs = _split_of(q), _split_of(kv)
+    scale = 256 ** -0.5 * gain
+    sp, out = rt.attention_tc(qs, kvs, heads, scale, want32=True)
+    qq = _join(qs).double().reshape(B, -1, heads, 256).permute(0, 2, 1, 3)
+    kk = _join(kvs).double().reshape(B, -1, 2, heads, 256).permute(2, 0, 3, 1, 4)
+    want = (((qq @ kk[0].transpose(-2, -1)) * scale).softmax(-1) @ kk[1]).transpose(1, 2).reshape(B, *Nq_hw, Cc).float().cpu()
+    assert float((out.cpu() - want).abs().max()) < 3e-5 * max(1.0, float(want.abs().max()))
+    assert float((_join(sp).cpu() - want).abs().max()) < 5e-5 * max(1.0, float(want.abs().max()))
+
+
+def test_attention_paths_agree(monkeypatch):
+    """A transformer_block Block through the tensor-core attention and through the fp32 CUDA-core kernel (IA_ATTENTION=simt)."""
+    tb = build_segformer_part('tb')
+    blk = copy.deepcopy(tb.ViT[0]).to(DEV)
+    x = torch.randn(2, 20 * 12, 1024, generator=torch.Generator().manual_seed(5)).to(DEV)
+    with torch.no_grad():
+        a = blk(x, 20, 12)
+        monkeypatch.setenv('IA_ATTENTION', 'simt')
+        b = blk(x, 20, 12)
+    assert rel_err(a, b) < 5e-5
+
+
 def test_dwconv_gelu_vs_torch():
     g = torch.Generator().manual_seed(3)
     C = 128

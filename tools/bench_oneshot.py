@@ -1,6 +1,6 @@
 """eval_updated_os.py one-shot path: e4e encode + uvnet_new.inversionNet.forward (two 128^2 x 48+48 renders, the two
 SegFormer-style decoders) on one source image, then the per-frame synthesis_withTexture driver, on cuda:0, with the per-kernel
-device-time breakdown and the roofline position of the two dominant kernels (tcgen05 GEMMs / CUDA-core attention).
+device-time breakdown and the roofline position of the two dominant kernels (tcgen05 GEMMs / mma.sync flash attention).
 Prints one JSON line.   python tools/bench_oneshot.py [steps]"""
 import json
 import os
@@ -82,6 +82,8 @@ print(json.dumps({
              'algorithmic_gflop': fl['algorithmic'] / 1e9, 'issued_mma_gflop': fl['issued_mma'] / 1e9,
              'achieved_tflops': fl['algorithmic'] / conv_ms / 1e9 if conv_ms else None,
              'peak_tflops_sustained': peaks.get('bf16_tflops_sustained'), 'bound': 'tensor'},
-    'attention': {'kernel': 'attention_kernel<256> (fp32 CUDA-core flash attention)', 'ms': att_ms, 'algorithmic_gflop': att_fl / 1e9,
-                  'achieved_tflops': att_fl / att_ms / 1e9 if att_ms else None, 'bound': 'fp32 FMA issue (CUDA cores), no tensor cores'},
+    'attention': {'kernel': 'attention_tc_kernel (flash attention on mma.sync.m16n8k16, 3-term bf16 split for q k^T and p v; IA_ATTENTION=simt: '
+                            'attention_kernel<256>, fp32 CUDA cores)', 'ms': att_ms, 'algorithmic_gflop': att_fl / 1e9,
+                  'achieved_tflops': att_fl / att_ms / 1e9 if att_ms else None,
+                  'issued_mma_tflops': 3 * att_fl / att_ms / 1e9 if att_ms else None, 'bound': 'tensor (mma.sync) / shared-memory operand fetch'},
 }))
