@@ -609,16 +609,48 @@ __device__ __forceinline__ void epilogue_chunk_v4(const Tc2Params& p, const floa
 
 // mode 2: ToRGB tail on a [32 rows][32 channels] chunk -- out = upsample2d(img_prev) + clamp(acc + bias), the arithmetic (and
 // the order of operations) of torgb_finish_vec4_kernel in ia_modconv.cu.  `prev` points at this image's img_prev, channel co0.
+// Per-row set-up of the ToRGB tail, computed once per tile by the lane that owns the row: pixel offset of the (y0, x0) tap inside
+// the half-resolution previous image (coordinates clamped into the image) and a code holding the steps to x1 / y1 (0 when clamped
+// away) and the four separable weights as indices into {0, 0.25, 0.75} (0 = tap outside the image: fmaf(0, q, up) == up, so the
+// sum equals the skip-the-tap formulation of torgb_finish_vec4_kernel bit for bit).
+__device__ __forceinline__ void torgb_row_setup(int y, int x, int h2, int w2, int& o00, int& code) {
+    const int my = y >> 1, mx = x >> 1;
+    int y0, y1, x0, x1, iy0, iy1, ix0, ix1;      // weight indices: 1 = 0.25, 2 = 0.75
+    if (y & 1) { y0 = my; y1 = my + 1; iy0 = 2; iy1 = 1; } else { y0 = my - 1; y1 = my; iy0 = 1; iy1 = 2; }
+    if (x & 1) { x0 = mx; x1 = mx + 1; ix0 = 2; ix1 = 1; } else { x0 = mx - 1; x1 = mx; ix0 = 1; ix1 = 2; }
+    if (y0 < 0) { y0 = 0; iy0 = 0; }
+    if (y1 >= h2) { y1 = h2 - 1; iy1 = 0; }
+    if (x0 < 0) { x0 = 0; ix0 = 0; }
+    if (x1 >= w2) { x1 = w2 - 1; ix1 = 0; }
+    o00 = y0 * w2 + x0;
+    code = (x1 - x0) | ((y1 - y0) << 1) | (iy0 << 2) | (iy1 << 4) | (ix0 << 6) | (ix1 << 8);
+}
+
+// mode 2: ToRGB tail on a [32 rows][32 channels] chunk -- out = upsample2d(img_prev) + clamp(acc + bias), the arithmetic (and
+// the order of operations) of torgb_finish_vec4_kernel in ia_modconv.cu.  `prev` points at this image's img_prev, channel co0.
+// The four taps of a row are loaded unconditionally (clamped addresses, zero weights) and back to back: one exposed L2 latency per
+// iteration instead of four.
 __device__ __forceinline__ void epilogue_chunk_v4_torgb(const Tc2Params& p, const float* tsm, int lane, uint32_t vmask, int my_pix,
-                                                        float* o32, const float4 bs, const float* prev) {
+                                                        int my_o00, int my_code, float* o32, const float4 bs, const float* prev) {
     const int rs = lane >> 3, c4 = lane & 7;
     const float clampv = p.clamp;
-    const int h2 = p.OH >> 1, w2 = p.OW >> 1;
+    const int w2 = p.OW >> 1;
 #pragma unroll 2
     for (int i = 0; i < 8; ++i) {
         const int rr = 4 * i + rs;
         const int pix_r = __shfl_sync(0xffffffffu, my_pix, rr);
-        if (!((vmask >> rr) & 1u)) continue;
+        const int o00 = __shfl_sync(0xffffffffu, my_o00, rr);
+        const int code = __shfl_sync(0xffffffffu, my_code, rr);
+        const bool ok = (vmask >> rr) & 1u;
+        float4 q00, q01, q10, q11;
+        if (prev) {      // rows that are not valid carry o00 = 0, code = 0: in-bounds loads, never stored
+            const float* b00 = prev + (int64_t)o00 * p.Cout;
+            const int dx = (code & 1) * p.Cout, dy = ((code >> 1) & 1) * w2 * p.Cout;
+            q00 = __ldg(reinterpret_cast<const float4*>(b00));
+            q01 = __ldg(reinterpret_cast<const float4*>(b00 + dx));
+            q10 = __ldg(reinterpret_cast<const float4*>(b00 + dy));
+            q11 = __ldg(reinterpret_cast<const float4*>(b00 + dy + dx));
+        }
         float4 v = *reinterpret_cast<const float4*>(tsm + rr * kTsmLd + c4 * 4);
         v.x += bs.x; v.y += bs.y; v.z += bs.z; v.w += bs.w;
         if (clampv >= 0.f) {
@@ -626,21 +658,16 @@ __device__ __forceinline__ void epilogue_chunk_v4_torgb(const Tc2Params& p, cons
             v.z = fminf(fmaxf(v.z, -clampv), clampv); v.w = fminf(fmaxf(v.w, -clampv), clampv);
         }
         if (prev) {
-            const int y = pix_r / p.OW, x = pix_r - y * p.OW;
-            const int my = y >> 1, mx = x >> 1;
-            int y0, y1, x0, x1; float wy0, wy1, wx0, wx1;
-            if (y & 1) { y0 = my; y1 = my + 1; wy0 = 0.75f; wy1 = 0.25f; } else { y0 = my - 1; y1 = my; wy0 = 0.25f; wy1 = 0.75f; }
-            if (x & 1) { x0 = mx; x1 = mx + 1; wx0 = 0.75f; wx1 = 0.25f; } else { x0 = mx - 1; x1 = mx; wx0 = 0.25f; wx1 = 0.75f; }
+            auto wt = [](int idx) { return 0.25f * (float)(idx + (idx >> 1)); };      // 0, 0.25, 0.75
+            const float wy0 = wt((code >> 2) & 3), wy1 = wt((code >> 4) & 3), wx0 = wt((code >> 6) & 3), wx1 = wt((code >> 8) & 3);
             float4 up = make_float4(0.f, 0.f, 0.f, 0.f);
-            auto tap = [&](int yy, int xx, float w) {
-                if (yy < 0 || yy >= h2 || xx < 0 || xx >= w2) return;
-                const float4 q = __ldg(reinterpret_cast<const float4*>(prev + ((int64_t)yy * w2 + xx) * p.Cout));
+            auto tap = [&](const float4& q, float w) {
                 up.x = fmaf(w, q.x, up.x); up.y = fmaf(w, q.y, up.y); up.z = fmaf(w, q.z, up.z); up.w = fmaf(w, q.w, up.w);
             };
-            tap(y0, x0, wy0 * wx0); tap(y0, x1, wy0 * wx1); tap(y1, x0, wy1 * wx0); tap(y1, x1, wy1 * wx1);
+            tap(q00, wy0 * wx0); tap(q01, wy0 * wx1); tap(q10, wy1 * wx0); tap(q11, wy1 * wx1);
             v.x += up.x; v.y += up.y; v.z += up.z; v.w += up.w;
         }
-        *reinterpret_cast<float4*>(o32 + (int64_t)pix_r * p.emit.out32_ld) = v;
+        if (ok) *reinterpret_cast<float4*>(o32 + (int64_t)pix_r * p.emit.out32_ld) = v;
     }
 }
 
@@ -941,6 +968,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                 const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
                 const int my_pix = (cat_img * p.OH + oy) * p.OW + ox;  // pixel index inside the image (fits in int)
                 float my_nz = 0.f;
+                int my_o00 = 0, my_code = 0;        // ToRGB tail (mode 2): per-row tap set-up, see torgb_row_setup
+                if (p.mode == 2 && p.img_prev && valid) torgb_row_setup(oy, ox, p.OH >> 1, p.OW >> 1, my_o00, my_code);
                 const int grp = img / p.ipg;
                 if (valid && p.mode == 1 && p.noise)
                     my_nz = p.noise[(int64_t)grp * p.noise_gstride + (int64_t)img * p.noise_bstride + my_pix] * p.noise_strength[grp];
@@ -1064,7 +1093,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                             }
                             if (p.mode == 2) {
                                 const float* prev = p.img_prev ? p.img_prev + (int64_t)img * (p.OH >> 1) * (p.OW >> 1) * p.Cout + co0 : nullptr;
-                                epilogue_chunk_v4_torgb(p, tsm, lane, vm, my_pix, o32, bs4, prev);
+                                epilogue_chunk_v4_torgb(p, tsm, lane, vm, my_pix, my_o00, my_code, o32, bs4, prev);
                             }
                             else if (p.mode == 0) epilogue_chunk_v4_dispatch<0>(p, tsm, lane, vm, my_pix, my_nz, o32, h1, l1, h2, l2, dc4, bs4, s14, s24, rg, racc, false);
                             else if (p.act == IA_ACT_LRELU) epilogue_chunk_v4_dispatch<IA_ACT_LRELU>(p, tsm, lane, vm, my_pix, my_nz, o32, h1, l1, h2, l2, dc4, bs4, s14, s24, rg, racc, rgb);
