@@ -46,7 +46,9 @@ int64_t ia_profile_report(char* buf, int64_t buflen);
 
 /* Activation ids follow the reference's cuda_idx (torch_utils/ops/bias_act.py:23-33). */
 enum { IA_ACT_LINEAR = 1, IA_ACT_RELU = 2, IA_ACT_LRELU = 3, IA_ACT_TANH = 4, IA_ACT_SIGMOID = 5,
-       IA_ACT_ELU = 6, IA_ACT_SELU = 7, IA_ACT_SOFTPLUS = 8, IA_ACT_SWISH = 9 };
+       IA_ACT_ELU = 6, IA_ACT_SELU = 7, IA_ACT_SOFTPLUS = 8, IA_ACT_SWISH = 9,
+       /* not a reference id: torch.nn.PReLU with per-channel slopes inside a convolution epilogue (ia_conv_params.slope) */
+       IA_ACT_PRELU = 10 };
 
 /* Element types of the three plugin-level entry points.  The reference dispatches bias_act / upfirdn2d over double, float
  * and half (AT_DISPATCH_FLOATING_TYPES_AND_HALF, bias_act.cpp:81, upfirdn2d.cpp:67) and filtered_lrelu over float / half
@@ -218,6 +220,10 @@ typedef struct {
      * (per split: tiles x 256 x N-tile x 4 bytes; counters: 8 per tile). */
     float* splitk_ws; int64_t splitk_ws_bytes; int32_t* splitk_counters; int32_t splitk_n_counters;
     int32_t op_fmt;          /* IA_OPFMT_* of a_* and w_* (a_lo / w_lo unused for F16X1) */
+    /* act == IA_ACT_PRELU (mode 1): v = prelu(v + bias; slope[co]) -- the PReLU that follows a convolution of the inversion encoder
+     * (helpers.py:111, unet_encoders.py:58-62), so that the layer emits the next convolution's operand (emit.hi1/lo1) without an fp32
+     * round trip.  slope: [Cout]; emit 2 must be unused. */
+    const float* slope;
 } ia_conv_params;
 /* Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05.mma, TMEM accumulators, TMA-fed). */
 int ia_conv_tc(const ia_conv_params* p, void* stream);
@@ -420,6 +426,9 @@ typedef struct {
     ia_view res; const float* res_scale; const float* res_shift;
     float* y; int64_t y_ld;
     int32_t B, H, W, C;
+    /* optional second output (all NULL / 0: none): the bf16 hi/lo operand [B][H][W][e_C_pad] of the next convolution,
+     * split(y * e_scale[c] + e_shift[c]) -- e.g. the BatchNorm that opens the next IR-SE unit (helpers.py:109) in eval mode */
+    const float* e_scale; const float* e_shift; uint16_t* e_hi; uint16_t* e_lo; int32_t e_C_pad;
 } ia_enc_affine_params;
 int ia_enc_affine_act(const ia_enc_affine_params* p, void* stream);
 /* pooled[b][c] = mean over H,W of x*scale[c] + shift[c] (AdaptiveAvgPool2d(1) of SEModule, helpers.py:65,74). */

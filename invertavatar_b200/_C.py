@@ -68,7 +68,8 @@ class ConvParams(C.Structure):
                 ('groups', C.c_int32), ('imgs_per_group', C.c_int32), ('noise_gstride', C.c_int64),
                 ('img_prev', c_f32p), ('a_img_rows', C.c_int32),
                 ('splitk_ws', c_f32p), ('splitk_ws_bytes', C.c_int64), ('splitk_counters', c_i32p), ('splitk_n_counters', C.c_int32),
-                ('op_fmt', C.c_int32)]
+                ('op_fmt', C.c_int32),
+                ('slope', c_f32p)]
 
 
 class FirParams(C.Structure):
@@ -165,7 +166,8 @@ class EncAffineParams(C.Structure):
                 ('gate', c_f32p),
                 ('res', View), ('res_scale', c_f32p), ('res_shift', c_f32p),
                 ('y', c_f32p), ('y_ld', C.c_int64),
-                ('B', C.c_int32), ('H', C.c_int32), ('W', C.c_int32), ('C', C.c_int32)]
+                ('B', C.c_int32), ('H', C.c_int32), ('W', C.c_int32), ('C', C.c_int32),
+                ('e_scale', c_f32p), ('e_shift', c_f32p), ('e_hi', c_u16p), ('e_lo', c_u16p), ('e_C_pad', C.c_int32)]
 
 
 class EncIm2colParams(C.Structure):

@@ -97,6 +97,7 @@ __device__ __forceinline__ float apply_act(float x, int act, float alpha) {
         case IA_ACT_SELU: return x > 0.f ? 1.0507009873554805f * x : 1.0507009873554805f * 1.6732632423543772f * expm1f(x);
         case IA_ACT_SOFTPLUS: return x > 20.f ? x : log1pf(expf(x));
         case IA_ACT_SWISH: return x / (1.f + expf(-x));
+        case IA_ACT_PRELU: return x > 0.f ? x : x * alpha;      // alpha = this channel's slope (convolution epilogues only)
     }
     return x;
 }

@@ -41,7 +41,7 @@ struct TcParams {
     int OH, OW, sy, sx, py, px;
     int mode; const float* dcoef; const float* noise; const float* noise_strength; const float* bias;
     long long noise_bstride;
-    int act; float alpha, gain, clamp;
+    int act; float alpha, gain, clamp; const float* slope;   // slope: per-channel PReLU slopes (IA_ACT_PRELU)
     ia_emit emit;
     int groups, ipg, n_taps_total; long long noise_gstride;   // grouped launch (see ia_conv_params)
     int nops;             // operand tensors per side: 2 (bf16 hi/lo, 3 MMAs per k-step) or 1 (fp16, 1 MMA)
@@ -334,7 +334,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                     if (p.mode == 1 && co + k < p.Cout) {
                         if (p.dcoef) a = fmaf(a, p.dcoef[(int64_t)img * p.Cout + co + k], nz); else a += nz;
                         if (bias_g) a += bias_g[co + k];
-                        a = act_gain_clamp(a, p.act, p.alpha, p.gain, p.clamp);
+                        a = act_gain_clamp(a, p.act, p.act == IA_ACT_PRELU ? p.slope[co + k] : p.alpha, p.gain, p.clamp);
                     }
                     v[k] = a;
                 }
@@ -472,7 +472,7 @@ struct Tc2Params {
     int OH, OW, sy, sx, py, px;
     int mode; const float* dcoef; const float* noise; const float* noise_strength; const float* bias;
     long long noise_bstride;
-    int act; float alpha, gain, clamp;
+    int act; float alpha, gain, clamp; const float* slope;   // slope: per-channel PReLU slopes (IA_ACT_PRELU)
     ia_emit emit;
     int groups, ipg, n_taps_total; long long noise_gstride;   // grouped launch (see ia_conv_params)
     // CTA-pair variant: the schedule of the plain variant with every (chunk, sub-problem, N tile) list of ic * T tiles padded to an
@@ -520,7 +520,7 @@ __device__ __forceinline__ void epilogue_chunk(const Tc2Params& p, const float* 
             a += bs;
             if (ACT == IA_ACT_LRELU) a = (a > 0.f ? a : a * alpha) * gain;
             else if (ACT == IA_ACT_LINEAR) a = a * gain;
-            else a = apply_act(a, p.act, alpha) * gain;
+            else a = apply_act(a, p.act, p.act == IA_ACT_PRELU ? s2v : alpha) * gain;      // PReLU: the slope travels in the s2 slot
             if (do_clamp) a = fminf(fmaxf(a, -clampv), clampv);
         }
         if (!cvalid) continue;
@@ -580,8 +580,13 @@ __device__ __forceinline__ void epilogue_chunk_v4(const Tc2Params& p, const floa
             } else if (ACT == IA_ACT_LINEAR) {
                 a.x *= gain; a.y *= gain; a.z *= gain; a.w *= gain;
             } else {
-                a.x = apply_act(a.x, p.act, alpha) * gain; a.y = apply_act(a.y, p.act, alpha) * gain;
-                a.z = apply_act(a.z, p.act, alpha) * gain; a.w = apply_act(a.w, p.act, alpha) * gain;
+                if (p.act == IA_ACT_PRELU) {      // per-channel slopes travel in the s2 slot (emit 2 is not available with PReLU)
+                    a.x = (a.x > 0.f ? a.x : a.x * s2.x) * gain; a.y = (a.y > 0.f ? a.y : a.y * s2.y) * gain;
+                    a.z = (a.z > 0.f ? a.z : a.z * s2.z) * gain; a.w = (a.w > 0.f ? a.w : a.w * s2.w) * gain;
+                } else {
+                    a.x = apply_act(a.x, p.act, alpha) * gain; a.y = apply_act(a.y, p.act, alpha) * gain;
+                    a.z = apply_act(a.z, p.act, alpha) * gain; a.w = apply_act(a.w, p.act, alpha) * gain;
+                }
             }
             if (do_clamp) {
                 a.x = fminf(fmaxf(a.x, -clampv), clampv); a.y = fminf(fmaxf(a.y, -clampv), clampv);
@@ -1073,6 +1078,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                                 }
                                 if (p.emit.hi1 && p.emit.s1) s14 = *reinterpret_cast<const float4*>(p.emit.s1 + (int64_t)img * p.Cout + co0);
                                 if (p.emit.hi2 && p.emit.s2) s24 = *reinterpret_cast<const float4*>(p.emit.s2 + (int64_t)img * p.Cout + co0);
+                                if (p.mode == 1 && p.act == IA_ACT_PRELU) s24 = *reinterpret_cast<const float4*>(p.slope + co0);
                             }
                             // rows of lanes whose channel group is past Cout are masked out, the shuffles inside stay warp-wide
                             const uint32_t vm = cval ? vmask : 0u;
@@ -1111,6 +1117,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                             if (p.mode == 1) { if (p.dcoef) dc = p.dcoef[(int64_t)img * p.Cout + co]; if (bias_g) bs = bias_g[co]; }
                             if (p.emit.hi1 && p.emit.s1) s1v = p.emit.s1[(int64_t)img * p.Cout + co];
                             if (p.emit.hi2 && p.emit.s2) s2v = p.emit.s2[(int64_t)img * p.Cout + co];
+                            if (p.mode == 1 && p.act == IA_ACT_PRELU) s2v = p.slope[co];
                         }
                         if (p.mode == 0) epilogue_chunk<0>(p, tsm, lane, vmask, my_pix, my_nz, img_pix0, img_pix1, co, cvalid, dc, bs, s1v, s2v);
                         else if (p.act == IA_ACT_LRELU) epilogue_chunk<IA_ACT_LRELU>(p, tsm, lane, vmask, my_pix, my_nz, img_pix0, img_pix1, co, cvalid, dc, bs, s1v, s2v);
@@ -1424,7 +1431,7 @@ int launch_v2(const ia_conv_params* const* ps, int nph, void* stream) {
     t.OH = p->OH; t.OW = p->OW; t.sy = p->sy; t.sx = p->sx; t.py = p->py; t.px = p->px;
     t.mode = p->mode; t.dcoef = p->dcoef; t.noise = p->noise; t.noise_strength = p->noise_strength; t.bias = p->bias;
     t.noise_bstride = p->noise_bstride;
-    t.act = p->act; t.alpha = p->alpha; t.gain = p->gain; t.clamp = p->clamp;
+    t.act = p->act; t.alpha = p->alpha; t.gain = p->gain; t.clamp = p->clamp; t.slope = p->slope;
     t.emit = p->emit;
     t.groups = p->groups > 1 ? p->groups : 1; t.ipg = p->groups > 1 ? p->imgs_per_group : (p->B > 0 ? p->B : 1);
     t.n_taps_total = p->n_taps_total; t.noise_gstride = p->groups > 1 ? p->noise_gstride : 0;
@@ -1560,7 +1567,7 @@ extern "C" int ia_conv_tc(const ia_conv_params* p, void* stream) {
     t.OH = p->OH; t.OW = p->OW; t.sy = p->sy; t.sx = p->sx; t.py = p->py; t.px = p->px;
     t.mode = p->mode; t.dcoef = p->dcoef; t.noise = p->noise; t.noise_strength = p->noise_strength; t.bias = p->bias;
     t.noise_bstride = p->noise_bstride;
-    t.act = p->act; t.alpha = p->alpha; t.gain = p->gain; t.clamp = p->clamp;
+    t.act = p->act; t.alpha = p->alpha; t.gain = p->gain; t.clamp = p->clamp; t.slope = p->slope;
     t.emit = p->emit;
 
     CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;

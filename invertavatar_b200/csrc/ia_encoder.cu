@@ -134,6 +134,43 @@ __global__ void __launch_bounds__(256) enc_affine_kernel(ia_enc_affine_params p)
     p.y[pix * p.y_ld + c] = a;
 }
 
+// Same arithmetic, 4 channels per thread, plus the operand of the NEXT convolution: split(y * e_scale[c] + e_shift[c]) as
+// [B][H][W][e_C_pad] bf16 hi/lo (zero padded) -- the BatchNorm affine that opens the next IR-SE unit, folded into the pass that
+// closes this one (no separate ia_enc_prep launch, no re-read of y).
+__global__ void __launch_bounds__(256) enc_affine_emit_kernel(ia_enc_affine_params p) {
+    const int groups = p.e_C_pad >> 2;
+    const int64_t total = (int64_t)p.B * p.H * p.W * groups;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int g = (int)(i % groups);
+    const int64_t pix = i / groups;
+    const int x = (int)(pix % p.W); const int64_t t = pix / p.W;
+    const int y = (int)(t % p.H); const int b = (int)(t / p.H);
+    float e[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int c = g * 4 + k;
+        e[k] = 0.f;
+        if (c >= p.C) continue;
+        float a = view_at(p.x, b, y, x, c);
+        if (p.scale) a = fmaf(a, p.scale[c], p.shift ? p.shift[c] : 0.f);
+        else if (p.shift) a += p.shift[c];
+        if (p.slope1) a = a >= 0.f ? a : a * p.slope1[c];
+        else a = apply_act(a, p.act, p.alpha);
+        if (p.slope2) a = a >= 0.f ? a : a * p.slope2[c];
+        if (p.gate) a *= p.gate[(int64_t)b * p.C + c];
+        if (p.res.p) {
+            float r = view_at(p.res, b, y, x, c);
+            if (p.res_scale) r = fmaf(r, p.res_scale[c], p.res_shift ? p.res_shift[c] : 0.f);
+            else if (p.res_shift) r += p.res_shift[c];
+            a += r;
+        }
+        p.y[pix * p.y_ld + c] = a;
+        e[k] = p.e_scale ? fmaf(a, p.e_scale[c], p.e_shift ? p.e_shift[c] : 0.f) : (p.e_shift ? a + p.e_shift[c] : a);
+    }
+    store_operand4(IA_OPFMT_BF16X3, p.e_hi + pix * p.e_C_pad + g * 4, p.e_lo + pix * p.e_C_pad + g * 4, e[0], e[1], e[2], e[3]);
+}
+
 // ---- global average pool of an affine'd view: grid (B, ceil(C/32), pixel chunks), block 32 x 8; partial sums are added
 // atomically into `pooled` (zeroed by the host wrapper), a second tiny kernel turns the sums into scale*mean + shift ------
 __global__ void __launch_bounds__(256) global_pool_kernel(ia_view v, int H, int W, int pix_per_block, float* __restrict__ pooled) {
@@ -305,6 +342,14 @@ extern "C" int ia_enc_affine_act(const ia_enc_affine_params* p, void* stream) {
     IA_CHECK(p->res.p == nullptr || (p->res.C >= p->C && p->res.ps >= 1), "ia_enc_affine_act: bad residual view");
     const int64_t total = (int64_t)p->B * p->H * p->W * p->C;
     if (total == 0) return 0;
+    if (p->e_hi) {
+        IA_CHECK(p->e_lo && p->e_C_pad >= p->C && (p->e_C_pad & 3) == 0, "ia_enc_affine_act: emitted operand needs e_lo and e_C_pad >= C, multiple of 4");
+        const int64_t tot4 = (int64_t)p->B * p->H * p->W * (p->e_C_pad >> 2);
+        ia::prof_begin("ia_enc_affine_act", as_stream(stream));
+        enc_affine_emit_kernel<<<(unsigned)cdiv(tot4, 256), 256, 0, as_stream(stream)>>>(*p);
+        IA_LAUNCH_CHECK("ia_enc_affine_act");
+        return 0;
+    }
     ia::prof_begin("ia_enc_affine_act", as_stream(stream));
     enc_affine_kernel<<<(unsigned)cdiv(total, 256), 256, 0, as_stream(stream)>>>(*p);
     IA_LAUNCH_CHECK("ia_enc_affine_act");

@@ -697,6 +697,9 @@ int ia_conv_validate(const ia_conv_params* p, const char* who) {
                               (!p->img_prev || ((p->OH & 1) == 0 && (p->OW & 1) == 0))),
              "%s: mode 2 (ToRGB tail) writes out32 only, stride 1, Cout %% 4 == 0, even output size with img_prev", who);
     IA_CHECK(p->noise == nullptr || p->noise_strength != nullptr, "%s: noise needs noise_strength", who);
+    IA_CHECK(p->act != IA_ACT_PRELU || (p->mode == 1 && p->slope && !p->emit.hi2 && !p->emit.rgb_out && (p->Cout & 3) == 0 && p->groups <= 1 &&
+                                        (reinterpret_cast<uintptr_t>(p->slope) & 15) == 0),
+             "%s: PReLU epilogue needs mode 1, 16-byte aligned slope[Cout], Cout %% 4 == 0, no emit 2 / fused ToRGB / groups", who);
     IA_CHECK(p->emit.out32 || p->emit.hi1 || p->emit.hi2 || p->emit.rgb_out, "%s: nothing to emit", who);
     IA_CHECK(!p->emit.rgb_out || (p->emit.rgb_w && p->emit.rgb_n >= 1 && p->emit.rgb_n <= 4 && p->mode == 1 && (p->Cout & 3) == 0 &&
                                   !p->emit.out32 && !p->emit.hi2),
@@ -712,6 +715,7 @@ extern "C" int ia_conv_simt(const ia_conv_params* p, void* stream) {
     IA_CHECK(p->groups <= 1, "ia_conv_simt: grouped launches are implemented by ia_conv_tc only");
     IA_CHECK(!p->emit.rgb_out, "ia_conv_simt: the fused ToRGB contraction is implemented by ia_conv_tc only");
     IA_CHECK(p->mode != 2, "ia_conv_simt: the fused ToRGB tail (mode 2) is implemented by ia_conv_tc only");
+    IA_CHECK(p->act != IA_ACT_PRELU, "ia_conv_simt: the PReLU epilogue is implemented by ia_conv_tc only");
     IA_CHECK(p->a_img_rows <= p->H && p->emit.e1_img_pix == 0, "ia_conv_simt: padded operand layouts are implemented by ia_conv_tc only");
     int64_t rows = (int64_t)p->B * p->GH * p->GW;
     dim3 grid((unsigned)cdiv(rows, SIMT_TM), (unsigned)cdiv(p->Cout_pad, SIMT_TN));

@@ -109,14 +109,29 @@ class bottleneck_IR_SE(Module):
             BatchNorm2d(depth),
             SEModule(depth, 16))
 
-    def run_nhwc(self, x):
-        """x [B,H,W,Cin] fp32 -> [B,H/s,W/s,depth]."""
+    def opening_affine(self):
+        """(scale, shift, C_pad) of the BatchNorm that opens this unit when it is a fixed affine (eval mode), else None: the unit in
+        front can then emit this unit's first operand from its closing pass (ia_enc_affine_params.e_*)."""
+        bn0, conv1 = self.res_layer[0], self.res_layer[1]
+        if bn0.training or not bn0.track_running_stats:
+            return None
+        sc0, sh0 = rt.enc_bn_fold(bn0, [])
+        return sc0, sh0, rt.ConvPack.current(conv1, '_ia_pack', conv1.weight, need_wsq=False).Cin_pad
+
+    def run_nhwc(self, x, a=None, emit=None):
+        """x [B,H,W,Cin] fp32 -> [B,H/s,W/s,depth].  a: this unit's first operand split(bn0(x)) when the caller already has it;
+        emit: the next unit's opening_affine() -> returns (y, split(bn0_next(y)))."""
         s = self.stride
         bn0, conv1, prelu, conv2, bn4, se = self.res_layer
-        sc0, sh0 = rt.enc_bn_fold(bn0, [x])
-        a, _ = rt.enc_prep([x], scale=sc0, shift=sh0, C_pad=rt.ConvPack.current(conv1, '_ia_pack', conv1.weight, need_wsq=False).Cin_pad)
-        raw1 = rt.enc_conv(a, conv1)
-        a, _ = rt.enc_prep([raw1], slope=prelu.weight, C_pad=rt.ConvPack.current(conv2, '_ia_pack', conv2.weight, need_wsq=False).Cin_pad)
+        if a is None:
+            sc0, sh0 = rt.enc_bn_fold(bn0, [x])
+            a, _ = rt.enc_prep([x], scale=sc0, shift=sh0, C_pad=rt.ConvPack.current(conv1, '_ia_pack', conv1.weight, need_wsq=False).Cin_pad)
+        pad2 = rt.ConvPack.current(conv2, '_ia_pack', conv2.weight, need_wsq=False).Cin_pad
+        if rt.enc_epilogue_fusion():
+            a = rt.enc_conv_act(a, conv1, pad2, slope=prelu.weight)      # PReLU + operand emission inside conv1's epilogue
+        else:
+            raw1 = rt.enc_conv(a, conv1)
+            a, _ = rt.enc_prep([raw1], slope=prelu.weight, C_pad=pad2)
         raw2 = _sub(rt.enc_conv(a, conv2), s)      # stride-s convolution = the stride-1 result sampled every s pixels
         sc4, sh4 = rt.enc_bn_fold(bn4, [raw2])
         gate = se.gate(raw2, sc4, sh4)
@@ -126,8 +141,8 @@ class bottleneck_IR_SE(Module):
             a, _ = rt.enc_prep([xs], C_pad=rt.ConvPack.current(conv_s, '_ia_pack', conv_s.weight, need_wsq=False).Cin_pad)
             raw_s = rt.enc_conv(a, conv_s, alg_stride=1)      # operand already sub-sampled
             rs, rsh = rt.enc_bn_fold(bn_s, [raw_s])
-            return rt.enc_affine_act(raw2, scale=sc4, shift=sh4, gate=gate, res=raw_s, res_scale=rs, res_shift=rsh)
-        return rt.enc_affine_act(raw2, scale=sc4, shift=sh4, gate=gate, res=xs)
+            return rt.enc_affine_act(raw2, scale=sc4, shift=sh4, gate=gate, res=raw_s, res_scale=rs, res_shift=rsh, emit=emit)
+        return rt.enc_affine_act(raw2, scale=sc4, shift=sh4, gate=gate, res=xs, emit=emit)
 
     def forward(self, x):
         return _nchw(self.run_nhwc(_nhwc(x)))
@@ -151,8 +166,13 @@ def _run_trunk(module, x, taps):
     sc, sh = rt.enc_bn_fold(bn, [raw])
     x = rt.enc_affine_act(raw, scale=sc, shift=sh, slope1=prelu.weight)
     feats = {}
-    for i, blk in enumerate(module.body):
-        x = blk.run_nhwc(x)
+    blocks = list(module.body)
+    a = None
+    for i, blk in enumerate(blocks):
+        # a unit whose successor opens with an eval-mode BatchNorm also writes the successor's first operand
+        nxt = blocks[i + 1].opening_affine() if i + 1 < len(blocks) else None
+        out = blk.run_nhwc(x, a=a, emit=nxt)
+        x, a = out if nxt is not None else (out, None)
         if i in taps:
             feats[i] = x
     return x, feats
@@ -305,8 +325,12 @@ class DoubleConv(Module):
         bn, c1, p1, c2, p2, p3 = self.double_conv
         sc, sh = rt.enc_bn_fold(bn, srcs)
         a, _ = rt.enc_prep(srcs, scale=sc, shift=sh, C_pad=rt.ConvPack.current(c1, '_ia_pack', c1.weight, need_wsq=False).Cin_pad)
-        raw = rt.enc_conv(a, c1)
-        a, _ = rt.enc_prep([raw], shift=c1.bias, slope=p1.weight, C_pad=rt.ConvPack.current(c2, '_ia_pack', c2.weight, need_wsq=False).Cin_pad)
+        pad2 = rt.ConvPack.current(c2, '_ia_pack', c2.weight, need_wsq=False).Cin_pad
+        if rt.enc_epilogue_fusion():
+            a = rt.enc_conv_act(a, c1, pad2, slope=p1.weight)            # bias + PReLU + operand emission inside c1's epilogue
+        else:
+            raw = rt.enc_conv(a, c1)
+            a, _ = rt.enc_prep([raw], shift=c1.bias, slope=p1.weight, C_pad=pad2)
         return rt.enc_affine_act(rt.enc_conv(a, c2), shift=c2.bias, slope1=p2.weight, slope2=p3.weight)
 
     def forward(self, x):

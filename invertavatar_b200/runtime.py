@@ -14,10 +14,12 @@ import torch
 
 from . import _C
 
-ACT_IDS = {'linear': 1, 'relu': 2, 'lrelu': 3, 'tanh': 4, 'sigmoid': 5, 'elu': 6, 'selu': 7, 'softplus': 8, 'swish': 9}
+ACT_IDS = {'linear': 1, 'relu': 2, 'lrelu': 3, 'tanh': 4, 'sigmoid': 5, 'elu': 6, 'selu': 7, 'softplus': 8, 'swish': 9,
+           'prelu': 10}      # prelu: convolution epilogues only (per-channel slopes, IA_ACT_PRELU)
 ACT_DEFAULTS = {  # name -> (def_alpha, def_gain), reference torch_utils/ops/bias_act.py:23-33
     'linear': (0.0, 1.0), 'relu': (0.0, math.sqrt(2)), 'lrelu': (0.2, math.sqrt(2)), 'tanh': (0.0, 1.0),
     'sigmoid': (0.0, 1.0), 'elu': (0.0, 1.0), 'selu': (0.0, 1.0), 'softplus': (0.0, 1.0), 'swish': (0.0, math.sqrt(2)),
+    'prelu': (0.0, 1.0),
 }
 
 _tls = threading.local()
@@ -713,7 +715,8 @@ def _set_group(p, group):
 
 
 def conv_same(hi, lo, pack, Cin_pad, out32, dcoef=None, noise=None, noise_strength=None, bias=None, act='linear',
-              gain=1.0, clamp=None, mode=1, impl=None, e1=None, e2=None, group=None, rgb=None, img_prev=None, alg_stride=1):
+              gain=1.0, clamp=None, mode=1, impl=None, e1=None, e2=None, group=None, rgb=None, img_prev=None, alg_stride=1, slope=None,
+              alpha=None):
     """k x k correlation, stride 1, 'same' padding (flip_weight=True branch of conv2d_resample, :134-136)."""
     st = _enter(hi)
     B, H, W, _ = hi.shape
@@ -733,7 +736,10 @@ def conv_same(hi, lo, pack, Cin_pad, out32, dcoef=None, noise=None, noise_streng
     p.mode = mode
     p.dcoef, p.noise, p.noise_strength, p.bias = _p(dcoef), _p(noise), _p(noise_strength), _p(bias)
     p.noise_bstride = _noise_bstride(noise)
-    p.act, p.alpha, p.gain, p.clamp = ACT_IDS[act], ACT_DEFAULTS[act][0], float(gain), float(-1 if clamp is None else clamp)
+    p.act, p.alpha, p.gain, p.clamp = ACT_IDS[act], ACT_DEFAULTS[act][0] if alpha is None else float(alpha), float(gain), float(-1 if clamp is None else clamp)
+    if act == 'prelu':
+        assert slope is not None and slope.numel() == pack.Cout and slope.is_contiguous()
+        p.slope = _p(slope)
     p.emit = _emit(out32, e1, e2, rgb)
     if img_prev is not None:
         assert mode == 2 and img_prev.is_contiguous() and tuple(img_prev.shape) == (B, H // 2, W // 2, pack.Cout), (img_prev.shape, hi.shape)
@@ -1141,12 +1147,26 @@ def enc_chan_stats(src):
     return sums, B * H * W
 
 
+class _FoldCache(_EngineCache):
+    """Folded eval-mode BatchNorm (scale, shift) hung on the module; dropped on deepcopy / pickle like every engine cache."""
+
+    def __init__(self, key, scale, shift):
+        self.key, self.scale, self.shift = key, scale, shift
+
+
 def enc_bn_fold(bn, srcs):
     """torch.nn.BatchNorm2d ``bn`` applied to cat(srcs, channel) -> per-channel (scale, shift) fp32 [C].
     Train mode (or no running statistics): batch statistics of the sources, running statistics updated as torch does."""
     dev = bn.weight.device if bn.weight is not None else srcs[0].device
     Cn = bn.num_features
     training = bn.training or not bn.track_running_stats
+    if not training:
+        # eval mode: (scale, shift) depend on the parameters and running statistics only -- folded once, reused until one of them
+        # changes (storage or version)
+        key = tuple((t.data_ptr(), t._version) for t in (bn.weight, bn.bias, bn.running_mean, bn.running_var) if t is not None) + (float(bn.eps), str(dev))
+        c = bn.__dict__.get('_ia_fold')
+        if c is not None and c.key == key:
+            return c.scale, c.shift
     scale = torch.empty(Cn, dtype=torch.float32, device=dev)
     shift = torch.empty_like(scale)
     sums, count = None, 0
@@ -1173,6 +1193,8 @@ def enc_bn_fold(bn, srcs):
                                      _p(scale), _p(shift), st), 'ia_enc_bn_fold')
     if training and track and bn.num_batches_tracked is not None:
         bn.num_batches_tracked += 1
+    if not training:
+        bn.__dict__['_ia_fold'] = _FoldCache(key, scale, shift)
     return scale, shift
 
 
@@ -1216,8 +1238,29 @@ def enc_conv(a, conv, alg_stride=None):
     return raw
 
 
+def enc_conv_act(a, conv, C_pad, slope=None, lrelu=None, want32=False):
+    """conv (3x3 pad 1 or 1x1, stride 1) + bias + PReLU(slope) / LeakyReLU(lrelu) with the activation applied in the convolution's
+    epilogue, which emits the next convolution's operand directly: -> Split [B,H,W,C_pad] (+ fp32 [B,H,W,Cout] when want32)."""
+    pack = ConvPack.current(conv, '_ia_pack', conv.weight, need_wsq=False)
+    assert (pack.kh, pack.kw) in ((1, 1), (3, 3)) and a.C_pad == pack.Cin_pad and pack.Cout % 4 == 0
+    B, H, W, _ = a.hi.shape
+    sp = new_split(B, H, W, C_pad, a.hi.device, C=pack.Cout)
+    out32 = torch.empty((B, H, W, pack.Cout), dtype=torch.float32, device=a.hi.device) if want32 else None
+    if slope is not None:
+        conv_same(a.hi, a.lo, pack, pack.Cin_pad, out32, bias=conv.bias, act='prelu', slope=slope, gain=1.0, mode=1, e1=(sp, None))
+    else:
+        conv_same(a.hi, a.lo, pack, pack.Cin_pad, out32, bias=conv.bias, act='lrelu', alpha=float(lrelu), gain=1.0, mode=1, e1=(sp, None))
+    return (sp, out32) if want32 else sp
+
+
+def enc_epilogue_fusion():
+    """Encoder convolutions apply the PReLU / LeakyReLU that follows them in their own epilogue and emit the next operand
+    (IA_ENC_FUSE=0: separate ia_enc_prep passes, the round-1 formulation)."""
+    return os.environ.get('IA_ENC_FUSE', '1') != '0' and _conv_impl == 'tc'
+
+
 def enc_affine_act(x, scale=None, shift=None, slope1=None, slope2=None, act='linear', alpha=0.0, gate=None, res=None,
-                   res_scale=None, res_shift=None, out=None):
+                   res_scale=None, res_shift=None, out=None, emit=None):
     """y = gate * act2(act1(x*scale + shift)) + (res*res_scale + res_shift); x/res: tensors [B,H,W,C] (any strides) or
     (tensor, ps).  out: optional [B,H,W,C] destination with unit channel stride and dense rows (a column slice of a
     wider NHWC buffer is fine)."""
@@ -1242,8 +1285,13 @@ def enc_affine_act(x, scale=None, shift=None, slope1=None, slope2=None, act='lin
     assert (W == 1 or H == 1 or out.stride(1) == W * y_ld) and (B == 1 or H * W == 1 or out.stride(0) == H * W * y_ld), (out.shape, out.stride())
     p.y, p.y_ld = _p(out), y_ld
     p.B, p.H, p.W, p.C = B, H, W, Cc
+    sp = None
+    if emit is not None:      # (e_scale, e_shift, C_pad): also write split(y * e_scale + e_shift), the next convolution's operand
+        e_scale, e_shift, C_pad = emit
+        sp = new_split(B, H, W, C_pad, out.device)
+        p.e_scale, p.e_shift, p.e_hi, p.e_lo, p.e_C_pad = _p(e_scale), _p(e_shift), _p(sp.hi), _p(sp.lo), C_pad
     _C.check(_C.lib().ia_enc_affine_act(C.byref(p), st), 'ia_enc_affine_act')
-    return out
+    return out if emit is None else (out, sp)
 
 
 def enc_global_pool(x, scale=None, shift=None):
