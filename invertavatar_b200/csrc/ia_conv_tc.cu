@@ -579,14 +579,12 @@ __device__ __forceinline__ void epilogue_chunk_v4(const Tc2Params& p, const floa
                 a.z = (a.z > 0.f ? a.z : a.z * alpha) * gain; a.w = (a.w > 0.f ? a.w : a.w * alpha) * gain;
             } else if (ACT == IA_ACT_LINEAR) {
                 a.x *= gain; a.y *= gain; a.z *= gain; a.w *= gain;
+            } else if (p.act == IA_ACT_PRELU) {    // per-channel slopes travel in the s2 slot (emit 2 is not available with PReLU)
+                a.x = (a.x > 0.f ? a.x : a.x * s2.x) * gain; a.y = (a.y > 0.f ? a.y : a.y * s2.y) * gain;
+                a.z = (a.z > 0.f ? a.z : a.z * s2.z) * gain; a.w = (a.w > 0.f ? a.w : a.w * s2.w) * gain;
             } else {
-                if (p.act == IA_ACT_PRELU) {      // per-channel slopes travel in the s2 slot (emit 2 is not available with PReLU)
-                    a.x = (a.x > 0.f ? a.x : a.x * s2.x) * gain; a.y = (a.y > 0.f ? a.y : a.y * s2.y) * gain;
-                    a.z = (a.z > 0.f ? a.z : a.z * s2.z) * gain; a.w = (a.w > 0.f ? a.w : a.w * s2.w) * gain;
-                } else {
-                    a.x = apply_act(a.x, p.act, alpha) * gain; a.y = apply_act(a.y, p.act, alpha) * gain;
-                    a.z = apply_act(a.z, p.act, alpha) * gain; a.w = apply_act(a.w, p.act, alpha) * gain;
-                }
+                a.x = apply_act(a.x, p.act, alpha) * gain; a.y = apply_act(a.y, p.act, alpha) * gain;
+                a.z = apply_act(a.z, p.act, alpha) * gain; a.w = apply_act(a.w, p.act, alpha) * gain;
             }
             if (do_clamp) {
                 a.x = fminf(fmaxf(a.x, -clampv), clampv); a.y = fminf(fmaxf(a.y, -clampv), clampv);
