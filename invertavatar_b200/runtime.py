@@ -14,12 +14,11 @@ import torch
 
 from . import _C
 
-ACT_IDS = {'linear': 1, 'relu': 2, 'lrelu': 3, 'tanh': 4, 'sigmoid': 5, 'elu': 6, 'selu': 7, 'softplus': 8, 'swish': 9,
-           'prelu': 10}      # prelu: convolution epilogues only (per-channel slopes, IA_ACT_PRELU)
+ACT_IDS = {'linear': 1, 'relu': 2, 'lrelu': 3, 'tanh': 4, 'sigmoid': 5, 'elu': 6, 'selu': 7, 'softplus': 8, 'swish': 9}
+ACT_PRELU = 10      # IA_ACT_PRELU: convolution epilogues only (per-channel slopes); not one of the reference's bias_act activations
 ACT_DEFAULTS = {  # name -> (def_alpha, def_gain), reference torch_utils/ops/bias_act.py:23-33
     'linear': (0.0, 1.0), 'relu': (0.0, math.sqrt(2)), 'lrelu': (0.2, math.sqrt(2)), 'tanh': (0.0, 1.0),
     'sigmoid': (0.0, 1.0), 'elu': (0.0, 1.0), 'selu': (0.0, 1.0), 'softplus': (0.0, 1.0), 'swish': (0.0, math.sqrt(2)),
-    'prelu': (0.0, 1.0),
 }
 
 _tls = threading.local()
@@ -736,10 +735,12 @@ def conv_same(hi, lo, pack, Cin_pad, out32, dcoef=None, noise=None, noise_streng
     p.mode = mode
     p.dcoef, p.noise, p.noise_strength, p.bias = _p(dcoef), _p(noise), _p(noise_strength), _p(bias)
     p.noise_bstride = _noise_bstride(noise)
-    p.act, p.alpha, p.gain, p.clamp = ACT_IDS[act], ACT_DEFAULTS[act][0] if alpha is None else float(alpha), float(gain), float(-1 if clamp is None else clamp)
     if act == 'prelu':
         assert slope is not None and slope.numel() == pack.Cout and slope.is_contiguous()
-        p.slope = _p(slope)
+        p.act, p.alpha, p.slope = ACT_PRELU, 0.0, _p(slope)
+    else:
+        p.act, p.alpha = ACT_IDS[act], ACT_DEFAULTS[act][0] if alpha is None else float(alpha)
+    p.gain, p.clamp = float(gain), float(-1 if clamp is None else clamp)
     p.emit = _emit(out32, e1, e2, rgb)
     if img_prev is not None:
         assert mode == 2 and img_prev.is_contiguous() and tuple(img_prev.shape) == (B, H // 2, W // 2, pack.Cout), (img_prev.shape, hi.shape)

@@ -15,6 +15,7 @@ if [ "$2" = "ab" ]; then
   timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err
 fi
 tail -3 $OUT/pytest.log
+grep -E "[0-9]+ (passed|failed)" $OUT/pytest.log | tail -1
 for f in $OUT/bench_*.json; do echo $f; python - "$f" <<'PY'
 import json, sys
 try:
