@@ -480,6 +480,7 @@ struct Tc2Params {
     int pp_cum[5];                 // pp_cum[q] = sum_{k<q} ceil(ic * T_k / 2)
     int chunk_pairs, total_pairs;  // n_tiles * pp_cum[nph]; (B / ic) * chunk_pairs
     uint32_t b_half_tx;            // bytes of the half weight tile one CTA of a pair stages
+    int dbg_skip_epi;              // IA_DBG_SKIP_EPI=1 (experiments only): drain TMEM but skip the epilogue arithmetic and stores
     // balanced schedule (plain variant): tiles ordered (image chunk, sub-problem, N tile, image, tile) with the sub-problems by
     // descending tap count, only real tiles enumerated -- see decode()
     int ic, chunk_tiles;           // images per chunk; schedule entries of one chunk = ic * n_tiles * ph_cum[nph]
@@ -1056,7 +1057,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                                 r[4 * q + 2] = __float_as_uint(a[q].z); r[4 * q + 3] = __float_as_uint(a[q].w);
                             }
                         }
-                        if (vmask == 0u) continue;
+                        if (vmask == 0u || p.dbg_skip_epi) continue;
                         __syncwarp();
                         if (p.epi_vec4) {
 #pragma unroll
@@ -1430,6 +1431,7 @@ int launch_v2(const ia_conv_params* const* ps, int nph, void* stream) {
     t.mode = p->mode; t.dcoef = p->dcoef; t.noise = p->noise; t.noise_strength = p->noise_strength; t.bias = p->bias;
     t.noise_bstride = p->noise_bstride;
     t.act = p->act; t.alpha = p->alpha; t.gain = p->gain; t.clamp = p->clamp; t.slope = p->slope;
+    { static int dbg = -1; if (dbg < 0) { const char* ev = getenv("IA_DBG_SKIP_EPI"); dbg = ev ? atoi(ev) : 0; } t.dbg_skip_epi = dbg; }
     t.emit = p->emit;
     t.groups = p->groups > 1 ? p->groups : 1; t.ipg = p->groups > 1 ? p->imgs_per_group : (p->B > 0 ? p->B : 1);
     t.n_taps_total = p->n_taps_total; t.noise_gstride = p->groups > 1 ? p->noise_gstride : 0;
