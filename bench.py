@@ -461,13 +461,14 @@ def run_c2(args, rank, world, local, dev):
             dist.all_gather_into_tensor(gathered, img.contiguous())
         return img
 
-    # The step is issued as ONE CUDA graph replay (invertavatar_b200.graphs.GraphedCall over mapping + synthesis: the same ~260
+    # The step is issued as ONE CUDA graph replay (invertavatar_b200.graphs.GraphedCall over mapping + synthesis: the same 105
     # kernels, captured once): issuing them one by one through Python + ctypes costs about as much host time as the step takes on
     # the device, which is what made the end-to-end number fall behind the device number when 8 ranks share one host.  The
     # cross-rank part of the step (peer barrier / NCCL gather) stays outside the graph; with the fused peer gather there is one
     # graph per slot of the double-buffered gathered tensor.  --no-graph issues the launches eagerly.
     graphs = None
     launches_per_step = None
+    graph_error = None
     if not args.no_graph:
         from invertavatar_b200.graphs import GraphedCall
 
@@ -484,13 +485,22 @@ def run_c2(args, rank, world, local, dev):
             rt.reset_launch_count()
             compute(z, cond, c, uv)
             launches_per_step = rt.launch_count()
-            graphs = []
-            for k in range(2 if peer is not None else 1):
-                if peer is not None:
-                    peer.cur = k
-                graphs.append(GraphedCall(compute, dict(z=z, cond=cond, c=c, uv=uv)))
+            try:
+                graphs = []
+                for k in range(2 if peer is not None else 1):
+                    if peer is not None:
+                        peer.cur = k
+                    graphs.append(GraphedCall(compute, dict(z=z, cond=cond, c=c, uv=uv)))
+            except Exception as ex:      # capture refused on this box / driver: issue eagerly and say so in the line
+                graphs, graph_error = None, f'{type(ex).__name__}: {ex}'[:200]
+                torch.cuda.synchronize()
             if peer is not None:
                 peer.cur, peer.last = 0, 0
+        if world > 1:      # every rank must take the same path (the peer barrier / NCCL gather are matched calls)
+            flag = torch.tensor([0 if graphs is None else 1], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                graphs = None
 
     def frame_batch_graph(new_inputs=None):
         g = graphs[peer.cur if peer is not None else 0]
@@ -635,7 +645,8 @@ def run_c2(args, rank, world, local, dev):
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'ms_per_step': ms_e2e / args.steps,
                     'readback': 'fp32 NCHW images' if args.e2e_f32 else 'uint8 HWC frames (layout_grid, reenact_avatar_next3d.py:117-131)'},
             'gpu_launches': launches,
-            'issue': ('eager (Python + ctypes launches)' if graphs is None else
+            'issue': ('eager (Python + ctypes launches)' + (f'; graph capture failed: {graph_error}' if not args.no_graph and graph_error else '')
+                      if graphs is None else
                       f'one CUDA graph replay per step (invertavatar_b200.graphs.GraphedCall over G.mapping + G.synthesis: {launches_per_step} kernels of '
                       'libinvertavatar_b200.so per step, counted on an eager step and captured once); gpu_launches = kernels per step x steps'),
             'step_ms': {'median': step_ms[len(step_ms) // 2], 'min': step_ms[0], 'max': step_ms[-1],
