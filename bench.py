@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument('--depth', type=int, default=48, help='coarse = importance depth samples per ray')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-roofline', action='store_true')
+    ap.add_argument('--c3-per-frame', action='store_true', help='workload c3: render the T driven frames with T batch-1 synthesis_withTexture calls (the loop of eval_seq.py:212) instead of one batch-T call')
     ap.add_argument('--no-graph', action='store_true', help='issue the step eagerly (Python + ctypes launches) instead of replaying its CUDA graph')
     ap.add_argument('--e2e-f32', action='store_true', help='end-to-end leg reads back the fp32 images instead of uint8 HWC frames')
     return ap.parse_args()
@@ -69,7 +70,8 @@ def workload_config(args, n_gpus, frames_per_step=None):
     fps = args.batch if frames_per_step is None else frames_per_step
     if args.workload == 'c3':
         return {'workload': f'eval_seq.py few-shot path (BASELINE configs[2]): encode B=1 + AR_eval_forward T={T_C3} ({args.res}^2 x {args.depth}+{args.depth} render inside) '
-                            f'+ {T_C3} x synthesis_withTexture, random-init inversionNet + generator, synthetic images/UV/cameras',
+                            + (f'+ {T_C3} x synthesis_withTexture (batch 1 each)' if getattr(args, 'c3_per_frame', False) else f'+ one batch-{T_C3} synthesis_withTexture call for the {T_C3} driven frames')
+                            + ', random-init inversionNet + generator, synthetic images/UV/cameras',
                 'frames_per_gpu_per_step': T_C3, 'global_frames_per_step': T_C3 * n_gpus, 'identities_per_gpu_per_step': 1,
                 'neural_res': args.res, 'depth_samples': [args.depth, args.depth],
                 'parallelism': f'{n_gpus} replica(s): identities are independent, the ConvGRU state is sequential inside one',
@@ -680,6 +682,13 @@ def run_c3(args, rank, world, local, dev):
         if draws is not None:
             G.renderer.depth_jitter, G.renderer.importance_u = draws[0], draws[1]
         upd, _ = net.AR_eval_forward(x, c, v, ws, [None, None], e4e_results={'w': ws, 'texture': tex, 'static': sta}, return_fake=False)
+        if not args.c3_per_frame:
+            # the T driven frames are independent given the updated features: one batch-T synthesis_withTexture call (the engine's API
+            # takes a batch, as AR_eval_forward's own T-frame render does) instead of the script's per-frame loop (eval_seq.py:212)
+            if draws is not None:
+                G.renderer.depth_jitter = torch.cat(list(draws[2]), dim=0)
+            return G.synthesis_withTexture(ws.expand(T_C3, -1, -1), [f.expand(T_C3, -1, -1, -1) for f in upd['texture']], c, v, noise_mode='const',
+                                           static_feats=[f.expand(T_C3, -1, -1, -1) for f in upd['static']], evaluation=True)['image']
         frames = []
         for i in range(T_C3):
             if draws is not None:
@@ -804,7 +813,11 @@ def run_c3(args, rank, world, local, dev):
             ar_ms, (upd, _) = t_ms(lambda: net.AR_eval_forward(x, res_in['c'], v, ws, [None, None], e4e_results=e4e, return_fake=False))
             fr_ms, _ = t_ms(lambda: G.synthesis_withTexture(ws, upd['texture'], res_in['c'][:1], {'uvcoords_image': res_in['uvimg'][:1]}, noise_mode='const',
                                                             static_feats=upd['static'], evaluation=True)['image'], n=8)
-            stages = {'encode_ms': enc_ms, 'ar_eval_forward_ms': ar_ms, 'synthesis_withTexture_ms_per_frame': fr_ms}
+            frT_ms, _ = t_ms(lambda: G.synthesis_withTexture(ws.expand(T_C3, -1, -1), [f.expand(T_C3, -1, -1, -1) for f in upd['texture']], res_in['c'], v,
+                                                             noise_mode='const', static_feats=[f.expand(T_C3, -1, -1, -1) for f in upd['static']],
+                                                             evaluation=True)['image'], n=8)
+            stages = {'encode_ms': enc_ms, 'ar_eval_forward_ms': ar_ms, 'synthesis_withTexture_ms_per_frame': fr_ms,
+                      f'synthesis_withTexture_batch{T_C3}_ms': frT_ms, 'note': 'eager (un-graphed) stage times'}
 
         cpu = parity = None
         if world == 1 and rank == 0 and not args.no_cpu_baseline:
