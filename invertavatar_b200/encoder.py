@@ -15,6 +15,7 @@ plus the small normalisation, pooling and ConvGRU gating kernels of csrc/ia_enco
 channels-last between layers; tensors handed to the caller are logical NCHW views of those buffers.  BatchNorm follows
 each module's ``training`` flag exactly like torch (eval_seq.py:92-97 leaves e4e and the UNet decoders in train mode:
 batch statistics).  Forward only."""
+import os
 from collections import namedtuple
 
 import numpy as np
@@ -247,16 +248,29 @@ class Encoder4Editing(Module):
             return w[:, i].view(B, 1, 1, 512)          # [B,1,1,512] destination with pixel stride n_styles*512
         w0 = self.styles[0].run_nhwc(c3)
         rt.enc_affine_act(w0.view(B, 1, 1, 512), shift=w_offset, out=row(0))
-        features = c3
-        p2 = None
-        for i in range(1, self.style_count):
-            if i == self.coarse_ind:
-                p2 = rt.enc_upsample_add(c3, _conv_bias_act([c2], self.latlayer1))
-                features = p2
-            elif i == self.middle_ind:
-                features = rt.enc_upsample_add(p2, _conv_bias_act([c1], self.latlayer2))
+        p2 = rt.enc_upsample_add(c3, _conv_bias_act([c2], self.latlayer1)) if self.style_count > self.coarse_ind else None
+        p1 = rt.enc_upsample_add(p2, _conv_bias_act([c1], self.latlayer2)) if self.style_count > self.middle_ind else None
+
+        def style(i):
+            features = c3 if i < self.coarse_ind else (p2 if i < self.middle_ind else p1)
             delta = self.styles[i].run_nhwc(features)
             rt.enc_affine_act(delta.view(B, 1, 1, 512), res=w0.view(B, 1, 1, 512), res_shift=w_offset, out=row(i))
+        # The map2style heads are independent chains of small, latency-bound launches (a few CTAs each): issue them round-robin
+        # on side streams and join before w is consumed (IA_E4E_STREAMS=0: one after the other on the caller's stream).
+        n_side = int(os.environ.get('IA_E4E_STREAMS', '4'))
+        if n_side <= 1 or self.style_count <= 2:
+            for i in range(1, self.style_count):
+                style(i)
+            return w
+        cur = torch.cuda.current_stream(c3.device)
+        side = rt.side_streams(c3.device, 2 + n_side)[2:]      # (the first two belong to AR_eval_forward's UNet pair)
+        for s_ in side:
+            s_.wait_stream(cur)
+        for i in range(1, self.style_count):
+            with torch.cuda.stream(side[(i - 1) % n_side]):
+                style(i)
+        for s_ in side:
+            cur.wait_stream(s_)
         return w
 
     def forward(self, x):
