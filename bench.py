@@ -677,8 +677,16 @@ def run_c3(args, rank, world, local, dev):
         x = {'image': inp['image'], 'uv': inp['uv']}
         c, v = inp['c'], {'uvcoords_image': inp['uvimg']}
         ws = net.encode(x['image'][:1])
+        # the two batch-1 backbone passes of eval_seq.py:170-171 are independent chains of small launches: side by side on two streams
+        cur = torch.cuda.current_stream(dev)
+        side = rt.side_streams(dev, 7)[6]
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            sta = G.backbone.synthesis(ws, cond_list=None, return_list=True, update_emas=False, noise_mode='const')
         tex = G.texture_backbone.synthesis(ws, cond_list=None, return_list=True, update_emas=False, noise_mode='const')
-        sta = G.backbone.synthesis(ws, cond_list=None, return_list=True, update_emas=False, noise_mode='const')
+        cur.wait_stream(side)
+        for t in sta:
+            t.record_stream(cur)
         if draws is not None:
             G.renderer.depth_jitter, G.renderer.importance_u = draws[0], draws[1]
         upd, _ = net.AR_eval_forward(x, c, v, ws, [None, None], e4e_results={'w': ws, 'texture': tex, 'static': sta}, return_fake=False)

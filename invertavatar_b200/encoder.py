@@ -453,6 +453,59 @@ class TriPlanefeat_Encoder(_UNetBase):
         return (out_list, r_list) if self.use_gru else out_list
 
 
+def _sft_head(mod, res, t):
+    """stack([condition_scale(t), condition_shift(t)]) -> logical [2,B,C,H,W] over one NHWC buffer (unet_encoders.py:337-345).  The two
+    branches share one operand of t; each first convolution applies its bias + LeakyReLU(0.2) in its epilogue and emits the second
+    convolution's operand."""
+    B, H, W, _ = t.shape
+    Cs = getattr(mod, f'condition_scale{res}')[2].out_channels
+    out = torch.empty((2, B, H, W, Cs), dtype=torch.float32, device=t.device)
+    fuse = rt.enc_epilogue_fusion()
+    a = None
+    for k, kind in enumerate(('scale', 'shift')):
+        c0, _, c2 = getattr(mod, f'condition_{kind}{res}')
+        if fuse and c0.out_channels % 4 == 0:
+            if a is None:
+                a, _ = rt.enc_prep([t], C_pad=rt.ConvPack.current(c0, '_ia_pack', c0.weight, need_wsq=False).Cin_pad)
+            a2 = rt.enc_conv_act(a, c0, rt.ConvPack.current(c2, '_ia_pack', c2.weight, need_wsq=False).Cin_pad, lrelu=0.2)
+            rt.enc_affine_act(rt.enc_conv(a2, c2), shift=c2.bias, out=out[k])
+        else:
+            y = _conv_bias_act([t], c0, lrelu=0.2)
+            _conv_bias_act([y], c2, out=out[k])
+    return out.permute(0, 1, 4, 2, 3)
+
+
+def _sft_heads(mod, ts):
+    """final_head + the five condition_scale / condition_shift heads of a tri-plane SFT UNet (unet_encoders.py:337-345).  The heads
+    of the four decoder levels are independent two-convolution chains: they are issued on side streams while the caller's stream
+    runs final_head and the 256^2 head, and joined before the dict is returned (IA_SFT_STREAMS=0: all on the caller's stream)."""
+    t1, t2, t3, t4 = ts
+    dev = t4.device
+    out = {}
+    side = []
+    if os.environ.get('IA_SFT_STREAMS', '1') != '0':
+        cur = torch.cuda.current_stream(dev)
+        side = rt.side_streams(dev, 11)[7:11]
+        for s_ in side:
+            s_.wait_stream(cur)
+    for k, (res, t) in enumerate(zip((16, 32, 64, 128), ts)):
+        if side:
+            with torch.cuda.stream(side[k % len(side)]):
+                out[res] = mod._head(res, t)
+        else:
+            out[res] = mod._head(res, t)
+    f0, p0, f2, p2 = mod.final_head
+    y = _conv_bias_act([(t4, mod.head.upscale_factor)], f0, slope=p0.weight)
+    t5 = _conv_bias_act([y], f2, slope=p2.weight)
+    out[256] = mod._head(256, t5)
+    if side:
+        for s_ in side:
+            cur.wait_stream(s_)
+        for res in (16, 32, 64, 128):
+            out[res].record_stream(cur)      # produced on a side stream, consumed (and eventually freed) on the caller's stream
+    return {res: out[res] for res in (16, 32, 64, 128, 256)}
+
+
 class TriPlaneSFTfeat_Encoder(_UNetBase):
     """Tri-plane SFT UNet, unet_encoders.py:249-362."""
 
@@ -475,22 +528,11 @@ class TriPlaneSFTfeat_Encoder(_UNetBase):
                     nn.Conv2d(out_channels, sft_out_channels, 3, 1, 1)))
 
     def _head(self, res, t):
-        """stack([condition_scale(t), condition_shift(t)]) -> logical [2,B,C,H,W] over one NHWC buffer."""
-        B, H, W, _ = t.shape
-        Cs = getattr(self, f'condition_scale{res}')[2].out_channels
-        out = torch.empty((2, B, H, W, Cs), dtype=torch.float32, device=t.device)
-        for k, kind in enumerate(('scale', 'shift')):
-            c0, _, c2 = getattr(self, f'condition_{kind}{res}')
-            y = _conv_bias_act([t], c0, lrelu=0.2)
-            _conv_bias_act([y], c2, out=out[k])
-        return out.permute(0, 1, 4, 2, 3)
+        return _sft_head(self, res, t)
 
     def forward(self, x, r_list=None):
         (t1, t2, t3, t4), r_list, _ = self._trunk_decoder(x, r_list)
-        f0, p0, f2, p2 = self.final_head
-        y = _conv_bias_act([(t4, self.head.upscale_factor)], f0, slope=p0.weight)
-        t5 = _conv_bias_act([y], f2, slope=p2.weight)
-        out = {res: self._head(res, t) for res, t in zip((16, 32, 64, 128, 256), (t1, t2, t3, t4, t5))}
+        out = _sft_heads(self, (t1, t2, t3, t4))
         return (out, r_list) if self.use_gru else out
 
 

@@ -21,7 +21,7 @@ import torch
 from torch import nn
 
 from . import runtime as rt
-from .encoder import (ConvGRU, DoubleConv, Encoder4Editing, _conv_bias_act, _face_pool, _make_trunk, _nchw, _nhwc, _run_trunk,
+from .encoder import (ConvGRU, DoubleConv, Encoder4Editing, _conv_bias_act, _face_pool, _make_trunk, _nchw, _nhwc, _run_trunk, _sft_head, _sft_heads,
                       inversionNet as _inversionNet_base)
 
 
@@ -373,21 +373,11 @@ class TriPlaneSFTfeat_SegformerDecoder(_SegformerDecoderBase):
                     nn.Conv2d(out_channels, sft_out_channels, 3, 1, 1)))
 
     def _head(self, res, t):
-        B, H, W, _ = t.shape
-        Cs = getattr(self, f'condition_scale{res}')[2].out_channels
-        out = torch.empty((2, B, H, W, Cs), dtype=torch.float32, device=t.device)
-        for k, kind in enumerate(('scale', 'shift')):
-            c0, _, c2 = getattr(self, f'condition_{kind}{res}')
-            y = _conv_bias_act([t], c0, lrelu=0.2)
-            _conv_bias_act([y], c2, out=out[k])
-        return out.permute(0, 1, 4, 2, 3)
+        return _sft_head(self, res, t)
 
     def forward(self, x, r_list=None):
         (t1, t2, t3, t4), r_list = self._trunk_decoder(x, r_list)
-        f0, p0, f2, p2 = self.final_head
-        y = _conv_bias_act([(t4, self.head.upscale_factor)], f0, slope=p0.weight)
-        t5 = _conv_bias_act([y], f2, slope=p2.weight)
-        out = {res: self._head(res, t) for res, t in zip((16, 32, 64, 128, 256), (t1, t2, t3, t4, t5))}
+        out = _sft_heads(self, (t1, t2, t3, t4))
         return (out, r_list) if self.use_gru else out
 
 
