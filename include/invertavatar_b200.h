@@ -434,6 +434,12 @@ int ia_enc_affine_act(const ia_enc_affine_params* p, void* stream);
 /* pooled[b][c] = mean over H,W of x*scale[c] + shift[c] (AdaptiveAvgPool2d(1) of SEModule, helpers.py:65,74). */
 int ia_enc_global_pool(const ia_view* x, const float* scale, const float* shift, int32_t B, int32_t H, int32_t W,
                        float* pooled, void* stream);
+/* The whole SEModule gate in one launch (helpers.py:62-80): gate[b][c] = sigmoid(w2 . relu(w1 . pooled[b])) with pooled as in
+ * ia_enc_global_pool; w1 [Cr][C], w2 [C][Cr] (the bias-free 1x1 convolutions fc1 / fc2).  sums [B][C] fp32 and counters [B] int32 are
+ * scratch that must be ZERO before the first launch that uses them; every launch leaves them zero again.  They belong to one stream
+ * at a time (launches on one stream may share them). */
+int ia_enc_se_gate(const ia_view* x, const float* scale, const float* shift, int32_t B, int32_t H, int32_t W, const float* w1,
+                   const float* w2, int32_t Cr, float* sums, int32_t* counters, float* gate, void* stream);
 /* k x k box average, NHWC out [B][H/k][W/k][C] (AdaptiveAvgPool2d((256,256)) on 512^2 inputs, uvnet.py:108-109,
  * unet_encoders.py:199-200; only integer ratios occur). */
 int ia_enc_avgpool(const ia_view* x, int32_t B, int32_t H, int32_t W, int32_t k, float* y, void* stream);

@@ -238,6 +238,8 @@ SIGNATURES = {
     'ia_enc_prep': (C.c_int, [C.POINTER(EncPrepParams), C.c_void_p]),
     'ia_enc_affine_act': (C.c_int, [C.POINTER(EncAffineParams), C.c_void_p]),
     'ia_enc_global_pool': (C.c_int, [C.POINTER(View), c_f32p, c_f32p, C.c_int32, C.c_int32, C.c_int32, c_f32p, C.c_void_p]),
+    'ia_enc_se_gate': (C.c_int, [C.POINTER(View), c_f32p, c_f32p, C.c_int32, C.c_int32, C.c_int32, c_f32p, c_f32p, C.c_int32, c_f32p, c_i32p, c_f32p,
+                                C.c_void_p]),
     'ia_enc_avgpool': (C.c_int, [C.POINTER(View), C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_f32p, C.c_void_p]),
     'ia_enc_upsample_add': (C.c_int, [c_f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_f32p, C.c_int32, C.c_int32, c_f32p, C.c_void_p]),
     'ia_enc_gru_gate': (C.c_int, [C.c_int32, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int64, C.c_int32, C.c_void_p]),

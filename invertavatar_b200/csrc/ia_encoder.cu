@@ -203,6 +203,66 @@ __global__ void global_pool_finish_kernel(float* __restrict__ pooled, const floa
     pooled[i] = m;
 }
 
+// ---- squeeze-excite gate in ONE launch (helpers.py:62-80): gate[b][c] = sigmoid(fc2(relu(fc1(mean_hw(x*scale + shift))))) ---------
+// grid (B, ceil(C/32), pixel chunks) as global_pool_kernel: partial channel sums are added atomically into `sums` [B][C]; the last
+// CTA of an image to arrive on the image's ticket (threadfence + atomic counter) turns the sums into the pooled vector, evaluates
+// the two tiny bias-free layers from shared memory and leaves `sums` / the counter zeroed for the next launch on the same stream.
+__global__ void __launch_bounds__(256) se_gate_kernel(ia_view v, const float* __restrict__ scale, const float* __restrict__ shift, int H, int W,
+                                                      int pix_per_block, float* __restrict__ sums, int* __restrict__ counters,
+                                                      const float* __restrict__ w1, const float* __restrict__ w2, int Cr,
+                                                      float* __restrict__ gate) {
+    const int b = blockIdx.x;
+    const int C = v.C;
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const int c = blockIdx.y * 32 + lane;
+    const int npix = H * W;
+    const int p0 = blockIdx.z * pix_per_block;
+    const int p1 = min(p0 + pix_per_block, npix);
+    float s = 0.f;
+    if (c < C) {
+        for (int p = p0 + wrp; p < p1; p += 8) s += view_at(v, b, p / W, p % W, c);
+    }
+    __shared__ float sh[8][32];
+    __shared__ int s_last;
+    sh[wrp][lane] = s;
+    __syncthreads();
+    if (wrp == 0 && c < C) {
+        for (int k = 1; k < 8; ++k) s += sh[k][lane];
+        atomicAdd(&sums[(int64_t)b * C + c], s);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&counters[b], 1) == (int)(gridDim.y * gridDim.z) - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    extern __shared__ float dyn[];          // pooled [C] | hidden [Cr]
+    float* pooled = dyn;
+    float* hid = dyn + C;
+    const float inv = 1.f / (float)npix;
+    for (int i = threadIdx.x; i < C; i += 256) {
+        float m = __ldcg(&sums[(int64_t)b * C + i]) * inv;
+        if (scale) m = fmaf(m, scale[i], shift ? shift[i] : 0.f);
+        pooled[i] = m;
+        sums[(int64_t)b * C + i] = 0.f;
+    }
+    if (threadIdx.x == 0) counters[b] = 0;
+    __syncthreads();
+    for (int o = wrp; o < Cr; o += 8) {     // fc1 + ReLU: one warp per output
+        float a = 0.f;
+        for (int i = lane; i < C; i += 32) a = fmaf(pooled[i], w1[(int64_t)o * C + i], a);
+#pragma unroll
+        for (int k = 16; k; k >>= 1) a += __shfl_xor_sync(0xffffffffu, a, k);
+        if (lane == 0) hid[o] = a > 0.f ? a : 0.f;
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < C; o += 256) {     // fc2 + sigmoid
+        float a = 0.f;
+        for (int i = 0; i < Cr; ++i) a = fmaf(hid[i], w2[(int64_t)o * Cr + i], a);
+        gate[(int64_t)b * C + o] = 1.f / (1.f + expf(-a));
+    }
+}
+
 __global__ void __launch_bounds__(256) avgpool_kernel(ia_view v, int B, int OH, int OW, int k, float* __restrict__ y) {
     const int64_t total = (int64_t)B * OH * OW * v.C;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -375,6 +435,24 @@ extern "C" int ia_enc_global_pool(const ia_view* x, const float* scale, const fl
     ia::prof_begin("ia_enc_global_pool", as_stream(stream));
     global_pool_finish_kernel<<<(unsigned)cdiv((int64_t)B * x->C, 128), 128, 0, as_stream(stream)>>>(pooled, scale, shift, B, x->C, 1.0f / (float)npix);
     IA_LAUNCH_CHECK("ia_enc_global_pool");
+    return 0;
+}
+
+extern "C" int ia_enc_se_gate(const ia_view* x, const float* scale, const float* shift, int32_t B, int32_t H, int32_t W, const float* w1,
+                              const float* w2, int32_t Cr, float* sums, int32_t* counters, float* gate, void* stream) {
+    if (int rc = check_view(x, "ia_enc_se_gate")) return rc;
+    IA_CHECK(w1 && w2 && sums && counters && gate && B > 0 && H > 0 && W > 0 && Cr > 0, "ia_enc_se_gate: bad arguments");
+    IA_CHECK((size_t)(x->C + Cr) * sizeof(float) <= 40 * 1024, "ia_enc_se_gate: C + Cr too large for the shared-memory vectors");
+    const int npix = H * W;
+    const int cblocks = (int)cdiv(x->C, 32);
+    int chunks = (int)cdiv(148 * 4, (int64_t)B * cblocks);
+    int ppb = (int)cdiv(npix, chunks);
+    if (ppb < 64) ppb = 64;
+    chunks = (int)cdiv(npix, ppb);
+    dim3 grid((unsigned)B, (unsigned)cblocks, (unsigned)chunks);
+    ia::prof_begin("ia_enc_se_gate", as_stream(stream));
+    se_gate_kernel<<<grid, 256, (size_t)(x->C + Cr) * sizeof(float), as_stream(stream)>>>(*x, scale, shift, H, W, ppb, sums, counters, w1, w2, Cr, gate);
+    IA_LAUNCH_CHECK("ia_enc_se_gate");
     return 0;
 }
 

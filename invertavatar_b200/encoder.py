@@ -82,8 +82,10 @@ class SEModule(Module):
 
     def gate(self, x, scale=None, shift=None):
         """sigmoid(fc2(relu(fc1(mean_hw(x*scale+shift))))) -> [B,C]."""
-        pooled = rt.enc_global_pool(x, scale, shift)
         Cr, Cc = self.fc1.weight.shape[:2]
+        if rt.enc_epilogue_fusion():      # pool + fc1 + ReLU + fc2 + sigmoid in one launch
+            return rt.enc_se_gate(x, scale, shift, self.fc1.weight.reshape(Cr, Cc), self.fc2.weight.reshape(Cc, Cr))
+        pooled = rt.enc_global_pool(x, scale, shift)
         g = rt.fully_connected(pooled, self.fc1.weight.reshape(Cr, Cc), None, act='relu', act_gain=1.0)
         return rt.fully_connected(g, self.fc2.weight.reshape(Cc, Cr), None, act='sigmoid', act_gain=1.0)
 

@@ -1303,6 +1303,28 @@ def enc_global_pool(x, scale=None, shift=None):
     return pooled
 
 
+_SE_SCRATCH = {}
+
+
+def enc_se_gate(x, scale, shift, w1, w2):
+    """SEModule gate in one launch: x [B,H,W,C] view, (scale, shift) the folded BatchNorm in front of it (or None), w1 [Cr,C], w2 [C,Cr]
+    -> gate [B,C].  Zero-initialised scratch per (device, stream), left zeroed by every launch."""
+    xv, (B, H, W, Cc) = _as_view(x)
+    st = _enter(xv._keep)
+    dev = xv._keep.device
+    key = (dev.index, int(st or 0))
+    buf = _SE_SCRATCH.get(key)
+    if buf is None or buf[0].numel() < B * Cc or buf[1].numel() < B:
+        buf = (torch.zeros(max(B * Cc, 64 * 1024), dtype=torch.float32, device=dev), torch.zeros(max(B, 256), dtype=torch.int32, device=dev))
+        _SE_SCRATCH[key] = buf
+    gate = torch.empty((B, Cc), dtype=torch.float32, device=dev)
+    Cr = w1.shape[0]
+    assert tuple(w1.shape) == (Cr, Cc) and tuple(w2.shape) == (Cc, Cr) and w1.is_contiguous() and w2.is_contiguous()
+    _C.check(_C.lib().ia_enc_se_gate(C.byref(xv), _p(scale), _p(shift), B, H, W, _p(w1), _p(w2), Cr, _p(buf[0]), _p(buf[1]), _p(gate), st),
+             'ia_enc_se_gate')
+    return gate
+
+
 def enc_avgpool(x, k):
     xv, (B, H, W, Cc) = _as_view(x)
     st = _enter(xv._keep)
