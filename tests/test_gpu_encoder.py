@@ -150,3 +150,34 @@ def test_ar_eval_forward_golden(npz, precision):
                     compare(t, unpack(f'{tag}/r{k}_{i}', g), RTOL, f'r{k}_{i}')
             assert fake['image'].shape == (T, 3, 512, 512) and bool(torch.isfinite(fake['image']).all())
             print(f'AR_eval_forward call {call}: worst feature error {worst:.2e}')
+
+
+def test_fused_and_unfused_encoder_paths_agree(net, monkeypatch):
+    """IA_ENC_FUSE=1 (PReLU / LeakyReLU in the producing convolution's epilogue with operand emission, the next unit's BatchNorm
+    operand emitted by the closing pass, one-launch squeeze-excite gate) against IA_ENC_FUSE=0 (separate passes): same arithmetic,
+    so the two agree to fp32 rounding of the re-associated SE sums (1e-5), on an eval-mode trunk slice, a DoubleConv and an SFT head."""
+    from invertavatar_b200 import encoder as enc
+    from invertavatar_b200 import runtime as rt
+    tri = copy.deepcopy(net.unet_encoder.triplane_unet).to(DEV).eval()
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(2, 64, 32, 32, generator=g).to(DEV)
+
+    def trunk_slice(xin):
+        # body[3] (64 -> 128, stride 2, projected shortcut) .. body[5]: chained emission across three units
+        a, y = None, xin.permute(0, 2, 3, 1)
+        blocks = list(tri.body)[3:6]
+        for i, blk in enumerate(blocks):
+            nxt = blocks[i + 1].opening_affine() if (i + 1 < len(blocks) and rt.enc_epilogue_fusion()) else None
+            out = blk.run_nhwc(y, a=a, emit=nxt)
+            y, a = out if nxt is not None else (out, None)
+        return y
+    t_in = torch.randn(2, 96, 24, 24, generator=g).to(DEV)
+    dc_in = torch.randn(2, 224, 16, 16, generator=g).to(DEV)
+    outs = {}
+    with torch.no_grad():
+        for flag in ('1', '0'):
+            monkeypatch.setenv('IA_ENC_FUSE', flag)
+            outs[flag] = (trunk_slice(x).clone(), tri.up3.conv(dc_in).clone(), enc._sft_head(tri, 128, t_in.permute(0, 2, 3, 1)).clone())
+    for a_, b_ in zip(outs['1'], outs['0']):
+        assert tuple(a_.shape) == tuple(b_.shape)
+        assert rel_err(a_, b_) < 1e-5
