@@ -543,19 +543,37 @@ class ConvPackGroup(_EngineCache):
 class StylePlan(_EngineCache):
     """Device table of ia_style_layer entries + output buffers for a group of layers that share one ws tensor."""
 
-    def __init__(self, entries, device):
+    def __init__(self, entries, device, share=None):
         # entries: list of dict(affine_w, affine_b, wsq|None, Cin, Cout, w_index, style_gain)
+        # share: optional list parallel to entries of None | (key, g, G): the entry's style / dcoef rows live in rows [g*B, (g+1)*B)
+        # of a [G*B, C] buffer shared by the G entries with the same key (the same layer of G networks evaluated as one grouped
+        # batch: the group-major vectors the grouped convolutions read exist without any concatenation)
         self.entries = entries
         self.device = device
+        self.share = share
+        self.shared = {}          # B -> {key: (styles [G*B,Cin], dcoefs [G*B,Cout] | None)}
         self._by_batch = {}       # B -> (styles, dcoefs, host table, device table): callers alternate between batch sizes (an identity of
                                   # eval_seq.py runs the backbones at B = 1 and the T-frame render at B = T), and a rebuild is an
                                   # unpinned H2D copy -- not allowed inside a CUDA-graph capture and a stall outside of one
 
     def _build(self, B):
         n = len(self.entries)
-        styles = [torch.empty((B, e['Cin']), dtype=torch.float32, device=self.device) for e in self.entries]
-        dcoefs = [torch.empty((B, e['Cout']), dtype=torch.float32, device=self.device) if e['wsq'] is not None else None
-                  for e in self.entries]
+        styles, dcoefs, shared = [], [], {}
+        for i, e in enumerate(self.entries):
+            sh = self.share[i] if self.share is not None else None
+            if sh is None:
+                styles.append(torch.empty((B, e['Cin']), dtype=torch.float32, device=self.device))
+                dcoefs.append(torch.empty((B, e['Cout']), dtype=torch.float32, device=self.device) if e['wsq'] is not None else None)
+                continue
+            key, g, G = sh
+            if key not in shared:
+                shared[key] = (torch.empty((G * B, e['Cin']), dtype=torch.float32, device=self.device),
+                               torch.empty((G * B, e['Cout']), dtype=torch.float32, device=self.device) if e['wsq'] is not None else None)
+            S, D = shared[key]
+            assert S.shape[1] == e['Cin'] and (D is None) == (e['wsq'] is None) and (D is None or D.shape[1] == e['Cout'])
+            styles.append(S[g * B:(g + 1) * B])
+            dcoefs.append(None if D is None else D[g * B:(g + 1) * B])
+        self.shared[B] = shared
         arr = (_C.StyleLayer * n)()
         for i, e in enumerate(self.entries):
             w_dim = e['affine_w'].shape[1]

@@ -234,14 +234,14 @@ def _layer_filter_ok(layer):
     return ok
 
 
-def _plan_for(owner, entries):
+def _plan_for(owner, entries, attr='_ia_plan', share=None):
     """StylePlan cached on ``owner``; rebuilt when any referenced tensor moved (new storage / device)."""
     key = tuple((e['affine_w'].data_ptr(), e['affine_b'].data_ptr(), 0 if e['wsq'] is None else e['wsq'].data_ptr(),
-                 e['w_index']) for e in entries)
-    cached = owner.__dict__.get('_ia_plan')
+                 e['w_index']) for e in entries) + (None if share is None else tuple(share),)
+    cached = owner.__dict__.get(attr)
     if cached is None or cached[1] is None or cached[0] != key:
-        cached = (key, rt.StylePlan(entries, entries[0]['affine_w'].device))
-        owner.__dict__['_ia_plan'] = cached
+        cached = (key, rt.StylePlan(entries, entries[0]['affine_w'].device, share=share))
+        owner.__dict__[attr] = cached
     return cached[1]
 
 
@@ -623,13 +623,37 @@ def synthesis_prefix_grouped(nets, ws, noise_mode='const', upto_res=32):
     ws = ws.to(torch.float32)
     B = ws.shape[0]
     dev = ws.device
-    passes = [n.style_pass(ws) for n in nets]
-    spans = passes[0][2]
     k_last = nets[0].block_resolutions.index(upto_res)
+    # ONE style / demodulation pass for all G networks (2 launches): the layers the grouped launches read -- every layer of the
+    # blocks up to upto_res plus the first layer of the block that follows -- write rows [g*B, (g+1)*B) of one group-major buffer
+    # per layer, so no concatenation is needed; the remaining layers get their own buffers, handed to each network's forward.
+    per_net = []
+    for n in nets:
+        entries, spans, w_idx = [], [], 0
+        for res in n.block_resolutions:
+            block = getattr(n, f'b{res}')
+            first = len(entries)
+            for j, (kind, layer) in enumerate(block.layers()):
+                entries.append(layer.style_entry(w_idx + j))
+            spans.append((first, len(entries)))
+            w_idx += block.num_conv
+        per_net.append((entries, spans))
+    spans = per_net[0][1]
+    n_shared = spans[k_last + 1][0] + 1
+    all_entries, share, offs = [], [], []
+    for g, (entries, _) in enumerate(per_net):
+        offs.append(len(all_entries))
+        for i, e in enumerate(entries):
+            all_entries.append(e)
+            share.append((i, g, G) if i < n_shared else None)
+    plan = _plan_for(nets[0], all_entries, attr='_ia_gplan', share=share)
+    st_all, dc_all = plan.run(ws)
+    shared = plan.shared[B]
+    passes = [(st_all[o:o + len(per_net[g][0])], dc_all[o:o + len(per_net[g][0])], per_net[g][1]) for g, o in enumerate(offs)]
     group = lambda gstride: (G, B, gstride)
 
-    def cat_layer(idx, which):       # per-layer styles / dcoefs of all networks, group-major
-        return torch.cat([ps[which][idx] for ps in passes], dim=0)
+    def cat_layer(idx, which):       # per-layer styles / dcoefs of all networks, group-major (rows g*B .. of the shared buffer)
+        return shared[idx][which]
 
     def layer_noise(layers):
         l0 = layers[0]
