@@ -610,7 +610,7 @@ def run_c2(args, rank, world, local, dev):
                     # 128->128 @512^2 layer at batch 8 reads 1.085 GB and writes 1.030 GB; its algorithmic bytes are the bf16 hi/lo
                     # operand in (1.074 GB) and the next layer's operand out (1.074 GB) -- no re-reads
                     'traffic': 1.127e9, 'traffic_launch': 'conv_tc2 128->128 @512x512 (SR block1 conv1, ToRGB fused), batch 8: dram read 1.100 GB + write 0.027 GB '
-                    '(profiles/r2_conv_full_v12.txt); algorithmic 1.074 GB of bf16 hi/lo operand + 0.6 MB of weights + 25 MB of rgb',
+                    '(profiles/r2_conv_full_v16.txt); algorithmic 1.074 GB of bf16 hi/lo operand + 0.6 MB of weights + 25 MB of rgb',
                     'algorithmic_flops_per_frame': counted['algorithmic'] / (B * args.steps),
                     'reference_flops_per_frame_incl_dead_layers': per_frame,
                     'issued_mma_flops_per_frame': counted['issued_mma'] / (B * args.steps),
