@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument('--depth', type=int, default=48, help='coarse = importance depth samples per ray')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-roofline', action='store_true')
+    ap.add_argument('--c3-inflight', type=int, default=1, help='workload c3: identities in flight per GPU and step, each replaying its own graph on its own stream (throughput mode; default 1 = one identity at a time)')
     ap.add_argument('--c3-per-frame', action='store_true', help='workload c3: render the T driven frames with T batch-1 synthesis_withTexture calls (the loop of eval_seq.py:212) instead of one batch-T call')
     ap.add_argument('--no-graph', action='store_true', help='issue the step eagerly (Python + ctypes launches) instead of replaying its CUDA graph')
     ap.add_argument('--e2e-f32', action='store_true', help='end-to-end leg reads back the fp32 images instead of uint8 HWC frames')
@@ -72,7 +73,8 @@ def workload_config(args, n_gpus, frames_per_step=None):
         return {'workload': f'eval_seq.py few-shot path (BASELINE configs[2]): encode B=1 + AR_eval_forward T={T_C3} ({args.res}^2 x {args.depth}+{args.depth} render inside) '
                             + (f'+ {T_C3} x synthesis_withTexture (batch 1 each)' if getattr(args, 'c3_per_frame', False) else f'+ one batch-{T_C3} synthesis_withTexture call for the {T_C3} driven frames')
                             + ', random-init inversionNet + generator, synthetic images/UV/cameras',
-                'frames_per_gpu_per_step': T_C3, 'global_frames_per_step': T_C3 * n_gpus, 'identities_per_gpu_per_step': 1,
+                'frames_per_gpu_per_step': T_C3 * getattr(args, 'c3_inflight', 1), 'global_frames_per_step': T_C3 * n_gpus * getattr(args, 'c3_inflight', 1),
+                'identities_per_gpu_per_step': getattr(args, 'c3_inflight', 1),
                 'neural_res': args.res, 'depth_samples': [args.depth, args.depth],
                 'parallelism': f'{n_gpus} replica(s): identities are independent, the ConvGRU state is sequential inside one',
                 'conv_precision': _conv_precision(), 'gather': 'none',
@@ -718,9 +720,29 @@ def run_c3(args, rank, world, local, dev):
             identity(res_in)
             launches_per_step = rt.launch_count()
         graphed = GraphedCall(lambda **kw: identity(kw), res_in)
+    # throughput mode (--c3-inflight n > 1): n independent identities per step, each on its own stream with its own graph -- the
+    # identity step is a chain of short, latency-bound launches (few CTAs each), so concurrent chains fill the idle SMs
+    n_fl = max(1, int(args.c3_inflight)) if graphed is not None else 1
+    extra = [GraphedCall(lambda **kw: identity(kw), res_in) for _ in range(n_fl - 1)] if n_fl > 1 else []
+    fl_streams = [torch.cuda.Stream(device=dev) for _ in range(n_fl - 1)]
+
+    def replay_all(inputs=None):
+        # -> list of the n identities' frame tensors; identity 0 on the caller's stream, the others on their own streams
+        cur = torch.cuda.current_stream(dev)
+        outs = [None] * n_fl
+        for k, (g, s_) in enumerate(zip(extra, fl_streams)):
+            s_.wait_stream(cur)
+            with torch.cuda.stream(s_):
+                outs[k + 1] = g(**inputs) if inputs else g()
+        outs[0] = graphed(**inputs) if inputs else graphed()
+        for s_ in fl_streams:
+            cur.wait_stream(s_)
+        return outs
 
     def step_resident():
-        return graphed() if graphed is not None else identity(res_in)
+        if graphed is None:
+            return identity(res_in)
+        return replay_all()[0] if n_fl > 1 else graphed()
 
     copy_stream = torch.cuda.Stream(device=dev)
     h = _Harness(dev, world, copy_stream)
@@ -736,6 +758,14 @@ def run_c3(args, rank, world, local, dev):
 
     def step_e2e():
         cur = torch.cuda.current_stream()
+        if graphed is not None and n_fl > 1:
+            imgs = replay_all(host_in)           # every identity uploads its own inputs on its own stream, then replays
+            img = torch.cat(imgs) if args.e2e_f32 else None
+            out = img if args.e2e_f32 else rt.layout_grid_u8(torch.cat(imgs), grid_w=T_C3 * n_fl, grid_h=1)
+            if rb['o'] is None:
+                rb['o'] = _Readback(out, copy_stream)
+            rb['o'].push(out)
+            return imgs[0]
         if graphed is not None:
             img = graphed(**host_in)             # pinned host -> the graph's static input buffers (H2D on the compute stream), replay
         else:
@@ -836,17 +866,20 @@ def run_c3(args, rank, world, local, dev):
             got = identity(res_in, draws=(jit_ar.to(dev), u_ar.to(dev), [j.to(dev) for j in jit_frames])).float().cpu()
             parity = _parity(got, ref_img, f'the {T_C3} driven frames of one identity step vs the oracle step of the cpu_baseline leg (same images, UV, cameras, pinned draws)')
 
-    frames = T_C3 * world * args.steps
+    frames = T_C3 * n_fl * world * args.steps
     if rank != 0:
         return None
+    if launches is not None:
+        launches = launches * n_fl if graphed is not None else launches
     line = {'metric': METRIC_C3, 'value': frames / (ms * 1e-3), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
             'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
             'data': 'synthetic', 'config': workload_config(args, world), 'clocks': clk,
-            'e2e': {'value': frames / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': sum(t.numel() * t.element_size() for t in host_in.values()),
+            'e2e': {'value': frames / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': n_fl * sum(t.numel() * t.element_size() for t in host_in.values()),
                     'd2h_bytes_per_step': rb['o'].bytes, 'ms_per_step': ms_e2e / args.steps,
                     'readback': 'fp32 NCHW images' if args.e2e_f32 else 'uint8 HWC frames (layout_grid, eval_seq.py:214)'},
-            'gpu_launches': launches, 'identities_per_s': world * args.steps / (ms * 1e-3),
-            'issue': 'eager (Python + ctypes launches)' if graphed is None else 'one CUDA graph per identity step (invertavatar_b200.graphs.GraphedCall), replayed'}
+            'gpu_launches': launches, 'identities_per_s': n_fl * world * args.steps / (ms * 1e-3),
+            'issue': 'eager (Python + ctypes launches)' if graphed is None else
+                     'one CUDA graph per identity step (invertavatar_b200.graphs.GraphedCall), replayed' + (f'; {n_fl} identities in flight per step on {n_fl} streams' if n_fl > 1 else '')}
     if stages is not None:
         line['stages'] = stages
     if roofline is not None:

@@ -11,6 +11,8 @@ on the capturing stream with static buffers; tensor maps are encoded on the host
 The numbers are those of the eager call (same kernels, same order).  Inputs keep the shapes they had at capture."""
 import torch
 
+from . import runtime as rt
+
 
 class GraphedSynthesis:
     def __init__(self, G, ws, c, uvcoords_image, texture_feats=None, static_feats=None, neural_rendering_resolution=None,
@@ -24,16 +26,17 @@ class GraphedSynthesis:
         self.sta = None if static_feats is None else [t.detach().clone() for t in static_feats]
         self.res = neural_rendering_resolution
         self.evaluation = evaluation
-        side = torch.cuda.Stream(device=ws.device)
-        side.wait_stream(torch.cuda.current_stream(ws.device))
-        with torch.cuda.stream(side), torch.no_grad():
-            for _ in range(warmup):          # builds every cache (packed weights, style plans, tap tables) outside the capture
-                self._call()
-        torch.cuda.current_stream(ws.device).wait_stream(side)
-        torch.cuda.synchronize(ws.device)
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.no_grad(), torch.cuda.graph(self.graph):
-            self.out = self._call()
+        with rt.capture_scope():     # persistent engine state built / requested in here is private to this graph (runtime._scratch_key)
+            side = torch.cuda.Stream(device=ws.device)
+            side.wait_stream(torch.cuda.current_stream(ws.device))
+            with torch.cuda.stream(side), torch.no_grad():
+                for _ in range(warmup):          # builds every cache (packed weights, style plans, tap tables) outside the capture
+                    self._call()
+            torch.cuda.current_stream(ws.device).wait_stream(side)
+            torch.cuda.synchronize(ws.device)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.no_grad(), torch.cuda.graph(self.graph):
+                self.out = self._call()
 
     def _call(self):
         mc = {'uvcoords_image': self.uv}
@@ -73,16 +76,17 @@ class GraphedCall:
         assert dev.type == 'cuda', 'GraphedCall needs CUDA tensors'
         self.fn = fn
         self.inputs = {k: v.detach().clone() for k, v in inputs.items()}
-        side = torch.cuda.Stream(device=dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side), torch.no_grad():
-            for _ in range(warmup):          # builds every cache (packed weights, style plans, tap tables, split-K scratch) outside the capture
-                fn(**self.inputs)
-        torch.cuda.current_stream(dev).wait_stream(side)
-        torch.cuda.synchronize(dev)
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.no_grad(), torch.cuda.graph(self.graph):
-            self.out = fn(**self.inputs)
+        with rt.capture_scope():     # persistent engine state built / requested in here is private to this graph (runtime._scratch_key)
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side), torch.no_grad():
+                for _ in range(warmup):          # builds every cache (packed weights, style plans, tap tables, split-K scratch) outside the capture
+                    fn(**self.inputs)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.no_grad(), torch.cuda.graph(self.graph):
+                self.out = fn(**self.inputs)
 
     def __call__(self, **new_inputs):
         for k, v in new_inputs.items():

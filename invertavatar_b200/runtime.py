@@ -556,6 +556,14 @@ class StylePlan(_EngineCache):
                                   # eval_seq.py runs the backbones at B = 1 and the T-frame render at B = T), and a rebuild is an
                                   # unpinned H2D copy -- not allowed inside a CUDA-graph capture and a stall outside of one
 
+    def _key(self, B):
+        """Output buffers are static per batch size -- and per capture scope: a graph captured by graphs.GraphedCall gets its own,
+        so that two graphs over the same module may replay concurrently (see _scratch_key)."""
+        return (B, _active_scope)
+
+    def shared_for(self, B):
+        return self.shared[self._key(B)]
+
     def _build(self, B):
         n = len(self.entries)
         styles, dcoefs, shared = [], [], {}
@@ -573,7 +581,7 @@ class StylePlan(_EngineCache):
             assert S.shape[1] == e['Cin'] and (D is None) == (e['wsq'] is None) and (D is None or D.shape[1] == e['Cout'])
             styles.append(S[g * B:(g + 1) * B])
             dcoefs.append(None if D is None else D[g * B:(g + 1) * B])
-        self.shared[B] = shared
+        self.shared[self._key(B)] = shared
         arr = (_C.StyleLayer * n)()
         for i, e in enumerate(self.entries):
             w_dim = e['affine_w'].shape[1]
@@ -582,7 +590,7 @@ class StylePlan(_EngineCache):
         raw = np.frombuffer(bytes(arr), dtype=np.uint8).copy()
         dev = torch.from_numpy(raw).to(self.device)
         built = (styles, dcoefs, arr, dev)
-        self._by_batch[B] = built
+        self._by_batch[self._key(B)] = built
         return built
 
     def run(self, ws):
@@ -592,7 +600,7 @@ class StylePlan(_EngineCache):
                 ws.stride(0) < ws.shape[1] * ws.shape[2]:   # (an expand()ed batch has stride 0: materialise it)
             ws = ws.float().contiguous()
         B = ws.shape[0]
-        built = self._by_batch.get(B) or self._build(B)
+        built = self._by_batch.get(self._key(B)) or self._build(B)
         styles, dcoefs, host, dev = built
         num_ws = max(ws.stride(0) // ws.shape[2], ws.shape[1])  # batch stride of a narrow() view, in rows
         _C.check(_C.lib().ia_styles(_p(dev), host, len(self.entries), _p(ws), B, num_ws, st), 'ia_styles')
@@ -689,6 +697,32 @@ def _emit(out32=None, e1=None, e2=None, rgb=None):
     return e
 
 
+# Persistent device state (split-K workspace + tickets, squeeze-excite sums, the static style / demodulation buffers of a StylePlan)
+# is owned by ONE stream at a time.  Two CUDA graphs captured separately use the same capture-stream handle and the same modules,
+# so keyed by (device, stream) / batch size alone they would share that state -- fine while their replays are serialised, a race
+# (corrupted tickets, illegal addresses, another identity's styles) when they replay concurrently on two streams.
+# graphs.GraphedCall / GraphedSynthesis therefore run their warm-up and capture inside ``capture_scope()``: state requested while a
+# scope is active is keyed by the scope as well, i.e. private to that graph (built during the warm-up, found again by the capture).
+_capture_scope_next = 0
+_active_scope = 0
+
+
+class capture_scope:
+    def __enter__(self):
+        global _capture_scope_next, _active_scope
+        _capture_scope_next += 1
+        self.prev, _active_scope = _active_scope, _capture_scope_next
+        return _active_scope
+
+    def __exit__(self, *exc):
+        global _active_scope
+        _active_scope = self.prev
+
+
+def _scratch_key(device, st):
+    return (device.index, int(st or 0), _active_scope)
+
+
 _SPLITK = {}
 _SPLITK_WS_BYTES = 48 << 20          # fp32 partial accumulators: tiles x 256 pixels x N tile x splits (<= ~150 tile-splits of 128 KB)
 _SPLITK_COUNTERS = 4096              # 8 tickets per tile; split launches have fewer tiles than SMs
@@ -699,7 +733,7 @@ def _splitk_scratch(p, device, st):
     a stream are ordered; the counters are zero between launches).  Persistent, so CUDA-graph captures may hold them."""
     if os.environ.get('IA_CONV_SPLITK', '') == '0':
         return
-    key = (device.index, int(st or 0))
+    key = _scratch_key(device, st)
     buf = _SPLITK.get(key)
     if buf is None:
         buf = (torch.empty(_SPLITK_WS_BYTES // 4, dtype=torch.float32, device=device), torch.zeros(_SPLITK_COUNTERS, dtype=torch.int32, device=device))
@@ -1330,7 +1364,7 @@ def enc_se_gate(x, scale, shift, w1, w2):
     xv, (B, H, W, Cc) = _as_view(x)
     st = _enter(xv._keep)
     dev = xv._keep.device
-    key = (dev.index, int(st or 0))
+    key = _scratch_key(dev, st)
     buf = _SE_SCRATCH.get(key)
     if buf is None or buf[0].numel() < B * Cc or buf[1].numel() < B:
         buf = (torch.zeros(max(B * Cc, 64 * 1024), dtype=torch.float32, device=dev), torch.zeros(max(B, 256), dtype=torch.int32, device=dev))

@@ -648,7 +648,7 @@ def synthesis_prefix_grouped(nets, ws, noise_mode='const', upto_res=32):
             share.append((i, g, G) if i < n_shared else None)
     plan = _plan_for(nets[0], all_entries, attr='_ia_gplan', share=share)
     st_all, dc_all = plan.run(ws)
-    shared = plan.shared[B]
+    shared = plan.shared_for(B)
     passes = [(st_all[o:o + len(per_net[g][0])], dc_all[o:o + len(per_net[g][0])], per_net[g][1]) for g, o in enumerate(offs)]
     group = lambda gstride: (G, B, gstride)
 

@@ -70,6 +70,38 @@ def test_graphed_synthesis_matches_eager():
         G.renderer.fixed_jitter = None
 
 
+def test_two_graphs_over_one_module_replay_concurrently():
+    """Two GraphedSynthesis objects over the SAME generator, with different latents, replayed at the same time on two streams: each
+    must reproduce its own eager result.  The engine's persistent state (split-K workspace / tickets, the static style and
+    demodulation buffers of a StylePlan) is private to a captured graph (runtime.capture_scope); shared, the second replay would
+    overwrite the first one's styles or corrupt its split-K tickets."""
+    import copy
+    from invertavatar_b200.graphs import GraphedSynthesis
+    G = copy.deepcopy(build_generator(16, 16)).to('cuda')
+    cond = synth.frontal_camera(1).cuda()
+    cams, uvs = synth.cameras(2).cuda(), synth.uvcoords_image(2).cuda()
+    with torch.no_grad():
+        G.renderer.fixed_jitter = synth.depth_jitter(1, 64 * 64, 16).cuda()
+        wss = [G.mapping(synth.latents(1, first=k).cuda(), cond, truncation_psi=0.7, truncation_cutoff=14) for k in (0, 5)]
+        assert float((wss[0] - wss[1]).abs().max()) > 1e-2
+        want = [G.synthesis(wss[k], cams[k:k + 1], {'uvcoords_image': uvs[k:k + 1]}, neural_rendering_resolution=64, noise_mode='const',
+                            evaluation=True)['image'].clone() for k in range(2)]
+        gs = [GraphedSynthesis(G, wss[k], cams[k:k + 1], uvs[k:k + 1], neural_rendering_resolution=64) for k in range(2)]
+        streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+        torch.cuda.synchronize()
+        for rep in range(4):
+            outs = []
+            for k in range(2):
+                streams[k].wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(streams[k]):
+                    outs.append(gs[k]()['image'])
+            for s_ in streams:
+                torch.cuda.current_stream().wait_stream(s_)
+            for k in range(2):
+                assert float((outs[k] - want[k]).abs().max()) <= 1e-6, (rep, k)
+        G.renderer.fixed_jitter = None
+
+
 @pytest.mark.parametrize('B,OH,C,use32,use1,use2', [(2, 128, 64, True, True, True), (1, 64, 128, False, True, False), (3, 32, 32, True, False, True)])
 def test_fir_epilogue_variants_agree(monkeypatch, B, OH, C, use32, use1, use2):
     """The three FIR-epilogue kernels (TMA-fed ring, two-column register kernel, one-column register kernel) perform the same
