@@ -243,8 +243,9 @@ __global__ void __launch_bounds__(256, 1) attention_kernel(ia_attention_params p
 // keys / values stream through two 32-key shared-memory tiles (K and V separately, so the load of the next K tile overlaps
 // softmax + p v and the load of the next V tile overlaps q k^T).  Rows are 512 bytes; 16-byte chunks are XOR-swizzled with the
 // row index so every ldmatrix phase touches 8 distinct bank groups.
+template <int QW>               // QW = warps per CTA = 16-query row groups per CTA
 struct AttnTcSmem {
-    uint16_t q[2][128 * 256];      // hi, lo
+    uint16_t q[2][16 * QW * 256];  // hi, lo
     uint16_t k[2][32 * 256];
     uint16_t v[2][32 * 256];
 };
@@ -271,12 +272,14 @@ __device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], 
 // byte offset of 16-byte chunk `chunk` (0..31) of row `row` inside a [rows][256] bf16 tile
 __device__ __forceinline__ uint32_t swz(int row, int chunk) { return (uint32_t)(row * 512 + ((chunk ^ (row & 7)) << 4)); }
 
-__global__ void __launch_bounds__(256, 1) attention_tc_kernel(ia_attention_tc_params p) {
+template <int QW>
+__global__ void __launch_bounds__(32 * QW, 1) attention_tc_kernel(ia_attention_tc_params p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    AttnTcSmem& sm = *reinterpret_cast<AttnTcSmem*>(smem_raw);
+    AttnTcSmem<QW>& sm = *reinterpret_cast<AttnTcSmem<QW>*>(smem_raw);
+    constexpr int NT = 32 * QW;          // threads
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+    const int q0 = blockIdx.x * (16 * QW), h = blockIdx.y, b = blockIdx.z;
     const float sscale = p.scale * 1.4426950408889634f;
     const uint16_t* qsrc[2] = {p.q_hi + ((int64_t)b * p.Nq) * p.q_ld + h * 256, p.q_lo + ((int64_t)b * p.Nq) * p.q_ld + h * 256};
     const uint16_t* ksrc[2] = {p.kv_hi + ((int64_t)b * p.Nk) * p.kv_ld + h * 256, p.kv_lo + ((int64_t)b * p.Nk) * p.kv_ld + h * 256};
@@ -286,12 +289,12 @@ __global__ void __launch_bounds__(256, 1) attention_tc_kernel(ia_attention_tc_pa
     const uint32_t v_s[2] = {smem_u32(sm.v[0]), smem_u32(sm.v[1])};
 
     auto load_kv_tile = [&](const uint32_t (&dst)[2], int k0, int coff) {
-        // 32 rows x 32 chunks x {hi, lo} = 2048 chunks of 16 bytes, 8 per thread
+        // 32 rows x 32 chunks x {hi, lo} = 2048 chunks of 16 bytes, 2048 / NT per thread
 #pragma unroll
         for (int part = 0; part < 2; ++part)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int idx = tid + i * 256;
+            for (int i = 0; i < 1024 / NT; ++i) {
+                const int idx = tid + i * NT;
                 const int row = idx >> 5, chunk = idx & 31;
                 const bool ok = k0 + row < p.Nk;
                 const uint16_t* src = ksrc[part] + (int64_t)(ok ? k0 + row : 0) * p.kv_ld + coff + chunk * 8;
@@ -302,8 +305,8 @@ __global__ void __launch_bounds__(256, 1) attention_tc_kernel(ia_attention_tc_pa
 #pragma unroll
     for (int part = 0; part < 2; ++part)
 #pragma unroll 4
-        for (int i = 0; i < 16; ++i) {
-            const int idx = tid + i * 256;
+        for (int i = 0; i < 16; ++i) {       // 16 * QW rows x 32 chunks / NT threads = 16 per thread and part
+            const int idx = tid + i * NT;
             const int row = idx >> 5, chunk = idx & 31;
             const bool ok = q0 + row < p.Nq;
             cp_async16(q_s[part] + swz(row, chunk), qsrc[part] + (int64_t)(ok ? q0 + row : 0) * p.q_ld + chunk * 8, ok);
@@ -480,6 +483,24 @@ int check_view_(const ia_view* v, const char* who) {
     return 0;
 }
 
+template <int QW>
+int launch_attention_tc(const ia_attention_tc_params* p, cudaStream_t st) {
+    const size_t smem = sizeof(AttnTcSmem<QW>);
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<QW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        IA_CHECK(e == cudaSuccess, "ia_attention_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        attr_set[dev] = true;
+    }
+    dim3 grid((unsigned)cdiv(p->Nq, 16 * QW), (unsigned)p->heads, (unsigned)p->B);
+    ia::prof_begin("ia_attention_tc", st);
+    attention_tc_kernel<QW><<<grid, 32 * QW, smem, st>>>(*p);
+    IA_LAUNCH_CHECK("ia_attention_tc");
+    return 0;
+}
+
 template <int HD>
 int launch_attention(const ia_attention_params* p, cudaStream_t st) {
     const size_t smem = sizeof(AttnSmem<HD>);
@@ -563,20 +584,15 @@ extern "C" int ia_attention_tc(const ia_attention_tc_params* p, void* stream) {
              "ia_attention_tc: row pitches must cover heads*256 (q, out) / 2*heads*256 (kv) channels and be multiples of 8");
     IA_CHECK((((uintptr_t)p->q_hi | (uintptr_t)p->q_lo | (uintptr_t)p->kv_hi | (uintptr_t)p->kv_lo) & 15) == 0, "ia_attention_tc: operands must be 16-byte aligned");
     IA_CHECK(!p->out32 || (p->out32_ld >= Cc && (p->out32_ld & 1) == 0), "ia_attention_tc: out32_ld");
-    const size_t smem = sizeof(AttnTcSmem);
-    static bool attr_set[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        IA_CHECK(e == cudaSuccess, "ia_attention_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        attr_set[dev] = true;
-    }
-    dim3 grid((unsigned)cdiv(p->Nq, 128), (unsigned)p->heads, (unsigned)p->B);
-    ia::prof_begin("ia_attention_tc", as_stream(stream));
-    attention_tc_kernel<<<grid, 256, smem, as_stream(stream)>>>(*p);
-    IA_LAUNCH_CHECK("ia_attention_tc");
-    return 0;
+    // queries per CTA: 128 (8 warps) when that already gives a CTA per SM, else 64 / 32 (4 / 2 warps): the short sequences of the
+    // low-resolution UpLayers (64 ... 1024 tokens) then spread over 2 - 4x as many SMs, each warp keeping the tensor pipe of its SM
+    // to fewer neighbours
+    const int64_t bh = (int64_t)p->B * p->heads;
+    int qw = 8;
+    if (cdiv(p->Nq, 128) * bh < 120) qw = 4;
+    if (qw == 4 && cdiv(p->Nq, 64) * bh < 120) qw = 2;
+    { const char* ev = getenv("IA_ATTENTION_QW"); if (ev) { const int v = atoi(ev); if (v == 2 || v == 4 || v == 8) qw = v; } }
+    return qw == 8 ? launch_attention_tc<8>(p, as_stream(stream)) : qw == 4 ? launch_attention_tc<4>(p, as_stream(stream)) : launch_attention_tc<2>(p, as_stream(stream));
 }
 
 extern "C" int ia_dwconv_gelu(const float* x, const float* in_bias, const float* w, const float* bias, int32_t B, int32_t H, int32_t W,
