@@ -401,6 +401,12 @@ int ia_enc_chan_stats(const ia_view* x, int32_t B, int32_t H, int32_t W, double*
 int ia_enc_bn_fold(const double* sums, int64_t count, const float* gamma, const float* beta, float* running_mean,
                    float* running_var, int32_t training, float momentum, float eps, int32_t C, float* scale, float* shift,
                    void* stream);
+/* ia_enc_chan_stats + ia_enc_bn_fold (training) of ONE view in one launch: the last CTA to finish its partial sums folds.  sums
+ * [2C] float64 and counter [1] int32 are scratch, ZERO before the first launch that uses them and left zero by every launch; they
+ * belong to one stream at a time. */
+int ia_enc_bn_stats_fold(const ia_view* x, int32_t B, int32_t H, int32_t W, double* sums, int32_t* counter, const float* gamma,
+                         const float* beta, float* running_mean, float* running_var, float momentum, float eps, float* scale,
+                         float* shift, void* stream);
 /* Operand builder of an encoder convolution: concatenates up to 4 views along channels (torch.cat of
  * unet_encoders.py:78,96, uvnet.py:121,183), applies the per-channel affine of a preceding BatchNorm (scale/shift over
  * the concatenated channel index, may be NULL), an optional bias-free activation -- PReLU with per-channel `slope`, or

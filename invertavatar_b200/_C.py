@@ -235,6 +235,8 @@ SIGNATURES = {
     'ia_enc_chan_stats': (C.c_int, [C.POINTER(View), C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     'ia_enc_bn_fold': (C.c_int, [C.c_void_p, C.c_int64, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int32, C.c_float, C.c_float, C.c_int32,
                                 c_f32p, c_f32p, C.c_void_p]),
+    'ia_enc_bn_stats_fold': (C.c_int, [C.POINTER(View), C.c_int32, C.c_int32, C.c_int32, C.c_void_p, c_i32p, c_f32p, c_f32p, c_f32p, c_f32p,
+                                      C.c_float, C.c_float, c_f32p, c_f32p, C.c_void_p]),
     'ia_enc_prep': (C.c_int, [C.POINTER(EncPrepParams), C.c_void_p]),
     'ia_enc_affine_act': (C.c_int, [C.POINTER(EncAffineParams), C.c_void_p]),
     'ia_enc_global_pool': (C.c_int, [C.POINTER(View), c_f32p, c_f32p, C.c_int32, C.c_int32, C.c_int32, c_f32p, C.c_void_p]),

@@ -70,6 +70,64 @@ __global__ void bn_fold_kernel(const double* __restrict__ sums, double count, co
     shift[c] = (beta ? beta[c] : 0.f) - mean * sc;
 }
 
+// ---- train-mode BatchNorm in ONE launch: per-channel sums (as chan_stats_kernel) + the fold of the last CTA to arrive --------------
+// `sums` [2C] float64 and `counter` are zero on entry and left zero; the last CTA (threadfence + ticket) computes mean / biased
+// variance, updates the running statistics as torch does and writes (scale, shift).
+__global__ void __launch_bounds__(256) bn_stats_fold_kernel(ia_view v, int B, int H, int W, int64_t pix_per_block, double* __restrict__ sums,
+                                                            int* __restrict__ counter, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, float* __restrict__ rmean, float* __restrict__ rvar,
+                                                            float momentum, float eps, float* __restrict__ scale, float* __restrict__ shift) {
+    const int C = v.C;
+    const int c = blockIdx.y * 32 + (threadIdx.x & 31);
+    const int lane_p = threadIdx.x >> 5;
+    const int64_t npix = (int64_t)B * H * W;
+    const int64_t p0 = (int64_t)blockIdx.x * pix_per_block;
+    const int64_t p1 = p0 + pix_per_block < npix ? p0 + pix_per_block : npix;
+    double s = 0.0, q = 0.0;
+    if (c < C) {
+        for (int64_t p = p0 + lane_p; p < p1; p += 8) {
+            const int x = (int)(p % W); const int64_t t = p / W;
+            const int y = (int)(t % H); const int b = (int)(t / H);
+            const double a = (double)view_at(v, b, y, x, c);
+            s += a; q += a * a;
+        }
+    }
+    __shared__ double sh[2][8][32];
+    __shared__ int s_last;
+    sh[0][lane_p][threadIdx.x & 31] = s;
+    sh[1][lane_p][threadIdx.x & 31] = q;
+    __syncthreads();
+    if (lane_p == 0 && c < C) {
+        for (int k = 1; k < 8; ++k) { s += sh[0][k][threadIdx.x & 31]; q += sh[1][k][threadIdx.x & 31]; }
+        atomicAdd(&sums[c], s);
+        atomicAdd(&sums[C + c], q);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(counter, 1) == (int)(gridDim.x * gridDim.y) - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const double count = (double)npix;
+    for (int i = threadIdx.x; i < C; i += 256) {
+        const double m = __ldcg(&sums[i]) / count;
+        double vv = __ldcg(&sums[C + i]) / count - m * m;
+        if (vv < 0.0) vv = 0.0;
+        sums[i] = 0.0; sums[C + i] = 0.0;
+        const float mean = (float)m, var = (float)vv;
+        if (rmean) rmean[i] = (1.f - momentum) * rmean[i] + momentum * mean;
+        if (rvar) {
+            const double unb = count > 1.0 ? vv * count / (count - 1.0) : vv;
+            rvar[i] = (1.f - momentum) * rvar[i] + momentum * (float)unb;
+        }
+        const float inv = 1.f / sqrtf(var + eps);
+        const float sc = (gamma ? gamma[i] : 1.f) * inv;
+        scale[i] = sc;
+        shift[i] = (beta ? beta[i] : 0.f) - mean * sc;
+    }
+    if (threadIdx.x == 0) *counter = 0;
+}
+
 // ---- operand builder -------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) enc_prep_kernel(ia_enc_prep_params p, int Ctot) {
     const int groups = (p.hi ? p.C_pad : Ctot + 3) >> 2;     // 4 channels per thread
@@ -373,6 +431,24 @@ extern "C" int ia_enc_bn_fold(const double* sums, int64_t count, const float* ga
     bn_fold_kernel<<<(unsigned)cdiv(C, 128), 128, 0, as_stream(stream)>>>(sums, (double)count, gamma, beta, running_mean, running_var,
                                                                           training, momentum, eps, C, scale, shift);
     IA_LAUNCH_CHECK("ia_enc_bn_fold");
+    return 0;
+}
+
+extern "C" int ia_enc_bn_stats_fold(const ia_view* x, int32_t B, int32_t H, int32_t W, double* sums, int32_t* counter, const float* gamma,
+                                    const float* beta, float* running_mean, float* running_var, float momentum, float eps, float* scale,
+                                    float* shift, void* stream) {
+    if (int rc = check_view(x, "ia_enc_bn_stats_fold")) return rc;
+    IA_CHECK(sums && counter && scale && shift && B > 0 && H > 0 && W > 0, "ia_enc_bn_stats_fold: bad arguments");
+    const int64_t npix = (int64_t)B * H * W;
+    const int cblocks = (int)cdiv(x->C, 32);
+    int64_t want_blocks = cdiv(148 * 4, cblocks);
+    int64_t ppb = cdiv(npix, want_blocks);
+    if (ppb < 64) ppb = 64;
+    dim3 grid((unsigned)cdiv(npix, ppb), (unsigned)cblocks);
+    ia::prof_begin("ia_enc_bn_stats_fold", as_stream(stream));
+    bn_stats_fold_kernel<<<grid, 256, 0, as_stream(stream)>>>(*x, B, H, W, ppb, sums, counter, gamma, beta, running_mean, running_var, momentum, eps,
+                                                             scale, shift);
+    IA_LAUNCH_CHECK("ia_enc_bn_stats_fold");
     return 0;
 }
 

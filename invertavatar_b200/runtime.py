@@ -1200,6 +1200,9 @@ def enc_chan_stats(src):
     return sums, B * H * W
 
 
+_BN_SCRATCH = {}
+
+
 class _FoldCache(_EngineCache):
     """Folded eval-mode BatchNorm (scale, shift) hung on the module; dropped on deepcopy / pickle like every engine cache."""
 
@@ -1223,6 +1226,26 @@ def enc_bn_fold(bn, srcs):
     scale = torch.empty(Cn, dtype=torch.float32, device=dev)
     shift = torch.empty_like(scale)
     sums, count = None, 0
+    if training and len(srcs) == 1 and enc_epilogue_fusion() and Cn <= 2048:
+        # one launch: channel sums + the fold by the last CTA to arrive (persistent zeroed scratch per device / stream / capture scope)
+        v, (B, H, W, Cc) = _as_view(srcs[0])
+        assert Cc == Cn, (Cc, Cn)
+        st = _enter(v._keep)
+        key = _scratch_key(dev, st)
+        buf = _BN_SCRATCH.get(key)
+        if buf is None:
+            buf = (torch.zeros(4096, dtype=torch.float64, device=dev), torch.zeros(1, dtype=torch.int32, device=dev))
+            _BN_SCRATCH[key] = buf
+        track = bn.track_running_stats and bn.running_mean is not None
+        momentum = 0.1 if bn.momentum is None else float(bn.momentum)
+        if track and bn.momentum is None:
+            momentum = 1.0 / float(int(bn.num_batches_tracked) + 1)
+        _C.check(_C.lib().ia_enc_bn_stats_fold(C.byref(v), B, H, W, _p(buf[0]), _p(buf[1]), _p(bn.weight), _p(bn.bias),
+                                               _p(bn.running_mean) if track else None, _p(bn.running_var) if track else None, momentum,
+                                               float(bn.eps), _p(scale), _p(shift), st), 'ia_enc_bn_stats_fold')
+        if track and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked += 1
+        return scale, shift
     if training:
         if len(srcs) == 1:
             sums, count = enc_chan_stats(srcs[0])
