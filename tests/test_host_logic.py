@@ -135,3 +135,27 @@ def test_checkpoint_hash_travels_to_the_pack_cache_key(tmp_path, monkeypatch):
     monkeypatch.setenv('IA_CONV_PRECISION', 'bf16x3')
     c = rt.pack_cache_path(digest + ':G_ema', cache_dir=str(tmp_path))
     assert a != b and a != c and a.startswith(str(tmp_path)) and a.endswith('.pt')
+
+
+def test_capture_scope_keys_engine_state_per_graph():
+    """Persistent engine state (split-K scratch, SE / BatchNorm sums, StylePlan buffers) is keyed by the capture scope that is active
+    when it is requested: scope 0 outside graphs.GraphedCall / GraphedSynthesis, a fresh scope per captured graph, restored on exit
+    (nested scopes included) -- so two graphs never share state, and eager calls never share a graph's."""
+    import torch
+    from invertavatar_b200 import runtime as rt
+    dev = torch.device('cuda', 0)
+    k0 = rt._scratch_key(dev, 5)
+    assert k0 == (0, 5, 0)
+    with rt.capture_scope() as s1:
+        k1 = rt._scratch_key(dev, 5)
+        with rt.capture_scope() as s2:
+            k2 = rt._scratch_key(dev, 5)
+        assert rt._scratch_key(dev, 5) == k1
+    assert rt._scratch_key(dev, 5) == k0
+    assert s1 != s2 and len({k0, k1, k2}) == 3 and k1[2] == s1 and k2[2] == s2
+    with rt.capture_scope() as s3:
+        assert s3 not in (s1, s2)
+    plan = rt.StylePlan.__new__(rt.StylePlan)
+    assert plan._key(8) == (8, 0)
+    with rt.capture_scope() as s4:
+        assert plan._key(8) == (8, s4)
