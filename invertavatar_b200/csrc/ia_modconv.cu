@@ -476,16 +476,8 @@ extern "C" int ia_fir_epilogue(const ia_fir_params* p, void* stream) {
 // ------------------------------------------------------------------------------------------------
 // ToRGB tail: img_out = upsample2d(img_prev) + clamp(raw + bias)
 // ------------------------------------------------------------------------------------------------
-__global__ void torgb_finish_kernel(ia_torgb_params p) {
-    int64_t total = (int64_t)p.B * p.H * p.W * p.C;
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    int c, x, y, b;
-    if (p.out_nchw) {
-        x = i % p.W; int64_t t = i / p.W; y = t % p.H; t /= p.H; c = t % p.C; b = (int)(t / p.C);
-    } else {
-        c = i % p.C; int64_t t = i / p.C; x = t % p.W; t /= p.W; y = t % p.H; b = (int)(t / p.H);
-    }
+// one output element: the arithmetic (and its order) every ToRGB-tail kernel below shares
+__device__ __forceinline__ float torgb_value(const ia_torgb_params& p, int b, int c, int y, int x) {
     float v = p.raw[(((int64_t)b * p.H + y) * p.W + x) * p.raw_ld + c];
     if (p.bias) v += p.bias[(p.groups > 1 ? b / p.imgs_per_group : 0) * p.C + c];
     if (p.clamp >= 0.f) v = fminf(fmaxf(v, -p.clamp), p.clamp);
@@ -510,6 +502,20 @@ __global__ void torgb_finish_kernel(ia_torgb_params p) {
         }
         v = up + v;
     }
+    return v;
+}
+
+__global__ void torgb_finish_kernel(ia_torgb_params p) {
+    int64_t total = (int64_t)p.B * p.H * p.W * p.C;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int c, x, y, b;
+    if (p.out_nchw) {
+        x = i % p.W; int64_t t = i / p.W; y = t % p.H; t /= p.H; c = t % p.C; b = (int)(t / p.C);
+    } else {
+        c = i % p.C; int64_t t = i / p.C; x = t % p.W; t /= p.W; y = t % p.H; b = (int)(t / p.H);
+    }
+    const float v = torgb_value(p, b, c, y, x);
     if (p.out_nchw) {
         const int64_t o = (((int64_t)b * p.C + c) * p.H + y) * p.W + x;
         p.img_out[o] = v;
@@ -522,6 +528,30 @@ __global__ void torgb_finish_kernel(ia_torgb_params p) {
         }
     } else {
         p.img_out[(((int64_t)b * p.H + y) * p.W + x) * p.C + c] = v;
+    }
+}
+
+// Planar output, 4 adjacent pixels of every channel per thread (W % 4 == 0, 16-byte aligned outputs): the raw NHWC pixels of
+// a warp are one contiguous run, every plane row is written as 16-byte stores, and the fused gather issues ONE
+// multimem.st.v4.f32 (or one 16-byte store per peer) per 4 values instead of four scalar ones.  Values are torgb_value's.
+__global__ void __launch_bounds__(256) torgb_finish_nchw4_kernel(ia_torgb_params p) {
+    const int w4 = p.W >> 2;
+    const unsigned total = (unsigned)p.B * p.H * w4;
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int x = (int)(i % w4) * 4;
+    unsigned t = i / w4;
+    const int y = (int)(t % p.H); const int b = (int)(t / p.H);
+    for (int c = 0; c < p.C; ++c) {
+        const float4 v = make_float4(torgb_value(p, b, c, y, x), torgb_value(p, b, c, y, x + 1), torgb_value(p, b, c, y, x + 2), torgb_value(p, b, c, y, x + 3));
+        const int64_t o = (((int64_t)b * p.C + c) * p.H + y) * p.W + x;
+        *reinterpret_cast<float4*>(p.img_out + o) = v;
+        if (p.mc_out) {
+            asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+                         ::"l"(p.mc_out + p.peer_offset + o), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+        } else {
+            for (int k = 0; k < p.n_peers; ++k) *reinterpret_cast<float4*>(p.peer_out[k] + p.peer_offset + o) = v;
+        }
     }
 }
 
@@ -564,6 +594,17 @@ __global__ void __launch_bounds__(256) torgb_finish_vec4_kernel(ia_torgb_params 
     *reinterpret_cast<float4*>(p.img_out + pix * p.C + c) = v;
 }
 
+// the planar 4-pixel kernel needs whole 16-byte groups in every buffer it stores to (IA_TORGB_NCHW4=0: element-per-thread kernel)
+static bool torgb_nchw4_ok(const ia_torgb_params* p) {
+    { const char* e = getenv("IA_TORGB_NCHW4"); if (e && atoi(e) == 0) return false; }
+    if ((p->W & 3) != 0 || (int64_t)p->B * p->H * (p->W >> 2) >= (int64_t)0x7fffffff) return false;
+    if ((reinterpret_cast<uintptr_t>(p->img_out) & 15) != 0 || (p->peer_offset & 3) != 0) return false;
+    if (p->mc_out && (reinterpret_cast<uintptr_t>(p->mc_out) & 15) != 0) return false;
+    for (int k = 0; k < p->n_peers; ++k)
+        if ((reinterpret_cast<uintptr_t>(p->peer_out[k]) & 15) != 0) return false;
+    return true;
+}
+
 extern "C" int ia_torgb_finish(const ia_torgb_params* p, void* stream) {
     IA_CHECK(p && p->raw && p->img_out, "ia_torgb_finish: null tensor");
     IA_CHECK(p->img_prev == nullptr || ((p->H & 1) == 0 && (p->W & 1) == 0), "ia_torgb_finish: odd size with skip image");
@@ -576,6 +617,8 @@ extern "C" int ia_torgb_finish(const ia_torgb_params* p, void* stream) {
         (reinterpret_cast<uintptr_t>(p->img_out) & 15) == 0 && (p->bias == nullptr || (reinterpret_cast<uintptr_t>(p->bias) & 15) == 0) &&
         (p->img_prev == nullptr || (reinterpret_cast<uintptr_t>(p->img_prev) & 15) == 0) && (reinterpret_cast<uintptr_t>(p->raw) & 15) == 0)
         torgb_finish_vec4_kernel<<<(unsigned)cdiv(total / 4, 256), 256, 0, as_stream(stream)>>>(*p);
+    else if (p->out_nchw && torgb_nchw4_ok(p))
+        torgb_finish_nchw4_kernel<<<(unsigned)cdiv((int64_t)p->B * p->H * (p->W >> 2), 256), 256, 0, as_stream(stream)>>>(*p);
     else
         torgb_finish_kernel<<<(unsigned)cdiv(total, 256), 256, 0, as_stream(stream)>>>(*p);
     IA_LAUNCH_CHECK("ia_torgb_finish");

@@ -252,3 +252,24 @@ def test_graphed_call_matches_eager():
             got = gc(image=imgs[i:i + 1]).clone()
             want = net.encode(imgs[i:i + 1])
             assert float((got - want).abs().max()) <= 1e-4 * max(1.0, float(want.abs().max())), i
+
+
+@pytest.mark.parametrize('shape', [(2, 3, 16, 16), (3, 3, 64, 128), (1, 32, 8, 12), (2, 3, 6, 6)])
+@pytest.mark.parametrize('with_prev', [True, False])
+def test_torgb_planar_vec4_matches_element_kernel(monkeypatch, shape, with_prev):
+    """The planar ToRGB tail that owns 4 adjacent pixels per thread (torgb_finish_nchw4_kernel: 16-byte plane stores, one
+    multimem.st.v4 per 4 values under the fused gather) gives the element-per-thread kernel's values bit for bit; widths that
+    are not a multiple of 4 take the element kernel."""
+    from invertavatar_b200 import runtime as rt
+    B, Cc, H, W = shape
+    g = torch.Generator().manual_seed(7)
+    raw = (torch.randn(B, H, W, Cc, generator=g) * 200).cuda()        # some values beyond the +-256 clamp
+    bias = torch.randn(Cc, generator=g).cuda()
+    prev = torch.randn(B, H // 2, W // 2, Cc, generator=g).cuda() if with_prev else None
+    monkeypatch.setenv('IA_TORGB_NCHW4', '0')
+    want = rt.torgb_finish(raw, bias, 256.0, prev, out_nchw=True).clone()
+    monkeypatch.setenv('IA_TORGB_NCHW4', '1')
+    got = rt.torgb_finish(raw, bias, 256.0, prev, out_nchw=True)
+    assert got.shape == want.shape and torch.equal(got, want)
+    nhwc = rt.torgb_finish(raw, bias, 256.0, prev, out_nchw=False)
+    assert torch.equal(rt.from_nhwc(nhwc) if hasattr(rt, 'from_nhwc') else nhwc.permute(0, 3, 1, 2), want)
