@@ -426,6 +426,151 @@ __global__ void __launch_bounds__(256, 2) fir_epilogue_x2_kernel(ia_fir_params p
     }
 }
 
+// The two-column kernel restructured around what its ncu capture showed (profiles/r2_fir_full_v24.txt: 39 % of the stall
+// samples on the long scoreboard -- not on the consumers of a row but on the register MOVES that rotated the prefetched rows
+// (r <- ra <- rb), which wait for the newest load and so shorten the prefetch distance to one row; issue slots 60 % busy at
+// 316 instructions per thread and row, 42 of them uniform compares / branches on launch-constant flags and 16 register
+// zeroings).  Here the three row buffers form a ring that is addressed statically (three copies of the loop body, no moves),
+// rows are zero-filled only when they really lie outside the image, the demodulation is always an FMA (coefficient 1 when
+// absent: fma(a, 1, n) == a + n bit for bit) and the emission layout is a template parameter for the two layouts the hot path
+// uses: EM = 1 -> operand 1 only, single-pass fp16 (backbone up-layers); EM = 2 -> operand 1 only, bf16 hi/lo (super-resolution
+// up-layers); EM = 0 -> whatever ia_emit says.  Same arithmetic in the same order as fir_epilogue_kernel: bit-identical
+// (tests/test_gpu_regress.py); IA_FIR_RING=0 selects the previous kernel.
+template <int ACT, int EM>
+__global__ void __launch_bounds__(256, 2) fir_epilogue_x2r_kernel(ia_fir_params p, int cg, int xt, int cchunks) {
+    const int c4 = threadIdx.x % cg;
+    const int xl = threadIdx.x / cg;
+    const int ox = (blockIdx.x * xt + xl) * 2;            // even output column; this thread owns ox and ox + 1 (OW is even)
+    const int oy0 = blockIdx.y * FIR_YT;
+    const int b = blockIdx.z / cchunks;
+    const int c0 = ((blockIdx.z % cchunks) * cg + c4) * 4;
+    if (ox >= p.OW || c0 >= p.C) return;
+    float fy[4], fx[4];
+    {
+        float tot = 0.f, rs[4] = {0.f, 0.f, 0.f, 0.f}, cs[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { const float f = p.fir[i * 4 + j]; rs[i] += f; cs[j] += f; tot += f; }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) { fy[t] = rs[3 - t]; fx[t] = cs[3 - t] / tot; }
+    }
+    const int oy1 = min(oy0 + FIR_YT, p.OH);
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 acc[2][3];                                     // [column][output rows ry-2, ry-1, ry]
+#pragma unroll
+    for (int j = 0; j < 2; ++j) { acc[j][0] = z4; acc[j][1] = z4; acc[j][2] = z4; }
+    const int grp = p.groups > 1 ? b / p.imgs_per_group : 0;
+    const bool has32 = EM == 0 && p.emit.out32 != nullptr;
+    const bool has1 = EM != 0 || p.emit.hi1 != nullptr;
+    const bool has2 = EM == 0 && p.emit.hi2 != nullptr;
+    const int fmt1 = EM == 1 ? IA_OPFMT_F16X1 : (EM == 2 ? IA_OPFMT_BF16X3 : p.emit.fmt1);
+    float dc[4], bs[4], s1[4], s2[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        dc[k] = p.dcoef ? p.dcoef[(int64_t)b * p.C + c0 + k] : 1.f;
+        bs[k] = p.bias ? p.bias[(int64_t)grp * p.C + c0 + k] : 0.f;
+        s1[k] = (has1 && p.emit.s1) ? p.emit.s1[(int64_t)b * p.C + c0 + k] : 1.f;
+        s2[k] = (has2 && p.emit.s2) ? p.emit.s2[(int64_t)b * p.C + c0 + k] : 1.f;
+    }
+    const float nstr = p.noise ? p.noise_strength[grp] : 0.f;
+    const float* nptr = p.noise ? p.noise + (int64_t)grp * p.noise_gstride + (int64_t)b * p.noise_bstride + (int64_t)oy0 * p.OW + ox : nullptr;
+    const int64_t row_f = (int64_t)p.RW * p.C;
+    const float* rq = p.raw + (int64_t)b * p.RH * row_f + (int64_t)(oy0 - 1) * row_f + (int64_t)(ox - 1) * p.C + c0;
+    const bool v0 = ox - 1 >= 0, v4 = ox + 3 < p.RW;      // raw columns ox, ox+1, ox+2 always exist (ox + 1 < OW = RW - 1)
+    const int C = p.C, RH = p.RH, OW = p.OW;
+    const int64_t opix = ((int64_t)b * p.OH + oy0) * p.OW + ox;
+    const uint32_t o32ld = (uint32_t)p.emit.out32_ld, c1p = (uint32_t)p.emit.c1_pad, c2p = (uint32_t)p.emit.c2_pad;
+    uint32_t o32 = has32 ? (uint32_t)(opix * o32ld + c0) : 0u, o1 = has1 ? (uint32_t)(opix * c1p + c0) : 0u, o2 = has2 ? (uint32_t)(opix * c2p + c0) : 0u;
+    const uint32_t o32row = (uint32_t)OW * o32ld, r1row = (uint32_t)OW * c1p, r2row = (uint32_t)OW * c2p;
+    const bool vec32 = (o32ld & 3) == 0;
+    const float gain = p.gain, alpha = p.alpha, clampv = p.clamp;
+    const bool clamped = clampv >= 0.f;
+    float nq0 = 0.f, nq1 = 0.f;                           // noise of the next output row to be emitted
+    int nrows_left = oy1 - oy0;                           // output rows whose noise has not been requested yet
+    if (nptr) { nq0 = nptr[0]; nq1 = nptr[1]; nptr += OW; --nrows_left; }
+    auto load_row = [&](float4 (&r)[5], int ry, const float* q) {
+        if (ry >= 0 && ry < RH) {
+            r[0] = z4; r[4] = z4;
+            if (v0) r[0] = __ldg(reinterpret_cast<const float4*>(q));
+            r[1] = __ldg(reinterpret_cast<const float4*>(q + C));
+            r[2] = __ldg(reinterpret_cast<const float4*>(q + 2 * C));
+            r[3] = __ldg(reinterpret_cast<const float4*>(q + 3 * C));
+            if (v4) r[4] = __ldg(reinterpret_cast<const float4*>(q + 4 * C));
+        } else {
+#pragma unroll
+            for (int k = 0; k < 5; ++k) r[k] = z4;
+        }
+    };
+    // raw row ry: horizontal taps for both columns, vertical accumulation, emission of output row ry - 2 when it completes
+    auto consume = [&](const float4 (&r)[5], int ry) {
+        const bool emit_row = ry - 2 >= oy0;              // output row ry-2 (< oy1 by the loop bound) completes with this raw row
+        float nz0 = 0.f, nz1 = 0.f;
+        if (emit_row && nptr) {
+            nz0 = nq0 * nstr; nz1 = nq1 * nstr;
+            if (nrows_left > 0) { nq0 = nptr[0]; nq1 = nptr[1]; nptr += OW; --nrows_left; }
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            float4 h;
+            h.x = fmaf(fx[3], r[j + 3].x, fmaf(fx[2], r[j + 2].x, fmaf(fx[1], r[j + 1].x, fx[0] * r[j].x)));
+            h.y = fmaf(fx[3], r[j + 3].y, fmaf(fx[2], r[j + 2].y, fmaf(fx[1], r[j + 1].y, fx[0] * r[j].y)));
+            h.z = fmaf(fx[3], r[j + 3].z, fmaf(fx[2], r[j + 2].z, fmaf(fx[1], r[j + 1].z, fx[0] * r[j].z)));
+            h.w = fmaf(fx[3], r[j + 3].w, fmaf(fx[2], r[j + 2].w, fmaf(fx[1], r[j + 1].w, fx[0] * r[j].w)));
+            float4& a0 = acc[j][0]; float4& a1 = acc[j][1]; float4& a2 = acc[j][2];
+            a0.x = fmaf(fy[3], h.x, a0.x); a0.y = fmaf(fy[3], h.y, a0.y); a0.z = fmaf(fy[3], h.z, a0.z); a0.w = fmaf(fy[3], h.w, a0.w);
+            a1.x = fmaf(fy[2], h.x, a1.x); a1.y = fmaf(fy[2], h.y, a1.y); a1.z = fmaf(fy[2], h.z, a1.z); a1.w = fmaf(fy[2], h.w, a1.w);
+            a2.x = fmaf(fy[1], h.x, a2.x); a2.y = fmaf(fy[1], h.y, a2.y); a2.z = fmaf(fy[1], h.z, a2.z); a2.w = fmaf(fy[1], h.w, a2.w);
+            const float4 a3 = make_float4(fy[0] * h.x, fy[0] * h.y, fy[0] * h.z, fy[0] * h.w);
+            if (emit_row) {
+                const float nz = j ? nz1 : nz0;
+                const float a4[4] = {a0.x, a0.y, a0.z, a0.w};
+                float v[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float t = fmaf(a4[k], dc[k], nz) + bs[k];                    // fma(x, dcoef, noise), networks_stylegan2_new.py:74
+                    if (ACT == IA_ACT_LRELU) t = (t > 0.f ? t : t * alpha) * gain;
+                    else if (ACT == IA_ACT_LINEAR) t = t * gain;
+                    else t = apply_act(t, p.act, alpha) * gain;
+                    v[k] = t;
+                }
+                if (clamped) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) v[k] = fminf(fmaxf(v[k], -clampv), clampv);
+                }
+                if (has32) {
+                    float* o = p.emit.out32 + (o32 + j * o32ld);
+                    if (vec32) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+                    else { o[0] = v[0]; o[1] = v[1]; o[2] = v[2]; o[3] = v[3]; }
+                }
+                if (has1)
+                    store_operand4(fmt1, p.emit.hi1 + (o1 + j * c1p), p.emit.lo1 + (o1 + j * c1p), v[0] * s1[0], v[1] * s1[1], v[2] * s1[2], v[3] * s1[3]);
+                if (has2)
+                    store_operand4(p.emit.fmt2, p.emit.hi2 + (o2 + j * c2p), p.emit.lo2 + (o2 + j * c2p), v[0] * s2[0], v[1] * s2[1], v[2] * s2[2], v[3] * s2[3]);
+            }
+            a0 = a1; a1 = a2; a2 = a3;
+        }
+        if (emit_row) { o32 += o32row; o1 += r1row; o2 += r2row; }
+    };
+    float4 ra[5], rb[5], rc[5];                           // ring of raw rows: one being consumed, two in flight
+    int ry = oy0 - 1;
+    const int last = oy1 + 1;
+    load_row(ra, ry, rq);
+    load_row(rb, ry + 1, rq + row_f);
+    rq += 2 * row_f;                                      // row ry + 2
+#define IA_FIR_STEP(CUR, NXT)                                   \
+    if (ry + 2 <= last) load_row(NXT, ry + 2, rq);              \
+    rq += row_f;                                                \
+    consume(CUR, ry);                                           \
+    if (++ry > last) break;
+    for (;;) {
+        IA_FIR_STEP(ra, rc)
+        IA_FIR_STEP(rb, ra)
+        IA_FIR_STEP(rc, rb)
+    }
+#undef IA_FIR_STEP
+}
+
 namespace ia {
 bool fir_tma_eligible(const ia_fir_params* p);      // ia_fir_tma.cu: TMA-fed streaming variant
 int fir_tma_launch(const ia_fir_params* p, void* stream);
@@ -453,7 +598,22 @@ extern "C" int ia_fir_epilogue(const ia_fir_params* p, void* stream) {
         dim3 grid((unsigned)cdiv(p->OW / 2, xt), (unsigned)cdiv(p->OH, FIR_YT), (unsigned)(p->B * cchunks));
         bool npf = true;       // noise of the next output row loaded one emission ahead (bit-identical; IA_FIR_NOISE_PREFETCH=0: in the consuming iteration)
         { const char* e = getenv("IA_FIR_NOISE_PREFETCH"); if (e && atoi(e) == 0) npf = false; }
-        if (npf) {
+        bool ring = npf;       // statically addressed row ring + templated emission layout (IA_FIR_RING=0: the previous two-column kernel)
+        { const char* e = getenv("IA_FIR_RING"); if (e && atoi(e) == 0) ring = false; }
+        if (ring) {
+            const bool only1 = p->emit.hi1 && !p->emit.hi2 && !p->emit.out32;
+            const int em = only1 ? (p->emit.fmt1 == IA_OPFMT_F16X1 ? 1 : 2) : 0;
+#define IA_FIR_RING_LAUNCH(A)                                                                                              \
+            do {                                                                                                           \
+                if (em == 1) fir_epilogue_x2r_kernel<A, 1><<<grid, 256, 0, as_stream(stream)>>>(*p, cg, xt, cchunks);       \
+                else if (em == 2) fir_epilogue_x2r_kernel<A, 2><<<grid, 256, 0, as_stream(stream)>>>(*p, cg, xt, cchunks);  \
+                else fir_epilogue_x2r_kernel<A, 0><<<grid, 256, 0, as_stream(stream)>>>(*p, cg, xt, cchunks);               \
+            } while (0)
+            if (p->act == IA_ACT_LRELU) IA_FIR_RING_LAUNCH(IA_ACT_LRELU);
+            else if (p->act == IA_ACT_LINEAR) IA_FIR_RING_LAUNCH(IA_ACT_LINEAR);
+            else IA_FIR_RING_LAUNCH(-1);
+#undef IA_FIR_RING_LAUNCH
+        } else if (npf) {
             if (p->act == IA_ACT_LRELU) fir_epilogue_x2_kernel<IA_ACT_LRELU, true><<<grid, 256, 0, as_stream(stream)>>>(*p, cg, xt, cchunks);
             else if (p->act == IA_ACT_LINEAR) fir_epilogue_x2_kernel<IA_ACT_LINEAR, true><<<grid, 256, 0, as_stream(stream)>>>(*p, cg, xt, cchunks);
             else fir_epilogue_x2_kernel<-1, true><<<grid, 256, 0, as_stream(stream)>>>(*p, cg, xt, cchunks);

@@ -113,12 +113,14 @@ def test_fir_epilogue_variants_agree(monkeypatch, B, OH, C, use32, use1, use2):
     noise, strength = torch.randn(OH, OH, generator=g).cuda(), torch.tensor(0.3).cuda()
     s1, s2 = torch.randn(B, C, generator=g).cuda(), torch.randn(B, C, generator=g).cuda()
     outs = {}
-    variants = [('tma', {'IA_FIR_TMA': '1'}), ('x2', {'IA_FIR_TMA': '0', 'IA_FIR_X2': '1'}), ('x1', {'IA_FIR_TMA': '0', 'IA_FIR_X2': '0'})]
+    variants = [('tma', {'IA_FIR_TMA': '1'}), ('x2', {'IA_FIR_TMA': '0', 'IA_FIR_X2': '1'}), ('x1', {'IA_FIR_TMA': '0', 'IA_FIR_X2': '0'}),
+                ('x2_ring', {'IA_FIR_TMA': '0', 'IA_FIR_X2': '1', 'IA_FIR_NOISE_PREFETCH': '1', 'IA_FIR_RING': '1'})]
     if os.environ.get('IA_TEST_OPTIN'):      # opt-in code paths that have not been through the suite on hardware yet
         variants += [('x2_npf', {'IA_FIR_TMA': '0', 'IA_FIR_X2': '1', 'IA_FIR_NOISE_PREFETCH': '1'}),
                      ('tma_npf', {'IA_FIR_TMA': '1', 'IA_FIR_NOISE_PREFETCH': '1'})]
     for name, env in variants:
         monkeypatch.setenv('IA_FIR_NOISE_PREFETCH', '0')
+        monkeypatch.setenv('IA_FIR_RING', '0')
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         out = torch.zeros(B, OH, OH, C, device='cuda') if use32 else None
@@ -273,3 +275,32 @@ def test_torgb_planar_vec4_matches_element_kernel(monkeypatch, shape, with_prev)
     assert got.shape == want.shape and torch.equal(got, want)
     nhwc = rt.torgb_finish(raw, bias, 256.0, prev, out_nchw=False)
     assert torch.equal(rt.from_nhwc(nhwc) if hasattr(rt, 'from_nhwc') else nhwc.permute(0, 3, 1, 2), want)
+
+
+@pytest.mark.parametrize('fmt', ['f16', 'bf16x3', 'both32'])
+@pytest.mark.parametrize('B,OH,C,act,noise,demod,clamp', [(2, 128, 64, 'lrelu', True, True, None), (1, 64, 128, 'lrelu', False, True, 256.0),
+                                                          (3, 34, 32, 'linear', True, False, None), (1, 70, 256, 'relu', False, False, 1.5)])
+def test_fir_epilogue_ring_kernel_bit_identical(monkeypatch, fmt, B, OH, C, act, noise, demod, clamp):
+    """The ring kernel (fir_epilogue_x2r_kernel: statically addressed row ring, emission layout as a template parameter) against
+    the one-column kernel on the layouts it specialises -- operand 1 alone in single-pass fp16 (backbone up-layers) or bf16 hi/lo
+    (super-resolution up-layers) -- and on the generic layout, with and without noise / demodulation / clamp, partial strips
+    (OH not a multiple of 32) included: every emitted tensor bit for bit."""
+    from invertavatar_b200 import runtime as rt
+    g = torch.Generator().manual_seed(B * 1000 + OH + C)
+    raw = torch.randn(B, OH + 1, OH + 1, C, generator=g).cuda()
+    dcoef = (torch.rand(B, C, generator=g).cuda() + 0.5) if demod else None
+    bias = torch.randn(C, generator=g).cuda()
+    nz, strength = (torch.randn(OH, OH, generator=g).cuda(), torch.tensor(0.3).cuda()) if noise else (None, None)
+    s1 = torch.randn(B, C, generator=g).cuda()
+    outs = {}
+    for name, env in [('x1', {'IA_FIR_X2': '0', 'IA_FIR_RING': '0'}), ('ring', {'IA_FIR_X2': '1', 'IA_FIR_RING': '1', 'IA_FIR_NOISE_PREFETCH': '1'})]:
+        monkeypatch.setenv('IA_FIR_TMA', '0')
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        out = torch.zeros(B, OH, OH, C, device='cuda') if fmt == 'both32' else None
+        e1 = rt.new_split(B, OH, OH, max(64, C), 'cuda', C=C, fmt=rt.FMT_F16X1 if fmt == 'f16' else rt.FMT_BF16X3)
+        rt.fir_epilogue(raw, rt.fir4x4_gain4('cuda'), out, dcoef, nz, strength, bias, act, 1.3, clamp, e1=(e1, s1))
+        torch.cuda.synchronize()
+        outs[name] = [t.clone() for t in ([out] if out is not None else []) + [e1.hi] + ([e1.lo] if e1.lo is not None else [])]
+    for a, b in zip(outs['x1'], outs['ring']):
+        assert torch.equal(a, b)
