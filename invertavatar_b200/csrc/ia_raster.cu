@@ -380,6 +380,120 @@ __global__ void __launch_bounds__(256) raster_hpass_kernel(ia_raster_level_param
     }
 }
 
+// Cell-merged horizontal pass (the 32 lanes of a warp share one pixel group, lpp == 32).  ncu of the kernel above
+// (profiles/r2_misc_full_v24.txt): L1 data path 60-75 % busy -- every 256^2 sample gathers its four texels although, on a 32^2 ...
+// 128^2 texture, 8 ... 2 consecutive samples of a row fall into the SAME texel cell.  The pass is linear in the texels:
+//     out_j = sum_x a_j(x) * sum_corner w_corner(x) * T[cell(x)][corner]  =  sum_cells sum_corner T[cell][corner] * (sum_{x in cell} a_j(x) * w_corner(x)),
+// so while consecutive samples stay in one cell only their 4 x NX scalar weight products are accumulated, and the cell's four
+// texels are gathered ONCE, when the cell changes (warp-uniform decision: the cell of a sample is broadcast to all lanes).  A
+// different summation order than the per-sample kernel (fp32 reassociation, ~1e-7 relative; IA_RASTER_MERGE=0 selects the
+// per-sample kernel, which is the bit-exact restatement of grid_sample followed by the resize).
+template <int KC, int NX>
+__global__ void __launch_bounds__(256) raster_hpass_merge_kernel(ia_raster_level_params p) {
+    const int rg = (p.r + NX - 1) / NX;
+    const int64_t total = (int64_t)p.B * p.UH * rg * 32;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int lane = (int)(i & 31);
+    int64_t t = i >> 5;
+    const int ox0 = (int)(t % rg) * NX; t /= rg;
+    const int y = (int)(t % p.UH); const int b = (int)(t / p.UH);
+    int xs[NX], xn[NX];
+    int x_lo = 1 << 30, x_hi = -(1 << 30);
+#pragma unroll
+    for (int j = 0; j < NX; ++j) {
+        const bool on = ox0 + j < p.r;
+        xs[j] = on ? p.ux_start[ox0 + j] : 0;
+        xn[j] = on ? p.ux_count[ox0 + j] : 0;
+        if (on) { x_lo = min(x_lo, xs[j]); x_hi = max(x_hi, xs[j] + xn[j]); }
+    }
+    const float* uvrow = p.uv + (int64_t)(b * p.UH + y) * p.UW * p.uv_ld;
+    const float* tbase = p.tex + (int64_t)b * p.Ht * p.Wt * p.C + lane * 4;
+    float4 acc[NX][KC];
+    float cw[NX][4];
+#pragma unroll
+    for (int j = 0; j < NX; ++j) {
+#pragma unroll
+        for (int k = 0; k < KC; ++k) acc[j][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        cw[j][0] = cw[j][1] = cw[j][2] = cw[j][3] = 0.f;
+    }
+    const int Wi = p.Wt, Hi = p.Ht;
+    constexpr int kstride = 32 * 4;
+    int c00 = -1, c01 = -1, c10 = -1, c11 = -1;           // texel offsets of the open cell (-1: none yet)
+    auto flush = [&]() {
+        float4 va[KC], vb[KC], vc[KC], vd[KC];
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+            va[k] = __ldg(reinterpret_cast<const float4*>(tbase + c00 + k * kstride));
+            vb[k] = __ldg(reinterpret_cast<const float4*>(tbase + c01 + k * kstride));
+            vc[k] = __ldg(reinterpret_cast<const float4*>(tbase + c10 + k * kstride));
+            vd[k] = __ldg(reinterpret_cast<const float4*>(tbase + c11 + k * kstride));
+        }
+#pragma unroll
+        for (int j = 0; j < NX; ++j) {
+#pragma unroll
+            for (int k = 0; k < KC; ++k) {
+                fma4(acc[j][k], va[k], cw[j][0]); fma4(acc[j][k], vb[k], cw[j][1]);
+                fma4(acc[j][k], vc[k], cw[j][2]); fma4(acc[j][k], vd[k], cw[j][3]);
+            }
+            cw[j][0] = cw[j][1] = cw[j][2] = cw[j][3] = 0.f;
+        }
+    };
+    for (int xb = x_lo; xb < x_hi; xb += 32) {
+        float mw00 = 0.f, mw01 = 0.f, mw10 = 0.f, mw11 = 0.f;
+        int mo00 = 0, mo01 = 0, mo10 = 0, mo11 = 0;
+        if (xb + lane < x_hi) {
+            // grid_sample(bilinear, zeros, align_corners=False), same arithmetic as raster_hpass_kernel's set-up
+            const int x = xb + lane;
+            const float gx = uvrow[(int64_t)x * p.uv_ld + 0], gy = uvrow[(int64_t)x * p.uv_ld + 1];
+            const float ix = ((gx + 1.f) * Wi - 1.f) / 2.f;
+            const float iy = ((gy + 1.f) * Hi - 1.f) / 2.f;
+            const float fx = floorf(ix), fy = floorf(iy);
+            const int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;
+            const float wnw = ((float)x1 - ix) * ((float)y1 - iy);
+            const float wne = (ix - (float)x0) * ((float)y1 - iy);
+            const float wsw = ((float)x1 - ix) * (iy - (float)y0);
+            const float wse = (ix - (float)x0) * (iy - (float)y0);
+            const bool vx0 = x0 >= 0 && x0 < Wi, vx1 = x1 >= 0 && x1 < Wi, vy0 = y0 >= 0 && y0 < Hi, vy1 = y1 >= 0 && y1 < Hi;
+            const int x0c = min(max(x0, 0), Wi - 1), x1c = min(max(x1, 0), Wi - 1);
+            const int y0c = min(max(y0, 0), Hi - 1), y1c = min(max(y1, 0), Hi - 1);
+            mw00 = (vy0 && vx0) ? wnw : 0.f; mw01 = (vy0 && vx1) ? wne : 0.f;
+            mw10 = (vy1 && vx0) ? wsw : 0.f; mw11 = (vy1 && vx1) ? wse : 0.f;
+            mo00 = (y0c * Wi + x0c) * p.C; mo01 = (y0c * Wi + x1c) * p.C;
+            mo10 = (y1c * Wi + x0c) * p.C; mo11 = (y1c * Wi + x1c) * p.C;
+        }
+        const int cnt = min(32, x_hi - xb);
+        for (int q = 0; q < cnt; ++q) {
+            const float w00 = __shfl_sync(0xffffffffu, mw00, q), w01 = __shfl_sync(0xffffffffu, mw01, q);
+            const float w10 = __shfl_sync(0xffffffffu, mw10, q), w11 = __shfl_sync(0xffffffffu, mw11, q);
+            const int o00 = __shfl_sync(0xffffffffu, mo00, q), o01 = __shfl_sync(0xffffffffu, mo01, q);
+            const int o10 = __shfl_sync(0xffffffffu, mo10, q), o11 = __shfl_sync(0xffffffffu, mo11, q);
+            if (o00 != c00 || o01 != c01 || o10 != c10 || o11 != c11) {
+                if (c00 >= 0) flush();
+                c00 = o00; c01 = o01; c10 = o10; c11 = o11;
+            }
+            const int x = xb + q;
+#pragma unroll
+            for (int j = 0; j < NX; ++j) {
+                const int tx = x - xs[j];
+                if (tx >= 0 && tx < xn[j]) {
+                    const float a = p.ux_w[(int64_t)(ox0 + j) * p.ux_max_taps + tx];
+                    cw[j][0] = fmaf(a, w00, cw[j][0]); cw[j][1] = fmaf(a, w01, cw[j][1]);
+                    cw[j][2] = fmaf(a, w10, cw[j][2]); cw[j][3] = fmaf(a, w11, cw[j][3]);
+                }
+            }
+        }
+    }
+    if (c00 >= 0) flush();
+#pragma unroll
+    for (int j = 0; j < NX; ++j) {
+        if (ox0 + j >= p.r) continue;
+        float* o = p.tmp + ((int64_t)(b * p.UH + y) * p.r + ox0 + j) * p.C + lane * 4;
+#pragma unroll
+        for (int k = 0; k < KC; ++k) *reinterpret_cast<float4*>(o + k * kstride) = acc[j][k];
+    }
+}
+
 __global__ void __launch_bounds__(256) raster_vpass_kernel(ia_raster_level_params p) {
     const int groups = p.C >> 2;
     const int64_t total = (int64_t)p.B * p.r * p.r * groups;
@@ -456,7 +570,10 @@ extern "C" int ia_raster_level(const ia_raster_level_params* p, void* stream) {
     static int coop_env = -1;      // IA_RASTER_COOP=0: every lane computes every sample's set-up (the round-1 kernel)
     if (coop_env < 0) { const char* e = getenv("IA_RASTER_COOP"); coop_env = e ? atoi(e) : 1; }
     const bool coop = coop_env != 0 && lpp == 32;
-#define IA_HPASS(K, N) do { if (coop) raster_hpass_kernel<K, N, true><<<grid1, 256, 0, as_stream(stream)>>>(*p, lpp); else raster_hpass_kernel<K, N, false><<<grid1, 256, 0, as_stream(stream)>>>(*p, lpp); } while (0)
+    // cell-merged gathers (IA_RASTER_MERGE=0: one gather set per sample, read per call so that tests can compare the two)
+    bool merge = coop;
+    { const char* e = getenv("IA_RASTER_MERGE"); if (e && atoi(e) == 0) merge = false; }
+#define IA_HPASS(K, N) do { if (merge) raster_hpass_merge_kernel<K, N><<<grid1, 256, 0, as_stream(stream)>>>(*p); else if (coop) raster_hpass_kernel<K, N, true><<<grid1, 256, 0, as_stream(stream)>>>(*p, lpp); else raster_hpass_kernel<K, N, false><<<grid1, 256, 0, as_stream(stream)>>>(*p, lpp); } while (0)
     if (kc == 4) { if (nx == 2) IA_HPASS(4, 2); else IA_HPASS(4, 1); }
     else if (kc == 2) { if (nx == 4) IA_HPASS(2, 4); else if (nx == 2) IA_HPASS(2, 2); else IA_HPASS(2, 1); }
     else { if (nx == 4) IA_HPASS(1, 4); else if (nx == 2) IA_HPASS(1, 2); else IA_HPASS(1, 1); }

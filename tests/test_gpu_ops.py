@@ -196,6 +196,32 @@ def test_raster_level_fused(Cc, tr, res):
     close(rt.from_nhwc(got), want, 5e-6 * max(1.0, float(want.abs().max())), f'raster_level C={Cc} r={res}')
 
 
+@pytest.mark.parametrize('Cc,tr,res', [(512, 32, 32), (512, 64, 64), (256, 128, 128), (128, 256, 256)])
+@pytest.mark.parametrize('uv_kind', ['smooth', 'random', 'outside'])
+def test_raster_level_cell_merged_vs_per_sample(monkeypatch, Cc, tr, res, uv_kind):
+    """The cell-merged horizontal pass (raster_hpass_merge_kernel: the four texels of a cell gathered once for the run of consecutive
+    samples that fall into it) against the per-sample kernel: the same sum in another order (fp32 reassociation only), on a smooth
+    UV map (long runs), a random one (no runs at all) and one that leaves the texture (zero-padding corners)."""
+    g = torch.Generator().manual_seed(Cc + res + len(uv_kind))
+    B = 2
+    tex = torch.randn(B, tr, tr, Cc, generator=g).to(DEV)
+    uv = synth_uv(B)
+    if uv_kind == 'random':
+        uv = torch.cat([torch.rand(B, 256, 256, 2, generator=g) * 2 - 1, uv[..., 2:]], dim=-1)
+    elif uv_kind == 'outside':
+        uv = torch.cat([uv[..., :2] * 1.3, uv[..., 2:]], dim=-1)
+    uv = uv.contiguous().to(DEV)
+    stat = torch.randn(B, tr, tr, Cc, generator=g).to(DEV)
+    sb = [round(i * tr / 256) for i in (57, 185, 64, 192)]
+    alpha = torch.rand(B, res, res, generator=g).to(DEV)
+    outs = {}
+    for mode in ('0', '1'):
+        monkeypatch.setenv('IA_RASTER_MERGE', mode)
+        outs[mode] = rt.raster_level(tex, uv, stat, (sb[0], sb[1], sb[2], sb[3]), alpha, res).clone()
+    scale = max(1.0, float(outs['0'].abs().max()))
+    assert float((outs['0'] - outs['1']).abs().max()) <= 2e-6 * scale
+
+
 def synth_uv(B):
     from invertavatar_b200 import synth
     return synth.uvcoords_image(B)
