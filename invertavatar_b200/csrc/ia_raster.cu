@@ -436,15 +436,20 @@ __global__ void __launch_bounds__(256) raster_hpass_merge_kernel(ia_raster_level
                 fma4(acc[j][k], va[k], cw[j][0]); fma4(acc[j][k], vb[k], cw[j][1]);
                 fma4(acc[j][k], vc[k], cw[j][2]); fma4(acc[j][k], vd[k], cw[j][3]);
             }
-            cw[j][0] = cw[j][1] = cw[j][2] = cw[j][3] = 0.f;
         }
     };
+    // 32 samples per round, ONE PER LANE: the lane computes its sample's bilinear set-up and the 4 x NX products
+    // a_j(x) * w_corner(x); runs of lanes with equal cells are found with one ballot and summed with a segmented warp scan
+    // (5 shuffle steps); only the per-run work -- 4 offsets + 4 x NX sums broadcast, gathers, FMAs -- is serial.
     for (int xb = x_lo; xb < x_hi; xb += 32) {
-        float mw00 = 0.f, mw01 = 0.f, mw10 = 0.f, mw11 = 0.f;
-        int mo00 = 0, mo01 = 0, mo10 = 0, mo11 = 0;
-        if (xb + lane < x_hi) {
+        const int cnt = min(32, x_hi - xb);
+        const int x = xb + lane;
+        int mo00 = -2 - lane, mo01 = 0, mo10 = 0, mo11 = 0;            // lanes past the end: cells of their own, never equal to a neighbour's
+        float pr[NX][4];
+#pragma unroll
+        for (int j = 0; j < NX; ++j) pr[j][0] = pr[j][1] = pr[j][2] = pr[j][3] = 0.f;
+        if (lane < cnt) {
             // grid_sample(bilinear, zeros, align_corners=False), same arithmetic as raster_hpass_kernel's set-up
-            const int x = xb + lane;
             const float gx = uvrow[(int64_t)x * p.uv_ld + 0], gy = uvrow[(int64_t)x * p.uv_ld + 1];
             const float ix = ((gx + 1.f) * Wi - 1.f) / 2.f;
             const float iy = ((gy + 1.f) * Hi - 1.f) / 2.f;
@@ -457,31 +462,54 @@ __global__ void __launch_bounds__(256) raster_hpass_merge_kernel(ia_raster_level
             const bool vx0 = x0 >= 0 && x0 < Wi, vx1 = x1 >= 0 && x1 < Wi, vy0 = y0 >= 0 && y0 < Hi, vy1 = y1 >= 0 && y1 < Hi;
             const int x0c = min(max(x0, 0), Wi - 1), x1c = min(max(x1, 0), Wi - 1);
             const int y0c = min(max(y0, 0), Hi - 1), y1c = min(max(y1, 0), Hi - 1);
-            mw00 = (vy0 && vx0) ? wnw : 0.f; mw01 = (vy0 && vx1) ? wne : 0.f;
-            mw10 = (vy1 && vx0) ? wsw : 0.f; mw11 = (vy1 && vx1) ? wse : 0.f;
+            const float mw00 = (vy0 && vx0) ? wnw : 0.f, mw01 = (vy0 && vx1) ? wne : 0.f;
+            const float mw10 = (vy1 && vx0) ? wsw : 0.f, mw11 = (vy1 && vx1) ? wse : 0.f;
             mo00 = (y0c * Wi + x0c) * p.C; mo01 = (y0c * Wi + x1c) * p.C;
             mo10 = (y1c * Wi + x0c) * p.C; mo11 = (y1c * Wi + x1c) * p.C;
-        }
-        const int cnt = min(32, x_hi - xb);
-        for (int q = 0; q < cnt; ++q) {
-            const float w00 = __shfl_sync(0xffffffffu, mw00, q), w01 = __shfl_sync(0xffffffffu, mw01, q);
-            const float w10 = __shfl_sync(0xffffffffu, mw10, q), w11 = __shfl_sync(0xffffffffu, mw11, q);
-            const int o00 = __shfl_sync(0xffffffffu, mo00, q), o01 = __shfl_sync(0xffffffffu, mo01, q);
-            const int o10 = __shfl_sync(0xffffffffu, mo10, q), o11 = __shfl_sync(0xffffffffu, mo11, q);
-            if (o00 != c00 || o01 != c01 || o10 != c10 || o11 != c11) {
-                if (c00 >= 0) flush();
-                c00 = o00; c01 = o01; c10 = o10; c11 = o11;
-            }
-            const int x = xb + q;
 #pragma unroll
             for (int j = 0; j < NX; ++j) {
                 const int tx = x - xs[j];
                 if (tx >= 0 && tx < xn[j]) {
-                    const float a = p.ux_w[(int64_t)(ox0 + j) * p.ux_max_taps + tx];
-                    cw[j][0] = fmaf(a, w00, cw[j][0]); cw[j][1] = fmaf(a, w01, cw[j][1]);
-                    cw[j][2] = fmaf(a, w10, cw[j][2]); cw[j][3] = fmaf(a, w11, cw[j][3]);
+                    const float a = p.ux_w[(ox0 + j) * p.ux_max_taps + tx];
+                    pr[j][0] = a * mw00; pr[j][1] = a * mw01; pr[j][2] = a * mw10; pr[j][3] = a * mw11;
                 }
             }
+        }
+        // run heads: lane 0, and every lane whose cell differs from its left neighbour's
+        const int l00 = __shfl_up_sync(0xffffffffu, mo00, 1), l01 = __shfl_up_sync(0xffffffffu, mo01, 1);
+        const int l10 = __shfl_up_sync(0xffffffffu, mo10, 1), l11 = __shfl_up_sync(0xffffffffu, mo11, 1);
+        const bool head = lane == 0 || l00 != mo00 || l01 != mo01 || l10 != mo10 || l11 != mo11;
+        const unsigned heads = __ballot_sync(0xffffffffu, head);
+        const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));      // first lane of this lane's run
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const bool take = lane - d >= start;
+#pragma unroll
+            for (int j = 0; j < NX; ++j)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float up = __shfl_up_sync(0xffffffffu, pr[j][c], d);
+                    if (take) pr[j][c] += up;
+                }
+        }
+        // the runs of this round, left to right (warp-uniform loop); a run that continues the open cell adds to its sums
+        unsigned m = heads & (cnt == 32 ? 0xffffffffu : ((1u << cnt) - 1u));
+        while (m) {
+            const int h = __ffs(m) - 1;
+            m &= m - 1;
+            const int tail = (m ? __ffs(m) - 1 : cnt) - 1;
+            const int o00 = __shfl_sync(0xffffffffu, mo00, h), o01 = __shfl_sync(0xffffffffu, mo01, h);
+            const int o10 = __shfl_sync(0xffffffffu, mo10, h), o11 = __shfl_sync(0xffffffffu, mo11, h);
+            const bool same = o00 == c00 && o01 == c01 && o10 == c10 && o11 == c11;
+            if (!same && c00 >= 0) flush();
+#pragma unroll
+            for (int j = 0; j < NX; ++j)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float sum = __shfl_sync(0xffffffffu, pr[j][c], tail);
+                    cw[j][c] = same ? cw[j][c] + sum : sum;
+                }
+            c00 = o00; c01 = o01; c10 = o10; c11 = o11;
         }
     }
     if (c00 >= 0) flush();
@@ -571,7 +599,9 @@ extern "C" int ia_raster_level(const ia_raster_level_params* p, void* stream) {
     if (coop_env < 0) { const char* e = getenv("IA_RASTER_COOP"); coop_env = e ? atoi(e) : 1; }
     const bool coop = coop_env != 0 && lpp == 32;
     // cell-merged gathers (IA_RASTER_MERGE=0: one gather set per sample, read per call so that tests can compare the two)
-    bool merge = coop;
+    int merge_min_scale = 2;                      // merge when the level shrinks the samples by at least this factor (IA_RASTER_MERGE_SCALE)
+    { const char* e = getenv("IA_RASTER_MERGE_SCALE"); if (e && atoi(e) > 0) merge_min_scale = atoi(e); }
+    bool merge = coop && p->UW >= merge_min_scale * p->r;
     { const char* e = getenv("IA_RASTER_MERGE"); if (e && atoi(e) == 0) merge = false; }
 #define IA_HPASS(K, N) do { if (merge) raster_hpass_merge_kernel<K, N><<<grid1, 256, 0, as_stream(stream)>>>(*p); else if (coop) raster_hpass_kernel<K, N, true><<<grid1, 256, 0, as_stream(stream)>>>(*p, lpp); else raster_hpass_kernel<K, N, false><<<grid1, 256, 0, as_stream(stream)>>>(*p, lpp); } while (0)
     if (kc == 4) { if (nx == 2) IA_HPASS(4, 2); else IA_HPASS(4, 1); }
