@@ -573,6 +573,181 @@ __global__ void __launch_bounds__(256) raster_vpass_kernel(ia_raster_level_param
     else { o[0] = res.x; o[1] = res.y; o[2] = res.z; o[3] = res.w; }
 }
 
+// One launch per level: the 2-D form of the cell merge.  The antialias filter is separable, so an output pixel is
+//     out(y', x') = sum_{y, x} ay(y', y) * ax(x', x) * bilinear(tex, uv[y][x])
+// over its (2 * scale)^2 window of 256^2 samples -- 256 samples for a 32^2 level, 64 for 64^2, 16 for 128^2 -- which on a smooth UV
+// map touch only a handful of texel cells.  One warp per output pixel: the LANES take the samples of the window (set-up, weight
+// product ay * ax * w_corner), runs of equal cells are summed with a segmented warp scan as in raster_hpass_merge_kernel, and the
+// run sums are collected in a table of up to 32 cells held one per lane (key = the cell's four clamped texel offsets; look-up =
+// one ballot).  When the window is done the lanes switch to channels: each table entry's four texels are gathered ONCE and applied
+// with its four summed weights.  (A table keyed per TEXEL gathers fewer texels -- a 3 x 3 block of cells shares 16 -- but needs four
+// look-ups per run: measured slower, 123 / 225 us against 91 / 198 us for the 32^2 / 64^2 levels; the serial per-run work bounds this kernel.)  Then the vertical-pass tail (static-crop resize, alpha blend) runs in the same thread.  Neither
+// the [B][256][r][C] intermediate nor the second launch exists; texel gathers drop from 4 per sample and output column to 4 per
+// touched cell and output pixel.  Deterministic (fixed sample, run and table order); against the two-pass kernels the sums are
+// reassociated (~1e-6 relative), IA_RASTER_FUSED=0 selects them.
+__device__ __forceinline__ void prefetch_l1(const void* q) { asm volatile("prefetch.global.L1 [%0];" ::"l"(q)); }
+
+template <int KC>
+__global__ void __launch_bounds__(256) raster_fused_kernel(ia_raster_level_params p) {
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= (int64_t)p.B * p.r * p.r) return;
+    const int ox = (int)(warp % p.r);
+    const int64_t tq = warp / p.r;
+    const int oy = (int)(tq % p.r), b = (int)(tq / p.r);
+    const int ys = p.uy_start[oy], yn = p.uy_count[oy], xs = p.ux_start[ox], xn = p.ux_count[ox];
+    const int n = yn * xn;
+    const float* wyp = p.uy_w + (int64_t)oy * p.uy_max_taps;
+    const float* wxp = p.ux_w + (int64_t)ox * p.ux_max_taps;
+    const float* uvb = p.uv + (int64_t)b * p.UH * p.UW * p.uv_ld;
+    const float* tbase = p.tex + (int64_t)b * p.Ht * p.Wt * p.C + lane * 4;
+    const int Wi = p.Wt, Hi = p.Ht;
+    constexpr int kstride = 32 * 4;
+    const unsigned full = 0xffffffffu;
+    // the static-crop taps the tail of this thread reads are known now: pull their lines towards L1 while the window is processed
+    {
+        const int sys_ = p.sy_start[oy], syn_ = p.sy_count[oy], sxs_ = p.sx_start[ox], sxn_ = p.sx_count[ox];
+        for (int ty = 0; ty < syn_; ++ty)
+            for (int tx = 0; tx < sxn_; ++tx) {
+                const float* q = p.stat + (((int64_t)b * p.SH + p.sy0 + sys_ + ty) * p.SW + p.sx0 + sxs_ + tx) * p.stat_ld + lane * 4;
+#pragma unroll
+                for (int k = 0; k < KC; ++k) prefetch_l1(q + k * kstride);
+            }
+    }
+    float4 acc[KC];
+#pragma unroll
+    for (int k = 0; k < KC; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int k00 = -1, k01 = -1, k10 = -1, k11 = -1;          // this lane's table entry: cell key ...
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;        // ... and its four summed corner weights
+    int nent = 0;                                        // entries in use (warp-uniform)
+    auto flush_all = [&]() {
+        for (int e = 0; e < nent; ++e) {
+            const int o00 = __shfl_sync(full, k00, e), o01 = __shfl_sync(full, k01, e);
+            const int o10 = __shfl_sync(full, k10, e), o11 = __shfl_sync(full, k11, e);
+            const float w0 = __shfl_sync(full, t0, e), w1 = __shfl_sync(full, t1, e);
+            const float w2 = __shfl_sync(full, t2, e), w3 = __shfl_sync(full, t3, e);
+            float4 va[KC], vb[KC], vc[KC], vd[KC];
+#pragma unroll
+            for (int k = 0; k < KC; ++k) {
+                va[k] = __ldg(reinterpret_cast<const float4*>(tbase + o00 + k * kstride));
+                vb[k] = __ldg(reinterpret_cast<const float4*>(tbase + o01 + k * kstride));
+                vc[k] = __ldg(reinterpret_cast<const float4*>(tbase + o10 + k * kstride));
+                vd[k] = __ldg(reinterpret_cast<const float4*>(tbase + o11 + k * kstride));
+            }
+#pragma unroll
+            for (int k = 0; k < KC; ++k) { fma4(acc[k], va[k], w0); fma4(acc[k], vb[k], w1); fma4(acc[k], vc[k], w2); fma4(acc[k], vd[k], w3); }
+        }
+        nent = 0;
+    };
+    for (int base = 0; base < n; base += 32) {
+        const int cnt = min(32, n - base);
+        const int idx = base + lane;
+        int mo00 = -2 - lane, mo01 = 0, mo10 = 0, mo11 = 0;            // lanes past the end: cells of their own
+        float pr0 = 0.f, pr1 = 0.f, pr2 = 0.f, pr3 = 0.f;
+        if (lane < cnt) {
+            const int sy = idx / xn, sx = idx - sy * xn;
+            const float a = wyp[sy] * wxp[sx];
+            const float* uvp = uvb + ((int64_t)(ys + sy) * p.UW + xs + sx) * p.uv_ld;
+            // grid_sample(bilinear, zeros, align_corners=False), same arithmetic as raster_hpass_kernel's set-up
+            const float gx = uvp[0], gy = uvp[1];
+            const float ix = ((gx + 1.f) * Wi - 1.f) / 2.f;
+            const float iy = ((gy + 1.f) * Hi - 1.f) / 2.f;
+            const float fx = floorf(ix), fy = floorf(iy);
+            const int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;
+            const float wnw = ((float)x1 - ix) * ((float)y1 - iy);
+            const float wne = (ix - (float)x0) * ((float)y1 - iy);
+            const float wsw = ((float)x1 - ix) * (iy - (float)y0);
+            const float wse = (ix - (float)x0) * (iy - (float)y0);
+            const bool vx0 = x0 >= 0 && x0 < Wi, vx1 = x1 >= 0 && x1 < Wi, vy0 = y0 >= 0 && y0 < Hi, vy1 = y1 >= 0 && y1 < Hi;
+            const int x0c = min(max(x0, 0), Wi - 1), x1c = min(max(x1, 0), Wi - 1);
+            const int y0c = min(max(y0, 0), Hi - 1), y1c = min(max(y1, 0), Hi - 1);
+            pr0 = (vy0 && vx0) ? a * wnw : 0.f; pr1 = (vy0 && vx1) ? a * wne : 0.f;
+            pr2 = (vy1 && vx0) ? a * wsw : 0.f; pr3 = (vy1 && vx1) ? a * wse : 0.f;
+            mo00 = (y0c * Wi + x0c) * p.C; mo01 = (y0c * Wi + x1c) * p.C;
+            mo10 = (y1c * Wi + x0c) * p.C; mo11 = (y1c * Wi + x1c) * p.C;
+        }
+        const int l00 = __shfl_up_sync(full, mo00, 1), l01 = __shfl_up_sync(full, mo01, 1);
+        const int l10 = __shfl_up_sync(full, mo10, 1), l11 = __shfl_up_sync(full, mo11, 1);
+        const bool head = lane == 0 || l00 != mo00 || l01 != mo01 || l10 != mo10 || l11 != mo11;
+        const unsigned heads = __ballot_sync(full, head);
+        const int start = 31 - __clz(heads & (full >> (31 - lane)));      // first lane of this lane's run
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const bool take = lane - d >= start;
+            const float u0 = __shfl_up_sync(full, pr0, d), u1 = __shfl_up_sync(full, pr1, d);
+            const float u2 = __shfl_up_sync(full, pr2, d), u3 = __shfl_up_sync(full, pr3, d);
+            if (take) { pr0 += u0; pr1 += u1; pr2 += u2; pr3 += u3; }
+        }
+        unsigned m = heads & (cnt == 32 ? full : ((1u << cnt) - 1u));
+        while (m) {
+            const int h = __ffs(m) - 1;
+            m &= m - 1;
+            const int tail = (m ? __ffs(m) - 1 : cnt) - 1;
+            const int o00 = __shfl_sync(full, mo00, h), o01 = __shfl_sync(full, mo01, h);
+            const int o10 = __shfl_sync(full, mo10, h), o11 = __shfl_sync(full, mo11, h);
+            const float r0 = __shfl_sync(full, pr0, tail), r1 = __shfl_sync(full, pr1, tail);
+            const float r2 = __shfl_sync(full, pr2, tail), r3 = __shfl_sync(full, pr3, tail);
+            const unsigned hit = __ballot_sync(full, lane < nent && k00 == o00 && k01 == o01 && k10 == o10 && k11 == o11);
+            if (hit) {
+                if (lane == __ffs(hit) - 1) { t0 += r0; t1 += r1; t2 += r2; t3 += r3; }
+            } else {
+                if (nent == 32) flush_all();
+                if (lane == nent) { k00 = o00; k01 = o01; k10 = o10; k11 = o11; t0 = r0; t1 = r1; t2 = r2; t3 = r3; }
+                ++nent;
+                // a new cell: start fetching this lane's share of its four texels (the gathers of flush_all then hit L1)
+#pragma unroll
+                for (int k = 0; k < KC; ++k) {
+                    prefetch_l1(tbase + o00 + k * kstride); prefetch_l1(tbase + o01 + k * kstride);
+                    prefetch_l1(tbase + o10 + k * kstride); prefetch_l1(tbase + o11 + k * kstride);
+                }
+            }
+        }
+    }
+    flush_all();
+    // tail of the two-pass path's second kernel: static crop resized to r x r (rows of horizontal taps, then the vertical weight:
+    // ATen's pass order), alpha blend, store -- this lane's channel groups lane*4 + 128*k
+    const int sys = p.sy_start[oy], syn = p.sy_count[oy], sxs = p.sx_start[ox], sxn = p.sx_count[ox];
+    const float* swy = p.sy_w + (int64_t)oy * p.sy_max_taps;
+    const float* swx = p.sx_w + (int64_t)ox * p.sx_max_taps;
+    const bool vec = (p.stat_ld & 3) == 0;
+    const float al = p.alpha[((int64_t)b * p.r + oy) * p.r + ox];
+    const float bl = 1.f - al;
+    // (taps outside, channel groups inside: the KC loads of a tap are independent and go out back to back; per channel the
+    // sums and their order are raster_vpass_kernel's)
+    float4 sacc[KC];
+#pragma unroll
+    for (int k = 0; k < KC; ++k) sacc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int ty = 0; ty < syn; ++ty) {
+        const float* row = p.stat + (((int64_t)b * p.SH + p.sy0 + sys + ty) * p.SW + p.sx0 + sxs) * p.stat_ld + lane * 4;
+        float4 rr[KC];
+#pragma unroll
+        for (int k = 0; k < KC; ++k) rr[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int tx = 0; tx < sxn; ++tx) {
+            float4 v[KC];
+#pragma unroll
+            for (int k = 0; k < KC; ++k) {
+                const float* q = row + (int64_t)tx * p.stat_ld + k * kstride;
+                if (vec) v[k] = __ldg(reinterpret_cast<const float4*>(q));
+                else v[k] = make_float4(q[0], q[1], q[2], q[3]);
+            }
+            const float w = swx[tx];
+#pragma unroll
+            for (int k = 0; k < KC; ++k) { rr[k].x += v[k].x * w; rr[k].y += v[k].y * w; rr[k].z += v[k].z * w; rr[k].w += v[k].w * w; }
+        }
+        const float w = swy[ty];
+#pragma unroll
+        for (int k = 0; k < KC; ++k) { sacc[k].x += rr[k].x * w; sacc[k].y += rr[k].y * w; sacc[k].z += rr[k].z * w; sacc[k].w += rr[k].w * w; }
+    }
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+        const float4 f = acc[k];
+        float* o = p.out + (((int64_t)b * p.r + oy) * p.r + ox) * p.out_ld + lane * 4 + k * kstride;
+        const float4 res = make_float4(f.x * al + sacc[k].x * bl, f.y * al + sacc[k].y * bl, f.z * al + sacc[k].z * bl, f.w * al + sacc[k].w * bl);
+        if ((p.out_ld & 3) == 0) *reinterpret_cast<float4*>(o) = res;
+        else { o[0] = res.x; o[1] = res.y; o[2] = res.z; o[3] = res.w; }
+    }
+}
+
 }  // namespace
 
 extern "C" int ia_raster_level(const ia_raster_level_params* p, void* stream) {
@@ -592,6 +767,26 @@ extern "C" int ia_raster_level(const ia_raster_level_params* p, void* stream) {
     int nx = p->UW >= 4 * p->r ? 4 : (p->UW >= 2 * p->r ? 2 : 1);
     { const char* e = getenv("IA_RASTER_NX"); if (e) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) nx = v; } }
     if (kc == 4 && nx == 4) nx = 2;      // 4 x 4 float4 accumulators + the sample would not fit the register budget
+    // one-launch 2-D cell merge when a warp's lanes cover the channels (C = 128 * kc) and the level shrinks the samples
+    {
+        // (scale 2 -- 16 samples and ~4 cells per output pixel -- leaves a warp too little to merge: the two-pass kernels win there)
+        int fused_min_scale = 4;
+        { const char* e = getenv("IA_RASTER_FUSED_SCALE"); if (e && atoi(e) > 0) fused_min_scale = atoi(e); }
+        bool fused = lpp == 32 && groups == 32 * kc && p->UW >= fused_min_scale * p->r && p->UH >= fused_min_scale * p->r &&
+                     (reinterpret_cast<uintptr_t>(p->tex) & 15) == 0;
+        { const char* e = getenv("IA_RASTER_FUSED"); if (e && atoi(e) == 0) fused = false; }
+        { const char* e = getenv("IA_RASTER_MERGE"); if (e && atoi(e) == 0) fused = false; }
+        if (fused) {
+            const int64_t warps = (int64_t)p->B * p->r * p->r;
+            const unsigned gridf = (unsigned)cdiv(warps * 32, 256);
+            ia::prof_begin("ia_raster_level(fused)", as_stream(stream));
+            if (kc == 4) raster_fused_kernel<4><<<gridf, 256, 0, as_stream(stream)>>>(*p);
+            else if (kc == 2) raster_fused_kernel<2><<<gridf, 256, 0, as_stream(stream)>>>(*p);
+            else raster_fused_kernel<1><<<gridf, 256, 0, as_stream(stream)>>>(*p);
+            IA_LAUNCH_CHECK("ia_raster_level(fused)");
+            return 0;
+        }
+    }
     const int64_t total1 = (int64_t)p->B * p->UH * cdiv(p->r, nx) * lpp;
     const unsigned grid1 = (unsigned)cdiv(total1, 256);
     ia::prof_begin("ia_raster_level(hpass)", as_stream(stream));

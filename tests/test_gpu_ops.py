@@ -199,8 +199,8 @@ def test_raster_level_fused(Cc, tr, res):
 @pytest.mark.parametrize('Cc,tr,res', [(512, 32, 32), (512, 64, 64), (256, 128, 128), (128, 256, 256)])
 @pytest.mark.parametrize('uv_kind', ['smooth', 'random', 'outside'])
 def test_raster_level_cell_merged_vs_per_sample(monkeypatch, Cc, tr, res, uv_kind):
-    """The cell-merged horizontal pass (raster_hpass_merge_kernel: the four texels of a cell gathered once for the run of consecutive
-    samples that fall into it) against the per-sample kernel: the same sum in another order (fp32 reassociation only), on a smooth
+    """The cell-merged kernels (raster_hpass_merge_kernel: the four texels of a cell gathered once for the run of consecutive samples of
+    a row that fall into it; raster_fused_kernel: the same over an output pixel's whole 2-D window, one launch) against the per-sample kernel: the same sum in another order (fp32 reassociation only), on a smooth
     UV map (long runs), a random one (no runs at all) and one that leaves the texture (zero-padding corners)."""
     g = torch.Generator().manual_seed(Cc + res + len(uv_kind))
     B = 2
@@ -215,11 +215,17 @@ def test_raster_level_cell_merged_vs_per_sample(monkeypatch, Cc, tr, res, uv_kin
     sb = [round(i * tr / 256) for i in (57, 185, 64, 192)]
     alpha = torch.rand(B, res, res, generator=g).to(DEV)
     outs = {}
-    for mode in ('0', '1'):
-        monkeypatch.setenv('IA_RASTER_MERGE', mode)
-        outs[mode] = rt.raster_level(tex, uv, stat, (sb[0], sb[1], sb[2], sb[3]), alpha, res).clone()
-    scale = max(1.0, float(outs['0'].abs().max()))
-    assert float((outs['0'] - outs['1']).abs().max()) <= 2e-6 * scale
+    for name, merge, fused in (('per_sample', '0', '0'), ('row_merge', '1', '0'), ('fused', '1', '1')):
+        monkeypatch.setenv('IA_RASTER_MERGE', merge)
+        monkeypatch.setenv('IA_RASTER_FUSED', fused)
+        monkeypatch.setenv('IA_RASTER_FUSED_SCALE', '2')        # exercise the one-launch kernel at scale 2 as well (default: scale >= 4)
+        outs[name] = rt.raster_level(tex, uv, stat, (sb[0], sb[1], sb[2], sb[3]), alpha, res).clone()
+    scale = max(1.0, float(outs['per_sample'].abs().max()))
+    assert float((outs['per_sample'] - outs['row_merge']).abs().max()) <= 2e-6 * scale
+    # the one-launch kernel (raster_fused_kernel: a warp per output pixel, 2-D window, table of cells) sums up to 256 samples per pixel
+    assert float((outs['per_sample'] - outs['fused']).abs().max()) <= 3e-6 * scale
+    again = rt.raster_level(tex, uv, stat, (sb[0], sb[1], sb[2], sb[3]), alpha, res)
+    assert torch.equal(again, outs['fused'])                 # deterministic: fixed sample, run and table order
 
 
 def synth_uv(B):
