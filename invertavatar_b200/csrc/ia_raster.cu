@@ -584,11 +584,13 @@ __global__ void __launch_bounds__(256) raster_vpass_kernel(ia_raster_level_param
 // look-ups per run: measured slower, 123 / 225 us against 91 / 198 us for the 32^2 / 64^2 levels; the serial per-run work bounds this kernel.)  Then the vertical-pass tail (static-crop resize, alpha blend) runs in the same thread.  Neither
 // the [B][256][r][C] intermediate nor the second launch exists; texel gathers drop from 4 per sample and output column to 4 per
 // touched cell and output pixel.  Deterministic (fixed sample, run and table order); against the two-pass kernels the sums are
-// reassociated (~1e-6 relative), IA_RASTER_FUSED=0 selects them.
+// reassociated (~1e-6 relative), IA_RASTER_FUSED=0 selects them.  Three CTAs per SM (80 registers: the gathers of a cell go out KB
+// channel groups at a time) measured faster than two with all gathers of a cell in flight (91 -> 84 us, 199 -> 178 us, 421 -> 336 us per
+// level) and than four (64 registers, spills: 143 / 285 / 324 us).
 __device__ __forceinline__ void prefetch_l1(const void* q) { asm volatile("prefetch.global.L1 [%0];" ::"l"(q)); }
 
 template <int KC>
-__global__ void __launch_bounds__(256) raster_fused_kernel(ia_raster_level_params p) {
+__global__ void __launch_bounds__(256, 3) raster_fused_kernel(ia_raster_level_params p) {
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= (int64_t)p.B * p.r * p.r) return;
@@ -603,6 +605,7 @@ __global__ void __launch_bounds__(256) raster_fused_kernel(ia_raster_level_param
     const float* tbase = p.tex + (int64_t)b * p.Ht * p.Wt * p.C + lane * 4;
     const int Wi = p.Wt, Hi = p.Ht;
     constexpr int kstride = 32 * 4;
+    constexpr int KB = KC == 4 ? 2 : KC;                 // channel groups processed together (see flush_all)
     const unsigned full = 0xffffffffu;
     // the static-crop taps the tail of this thread reads are known now: pull their lines towards L1 while the window is processed
     {
@@ -626,16 +629,23 @@ __global__ void __launch_bounds__(256) raster_fused_kernel(ia_raster_level_param
             const int o10 = __shfl_sync(full, k10, e), o11 = __shfl_sync(full, k11, e);
             const float w0 = __shfl_sync(full, t0, e), w1 = __shfl_sync(full, t1, e);
             const float w2 = __shfl_sync(full, t2, e), w3 = __shfl_sync(full, t3, e);
-            float4 va[KC], vb[KC], vc[KC], vd[KC];
+            // (KB channel groups at a time: 4 x KB gathers in flight -- with all four groups of a 512-channel level the kernel needs
+            // 128 registers and two CTAs per SM; with two it fits three, and the occupancy is worth more than the deeper batch)
 #pragma unroll
-            for (int k = 0; k < KC; ++k) {
-                va[k] = __ldg(reinterpret_cast<const float4*>(tbase + o00 + k * kstride));
-                vb[k] = __ldg(reinterpret_cast<const float4*>(tbase + o01 + k * kstride));
-                vc[k] = __ldg(reinterpret_cast<const float4*>(tbase + o10 + k * kstride));
-                vd[k] = __ldg(reinterpret_cast<const float4*>(tbase + o11 + k * kstride));
+            for (int k0 = 0; k0 < KC; k0 += KB) {
+                float4 va[KB], vb[KB], vc[KB], vd[KB];
+#pragma unroll
+                for (int k = 0; k < KB; ++k) {
+                    va[k] = __ldg(reinterpret_cast<const float4*>(tbase + o00 + (k0 + k) * kstride));
+                    vb[k] = __ldg(reinterpret_cast<const float4*>(tbase + o01 + (k0 + k) * kstride));
+                    vc[k] = __ldg(reinterpret_cast<const float4*>(tbase + o10 + (k0 + k) * kstride));
+                    vd[k] = __ldg(reinterpret_cast<const float4*>(tbase + o11 + (k0 + k) * kstride));
+                }
+#pragma unroll
+                for (int k = 0; k < KB; ++k) {
+                    fma4(acc[k0 + k], va[k], w0); fma4(acc[k0 + k], vb[k], w1); fma4(acc[k0 + k], vc[k], w2); fma4(acc[k0 + k], vd[k], w3);
+                }
             }
-#pragma unroll
-            for (int k = 0; k < KC; ++k) { fma4(acc[k], va[k], w0); fma4(acc[k], vb[k], w1); fma4(acc[k], vc[k], w2); fma4(acc[k], vd[k], w3); }
         }
         nent = 0;
     };
@@ -714,37 +724,40 @@ __global__ void __launch_bounds__(256) raster_fused_kernel(ia_raster_level_param
     const float bl = 1.f - al;
     // (taps outside, channel groups inside: the KC loads of a tap are independent and go out back to back; per channel the
     // sums and their order are raster_vpass_kernel's)
-    float4 sacc[KC];
 #pragma unroll
-    for (int k = 0; k < KC; ++k) sacc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int ty = 0; ty < syn; ++ty) {
-        const float* row = p.stat + (((int64_t)b * p.SH + p.sy0 + sys + ty) * p.SW + p.sx0 + sxs) * p.stat_ld + lane * 4;
-        float4 rr[KC];
+    for (int k0 = 0; k0 < KC; k0 += KB) {
+        float4 sacc[KB];
 #pragma unroll
-        for (int k = 0; k < KC; ++k) rr[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int tx = 0; tx < sxn; ++tx) {
-            float4 v[KC];
+        for (int k = 0; k < KB; ++k) sacc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int ty = 0; ty < syn; ++ty) {
+            const float* row = p.stat + (((int64_t)b * p.SH + p.sy0 + sys + ty) * p.SW + p.sx0 + sxs) * p.stat_ld + lane * 4 + k0 * kstride;
+            float4 rr[KB];
 #pragma unroll
-            for (int k = 0; k < KC; ++k) {
-                const float* q = row + (int64_t)tx * p.stat_ld + k * kstride;
-                if (vec) v[k] = __ldg(reinterpret_cast<const float4*>(q));
-                else v[k] = make_float4(q[0], q[1], q[2], q[3]);
+            for (int k = 0; k < KB; ++k) rr[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int tx = 0; tx < sxn; ++tx) {
+                float4 v[KB];
+#pragma unroll
+                for (int k = 0; k < KB; ++k) {
+                    const float* q = row + (int64_t)tx * p.stat_ld + k * kstride;
+                    if (vec) v[k] = __ldg(reinterpret_cast<const float4*>(q));
+                    else v[k] = make_float4(q[0], q[1], q[2], q[3]);
+                }
+                const float w = swx[tx];
+#pragma unroll
+                for (int k = 0; k < KB; ++k) { rr[k].x += v[k].x * w; rr[k].y += v[k].y * w; rr[k].z += v[k].z * w; rr[k].w += v[k].w * w; }
             }
-            const float w = swx[tx];
+            const float w = swy[ty];
 #pragma unroll
-            for (int k = 0; k < KC; ++k) { rr[k].x += v[k].x * w; rr[k].y += v[k].y * w; rr[k].z += v[k].z * w; rr[k].w += v[k].w * w; }
+            for (int k = 0; k < KB; ++k) { sacc[k].x += rr[k].x * w; sacc[k].y += rr[k].y * w; sacc[k].z += rr[k].z * w; sacc[k].w += rr[k].w * w; }
         }
-        const float w = swy[ty];
 #pragma unroll
-        for (int k = 0; k < KC; ++k) { sacc[k].x += rr[k].x * w; sacc[k].y += rr[k].y * w; sacc[k].z += rr[k].z * w; sacc[k].w += rr[k].w * w; }
-    }
-#pragma unroll
-    for (int k = 0; k < KC; ++k) {
-        const float4 f = acc[k];
-        float* o = p.out + (((int64_t)b * p.r + oy) * p.r + ox) * p.out_ld + lane * 4 + k * kstride;
-        const float4 res = make_float4(f.x * al + sacc[k].x * bl, f.y * al + sacc[k].y * bl, f.z * al + sacc[k].z * bl, f.w * al + sacc[k].w * bl);
-        if ((p.out_ld & 3) == 0) *reinterpret_cast<float4*>(o) = res;
-        else { o[0] = res.x; o[1] = res.y; o[2] = res.z; o[3] = res.w; }
+        for (int k = 0; k < KB; ++k) {
+            const float4 f = acc[k0 + k];
+            float* o = p.out + (((int64_t)b * p.r + oy) * p.r + ox) * p.out_ld + lane * 4 + (k0 + k) * kstride;
+            const float4 res = make_float4(f.x * al + sacc[k].x * bl, f.y * al + sacc[k].y * bl, f.z * al + sacc[k].z * bl, f.w * al + sacc[k].w * bl);
+            if ((p.out_ld & 3) == 0) *reinterpret_cast<float4*>(o) = res;
+            else { o[0] = res.x; o[1] = res.y; o[2] = res.z; o[3] = res.w; }
+        }
     }
 }
 
@@ -769,8 +782,8 @@ extern "C" int ia_raster_level(const ia_raster_level_params* p, void* stream) {
     if (kc == 4 && nx == 4) nx = 2;      // 4 x 4 float4 accumulators + the sample would not fit the register budget
     // one-launch 2-D cell merge when a warp's lanes cover the channels (C = 128 * kc) and the level shrinks the samples
     {
-        // (scale 2 -- 16 samples and ~4 cells per output pixel -- leaves a warp too little to merge: the two-pass kernels win there)
-        int fused_min_scale = 4;
+        // (measured per level, tools/prof_raster.py: 135 -> 84 us @32^2, 292 -> 178 us @64^2, 411 -> 336 us @128^2 against the two-pass kernels)
+        int fused_min_scale = 2;
         { const char* e = getenv("IA_RASTER_FUSED_SCALE"); if (e && atoi(e) > 0) fused_min_scale = atoi(e); }
         bool fused = lpp == 32 && groups == 32 * kc && p->UW >= fused_min_scale * p->r && p->UH >= fused_min_scale * p->r &&
                      (reinterpret_cast<uintptr_t>(p->tex) & 15) == 0;
