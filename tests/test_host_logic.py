@@ -159,3 +159,50 @@ def test_capture_scope_keys_engine_state_per_graph():
     assert plan._key(8) == (8, 0)
     with rt.capture_scope() as s4:
         assert plan._key(8) == (8, s4)
+
+
+def test_cell_merged_rasterizer_algebra():
+    """The identity raster_hpass_merge_kernel / raster_fused_kernel rest on, restated with torch on the CPU: an output pixel of
+    aa_resize(grid_sample(tex, uv)) is linear in the texels, so summing the weight products ay*ax*w_corner of all samples that fall
+    into one texel cell and gathering the cell's four texels once gives the per-sample sum (triplane_v20.py:331-337) up to fp32
+    reassociation."""
+    import numpy as np
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(11)
+    Ht = Wt = 8
+    Cc, U, r = 6, 32, 8                                   # 32^2 samples -> 8^2 outputs (scale 4: 8 x 8 samples per output window)
+    tex = torch.randn(1, Cc, Ht, Wt, generator=g, dtype=torch.float64)
+    lin = (torch.arange(U, dtype=torch.float64) + 0.5) / U * 2 - 1
+    yy, xx = torch.meshgrid(lin, lin, indexing='ij')
+    uv = torch.stack([xx + 0.05 * torch.sin(3 * yy), yy * 1.1 + 0.05 * torch.cos(2 * xx)], dim=-1).unsqueeze(0)   # leaves the texture at the rim
+    want = F.interpolate(F.grid_sample(tex, uv, mode='bilinear', padding_mode='zeros', align_corners=False), size=(r, r), mode='bilinear',
+                         antialias=True)[0]
+    # separable antialias taps (SURVEY App. C): scale 4, support 4, triangle weights normalised per output
+    def taps(i):
+        scale = U / r
+        center = scale * (i + 0.5)
+        lo, hi = max(0, int(center - scale + 0.5)), min(U, int(center + scale + 0.5))
+        w = torch.tensor([max(0.0, 1 - abs((j - center + 0.5) / scale)) for j in range(lo, hi)], dtype=torch.float64)
+        return lo, w / w.sum()
+    got = torch.zeros(Cc, r, r, dtype=torch.float64)
+    for oy in range(r):
+        ys, wy = taps(oy)
+        for ox in range(r):
+            xs, wx = taps(ox)
+            cells = {}                                    # (y0, x0) -> four summed corner weights (zero-padding corners carry none)
+            for sy, ay in enumerate(wy):
+                for sx, ax in enumerate(wx):
+                    gx, gy = float(uv[0, ys + sy, xs + sx, 0]), float(uv[0, ys + sy, xs + sx, 1])
+                    ix, iy = ((gx + 1) * Wt - 1) / 2, ((gy + 1) * Ht - 1) / 2
+                    x0, y0 = int(np.floor(ix)), int(np.floor(iy))
+                    w4 = [(x0 + 1 - ix) * (y0 + 1 - iy), (ix - x0) * (y0 + 1 - iy), (x0 + 1 - ix) * (iy - y0), (ix - x0) * (iy - y0)]
+                    acc = cells.setdefault((y0, x0), [0.0, 0.0, 0.0, 0.0])
+                    for k in range(4):
+                        acc[k] += float(ay * ax) * w4[k]
+            assert len(cells) < len(wy) * len(wx) / 3     # the window really collapses onto a handful of cells
+            for (y0, x0), w4 in cells.items():
+                for k, (dy, dx) in enumerate(((0, 0), (0, 1), (1, 0), (1, 1))):
+                    yq, xq = y0 + dy, x0 + dx
+                    if 0 <= yq < Ht and 0 <= xq < Wt:
+                        got[:, oy, ox] += w4[k] * tex[0, :, yq, xq]
+    assert float((got - want).abs().max()) < 1e-12
