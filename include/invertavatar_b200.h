@@ -304,7 +304,10 @@ int ia_lerp_alpha(const ia_lerp_params* p, void* stream);
 
 /* One pyramid level of TriPlaneGenerator.rasterize (triplane_v20.py:328-338) without the [B][256][256][C] intermediate:
  *   out = aa_resize(grid_sample(tex, uv))*alpha + aa_resize(static[crop])*(1 - alpha)
- * as two passes: (1) grid_sample fused with the horizontal antialias taps -> tmp [B][UH][r][C]; (2) vertical taps + the
+ * Levels that shrink the samples (UW >= 2r) with C = 128, 256 or 512 run as ONE launch: a warp per output pixel sums the weights of
+ * the samples of its window per texel cell, gathers each cell's four texels once and applies the static-crop resize and the alpha
+ * blend (tmp is not touched; fp32 reassociation against the two-pass form, IA_RASTER_FUSED=0 / IA_RASTER_MERGE=0 select it).
+ * Otherwise two passes: (1) grid_sample fused with the horizontal antialias taps -> tmp [B][UH][r][C]; (2) vertical taps + the
  * (up-sampling) resize of the static crop + the alpha blend.  Tap tables as in ia_resize_aa: (ux_*) UW -> r, (uy_*) UH -> r,
  * (sx_*) sw -> r, (sy_*) sh -> r.  tex is contiguous NHWC; C must be a multiple of 4. */
 typedef struct {
